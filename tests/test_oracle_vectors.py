@@ -1,0 +1,177 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold for
+the liftover + stats path.  file:line cites are into the reference tree."""
+import hashlib
+import struct
+
+import numpy as np
+import pytest
+
+import orc
+
+F_PAF = "Q 10 2 10 + T 40 12 20 3 9 60 cg:Z:4M1I1=1D2="
+R_PAF = "Q 10 2 10 - T 40 12 20 3 9 60 cg:Z:4M1I1=1D2="
+# liftover.rs:253-300 (test_aln_pair_liftover): six regions, alternating +,- strand
+REGIONS = [(14, 15), (14, 18), (12, 20), (12, 30), (5, 20), (5, 30)]
+STS = [4, 7, 4, 4, 2, 2, 2, 2, 2, 2, 2, 2]
+ENS = [5, 8, 8, 8, 10, 10, 10, 10, 10, 10, 10, 10]
+
+
+@pytest.mark.parametrize("policy", [orc.RIGHTMOST, orc.EARLY_EXIT])
+def test_aln_pair_liftover(policy):
+    idx = 0
+    for st, en in REGIONS:
+        for line in (F_PAF, R_PAF):
+            out = orc.trim_line(line, "T", st, en, "", policy)
+            assert out is not None
+            f = out.split("\t")
+            assert int(f[2]) == STS[idx], (st, en, line, out)
+            assert int(f[3]) == ENS[idx], (st, en, line, out)
+            idx += 1
+
+
+def test_break_paf_on_indels_doctest():
+    # liftover.rs:169-181 — the doctest asserts on the LAST `rec` only (5=5I5= on '-')
+    for line in ["Q 15 0 15 - T 10 0 10 9 15 60 cg:Z:5=5I5="]:
+        parts = orc.break_paf(line, 0)
+        assert len(parts) == 2
+        for p in parts:
+            f = p.split("\t")
+            assert int(f[8]) - int(f[7]) == 5
+
+
+def test_make_fake_paf_rec_cigar():
+    # paf.rs:375-376 + 1096-1100: aligned_pairs leaves the cigar "4M1I1D3="
+    out = orc.aligned_pairs_line("Q 10 2 10 - T 20 12 20 3 9 60 cg:Z:4M1I1D3=")
+    assert out.split("\t")[-1] == "cg:Z:4M1I1D3="
+
+
+def test_cigar_parse_doctest():
+    # paf.rs:1007-1012: hand parser == htslib parser on these two strings
+    assert orc.parse_cigar("10M4D100I1102=") == [(10, "M"), (4, "D"), (100, "I"), (1102, "=")]
+    assert orc.parse_cigar("100000M20=5P10X4M") == [(100000, "M"), (20, "="), (5, "P"), (10, "X"), (4, "M")]
+
+
+@pytest.mark.parametrize("bad", ["", "M", "10", "5=3", "5Q", "=5", "4294967296M", "5=3H2=", "2S5=3S1="])
+def test_cigar_parse_errors(bad):
+    if bad == "":
+        assert orc.parse_cigar("") == []
+        return
+    with pytest.raises(orc.ReferencePanic):
+        orc.parse_cigar(bad)
+
+
+def test_cigar_parse_edges():
+    assert orc.parse_cigar("007M") == [(7, "M")]
+    assert orc.parse_cigar("4294967295=") == [(4294967295, "=")]
+    assert orc.parse_cigar("0M") == [(0, "M")]
+    assert orc.parse_cigar("3H2S5=1S4H") == [(3, "H"), (2, "S"), (5, "="), (1, "S"), (4, "H")]
+
+
+def test_add_cigar_stats():
+    # bamstats.rs:287-295: 10=10X -> id_by_all == 50.0
+    s = orc.cigar_stats("10=10X")
+    assert abs(50.0 - s["id_by_all"]) < 1e-10
+    assert s["equal"] == 10 and s["diff"] == 10
+
+
+def test_stats_m_counts_as_mismatch():
+    # bamstats.rs:121-124 (Q12)
+    s = orc.cigar_stats("10M5=2I3D1I")
+    assert (s["equal"], s["diff"], s["matches"], s["ins"], s["del"], s["ins_events"], s["del_events"]) == (5, 10, 10, 3, 3, 2, 1)
+
+
+def test_paf_from_file_doctest():
+    # paf.rs:53-61: 249 records, all pass check_integrity (run_stats parses + checks every line)
+    out = orc.run_stats(orc.golden_paf())
+    assert out.count(b"\n") == 250  # header + 249 rows
+
+
+def test_parse_bed_doctests():
+    # bed.rs:130-139 and 167-170
+    assert orc.parse_bed(b"chr1\t0\t1000\tid\n") == [("chr1", 0, 1000, "id")]
+    assert orc.parse_bed(b"chr1\t2\t2000\n") == [("chr1", 2, 2000, "chr1:3-2000")]
+    rows = orc.parse_bed(orc.golden_bed())
+    assert len(rows) == 10
+    assert rows[0] == ("chr20", 106240, 10850788, "A")
+
+
+def test_bundled_fixture_end_to_end_regression():
+    """No reference-owned expected output exists for config 1 ("parity unpinned"); these md5s
+    are the ones an independent per-base Python model produced at survey time."""
+    lifted = orc.run_liftover(orc.golden_paf(), orc.golden_bed(), threads=4)
+    assert lifted.count(b"\n") == 12 and len(lifted) == 508497
+    assert hashlib.md5(lifted).hexdigest() == "f009e11b3bc56a4967cf594f750123a9"
+    st = orc.run_stats(lifted)
+    assert hashlib.md5(st).hexdigest() == "3c05b90d6e2677dd3da73b86a453f7ac"
+    row = st.split(b"\n")[1].decode().split("\t")
+    assert row == "chr20 106240 10850788 66210247 + chr20 63840 10807816 64444167 99.89702 99.87144 99.14145 10692453 11023 1441 1300 41072 40500".split()
+
+
+def test_threads_do_not_change_output():
+    a = orc.run_liftover(orc.golden_paf(), orc.golden_bed(), threads=1)
+    b = orc.run_liftover(orc.golden_paf(), orc.golden_bed(), threads=8)
+    assert a == b
+
+
+def test_fmt_f32_known():
+    assert orc.fmt_f32(50.0) == "50"
+    assert orc.fmt_f32(100.0) == "100"
+    assert orc.fmt_f32(0.0) == "0"
+    assert orc.fmt_f32(float("nan")) == "NaN"
+    assert orc.fmt_f32(float("inf")) == "inf"
+    assert orc.fmt_f32(99.89702) == "99.89702"
+    assert orc.fmt_f32(0.1) == "0.1"
+    assert orc.fmt_f32(1e-5) == "0.00001"
+    assert orc.fmt_f32(16777216.0) == "16777216"
+
+
+def test_fmt_f32_roundtrips_and_is_shortest():
+    rng = np.random.default_rng(7)
+    eq = rng.integers(0, 2**31, 4000, dtype=np.uint64)
+    tot = eq + rng.integers(0, 2**20, 4000, dtype=np.uint64)
+    vals = (np.float32(100.0) * eq.astype(np.float32)) / np.maximum(tot, 1).astype(np.float32)
+    for v in vals.tolist() + [1.17549435e-38, 3.4028235e38, 33554432.0, 8388608.0]:
+        v32 = struct.unpack("f", struct.pack("f", v))[0]
+        s = orc.fmt_f32(v32)
+        assert "e" not in s
+        assert np.float32(s) == np.float32(v32), (v32, s)
+        # shortest: dropping the last significant digit (either rounding) no longer round-trips
+        digits = s.replace(".", "").lstrip("0")
+        if len(digits.rstrip("0")) > 1 and "." in s:
+            shorter_dn = s[:-1]
+            assert np.float32(shorter_dn) != np.float32(v32) or shorter_dn.endswith(".")
+
+
+def test_q3_early_return_keeps_record_id_and_uncollapsed_cigar():
+    # liftover.rs:19-25 / SURVEY Q3 + Q15
+    out = orc.trim_line("Q 20 0 13 + T 100 10 23 0 0 60 cg:Z:5=3=5=", "T", 5, 50, "W")
+    assert out.endswith("id:Z:\tcg:Z:5=3=5=")
+    out = orc.trim_line("Q 20 0 13 + T 100 10 23 0 0 60 cg:Z:5=3=5=", "T", 10, 50, "W")
+    assert out.endswith("id:Z:W\tcg:Z:13=")
+
+
+def test_q9_leading_insertion_strip_and_leading_deletion_panics():
+    out = orc.aligned_pairs_line("Q 20 0 12 + T 100 10 23 0 0 60 cg:Z:2I5=3D5=")
+    f = out.split("\t")
+    assert f[2] == "2" and f[12] == "id:Z:_TO.2I." and f[13] == "cg:Z:5=3D5="
+    out = orc.aligned_pairs_line("Q 20 0 12 - T 100 10 23 0 0 60 cg:Z:2I5=3D5=")
+    f = out.split("\t")
+    assert (f[2], f[3]) == ("0", "10")
+    out = orc.aligned_pairs_line("Q 20 0 12 + T 100 10 23 0 0 60 cg:Z:5=5=2I3D")
+    f = out.split("\t")
+    assert (f[3], f[8], f[12], f[13]) == ("10", "20", "id:Z:_TO..3D2I", "cg:Z:5=5=")
+    with pytest.raises(orc.ReferencePanic):
+        orc.aligned_pairs_line("Q 20 0 10 + T 100 10 23 0 0 60 cg:Z:3D5=5=")
+
+
+def test_q7_window_inside_deletion_is_dropped():
+    assert orc.trim_line("Q 20 0 10 + T 100 10 30 0 0 60 cg:Z:5=10D5=", "T", 16, 24, "W") is None
+
+
+def test_q2_policies_differ_only_after_insertions():
+    # base 14 (last '=' of the first run) is followed by an insertion
+    line = "Q 30 0 13 + T 100 10 20 0 0 60 cg:Z:5=3I5="
+    a = orc.trim_line(line, "T", 14, 18, "W", orc.RIGHTMOST)
+    assert a.split("\t")[7] == "15" and a.endswith("cg:Z:3=")
+    b = orc.trim_line(line, "T", 14, 18, "W", orc.EARLY_EXIT)
+    assert b.split("\t")[7] in ("14", "15")
