@@ -251,7 +251,9 @@ void PafRecord::remove_trailing_indels() {
 
     cigar.erase(cigar.begin(), cigar.begin() + (ptrdiff_t)remove_st_opts);
     if (cigar.size() >= remove_en_opts) cigar.resize(cigar.size() - remove_en_opts);
-    // else: usize wrap in a release build -> truncate(huge) is a no-op
+    else  // all-indel CIGAR: `self.cigar.len() - remove_en_opts` underflows usize (paf.rs:757) — a panic in
+          // debug builds; a release build would carry on with wrapped spans.  Modelled as the panic.
+        throw Abort("attempt to subtract with overflow (all-indel CIGAR, paf.rs:757)");
 
     t_st += remove_st_t;
     t_en -= remove_en_t;

@@ -1,0 +1,235 @@
+// lift_core.cuh — run-length ("closed form") statement of one (BED window, PAF record) liftover.
+//
+// Replaces, per pair, the reference's per-base machinery:
+//   liftover.rs:17-105   trim_paf_rec_to_rgn
+//   paf.rs:541-561       tpos_to_idx / tpos_to_idx_match   (binary search over 8 B/column + slide)
+//   paf.rs:593-620       subset_cigar / collapse_long_cigar
+//   paf.rs:825-857       check_integrity (recomputes nmatch / aln_len)
+//   bamstats.rs:107-142  add_stats_from_cigar on the trimmed CIGAR (fused: prefix-sum differences)
+// with two searches over the sampled target prefix sums (one 48-byte sample per 32 ops) plus a
+// <=32-op walk each.  Column indices of the reference's arrays are never built: column c of a
+// record == (op index, offset in op), and A (columns before an op) is one of the counters.
+//
+// __host__ __device__: the same code is fuzzed on the CPU against the literal per-base oracle
+// (tests/native/lift_core_check.cpp) and runs inside k_lift on the GPU.
+#pragma once
+#include "rb_common.cuh"
+
+namespace rb {
+
+struct OpsView {
+    const uint32_t* ops;
+    const Ctr* samples;
+};
+
+enum : int { POLICY_RIGHTMOST = 0, POLICY_EARLY_EXIT = 1 };
+enum : uint32_t { LIFT_OK = 0, LIFT_ERR_NOT_FOUND = 1 };  // NOT_FOUND == the reference's "Problem getting index in cigar" panic
+
+// Counters accumulated from the record's first op up to (excluding) op k.
+RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k) {
+    const uint64_t base = (k >> SAMPLE_LOG2) << SAMPLE_LOG2;
+    Ctr c;
+    uint64_t j;
+    if (base > r.op_first) { c = v.samples[k >> SAMPLE_LOG2]; j = base; }
+    else { c = ctr_zero(); j = r.op_first; }
+    for (; j < k; j++) ctr_add_op(c, v.ops[j]);
+    return c;
+}
+
+// The reference-consuming op i (len > 0) with T_i <= p < T_i + L_i ; o = p - T_i ; `before` = counters before op i.
+RB_HD bool find_op(const OpsView& v, const RecInfo& r, uint32_t p, uint64_t& i, uint32_t& o, Ctr& before) {
+    if (r.op_end <= r.op_first) return false;
+    uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
+    while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
+        const uint64_t mid = (lo + hi + 1) >> 1;
+        if (v.samples[mid].T <= p) lo = mid;
+        else hi = mid - 1;
+    }
+    uint64_t k = lo << SAMPLE_LOG2;
+    Ctr c;
+    if (k > r.op_first) c = v.samples[lo];
+    else { c = ctr_zero(); k = r.op_first; }
+    for (; k < r.op_end; k++) {
+        const uint32_t w = v.ops[k];
+        const uint32_t L = op_len(w);
+        if (is_ref(op_code(w)) && L > 0 && p - c.T < L) {
+            i = k; o = p - c.T; before = c;
+            return true;
+        }
+        ctr_add_op(c, w);
+    }
+    return false;
+}
+
+// core::slice::binary_search of Rust 1.52..=1.81 over a column array whose entries equal to the
+// target are exactly columns [ca, cb]: returns the first probe that compares Equal.
+RB_HD uint32_t early_exit_probe(uint32_t n, uint32_t ca, uint32_t cb) {
+    uint64_t size = n, left = 0, right = n;
+    while (left < right) {
+        const uint64_t mid = left + size / 2;
+        if (mid < ca) left = mid + 1;
+        else if (mid > cb) right = mid;
+        else return (uint32_t)mid;
+        size = right - left;
+    }
+    return ca;  // unreachable when ca <= cb < n
+}
+
+// Merge walk over the trimmed op range (collapse_long_cigar semantics, paf.rs:602-620): zero-length
+// ops vanish, adjacent same-class ops fuse.  `emit(len, code)` is called once per printed op.
+template <class Emit>
+RB_HD void merged_walk(const uint32_t* ops, uint64_t si, uint64_t ei, uint32_t s_len, uint32_t e_len, Emit&& emit) {
+    uint32_t prev = 0xFFFFFFFFu, run = 0;
+    for (uint64_t k = si; k <= ei; k++) {
+        const uint32_t w = ops[k];
+        const uint32_t code = op_code(w);
+        const uint32_t L = (k == si) ? s_len : (k == ei ? e_len : op_len(w));
+        if (L == 0) continue;
+        if (code == prev) run += L;
+        else {
+            if (prev != 0xFFFFFFFFu) emit(run, prev);
+            prev = code;
+            run = L;
+        }
+    }
+    if (prev != 0xFFFFFFFFu) emit(run, prev);
+}
+
+RB_HD void fill_stats(PairRes& out, const Ctr& d) {
+    out.equal = d.EQ; out.diff = d.X + d.M; out.matches = d.M;
+    out.ins = d.I; out.del = d.D; out.ins_ev = d.IEV; out.del_ev = d.DEV;
+}
+
+// One pair.  Returns LIFT_OK (out.kind says DROP / TRIM / EARLY) or LIFT_ERR_NOT_FOUND.
+RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, int policy, PairRes& out) {
+    out.pad = 0;
+    // liftover.rs:22-25 (Q3): record strictly inside the window -> the record itself, uncollapsed
+    if (r.t_st > w_st && r.t_en < w_en) {
+        out.kind = PK_EARLY;
+        out.t_st = r.t_st; out.t_en = r.t_en; out.q_st = r.q_st; out.q_en = r.q_en;
+        out.nmatch = (uint64_t)(uint32_t)(r.tot.EQ + r.tot.X + r.tot.M);
+        out.aln_len = r.tot.A;
+        out.si = r.eo0; out.ei = r.eo1 - 1;
+        out.s_len = 0; out.e_len = 0;
+        out.cg_bytes = r.tot.TXT;
+        fill_stats(out, r.tot);
+        return LIFT_OK;
+    }
+    out.kind = PK_DROP;
+    out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
+    out.s_len = out.e_len = out.cg_bytes = 0;
+    out.equal = out.diff = out.ins = out.del = out.ins_ev = out.del_ev = out.matches = 0;
+    if (r.t_en <= r.t_st) return LIFT_ERR_NOT_FOUND;
+
+    const uint32_t ps = (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st);       // liftover.rs:28
+    const uint32_t pe = (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st);   // liftover.rs:38-40
+
+    // ---- START: tpos_to_idx_match(t_st, search_right = true) ----
+    uint64_t i; uint32_t o; Ctr before;
+    if (!find_op(v, r, ps, i, o, before)) return LIFT_ERR_NOT_FOUND;
+    uint32_t w = v.ops[i];
+    uint32_t L = op_len(w), code = op_code(w);
+    bool slide = false;
+    if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
+        uint64_t k2 = i + 1;
+        while (k2 < r.eo1 && op_len(v.ops[k2]) == 0) k2++;
+        if (k2 < r.eo1 && !is_ref(op_code(v.ops[k2]))) slide = true;
+    }
+    if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
+        const uint32_t ca = before.A + o - r.a_lead;
+        uint32_t extra = 0;
+        for (uint64_t k = i + 1; k < r.eo1; k++) {
+            const uint32_t w2 = v.ops[k];
+            if (op_len(w2) == 0) continue;
+            if (is_ref(op_code(w2))) break;
+            extra += op_len(w2);
+        }
+        if (early_exit_probe(r.tot.A, ca, ca + extra) == ca) slide = false;
+    }
+    uint64_t si; uint32_t so; Ctr cs;
+    if (!slide && is_match(code)) {
+        si = i; so = o; cs = before;
+        ctr_add_bases(cs, code, o);
+    } else {
+        Ctr c = before;
+        ctr_add_op(c, w);
+        uint64_t k = i + 1;
+        bool found = false;
+        for (; k < r.eo1; k++) {
+            const uint32_t w2 = v.ops[k];
+            if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+            ctr_add_op(c, w2);
+        }
+        if (!found) return LIFT_OK;  // start index == number of columns > any end index (liftover.rs:52-54)
+        si = k; so = 0; cs = c;
+    }
+
+    // ---- END: tpos_to_idx_match(t_en - 1, search_right = false) ----
+    if (!find_op(v, r, pe, i, o, before)) return LIFT_ERR_NOT_FOUND;
+    w = v.ops[i];
+    L = op_len(w); code = op_code(w);
+    uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
+    if (is_match(code)) {
+        ei = i; eo = o; ce = before; txt_before_ei = before.TXT;
+        ctr_add_bases(ce, code, o + 1);
+    } else {
+        Ctr c = before;
+        uint64_t k = i;
+        bool found = false;
+        while (k > r.eo0) {
+            k--;
+            const uint32_t w2 = v.ops[k];
+            ctr_sub_op(c, w2);
+            if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+        }
+        if (!found) return LIFT_OK;  // slid to column 0 which is not a match column -> start > end
+        ei = k; eo = op_len(v.ops[k]) - 1; ce = c; txt_before_ei = c.TXT;
+        ctr_add_bases(ce, op_code(v.ops[k]), eo + 1);
+    }
+
+    if (cs.A >= ce.A) return LIFT_OK;  // start column > end column: window lies inside an indel (Q7)
+
+    out.kind = PK_TRIM;
+    out.t_st = r.t_st + cs.T;
+    out.t_en = r.t_st + ce.T;
+    if (r.flags & RF_MINUS) {  // Q8: columns walk the query downward from q_en
+        out.q_st = r.q_en0 - ce.Q;
+        out.q_en = r.q_en0 - cs.Q;
+    } else {
+        out.q_st = r.q_st0 + cs.Q;
+        out.q_en = r.q_st0 + ce.Q;
+    }
+    Ctr d = ce;
+    ctr_sub(d, cs);
+    out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
+    out.aln_len = d.A;
+    fill_stats(out, d);
+    out.si = si; out.ei = ei;
+    const uint32_t L_si = op_len(v.ops[si]);
+    if (si == ei) {
+        out.s_len = eo - so + 1; out.e_len = 0;
+        out.cg_bytes = ndigits32(out.s_len) + 1;
+    } else {
+        out.s_len = L_si - so; out.e_len = eo + 1;
+        out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
+    }
+    if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
+        uint32_t bytes = 0, iev = 0, dev = 0;
+        merged_walk(v.ops, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
+            bytes += ndigits32(len) + 1;
+            iev += (c2 == OP_I);
+            dev += (c2 == OP_D);
+        });
+        out.cg_bytes = bytes; out.ins_ev = iev; out.del_ev = dev;
+    }
+    return LIFT_OK;
+}
+
+// Bytes of the printed PAF line (paf.rs:923-943), '\n' included.
+RB_HD uint32_t line_bytes(const RecInfo& r, const PairRes& p, uint32_t q_name_len, uint32_t t_name_len, uint32_t id_len) {
+    return q_name_len + t_name_len + id_len + ndigits64(r.q_len) + ndigits64(p.q_st) + ndigits64(p.q_en) + 1 /*strand*/ +
+           ndigits64(r.t_len) + ndigits64(p.t_st) + ndigits64(p.t_en) + ndigits64(p.nmatch) + ndigits64(p.aln_len) +
+           ndigits64(r.mapq) + 11 /*tabs between the 12 columns*/ + 6 /*\tid:Z:*/ + 6 /*\tcg:Z:*/ + p.cg_bytes + 1 /*\n*/;
+}
+
+}  // namespace rb
