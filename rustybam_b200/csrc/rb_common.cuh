@@ -61,30 +61,32 @@ struct Ctr {
     uint32_t IEV;  // insertion events (ops)
     uint32_t DEV;  // deletion events (ops)
     uint32_t TXT;  // bytes of the canonical "{len}{op}" text
-    uint32_t ovf;  // sticky: the A sum wrapped past 2^32
+    uint32_t aux;  // bit 31: sticky, the A sum wrapped past 2^32 ; bits 30..0: number of "slow" ops
+                   // (zero-length, or same class as the op before it in the record) -> RF_SLOW
 };
+constexpr uint32_t AUX_OVF = 0x80000000u, AUX_CNT = 0x7FFFFFFFu;
 
 RB_HD Ctr ctr_zero() {
     Ctr c;
-    c.T = c.Q = c.A = c.EQ = c.X = c.M = c.I = c.D = c.IEV = c.DEV = c.TXT = c.ovf = 0;
+    c.T = c.Q = c.A = c.EQ = c.X = c.M = c.I = c.D = c.IEV = c.DEV = c.TXT = c.aux = 0;
     return c;
 }
 RB_HD void ctr_add(Ctr& a, const Ctr& b) {
     a.T += b.T; a.Q += b.Q;
-    uint32_t s = a.A + b.A;
-    a.ovf |= b.ovf | (uint32_t)(s < a.A);
+    const uint32_t s = a.A + b.A;
+    a.aux = (((a.aux & AUX_CNT) + (b.aux & AUX_CNT)) & AUX_CNT) | ((a.aux | b.aux) & AUX_OVF) | (s < a.A ? AUX_OVF : 0u);
     a.A = s;
     a.EQ += b.EQ; a.X += b.X; a.M += b.M; a.I += b.I; a.D += b.D;
     a.IEV += b.IEV; a.DEV += b.DEV; a.TXT += b.TXT;
 }
-RB_HD void ctr_sub(Ctr& a, const Ctr& b) {
+RB_HD void ctr_sub(Ctr& a, const Ctr& b) {  // aux is left alone
     a.T -= b.T; a.Q -= b.Q; a.A -= b.A; a.EQ -= b.EQ; a.X -= b.X; a.M -= b.M; a.I -= b.I; a.D -= b.D;
     a.IEV -= b.IEV; a.DEV -= b.DEV; a.TXT -= b.TXT;
 }
 // `n` bases of an op of class `code`; `whole` adds the event and the text of the complete op
 RB_HD void ctr_add_bases(Ctr& c, uint32_t code, uint32_t n) {
-    uint32_t s = c.A + n;
-    c.ovf |= (uint32_t)(s < c.A);
+    const uint32_t s = c.A + n;
+    if (s < c.A) c.aux |= AUX_OVF;
     c.A = s;
     if (is_ref(code)) c.T += n;
     if (is_qry(code)) c.Q += n;

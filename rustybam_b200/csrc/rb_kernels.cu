@@ -1,0 +1,1079 @@
+// rb_kernels.cu — hand-written sm_100a kernels of the PAF liftover + stats path.
+//
+//   K1 k_tokenise     CIGAR text -> packed ops, single pass, decoupled look-back on op counts
+//                     (replaces rust-htslib CigarString::try_from via paf.rs:398-399)
+//   K1b k_rec_ops     per-record op offsets + record-head bitmap + boundary validation
+//   K2 k_samples      segmented exclusive scan (decoupled look-back) of 11 prefix counters, sampled
+//                     every 32 ops (replaces the per-base arrays of aligned_pairs, paf.rs:501-538)
+//   K3 k_rec_prep     indel strip + integrity + window join bounds per record
+//                     (paf.rs:656-783, 825-857, 622-627; liftover.rs:123-127)
+//      k_pair_scan    pair offsets in emission order (liftover.rs:151-164)
+//   K4 k_lift         one thread per (window, record) pair: closed-form lift/trim + fused stats
+//                     (liftover.rs:17-105, paf.rs:541-620, bamstats.rs:107-142) — lift_core.cuh
+//      k_scan_lines   exclusive scan of line sizes / valid rows (decoupled look-back)
+//   K5 k_serialise    PAF text + numeric mirror + stats rows (paf.rs:923-943, bamstats.rs:138-142)
+//
+// All of it is HBM-bound integer/byte work: no tensor cores on purpose.
+#include <cstdio>
+
+#include "lift_core.cuh"
+#include "rb_kernels.cuh"
+#include "rec_core.cuh"
+
+namespace rb {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void report(unsigned long long* slot, uint64_t key, uint32_t code) {
+    atomicMin(slot, (unsigned long long)((key << 8) | code));
+}
+// per-byte "is not an ASCII digit" as 0xFF/0x00 lanes of a 32-bit word
+__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t x) { return __vcmpgtu4(x ^ 0x30303030u, 0x09090909u); }
+__device__ __forceinline__ uint32_t nondigit_count(uint4 c) {
+    return (__popc(nondigit_bytes(c.x)) + __popc(nondigit_bytes(c.y)) + __popc(nondigit_bytes(c.z)) + __popc(nondigit_bytes(c.w))) >> 3;
+}
+// op character -> BAM code (15 = not one of MIDNSHP=X).  (c & 31) is a perfect hash of the alphabet:
+// D=4 H=8 I=9 M=13 N=14 P=16 S=19 X=24 '='=29 ; two 16-nibble tables, then an exact compare.
+constexpr unsigned long long make_code_table(int half) {
+    unsigned long long t = ~0ull;
+    const char alphabet[10] = "MIDNSHP=X";
+    for (int c = 0; c < 9; c++) {
+        const int k = alphabet[c] & 31;
+        if ((k >> 4) == half) {
+            t &= ~(15ull << ((k & 15) * 4));
+            t |= ((unsigned long long)c) << ((k & 15) * 4);
+        }
+    }
+    return t;
+}
+constexpr unsigned long long CODE_TBL_LO = make_code_table(0), CODE_TBL_HI = make_code_table(1);
+constexpr unsigned long long CODE_CHARS = 0x3D5048534E44494Dull;  // bytes "MIDNSHP=" little-endian, code 8 = 'X'
+__device__ __forceinline__ uint32_t char_of_code(uint32_t code) {
+    return (code < 8u) ? (uint32_t)((CODE_CHARS >> (code * 8)) & 0xFFu) : 0x58u;
+}
+__device__ __forceinline__ uint32_t code_of_char(uint32_t ch) {
+    const uint32_t k = ch & 31u;
+    const uint32_t code = (uint32_t)(((k & 16u) ? CODE_TBL_HI : CODE_TBL_LO) >> ((k & 15u) * 4)) & 15u;
+    return (code <= 8u && char_of_code(code) == ch) ? code : 15u;
+}
+
+__constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+
+// ------------------------------------------------------------------------------------------------
+// decoupled look-back, one 64-bit word per tile: [63:62] = 0 invalid / 1 aggregate / 2 inclusive prefix
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long LB_AGG = 1ull << 62, LB_PRE = 2ull << 62, LB_VAL = (1ull << 62) - 1;
+
+// executed by one full warp; returns the exclusive prefix of `tile` and publishes its inclusive prefix
+__device__ __forceinline__ unsigned long long lookback_u64(unsigned long long* state, uint64_t tile, unsigned long long agg) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) atomicExch(&state[0], LB_PRE | agg);
+        return 0;
+    }
+    if (lane == 0) atomicExch(&state[tile], LB_AGG | agg);
+    unsigned long long excl = 0;
+    long long look = (long long)tile - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        unsigned long long s = LB_PRE;  // before tile 0: prefix 0
+        if (idx >= 0) {
+            do { s = ld_volatile_u64(&state[idx]); } while ((s >> 62) == 0);
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        unsigned long long v = (lane <= first) ? (s & LB_VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (pm) break;
+        look -= 32;
+    }
+    if (lane == 0) atomicExch(&state[tile], LB_PRE | (excl + agg));
+    return excl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  tokeniser
+// ------------------------------------------------------------------------------------------------
+// exact re-parse of the number that ends right before the op character at byte `pos` (rare path:
+// >= 9 digits, numbers that span more than one 16-byte chunk).  Returns false on error.
+__device__ __noinline__ bool exact_len(const uint8_t* text, uint64_t pos, uint32_t& len, uint32_t& err) {
+    long long s = (long long)pos;
+    while (text[s - 1] >= '0' && text[s - 1] <= '9') s--;  // text[-1..-16] is 0xFF
+    if (s == (long long)pos) { err = RE_CIGAR_PARSE; return false; }
+    unsigned long long v = 0;
+    for (long long k = s; k < (long long)pos; k++) {
+        v = v * 10ull + (unsigned long long)(text[k] - '0');
+        if (v > 0xFFFFFFFFull) { err = RE_CIGAR_PARSE; return false; }  // u32::from_str overflow
+    }
+    if (v > MAX_OP_LEN) { err = RE_UNSUPPORTED; return false; }
+    len = (uint32_t)v;
+    return true;
+}
+
+__global__ void __launch_bounds__(TOK_THREADS)
+k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigned long long* tile_state, unsigned int* ticket,
+           ErrSlots err, uint32_t* misc_flags) {
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_tail_v[TOK_THREADS];
+    __shared__ uint32_t s_tail_nd[TOK_THREADS];
+    __shared__ uint32_t s_warp[TOK_THREADS / 32];
+    __shared__ unsigned long long s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t g0 = tile * (uint64_t)TOK_TILE + (uint64_t)tid * 16u;
+
+    const uint4 c = ld_nc_v4(text + g0);
+    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
+    const uint32_t cnt = nondigit_count(c);
+
+    // block exclusive scan of op counts
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wpre = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < TOK_THREADS / 32; k++) {
+        const uint32_t t = s_warp[k];
+        if (k < warp) wpre += t;
+        total += t;
+    }
+    if (warp == 0) {
+        const unsigned long long ex = lookback_u64(tile_state, tile, total);
+        if (lane == 0) s_base = ex;
+    }
+
+    uint32_t v = 0, nd = 0, n = 0;
+    uint32_t first_v = 0, first_nd = 0, first_code = 0;
+    __syncthreads();
+    const uint64_t base = s_base + wpre + (inc - cnt);
+    uint32_t seen_clip = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint32_t ch = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
+        const uint32_t d = ch - 48u;
+        if (d < 10u) {
+            v = v * 10u + d;
+            nd++;
+        } else {
+            const uint32_t code = code_of_char(ch);
+            seen_clip |= (code == OP_S) | (code == OP_H);
+            if (n == 0) {
+                first_v = v; first_nd = nd; first_code = code;
+            } else {
+                uint32_t len = v;
+                if (nd == 0 || nd >= 9 || code == 15u) {
+                    uint32_t e = RE_CIGAR_PARSE;
+                    if (code == 15u || !exact_len(text, g0 + j, len, e)) { report(err.tok, g0 + j, e); len = 0; }
+                }
+                ops[base + n] = (len << 4) | (code & 15u);
+            }
+            n++;
+            v = 0; nd = 0;
+        }
+    }
+    s_tail_v[tid] = v;
+    s_tail_nd[tid] = (n == 0) ? 16u : nd;
+    __syncthreads();
+    if (n > 0) {
+        uint32_t cv = 0, cnd = 0;
+        if (tid > 0) {
+            cv = s_tail_v[tid - 1]; cnd = s_tail_nd[tid - 1];
+        } else {
+            // trailing digit run of the 16 bytes in front of the tile (0xFF pad in front of tile 0)
+            const uint4 pc = ld_nc_v4(text + g0 - 16);
+            const uint32_t pw[4] = {pc.x, pc.y, pc.z, pc.w};
+            bool all = true;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t d = ((pw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) - 48u;
+                if (d < 10u) { cv = cv * 10u + d; cnd++; }
+                else { cv = 0; cnd = 0; all = false; }
+            }
+            if (all) cnd = 16u;
+        }
+        uint32_t len = cv * c_pow10[first_nd < 10 ? first_nd : 9] + first_v;
+        const uint32_t tnd = cnd + first_nd;
+        if (tnd == 0 || tnd >= 9 || first_code == 15u) {
+            uint32_t e = RE_CIGAR_PARSE;
+            const uint64_t pos = g0 + first_nd;  // byte of the first op character
+            if (first_code == 15u || !exact_len(text, pos, len, e)) { report(err.tok, pos, e); len = 0; }
+        }
+        ops[base] = (len << 4) | (first_code & 15u);
+    }
+    if (seen_clip) atomicOr(misc_flags, 1u);
+}
+
+// K1b: warp per record (r = 0..n_rec inclusive; r == n_rec yields the total)
+__global__ void __launch_bounds__(256)
+k_rec_ops(const uint8_t* __restrict__ text, const uint64_t* __restrict__ cigar_off, uint32_t n_rec,
+          const unsigned long long* __restrict__ tile_state, uint64_t* __restrict__ op_off, uint32_t* heads, ErrSlots err) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r > n_rec) return;
+    const uint64_t c = cigar_off[r];
+    const uint64_t tile = c / TOK_TILE, tbase = tile * (uint64_t)TOK_TILE;
+    const uint64_t prefix = tile ? (tile_state[tile - 1] & LB_VAL) : 0ull;
+    const uint32_t nfull = (uint32_t)((c - tbase) >> 4), rem = (uint32_t)((c - tbase) & 15u);
+    uint32_t cnt = 0;
+    for (uint32_t j = lane; j < nfull; j += 32) cnt += nondigit_count(ld_nc_v4(text + tbase + (uint64_t)j * 16u));
+    if (lane == 0 && rem) {
+        const uint4 x = ld_nc_v4(text + tbase + (uint64_t)nfull * 16u);
+        const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+        for (uint32_t j = 0; j < rem; j++) cnt += ((((xw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) - 48u) >= 10u);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (lane == 0) {
+        const uint64_t o = prefix + cnt;
+        op_off[r] = o;
+        if (r < n_rec) {
+            const uint64_t len = cigar_off[r + 1] - c;
+            if (len > 0) {
+                atomicOr(&heads[o >> 5], 1u << (o & 31u));
+                const uint32_t last = text[c + len - 1], first = text[c];
+                if ((last - 48u) < 10u) report(err.rec, r, RE_CIGAR_PARSE);   // "10" : `&bytes[j]` out of bounds
+                if ((first - 48u) >= 10u) report(err.rec, r, RE_CIGAR_PARSE); // "M.." : expected length
+            }
+        }
+    }
+}
+
+// rust-htslib placement rules for clips (rare; only launched when the tokeniser saw S or H):
+// H only as the first or last op; S only at the ends or separated from them by H only.
+__global__ void k_check_clips(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_off, uint32_t n_rec, ErrSlots err) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t a = op_off[r], b = op_off[r + 1];
+    for (uint64_t k = a; k < b; k++) {
+        const uint32_t code = op_code(ops[k]);
+        if (code == OP_H) {
+            if (k != a && k + 1 != b) { report(err.rec, r, RE_CIGAR_PARSE); return; }
+        } else if (code == OP_S) {
+            bool ok = (k == a) || (k + 1 == b) || (op_code(ops[k - 1]) == OP_H);
+            if (!ok) {
+                ok = true;
+                for (uint64_t j = k + 1; j < b; j++)
+                    if (op_code(ops[j]) != OP_H) { ok = false; break; }
+            }
+            if (!ok) { report(err.rec, r, RE_CIGAR_PARSE); return; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  sampled segmented scan of the prefix counters
+// ------------------------------------------------------------------------------------------------
+struct SegVal {
+    Ctr c;
+    uint32_t flag;
+};
+// a = earlier span, b = later span
+__device__ __forceinline__ SegVal seg_combine(const SegVal& a, const SegVal& b) {
+    SegVal r = b;
+    if (!b.flag) {
+        r.c = a.c;
+        ctr_add(r.c, b.c);
+    }
+    r.flag = a.flag | b.flag;
+    return r;
+}
+__device__ __forceinline__ SegVal seg_shfl(const SegVal& v, int src_lane) {
+    SegVal r;
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(&v);
+    uint32_t* out = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < 13; k++) out[k] = __shfl_sync(0xffffffffu, in[k], src_lane);
+    return r;
+}
+__device__ __forceinline__ SegVal seg_identity() {
+    SegVal r;
+    r.c = ctr_zero();
+    r.flag = 0;
+    return r;
+}
+__device__ __forceinline__ void payload_store(ScanPayload* p, const SegVal& v) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(&v);
+    uint4* o = reinterpret_cast<uint4*>(p);
+    o[0] = make_uint4(in[0], in[1], in[2], in[3]);
+    o[1] = make_uint4(in[4], in[5], in[6], in[7]);
+    o[2] = make_uint4(in[8], in[9], in[10], in[11]);
+    o[3] = make_uint4(in[12], 0, 0, 0);
+}
+__device__ __forceinline__ SegVal payload_load(const ScanPayload* p) {
+    SegVal v;
+    uint32_t* out = reinterpret_cast<uint32_t*>(&v);
+    const uint4 a = ld_cg_v4(reinterpret_cast<const uint4*>(p) + 0), b = ld_cg_v4(reinterpret_cast<const uint4*>(p) + 1),
+                c = ld_cg_v4(reinterpret_cast<const uint4*>(p) + 2), d = ld_cg_v4(reinterpret_cast<const uint4*>(p) + 3);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+    out[8] = c.x; out[9] = c.y; out[10] = c.z; out[11] = c.w;
+    out[12] = d.x;
+    return v;
+}
+
+// Warp-parallel decoupled look-back with a (Ctr, head flag) payload.  Executed by one full warp.
+// Returns the segmented exclusive prefix of block `b` (flag set if a head lies in front inside the chain).
+__device__ __forceinline__ SegVal lookback_seg(uint32_t* state, ScanPayload* agg, ScanPayload* pre, uint64_t b, const SegVal& mine) {
+    const int lane = threadIdx.x & 31;
+    SegVal acc = seg_identity();
+    if (b == 0) {
+        if (lane == 0) {
+            payload_store(&pre[0], mine);
+            __threadfence();
+            atomicExch(&state[0], 2u);
+        }
+        return acc;
+    }
+    if (lane == 0) {
+        payload_store(&agg[b], mine);
+        __threadfence();
+        atomicExch(&state[b], 1u);
+    }
+    long long look = (long long)b - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        uint32_t st = 2u;
+        SegVal x = seg_identity();
+        if (idx >= 0) {
+            do { st = ld_volatile_u32(&state[idx]); } while (st == 0);
+            __threadfence();
+            x = payload_load(st == 2u ? &pre[idx] : &agg[idx]);
+        }
+        // the chain stops at the nearest predecessor that already has its prefix, or whose span holds a head
+        const unsigned stopm = __ballot_sync(0xffffffffu, st == 2u || x.flag);
+        const int stop = stopm ? (__ffs(stopm) - 1) : 31;
+        if (lane > stop) x = seg_identity();
+        // ordered reduction: lane l absorbs the EARLIER span held by lane l + d
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const SegVal y = seg_shfl(x, (lane + d) & 31);
+            if (lane + d < 32) x = seg_combine(y, x);
+        }
+        const SegVal tot = seg_shfl(x, 0);
+        acc = seg_combine(tot, acc);
+        if (stopm) break;
+        look -= 32;
+        if (look < 0) break;
+    }
+    if (lane == 0) {
+        const SegVal incl = seg_combine(acc, mine);
+        payload_store(&pre[b], incl);
+        __threadfence();
+        atomicExch(&state[b], 2u);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(SMP_THREADS)
+k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
+          Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket) {
+    __shared__ uint32_t s_ops[SMP_THREADS * 33];
+    __shared__ SegVal s_warp[SMP_THREADS / 32];
+    __shared__ SegVal s_blk;
+    __shared__ unsigned int s_b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_ops = *n_ops_dev;
+    if (tid == 0) s_b = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t b = s_b;
+    const uint64_t op0 = b * (uint64_t)SMP_OPS;
+    if (op0 >= n_ops && !(n_ops == 0 && b == 0)) return;  // blocks past the end have no successors
+
+    // coalesced load, transposed into a 33-word pitch so that thread t owns s_ops[t*33 .. t*33+31]
+#pragma unroll 8
+    for (int i = 0; i < (int)SAMPLE; i++) {
+        const uint32_t idx = (uint32_t)i * SMP_THREADS + tid;
+        const uint64_t g = op0 + idx;
+        s_ops[(idx >> 5) * 33 + (idx & 31)] = (g < n_ops) ? ops[g] : 0u;
+    }
+    __syncthreads();
+
+    const uint64_t chunk = b * SMP_THREADS + tid;
+    const uint64_t first = chunk << SAMPLE_LOG2;
+    int nvalid = 0;
+    if (first < n_ops) nvalid = (n_ops - first) < SAMPLE ? (int)(n_ops - first) : (int)SAMPLE;
+    const uint32_t h = nvalid ? heads[chunk] : 0u;
+    uint32_t prev_code = 99u;
+    if (nvalid) {
+        if (tid > 0) prev_code = op_code(s_ops[(tid - 1) * 33 + 31]);
+        else if (first > 0) prev_code = op_code(ops[first - 1]);
+    }
+    SegVal mine = seg_identity();
+    for (int j = 0; j < nvalid; j++) {
+        const uint32_t w = s_ops[tid * 33 + j];
+        const bool head = (h >> j) & 1u;
+        if (head) mine.c = ctr_zero();
+        const uint32_t code = op_code(w);
+        const uint32_t slow = (op_len(w) == 0u) | ((!head) & (code == prev_code));
+        ctr_add_op(mine.c, w);
+        mine.c.aux += slow;
+        prev_code = code;
+    }
+    mine.flag = (h != 0u);
+
+    // block-level segmented scan of the per-chunk aggregates
+    SegVal inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SegVal y = seg_shfl(inc, (lane - d) & 31);
+        if (lane >= d) inc = seg_combine(y, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    SegVal exl = seg_shfl(inc, (lane - 1) & 31);
+    if (lane == 0) exl = seg_identity();
+    __syncthreads();
+    SegVal wpre = seg_identity(), btot = seg_identity();
+#pragma unroll
+    for (int k = 0; k < SMP_THREADS / 32; k++) {
+        const SegVal t = s_warp[k];
+        if (k < warp) wpre = seg_combine(wpre, t);
+        btot = seg_combine(btot, t);
+    }
+    if (warp == 0) {
+        const SegVal ex = lookback_seg(blk_state, blk_agg, blk_pre, b, btot);
+        if (lane == 0) s_blk = ex;
+    }
+    __syncthreads();
+    if (nvalid) {
+        SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
+        if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
+        samples[chunk] = pre.c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  per-record preparation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Ctr ctr_range(const OpsView& v, const RecInfo& r, uint64_t a, uint64_t b) {  // ops [a, b), b > a
+    Ctr hi = ctr_before(v, r, b - 1);
+    ctr_add_op(hi, v.ops[b - 1]);
+    const Ctr lo = ctr_before(v, r, a);
+    Ctr d = hi;
+    ctr_sub(d, lo);
+    d.aux = hi.aux;  // flags/slow count of the whole prefix (conservative)
+    return d;
+}
+
+__device__ __forceinline__ void write_stats(const StatsDev& st, uint64_t i, uint32_t equal, uint32_t diff, uint32_t ins, uint32_t del,
+                                            uint32_t ins_ev, uint32_t del_ev, uint32_t matches) {
+    st.equal[i] = equal; st.diff[i] = diff; st.ins[i] = ins; st.del[i] = del;
+    st.ins_ev[i] = ins_ev; st.del_ev[i] = del_ev; st.matches[i] = matches;
+    // bamstats.rs:138-142 — f32: (100.0 * equal as f32) / (u32 sum) as f32 ; IEEE mul + div, no contraction
+    const float num = __fmul_rn(100.0f, __uint2float_rn(equal));
+    st.id_a[i] = __fdiv_rn(num, __uint2float_rn(equal + diff + del + ins));
+    st.id_e[i] = __fdiv_rn(num, __uint2float_rn(equal + diff + del_ev + ins_ev));
+    st.id_m[i] = __fdiv_rn(num, __uint2float_rn(equal + diff));
+}
+
+__global__ void __launch_bounds__(128)
+k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uint32_t* __restrict__ ops,
+           const Ctr* __restrict__ samples, WinView win, RecInfo* __restrict__ recs, uint32_t* __restrict__ pair_cnt, StatsDev st,
+           ErrSlots err) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= in.n_rec) return;
+    OpsView v{ops, samples};
+    RecInfo ri;
+    ri.op_first = op_off[r]; ri.op_end = op_off[r + 1];
+    ri.eo0 = ri.op_first; ri.eo1 = ri.op_end;
+    ri.t_st = in.t_st[r]; ri.t_en = in.t_en[r];
+    ri.q_st0 = in.q_st[r]; ri.q_en0 = in.q_en[r];
+    ri.q_st = ri.q_st0; ri.q_en = ri.q_en0;
+    ri.q_len = in.q_len[r]; ri.t_len = in.t_len[r]; ri.mapq = in.mapq[r];
+    ri.q_name = in.q_id[r]; ri.t_name = in.t_id[r];
+    ri.flags = (in.strand[r] == '-') ? RF_MINUS : 0u;
+    ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.pad = 0;
+    ri.tot = ctr_zero();
+
+    // integrity at load (paf.rs:70): spans of the UNSTRIPPED record against the full CIGAR
+    Ctr full = ctr_zero();
+    if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end);
+    if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
+    if ((uint64_t)full.T != ri.t_en - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
+    if (full.aux & 0x7FFFFFFFu) ri.flags |= RF_SLOW;
+
+    if (mode == 0) {  // rb stats --paf: counters of the record as read (bamstats.rs:91-105)
+        ri.tot = full;
+        write_stats(st, r, full.EQ, full.X + full.M, full.I, full.D, full.IEV, full.DEV, full.M);
+        recs[r] = ri;
+        return;
+    }
+    const uint32_t e = strip_record(ops, ri);
+    if (e != RE_OK) {
+        report(err.rec, r, e);
+        pair_cnt[r] = 0;
+        recs[r] = ri;
+        return;
+    }
+    ri.tot = (ri.eo0 == ri.op_first && ri.eo1 == ri.op_end) ? full : ctr_range(v, ri, ri.eo0, ri.eo1);
+
+    // join: windows of this contig with en > t_st && st < t_en (paf.rs:622-627, on stripped coordinates)
+    uint32_t cnt = 0;
+    if (win.st != nullptr && !win.general) {
+        const uint32_t clo = win.cont_lo[ri.t_name], chi = win.cont_hi[ri.t_name];
+        uint32_t lo = clo, hi = chi;
+        while (lo < hi) {  // first window whose running max of `en` exceeds t_st
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (win.en_pm[mid] > ri.t_st) hi = mid; else lo = mid + 1;
+        }
+        ri.wlo = lo;
+        hi = chi;
+        while (lo < hi) {  // first window with st >= t_en
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (win.st[mid] >= ri.t_en) hi = mid; else lo = mid + 1;
+        }
+        ri.whi = lo;
+        cnt = ri.whi - ri.wlo;
+    }
+    pair_cnt[r] = cnt;
+    recs[r] = ri;
+}
+
+// pair offsets in emission order: exclusive scan of pair_cnt[rec_order[k]] (single block; n_rec is small)
+__global__ void __launch_bounds__(1024) k_pair_scan(const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ rec_order,
+                                                    uint32_t n_rec, uint64_t* __restrict__ pair_off) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_rec; base += 1024) {
+        const uint32_t k = base + tid;
+        const unsigned long long x = (k < n_rec) ? pair_cnt[rec_order[k]] : 0ull;
+        unsigned long long inc = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long wpre = 0, tot = 0;
+        for (int j = 0; j < 32; j++) {
+            const unsigned long long t = s_warp[j];
+            if (j < warp) wpre += t;
+            tot += t;
+        }
+        const unsigned long long carry = s_carry;
+        if (k < n_rec) pair_off[k] = carry + wpre + inc - x;
+        __syncthreads();
+        if (tid == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (tid == 0) pair_off[n_rec] = s_carry;
+}
+
+// general path: cartesian product + overlap filter in BED file order (liftover.rs:123-127); block per record
+__global__ void __launch_bounds__(256) k_pair_count_bf(const RecInfo* __restrict__ recs, uint32_t n_rec, WinView win, uint32_t* pair_cnt) {
+    const uint32_t r = blockIdx.x;
+    if (r >= n_rec) return;
+    const RecInfo& ri = recs[r];
+    const uint32_t clo = win.cont_lo[ri.t_name], chi = win.cont_hi[ri.t_name];
+    uint32_t cnt = 0;
+    for (uint32_t w = clo + threadIdx.x; w < chi; w += blockDim.x) cnt += (ri.t_en > win.st[w] && ri.t_st < win.en[w]);
+    __shared__ uint32_t s[8];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int k = 0; k < 8; k++) t += s[k];
+        pair_cnt[r] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_pair_fill_bf(const RecInfo* __restrict__ recs, const uint32_t* __restrict__ rec_rank,
+                                                     uint32_t n_rec, WinView win, const uint64_t* __restrict__ pair_off,
+                                                     uint32_t* __restrict__ pair_win) {
+    const uint32_t r = blockIdx.x;
+    if (r >= n_rec) return;
+    const RecInfo& ri = recs[r];
+    const uint32_t clo = win.cont_lo[ri.t_name], chi = win.cont_hi[ri.t_name];
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const uint64_t out0 = pair_off[rec_rank[r]];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t w0 = clo; w0 < chi; w0 += blockDim.x) {
+        const uint32_t w = w0 + threadIdx.x;
+        const bool hit = (w < chi) && (ri.t_en > win.st[w] && ri.t_st < win.en[w]);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t pre = s_base, tot = 0;
+        for (int k = 0; k < 8; k++) {
+            if (k < warp) pre += s_w[k];
+            tot += s_w[k];
+        }
+        if (hit) pair_win[out0 + pre + __popc(m & ((1u << lane) - 1u))] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) s_base += tot;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  lift: one thread per (window, record) pair
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rank_of_pair(const uint64_t* __restrict__ pair_off, uint32_t n_rec, uint64_t p) {
+    uint32_t lo = 0, hi = n_rec;  // largest k with pair_off[k] <= p
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (pair_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128)
+k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
+       const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
+       const uint64_t* __restrict__ names_off, int policy, PairRes* __restrict__ res, uint32_t* __restrict__ line_len, ErrSlots err) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t k = rank_of_pair(pair_off, n_rec, p);
+    const uint32_t r = rec_order[k];
+    const RecInfo ri = recs[r];
+    const uint64_t j = p - pair_off[k];
+    const uint32_t w = win.pair_win ? win.pair_win[p] : (ri.wlo + (uint32_t)j);
+    const uint64_t w_st = win.st[w], w_en = win.en[w];
+    PairRes pr;
+    uint32_t len = 0;
+    if (ri.t_en > w_st && ri.t_st < w_en) {  // nested windows can make the [wlo,whi) range a superset
+        OpsView v{ops, samples};
+        const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, pr);
+        if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
+        if (pr.kind != PK_DROP) {
+            const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
+            const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
+            const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+            len = line_bytes(ri, pr, qn, tn, idl);
+        }
+    } else {
+        pr.kind = PK_DROP; pr.pad = 0;
+        pr.t_st = pr.t_en = pr.q_st = pr.q_en = pr.nmatch = pr.aln_len = pr.si = pr.ei = 0;
+        pr.s_len = pr.e_len = pr.cg_bytes = 0;
+        pr.equal = pr.diff = pr.ins = pr.del = pr.ins_ev = pr.del_ev = pr.matches = 0;
+    }
+    res[p] = pr;
+    line_len[p] = len;
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of line sizes and of valid-row flags (decoupled look-back, 16-byte payload)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ ulonglong2 lookback_2u64(uint32_t* state, ulonglong2* agg, ulonglong2* pre, uint64_t b, ulonglong2 mine) {
+    const int lane = threadIdx.x & 31;
+    ulonglong2 acc = make_ulonglong2(0, 0);
+    if (b == 0) {
+        if (lane == 0) {
+            pre[0] = mine;
+            __threadfence();
+            atomicExch(&state[0], 2u);
+        }
+        return acc;
+    }
+    if (lane == 0) {
+        agg[b] = mine;
+        __threadfence();
+        atomicExch(&state[b], 1u);
+    }
+    long long look = (long long)b - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        uint32_t st = 2u;
+        ulonglong2 x = make_ulonglong2(0, 0);
+        if (idx >= 0) {
+            do { st = ld_volatile_u32(&state[idx]); } while (st == 0);
+            __threadfence();
+            const uint4 raw = ld_cg_v4(st == 2u ? &pre[idx] : &agg[idx]);
+            x.x = ((unsigned long long)raw.y << 32) | raw.x;
+            x.y = ((unsigned long long)raw.w << 32) | raw.z;
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, st == 2u);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        if (lane > first) x = make_ulonglong2(0, 0);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            x.x += __shfl_xor_sync(0xffffffffu, x.x, d);
+            x.y += __shfl_xor_sync(0xffffffffu, x.y, d);
+        }
+        acc.x += x.x; acc.y += x.y;
+        if (pm) break;
+        look -= 32;
+        if (look < 0) break;
+    }
+    if (lane == 0) {
+        pre[b] = make_ulonglong2(acc.x + mine.x, acc.y + mine.y);
+        __threadfence();
+        atomicExch(&state[b], 2u);
+    }
+    return acc;
+}
+
+constexpr int LNS_ITEMS = 4;  // items per thread
+__global__ void __launch_bounds__(LNS_THREADS)
+k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t* __restrict__ line_off, uint64_t* __restrict__ out_idx,
+             uint32_t* blk_state, ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket) {
+    __shared__ ulonglong2 s_warp[LNS_THREADS / 32];
+    __shared__ ulonglong2 s_blk;
+    __shared__ unsigned int s_b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_b = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint64_t b = s_b;
+    const uint64_t i0 = (b * LNS_THREADS + tid) * LNS_ITEMS;
+    uint32_t x[LNS_ITEMS];
+    unsigned long long sb = 0, sc = 0;
+#pragma unroll
+    for (int k = 0; k < LNS_ITEMS; k++) {
+        x[k] = (i0 + k < n) ? line_len[i0 + k] : 0u;
+        sb += x[k];
+        sc += (x[k] != 0u);
+    }
+    unsigned long long ib = sb, ic = sc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { ib += tb; ic += tc; }
+    }
+    if (lane == 31) s_warp[warp] = make_ulonglong2(ib, ic);
+    __syncthreads();
+    unsigned long long wb = 0, wc = 0, tb = 0, tc = 0;
+#pragma unroll
+    for (int k = 0; k < LNS_THREADS / 32; k++) {
+        const ulonglong2 t = s_warp[k];
+        if (k < warp) { wb += t.x; wc += t.y; }
+        tb += t.x; tc += t.y;
+    }
+    if (warp == 0) {
+        const ulonglong2 ex = lookback_2u64(blk_state, blk_agg, blk_pre, b, make_ulonglong2(tb, tc));
+        if (lane == 0) s_blk = ex;
+    }
+    __syncthreads();
+    unsigned long long ob = s_blk.x + wb + ib - sb, oc = s_blk.y + wc + ic - sc;
+#pragma unroll
+    for (int k = 0; k < LNS_ITEMS; k++) {
+        if (i0 + k < n) { line_off[i0 + k] = ob; out_idx[i0 + k] = oc; }
+        ob += x[k];
+        oc += (x[k] != 0u);
+    }
+    // the block that owns the last item also writes the totals at index n
+    if (i0 < n && i0 + LNS_ITEMS >= n) { line_off[n] = ob; out_idx[n] = oc; }
+    if (n == 0 && b == 0 && tid == 0) { line_off[0] = 0; out_idx[0] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  serialiser
+// ------------------------------------------------------------------------------------------------
+template <class P>
+__device__ __forceinline__ P put_u32(P p, uint32_t v) {
+    const uint32_t nd = ndigits32(v);
+    for (int i = (int)nd - 1; i >= 0; i--) {
+        p[i] = (uint8_t)('0' + v % 10u);
+        v /= 10u;
+    }
+    return p + nd;
+}
+template <class P>
+__device__ __forceinline__ P put_u64(P p, uint64_t v) {
+    if (v < 4294967296ull) return put_u32(p, (uint32_t)v);
+    const uint32_t nd = ndigits64(v);
+    for (int i = (int)nd - 1; i >= 0; i--) {
+        p[i] = (uint8_t)('0' + (uint32_t)(v % 10ull));
+        v /= 10ull;
+    }
+    return p + nd;
+}
+template <class P>
+__device__ __forceinline__ P put_bytes(P p, const uint8_t* __restrict__ src, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) p[i] = src[i];
+    return p + n;
+}
+template <class P>
+__device__ __forceinline__ P put_op(P p, uint32_t len, uint32_t code) {
+    p = put_u32(p, len);
+    *p = (uint8_t)char_of_code(code);
+    return p + 1;
+}
+
+struct SerArgs {
+    const RecInfo* recs;
+    const uint32_t* ops;
+    WinView win;
+    const uint64_t* names_off;
+    const uint8_t* names;
+};
+
+// "_TO.<leading ops>.<trailing ops, last first>" (paf.rs:726-732)
+template <class P>
+__device__ __forceinline__ P put_strip_id(P p, const RecInfo& ri, const uint32_t* __restrict__ ops) {
+    *p++ = '_'; *p++ = 'T'; *p++ = 'O'; *p++ = '.';
+    for (uint64_t k = ri.op_first; k < ri.eo0; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
+    *p++ = '.';
+    for (uint64_t k = ri.op_end; k > ri.eo1; k--) p = put_op(p, op_len(ops[k - 1]), op_code(ops[k - 1]));
+    return p;
+}
+
+// the 12 columns + "id:Z:..." + "\tcg:Z:" (paf.rs:923-943), sequential
+template <class P>
+__device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri, const PairRes& pr, uint32_t w) {
+    p = put_bytes(p, a.names + a.names_off[ri.q_name], (uint32_t)(a.names_off[ri.q_name + 1] - a.names_off[ri.q_name]));
+    *p++ = '\t'; p = put_u64(p, ri.q_len);
+    *p++ = '\t'; p = put_u64(p, pr.q_st);
+    *p++ = '\t'; p = put_u64(p, pr.q_en);
+    *p++ = '\t'; *p++ = (ri.flags & RF_MINUS) ? '-' : '+';
+    *p++ = '\t';
+    p = put_bytes(p, a.names + a.names_off[ri.t_name], (uint32_t)(a.names_off[ri.t_name + 1] - a.names_off[ri.t_name]));
+    *p++ = '\t'; p = put_u64(p, ri.t_len);
+    *p++ = '\t'; p = put_u64(p, pr.t_st);
+    *p++ = '\t'; p = put_u64(p, pr.t_en);
+    *p++ = '\t'; p = put_u64(p, pr.nmatch);
+    *p++ = '\t'; p = put_u64(p, pr.aln_len);
+    *p++ = '\t'; p = put_u64(p, ri.mapq);
+    *p++ = '\t'; *p++ = 'i'; *p++ = 'd'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
+    if (pr.kind == PK_EARLY) {
+        if (ri.flags & RF_STRIPPED) p = put_strip_id(p, ri, a.ops);
+    } else {
+        p = put_bytes(p, a.win.ids + a.win.ids_off[w], (uint32_t)(a.win.ids_off[w + 1] - a.win.ids_off[w]));
+    }
+    *p++ = '\t'; *p++ = 'c'; *p++ = 'g'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
+    return p;
+}
+
+// trimmed / early-return CIGAR text, sequential
+template <class P>
+__device__ __forceinline__ P put_cigar_seq(P p, const SerArgs& a, const RecInfo& ri, const PairRes& pr) {
+    const uint32_t* __restrict__ ops = a.ops;
+    if (pr.kind == PK_EARLY) {
+        for (uint64_t k = pr.si; k <= pr.ei; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
+    } else if (ri.flags & RF_SLOW) {
+        merged_walk(ops, pr.si, pr.ei, pr.s_len, pr.e_len, [&](uint32_t len, uint32_t code) { p = put_op(p, len, code); });
+    } else {
+        p = put_op(p, pr.s_len, op_code(ops[pr.si]));
+        for (uint64_t k = pr.si + 1; k < pr.ei; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
+        if (pr.ei > pr.si) p = put_op(p, pr.e_len, op_code(ops[pr.ei]));
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(SER_LINES)
+k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
+            SerArgs a, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off, const uint64_t* __restrict__ out_idx,
+            uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st) {
+    extern __shared__ __align__(16) uint8_t s_buf[];
+    __shared__ uint8_t s_stage[SER_LINES / 32][384];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t p0 = (uint64_t)blockIdx.x * SER_LINES;
+    const uint64_t p = p0 + tid;
+    const uint64_t pend = (p0 + SER_LINES < n_pairs) ? (p0 + SER_LINES) : n_pairs;
+    const uint64_t byte0 = line_off[p0], byte1 = line_off[pend];
+    const uint64_t region = byte1 - byte0;
+
+    PairRes pr;
+    pr.kind = PK_DROP;
+    uint64_t my_off = 0, my_len = 0;
+    uint32_t r = 0, w = 0;
+    if (p < n_pairs) {
+        pr = res[p];
+        my_off = line_off[p];
+        my_len = line_off[p + 1] - my_off;
+    }
+    const bool live = (pr.kind != PK_DROP);
+    if (live) {
+        const uint32_t k = rank_of_pair(pair_off, n_rec, p);
+        r = rec_order[k];
+        w = a.win.pair_win ? a.win.pair_win[p] : (a.recs[r].wlo + (uint32_t)(p - pair_off[k]));
+        const uint64_t o = out_idx[p];
+        if (out_line_off) out_line_off[o] = my_off;
+        if (num.q_st) {
+            num.q_st[o] = pr.q_st; num.q_en[o] = pr.q_en; num.t_st[o] = pr.t_st; num.t_en[o] = pr.t_en;
+            num.nmatch[o] = pr.nmatch; num.aln_len[o] = pr.aln_len;
+            num.rec_idx[o] = r; num.win_idx[o] = a.win.bed_row[w];
+        }
+        if (st.equal) write_stats(st, o, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
+    }
+    if (out_line_off && p0 + SER_LINES >= n_pairs && tid == 0) out_line_off[out_idx[n_pairs]] = line_off[n_pairs];
+    if (out_text == nullptr || region == 0) return;
+
+    const bool small = __syncthreads_and(my_len <= 2048) && region <= (uint64_t)(SER_CAP - 16);
+    if (small) {
+        // compose the whole line group in shared memory, one thread per line, then stream it out
+        const uint32_t shift = (uint32_t)((uintptr_t)(out_text + byte0) & 15u);  // keep smem/global 16-byte phase equal
+        if (live) {
+            const RecInfo& ri = a.recs[r];
+            uint8_t* q = s_buf + shift + (my_off - byte0);
+            q = put_header(q, a, ri, pr, w);
+            q = put_cigar_seq(q, a, ri, pr);
+            *q = '\n';
+        }
+        __syncthreads();
+        uint8_t* dst = out_text + byte0;
+        const uint32_t n = (uint32_t)region;
+        const uint32_t head = (16u - shift) & 15u;  // bytes until dst is 16-byte aligned
+        const uint32_t hb = head < n ? head : n;
+        for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = s_buf[shift + i];
+        const uint32_t nvec = (n - hb) >> 4;
+        const uint4* sv = reinterpret_cast<const uint4*>(s_buf + shift + hb);
+        uint4* dv = reinterpret_cast<uint4*>(dst + hb);
+        for (uint32_t i = tid; i < nvec; i += SER_LINES) dv[i] = sv[i];
+        for (uint32_t i = hb + (nvec << 4) + tid; i < n; i += SER_LINES) dst[i] = s_buf[shift + i];
+        return;
+    }
+
+    // long lines: one warp per line, straight to global memory
+    for (uint64_t q = p0 + warp; q < pend; q += SER_LINES / 32) {
+        const PairRes lp = res[q];
+        if (lp.kind == PK_DROP) continue;
+        const uint32_t k = rank_of_pair(pair_off, n_rec, q);
+        const uint32_t rr = rec_order[k];
+        const RecInfo& ri = a.recs[rr];
+        const uint32_t ww = a.win.pair_win ? a.win.pair_win[q] : (ri.wlo + (uint32_t)(q - pair_off[k]));
+        uint8_t* dst = out_text + line_off[q];
+        const uint64_t llen = line_off[q + 1] - line_off[q];
+        const uint64_t hdr = llen - lp.cg_bytes - 1;
+        if (hdr <= 384) {
+            if (lane == 0) put_header(&s_stage[warp][0], a, ri, lp, ww);
+            __syncwarp();
+            for (uint32_t i = lane; i < hdr; i += 32) dst[i] = s_stage[warp][i];
+        } else if (lane == 0) {
+            put_header(dst, a, ri, lp, ww);
+        }
+        __syncwarp();
+        dst += hdr;
+        if ((ri.flags & RF_SLOW) && lp.kind == PK_TRIM) {
+            if (lane == 0) put_cigar_seq(dst, a, ri, lp);
+        } else {
+            // 32 ops per round: per-lane text, warp scan of sizes, stage, coalesced byte copy
+            uint64_t pos = 0;
+            for (uint64_t k0 = lp.si; k0 <= lp.ei; k0 += 32) {
+                const uint64_t kk = k0 + lane;
+                uint32_t len = 0, code = 0, nb = 0;
+                if (kk <= lp.ei) {
+                    const uint32_t ow = a.ops[kk];
+                    code = op_code(ow);
+                    len = op_len(ow);
+                    if (lp.kind == PK_TRIM) {
+                        if (kk == lp.si) len = lp.s_len;
+                        else if (kk == lp.ei) len = lp.e_len;
+                    }
+                    nb = ndigits32(len) + 1;
+                }
+                uint32_t inc = nb;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += t;
+                }
+                const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                __syncwarp();
+                if (nb) put_op(&s_stage[warp][inc - nb], len, code);
+                __syncwarp();
+                for (uint32_t i = lane; i < tot; i += 32) dst[pos + i] = s_stage[warp][i];
+                pos += tot;
+            }
+        }
+        if (lane == 0) out_text[line_off[q + 1] - 1] = '\n';
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsigned long long* tile_state, unsigned int* ticket,
+                     ErrSlots err, uint32_t* misc_flags, cudaStream_t s) {
+    if (n_tiles == 0) return;
+    k_tokenise<<<(unsigned)n_tiles, TOK_THREADS, 0, s>>>(text, ops, tile_state, ticket, err, misc_flags);
+}
+void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,
+                    uint64_t* op_off, uint32_t* heads, ErrSlots err, cudaStream_t s) {
+    const uint64_t warps = (uint64_t)n_rec + 1;
+    k_rec_ops<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(text, cigar_off, n_rec, tile_state, op_off, heads, err);
+}
+void launch_samples(const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads, Ctr* samples,
+                    uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket, cudaStream_t s) {
+    const uint64_t blocks = (n_ops_bound + SMP_OPS - 1) / SMP_OPS;
+    if (blocks == 0) return;
+    k_samples<<<(unsigned)blocks, SMP_THREADS, 0, s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+}
+void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, ErrSlots err, cudaStream_t s) {
+    if (n_rec == 0) return;
+    k_check_clips<<<(n_rec + 127) / 128, 128, 0, s>>>(ops, op_off, n_rec, err);
+}
+void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32_t* ops, const Ctr* samples, WinView win,
+                     RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s) {
+    if (in.n_rec == 0) return;
+    k_rec_prep<<<(in.n_rec + 127) / 128, 128, 0, s>>>(mode, in, op_off, ops, samples, win, recs, pair_cnt, st, err);
+}
+void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s) {
+    k_pair_scan<<<1, 1024, 0, s>>>(pair_cnt, rec_order, n_rec, pair_off);
+}
+void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, PairRes* res,
+                 uint32_t* line_len, ErrSlots err, cudaStream_t s) {
+    if (n_pairs == 0) return;
+    k_lift<<<(unsigned)((n_pairs + 127) / 128), 128, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
+                                                             policy, res, line_len, err);
+}
+void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
+                       ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s) {
+    const uint64_t per = (uint64_t)LNS_THREADS * LNS_ITEMS;
+    const uint64_t blocks = n ? (n + per - 1) / per : 1;
+    k_scan_lines<<<(unsigned)blocks, LNS_THREADS, 0, s>>>(line_len, n, line_off, out_idx, blk_state, blk_agg, blk_pre, ticket);
+}
+void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                      const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
+                      const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
+                      StatsDev st, cudaStream_t s) {
+    if (n_pairs == 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
+        attr_set = true;
+    }
+    SerArgs a{recs, ops, win, names_off, names};
+    k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
+        n_pairs, pair_off, rec_order, n_rec, a, res, line_off, out_idx, out_text, out_line_off, num, st);
+}
+void launch_pair_count_bf(const RecInfo* recs, uint32_t n_rec, WinView win, uint32_t* pair_cnt, cudaStream_t s) {
+    if (n_rec == 0) return;
+    k_pair_count_bf<<<n_rec, 256, 0, s>>>(recs, n_rec, win, pair_cnt);
+}
+void launch_pair_fill_bf(const RecInfo* recs, const uint32_t* rec_rank, uint32_t n_rec, WinView win,
+                         const uint64_t* pair_off, uint32_t* pair_win, cudaStream_t s) {
+    if (n_rec == 0) return;
+    k_pair_fill_bf<<<n_rec, 256, 0, s>>>(recs, rec_rank, n_rec, win, pair_off, pair_win);
+}
+
+}  // namespace rb

@@ -1,0 +1,87 @@
+// rb_kernels.cuh — launchers of the sm_100a kernels (definitions in rb_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rb_common.cuh"
+
+namespace rb {
+
+constexpr int TOK_THREADS = 256;
+constexpr int TOK_TILE = TOK_THREADS * 16;  // text bytes per tokeniser tile
+constexpr int TEXT_FRONT_PAD = 16;          // bytes of 0xFF in front of the text (look-behind halo of tile 0)
+constexpr int SMP_THREADS = 256;
+constexpr int SMP_OPS = SMP_THREADS * (int)SAMPLE;  // ops per sample-scan block
+constexpr int LNS_THREADS = 256;
+constexpr int SER_LINES = 128;              // lines per serialiser block
+constexpr int SER_CAP = 40 * 1024;          // smem bytes for composing a line group
+
+struct ScanPayload {  // look-back payload of the segmented sample scan: 64 B, 16-byte aligned
+    Ctr c;
+    uint32_t flag;    // a record head lies inside the span this aggregate covers
+    uint32_t pad[3];
+};
+
+struct WinView {
+    const uint64_t* st;
+    const uint64_t* en;
+    const uint64_t* en_pm;     // prefix max of en within the contig (== en when en is monotone)
+    const uint64_t* ids_off;
+    const uint8_t* ids;
+    const uint32_t* bed_row;
+    const uint32_t* cont_lo;   // per name id: window range of that contig
+    const uint32_t* cont_hi;
+    const uint32_t* pair_win;  // general path: explicit window per pair (nullptr on the fast path)
+    uint32_t general;          // 1: arrays are in BED file order (grouped by contig), pairs come from the brute-force join
+};
+
+struct RecInput {  // device copies of rb_records columns
+    const uint64_t* cigar_off;
+    const uint64_t *q_len, *q_st, *q_en, *t_len, *t_st, *t_en, *mapq;
+    const uint8_t* strand;
+    const uint32_t *q_id, *t_id;
+    const uint64_t* names_off;
+    const uint8_t* names;
+    uint32_t n_rec;
+};
+
+struct StatsDev {  // device SoA of rb_stats_out
+    uint32_t *equal, *diff, *ins, *del, *ins_ev, *del_ev, *matches;
+    float *id_m, *id_e, *id_a;
+};
+struct NumDev {  // device SoA of the numeric mirror
+    uint64_t *q_st, *q_en, *t_st, *t_en, *nmatch, *aln_len;
+    uint32_t *rec_idx, *win_idx;
+};
+
+// error slots (device, u64 each, initialised to ~0): min over (key << 8 | code)
+struct ErrSlots {
+    unsigned long long* tok;  // key = byte position in the text
+    unsigned long long* rec;  // key = record index
+};
+
+void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsigned long long* tile_state,
+                     unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, cudaStream_t s);
+void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,
+                    uint64_t* op_off, uint32_t* heads, ErrSlots err, cudaStream_t s);
+void launch_samples(const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads, Ctr* samples,
+                    uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket, cudaStream_t s);
+void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, ErrSlots err, cudaStream_t s);
+// mode 0: rb stats (full record, no strip) ; mode 1: liftover (strip + join)
+void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32_t* ops, const Ctr* samples, WinView win,
+                     RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s);
+void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s);
+void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, PairRes* res,
+                 uint32_t* line_len, ErrSlots err, cudaStream_t s);
+void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
+                       ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s);
+void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                      const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
+                      const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
+                      StatsDev st, cudaStream_t s);
+// general path (unsorted / nested BED rows): the reference's cartesian product + overlap filter (liftover.rs:123-127)
+void launch_pair_count_bf(const RecInfo* recs, uint32_t n_rec, WinView win, uint32_t* pair_cnt, cudaStream_t s);
+void launch_pair_fill_bf(const RecInfo* recs, const uint32_t* rec_rank, uint32_t n_rec, WinView win,
+                         const uint64_t* pair_off, uint32_t* pair_win, cudaStream_t s);
+
+}  // namespace rb

@@ -1,0 +1,778 @@
+// rbcuda.cu — C ABI (include/rbcuda.h) over the sm_100a kernels: context, HBM / pinned buffer
+// pools, and the upload -> tokenise -> scan -> join -> lift -> serialise -> download pipeline.
+// There is NO CPU implementation behind these entry points: without a compute-capability-10
+// device they fail with RB_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rbcuda.h"
+#include "rb_kernels.cuh"
+#include "rec_core.cuh"
+
+using namespace rb;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 8 + 256;  // head-room so that steady-state calls never reallocate
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); want = n; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBlock {
+    void* p = nullptr;
+    size_t cap = 0;
+    bool in_use = false;
+};
+
+struct KEvent {
+    const char* name;
+    cudaEvent_t a, b;
+};
+
+}  // namespace
+
+struct rb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    bool profiling = false;
+    std::vector<KEvent> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<rb_kernel_time> times;
+    std::vector<PinnedBlock*> pinned;
+    rb_batch* scratch = nullptr;  // reused by rb_liftover / rb_stats
+    DevBuf scalars;               // small device scalars
+    void* h_scalars = nullptr;    // pinned mirror
+};
+
+struct rb_batch {
+    uint32_t n_rec = 0, n_win = 0, n_names = 0;
+    uint64_t n_bytes = 0, n_tiles = 0, ops_bound = 0;
+    bool general = false;  // BED rows not (sorted, monotone `en`, file order == sorted order): brute-force join
+    std::vector<uint64_t> h_cigar_off;
+    // inputs
+    DevBuf text_raw, cigar_off, cols64, strand, ids32, names, names_off, rec_order, rec_rank;
+    DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, cont_lo, cont_hi;
+    // intermediates
+    DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
+    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre;
+    // outputs (device)
+    DevBuf out_text, out_line_off, out_num, out_stats;
+    rb_summary sum{};
+    bool have_lift = false, have_stats = false, with_stats = false;
+    uint64_t stats_n = 0;
+};
+
+namespace {
+
+// device scalar slots
+enum { SC_TICKET_TOK = 0, SC_TICKET_SMP = 1, SC_TICKET_LNS = 2, SC_MISC = 3, SC_ERR_TOK = 4 /*u64*/, SC_ERR_REC = 6 /*u64*/, SC_WORDS = 8 };
+
+int fail(rb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            (void)cudaGetLastError();                                                              \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+        }                                                                                          \
+    } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+PinnedBlock* pinned_get(rb_ctx* ctx, size_t n) {
+    PinnedBlock* best = nullptr;
+    for (PinnedBlock* b : ctx->pinned)
+        if (!b->in_use && b->cap >= n && (!best || b->cap < best->cap)) best = b;
+    if (!best) {
+        // drop the largest idle block that is too small, so the pool does not grow without bound
+        for (size_t i = 0; i < ctx->pinned.size(); i++)
+            if (!ctx->pinned[i]->in_use) {
+                cudaFreeHost(ctx->pinned[i]->p);
+                delete ctx->pinned[i];
+                ctx->pinned.erase(ctx->pinned.begin() + (long)i);
+                break;
+            }
+        best = new PinnedBlock();
+        const size_t want = n + n / 8 + 4096;
+        if (cudaHostAlloc(&best->p, want, cudaHostAllocDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            delete best;
+            return nullptr;
+        }
+        best->cap = want;
+        ctx->pinned.push_back(best);
+    }
+    best->in_use = true;
+    return best;
+}
+
+// ---- per-kernel CUDA-event timing ----
+struct KScope {
+    rb_ctx* ctx;
+    KEvent ev{};
+    bool on;
+    KScope(rb_ctx* c, const char* name) : ctx(c), on(c->profiling) {
+        if (!on) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->ev_pool.empty()) { e = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+            else cudaEventCreate(&e);
+            return e;
+        };
+        ev.name = name; ev.a = get(); ev.b = get();
+        cudaEventRecord(ev.a, ctx->stream);
+    }
+    ~KScope() {
+        if (!on) return;
+        cudaEventRecord(ev.b, ctx->stream);
+        ctx->pending.push_back(ev);
+    }
+};
+void flush_times(rb_ctx* ctx) {  // call after a stream sync
+    for (KEvent& k : ctx->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, k.a, k.b) != cudaSuccess) (void)cudaGetLastError();
+        rb_kernel_time* slot = nullptr;
+        for (auto& t : ctx->times)
+            if (strcmp(t.name, k.name) == 0) slot = &t;
+        if (!slot) {
+            rb_kernel_time t{};
+            strncpy(t.name, k.name, sizeof t.name - 1);
+            ctx->times.push_back(t);
+            slot = &ctx->times.back();
+        }
+        slot->launches++;
+        slot->ms += ms;
+        ctx->ev_pool.push_back(k.a);
+        ctx->ev_pool.push_back(k.b);
+    }
+    ctx->pending.clear();
+}
+
+int map_err(rb_ctx* ctx, rb_batch* b, uint64_t e_tok, uint64_t e_rec) {
+    uint64_t best_rec = UINT64_MAX;
+    uint32_t code = 0;
+    if (e_tok != UINT64_MAX) {
+        const uint64_t pos = e_tok >> 8;
+        auto it = std::upper_bound(b->h_cigar_off.begin(), b->h_cigar_off.end(), pos);
+        best_rec = (uint64_t)(it - b->h_cigar_off.begin()) - 1;
+        code = (uint32_t)(e_tok & 0xFF);
+    }
+    if (e_rec != UINT64_MAX && (e_rec >> 8) < best_rec) {
+        best_rec = e_rec >> 8;
+        code = (uint32_t)(e_rec & 0xFF);
+    }
+    if (best_rec == UINT64_MAX) return RB_OK;
+    switch (code) {
+        case RE_CIGAR_PARSE: return fail(ctx, RB_ERR_REF_CIGAR_PARSE, "record %llu: Unable to parse cigar string (reference panics, paf.rs:399)", (unsigned long long)best_rec);
+        case RE_INTEGRITY: return fail(ctx, RB_ERR_REF_INTEGRITY, "record %llu: CIGAR does not match the record's spans (check_integrity().unwrap(), paf.rs:70)", (unsigned long long)best_rec);
+        case RE_STRIP_PANIC: return fail(ctx, RB_ERR_REF_STRIP, "record %llu: remove_trailing_indels panics in the reference (empty / leading-deletion / all-indel CIGAR)", (unsigned long long)best_rec);
+        case RE_INDEX_PANIC: return fail(ctx, RB_ERR_REF_INDEX, "record %llu: Problem getting index in cigar (liftover.rs:31-49)", (unsigned long long)best_rec);
+        default: return fail(ctx, RB_ERR_UNSUPPORTED, "record %llu: op length >= 2^28 or per-record sums >= 2^32", (unsigned long long)best_rec);
+    }
+}
+
+RecInput rec_input(const rb_batch* b) {
+    RecInput in{};
+    const uint64_t* c = b->cols64.as<uint64_t>();
+    const size_t n = b->n_rec;
+    in.cigar_off = b->cigar_off.as<uint64_t>();
+    in.q_len = c + 0 * n; in.q_st = c + 1 * n; in.q_en = c + 2 * n; in.t_len = c + 3 * n;
+    in.t_st = c + 4 * n; in.t_en = c + 5 * n; in.mapq = c + 6 * n;
+    in.strand = b->strand.as<uint8_t>();
+    in.q_id = b->ids32.as<uint32_t>(); in.t_id = b->ids32.as<uint32_t>() + n;
+    in.names_off = b->names_off.as<uint64_t>(); in.names = b->names.as<uint8_t>();
+    in.n_rec = b->n_rec;
+    return in;
+}
+WinView win_view(const rb_batch* b) {
+    WinView w{};
+    if (b->n_win == 0) return w;
+    w.st = b->w_st.as<uint64_t>(); w.en = b->w_en.as<uint64_t>(); w.en_pm = w.en;
+    w.ids_off = b->w_ids_off.as<uint64_t>(); w.ids = b->w_ids.as<uint8_t>();
+    w.bed_row = b->w_bed_row.as<uint32_t>();
+    w.cont_lo = b->cont_lo.as<uint32_t>(); w.cont_hi = b->cont_hi.as<uint32_t>();
+    w.pair_win = nullptr;
+    w.general = b->general ? 1u : 0u;
+    return w;
+}
+StatsDev stats_view(const rb_batch* b, uint64_t n) {
+    StatsDev s{};
+    uint32_t* p = b->out_stats.as<uint32_t>();
+    s.equal = p; s.diff = p + n; s.ins = p + 2 * n; s.del = p + 3 * n; s.ins_ev = p + 4 * n; s.del_ev = p + 5 * n;
+    s.matches = p + 6 * n;
+    s.id_m = reinterpret_cast<float*>(p + 7 * n); s.id_e = reinterpret_cast<float*>(p + 8 * n);
+    s.id_a = reinterpret_cast<float*>(p + 9 * n);
+    return s;
+}
+NumDev num_view(const rb_batch* b, uint64_t n) {
+    NumDev d{};
+    uint64_t* p = b->out_num.as<uint64_t>();
+    d.q_st = p; d.q_en = p + n; d.t_st = p + 2 * n; d.t_en = p + 3 * n; d.nmatch = p + 4 * n; d.aln_len = p + 5 * n;
+    d.rec_idx = reinterpret_cast<uint32_t*>(p + 6 * n);
+    d.win_idx = d.rec_idx + n;
+    return d;
+}
+
+// tokenise + record offsets + sampled scan (shared by liftover and stats)
+int run_front(rb_ctx* ctx, rb_batch* b) {
+    cudaStream_t s = ctx->stream;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    CU(cudaMemsetAsync(sc, 0, 4 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(sc + SC_ERR_TOK, 0xFF, 4 * sizeof(uint32_t), s));
+    CU(cudaMemsetAsync(b->tile_state.p, 0, b->n_tiles * 8, s));
+    CU(cudaMemsetAsync(b->heads.p, 0, (b->ops_bound / SAMPLE + 2) * 4, s));
+    CU(cudaMemsetAsync(b->blk_state.p, 0, (b->ops_bound / SMP_OPS + 2) * 4, s));
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    const uint8_t* text = b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD;
+    {
+        KScope k(ctx, "k_tokenise");
+        launch_tokenise(text, b->n_tiles, b->ops.as<uint32_t>(), b->tile_state.as<unsigned long long>(), sc + SC_TICKET_TOK, err,
+                        sc + SC_MISC, s);
+    }
+    {
+        KScope k(ctx, "k_rec_ops");
+        launch_rec_ops(text, b->cigar_off.as<uint64_t>(), b->n_rec, b->tile_state.as<unsigned long long>(), b->op_off.as<uint64_t>(),
+                       b->heads.as<uint32_t>(), err, s);
+    }
+    {
+        KScope k(ctx, "k_samples");
+        launch_samples(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + b->n_rec, b->ops_bound, b->heads.as<uint32_t>(),
+                       b->samples.as<Ctr>(), b->blk_state.as<uint32_t>(), b->blk_agg.as<ScanPayload>(), b->blk_pre.as<ScanPayload>(),
+                       sc + SC_TICKET_SMP, s);
+    }
+    CU(cudaGetLastError());
+    return RB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* rb_version(void) { return "rbcuda 0.1 (sm_100a)"; }
+
+rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
+    auto set = [&](int s) { if (status) *status = s; };
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        set(RB_ERR_NO_DEVICE);
+        return nullptr;
+    }
+    const int dev = (device_ids && n_devices > 0) ? device_ids[0] : 0;
+    cudaDeviceProp prop{};
+    if (dev < 0 || dev >= count || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        (void)cudaGetLastError();
+        set(RB_ERR_NO_DEVICE);  // kernels are compiled for sm_100a only; there is no fallback
+        return nullptr;
+    }
+    rb_ctx* ctx = new rb_ctx();
+    ctx->device = dev;
+    cudaSetDevice(dev);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete ctx;
+        set(RB_ERR_CUDA);
+        return nullptr;
+    }
+    set(RB_OK);
+    return ctx;
+}
+
+void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
+    if (!b) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    DevBuf* all[] = {&b->text_raw, &b->cigar_off, &b->cols64, &b->strand, &b->ids32, &b->names, &b->names_off, &b->rec_order,
+                     &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->cont_lo, &b->cont_hi, &b->ops,
+                     &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
+                     &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
+                     &b->ln_agg, &b->ln_pre, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+    for (DevBuf* d : all) d->release();
+    delete b;
+}
+
+void rb_ctx_destroy(rb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) rb_batch_free(ctx, ctx->scratch);
+    for (PinnedBlock* b : ctx->pinned) { cudaFreeHost(b->p); delete b; }
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    ctx->scalars.release();
+    if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rb_last_error(const rb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no usable sm_100 device?)"; }
+
+int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return RB_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        ctx->own_stream = true;
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamCreate");
+    }
+    return RB_OK;
+}
+
+int rb_ctx_set_profiling(rb_ctx* ctx, int on) {
+    if (!ctx) return RB_ERR_BAD_ARG;
+    ctx->profiling = on != 0;
+    return RB_OK;
+}
+
+int rb_ctx_kernel_times(rb_ctx* ctx, rb_kernel_time* out, int cap, int reset) {
+    if (!ctx) return 0;
+    int n = 0;
+    for (auto& t : ctx->times) {
+        if (n < cap && out) out[n] = t;
+        n++;
+    }
+    if (reset) ctx->times.clear();
+    return n;
+}
+
+int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, uint32_t* perm_out) {
+    if (n_win && (!t_id || !st || !perm_out)) return RB_ERR_BAD_ARG;
+    for (uint32_t i = 0; i < n_win; i++) perm_out[i] = i;
+    std::stable_sort(perm_out, perm_out + n_win, [&](uint32_t a, uint32_t b) {
+        if (t_id[a] != t_id[b]) return t_id[a] < t_id[b];
+        return st[a] < st[b];
+    });
+    return RB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    cudaStream_t s = ctx->stream;
+    if (!R || (R->n_rec && (!R->cigar_off || !R->q_len || !R->q_st || !R->q_en || !R->t_len || !R->t_st || !R->t_en || !R->mapq ||
+                            !R->strand || !R->q_id || !R->t_id || !R->names_off)) ||
+        (R->cigar_nbytes && !R->cigar))
+        return fail(ctx, RB_ERR_BAD_ARG, "rb_records: null column");
+    const uint32_t n = R->n_rec;
+    b->n_rec = n; b->n_names = R->n_names; b->n_bytes = R->cigar_nbytes;
+    b->n_win = W ? W->n_win : 0;
+    b->have_lift = b->have_stats = false;
+    b->h_cigar_off.assign(R->cigar_off, R->cigar_off + (n ? n + 1 : 0));
+    if (n == 0) b->h_cigar_off.assign(1, 0);
+    if (b->h_cigar_off[0] != 0 || b->h_cigar_off[n] != R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
+    for (uint32_t i = 0; i < n; i++) {
+        if (b->h_cigar_off[i] > b->h_cigar_off[i + 1]) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone at record %u", i);
+        if (R->q_id[i] >= R->n_names || R->t_id[i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", i);
+    }
+    b->n_tiles = b->n_bytes / TOK_TILE + 1;
+    b->ops_bound = b->n_bytes / 2 + 1;
+    const size_t padded = b->n_tiles * (size_t)TOK_TILE + 32;
+
+    CU(b->text_raw.ensure(TEXT_FRONT_PAD + padded));
+    CU(b->cigar_off.ensure((size_t)(n + 1) * 8));
+    CU(b->cols64.ensure((size_t)n * 7 * 8 + 8));
+    CU(b->strand.ensure(n + 8));
+    CU(b->ids32.ensure((size_t)n * 2 * 4 + 8));
+    CU(b->names_off.ensure((size_t)(R->n_names + 1) * 8));
+    const uint64_t names_bytes = R->n_names ? R->names_off[R->n_names] : 0;
+    CU(b->names.ensure(names_bytes + 8));
+    CU(b->rec_order.ensure((size_t)n * 4 + 8));
+    CU(b->rec_rank.ensure((size_t)n * 4 + 8));
+    CU(b->ops.ensure(b->ops_bound * 4 + 64));
+    CU(b->tile_state.ensure(b->n_tiles * 8));
+    CU(b->heads.ensure((b->ops_bound / SAMPLE + 2) * 4));
+    CU(b->samples.ensure((b->ops_bound / SAMPLE + 2) * sizeof(Ctr)));
+    const size_t smp_blocks = b->ops_bound / SMP_OPS + 2;
+    CU(b->blk_state.ensure(smp_blocks * 4));
+    CU(b->blk_agg.ensure(smp_blocks * sizeof(ScanPayload)));
+    CU(b->blk_pre.ensure(smp_blocks * sizeof(ScanPayload)));
+    CU(b->op_off.ensure((size_t)(n + 1) * 8));
+    CU(b->recs.ensure((size_t)n * sizeof(RecInfo) + 8));
+    CU(b->pair_cnt.ensure((size_t)n * 4 + 8));
+    CU(b->pair_off.ensure((size_t)(n + 1) * 8));
+
+    uint8_t* raw = b->text_raw.as<uint8_t>();
+    CU(cudaMemsetAsync(raw, 0xFF, TEXT_FRONT_PAD, s));
+    if (b->n_bytes) CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD, R->cigar, b->n_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(raw + TEXT_FRONT_PAD + b->n_bytes, '0', padded - b->n_bytes, s));
+    CU(cudaMemcpyAsync(b->cigar_off.p, b->h_cigar_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+    const uint64_t* cols[7] = {R->q_len, R->q_st, R->q_en, R->t_len, R->t_st, R->t_en, R->mapq};
+    for (int k = 0; k < 7 && n; k++)
+        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k], (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    if (n) {
+        CU(cudaMemcpyAsync(b->strand.p, R->strand, n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), R->q_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, R->t_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (R->n_names) {
+        CU(cudaMemcpyAsync(b->names_off.p, R->names_off, (size_t)(R->n_names + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (names_bytes) CU(cudaMemcpyAsync(b->names.p, R->names, names_bytes, cudaMemcpyHostToDevice, s));
+    }
+
+    // emission order (liftover.rs:151-164): contigs by first appearance of t_name, records in file order inside
+    std::vector<uint32_t> order(n), rank(n);
+    {
+        std::vector<int64_t> first(R->n_names, -1);
+        std::vector<uint32_t> cnt;
+        std::vector<uint32_t> grp(n);
+        for (uint32_t i = 0; i < n; i++) {
+            int64_t& f = first[R->t_id[i]];
+            if (f < 0) { f = (int64_t)cnt.size(); cnt.push_back(0); }
+            grp[i] = (uint32_t)f;
+            cnt[grp[i]]++;
+        }
+        std::vector<uint32_t> start(cnt.size() + 1, 0);
+        for (size_t g = 0; g < cnt.size(); g++) start[g + 1] = start[g] + cnt[g];
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t k = start[grp[i]]++;
+            order[k] = i;
+            rank[i] = k;
+        }
+    }
+    if (n) {
+        CU(cudaMemcpyAsync(b->rec_order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->rec_rank.p, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    }
+
+    // windows
+    if (W && W->n_win) {
+        const uint32_t nw = W->n_win;
+        if (!W->t_id || !W->st || !W->en || !W->bed_row || !W->ids_off) return fail(ctx, RB_ERR_BAD_ARG, "rb_windows: null column");
+        bool fast = true;
+        for (uint32_t i = 0; i < nw; i++) {
+            if (W->t_id[i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "window %u: t_id out of range", i);
+            if (i) {
+                if (W->t_id[i] < W->t_id[i - 1] || (W->t_id[i] == W->t_id[i - 1] && W->st[i] < W->st[i - 1]))
+                    return fail(ctx, RB_ERR_BAD_ARG, "windows must be sorted by (t_id, st) (see rb_sort_windows)");
+                if (W->t_id[i] == W->t_id[i - 1] && (W->en[i] < W->en[i - 1] || W->bed_row[i] < W->bed_row[i - 1])) fast = false;
+            }
+        }
+        b->general = !fast;
+        std::vector<uint32_t> perm;
+        std::vector<uint64_t> st_g, en_g, off_g;
+        std::vector<uint32_t> row_g, tid_g;
+        std::vector<uint8_t> ids_g;
+        const uint64_t *h_st = W->st, *h_en = W->en, *h_off = W->ids_off;
+        const uint32_t *h_row = W->bed_row, *h_tid = W->t_id;
+        const uint8_t* h_ids = W->ids;
+        if (b->general) {  // BED file order inside each contig (Q5): stable sort by (t_id, bed_row)
+            perm.resize(nw);
+            for (uint32_t i = 0; i < nw; i++) perm[i] = i;
+            std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t c) {
+                if (W->t_id[a] != W->t_id[c]) return W->t_id[a] < W->t_id[c];
+                return W->bed_row[a] < W->bed_row[c];
+            });
+            st_g.resize(nw); en_g.resize(nw); off_g.resize(nw + 1); row_g.resize(nw); tid_g.resize(nw);
+            off_g[0] = 0;
+            for (uint32_t i = 0; i < nw; i++) {
+                const uint32_t j = perm[i];
+                st_g[i] = W->st[j]; en_g[i] = W->en[j]; row_g[i] = W->bed_row[j]; tid_g[i] = W->t_id[j];
+                off_g[i + 1] = off_g[i] + (W->ids_off[j + 1] - W->ids_off[j]);
+            }
+            ids_g.resize(off_g[nw] + 1);
+            for (uint32_t i = 0; i < nw; i++) {
+                const uint32_t j = perm[i];
+                memcpy(ids_g.data() + off_g[i], W->ids + W->ids_off[j], W->ids_off[j + 1] - W->ids_off[j]);
+            }
+            h_st = st_g.data(); h_en = en_g.data(); h_off = off_g.data(); h_row = row_g.data(); h_tid = tid_g.data();
+            h_ids = ids_g.data();
+        }
+        std::vector<uint32_t> clo(R->n_names + 1, 0), chi(R->n_names + 1, 0);
+        for (uint32_t i = 0; i < nw; i++) {
+            const uint32_t t = h_tid[i];
+            if (i == 0 || h_tid[i - 1] != t) clo[t] = i;
+            chi[t] = i + 1;
+        }
+        const uint64_t ids_bytes = h_off[nw];
+        CU(b->w_st.ensure((size_t)nw * 8)); CU(b->w_en.ensure((size_t)nw * 8)); CU(b->w_ids_off.ensure((size_t)(nw + 1) * 8));
+        CU(b->w_ids.ensure(ids_bytes + 8)); CU(b->w_bed_row.ensure((size_t)nw * 4));
+        CU(b->cont_lo.ensure((size_t)(R->n_names + 1) * 4)); CU(b->cont_hi.ensure((size_t)(R->n_names + 1) * 4));
+        CU(cudaMemcpyAsync(b->w_st.p, h_st, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->w_en.p, h_en, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->w_ids_off.p, h_off, (size_t)(nw + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (ids_bytes) CU(cudaMemcpyAsync(b->w_ids.p, h_ids, ids_bytes, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->w_bed_row.p, h_row, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->cont_lo.p, clo.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->cont_hi.p, chi.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));  // the staging vectors above die at scope exit
+    } else {
+        b->general = false;
+        CU(cudaStreamSynchronize(s));
+    }
+    b->sum = rb_summary{};
+    b->sum.cigar_bytes = b->n_bytes;
+    return RB_OK;
+}
+
+rb_batch* rb_batch_upload(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int* status) {
+    auto set = [&](int s) { if (status) *status = s; };
+    if (!ctx) { set(RB_ERR_NO_DEVICE); return nullptr; }
+    cudaSetDevice(ctx->device);
+    rb_batch* b = new rb_batch();
+    const int rc = upload_into(ctx, b, recs, wins);
+    set(rc);
+    if (rc != RB_OK) { rb_batch_free(ctx, b); return nullptr; }
+    return b;
+}
+
+int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
+    if (!ctx || !b) return RB_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    int rc = run_front(ctx, b);
+    if (rc != RB_OK) return rc;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    CU(b->out_stats.ensure((size_t)b->n_rec * 40 + 64));
+    {
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(0, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), WinView{},
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), stats_view(b, b->n_rec), err, s);
+    }
+    uint64_t* hs = reinterpret_cast<uint64_t*>(ctx->h_scalars);
+    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 2, b->op_off.as<uint64_t>() + b->n_rec, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 3, sc + SC_MISC, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if ((uint32_t)hs[3] & 1u) {  // clips present: validate their placement like rust-htslib does
+        launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), b->n_rec, err, s);
+        CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    flush_times(ctx);
+    CU(cudaGetLastError());
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) return rc;
+    b->sum.n_ops = hs[2];
+    b->have_stats = true; b->stats_n = b->n_rec;
+    if (summary) *summary = b->sum;
+    return RB_OK;
+}
+
+int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, int with_stats, rb_summary* summary) {
+    if (!ctx || !b) return RB_ERR_BAD_ARG;
+    if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    b->have_lift = false;
+    int rc = run_front(ctx, b);
+    if (rc != RB_OK) return rc;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    WinView win = win_view(b);
+    const uint32_t n = b->n_rec;
+    {
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), win,
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+    }
+    if (b->general && b->n_win) {
+        KScope k(ctx, "k_pair_count_bf");
+        launch_pair_count_bf(b->recs.as<RecInfo>(), n, win, b->pair_cnt.as<uint32_t>(), s);
+    }
+    {
+        KScope k(ctx, "k_pair_scan");
+        launch_pair_scan(b->pair_cnt.as<uint32_t>(), b->rec_order.as<uint32_t>(), n, b->pair_off.as<uint64_t>(), s);
+    }
+    uint64_t* hs = reinterpret_cast<uint64_t*>(ctx->h_scalars);
+    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 2, b->op_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 3, sc + SC_MISC, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 4, b->pair_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if ((uint32_t)hs[3] & 1u) {
+        launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, err, s);
+        CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) { flush_times(ctx); return rc; }
+    const uint64_t n_ops = hs[2], P = hs[4];
+
+    CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
+    CU(b->line_len.ensure(P * 4 + 64));
+    CU(b->line_off.ensure((P + 1) * 8 + 64));
+    CU(b->out_idx.ensure((P + 1) * 8 + 64));
+    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    CU(b->ln_state.ensure(ln_blocks * 4));
+    CU(b->ln_agg.ensure(ln_blocks * 16));
+    CU(b->ln_pre.ensure(ln_blocks * 16));
+    CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
+    if (b->general && P) {
+        CU(b->pair_win.ensure(P * 4 + 64));
+        KScope k(ctx, "k_pair_fill_bf");
+        launch_pair_fill_bf(b->recs.as<RecInfo>(), b->rec_rank.as<uint32_t>(), n, win, b->pair_off.as<uint64_t>(),
+                            b->pair_win.as<uint32_t>(), s);
+        win.pair_win = b->pair_win.as<uint32_t>();
+    }
+    {
+        KScope k(ctx, "k_lift");
+        launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                    b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->pair_res.as<PairRes>(),
+                    b->line_len.as<uint32_t>(), err, s);
+    }
+    {
+        KScope k(ctx, "k_scan_lines");
+        launch_scan_lines(b->line_len.as<uint32_t>(), P, b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
+                          b->ln_state.as<uint32_t>(), b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
+    }
+    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 5, b->line_off.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hs + 6, b->out_idx.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) { flush_times(ctx); return rc; }
+    const uint64_t out_bytes = hs[5], n_out = hs[6];
+
+    CU(b->out_text.ensure(out_bytes + 64));
+    CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
+    CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
+    b->with_stats = with_stats != 0;
+    if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
+    {
+        KScope k(ctx, "k_serialise");
+        launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                         win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(), b->pair_res.as<PairRes>(),
+                         b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), b->out_text.as<uint8_t>(),
+                         b->out_line_off.as<uint64_t>(), num_view(b, n_out), with_stats ? stats_view(b, n_out) : StatsDev{}, s);
+    }
+    if (P == 0) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
+    CU(cudaGetLastError());
+    if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
+    b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
+    b->have_lift = true; b->stats_n = n_out;
+    if (summary) *summary = b->sum;
+    return RB_OK;
+}
+
+static int download_stats(rb_ctx* ctx, rb_batch* b, uint64_t n, rb_stats_out* st) {
+    memset(st, 0, sizeof *st);
+    PinnedBlock* blk = pinned_get(ctx, (size_t)n * 40 + 64);
+    if (!blk) return fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)(n * 40));
+    if (n) CU(cudaMemcpyAsync(blk->p, b->out_stats.p, (size_t)n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+    uint32_t* p = reinterpret_cast<uint32_t*>(blk->p);
+    st->n = n;
+    st->equal = p; st->diff = p + n; st->ins = p + 2 * n; st->del = p + 3 * n; st->ins_events = p + 4 * n;
+    st->del_events = p + 5 * n; st->matches = p + 6 * n;
+    st->id_by_matches = reinterpret_cast<float*>(p + 7 * n); st->id_by_events = reinterpret_cast<float*>(p + 8 * n);
+    st->id_by_all = reinterpret_cast<float*>(p + 9 * n);
+    st->_owner = blk;
+    return RB_OK;
+}
+
+int rb_batch_download_stats(rb_ctx* ctx, rb_batch* b, rb_stats_out* st) {
+    if (!ctx || !b || !st) return RB_ERR_BAD_ARG;
+    if (!b->have_stats) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_stats has not run on this batch");
+    cudaSetDevice(ctx->device);
+    const int rc = download_stats(ctx, b, b->n_rec, st);
+    if (rc != RB_OK) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out* out, rb_stats_out* st) {
+    if (!ctx || !b || !out) return RB_ERR_BAD_ARG;
+    if (!b->have_lift) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover has not run on this batch");
+    if (st && !b->with_stats) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover ran without stats");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    memset(out, 0, sizeof *out);
+    const uint64_t n = b->sum.n_out, nb = b->sum.out_bytes;
+    size_t need = 64;
+    const size_t o_text = need; if (want & RB_WANT_TEXT) need += align_up(nb + 1, 64);
+    const size_t o_loff = need; if (want & RB_WANT_TEXT) need += align_up((n + 1) * 8, 64);
+    const size_t o_num = need; if (want & RB_WANT_NUMERIC) need += align_up(n * 56, 64);
+    PinnedBlock* blk = pinned_get(ctx, need);
+    if (!blk) return fail(ctx, RB_ERR_OOM, "pinned allocation of %zu bytes failed", need);
+    uint8_t* base = reinterpret_cast<uint8_t*>(blk->p);
+    out->n_out = n; out->paf_nbytes = nb; out->n_pairs = b->sum.n_pairs; out->_owner = blk;
+    if (want & RB_WANT_TEXT) {
+        out->paf_text = base + o_text;
+        out->line_off = reinterpret_cast<uint64_t*>(base + o_loff);
+        if (nb) CU(cudaMemcpyAsync(out->paf_text, b->out_text.p, nb, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(out->line_off, b->out_line_off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (want & RB_WANT_NUMERIC) {
+        uint64_t* p = reinterpret_cast<uint64_t*>(base + o_num);
+        if (n) CU(cudaMemcpyAsync(p, b->out_num.p, n * 56, cudaMemcpyDeviceToHost, s));
+        out->q_st = p; out->q_en = p + n; out->t_st = p + 2 * n; out->t_en = p + 3 * n; out->nmatch = p + 4 * n;
+        out->aln_len = p + 5 * n;
+        out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * n);
+        out->win_idx = out->rec_idx + n;
+    }
+    if (st) {
+        const int rc = download_stats(ctx, b, n, st);
+        if (rc != RB_OK) return rc;
+    }
+    CU(cudaStreamSynchronize(s));
+    if (out->paf_text) out->paf_text[nb] = 0;
+    return RB_OK;
+}
+
+void rb_free_lift_out(rb_ctx*, rb_lift_out* out) {
+    if (!out) return;
+    if (out->_owner) reinterpret_cast<PinnedBlock*>(out->_owner)->in_use = false;
+    memset(out, 0, sizeof *out);
+}
+void rb_free_stats_out(rb_ctx*, rb_stats_out* st) {
+    if (!st) return;
+    if (st->_owner) reinterpret_cast<PinnedBlock*>(st->_owner)->in_use = false;
+    memset(st, 0, sizeof *st);
+}
+
+int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
+                rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out) return fail(ctx, RB_ERR_BAD_ARG, "out is null");
+    cudaSetDevice(ctx->device);
+    if (!ctx->scratch) ctx->scratch = new rb_batch();
+    int rc = upload_into(ctx, ctx->scratch, recs, wins);
+    if (rc != RB_OK) return rc;
+    rc = rb_batch_liftover(ctx, ctx->scratch, policy, stats != nullptr, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_lift(ctx, ctx->scratch, want, out, stats);
+}
+
+int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!stats) return fail(ctx, RB_ERR_BAD_ARG, "stats is null");
+    cudaSetDevice(ctx->device);
+    if (!ctx->scratch) ctx->scratch = new rb_batch();
+    int rc = upload_into(ctx, ctx->scratch, recs, nullptr);
+    if (rc != RB_OK) return rc;
+    rc = rb_batch_stats(ctx, ctx->scratch, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_stats(ctx, ctx->scratch, stats);
+}
+
+}  // extern "C"

@@ -1,0 +1,25 @@
+"""liftover::trim_paf_by_rgns (src/liftover.rs:134-167) + Display (src/paf.rs:923-943) on the GPU."""
+from . import bed as _bed
+from .capi import POLICY_RIGHTMOST, WANT_NUMERIC, WANT_TEXT, RbError, REF_PANIC_CODES
+from .paf import Paf, ReferencePanic
+
+
+def trim_paf_by_rgns(ctx, rgns, paf: Paf, invert_query=False, policy=POLICY_RIGHTMOST, stats=True, want=WANT_TEXT | WANT_NUMERIC):
+    """Returns the dict of rb_lift_out arrays; res["paf_text"] is what `rb liftover` prints."""
+    if invert_query:
+        raise NotImplementedError("--qbed is a SURVEY §8(f) 'next' row")
+    recs = paf.pack()
+    wins = _bed.pack_windows(rgns, recs.name_index)
+    try:
+        return ctx.liftover(recs, wins, policy=policy, want=want, stats=stats)
+    except RbError as e:
+        if e.code in REF_PANIC_CODES:
+            raise ReferencePanic(str(e)) from e
+        raise
+
+
+def run_liftover(ctx, paf_text: bytes, bed_text: bytes, policy=POLICY_RIGHTMOST) -> bytes:
+    """`rb liftover --bed BED PAF` (main.rs:186-214): stdout bytes."""
+    rgns = _bed.parse_bed_text(bed_text)
+    paf = Paf.from_text(paf_text)
+    return trim_paf_by_rgns(ctx, rgns, paf, policy=policy, stats=False, want=WANT_TEXT)["paf_text"]

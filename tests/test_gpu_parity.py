@@ -1,0 +1,211 @@
+"""Parity tests proper: the CUDA path through the C ABI (rbcuda.h) against the CPU oracle,
+byte-for-byte.  Every test here needs a real B200 (pytest -m gpu)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import gen
+import orc
+from rustybam_b200 import bamstats, bed, capi, liftover
+from rustybam_b200.paf import Paf, ReferencePanic
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def lift_and_stats(ctx, paf_text, bed_text, policy=0):
+    """(`rb liftover` bytes, `rb stats --paf` bytes of that output) from the GPU path."""
+    paf = Paf.from_text(paf_text)
+    rgns = bed.parse_bed_text(bed_text)
+    res = liftover.trim_paf_by_rgns(ctx, rgns, paf, policy=policy, stats=True)
+    lifted = res["paf_text"]
+    # the fused per-row stats, printed with the lifted rows' own columns (what `| rb stats --paf` prints)
+    out_paf = Paf.from_text(lifted)
+    assert len(out_paf) == res["n_out"]
+    stats_txt = (bamstats.print_cigar_stats_header() + bamstats.stats_rows(out_paf, res["stats"])).encode()
+    return res, lifted, stats_txt
+
+
+def check_against_oracle(ctx, paf_text, bed_text, policy=0):
+    want = orc.run_liftover(paf_text, bed_text, policy=policy, threads=4)
+    res, lifted, stats_txt = lift_and_stats(ctx, paf_text, bed_text, policy)
+    assert lifted == want
+    assert stats_txt == orc.run_stats(want)
+    # numeric mirror agrees with the text
+    rows = [ln.split(b"\t") for ln in lifted.splitlines()]
+    assert [int(r[2]) for r in rows] == res["q_st"].tolist()
+    assert [int(r[3]) for r in rows] == res["q_en"].tolist()
+    assert [int(r[7]) for r in rows] == res["t_st"].tolist()
+    assert [int(r[8]) for r in rows] == res["t_en"].tolist()
+    assert [int(r[9]) for r in rows] == res["nmatch"].tolist()
+    assert [int(r[10]) for r in rows] == res["aln_len"].tolist()
+    off = res["line_off"]
+    assert off[0] == 0 and off[-1] == len(lifted)
+    assert all(lifted[int(o) - 1:int(o)] == b"\n" for o in off[1:])
+    return res
+
+
+# ---------------------------------------------------------------- config 1: bundled fixture
+def test_c1_bundled_liftover_and_stats(ctx):
+    res = check_against_oracle(ctx, orc.golden_paf(), orc.golden_bed())
+    assert res["n_out"] == 12 and res["paf_nbytes"] == 508497
+    assert hashlib.md5(res["paf_text"]).hexdigest() == "f009e11b3bc56a4967cf594f750123a9"
+
+
+def test_c1_stats_of_input_paf(ctx):
+    got = bamstats.run_stats(ctx, orc.golden_paf())
+    assert got == orc.run_stats(orc.golden_paf())
+
+
+@pytest.mark.parametrize("width", [100_000, 10_000])
+def test_c1_tiling_windows(ctx, width):
+    paf_text = orc.golden_paf()
+    contigs = {}
+    for ln in paf_text.splitlines():
+        f = ln.split(b"\t")
+        contigs[f[5].decode()] = int(f[6])
+    bed_text = gen.tiling_bed(contigs, width)
+    res = check_against_oracle(ctx, paf_text, bed_text)
+    assert res["n_out"] == {100_000: 1657, 10_000: 14385}[width]
+
+
+# ---------------------------------------------------------------- the reference's own vectors, through the C ABI
+F_PAF = b"Q\t10\t2\t10\t+\tT\t40\t12\t20\t3\t9\t60\tcg:Z:4M1I1=1D2=\n"
+R_PAF = b"Q\t10\t2\t10\t-\tT\t40\t12\t20\t3\t9\t60\tcg:Z:4M1I1=1D2=\n"
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_aln_pair_liftover_vectors(ctx, policy):
+    # liftover.rs:233-325: (q_st, q_en) for six regions, + and - strand
+    regions = [(14, 15), (14, 18), (12, 20), (12, 30), (5, 20), (5, 30)]
+    sts = [4, 7, 4, 4, 2, 2, 2, 2, 2, 2, 2, 2]
+    ens = [5, 8, 8, 8, 10, 10, 10, 10, 10, 10, 10, 10]
+    bed_text = "".join(f"T\t{a}\t{b}\n" for a, b in regions).encode()
+    idx = 0
+    got = {}
+    for name, text in (("f", F_PAF), ("r", R_PAF)):
+        res = liftover.trim_paf_by_rgns(ctx, bed.parse_bed_text(bed_text), Paf.from_text(text), policy=policy)
+        assert res["n_out"] == 6
+        got[name] = res
+    for k in range(6):
+        for name in ("f", "r"):
+            assert int(got[name]["q_st"][k]) == sts[idx] and int(got[name]["q_en"][k]) == ens[idx]
+            idx += 1
+
+
+def test_add_cigar_stats_vector(ctx):
+    # bamstats.rs:287-295
+    st = bamstats.stats_from_paf(ctx, Paf.from_text(b"Q\t20\t0\t20\t+\tT\t20\t0\t20\t0\t0\t60\tcg:Z:10=10X\n"))
+    assert st["id_by_all"][0] == np.float32(50.0) and st["equal"][0] == 10 and st["diff"][0] == 10
+
+
+def test_tokeniser_vs_reference_parser_doctest(ctx):
+    # paf.rs:1007-1012 strings; checked through the stats counters + integrity check of the spans
+    for cg, t, q in (("10M4D100I1102=", 10 + 4 + 1102, 10 + 100 + 1102), ("100000M20=5P10X4M", 100034, 100034)):
+        line = f"Q\t{q}\t0\t{q}\t+\tT\t{t}\t0\t{t}\t0\t0\t60\tcg:Z:{cg}\n".encode()
+        assert bamstats.run_stats(ctx, line) == orc.run_stats(line)
+
+
+# ---------------------------------------------------------------- randomised parity, edge cases included
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("policy", [0, 1])
+def test_random_eqx_tiling(ctx, seed, policy):
+    paf_text, contigs = gen.random_paf(seed, n_contigs=4, recs_per_contig=8)
+    check_against_oracle(ctx, paf_text, gen.tiling_bed(contigs, 7 + seed), policy)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_unsorted_nested_bed_general_path(ctx, seed):
+    # BED file order is never sorted by the reference (Q5); nested + duplicate rows
+    paf_text, contigs = gen.random_paf(100 + seed, n_contigs=3, recs_per_contig=6)
+    check_against_oracle(ctx, paf_text, gen.random_bed(seed, contigs, 60, with_ids=(seed % 2 == 0)), seed % 2)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_sorted_overlapping_bed(ctx, seed):
+    paf_text, contigs = gen.random_paf(200 + seed, n_contigs=3, recs_per_contig=6)
+    check_against_oracle(ctx, paf_text, gen.random_bed(seed, contigs, 80, sort=True))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_all_ops_noncanonical(ctx, seed):
+    # M/N/P ops, zero-length ops, adjacent same-class ops (Q15 re-collapse), clips
+    paf_text, contigs = gen.random_paf(300 + seed, style="all", canonical=False, allow_zero=True, clips=(seed % 2 == 0))
+    check_against_oracle(ctx, paf_text, gen.tiling_bed(contigs, 11), seed % 2)
+    assert bamstats.run_stats(ctx, paf_text) == orc.run_stats(paf_text)
+
+
+def test_many_tiny_records_in_one_tile(ctx):
+    paf_text, contigs = gen.random_paf(7, n_contigs=2, recs_per_contig=400, max_ops=3, lead_trail=False)
+    check_against_oracle(ctx, paf_text, gen.tiling_bed(contigs, 50))
+    assert bamstats.run_stats(ctx, paf_text) == orc.run_stats(paf_text)
+
+
+def test_long_numbers_and_leading_zeros(ctx):
+    cg = "0000000000000000000012=3X000004=1I0000000000000000000000000000000000007=268435455D5="
+    t = 12 + 3 + 4 + 7 + 268435455 + 5
+    q = 12 + 3 + 4 + 1 + 7 + 5
+    line = f"Q\t{q}\t0\t{q}\t+\tT\t{t + 10}\t5\t{t + 5}\t0\t0\t60\tcg:Z:{cg}\n".encode()
+    assert bamstats.run_stats(ctx, line) == orc.run_stats(line)
+    check_against_oracle(ctx, line, b"T\t0\t20\nT\t10\t268435480\nT\t268435470\t268435999\n")
+
+
+def test_empty_inputs(ctx):
+    res = liftover.trim_paf_by_rgns(ctx, [], Paf.from_text(F_PAF))
+    assert res["n_out"] == 0 and res["paf_text"] == b""
+    res = liftover.trim_paf_by_rgns(ctx, bed.parse_bed_text(b"T\t0\t5\n"), Paf.from_text(F_PAF))  # no overlap
+    assert res["n_out"] == 0
+    res = liftover.trim_paf_by_rgns(ctx, bed.parse_bed_text(b"T\t0\t5\n"), Paf.from_text(b""))
+    assert res["n_out"] == 0
+    assert bamstats.run_stats(ctx, b"") == orc.run_stats(b"")
+
+
+def test_record_without_cigar_and_zero_spans(ctx):
+    line = b"Q\t10\t3\t3\t+\tT\t40\t12\t12\t0\t0\t60\ttp:A:P\n"
+    assert bamstats.run_stats(ctx, line) == orc.run_stats(line)  # NaN identities
+
+
+# ---------------------------------------------------------------- where the reference panics, the call fails loudly
+@pytest.mark.parametrize("cg,t,q", [("3D5=", 8, 5), ("5Q", 5, 5), ("5=3", 5, 5), ("=5", 5, 5), ("5==", 5, 5), ("4294967296=", 5, 5),
+                                    ("5=3H2=", 7, 7), ("2I3D", 3, 2)])
+def test_reference_panics_liftover(ctx, cg, t, q):
+    line = f"Q\t{q + 5}\t0\t{q}\t+\tT\t{t + 5}\t0\t{t}\t0\t0\t60\tcg:Z:{cg}\n".encode()
+    with pytest.raises(orc.ReferencePanic):
+        orc.run_liftover(line, b"T\t0\t100\n")
+    with pytest.raises(ReferencePanic):
+        liftover.run_liftover(ctx, line, b"T\t0\t100\n")
+
+
+def test_integrity_panic(ctx):
+    line = b"Q\t20\t0\t11\t+\tT\t20\t0\t10\t0\t0\t60\tcg:Z:10=\n"
+    with pytest.raises(orc.ReferencePanic):
+        orc.run_stats(line)
+    with pytest.raises(ReferencePanic):
+        bamstats.run_stats(ctx, line)
+
+
+def test_after_an_error_the_context_still_works(ctx):
+    with pytest.raises(ReferencePanic):
+        bamstats.run_stats(ctx, b"Q\t20\t0\t11\t+\tT\t20\t0\t10\t0\t0\t60\tcg:Z:10=\n")
+    assert bamstats.run_stats(ctx, F_PAF) == orc.run_stats(F_PAF)
+
+
+def test_resident_batch_is_repeatable(ctx):
+    paf_text, contigs = gen.random_paf(11, n_contigs=3, recs_per_contig=10)
+    paf = Paf.from_text(paf_text)
+    recs = paf.pack()
+    wins = bed.pack_windows(bed.parse_bed_text(gen.tiling_bed(contigs, 9)), recs.name_index)
+    b = ctx.upload(recs, wins)
+    s1 = ctx.batch_liftover(b)
+    s2 = ctx.batch_liftover(b)
+    assert s1 == s2
+    out = ctx.batch_download_lift(b)
+    assert out["paf_text"] == orc.run_liftover(paf_text, gen.tiling_bed(contigs, 9))
+    ctx.batch_free(b)

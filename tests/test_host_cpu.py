@@ -1,0 +1,98 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/rbcuda.h declares
+(no compute without a GPU), the host packing mirrors the reference's parser, and the product
+path fails loudly without a device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gen
+import orc
+from rustybam_b200 import bamstats, bed, build, capi
+from rustybam_b200.paf import Paf, ReferencePanic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build.build_cuda()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "rbcuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_device_means_error_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.RbError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.RB_ERR_NO_DEVICE
+
+
+def test_product_does_not_reference_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "rustybam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(d, f), errors="ignore").read()
+                assert "rb_oracle" not in src and "liborc" not in src and "import orc" not in src, f
+
+
+def test_paf_pack_layout():
+    p = Paf.from_text(orc.golden_paf())
+    assert len(p) == 249 and p.skipped == 0
+    r = p.pack()
+    assert r.n_rec == 249 and r.cigar_nbytes == 2049269
+    assert int(r.cigar_off[0]) == 0 and int(r.cigar_off[-1]) == r.cigar_nbytes
+    assert bytes(r.cigar[:8]) == b"2395=14D"
+    assert r.names[int(r.t_id[0])] == b"chr20"
+
+
+def test_paf_parser_mirrors_reference_quirks():
+    with pytest.raises(ReferencePanic):
+        Paf.from_text(b"a\tb\n")  # < 12 columns -> assert (paf.rs:381)
+    with pytest.raises(ReferencePanic):
+        Paf.from_text(b"\n")
+    p = Paf.from_text(b"Q 10 x 10 + T 40 12 20 3 9 60 cg:Z:8=\n")  # non-numeric column -> skipped (paf.rs:73)
+    assert len(p) == 0 and p.skipped == 1
+    p = Paf.from_text(b"Q 10 2 10 + T 40 12 20 3 9 60 cs:Z::8 cg:Z:8= cg:Z:4=\n")  # first cg wins, any whitespace splits
+    assert p.cigars == [b"8="]
+    with pytest.raises(ReferencePanic):
+        Paf.from_text(b"Q 10 2 10 + T 40 12 20 3 9 60 notatag\n")
+
+
+def test_bed_parser_matches_oracle():
+    texts = [orc.golden_bed(), b"chr1\t2\t2000\n", b"chr1\t0\t1000\tid\n", b"#c\nchr1\t5\t9\tA\textra\nchr2\t1\t2\tB\textra\nchr3\t1\t2\n",
+             b"chr1\t5\t9\r\nchr1\tx\t9\nchr1\t10\t12\n"]
+    for t in texts:
+        got = [(r.name.decode(), r.st, r.en, r.id.decode()) for r in bed.parse_bed_text(t)]
+        assert got == orc.parse_bed(t)
+
+
+def test_window_packing_sorts_and_keeps_bed_rows():
+    paf_text, contigs = gen.random_paf(3)
+    recs = Paf.from_text(paf_text).pack()
+    rg = bed.parse_bed_text(gen.random_bed(5, contigs, 40))
+    w = bed.pack_windows(rg, recs.name_index)
+    key = list(zip(w.t_id.tolist(), w.st.tolist()))
+    assert key == sorted(key)
+    assert sorted(w.bed_row.tolist()) == list(range(w.n_win))
+
+
+def test_fmt_f32_matches_oracle():
+    rng = np.random.default_rng(3)
+    eq = rng.integers(0, 2**31, 3000, dtype=np.uint64)
+    tot = eq + rng.integers(0, 2**22, 3000, dtype=np.uint64)
+    vals = (np.float32(100.0) * eq.astype(np.float32)) / np.maximum(tot, 1).astype(np.float32)
+    for v in list(vals) + [np.float32("nan"), np.float32(0), np.float32(100), np.float32(1e-7), np.float32(50)]:
+        assert bamstats.fmt_f32(v) == orc.fmt_f32(float(v)), v
