@@ -174,6 +174,11 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b);
  * perm_out[n_win] receives, for each sorted position, the BED row it came from. */
 int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, uint32_t* perm_out);
 
+/* ---- host helper: page-lock caller-owned buffers (cudaHostRegister) so that the H2D copies of
+ * rb_liftover / rb_batch_upload are asynchronous DMA; for hosts without their own CUDA binding. */
+int rb_host_register(void* ptr, uint64_t nbytes);
+int rb_host_unregister(void* ptr);
+
 const char* rb_version(void);
 
 #ifdef __cplusplus

@@ -23,7 +23,8 @@ WANT_TEXT, WANT_NUMERIC = 1, 2
 EXPORTS = [
     "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_kernel_times",
     "rb_liftover", "rb_stats", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
-    "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version",
+    "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
+    "rb_host_unregister",
 ]
 
 u8p, u32p, u64p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
@@ -99,6 +100,8 @@ def load():
     lib.rb_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb_sort_windows.argtypes = [C.c_uint32, u32p, u64p, u32p]
     lib.rb_version.restype = C.c_char_p
+    lib.rb_host_register.argtypes = [C.c_void_p, C.c_uint64]
+    lib.rb_host_unregister.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

@@ -520,7 +520,14 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end);
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
     if ((uint64_t)full.T != ri.t_en - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
-    if (full.aux & 0x7FFFFFFFu) ri.flags |= RF_SLOW;
+    if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
+    if (ri.op_end > ri.op_first) {  // the sampled count stops at the last chunk boundary: look at the tail ops too
+        const uint64_t base = ((ri.op_end - 1) >> SAMPLE_LOG2) << SAMPLE_LOG2;
+        for (uint64_t k = base > ri.op_first ? base : ri.op_first; k < ri.op_end; k++) {
+            const uint32_t w = ops[k];
+            if (op_len(w) == 0u || (k > ri.op_first && op_code(w) == op_code(ops[k - 1]))) ri.flags |= RF_SLOW;
+        }
+    }
 
     if (mode == 0) {  // rb stats --paf: counters of the record as read (bamstats.rs:91-105)
         ri.tot = full;

@@ -278,6 +278,17 @@ extern "C" {
 
 const char* rb_version(void) { return "rbcuda 0.1 (sm_100a)"; }
 
+int rb_host_register(void* ptr, uint64_t nbytes) {
+    if (!ptr || !nbytes) return RB_ERR_BAD_ARG;
+    if (cudaHostRegister(ptr, nbytes, cudaHostRegisterDefault) != cudaSuccess) { (void)cudaGetLastError(); return RB_ERR_CUDA; }
+    return RB_OK;
+}
+int rb_host_unregister(void* ptr) {
+    if (!ptr) return RB_ERR_BAD_ARG;
+    if (cudaHostUnregister(ptr) != cudaSuccess) { (void)cudaGetLastError(); return RB_ERR_CUDA; }
+    return RB_OK;
+}
+
 rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
     auto set = [&](int s) { if (status) *status = s; };
     int count = 0;

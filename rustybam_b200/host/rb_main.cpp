@@ -1,0 +1,94 @@
+// rb — the host CLI for the two subcommands on the hot path, same flags as the reference
+// (src/cli.rs:16-27,49-60,100-115; drivers src/main.rs:50-58,186-214):
+//     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]
+//     rb [-t N] stats --paf [--qbed] [PAF|-]
+// Text (plain / .gz / .bgz / stdin) is read and split on the host; CIGAR tokenising, liftover,
+// trimming, serialisation and identity counting run on the B200 through include/rbcuda.h.
+// Exit status 101 where the reference panics.  There is no CPU fallback: without an sm_100
+// device the program fails.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "rbhost.hpp"
+
+static int usage() {
+    fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n");
+    return 2;
+}
+
+int main(int argc, char** argv) {
+    std::string cmd, bed, input = "-";
+    bool qbed = false, largest = false, paf_flag = false;
+    int policy = RB_POLICY_RIGHTMOST;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        if ((a == "-t" || a == "--threads") && i + 1 < argc) i++;  // accepted for compatibility; the GPU path has no thread knob
+        else if (a == "-v" || a == "-vv" || a == "-vvv") {}
+        else if ((a == "--bed" || a == "-b") && i + 1 < argc) bed = argv[++i];
+        else if (a == "--qbed" || a == "-q") qbed = true;
+        else if (a == "--largest" || a == "-l") largest = true;
+        else if (a == "--paf" || a == "-p") paf_flag = true;
+        else if (a == "--policy" && i + 1 < argc) policy = strcmp(argv[++i], "early-exit") == 0 ? RB_POLICY_EARLY_EXIT : RB_POLICY_RIGHTMOST;
+        else if (cmd.empty()) cmd = a;
+        else input = a;
+    }
+    if (cmd != "liftover" && !(cmd == "stats" && paf_flag)) return usage();
+    if (cmd == "liftover" && (qbed || largest)) {
+        fprintf(stderr, "rb: --qbed / --largest are not on the GPU path yet (SURVEY 8f 'next')\n");
+        return 2;
+    }
+    int status = 0;
+    rb_ctx* ctx = rb_ctx_create(nullptr, 0, &status);
+    if (!ctx) {
+        fprintf(stderr, "rb: no usable sm_100 CUDA device (status %d); this build has no CPU path\n", status);
+        return 3;
+    }
+    int rc = 0;
+    try {
+        if (cmd == "stats") {
+            fputs(rbh::stats_header(qbed).c_str(), stdout);  // printed before the input is read (main.rs:51)
+            fflush(stdout);
+            rbh::Paf paf = rbh::Paf::from_file(input);
+            if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
+            rb_records recs = paf.view();
+            rb_stats_out st{};
+            rc = rb_stats(ctx, &recs, &st);
+            if (rc == RB_OK) {
+                std::string out;
+                for (size_t i = 0; i < paf.size(); i++) {
+                    rbh::append_stats_row(out, paf, i, st, qbed);
+                    if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+                }
+                fwrite(out.data(), 1, out.size(), stdout);
+                rb_free_stats_out(ctx, &st);
+            }
+        } else {
+            if (bed.empty()) return usage();
+            std::vector<rbh::Region> rgns = rbh::parse_bed(bed);
+            rbh::Paf paf = rbh::Paf::from_file(input);
+            if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
+            rbh::Windows wins = rbh::Windows::pack(rgns, paf);
+            rb_records recs = paf.view();
+            rb_windows w = wins.view();
+            rb_lift_out out{};
+            rc = rb_liftover(ctx, &recs, &w, policy, RB_WANT_TEXT, &out, nullptr);
+            if (rc == RB_OK) {
+                fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                rb_free_lift_out(ctx, &out);
+            }
+        }
+    } catch (const rbh::Panic& e) {
+        fprintf(stderr, "thread 'main' panicked: %s\n", e.what());
+        rb_ctx_destroy(ctx);
+        return 101;
+    }
+    if (rc != RB_OK) {
+        fprintf(stderr, "rb: %s\n", rb_last_error(ctx));
+        const bool ref_panic = rc <= RB_ERR_REF_CIGAR_PARSE && rc >= RB_ERR_REF_INDEX;
+        rb_ctx_destroy(ctx);
+        return ref_panic ? 101 : 1;
+    }
+    rb_ctx_destroy(ctx);
+    return 0;
+}

@@ -1,0 +1,306 @@
+// rbhost.cpp — host-side text I/O, packing and printing (see rbhost.hpp for the reference lines).
+#include "rbhost.hpp"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+namespace rbh {
+
+// ---------------------------------------------------------------------------------------------
+// myio.rs:41-64 — extension decides: .gz / .bgz -> inflate (zlib reads concatenated BGZF members), else plain
+// ---------------------------------------------------------------------------------------------
+std::string read_all(const std::string& path) {
+    auto ends_with = [&](const char* suf) {
+        const size_t n = strlen(suf);
+        return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
+    };
+    std::string out;
+    if (path == "-") {
+        std::ostringstream ss;
+        ss << std::cin.rdbuf();
+        return ss.str();
+    }
+    if (ends_with(".gz") || ends_with(".bgz")) {
+        gzFile f = gzopen(path.c_str(), "rb");
+        if (!f) throw Panic("couldn't open " + path);
+        gzbuffer(f, 1 << 20);
+        std::vector<char> buf(1 << 22);
+        for (;;) {
+            const int n = gzread(f, buf.data(), (unsigned)buf.size());
+            if (n < 0) { gzclose(f); throw Panic("error inflating " + path); }
+            if (n == 0) break;
+            out.append(buf.data(), (size_t)n);
+        }
+        gzclose(f);
+        return out;
+    }
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw Panic("Error: cannot read input file " + path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz > 0) {
+        out.resize((size_t)sz);
+        if (fread(&out[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); throw Panic("short read on " + path); }
+    }
+    fclose(f);
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PAF
+// ---------------------------------------------------------------------------------------------
+static inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\x0C' || c == '\r'; }
+
+static bool parse_u64(const char* s, size_t n, uint64_t& out) {  // Rust str::parse::<u64>
+    size_t i = 0;
+    if (n && s[0] == '+') i = 1;
+    if (i >= n) return false;
+    uint64_t v = 0;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        const uint64_t d = (uint64_t)(s[i] - '0');
+        if (v > (UINT64_MAX - d) / 10) return false;
+        v = v * 10 + d;
+    }
+    out = v;
+    return true;
+}
+
+uint32_t Paf::name_id(const std::string& s) {
+    // small tables: linear probe over a sorted vector rebuilt lazily would be overkill; use binary search on index_
+    auto it = std::lower_bound(index_.begin(), index_.end(), s,
+                               [](const std::pair<std::string, uint32_t>& a, const std::string& b) { return a.first < b; });
+    if (it != index_.end() && it->first == s) return it->second;
+    const uint32_t id = (uint32_t)names.size();
+    names.push_back(s);
+    index_.insert(it, {s, id});
+    return id;
+}
+int64_t Paf::find_name(const std::string& s) const {
+    auto it = std::lower_bound(index_.begin(), index_.end(), s,
+                               [](const std::pair<std::string, uint32_t>& a, const std::string& b) { return a.first < b; });
+    if (it != index_.end() && it->first == s) return it->second;
+    return -1;
+}
+
+// paf.rs:62-78 + 379-430: lines() split at '\n' (one trailing '\r' dropped), split_ascii_whitespace,
+// >= 12 columns or panic, every extra token must look like a tag or panic, first cg:Z: wins,
+// unparsable numeric column -> the line is skipped.  The CIGAR payload is copied verbatim.
+Paf Paf::from_text(const char* text, size_t n) {
+    Paf paf;
+    size_t i = 0;
+    std::vector<std::pair<const char*, size_t>> t;
+    while (i < n) {
+        const char* nl = (const char*)memchr(text + i, '\n', n - i);
+        const size_t j = nl ? (size_t)(nl - text) : n;
+        size_t e = j;
+        if (nl && e > i && text[e - 1] == '\r') e--;
+        t.clear();
+        size_t p = i;
+        while (p < e) {
+            while (p < e && is_ws(text[p])) p++;
+            size_t q = p;
+            while (q < e && !is_ws(text[q])) q++;
+            if (q > p) t.emplace_back(text + p, q - p);
+            p = q;
+        }
+        i = nl ? j + 1 : n;
+        if (t.size() < 12) throw Panic("assertion failed: t.len() >= 12");
+        const char* cg = nullptr;
+        size_t cg_n = 0;
+        for (size_t k = 12; k < t.size(); k++) {
+            const char* tok = t[k].first;
+            const size_t tn = t[k].second;
+            size_t m = SIZE_MAX;
+            for (size_t a = 0; a + 5 <= tn; a++)
+                if (tok[a + 2] == ':' && tok[a + 4] == ':') { m = a; break; }
+            if (m == SIZE_MAX) throw Panic("assertion failed: PAF_TAG.is_match(token)");
+            if (tok[m] == 'c' && tok[m + 1] == 'g' && cg_n == 0) { cg = tok + m + 5; cg_n = tn - (m + 5); }
+        }
+        uint64_t v[9];
+        static const int colidx[9] = {1, 2, 3, 6, 7, 8, 9, 10, 11};
+        bool ok = true;
+        for (int c = 0; c < 9 && ok; c++) ok = parse_u64(t[colidx[c]].first, t[colidx[c]].second, v[c]);
+        if (!ok || t[4].second != 1) { paf.skipped++; continue; }
+        paf.q_len.push_back(v[0]); paf.q_st.push_back(v[1]); paf.q_en.push_back(v[2]);
+        paf.t_len.push_back(v[3]); paf.t_st.push_back(v[4]); paf.t_en.push_back(v[5]);
+        paf.mapq.push_back(v[8]);
+        paf.strand.push_back((uint8_t)t[4].first[0]);
+        paf.q_id.push_back(paf.name_id(std::string(t[0].first, t[0].second)));
+        paf.t_id.push_back(paf.name_id(std::string(t[5].first, t[5].second)));
+        if (cg_n) paf.cigar.insert(paf.cigar.end(), (const uint8_t*)cg, (const uint8_t*)cg + cg_n);
+        paf.cigar_off.push_back(paf.cigar.size());
+    }
+    return paf;
+}
+
+rb_records Paf::view() {
+    names_blob.clear();
+    names_off.assign(1, 0);
+    for (const std::string& s : names) {
+        names_blob.insert(names_blob.end(), s.begin(), s.end());
+        names_off.push_back(names_blob.size());
+    }
+    if (names_blob.empty()) names_blob.push_back(0);
+    rb_records r{};
+    r.n_rec = (uint32_t)size();
+    r.cigar = cigar.data(); r.cigar_nbytes = cigar.size(); r.cigar_off = cigar_off.data();
+    r.q_len = q_len.data(); r.q_st = q_st.data(); r.q_en = q_en.data();
+    r.t_len = t_len.data(); r.t_st = t_st.data(); r.t_en = t_en.data(); r.mapq = mapq.data();
+    r.strand = strand.data(); r.q_id = q_id.data(); r.t_id = t_id.data();
+    r.names = names_blob.data(); r.names_off = names_off.data(); r.n_names = (uint32_t)names.size();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BED — bed.rs:140-194 over bio 1.6.0 bed::Reader (csv: tab, '#' comments, fixed field count)
+// ---------------------------------------------------------------------------------------------
+std::vector<Region> parse_bed_text(const char* text, size_t n) {
+    std::vector<Region> out;
+    size_t i = 0, nf0 = 0;
+    std::vector<std::pair<size_t, size_t>> f;
+    while (i < n) {
+        size_t j = i;
+        while (j < n && text[j] != '\n' && text[j] != '\r') j++;
+        const size_t a = i, b = j;
+        i = j;
+        while (i < n && (text[i] == '\n' || text[i] == '\r')) i++;
+        if (a == b || text[a] == '#') continue;
+        f.clear();
+        size_t p = a;
+        for (;;) {
+            const char* tab = (const char*)memchr(text + p, '\t', b - p);
+            if (!tab) { f.emplace_back(p, b - p); break; }
+            f.emplace_back(p, (size_t)(tab - text) - p);
+            p = (size_t)(tab - text) + 1;
+        }
+        if (nf0 == 0) nf0 = f.size();
+        else if (f.size() != nf0) continue;
+        if (f.size() < 3) continue;
+        Region r;
+        auto strict = [&](std::pair<size_t, size_t> s, uint64_t& v) {
+            if (s.second == 0) return false;
+            uint64_t x = 0;
+            for (size_t k = 0; k < s.second; k++) {
+                const char c = text[s.first + k];
+                if (c < '0' || c > '9') return false;
+                const uint64_t d = (uint64_t)(c - '0');
+                if (x > (UINT64_MAX - d) / 10) return false;
+                x = x * 10 + d;
+            }
+            v = x;
+            return true;
+        };
+        if (!strict(f[1], r.st) || !strict(f[2], r.en)) continue;
+        r.name.assign(text + f[0].first, f[0].second);
+        if (f.size() > 3) r.id.assign(text + f[3].first, f[3].second);
+        else r.id = r.name + ":" + std::to_string(r.st + 1) + "-" + std::to_string(r.en);  // bed.rs:150-153
+        out.push_back(std::move(r));
+    }
+    return out;
+}
+
+Windows Windows::pack(const std::vector<Region>& rgns, const Paf& paf) {
+    struct Row { uint32_t t; uint64_t st; uint32_t row; };
+    std::vector<Row> rows;
+    rows.reserve(rgns.size());
+    for (size_t i = 0; i < rgns.size(); i++) {
+        const int64_t id = paf.find_name(rgns[i].name);
+        if (id < 0) continue;  // BED rows on contigs absent from the PAF are never visited (liftover.rs:151-164)
+        rows.push_back(Row{(uint32_t)id, rgns[i].st, (uint32_t)i});
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.t != b.t ? a.t < b.t : a.st < b.st; });
+    Windows w;
+    w.ids_off.push_back(0);
+    for (const Row& r : rows) {
+        const Region& g = rgns[r.row];
+        w.t_id.push_back(r.t); w.st.push_back(g.st); w.en.push_back(g.en); w.bed_row.push_back(r.row);
+        w.ids.insert(w.ids.end(), g.id.begin(), g.id.end());
+        w.ids_off.push_back(w.ids.size());
+    }
+    if (w.ids.empty()) w.ids.push_back(0);
+    return w;
+}
+rb_windows Windows::view() const {
+    rb_windows v{};
+    v.n_win = (uint32_t)t_id.size();
+    v.t_id = t_id.data(); v.st = st.data(); v.en = en.data(); v.bed_row = bed_row.data();
+    v.ids = ids.data(); v.ids_off = ids_off.data();
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// printing
+// ---------------------------------------------------------------------------------------------
+std::string fmt_f32(float v) {
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    char buf[128];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);  // shortest round trip, positional
+    return std::string(buf, r.ptr);
+}
+
+std::string stats_header(bool qbed) {
+    std::string s = qbed ? "#query_name\tquery_start\tquery_end\tquery_length\tstrand\treference_name\treference_start\treference_end\treference_length\t"
+                         : "#reference_name\treference_start\treference_end\treference_length\tstrand\tquery_name\tquery_start\tquery_end\tquery_length\t";
+    s += "perID_by_matches\tperID_by_events\tperID_by_all\tmatches\tmismatches\tdeletion_events\tinsertion_events\tdeletions\tinsertions\n";
+    return s;
+}
+
+void append_stats_row(std::string& s, const Paf& paf, size_t i, const rb_stats_out& st, bool qbed) {
+    auto q = [&] {
+        s += paf.names[paf.q_id[i]]; s += '\t'; s += std::to_string((int64_t)paf.q_st[i]); s += '\t';
+        s += std::to_string((int64_t)paf.q_en[i]); s += '\t'; s += std::to_string((int64_t)paf.q_len[i]); s += '\t';
+    };
+    auto r = [&] {
+        s += paf.names[paf.t_id[i]]; s += '\t'; s += std::to_string((int64_t)paf.t_st[i]); s += '\t';
+        s += std::to_string((int64_t)paf.t_en[i]); s += '\t'; s += std::to_string((int64_t)paf.t_len[i]); s += '\t';
+    };
+    if (qbed) { q(); s += (char)paf.strand[i]; s += '\t'; r(); }
+    else { r(); s += (char)paf.strand[i]; s += '\t'; q(); }
+    s += fmt_f32(st.id_by_matches[i]); s += '\t';
+    s += fmt_f32(st.id_by_events[i]); s += '\t';
+    s += fmt_f32(st.id_by_all[i]); s += '\t';
+    s += std::to_string(st.equal[i]); s += '\t';
+    s += std::to_string(st.diff[i]); s += '\t';
+    s += std::to_string(st.del_events[i]); s += '\t';
+    s += std::to_string(st.ins_events[i]); s += '\t';
+    s += std::to_string(st.del[i]); s += '\t';
+    s += std::to_string(st.ins[i]); s += '\n';
+}
+
+std::string paf_text(const Paf& paf, size_t lo, size_t hi) {
+    std::string s;
+    for (size_t i = lo; i < hi && i < paf.size(); i++) {
+        s += paf.names[paf.q_id[i]]; s += '\t';
+        s += std::to_string(paf.q_len[i]); s += '\t'; s += std::to_string(paf.q_st[i]); s += '\t';
+        s += std::to_string(paf.q_en[i]); s += '\t'; s += (char)paf.strand[i]; s += '\t';
+        s += paf.names[paf.t_id[i]]; s += '\t';
+        s += std::to_string(paf.t_len[i]); s += '\t'; s += std::to_string(paf.t_st[i]); s += '\t';
+        s += std::to_string(paf.t_en[i]); s += "\t0\t0\t"; s += std::to_string(paf.mapq[i]);
+        s += "\tcg:Z:";
+        s.append((const char*)paf.cigar.data() + paf.cigar_off[i], paf.cigar_off[i + 1] - paf.cigar_off[i]);
+        s += '\n';
+    }
+    return s;
+}
+
+std::string bed_text(const std::vector<Region>& rgns, bool with_ids) {
+    std::string s;
+    for (const Region& r : rgns) {
+        s += r.name; s += '\t'; s += std::to_string(r.st); s += '\t'; s += std::to_string(r.en);
+        if (with_ids) { s += '\t'; s += r.id; }
+        s += '\n';
+    }
+    return s;
+}
+
+}  // namespace rbh

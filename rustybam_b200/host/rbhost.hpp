@@ -1,0 +1,94 @@
+// rbhost.hpp — C++ host side above the C ABI (include/rbcuda.h): text I/O stays on the host.
+//
+// Mirrors the reference's host-facing pieces for this path (file:line into the reference):
+//   src/myio.rs:41-64        reader(): plain / .gz / .bgz / stdin          -> read_all()
+//   src/paf.rs:62-78,379-430 Paf::from_file / PafRecord::new               -> Paf::from_text / from_file
+//   src/bed.rs:140-194       parse_bed (bio bed::Reader semantics)         -> parse_bed_text / parse_bed
+//   src/liftover.rs:134-167  trim_paf_by_rgns                              -> trim_paf_by_rgns (GPU, via rb_liftover)
+//   src/bamstats.rs:91-105   stats_from_paf, :225-270 printers             -> stats_from_paf (GPU, via rb_stats) + printers
+//   src/main.rs:50-58,186-214 `rb stats --paf`, `rb liftover`              -> rb_main.cpp
+// CIGAR text is never tokenised here: the cg:Z: payload bytes are packed verbatim for the GPU.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rbcuda.h"
+
+namespace rbh {
+
+struct Panic : std::runtime_error {  // the reference would panic (exit status 101)
+    explicit Panic(const std::string& m) : std::runtime_error(m) {}
+};
+
+std::string read_all(const std::string& path);  // "-" = stdin; .gz/.bgz inflated with zlib
+
+// Packed records (what rb_records points into).  Name ids are shared by query and target names.
+struct Paf {
+    std::vector<uint8_t> cigar;
+    std::vector<uint64_t> cigar_off{0};
+    std::vector<uint64_t> q_len, q_st, q_en, t_len, t_st, t_en, mapq;
+    std::vector<uint8_t> strand;
+    std::vector<uint32_t> q_id, t_id;
+    std::vector<std::string> names;
+    std::vector<uint8_t> names_blob;
+    std::vector<uint64_t> names_off;
+    size_t skipped = 0;
+
+    size_t size() const { return q_id.size(); }
+    uint32_t name_id(const std::string& s);            // interns
+    int64_t find_name(const std::string& s) const;     // -1 if absent
+    static Paf from_text(const char* text, size_t n);  // throws Panic like PafRecord::new's asserts
+    static Paf from_file(const std::string& path) {
+        std::string t = read_all(path);
+        return from_text(t.data(), t.size());
+    }
+    rb_records view();  // finalises the name table and returns the SoA view
+
+   private:
+    std::vector<std::pair<std::string, uint32_t>> index_;  // sorted lazily
+    bool index_sorted_ = true;
+};
+
+struct Region {
+    std::string name;
+    uint64_t st = 0, en = 0;
+    std::string id;
+};
+std::vector<Region> parse_bed_text(const char* text, size_t n);
+inline std::vector<Region> parse_bed(const std::string& path) {
+    std::string t = read_all(path);
+    return parse_bed_text(t.data(), t.size());
+}
+
+// rb_windows builder: drops rows on contigs absent from the PAF, sorts by (t_id, st) keeping bed_row
+struct Windows {
+    std::vector<uint32_t> t_id, bed_row;
+    std::vector<uint64_t> st, en, ids_off;
+    std::vector<uint8_t> ids;
+    rb_windows view() const;
+    static Windows pack(const std::vector<Region>& rgns, const Paf& paf);
+};
+
+std::string fmt_f32(float v);                 // Rust `{}` for f32 (shortest round trip, positional)
+std::string stats_header(bool qbed);          // bamstats.rs:225-236
+// bamstats.rs:239-270 for row i of `paf` with the GPU counters of row i
+void append_stats_row(std::string& out, const Paf& paf, size_t i, const rb_stats_out& st, bool qbed);
+
+// ---- synthetic whole-genome-scale eqx PAF ----
+struct SynthParams {
+    uint64_t seed = 20261017;
+    double scale = 1.0;   // multiplies the CHM13-like contig lengths
+    int n_hap = 1;        // haplotypes (independent streams) concatenated
+    int threads = 8;
+};
+Paf synth_paf(const SynthParams& p);
+// `bedtools makewindows`-style tiling of every target contig of `paf`, 3 columns (id = chrom:st+1-en), sorted
+std::vector<Region> tiling_windows(const Paf& paf, uint64_t width);
+Windows tiling_windows_packed(const Paf& paf, uint64_t width);
+// PAF text of records [lo, hi) (12 columns + cg:Z:) — input for the CPU oracle / reference
+std::string paf_text(const Paf& paf, size_t lo, size_t hi);
+std::string bed_text(const std::vector<Region>& rgns, bool with_ids);
+
+}  // namespace rbh
