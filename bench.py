@@ -190,7 +190,7 @@ def main():
     b = ctx.upload(shard, wins)
     summ = None
     for _ in range(args.warmup):
-        summ = ctx.batch_liftover(b, with_stats=True)
+        summ = ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -200,7 +200,7 @@ def main():
         flush.fill_(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        summ = ctx.batch_liftover(b, with_stats=True)
+        summ = ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
         e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
@@ -214,7 +214,7 @@ def main():
     ctx.kernel_times(reset=True)
     for _ in range(max(3, args.steps // 4)):
         flush.fill_(1)
-        ctx.batch_liftover(b, with_stats=True)
+        ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
     torch.cuda.synchronize()
     ktimes = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)

@@ -164,7 +164,8 @@ void rb_free_stats_out(rb_ctx* ctx, rb_stats_out* stats);
 
 /* ---- resident batches: upload once, run the kernels with inputs already in HBM ---- */
 rb_batch* rb_batch_upload(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins /* nullable */, int* status);
-int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, int with_stats, rb_summary* summary);
+/* `want`: which outputs the kernels materialise in HBM (RB_WANT_* bits); rb_batch_download_lift may ask for a subset */
+int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int with_stats, rb_summary* summary);
 int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary);
 int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out* out, rb_stats_out* stats);
 int rb_batch_download_stats(rb_ctx* ctx, rb_batch* b, rb_stats_out* stats);

@@ -37,7 +37,8 @@ def build_cuda(force=False, verbose=False):
     deps = srcs + _sources(CSRC, (".cuh",)) + [os.path.join(ROOT, "include", "rbcuda.h"), os.path.abspath(__file__)]
     if not force and not _newer(LIB, deps):
         return LIB
-    cmd = [nvcc] + NVCC_FLAGS + ["-shared", "-o", LIB] + srcs
+    extra = [f"-DRB_SAMPLE_LOG2={os.environ['RB_SAMPLE_LOG2']}"] if os.environ.get("RB_SAMPLE_LOG2") else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-shared", "-o", LIB] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -93,7 +93,7 @@ def load():
     lib.rb_free_stats_out.argtypes = [C.c_void_p, C.POINTER(RbStatsOut)]
     lib.rb_batch_upload.restype = C.c_void_p
     lib.rb_batch_upload.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.POINTER(RbWindows), C.POINTER(C.c_int)]
-    lib.rb_batch_liftover.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(RbSummary)]
+    lib.rb_batch_liftover.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_int, C.POINTER(RbSummary)]
     lib.rb_batch_stats.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RbSummary)]
     lib.rb_batch_download_lift.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(RbLiftOut), C.POINTER(RbStatsOut)]
     lib.rb_batch_download_stats.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RbStatsOut)]
@@ -262,9 +262,9 @@ class Context:
             raise RbError(st.value, self.lib.rb_last_error(self.h).decode())
         return b
 
-    def batch_liftover(self, b, policy=POLICY_RIGHTMOST, with_stats=True):
+    def batch_liftover(self, b, policy=POLICY_RIGHTMOST, with_stats=True, want=WANT_TEXT | WANT_NUMERIC):
         s = RbSummary()
-        self._check(self.lib.rb_batch_liftover(self.h, b, policy, int(with_stats), C.byref(s)))
+        self._check(self.lib.rb_batch_liftover(self.h, b, policy, want, int(with_stats), C.byref(s)))
         return dict(n_ops=int(s.n_ops), n_pairs=int(s.n_pairs), n_out=int(s.n_out), out_bytes=int(s.out_bytes), cigar_bytes=int(s.cigar_bytes))
 
     def batch_stats(self, b):

@@ -25,40 +25,73 @@ struct OpsView {
 enum : int { POLICY_RIGHTMOST = 0, POLICY_EARLY_EXIT = 1 };
 enum : uint32_t { LIFT_OK = 0, LIFT_ERR_NOT_FOUND = 1 };  // NOT_FOUND == the reference's "Problem getting index in cigar" panic
 
-// Counters accumulated from the record's first op up to (excluding) op k.
-RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k) {
+// Counters accumulated from the record's first op up to (excluding) op k (op_first <= k < op_end).
+RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k, ClassAcc& acc) {
     const uint64_t base = (k >> SAMPLE_LOG2) << SAMPLE_LOG2;
     Ctr c;
     uint64_t j;
     if (base > r.op_first) { c = v.samples[k >> SAMPLE_LOG2]; j = base; }
     else { c = ctr_zero(); j = r.op_first; }
-    for (; j < k; j++) ctr_add_op(c, v.ops[j]);
+    acc_reset(acc);
+    const uint64_t j0 = j;
+    for (; j < k; j++) acc_add_op(acc, v.ops[j]);
+    if (acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
+        for (j = j0; j < k; j++) ctr_add_op(c, v.ops[j]);
+        return c;
+    }
+    acc_flush(acc, c);
     return c;
 }
 
+// Warp reconvergence point (device only).  lift_pair is written in stages without early returns so that
+// every lane executes the same sequence of these barriers: lanes leave the walk loops at different
+// times, and without them the straight-line code after a loop runs once per straggler group.
+#if defined(__CUDA_ARCH__)
+#define RB_CONVERGE() __syncwarp()
+#else
+#define RB_CONVERGE() ((void)0)
+#endif
+
 // The reference-consuming op i (len > 0) with T_i <= p < T_i + L_i ; o = p - T_i ; `before` = counters before op i.
-RB_HD bool find_op(const OpsView& v, const RecInfo& r, uint32_t p, uint64_t& i, uint32_t& o, Ctr& before) {
-    if (r.op_end <= r.op_first) return false;
-    uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
-    while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
-        const uint64_t mid = (lo + hi + 1) >> 1;
-        if (v.samples[mid].T <= p) lo = mid;
-        else hi = mid - 1;
-    }
-    uint64_t k = lo << SAMPLE_LOG2;
-    Ctr c;
-    if (k > r.op_first) c = v.samples[lo];
-    else { c = ctr_zero(); k = r.op_first; }
-    for (; k < r.op_end; k++) {
-        const uint32_t w = v.ops[k];
-        const uint32_t L = op_len(w);
-        if (is_ref(op_code(w)) && L > 0 && p - c.T < L) {
-            i = k; o = p - c.T; before = c;
-            return true;
+// `live` == false: does nothing (keeps the lane in step with its warp).
+RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, uint64_t& i, uint32_t& o, Ctr& before, ClassAcc& acc) {
+    bool found = false;
+    Ctr c = ctr_zero();
+    uint64_t k0 = 0;
+    uint32_t n = 0, j = 0;
+    if (live && r.op_end > r.op_first) {
+        uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
+        while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if (v.samples[mid].T <= p) lo = mid;
+            else hi = mid - 1;
         }
-        ctr_add_op(c, w);
+        k0 = lo << SAMPLE_LOG2;
+        if (k0 > r.op_first) c = v.samples[lo];
+        else k0 = r.op_first;
+        const uint64_t left = r.op_end - k0;
+        n = left > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)left;
     }
-    return false;
+    RB_CONVERGE();
+    const uint32_t rel = p - c.T;  // target offset relative to the chunk start
+    const uint32_t* q = v.ops + k0;
+    acc_reset(acc);
+    for (; j < n; j++) {
+        const uint32_t w = q[j];
+        const uint32_t L = op_len(w);
+        if (is_ref(op_code(w)) && L > 0 && rel - acc.T < L) { found = true; break; }
+        acc_add_op(acc, w);
+    }
+    RB_CONVERGE();
+    if (found) {
+        if (acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
+            for (uint32_t t = 0; t < j; t++) ctr_add_op(c, q[t]);
+        } else {
+            acc_flush(acc, c);
+        }
+        i = k0 + j; o = p - c.T; before = c;
+    }
+    return found;
 }
 
 // core::slice::binary_search of Rust 1.52..=1.81 over a column array whose entries equal to the
@@ -101,128 +134,139 @@ RB_HD void fill_stats(PairRes& out, const Ctr& d) {
 }
 
 // One pair.  Returns LIFT_OK (out.kind says DROP / TRIM / EARLY) or LIFT_ERR_NOT_FOUND.
-RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, int policy, PairRes& out) {
+// Staged, no early returns (see RB_CONVERGE): a lane that is done just stops being `live`.
+// `enabled` == false (a candidate pair that does not overlap): produces PK_DROP, keeps the lane in step.
+RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, int policy, bool enabled, PairRes& out,
+                         ClassAcc& acc) {
+    uint32_t status = LIFT_OK;
+    bool live = enabled;
     out.pad = 0;
+    out.kind = PK_DROP;
+    out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
+    out.s_len = out.e_len = out.cg_bytes = 0;
+    out.equal = out.diff = out.ins = out.del = out.ins_ev = out.del_ev = out.matches = 0;
     // liftover.rs:22-25 (Q3): record strictly inside the window -> the record itself, uncollapsed
-    if (r.t_st > w_st && r.t_en < w_en) {
+    if (live && r.t_st > w_st && r.t_en < w_en) {
         out.kind = PK_EARLY;
         out.t_st = r.t_st; out.t_en = r.t_en; out.q_st = r.q_st; out.q_en = r.q_en;
         out.nmatch = (uint64_t)(uint32_t)(r.tot.EQ + r.tot.X + r.tot.M);
         out.aln_len = r.tot.A;
         out.si = r.eo0; out.ei = r.eo1 - 1;
-        out.s_len = 0; out.e_len = 0;
         out.cg_bytes = r.tot.TXT;
         fill_stats(out, r.tot);
-        return LIFT_OK;
+        live = false;
+    } else if (live && r.t_en <= r.t_st) {
+        status = LIFT_ERR_NOT_FOUND;
+        live = false;
     }
-    out.kind = PK_DROP;
-    out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
-    out.s_len = out.e_len = out.cg_bytes = 0;
-    out.equal = out.diff = out.ins = out.del = out.ins_ev = out.del_ev = out.matches = 0;
-    if (r.t_en <= r.t_st) return LIFT_ERR_NOT_FOUND;
-
-    const uint32_t ps = (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st);       // liftover.rs:28
-    const uint32_t pe = (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st);   // liftover.rs:38-40
+    const uint32_t ps = live ? (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st) : 0u;      // liftover.rs:28
+    const uint32_t pe = live ? (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st) : 0u;  // liftover.rs:38-40
 
     // ---- START: tpos_to_idx_match(t_st, search_right = true) ----
-    uint64_t i; uint32_t o; Ctr before;
-    if (!find_op(v, r, ps, i, o, before)) return LIFT_ERR_NOT_FOUND;
-    uint32_t w = v.ops[i];
-    uint32_t L = op_len(w), code = op_code(w);
-    bool slide = false;
-    if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
-        uint64_t k2 = i + 1;
-        while (k2 < r.eo1 && op_len(v.ops[k2]) == 0) k2++;
-        if (k2 < r.eo1 && !is_ref(op_code(v.ops[k2]))) slide = true;
-    }
-    if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
-        const uint32_t ca = before.A + o - r.a_lead;
-        uint32_t extra = 0;
-        for (uint64_t k = i + 1; k < r.eo1; k++) {
-            const uint32_t w2 = v.ops[k];
-            if (op_len(w2) == 0) continue;
-            if (is_ref(op_code(w2))) break;
-            extra += op_len(w2);
+    uint64_t i = 0; uint32_t o = 0; Ctr before = ctr_zero();
+    if (!find_op(v, r, live, ps, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    uint64_t si = 0; uint32_t so = 0; Ctr cs = ctr_zero();
+    if (live) {
+        const uint32_t w = v.ops[i];
+        const uint32_t L = op_len(w), code = op_code(w);
+        bool slide = false;
+        if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
+            uint64_t k2 = i + 1;
+            while (k2 < r.eo1 && op_len(v.ops[k2]) == 0) k2++;
+            if (k2 < r.eo1 && !is_ref(op_code(v.ops[k2]))) slide = true;
         }
-        if (early_exit_probe(r.tot.A, ca, ca + extra) == ca) slide = false;
-    }
-    uint64_t si; uint32_t so; Ctr cs;
-    if (!slide && is_match(code)) {
-        si = i; so = o; cs = before;
-        ctr_add_bases(cs, code, o);
-    } else {
-        Ctr c = before;
-        ctr_add_op(c, w);
-        uint64_t k = i + 1;
-        bool found = false;
-        for (; k < r.eo1; k++) {
-            const uint32_t w2 = v.ops[k];
-            if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
-            ctr_add_op(c, w2);
+        if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
+            const uint32_t ca = before.A + o - r.a_lead;
+            uint32_t extra = 0;
+            for (uint64_t k = i + 1; k < r.eo1; k++) {
+                const uint32_t w2 = v.ops[k];
+                if (op_len(w2) == 0) continue;
+                if (is_ref(op_code(w2))) break;
+                extra += op_len(w2);
+            }
+            if (early_exit_probe(r.tot.A, ca, ca + extra) == ca) slide = false;
         }
-        if (!found) return LIFT_OK;  // start index == number of columns > any end index (liftover.rs:52-54)
-        si = k; so = 0; cs = c;
+        if (!slide && is_match(code)) {
+            si = i; so = o; cs = before;
+            ctr_add_bases(cs, code, o);
+        } else {
+            Ctr c = before;
+            ctr_add_op(c, w);
+            uint64_t k = i + 1;
+            bool found = false;
+            for (; k < r.eo1; k++) {
+                const uint32_t w2 = v.ops[k];
+                if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+                ctr_add_op(c, w2);
+            }
+            if (!found) live = false;  // start index == number of columns > any end index (liftover.rs:52-54)
+            si = k; so = 0; cs = c;
+        }
     }
+    RB_CONVERGE();
 
     // ---- END: tpos_to_idx_match(t_en - 1, search_right = false) ----
-    if (!find_op(v, r, pe, i, o, before)) return LIFT_ERR_NOT_FOUND;
-    w = v.ops[i];
-    L = op_len(w); code = op_code(w);
-    uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
-    if (is_match(code)) {
-        ei = i; eo = o; ce = before; txt_before_ei = before.TXT;
-        ctr_add_bases(ce, code, o + 1);
-    } else {
-        Ctr c = before;
-        uint64_t k = i;
-        bool found = false;
-        while (k > r.eo0) {
-            k--;
-            const uint32_t w2 = v.ops[k];
-            ctr_sub_op(c, w2);
-            if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+    if (!find_op(v, r, live, pe, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    if (live) {
+        const uint32_t w = v.ops[i];
+        const uint32_t code = op_code(w);
+        uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
+        if (is_match(code)) {
+            ei = i; eo = o; ce = before; txt_before_ei = before.TXT;
+            ctr_add_bases(ce, code, o + 1);
+        } else {
+            Ctr c = before;
+            uint64_t k = i;
+            bool found = false;
+            while (k > r.eo0) {
+                k--;
+                const uint32_t w2 = v.ops[k];
+                ctr_sub_op(c, w2);
+                if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+            }
+            if (!found) live = false;  // slid to column 0 which is not a match column -> start > end
+            ei = k; eo = found ? op_len(v.ops[k]) - 1 : 0; ce = c; txt_before_ei = c.TXT;
+            if (found) ctr_add_bases(ce, op_code(v.ops[k]), eo + 1);
         }
-        if (!found) return LIFT_OK;  // slid to column 0 which is not a match column -> start > end
-        ei = k; eo = op_len(v.ops[k]) - 1; ce = c; txt_before_ei = c.TXT;
-        ctr_add_bases(ce, op_code(v.ops[k]), eo + 1);
+        if (live && cs.A >= ce.A) live = false;  // start column > end column: window lies inside an indel (Q7)
+        if (live) {
+            out.kind = PK_TRIM;
+            out.t_st = r.t_st + cs.T;
+            out.t_en = r.t_st + ce.T;
+            if (r.flags & RF_MINUS) {  // Q8: columns walk the query downward from q_en
+                out.q_st = r.q_en0 - ce.Q;
+                out.q_en = r.q_en0 - cs.Q;
+            } else {
+                out.q_st = r.q_st0 + cs.Q;
+                out.q_en = r.q_st0 + ce.Q;
+            }
+            Ctr d = ce;
+            ctr_sub(d, cs);
+            out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
+            out.aln_len = d.A;
+            fill_stats(out, d);
+            out.si = si; out.ei = ei;
+            const uint32_t L_si = op_len(v.ops[si]);
+            if (si == ei) {
+                out.s_len = eo - so + 1; out.e_len = 0;
+                out.cg_bytes = ndigits32(out.s_len) + 1;
+            } else {
+                out.s_len = L_si - so; out.e_len = eo + 1;
+                out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
+            }
+            if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
+                uint32_t bytes = 0, iev = 0, dev = 0;
+                merged_walk(v.ops, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
+                    bytes += ndigits32(len) + 1;
+                    iev += (c2 == OP_I);
+                    dev += (c2 == OP_D);
+                });
+                out.cg_bytes = bytes; out.ins_ev = iev; out.del_ev = dev;
+            }
+        }
     }
-
-    if (cs.A >= ce.A) return LIFT_OK;  // start column > end column: window lies inside an indel (Q7)
-
-    out.kind = PK_TRIM;
-    out.t_st = r.t_st + cs.T;
-    out.t_en = r.t_st + ce.T;
-    if (r.flags & RF_MINUS) {  // Q8: columns walk the query downward from q_en
-        out.q_st = r.q_en0 - ce.Q;
-        out.q_en = r.q_en0 - cs.Q;
-    } else {
-        out.q_st = r.q_st0 + cs.Q;
-        out.q_en = r.q_st0 + ce.Q;
-    }
-    Ctr d = ce;
-    ctr_sub(d, cs);
-    out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
-    out.aln_len = d.A;
-    fill_stats(out, d);
-    out.si = si; out.ei = ei;
-    const uint32_t L_si = op_len(v.ops[si]);
-    if (si == ei) {
-        out.s_len = eo - so + 1; out.e_len = 0;
-        out.cg_bytes = ndigits32(out.s_len) + 1;
-    } else {
-        out.s_len = L_si - so; out.e_len = eo + 1;
-        out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
-    }
-    if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
-        uint32_t bytes = 0, iev = 0, dev = 0;
-        merged_walk(v.ops, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
-            bytes += ndigits32(len) + 1;
-            iev += (c2 == OP_I);
-            dev += (c2 == OP_D);
-        });
-        out.cg_bytes = bytes; out.ins_ev = iev; out.del_ev = dev;
-    }
-    return LIFT_OK;
+    RB_CONVERGE();
+    return status;
 }
 
 // Bytes of the printed PAF line (paf.rs:923-943), '\n' included.

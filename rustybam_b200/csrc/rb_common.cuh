@@ -26,7 +26,10 @@ constexpr uint32_t MASK_REF = (1u << OP_M) | (1u << OP_D) | (1u << OP_N) | (1u <
 constexpr uint32_t MASK_QRY = (1u << OP_M) | (1u << OP_I) | (1u << OP_S) | (1u << OP_EQ) | (1u << OP_X);  // paf.rs:958-963
 constexpr uint32_t MASK_MATCH = (1u << OP_M) | (1u << OP_EQ) | (1u << OP_X);                              // paf.rs:973-975
 constexpr uint32_t MAX_OP_LEN = (1u << 28) - 1;
-constexpr int SAMPLE_LOG2 = 5;
+#ifndef RB_SAMPLE_LOG2
+#define RB_SAMPLE_LOG2 5
+#endif
+constexpr int SAMPLE_LOG2 = RB_SAMPLE_LOG2;  // 5 or 4
 constexpr uint32_t SAMPLE = 1u << SAMPLE_LOG2;  // ops per sample chunk (== bits of a heads word)
 
 RB_HD uint32_t op_len(uint32_t w) { return w >> 4; }
@@ -35,9 +38,28 @@ RB_HD bool is_ref(uint32_t code) { return (MASK_REF >> code) & 1u; }
 RB_HD bool is_qry(uint32_t code) { return (MASK_QRY >> code) & 1u; }
 RB_HD bool is_match(uint32_t code) { return (MASK_MATCH >> code) & 1u; }
 
+RB_HD uint32_t clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__clz((int)v);
+#else
+    return v ? (uint32_t)__builtin_clz(v) : 32u;
+#endif
+}
+// decimal digits of v (v < 2^32)
 RB_HD uint32_t ndigits32(uint32_t v) {
-    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
-           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+    uint32_t n = 1u;
+    if (v >= 10u) n++;
+    if (v >= 100u) n++;
+    if (v >= 1000u) n++;
+    if (v >= 10000u) {
+        n++;
+        if (v >= 100000u) n++;
+        if (v >= 1000000u) n++;
+        if (v >= 10000000u) n++;
+        if (v >= 100000000u) n++;
+        if (v >= 1000000000u) n++;
+    }
+    return n;
 }
 RB_HD uint32_t ndigits64(uint64_t v) {
     if (v < 4294967296ull) return ndigits32((uint32_t)v);
@@ -83,24 +105,45 @@ RB_HD void ctr_sub(Ctr& a, const Ctr& b) {  // aux is left alone
     a.T -= b.T; a.Q -= b.Q; a.A -= b.A; a.EQ -= b.EQ; a.X -= b.X; a.M -= b.M; a.I -= b.I; a.D -= b.D;
     a.IEV -= b.IEV; a.DEV -= b.DEV; a.TXT -= b.TXT;
 }
-// `n` bases of an op of class `code`; `whole` adds the event and the text of the complete op
+// class flags per BAM code, 7 bits each (9 codes = 63 bits of one constant):
+//   bit0 target-consuming  bit1 query-consuming  bit2 '='  bit3 'X'  bit4 'M'  bit5 'I'  bit6 'D'
+constexpr uint64_t class_flags_table() {
+    const uint64_t f[9] = {0x13 /*M*/, 0x22 /*I*/, 0x41 /*D*/, 0x01 /*N*/, 0x02 /*S*/, 0x00 /*H*/, 0x00 /*P*/, 0x07 /*=*/, 0x0B /*X*/};
+    uint64_t t = 0;
+    for (int c = 0; c < 9; c++) t |= f[c] << (7 * c);
+    return t;
+}
+constexpr uint64_t CLASS_FLAGS = class_flags_table();
+RB_HD uint32_t class_flags(uint32_t code) { return (uint32_t)(CLASS_FLAGS >> (7u * code)) & 0x7Fu; }
+
+// `n` bases of an op of class `code` (no event, no text).  Written as bit tests so that the
+// compiler emits one predicate + one predicated add per counter.
 RB_HD void ctr_add_bases(Ctr& c, uint32_t code, uint32_t n) {
+    const uint32_t f = class_flags(code);
     const uint32_t s = c.A + n;
-    if (s < c.A) c.aux |= AUX_OVF;
+    if (s < n) c.aux |= AUX_OVF;
     c.A = s;
-    if (is_ref(code)) c.T += n;
-    if (is_qry(code)) c.Q += n;
-    if (code == OP_EQ) c.EQ += n;
-    else if (code == OP_X) c.X += n;
-    else if (code == OP_M) c.M += n;
-    else if (code == OP_I) c.I += n;
-    else if (code == OP_D) c.D += n;
+    if (f & 1u) c.T += n;
+    if (f & 2u) c.Q += n;
+    if (f & 4u) c.EQ += n;
+    if (f & 8u) c.X += n;
+    if (f & 16u) c.M += n;
+    if (f & 32u) c.I += n;
+    if (f & 64u) c.D += n;
 }
 RB_HD void ctr_add_op(Ctr& c, uint32_t w) {
     const uint32_t code = op_code(w), n = op_len(w);
-    ctr_add_bases(c, code, n);
-    c.IEV += (code == OP_I);
-    c.DEV += (code == OP_D);
+    const uint32_t f = class_flags(code);
+    const uint32_t s = c.A + n;
+    if (s < n) c.aux |= AUX_OVF;
+    c.A = s;
+    if (f & 1u) c.T += n;
+    if (f & 2u) c.Q += n;
+    if (f & 4u) c.EQ += n;
+    if (f & 8u) c.X += n;
+    if (f & 16u) c.M += n;
+    if (f & 32u) { c.I += n; c.IEV++; }
+    if (f & 64u) { c.D += n; c.DEV++; }
     c.TXT += ndigits32(n) + 1u;
 }
 RB_HD void ctr_sub_op(Ctr& c, uint32_t w) {
@@ -108,6 +151,48 @@ RB_HD void ctr_sub_op(Ctr& c, uint32_t w) {
     ctr_add_op(t, w);
     ctr_sub(c, t);
 }
+
+// ---- cheap accumulation for the hot walks -------------------------------------------------------
+// Exactly one class sum changes per op, so the walks keep nine per-thread class sums in an indexed
+// array (shared memory on the device: sum[code * stride], stride = threads per block, conflict-free;
+// a local array on the host) and derive the 11 counters only when a chunk / boundary is flushed.
+struct ClassAcc {
+    uint32_t* sum;     // sum[code * stride], codes 0..8
+    uint32_t stride;
+    uint32_t T;        // running target bases (the find test needs it every op)
+    uint32_t iev, dev, txt;
+    uint32_t big;      // OR of all lengths seen: class sums of <= 32 ops cannot wrap while every len < 2^26
+};
+RB_HD void acc_reset(ClassAcc& a) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t c = 0; c < 9u; c++) a.sum[c * a.stride] = 0u;
+    a.T = a.iev = a.dev = a.txt = a.big = 0u;
+}
+RB_HD void acc_add_op(ClassAcc& a, uint32_t w) {
+    const uint32_t code = op_code(w), n = op_len(w);
+    a.sum[code * a.stride] += n;
+    if (is_ref(code)) a.T += n;
+    a.iev += (code == OP_I);
+    a.dev += (code == OP_D);
+    a.txt += ndigits32(n) + 1u;
+    a.big |= n;
+}
+// c += everything accumulated since acc_reset
+RB_HD void acc_flush(const ClassAcc& a, Ctr& c) {
+    const uint32_t M = a.sum[OP_M * a.stride], I = a.sum[OP_I * a.stride], D = a.sum[OP_D * a.stride],
+                   N = a.sum[OP_N * a.stride], S = a.sum[OP_S * a.stride], H = a.sum[OP_H * a.stride],
+                   P = a.sum[OP_P * a.stride], E = a.sum[OP_EQ * a.stride], X = a.sum[OP_X * a.stride];
+    const uint64_t all = (uint64_t)M + I + D + N + S + H + P + E + X + c.A;
+    if (all >> 32) c.aux |= AUX_OVF;
+    c.A = (uint32_t)all;
+    c.T += M + D + N + E + X;
+    c.Q += M + I + S + E + X;
+    c.EQ += E; c.X += X; c.M += M; c.I += I; c.D += D;
+    c.IEV += a.iev; c.DEV += a.dev; c.TXT += a.txt;
+}
+constexpr uint32_t ACC_BIG = 1u << 26;
 
 // record flags
 enum : uint32_t {

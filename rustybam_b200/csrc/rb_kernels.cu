@@ -48,10 +48,13 @@ __device__ __forceinline__ uint4 ld_cg_v4(const void* p) {
 __device__ __forceinline__ void report(unsigned long long* slot, uint64_t key, uint32_t code) {
     atomicMin(slot, (unsigned long long)((key << 8) | code));
 }
-// per-byte "is not an ASCII digit" as 0xFF/0x00 lanes of a 32-bit word
-__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t x) { return __vcmpgtu4(x ^ 0x30303030u, 0x09090909u); }
+// per-byte "is not an ASCII digit": bit 7 of each byte lane set for a non-digit (exact for all 256 byte values)
+__device__ __forceinline__ uint32_t nondigit_bytes(uint32_t x) {
+    const uint32_t t = x ^ 0x30303030u;  // digits -> 0x00..0x09
+    return (((t & 0x7F7F7F7Fu) + 0x76767676u) | t) & 0x80808080u;
+}
 __device__ __forceinline__ uint32_t nondigit_count(uint4 c) {
-    return (__popc(nondigit_bytes(c.x)) + __popc(nondigit_bytes(c.y)) + __popc(nondigit_bytes(c.z)) + __popc(nondigit_bytes(c.w))) >> 3;
+    return __popc(nondigit_bytes(c.x)) + __popc(nondigit_bytes(c.y)) + __popc(nondigit_bytes(c.z)) + __popc(nondigit_bytes(c.w));
 }
 // op character -> BAM code (15 = not one of MIDNSHP=X).  (c & 31) is a perfect hash of the alphabet:
 // D=4 H=8 I=9 M=13 N=14 P=16 S=19 X=24 '='=29 ; two 16-nibble tables, then an exact compare.
@@ -133,26 +136,76 @@ __device__ __noinline__ bool exact_len(const uint8_t* text, uint64_t pos, uint32
     return true;
 }
 
+// ---- async bulk copy (TMA engine, 1-D) + mbarrier: global -> shared staging of a text tile ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 4 ASCII digits (most significant in the LOW byte; zeroed bytes count as leading zeros) -> value
+__device__ __forceinline__ uint32_t parse4(uint32_t x) {
+    x &= 0x0F0F0F0Fu;
+    const uint32_t pairs = ((x * 2561u) >> 8) & 0x00FF00FFu;  // d0*10+d1 | d2*10+d3
+    return (pairs * 6553601u) >> 16;                          // (d0d1)*100 + d2d3
+}
+
+// One tile = TOK_TILE text bytes.  (1) bulk-copy tile + 16-byte look-behind halo into shared memory,
+// (2) per thread: 16-byte vector load, op-character bitmask, count; block scan + decoupled look-back give
+// the global op index, (3) op positions are compacted into shared memory, (4) one op per thread:
+// the 8 bytes in front of the op character are decoded with two SWAR multiplies, stores are coalesced.
 __global__ void __launch_bounds__(TOK_THREADS)
 k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigned long long* tile_state, unsigned int* ticket,
            ErrSlots err, uint32_t* misc_flags) {
-    __shared__ unsigned int s_tile;
-    __shared__ uint32_t s_tail_v[TOK_THREADS];
-    __shared__ uint32_t s_tail_nd[TOK_THREADS];
+    __shared__ __align__(16) uint8_t s_text[16 + TOK_TILE + 16];
+    __shared__ uint16_t s_pos[TOK_TILE / 2];
+    __shared__ uint8_t s_lut[256];  // byte -> BAM op code (15 = not an op character)
+    __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_warp[TOK_THREADS / 32];
     __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    s_lut[tid] = (uint8_t)code_of_char((uint32_t)tid);
+    if (tid == 0) {
+        s_tile = atomicAdd(ticket, 1u);
+        mbar_init(&s_bar, 1);
+    }
     __syncthreads();
     const uint64_t tile = s_tile;
-    const uint64_t g0 = tile * (uint64_t)TOK_TILE + (uint64_t)tid * 16u;
+    const uint64_t tbase = tile * (uint64_t)TOK_TILE;
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, 16 + TOK_TILE);
+        bulk_g2s(s_text, text + tbase - 16, 16 + TOK_TILE, &s_bar);  // text[-16..0) is 0xFF padding
+    }
+    mbar_wait(&s_bar, 0);
 
-    const uint4 c = ld_nc_v4(text + g0);
-    const uint32_t w[4] = {c.x, c.y, c.z, c.w};
-    const uint32_t cnt = nondigit_count(c);
+    const uint4 c = *reinterpret_cast<const uint4*>(s_text + 16 + tid * 16);
+    const uint32_t M = 0x01020408u;  // gathers the low bit of each byte into a nibble
+    const uint32_t m16 = ((((nondigit_bytes(c.x) >> 7) * M) >> 24) & 0xFu) | (((((nondigit_bytes(c.y) >> 7) * M) >> 24) & 0xFu) << 4) |
+                         (((((nondigit_bytes(c.z) >> 7) * M) >> 24) & 0xFu) << 8) | (((((nondigit_bytes(c.w) >> 7) * M) >> 24) & 0xFu) << 12);
+    const uint32_t cnt = __popc(m16);
 
-    // block exclusive scan of op counts
     uint32_t inc = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -160,78 +213,64 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
         if (lane >= d) inc += t;
     }
     if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint32_t wpre = 0, total = 0;
+    {   // compact this thread's op positions (tile-relative) while the scan totals settle
+        uint32_t mm = m16, k = 0;
+        // exclusive index inside the warp is known now; the warp offset is added after the barrier
+        const uint32_t wex = inc - cnt;
+        // stash (warp-relative) positions in registers' stead: write after the barrier
+        __syncthreads();
+        uint32_t wpre = 0, total = 0;
 #pragma unroll
-    for (int k = 0; k < TOK_THREADS / 32; k++) {
-        const uint32_t t = s_warp[k];
-        if (k < warp) wpre += t;
-        total += t;
-    }
-    if (warp == 0) {
-        const unsigned long long ex = lookback_u64(tile_state, tile, total);
-        if (lane == 0) s_base = ex;
-    }
-
-    uint32_t v = 0, nd = 0, n = 0;
-    uint32_t first_v = 0, first_nd = 0, first_code = 0;
-    __syncthreads();
-    const uint64_t base = s_base + wpre + (inc - cnt);
-    uint32_t seen_clip = 0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) {
-        const uint32_t ch = (w[j >> 2] >> ((j & 3) * 8)) & 0xFFu;
-        const uint32_t d = ch - 48u;
-        if (d < 10u) {
-            v = v * 10u + d;
-            nd++;
-        } else {
-            const uint32_t code = code_of_char(ch);
-            seen_clip |= (code == OP_S) | (code == OP_H);
-            if (n == 0) {
-                first_v = v; first_nd = nd; first_code = code;
+        for (int w = 0; w < TOK_THREADS / 32; w++) {
+            const uint32_t t = s_warp[w];
+            if (w < warp) wpre += t;
+            total += t;
+        }
+        if (warp == 0) {
+            const unsigned long long ex = lookback_u64(tile_state, tile, total);
+            if (lane == 0) s_base = ex;
+        }
+        uint32_t idx = wpre + wex;
+        while (mm) {
+            const uint32_t j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            s_pos[idx + k] = (uint16_t)(tid * 16 + j);
+            k++;
+        }
+        __syncthreads();
+        const uint64_t base = s_base;
+        const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_text);
+        uint32_t seen_clip = 0;
+        for (uint32_t q = tid; q < total; q += TOK_THREADS) {
+            const uint32_t e = s_pos[q];                    // op character at tile byte e
+            const uint32_t a = (e + 8) >> 2, sh = ((e + 8) & 3) * 8;
+            const uint32_t w0 = s_w[a], w1 = s_w[a + 1], w2 = s_w[a + 2];
+            uint32_t lo = __funnelshift_r(w0, w1, sh);      // bytes e-8 .. e-5
+            uint32_t hi = __funnelshift_r(w1, w2, sh);      // bytes e-4 .. e-1
+            uint32_t nd;                                    // digits right before e (capped at 8)
+            if (q > 0) {
+                nd = e - s_pos[q - 1] - 1u;                 // everything between two op characters is digits
+                nd = nd > 8u ? 8u : nd;
+            } else {                                        // first op of the tile: the run may reach into the halo
+                const uint32_t nh = nondigit_bytes(hi), nl = nondigit_bytes(lo);
+                nd = nh ? (__clz(nh) >> 3) : (4u + (nl ? (__clz(nl) >> 3) : 4u));
+            }
+            const uint32_t code = s_lut[s_text[16 + e]];
+            uint32_t len;
+            if (nd == 0u || nd == 8u || code == 15u) {      // rare: empty length, >= 8 digits, bad op character
+                uint32_t ecode = RE_CIGAR_PARSE;
+                len = 0;
+                if (code == 15u || !exact_len(text, tbase + e, len, ecode)) { report(err.tok, tbase + e, ecode); len = 0; }
             } else {
-                uint32_t len = v;
-                if (nd == 0 || nd >= 9 || code == 15u) {
-                    uint32_t e = RE_CIGAR_PARSE;
-                    if (code == 15u || !exact_len(text, g0 + j, len, e)) { report(err.tok, g0 + j, e); len = 0; }
-                }
-                ops[base + n] = (len << 4) | (code & 15u);
+                hi &= (nd >= 4u) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8u * (4u - nd)));
+                len = parse4(hi);
+                if (nd > 4u) len += parse4(lo & (0xFFFFFFFFu << (8u * (8u - nd)))) * 10000u;
             }
-            n++;
-            v = 0; nd = 0;
+            seen_clip |= (code == OP_S) | (code == OP_H);
+            ops[base + q] = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
         }
+        if (seen_clip) atomicOr(misc_flags, 1u);
     }
-    s_tail_v[tid] = v;
-    s_tail_nd[tid] = (n == 0) ? 16u : nd;
-    __syncthreads();
-    if (n > 0) {
-        uint32_t cv = 0, cnd = 0;
-        if (tid > 0) {
-            cv = s_tail_v[tid - 1]; cnd = s_tail_nd[tid - 1];
-        } else {
-            // trailing digit run of the 16 bytes in front of the tile (0xFF pad in front of tile 0)
-            const uint4 pc = ld_nc_v4(text + g0 - 16);
-            const uint32_t pw[4] = {pc.x, pc.y, pc.z, pc.w};
-            bool all = true;
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t d = ((pw[j >> 2] >> ((j & 3) * 8)) & 0xFFu) - 48u;
-                if (d < 10u) { cv = cv * 10u + d; cnd++; }
-                else { cv = 0; cnd = 0; all = false; }
-            }
-            if (all) cnd = 16u;
-        }
-        uint32_t len = cv * c_pow10[first_nd < 10 ? first_nd : 9] + first_v;
-        const uint32_t tnd = cnd + first_nd;
-        if (tnd == 0 || tnd >= 9 || first_code == 15u) {
-            uint32_t e = RE_CIGAR_PARSE;
-            const uint64_t pos = g0 + first_nd;  // byte of the first op character
-            if (first_code == 15u || !exact_len(text, pos, len, e)) { report(err.tok, pos, e); len = 0; }
-        }
-        ops[base] = (len << 4) | (first_code & 15u);
-    }
-    if (seen_clip) atomicOr(misc_flags, 1u);
 }
 
 // K1b: warp per record (r = 0..n_rec inclusive; r == n_rec yields the total)
@@ -395,10 +434,11 @@ __device__ __forceinline__ SegVal lookback_seg(uint32_t* state, ScanPayload* agg
     return acc;
 }
 
-__global__ void __launch_bounds__(SMP_THREADS)
+__global__ void __launch_bounds__(SMP_THREADS, 3)
 k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
           Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket) {
-    __shared__ uint32_t s_ops[SMP_THREADS * 33];
+    __shared__ uint32_t s_ops[SMP_THREADS * (SAMPLE + 1)];
+    __shared__ uint32_t s_acc[9 * SMP_THREADS];
     __shared__ SegVal s_warp[SMP_THREADS / 32];
     __shared__ SegVal s_blk;
     __shared__ unsigned int s_b;
@@ -415,7 +455,7 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
     for (int i = 0; i < (int)SAMPLE; i++) {
         const uint32_t idx = (uint32_t)i * SMP_THREADS + tid;
         const uint64_t g = op0 + idx;
-        s_ops[(idx >> 5) * 33 + (idx & 31)] = (g < n_ops) ? ops[g] : 0u;
+        s_ops[(idx >> SAMPLE_LOG2) * (SAMPLE + 1) + (idx & (SAMPLE - 1))] = (g < n_ops) ? ops[g] : 0u;
     }
     __syncthreads();
 
@@ -423,23 +463,36 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
     const uint64_t first = chunk << SAMPLE_LOG2;
     int nvalid = 0;
     if (first < n_ops) nvalid = (n_ops - first) < SAMPLE ? (int)(n_ops - first) : (int)SAMPLE;
-    const uint32_t h = nvalid ? heads[chunk] : 0u;
+    const uint32_t h = nvalid ? (uint32_t)((heads[first >> 5] >> (first & 31u)) & (uint32_t)((1ull << SAMPLE) - 1ull)) : 0u;
     uint32_t prev_code = 99u;
     if (nvalid) {
-        if (tid > 0) prev_code = op_code(s_ops[(tid - 1) * 33 + 31]);
+        if (tid > 0) prev_code = op_code(s_ops[(tid - 1) * (SAMPLE + 1) + (SAMPLE - 1)]);
         else if (first > 0) prev_code = op_code(ops[first - 1]);
     }
     SegVal mine = seg_identity();
+    ClassAcc acc;
+    acc.sum = s_acc + tid; acc.stride = SMP_THREADS;
+    acc_reset(acc);
+    uint32_t slowc = 0;
+    const uint32_t* my_ops = s_ops + tid * (SAMPLE + 1);
     for (int j = 0; j < nvalid; j++) {
-        const uint32_t w = s_ops[tid * 33 + j];
+        const uint32_t w = my_ops[j];
         const bool head = (h >> j) & 1u;
-        if (head) mine.c = ctr_zero();
+        if (head) { acc_reset(acc); slowc = 0; }  // a record starts here: the span before it is not part of this aggregate
         const uint32_t code = op_code(w);
-        const uint32_t slow = (op_len(w) == 0u) | ((!head) & (code == prev_code));
-        ctr_add_op(mine.c, w);
-        mine.c.aux += slow;
+        slowc += (op_len(w) == 0u) | ((!head) & (code == prev_code));
+        acc_add_op(acc, w);
         prev_code = code;
     }
+    if (acc.big >= ACC_BIG) {  // huge ops: a class sum may have wrapped, redo the chunk with exact counters
+        int j0 = 0;
+        for (int j = 0; j < nvalid; j++)
+            if ((h >> j) & 1u) j0 = j;
+        for (int j = j0; j < nvalid; j++) ctr_add_op(mine.c, my_ops[j]);
+    } else {
+        acc_flush(acc, mine.c);
+    }
+    mine.c.aux = (mine.c.aux & AUX_OVF) | (slowc & AUX_CNT);
     mine.flag = (h != 0u);
 
     // block-level segmented scan of the per-chunk aggregates
@@ -475,10 +528,10 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
 // ------------------------------------------------------------------------------------------------
 // K3  per-record preparation
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Ctr ctr_range(const OpsView& v, const RecInfo& r, uint64_t a, uint64_t b) {  // ops [a, b), b > a
-    Ctr hi = ctr_before(v, r, b - 1);
+__device__ __forceinline__ Ctr ctr_range(const OpsView& v, const RecInfo& r, uint64_t a, uint64_t b, ClassAcc& acc) {  // ops [a, b), b > a
+    Ctr hi = ctr_before(v, r, b - 1, acc);
     ctr_add_op(hi, v.ops[b - 1]);
-    const Ctr lo = ctr_before(v, r, a);
+    const Ctr lo = ctr_before(v, r, a, acc);
     Ctr d = hi;
     ctr_sub(d, lo);
     d.aux = hi.aux;  // flags/slow count of the whole prefix (conservative)
@@ -500,9 +553,12 @@ __global__ void __launch_bounds__(128)
 k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uint32_t* __restrict__ ops,
            const Ctr* __restrict__ samples, WinView win, RecInfo* __restrict__ recs, uint32_t* __restrict__ pair_cnt, StatsDev st,
            ErrSlots err) {
+    __shared__ uint32_t s_acc[9 * 128];
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= in.n_rec) return;
     OpsView v{ops, samples};
+    ClassAcc acc;
+    acc.sum = s_acc + threadIdx.x; acc.stride = 128;
     RecInfo ri;
     ri.op_first = op_off[r]; ri.op_end = op_off[r + 1];
     ri.eo0 = ri.op_first; ri.eo1 = ri.op_end;
@@ -517,7 +573,7 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
 
     // integrity at load (paf.rs:70): spans of the UNSTRIPPED record against the full CIGAR
     Ctr full = ctr_zero();
-    if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end);
+    if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end, acc);
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
     if ((uint64_t)full.T != ri.t_en - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
     if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
@@ -542,7 +598,7 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
         recs[r] = ri;
         return;
     }
-    ri.tot = (ri.eo0 == ri.op_first && ri.eo1 == ri.op_end) ? full : ctr_range(v, ri, ri.eo0, ri.eo1);
+    ri.tot = (ri.eo0 == ri.op_first && ri.eo1 == ri.op_end) ? full : ctr_range(v, ri, ri.eo0, ri.eo1, acc);
 
     // join: windows of this contig with en > t_st && st < t_en (paf.rs:622-627, on stripped coordinates)
     uint32_t cnt = 0;
@@ -666,8 +722,11 @@ __global__ void __launch_bounds__(128)
 k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
        const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
        const uint64_t* __restrict__ names_off, int policy, PairRes* __restrict__ res, uint32_t* __restrict__ line_len, ErrSlots err) {
+    __shared__ uint32_t s_acc[9 * 128];
     const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
+    ClassAcc acc;
+    acc.sum = s_acc + threadIdx.x; acc.stride = 128;
     const uint32_t k = rank_of_pair(pair_off, n_rec, p);
     const uint32_t r = rec_order[k];
     const RecInfo ri = recs[r];
@@ -676,21 +735,16 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     const uint64_t w_st = win.st[w], w_en = win.en[w];
     PairRes pr;
     uint32_t len = 0;
-    if (ri.t_en > w_st && ri.t_st < w_en) {  // nested windows can make the [wlo,whi) range a superset
-        OpsView v{ops, samples};
-        const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, pr);
-        if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
-        if (pr.kind != PK_DROP) {
-            const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
-            const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
-            const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
-            len = line_bytes(ri, pr, qn, tn, idl);
-        }
-    } else {
-        pr.kind = PK_DROP; pr.pad = 0;
-        pr.t_st = pr.t_en = pr.q_st = pr.q_en = pr.nmatch = pr.aln_len = pr.si = pr.ei = 0;
-        pr.s_len = pr.e_len = pr.cg_bytes = 0;
-        pr.equal = pr.diff = pr.ins = pr.del = pr.ins_ev = pr.del_ev = pr.matches = 0;
+    OpsView v{ops, samples};
+    const bool overlaps = ri.t_en > w_st && ri.t_st < w_en;  // the brute-force / nested-window candidates can be a superset
+    const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, overlaps, pr, acc);
+    __syncwarp();
+    if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
+    if (pr.kind != PK_DROP) {
+        const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
+        const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
+        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+        len = line_bytes(ri, pr, qn, tn, idl);
     }
     res[p] = pr;
     line_len[p] = len;
@@ -805,10 +859,31 @@ k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t* __rest
 // ------------------------------------------------------------------------------------------------
 template <class P>
 __device__ __forceinline__ P put_u32(P p, uint32_t v) {
+    if (v < 1000u) {  // CIGAR lengths are mostly 1-3 digits: straight-line code, no loop
+        if (v < 10u) { p[0] = (uint8_t)('0' + v); return p + 1; }
+        const uint32_t h = (v * 41u) >> 12;    // v / 100 for v < 1000
+        const uint32_t r = v - h * 100u;
+        const uint32_t t = (r * 103u) >> 10;   // r / 10 for r < 100
+        if (v < 100u) { p[0] = (uint8_t)('0' + t); p[1] = (uint8_t)('0' + (r - t * 10u)); return p + 2; }
+        p[0] = (uint8_t)('0' + h); p[1] = (uint8_t)('0' + t); p[2] = (uint8_t)('0' + (r - t * 10u));
+        return p + 3;
+    }
     const uint32_t nd = ndigits32(v);
-    for (int i = (int)nd - 1; i >= 0; i--) {
-        p[i] = (uint8_t)('0' + v % 10u);
-        v /= 10u;
+    int i = (int)nd;
+    while (v >= 100u) {  // two digits per division
+        const uint32_t q = v / 100u, r = v - q * 100u;
+        const uint32_t d1 = (r * 103u) >> 10;  // r / 10 for r < 100
+        p[i - 1] = (uint8_t)('0' + (r - d1 * 10u));
+        p[i - 2] = (uint8_t)('0' + d1);
+        i -= 2;
+        v = q;
+    }
+    if (v >= 10u) {
+        const uint32_t d1 = (v * 103u) >> 10;
+        p[i - 1] = (uint8_t)('0' + (v - d1 * 10u));
+        p[i - 2] = (uint8_t)('0' + d1);
+    } else {
+        p[i - 1] = (uint8_t)('0' + v);
     }
     return p + nd;
 }

@@ -77,6 +77,7 @@ struct rb_batch {
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
     bool have_lift = false, have_stats = false, with_stats = false;
+    uint32_t want = 0;
     uint64_t stats_n = 0;
 };
 
@@ -590,7 +591,7 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
     return RB_OK;
 }
 
-int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, int with_stats, rb_summary* summary) {
+int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int with_stats, rb_summary* summary) {
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
     cudaSetDevice(ctx->device);
@@ -665,19 +666,23 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, int with_stats, rb_s
     if (rc != RB_OK) { flush_times(ctx); return rc; }
     const uint64_t out_bytes = hs[5], n_out = hs[6];
 
-    CU(b->out_text.ensure(out_bytes + 64));
-    CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
-    CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
+    b->want = want;
+    if (want & RB_WANT_TEXT) {
+        CU(b->out_text.ensure(out_bytes + 64));
+        CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
+    }
+    if (want & RB_WANT_NUMERIC) CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
     b->with_stats = with_stats != 0;
     if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
     {
         KScope k(ctx, "k_serialise");
         launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
                          win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(), b->pair_res.as<PairRes>(),
-                         b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), b->out_text.as<uint8_t>(),
-                         b->out_line_off.as<uint64_t>(), num_view(b, n_out), with_stats ? stats_view(b, n_out) : StatsDev{}, s);
+                         b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
+                         (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
+                         (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{}, s);
     }
-    if (P == 0) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
+    if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
     CU(cudaGetLastError());
     if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
     b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
@@ -715,6 +720,7 @@ int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out*
     if (!ctx || !b || !out) return RB_ERR_BAD_ARG;
     if (!b->have_lift) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover has not run on this batch");
     if (st && !b->with_stats) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover ran without stats");
+    if (want & ~b->want) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover did not materialise the requested outputs");
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     memset(out, 0, sizeof *out);
@@ -769,7 +775,7 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     if (!ctx->scratch) ctx->scratch = new rb_batch();
     int rc = upload_into(ctx, ctx->scratch, recs, wins);
     if (rc != RB_OK) return rc;
-    rc = rb_batch_liftover(ctx, ctx->scratch, policy, stats != nullptr, nullptr);
+    rc = rb_batch_liftover(ctx, ctx->scratch, policy, want, stats != nullptr, nullptr);
     if (rc != RB_OK) return rc;
     return rb_batch_download_lift(ctx, ctx->scratch, want, out, stats);
 }

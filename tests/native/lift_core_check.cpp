@@ -103,6 +103,9 @@ int main(int argc, char** argv) {
         }
     }
     OpsView view{ops.data(), samples.data()};
+    uint32_t acc_mem[16];
+    ClassAcc acc;
+    acc.sum = acc_mem; acc.stride = 1;
 
     long n_pairs = 0, n_trim = 0, n_early = 0, n_drop = 0, n_abort = 0, n_slow = 0, n_fail = 0;
     for (size_t r = 0; r < recs.size(); r++) {
@@ -133,9 +136,9 @@ int main(int argc, char** argv) {
             if (op_len(ops[k]) == 0) ri.flags |= RF_SLOW;
             if (k > ri.op_first && op_code(ops[k]) == op_code(ops[k - 1])) ri.flags |= RF_SLOW;
         }
-        ri.tot = ctr_before(view, ri, ri.eo1 - 1);
+        ri.tot = ctr_before(view, ri, ri.eo1 - 1, acc);
         ctr_add_op(ri.tot, ops[ri.eo1 - 1]);
-        Ctr lead = ctr_before(view, ri, ri.eo0);
+        Ctr lead = ctr_before(view, ri, ri.eo0, acc);
         ctr_sub(ri.tot, lead);
         if (ri.flags & RF_SLOW) n_slow++;
         std::string rec_id;
@@ -168,7 +171,7 @@ int main(int argc, char** argv) {
                 try { some = orc::trim_paf_rec_to_rgn(rg, orec, policy, ot); }
                 catch (const orc::Abort&) { opanic = true; }
                 PairRes pr;
-                uint32_t lerr = lift_pair(view, ri, a, b, policy, pr);
+                uint32_t lerr = lift_pair(view, ri, a, b, policy, true, pr, acc);
                 if ((lerr != LIFT_OK) != opanic) {
                     fprintf(stderr, "FAIL panic mismatch rec %zu win %lu-%lu lerr=%u opanic=%d\n%s\n", r, a, b, lerr, (int)opanic, tr.line.c_str());
                     n_fail++;

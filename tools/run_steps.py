@@ -23,7 +23,7 @@ wins = paf.tiling_windows(args.window)
 ctx = capi.Context(0)
 b = ctx.upload(paf, None if args.stats_only else wins)
 for i in range(args.warmup + args.steps):
-    s = ctx.batch_stats(b) if args.stats_only else ctx.batch_liftover(b, with_stats=True)
+    s = ctx.batch_stats(b) if args.stats_only else ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
 print(s)
 ctx.batch_free(b)
 ctx.close()
