@@ -17,9 +17,17 @@
 
 namespace rb {
 
+// Read access to ops / samples.  A thread block may stage a window of both in shared memory
+// (s_ops / s_smp cover ops [so_lo, so_hi) and chunks [sc_lo, sc_hi)); everything else comes from HBM.
 struct OpsView {
     const uint32_t* ops;
     const Ctr* samples;
+    const uint32_t* s_ops = nullptr;
+    const Ctr* s_smp = nullptr;
+    uint64_t so_lo = 0, so_hi = 0, sc_lo = 0, sc_hi = 0;
+    RB_HD uint32_t op(uint64_t k) const { return (k - so_lo < so_hi - so_lo) ? s_ops[k - so_lo] : ops[k]; }
+    RB_HD Ctr smp(uint64_t c) const { return (c - sc_lo < sc_hi - sc_lo) ? s_smp[c - sc_lo] : samples[c]; }
+    RB_HD uint32_t smp_T(uint64_t c) const { return (c - sc_lo < sc_hi - sc_lo) ? s_smp[c - sc_lo].T : samples[c].T; }
 };
 
 enum : int { POLICY_RIGHTMOST = 0, POLICY_EARLY_EXIT = 1 };
@@ -30,13 +38,13 @@ RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k, ClassAcc& a
     const uint64_t base = (k >> SAMPLE_LOG2) << SAMPLE_LOG2;
     Ctr c;
     uint64_t j;
-    if (base > r.op_first) { c = v.samples[k >> SAMPLE_LOG2]; j = base; }
+    if (base > r.op_first) { c = v.smp(k >> SAMPLE_LOG2); j = base; }
     else { c = ctr_zero(); j = r.op_first; }
     acc_reset(acc);
     const uint64_t j0 = j;
-    for (; j < k; j++) acc_add_op(acc, v.ops[j]);
+    for (; j < k; j++) acc_add_op(acc, v.op(j));
     if (acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
-        for (j = j0; j < k; j++) ctr_add_op(c, v.ops[j]);
+        for (j = j0; j < k; j++) ctr_add_op(c, v.op(j));
         return c;
     }
     acc_flush(acc, c);
@@ -61,23 +69,28 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     uint32_t n = 0, j = 0;
     if (live && r.op_end > r.op_first) {
         uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
+        // narrow to the staged chunk window when the answer provably lies inside it (all probes then hit smem)
+        if (v.sc_hi > v.sc_lo) {
+            const uint64_t a = v.sc_lo, z = v.sc_hi - 1;
+            if (a > lo && a <= hi && v.smp_T(a) <= p) lo = a;
+            if (z > lo && z <= hi && v.smp_T(z) > p) hi = z - 1;
+        }
         while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
             const uint64_t mid = (lo + hi + 1) >> 1;
-            if (v.samples[mid].T <= p) lo = mid;
+            if (v.smp_T(mid) <= p) lo = mid;
             else hi = mid - 1;
         }
         k0 = lo << SAMPLE_LOG2;
-        if (k0 > r.op_first) c = v.samples[lo];
+        if (k0 > r.op_first) c = v.smp(lo);
         else k0 = r.op_first;
         const uint64_t left = r.op_end - k0;
         n = left > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)left;
     }
     RB_CONVERGE();
     const uint32_t rel = p - c.T;  // target offset relative to the chunk start
-    const uint32_t* q = v.ops + k0;
     acc_reset(acc);
     for (; j < n; j++) {
-        const uint32_t w = q[j];
+        const uint32_t w = v.op(k0 + j);
         const uint32_t L = op_len(w);
         if (is_ref(op_code(w)) && L > 0 && rel - acc.T < L) { found = true; break; }
         acc_add_op(acc, w);
@@ -85,7 +98,7 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     RB_CONVERGE();
     if (found) {
         if (acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
-            for (uint32_t t = 0; t < j; t++) ctr_add_op(c, q[t]);
+            for (uint32_t t = 0; t < j; t++) ctr_add_op(c, v.op(k0 + t));
         } else {
             acc_flush(acc, c);
         }
@@ -111,10 +124,10 @@ RB_HD uint32_t early_exit_probe(uint32_t n, uint32_t ca, uint32_t cb) {
 // Merge walk over the trimmed op range (collapse_long_cigar semantics, paf.rs:602-620): zero-length
 // ops vanish, adjacent same-class ops fuse.  `emit(len, code)` is called once per printed op.
 template <class Emit>
-RB_HD void merged_walk(const uint32_t* ops, uint64_t si, uint64_t ei, uint32_t s_len, uint32_t e_len, Emit&& emit) {
+RB_HD void merged_walk(const OpsView& v, uint64_t si, uint64_t ei, uint32_t s_len, uint32_t e_len, Emit&& emit) {
     uint32_t prev = 0xFFFFFFFFu, run = 0;
     for (uint64_t k = si; k <= ei; k++) {
-        const uint32_t w = ops[k];
+        const uint32_t w = v.op(k);
         const uint32_t code = op_code(w);
         const uint32_t L = (k == si) ? s_len : (k == ei ? e_len : op_len(w));
         if (L == 0) continue;
@@ -167,19 +180,19 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
     if (!find_op(v, r, live, ps, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
     uint64_t si = 0; uint32_t so = 0; Ctr cs = ctr_zero();
     if (live) {
-        const uint32_t w = v.ops[i];
+        const uint32_t w = v.op(i);
         const uint32_t L = op_len(w), code = op_code(w);
         bool slide = false;
         if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
             uint64_t k2 = i + 1;
-            while (k2 < r.eo1 && op_len(v.ops[k2]) == 0) k2++;
-            if (k2 < r.eo1 && !is_ref(op_code(v.ops[k2]))) slide = true;
+            while (k2 < r.eo1 && op_len(v.op(k2)) == 0) k2++;
+            if (k2 < r.eo1 && !is_ref(op_code(v.op(k2)))) slide = true;
         }
         if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
             const uint32_t ca = before.A + o - r.a_lead;
             uint32_t extra = 0;
             for (uint64_t k = i + 1; k < r.eo1; k++) {
-                const uint32_t w2 = v.ops[k];
+                const uint32_t w2 = v.op(k);
                 if (op_len(w2) == 0) continue;
                 if (is_ref(op_code(w2))) break;
                 extra += op_len(w2);
@@ -195,7 +208,7 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
             uint64_t k = i + 1;
             bool found = false;
             for (; k < r.eo1; k++) {
-                const uint32_t w2 = v.ops[k];
+                const uint32_t w2 = v.op(k);
                 if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
                 ctr_add_op(c, w2);
             }
@@ -208,7 +221,7 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
     // ---- END: tpos_to_idx_match(t_en - 1, search_right = false) ----
     if (!find_op(v, r, live, pe, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
     if (live) {
-        const uint32_t w = v.ops[i];
+        const uint32_t w = v.op(i);
         const uint32_t code = op_code(w);
         uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
         if (is_match(code)) {
@@ -220,13 +233,13 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
             bool found = false;
             while (k > r.eo0) {
                 k--;
-                const uint32_t w2 = v.ops[k];
+                const uint32_t w2 = v.op(k);
                 ctr_sub_op(c, w2);
                 if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
             }
             if (!found) live = false;  // slid to column 0 which is not a match column -> start > end
-            ei = k; eo = found ? op_len(v.ops[k]) - 1 : 0; ce = c; txt_before_ei = c.TXT;
-            if (found) ctr_add_bases(ce, op_code(v.ops[k]), eo + 1);
+            ei = k; eo = found ? op_len(v.op(k)) - 1 : 0; ce = c; txt_before_ei = c.TXT;
+            if (found) ctr_add_bases(ce, op_code(v.op(k)), eo + 1);
         }
         if (live && cs.A >= ce.A) live = false;  // start column > end column: window lies inside an indel (Q7)
         if (live) {
@@ -246,7 +259,7 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
             out.aln_len = d.A;
             fill_stats(out, d);
             out.si = si; out.ei = ei;
-            const uint32_t L_si = op_len(v.ops[si]);
+            const uint32_t L_si = op_len(v.op(si));
             if (si == ei) {
                 out.s_len = eo - so + 1; out.e_len = 0;
                 out.cg_bytes = ndigits32(out.s_len) + 1;
@@ -256,7 +269,7 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
             }
             if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
                 uint32_t bytes = 0, iev = 0, dev = 0;
-                merged_walk(v.ops, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
+                merged_walk(v, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
                     bytes += ndigits32(len) + 1;
                     iev += (c2 == OP_I);
                     dev += (c2 == OP_D);

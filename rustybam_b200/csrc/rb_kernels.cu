@@ -530,7 +530,7 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ Ctr ctr_range(const OpsView& v, const RecInfo& r, uint64_t a, uint64_t b, ClassAcc& acc) {  // ops [a, b), b > a
     Ctr hi = ctr_before(v, r, b - 1, acc);
-    ctr_add_op(hi, v.ops[b - 1]);
+    ctr_add_op(hi, v.op(b - 1));
     const Ctr lo = ctr_before(v, r, a, acc);
     Ctr d = hi;
     ctr_sub(d, lo);
@@ -556,7 +556,8 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     __shared__ uint32_t s_acc[9 * 128];
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= in.n_rec) return;
-    OpsView v{ops, samples};
+    OpsView v;
+    v.ops = ops; v.samples = samples;
     ClassAcc acc;
     acc.sum = s_acc + threadIdx.x; acc.stride = 128;
     RecInfo ri;
@@ -735,7 +736,8 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     const uint64_t w_st = win.st[w], w_en = win.en[w];
     PairRes pr;
     uint32_t len = 0;
-    OpsView v{ops, samples};
+    OpsView v;
+    v.ops = ops; v.samples = samples;
     const bool overlaps = ri.t_en > w_st && ri.t_st < w_en;  // the brute-force / nested-window candidates can be a superset
     const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, overlaps, pr, acc);
     __syncwarp();
@@ -911,7 +913,7 @@ __device__ __forceinline__ P put_op(P p, uint32_t len, uint32_t code) {
 
 struct SerArgs {
     const RecInfo* recs;
-    const uint32_t* ops;
+    OpsView v;
     WinView win;
     const uint64_t* names_off;
     const uint8_t* names;
@@ -919,11 +921,11 @@ struct SerArgs {
 
 // "_TO.<leading ops>.<trailing ops, last first>" (paf.rs:726-732)
 template <class P>
-__device__ __forceinline__ P put_strip_id(P p, const RecInfo& ri, const uint32_t* __restrict__ ops) {
+__device__ __forceinline__ P put_strip_id(P p, const RecInfo& ri, const OpsView& v) {
     *p++ = '_'; *p++ = 'T'; *p++ = 'O'; *p++ = '.';
-    for (uint64_t k = ri.op_first; k < ri.eo0; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
+    for (uint64_t k = ri.op_first; k < ri.eo0; k++) p = put_op(p, op_len(v.op(k)), op_code(v.op(k)));
     *p++ = '.';
-    for (uint64_t k = ri.op_end; k > ri.eo1; k--) p = put_op(p, op_len(ops[k - 1]), op_code(ops[k - 1]));
+    for (uint64_t k = ri.op_end; k > ri.eo1; k--) p = put_op(p, op_len(v.op(k - 1)), op_code(v.op(k - 1)));
     return p;
 }
 
@@ -945,7 +947,7 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     *p++ = '\t'; p = put_u64(p, ri.mapq);
     *p++ = '\t'; *p++ = 'i'; *p++ = 'd'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
     if (pr.kind == PK_EARLY) {
-        if (ri.flags & RF_STRIPPED) p = put_strip_id(p, ri, a.ops);
+        if (ri.flags & RF_STRIPPED) p = put_strip_id(p, ri, a.v);
     } else {
         p = put_bytes(p, a.win.ids + a.win.ids_off[w], (uint32_t)(a.win.ids_off[w + 1] - a.win.ids_off[w]));
     }
@@ -956,15 +958,15 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
 // trimmed / early-return CIGAR text, sequential
 template <class P>
 __device__ __forceinline__ P put_cigar_seq(P p, const SerArgs& a, const RecInfo& ri, const PairRes& pr) {
-    const uint32_t* __restrict__ ops = a.ops;
+    const OpsView& v = a.v;
     if (pr.kind == PK_EARLY) {
-        for (uint64_t k = pr.si; k <= pr.ei; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
+        for (uint64_t k = pr.si; k <= pr.ei; k++) { const uint32_t w = v.op(k); p = put_op(p, op_len(w), op_code(w)); }
     } else if (ri.flags & RF_SLOW) {
-        merged_walk(ops, pr.si, pr.ei, pr.s_len, pr.e_len, [&](uint32_t len, uint32_t code) { p = put_op(p, len, code); });
+        merged_walk(v, pr.si, pr.ei, pr.s_len, pr.e_len, [&](uint32_t len, uint32_t code) { p = put_op(p, len, code); });
     } else {
-        p = put_op(p, pr.s_len, op_code(ops[pr.si]));
-        for (uint64_t k = pr.si + 1; k < pr.ei; k++) p = put_op(p, op_len(ops[k]), op_code(ops[k]));
-        if (pr.ei > pr.si) p = put_op(p, pr.e_len, op_code(ops[pr.ei]));
+        p = put_op(p, pr.s_len, op_code(v.op(pr.si)));
+        for (uint64_t k = pr.si + 1; k < pr.ei; k++) { const uint32_t w = v.op(k); p = put_op(p, op_len(w), op_code(w)); }
+        if (pr.ei > pr.si) p = put_op(p, pr.e_len, op_code(v.op(pr.ei)));
     }
     return p;
 }
@@ -1062,7 +1064,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
                 const uint64_t kk = k0 + lane;
                 uint32_t len = 0, code = 0, nb = 0;
                 if (kk <= lp.ei) {
-                    const uint32_t ow = a.ops[kk];
+                    const uint32_t ow = a.v.op(kk);
                     code = op_code(ow);
                     len = op_len(ow);
                     if (lp.kind == PK_TRIM) {
@@ -1144,7 +1146,9 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
         cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
         attr_set = true;
     }
-    SerArgs a{recs, ops, win, names_off, names};
+    OpsView view;
+    view.ops = ops; view.samples = nullptr;
+    SerArgs a{recs, view, win, names_off, names};
     k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
         n_pairs, pair_off, rec_order, n_rec, a, res, line_off, out_idx, out_text, out_line_off, num, st);
 }

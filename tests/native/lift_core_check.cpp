@@ -102,7 +102,8 @@ int main(int argc, char** argv) {
             ctr_add_op(run, ops[k]);
         }
     }
-    OpsView view{ops.data(), samples.data()};
+    OpsView view;
+    view.ops = ops.data(); view.samples = samples.data();
     uint32_t acc_mem[16];
     ClassAcc acc;
     acc.sum = acc_mem; acc.stride = 1;
@@ -193,7 +194,7 @@ int main(int argc, char** argv) {
                     n_trim++;
                     id = rg.id;
                     if (ri.flags & RF_SLOW) {
-                        merged_walk(ops.data(), pr.si, pr.ei, pr.s_len, pr.e_len,
+                        merged_walk(view, pr.si, pr.ei, pr.s_len, pr.e_len,
                                     [&](uint32_t len, uint32_t c) { cg += std::to_string(len) + OPC[c]; });
                     } else if (pr.si == pr.ei) {
                         cg = std::to_string(pr.s_len) + OPC[op_code(ops[pr.si])];
