@@ -57,7 +57,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -206,7 +206,6 @@ def main():
         step_ms.append(e0.elapsed_time(e1))
     barrier()
     wall_resident = time.perf_counter() - wall0
-    clocks = sampler.stop()
     ms_resident = sum(step_ms) / len(step_ms)
 
     # ---- per-kernel times for the roofline of the dominant kernel (separate pass, events around each launch) ----
@@ -234,6 +233,7 @@ def main():
         e1.synchronize()
         e2e_ms.append(e0.elapsed_time(e1))
     barrier()
+    clocks = sampler.stop()  # sampled across the resident, per-kernel and end-to-end timed loops
     ms_e2e = sum(e2e_ms) / len(e2e_ms)
 
     n_out, n_pairs, n_ops = summ["n_out"], summ["n_pairs"], summ["n_ops"]

@@ -1,0 +1,135 @@
+"""Full-size checks of the CUDA path (BASELINE.json configs C2-C4 shapes): exact parity against the
+oracle where the oracle finishes in seconds (2 % genome scale), and size-independent properties at
+the full ~3.1 Gbp / ~50 M-op scale (independent numpy tokeniser, conservation of matched bases over
+tiling windows, idempotence of lifting the lifted rows, offsets/sortedness)."""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import orc
+from rustybam_b200 import bamstats, capi, hostlib
+from rustybam_b200.paf import Paf
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def full():
+    return hostlib.HostPaf.synth(scale=1.0)
+
+
+@pytest.mark.parametrize("width", [1000, 100_000])
+def test_synth_2pct_exact_parity(ctx, width):
+    paf = hostlib.HostPaf.synth(scale=0.02)
+    wins = paf.tiling_windows(width)
+    res = ctx.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    paf_text, bed_text = paf.text(), paf.tiling_bed_text(width)
+    want = orc.run_liftover(paf_text, bed_text, threads=8)
+    assert res["paf_text"] == want
+    out = Paf.from_text(res["paf_text"])
+    st = (bamstats.print_cigar_stats_header() + bamstats.stats_rows(out, res["stats"])).encode()
+    assert st == orc.run_stats(want)
+    assert bamstats.run_stats(ctx, paf_text) == orc.run_stats(paf_text)
+
+
+def numpy_record_stats(paf):
+    """Independent tokeniser: per-record (=, X, I, D bases; I, D events) straight from the CIGAR bytes."""
+    n = paf.n_rec
+    off = np.ctypeslib.as_array(paf.c.cigar_off, shape=(n + 1,)).astype(np.int64)
+    cig = np.ctypeslib.as_array(paf.c.cigar, shape=(paf.cigar_nbytes,))
+    out = np.zeros((n, 6), dtype=np.int64)
+    r0 = 0
+    while r0 < n:  # slices of ~32 MB of text, aligned to record boundaries
+        r1 = r0 + 1
+        while r1 < n and off[r1 + 1] - off[r0] < (32 << 20):
+            r1 += 1
+        b = cig[off[r0]:off[r1]]
+        is_op = (b < 48) | (b > 57)
+        idx = np.nonzero(is_op)[0]
+        before = np.cumsum(is_op) - is_op          # ops strictly before each byte
+        nxt = idx[np.minimum(before, len(idx) - 1)]  # position of the op character that ends this byte's number
+        expo = (nxt - np.arange(len(b)) - 1).astype(np.int64)
+        digit = np.where(is_op, 0, b - 48).astype(np.float64)
+        lens = np.bincount(before[~is_op], weights=(digit * np.power(10.0, np.maximum(expo, 0)))[~is_op], minlength=len(idx))
+        lens = np.rint(lens).astype(np.int64)
+        codes = b[idx]
+        rec_of_op = np.searchsorted(off[r0:r1 + 1] - off[r0], idx, side="right") - 1
+        for col, ch in enumerate(b"=XID"):
+            out[r0:r1, col] = np.bincount(rec_of_op[codes == ch], weights=lens[codes == ch], minlength=r1 - r0)
+        out[r0:r1, 4] = np.bincount(rec_of_op[codes == ord("I")], minlength=r1 - r0)
+        out[r0:r1, 5] = np.bincount(rec_of_op[codes == ord("D")], minlength=r1 - r0)
+        r0 = r1
+    return out
+
+
+def test_full_scale_stats_vs_numpy_tokeniser(ctx, full):
+    st = ctx.stats(full)
+    ref = numpy_record_stats(full)
+    assert st["n"] == full.n_rec
+    assert (st["equal"].astype(np.int64) == ref[:, 0]).all()
+    assert (st["diff"].astype(np.int64) == ref[:, 1]).all()
+    assert (st["ins"].astype(np.int64) == ref[:, 2]).all()
+    assert (st["del"].astype(np.int64) == ref[:, 3]).all()
+    assert (st["ins_events"].astype(np.int64) == ref[:, 4]).all()
+    assert (st["del_events"].astype(np.int64) == ref[:, 5]).all()
+    # bamstats.rs:138-142 recomputed in numpy f32: 0 ULP
+    eq, tot = st["equal"].astype(np.float32), (st["equal"] + st["diff"] + st["del"] + st["ins"]).astype(np.float32)
+    assert (st["id_by_all"] == (np.float32(100.0) * eq) / tot).all()
+
+
+def test_full_scale_liftover_properties(ctx, full):
+    wins = full.tiling_windows(1000)
+    res = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    n_out, text, off = res["n_out"], res["paf_text"], res["line_off"]
+    assert n_out > 3_000_000 and res["n_pairs"] >= n_out
+    assert off[0] == 0 and off[-1] == len(text) and (np.diff(off.astype(np.int64)) > 0).all()
+    ends = np.frombuffer(text, dtype=np.uint8)[off[1:].astype(np.int64) - 1]
+    assert (ends == 10).all()
+    # conservation: tiling windows partition every record's match columns; the only bases that may go missing
+    # are the ones the reference itself loses (Q2: a window that starts on the last base before an insertion
+    # slides past the insertion, and the previous window ended one base earlier) -> at most one per row
+    rec_stats = ctx.stats(full)
+    for key in ("equal", "diff"):
+        lost = int(rec_stats[key].astype(np.int64).sum()) - int(res["stats"][key].astype(np.int64).sum())
+        assert 0 <= lost <= n_out // 100, (key, lost)
+    # rows are in emission order: record-major (file order inside a contig), window-minor
+    assert (np.diff(res["rec_idx"].astype(np.int64)) >= 0).all()
+    # every row lies inside its window and the numeric mirror matches the text (sample of rows)
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, n_out, 2000):
+        f = text[int(off[i]):int(off[i + 1]) - 1].split(b"\t")
+        assert (int(f[2]), int(f[3]), int(f[7]), int(f[8]), int(f[9]), int(f[10])) == (
+            int(res["q_st"][i]), int(res["q_en"][i]), int(res["t_st"][i]), int(res["t_en"][i]), int(res["nmatch"][i]), int(res["aln_len"][i]))
+        w = int(res["win_idx"][i])
+        assert f[12] == b"id:Z:" + f[5] + b":" + str(int(f[7]) // 1000 * 1000 + 1).encode() + b"-" + f[12].split(b"-")[-1]
+    # idempotence: lifting the lifted rows of one contig over the same windows returns them unchanged
+    lo, hi = int(off[0]), int(off[200_000])
+    sub = hostlib.HostPaf.from_text(text[lo:hi])
+    again = ctx.liftover(sub, sub.windows_from_bed_text(full.tiling_bed_text(1000)), want=capi.WANT_TEXT, stats=False)
+    assert again["paf_text"] == text[lo:hi]
+
+
+def test_rb_cli_matches_oracle(tmp_path):
+    rb = os.path.join(ROOT, "rustybam_b200", "rb")
+    paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
+    bed = os.path.join(ROOT, "tests", "golden", "asm_small.bed")
+    lifted = subprocess.run([rb, "-t", "4", "liftover", "--bed", bed, paf_gz], capture_output=True, check=True).stdout
+    assert lifted == orc.run_liftover(orc.golden_paf(), orc.golden_bed())
+    st = subprocess.run([rb, "stats", "--paf", "-"], input=lifted, capture_output=True, check=True).stdout
+    assert st == orc.run_stats(lifted)
+    bad = tmp_path / "bad.paf"
+    bad.write_bytes(b"Q\t10\t0\t8\t+\tT\t20\t0\t8\t0\t0\t60\tcg:Z:3D5=\n")
+    r = subprocess.run([rb, "liftover", "--bed", bed, str(bad)], capture_output=True)
+    assert r.returncode == 101 and r.stdout == b""
