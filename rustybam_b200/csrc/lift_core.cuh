@@ -146,27 +146,144 @@ RB_HD void fill_stats(PairRes& out, const Ctr& d) {
     out.ins = d.I; out.del = d.D; out.ins_ev = d.IEV; out.del_ev = d.DEV;
 }
 
-// One pair.  Returns LIFT_OK (out.kind says DROP / TRIM / EARLY) or LIFT_ERR_NOT_FOUND.
+// ---- the three stages of one pair ----------------------------------------------------------------
+// Split so that two drivers can share them: lift_pair (search per pair: k_lift, general path) and the
+// streaming driver of stream_core.cuh (k_scan_lift: every 32-op chunk resolves the window boundaries
+// that fall into it while it scans, and leaves one half-result per boundary).
+
+// START: tpos_to_idx_match(t_st, search_right = true) given the found op (i, o, counters before i).
+// Returns false when the start index would be the number of columns (liftover.rs:52-54 -> None).
+RB_HD bool lift_start(const OpsView& v, uint64_t eo1, uint32_t a_lead, uint32_t tot_A, int policy, uint64_t i, uint32_t o,
+                      const Ctr& before, uint64_t& si, uint32_t& so, Ctr& cs) {
+    const uint32_t w = v.op(i);
+    const uint32_t L = op_len(w), code = op_code(w);
+    bool slide = false;
+    if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
+        uint64_t k2 = i + 1;
+        while (k2 < eo1 && op_len(v.op(k2)) == 0) k2++;
+        if (k2 < eo1 && !is_ref(op_code(v.op(k2)))) slide = true;
+    }
+    if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
+        const uint32_t ca = before.A + o - a_lead;
+        uint32_t extra = 0;
+        for (uint64_t k = i + 1; k < eo1; k++) {
+            const uint32_t w2 = v.op(k);
+            if (op_len(w2) == 0) continue;
+            if (is_ref(op_code(w2))) break;
+            extra += op_len(w2);
+        }
+        if (early_exit_probe(tot_A, ca, ca + extra) == ca) slide = false;
+    }
+    if (!slide && is_match(code)) {
+        si = i; so = o; cs = before;
+        ctr_add_bases(cs, code, o);
+        return true;
+    }
+    Ctr c = before;
+    ctr_add_op(c, w);
+    uint64_t k = i + 1;
+    bool found = false;
+    for (; k < eo1; k++) {
+        const uint32_t w2 = v.op(k);
+        if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+        ctr_add_op(c, w2);
+    }
+    si = k; so = 0; cs = c;
+    return found;  // not found: start index == number of columns > any end index
+}
+
+// END: tpos_to_idx_match(t_en - 1, search_right = false) given the found op.  Returns false when the
+// search slid to column 0 without meeting a match column (start > end -> None).
+RB_HD bool lift_end(const OpsView& v, uint64_t eo0, uint64_t i, uint32_t o, const Ctr& before, uint64_t& ei, uint32_t& eo, Ctr& ce,
+                    uint32_t& txt_before_ei) {
+    const uint32_t w = v.op(i);
+    const uint32_t code = op_code(w);
+    if (is_match(code)) {
+        ei = i; eo = o; ce = before; txt_before_ei = before.TXT;
+        ctr_add_bases(ce, code, o + 1);
+        return true;
+    }
+    Ctr c = before;
+    uint64_t k = i;
+    bool found = false;
+    while (k > eo0) {
+        k--;
+        const uint32_t w2 = v.op(k);
+        ctr_sub_op(c, w2);
+        if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
+    }
+    ei = k; eo = found ? op_len(v.op(k)) - 1 : 0; ce = c; txt_before_ei = c.TXT;
+    if (found) ctr_add_bases(ce, op_code(v.op(k)), eo + 1);
+    return found;
+}
+
+// FINISH: coordinates, nmatch / aln_len, fused stats and the trimmed CIGAR's byte count from the two ends.
+// L_si = length of op si.  Leaves out.kind == PK_DROP when start column > end column (Q7).
+RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t so, const Ctr& cs, uint32_t L_si, uint64_t ei,
+                       uint32_t eo, const Ctr& ce, uint32_t txt_before_ei, PairRes& out) {
+    if (cs.A >= ce.A) return;  // start column > end column: window lies inside an indel (Q7)
+    out.kind = PK_TRIM;
+    out.t_st = r.t_st + cs.T;
+    out.t_en = r.t_st + ce.T;
+    if (r.flags & RF_MINUS) {  // Q8: columns walk the query downward from q_en
+        out.q_st = r.q_en0 - ce.Q;
+        out.q_en = r.q_en0 - cs.Q;
+    } else {
+        out.q_st = r.q_st0 + cs.Q;
+        out.q_en = r.q_st0 + ce.Q;
+    }
+    Ctr d = ce;
+    ctr_sub(d, cs);
+    out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
+    out.aln_len = d.A;
+    fill_stats(out, d);
+    out.si = si; out.ei = ei;
+    if (si == ei) {
+        out.s_len = eo - so + 1; out.e_len = 0;
+        out.cg_bytes = ndigits32(out.s_len) + 1;
+    } else {
+        out.s_len = L_si - so; out.e_len = eo + 1;
+        out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
+    }
+    if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
+        uint32_t bytes = 0, iev = 0, dev = 0;
+        merged_walk(v, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
+            bytes += ndigits32(len) + 1;
+            iev += (c2 == OP_I);
+            dev += (c2 == OP_D);
+        });
+        out.cg_bytes = bytes; out.ins_ev = iev; out.del_ev = dev;
+    }
+}
+
+RB_HD void pair_clear(PairRes& out) {
+    out.pad = 0;
+    out.kind = PK_DROP;
+    out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
+    out.s_len = out.e_len = out.cg_bytes = 0;
+    out.equal = out.diff = out.ins = out.del = out.ins_ev = out.del_ev = out.matches = 0;
+}
+// liftover.rs:22-25 (Q3): record strictly inside the window -> the record itself, uncollapsed
+RB_HD void pair_early(const RecInfo& r, PairRes& out) {
+    out.kind = PK_EARLY;
+    out.t_st = r.t_st; out.t_en = r.t_en; out.q_st = r.q_st; out.q_en = r.q_en;
+    out.nmatch = (uint64_t)(uint32_t)(r.tot.EQ + r.tot.X + r.tot.M);
+    out.aln_len = r.tot.A;
+    out.si = r.eo0; out.ei = r.eo1 - 1;
+    out.cg_bytes = r.tot.TXT;
+    fill_stats(out, r.tot);
+}
+
+// One pair, searching for both ends.  Returns LIFT_OK (out.kind says DROP / TRIM / EARLY) or LIFT_ERR_NOT_FOUND.
 // Staged, no early returns (see RB_CONVERGE): a lane that is done just stops being `live`.
 // `enabled` == false (a candidate pair that does not overlap): produces PK_DROP, keeps the lane in step.
 RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, int policy, bool enabled, PairRes& out,
                          ClassAcc& acc) {
     uint32_t status = LIFT_OK;
     bool live = enabled;
-    out.pad = 0;
-    out.kind = PK_DROP;
-    out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
-    out.s_len = out.e_len = out.cg_bytes = 0;
-    out.equal = out.diff = out.ins = out.del = out.ins_ev = out.del_ev = out.matches = 0;
-    // liftover.rs:22-25 (Q3): record strictly inside the window -> the record itself, uncollapsed
+    pair_clear(out);
     if (live && r.t_st > w_st && r.t_en < w_en) {
-        out.kind = PK_EARLY;
-        out.t_st = r.t_st; out.t_en = r.t_en; out.q_st = r.q_st; out.q_en = r.q_en;
-        out.nmatch = (uint64_t)(uint32_t)(r.tot.EQ + r.tot.X + r.tot.M);
-        out.aln_len = r.tot.A;
-        out.si = r.eo0; out.ei = r.eo1 - 1;
-        out.cg_bytes = r.tot.TXT;
-        fill_stats(out, r.tot);
+        pair_early(r, out);
         live = false;
     } else if (live && r.t_en <= r.t_st) {
         status = LIFT_ERR_NOT_FOUND;
@@ -175,111 +292,47 @@ RB_HD uint32_t lift_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint
     const uint32_t ps = live ? (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st) : 0u;      // liftover.rs:28
     const uint32_t pe = live ? (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st) : 0u;  // liftover.rs:38-40
 
-    // ---- START: tpos_to_idx_match(t_st, search_right = true) ----
     uint64_t i = 0; uint32_t o = 0; Ctr before = ctr_zero();
     if (!find_op(v, r, live, ps, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
     uint64_t si = 0; uint32_t so = 0; Ctr cs = ctr_zero();
-    if (live) {
-        const uint32_t w = v.op(i);
-        const uint32_t L = op_len(w), code = op_code(w);
-        bool slide = false;
-        if (o == L - 1) {  // the right-most column holding this target position may be an insertion column
-            uint64_t k2 = i + 1;
-            while (k2 < r.eo1 && op_len(v.op(k2)) == 0) k2++;
-            if (k2 < r.eo1 && !is_ref(op_code(v.op(k2)))) slide = true;
-        }
-        if (slide && policy == POLICY_EARLY_EXIT && is_match(code)) {
-            const uint32_t ca = before.A + o - r.a_lead;
-            uint32_t extra = 0;
-            for (uint64_t k = i + 1; k < r.eo1; k++) {
-                const uint32_t w2 = v.op(k);
-                if (op_len(w2) == 0) continue;
-                if (is_ref(op_code(w2))) break;
-                extra += op_len(w2);
-            }
-            if (early_exit_probe(r.tot.A, ca, ca + extra) == ca) slide = false;
-        }
-        if (!slide && is_match(code)) {
-            si = i; so = o; cs = before;
-            ctr_add_bases(cs, code, o);
-        } else {
-            Ctr c = before;
-            ctr_add_op(c, w);
-            uint64_t k = i + 1;
-            bool found = false;
-            for (; k < r.eo1; k++) {
-                const uint32_t w2 = v.op(k);
-                if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
-                ctr_add_op(c, w2);
-            }
-            if (!found) live = false;  // start index == number of columns > any end index (liftover.rs:52-54)
-            si = k; so = 0; cs = c;
-        }
-    }
+    if (live && !lift_start(v, r.eo1, r.a_lead, r.tot.A, policy, i, o, before, si, so, cs)) live = false;
     RB_CONVERGE();
 
-    // ---- END: tpos_to_idx_match(t_en - 1, search_right = false) ----
     if (!find_op(v, r, live, pe, i, o, before, acc) && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
     if (live) {
-        const uint32_t w = v.op(i);
-        const uint32_t code = op_code(w);
         uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
-        if (is_match(code)) {
-            ei = i; eo = o; ce = before; txt_before_ei = before.TXT;
-            ctr_add_bases(ce, code, o + 1);
-        } else {
-            Ctr c = before;
-            uint64_t k = i;
-            bool found = false;
-            while (k > r.eo0) {
-                k--;
-                const uint32_t w2 = v.op(k);
-                ctr_sub_op(c, w2);
-                if (is_match(op_code(w2)) && op_len(w2) > 0) { found = true; break; }
-            }
-            if (!found) live = false;  // slid to column 0 which is not a match column -> start > end
-            ei = k; eo = found ? op_len(v.op(k)) - 1 : 0; ce = c; txt_before_ei = c.TXT;
-            if (found) ctr_add_bases(ce, op_code(v.op(k)), eo + 1);
-        }
-        if (live && cs.A >= ce.A) live = false;  // start column > end column: window lies inside an indel (Q7)
-        if (live) {
-            out.kind = PK_TRIM;
-            out.t_st = r.t_st + cs.T;
-            out.t_en = r.t_st + ce.T;
-            if (r.flags & RF_MINUS) {  // Q8: columns walk the query downward from q_en
-                out.q_st = r.q_en0 - ce.Q;
-                out.q_en = r.q_en0 - cs.Q;
-            } else {
-                out.q_st = r.q_st0 + cs.Q;
-                out.q_en = r.q_st0 + ce.Q;
-            }
-            Ctr d = ce;
-            ctr_sub(d, cs);
-            out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
-            out.aln_len = d.A;
-            fill_stats(out, d);
-            out.si = si; out.ei = ei;
-            const uint32_t L_si = op_len(v.op(si));
-            if (si == ei) {
-                out.s_len = eo - so + 1; out.e_len = 0;
-                out.cg_bytes = ndigits32(out.s_len) + 1;
-            } else {
-                out.s_len = L_si - so; out.e_len = eo + 1;
-                out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
-            }
-            if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
-                uint32_t bytes = 0, iev = 0, dev = 0;
-                merged_walk(v, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
-                    bytes += ndigits32(len) + 1;
-                    iev += (c2 == OP_I);
-                    dev += (c2 == OP_D);
-                });
-                out.cg_bytes = bytes; out.ins_ev = iev; out.del_ev = dev;
-            }
-        }
+        if (lift_end(v, r.eo0, i, o, before, ei, eo, ce, txt_before_ei))
+            lift_finish(v, r, si, so, cs, op_len(v.op(si)), ei, eo, ce, txt_before_ei, out);
     }
     RB_CONVERGE();
     return status;
+}
+
+// ---- half results of the streaming driver (one per window boundary, 64 B each) ----
+struct HalfS {       // start of the trimmed alignment
+    Ctr c;           // counters before the start column; c.aux = 1 if a start column exists
+    uint32_t so;     // offset of the start column in op si
+    uint32_t L_si;   // length of op si
+    uint64_t si;
+};
+struct HalfE {       // end of the trimmed alignment
+    Ctr c;           // counters up to and including the end column; c.aux = 1 if an end column exists
+    uint32_t eo;     // offset of the end column in op ei
+    uint32_t txt_before_ei;
+    uint64_t ei;
+};
+
+// Pair = (record, window) from its two halves.  Same result as lift_pair for every pair whose two
+// boundaries were resolved (all overlapping pairs of a record that passes check_integrity).
+RB_HD uint32_t combine_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, const HalfS& hs, const HalfE& he,
+                            PairRes& out) {
+    pair_clear(out);
+    if (r.t_st > w_st && r.t_en < w_en) { pair_early(r, out); return LIFT_OK; }
+    if (r.t_en <= r.t_st) return LIFT_ERR_NOT_FOUND;
+    // (the index guard only matters for unwritten halves of a record that fails check_integrity: no wild reads)
+    if (hs.c.aux == 1u && he.c.aux == 1u && hs.si >= r.eo0 && he.ei < r.eo1 && hs.si <= he.ei)
+        lift_finish(v, r, hs.si, hs.so, hs.c, hs.L_si, he.ei, he.eo, he.c, he.txt_before_ei, out);
+    return LIFT_OK;
 }
 
 // Bytes of the printed PAF line (paf.rs:923-943), '\n' included.

@@ -4,7 +4,9 @@
 // zero-length ops, adjacent same-class ops, N/P, leading/trailing indels and clips.
 //   usage: lift_core_check <seed> <n_records>
 #include <cstdio>
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <string>
 #include <vector>
@@ -12,6 +14,7 @@
 #include "lift_core.cuh"
 #include "rb_oracle.hpp"
 #include "rec_core.cuh"
+#include "stream_core.cuh"
 
 using namespace rb;
 
@@ -108,6 +111,7 @@ int main(int argc, char** argv) {
     ClassAcc acc;
     acc.sum = acc_mem; acc.stride = 1;
 
+    long n_stream = 0;
     long n_pairs = 0, n_trim = 0, n_early = 0, n_drop = 0, n_abort = 0, n_slow = 0, n_fail = 0;
     for (size_t r = 0; r < recs.size(); r++) {
         const TestRec& tr = recs[r];
@@ -232,8 +236,61 @@ int main(int argc, char** argv) {
                 }
             }
         }
+
+        // ---- streaming driver (stream_core.cuh, what k_scan_lift runs): sorted windows merged against the op stream,
+        //      chunked exactly like the kernel (32-op chunks of the GLOBAL op index); must equal lift_pair bit for bit ----
+        {
+            std::vector<std::pair<uint64_t, uint64_t>> wins;
+            const int nw = (int)U(1, 12);
+            for (int k = 0; k < nw; k++) {
+                uint64_t a = U(ri.t_st > 3 ? ri.t_st - 3 : 0, ri.t_en + 1), b = U(ri.t_st > 3 ? ri.t_st - 3 : 0, ri.t_en + 3);
+                if (a > b) std::swap(a, b);
+                if (k == 0 && U(0, 3) == 0) { a = 0; b = ri.t_en + 5; }
+                if (ri.t_en > a && ri.t_st < b) wins.push_back({a, b});
+            }
+            std::sort(wins.begin(), wins.end());
+            for (size_t k = 1; k < wins.size(); k++) wins[k].second = std::max(wins[k].second, wins[k - 1].second);  // en monotone
+            std::vector<uint64_t> wst, wen;
+            for (auto& w : wins) if (ri.t_en > w.first && ri.t_st < w.second) { wst.push_back(w.first); wen.push_back(w.second); }
+            const uint32_t W = (uint32_t)wst.size();
+            HalfS junk_s; HalfE junk_e;
+            memset(&junk_s, 0xAB, sizeof junk_s); memset(&junk_e, 0xCD, sizeof junk_e);
+            std::vector<HalfS> hs(W, junk_s);
+            std::vector<HalfE> he(W, junk_e);
+            std::vector<int> ws(W, 0), we(W, 0);
+            SegRec sr{ri.eo0, ri.eo1, 0u, W, 0ull};
+            WinGlobal wa{wst.data(), wen.data(), ri.t_st, ri.t_en};
+            Ctr run = ctr_zero();
+            uint64_t k = ri.op_first;
+            while (k < ri.op_end) {
+                const uint64_t kend = std::min<uint64_t>(ri.op_end, ((k >> SAMPLE_LOG2) + 1) << SAMPLE_LOG2);
+                uint32_t Tseg = 0;
+                for (uint64_t t = k; t < kend; t++) if (is_ref(op_code(ops[t]))) Tseg += op_len(ops[t]);
+                stream_segment(view, sr, wa, k, (uint32_t)(kend - k), [&](uint32_t j) { return ops[k + j]; }, run, Tseg, acc,
+                               [&](uint64_t p, const HalfS& h) { hs[p] = h; ws[p]++; },
+                               [&](uint64_t p, const HalfE& h) { he[p] = h; we[p]++; });
+                for (uint64_t t = k; t < kend; t++) ctr_add_op(run, ops[t]);
+                k = kend;
+            }
+            for (uint32_t j = 0; j < W; j++) {
+                n_stream++;
+                PairRes a, b;
+                const uint32_t e1 = lift_pair(view, ri, wst[j], wen[j], POLICY_RIGHTMOST, true, a, acc);
+                const uint32_t e2 = combine_pair(view, ri, wst[j], wen[j], hs[j], he[j], b);
+                const bool early = ri.t_st > wst[j] && ri.t_en < wen[j];
+                // every boundary of a non-early pair is resolved exactly once (early rows never read their halves)
+                bool ok = e1 == e2 && memcmp(&a, &b, sizeof a) == 0 && ws[j] <= 1 && we[j] <= 1 && (early || (ws[j] == 1 && we[j] == 1));
+                if (!ok) {
+                    n_fail++;
+                    if (n_fail < 20)
+                        fprintf(stderr, "FAIL stream rec %zu win %lu-%lu: e %u/%u kind %u/%u writes %d/%d t %lu-%lu / %lu-%lu si %lu/%lu ei %lu/%lu\n%s\n", r,
+                                wst[j], wen[j], e1, e2, a.kind, b.kind, ws[j], we[j], a.t_st, a.t_en, b.t_st, b.t_en, a.si, b.si, a.ei, b.ei,
+                                tr.line.c_str());
+                }
+            }
+        }
     }
-    printf("records=%zu aborts=%ld slow=%ld pairs=%ld trim=%ld early=%ld drop=%ld FAIL=%ld\n", recs.size(), n_abort, n_slow,
-           n_pairs, n_trim, n_early, n_drop, n_fail);
+    printf("records=%zu aborts=%ld slow=%ld stream=%ld pairs=%ld trim=%ld early=%ld drop=%ld FAIL=%ld\n", recs.size(), n_abort, n_slow,
+           n_stream, n_pairs, n_trim, n_early, n_drop, n_fail);
     return n_fail ? 1 : 0;
 }
