@@ -211,7 +211,8 @@ def main():
     # ---- per-kernel times for the roofline of the dominant kernel (separate pass, events around each launch) ----
     ctx.set_profiling(True)
     ctx.kernel_times(reset=True)
-    for _ in range(max(3, args.steps // 4)):
+    n_prof = max(3, args.steps // 4)
+    for _ in range(n_prof):
         flush.fill_(1)
         ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
     torch.cuda.synchronize()
@@ -256,6 +257,8 @@ def main():
         alg = {
             "k_tokenise": cigar_bytes + 4 * n_ops,
             "k_samples": 4 * n_ops + (n_ops // 32) * (4 + 48),
+            "k_scan_lift": 4 * n_ops + (n_ops // 32) * (4 + 48) + 16 * wins.n_win + 128 * n_pairs,
+            "k_combine": n_pairs * (128 + 16 + 112 + 4),
             "k_lift": n_pairs * (16 + 116 + 2 * (48 + 64)),
             "k_serialise": n_pairs * (112 + 16) + 4 * n_ops + out_bytes + n_out * (40 + 8),
             "k_scan_lines": n_pairs * (4 + 16),
@@ -284,7 +287,7 @@ def main():
             "cigar_gb_per_s": tot[1] / (tmax[0] * 1e-3) / 1e9,
             "e2e": {"value": tot[0] / (tmax[1] * 1e-3), "unit": UNIT, "ms_per_step": tmax[1], "h2d_bytes_per_step": int(tot[5]),
                     "d2h_bytes_per_step": int(tot[6]), "cigar_gb_per_s": tot[1] / (tmax[1] * 1e-3) / 1e9},
-            "gpu_launches": 8 * args.steps,
+            "gpu_launches": int(sum(v[0] for v in ktimes.values()) // n_prof) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg[dom]),

@@ -149,6 +149,13 @@ void rb_ctx_destroy(rb_ctx* ctx);
 const char* rb_last_error(const rb_ctx* ctx);
 /* launch everything on the caller's stream (a cudaStream_t, e.g. torch's current stream); NULL = own stream */
 int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream);
+/* how rb_liftover resolves the window boundaries (results are identical):
+ *   RB_LIFT_SEARCH  one search per (window, record) pair over the sampled prefix sums (default)
+ *   RB_LIFT_STREAM  sorted BED rows + right-most policy: boundaries are resolved while the prefix scan streams
+ *                   over the ops; other inputs silently use RB_LIFT_SEARCH */
+#define RB_LIFT_SEARCH 0
+#define RB_LIFT_STREAM 1
+int rb_ctx_set_lift_mode(rb_ctx* ctx, int mode);
 /* per-kernel CUDA-event timing (off by default; adds an event pair around every launch) */
 int rb_ctx_set_profiling(rb_ctx* ctx, int on);
 int rb_ctx_kernel_times(rb_ctx* ctx, rb_kernel_time* out, int cap, int reset); /* returns count */

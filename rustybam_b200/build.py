@@ -37,7 +37,7 @@ def build_cuda(force=False, verbose=False):
     deps = srcs + _sources(CSRC, (".cuh",)) + [os.path.join(ROOT, "include", "rbcuda.h"), os.path.abspath(__file__)]
     if not force and not _newer(LIB, deps):
         return LIB
-    extra = [f"-DRB_SAMPLE_LOG2={os.environ['RB_SAMPLE_LOG2']}"] if os.environ.get("RB_SAMPLE_LOG2") else []
+    extra = os.environ.get("RB_NVCC_DEFS", "").split()  # e.g. "-DRB_LIFT_THREADS=256 -DRB_LIFT_MINB=2" (tuning sweeps)
     cmd = [nvcc] + NVCC_FLAGS + extra + ["-shared", "-o", LIB] + srcs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode != 0:

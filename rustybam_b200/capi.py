@@ -19,9 +19,10 @@ RB_ERR_UNSUPPORTED, RB_ERR_OOM = -8, -9
 REF_PANIC_CODES = (RB_ERR_REF_CIGAR_PARSE, RB_ERR_REF_INTEGRITY, RB_ERR_REF_STRIP, RB_ERR_REF_INDEX)
 POLICY_RIGHTMOST, POLICY_EARLY_EXIT = 0, 1
 WANT_TEXT, WANT_NUMERIC = 1, 2
+LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
-    "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_kernel_times",
+    "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_kernel_times",
     "rb_liftover", "rb_stats", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
     "rb_host_unregister",
@@ -85,6 +86,7 @@ def load():
     lib.rb_last_error.argtypes = [C.c_void_p]
     lib.rb_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    lib.rb_ctx_set_lift_mode.argtypes = [C.c_void_p, C.c_int]
     lib.rb_ctx_kernel_times.argtypes = [C.c_void_p, C.POINTER(RbKernelTime), C.c_int, C.c_int]
     lib.rb_liftover.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.POINTER(RbWindows), C.c_int, C.c_uint32, C.POINTER(RbLiftOut),
                                 C.POINTER(RbStatsOut)]
@@ -205,6 +207,9 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.rb_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_lift_mode(self, mode):
+        self._check(self.lib.rb_ctx_set_lift_mode(self.h, int(mode)))
 
     def set_profiling(self, on=True):
         self._check(self.lib.rb_ctx_set_profiling(self.h, int(on)))

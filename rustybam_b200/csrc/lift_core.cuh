@@ -26,8 +26,25 @@ struct OpsView {
     const Ctr* s_smp = nullptr;
     uint64_t so_lo = 0, so_hi = 0, sc_lo = 0, sc_hi = 0;
     RB_HD uint32_t op(uint64_t k) const { return (k - so_lo < so_hi - so_lo) ? s_ops[k - so_lo] : ops[k]; }
-    RB_HD Ctr smp(uint64_t c) const { return (c - sc_lo < sc_hi - sc_lo) ? s_smp[c - sc_lo] : samples[c]; }
-    RB_HD uint32_t smp_T(uint64_t c) const { return (c - sc_lo < sc_hi - sc_lo) ? s_smp[c - sc_lo].T : samples[c].T; }
+    RB_HD const Ctr& ent(uint64_t c, uint32_t s) const {  // entry s of chunk c (0 = absolute sample, 1.. = sub-samples)
+        return (c - sc_lo < sc_hi - sc_lo) ? s_smp[(c - sc_lo) * SUBS + s] : samples[c * SUBS + s];
+    }
+    RB_HD Ctr smp(uint64_t c) const { return ent(c, 0); }
+    RB_HD uint32_t smp_T(uint64_t c) const { return ent(c, 0).T; }
+    // target bases of the record before op 32c + 8s (s >= 1; the position must lie inside the record)
+    RB_HD uint32_t sub_T(uint64_t c, uint32_t s) const {
+        const Ctr& e = ent(c, s);
+        return (e.aux & SUB_ABS) ? e.T : e.T + ent(c, 0).T;
+    }
+    // counters of the record before op 32c + 8s (the position must lie inside the record, after its first op)
+    RB_HD Ctr at(uint64_t c, uint32_t s) const {
+        Ctr e = ent(c, s);
+        if (s == 0) return e;
+        const bool abs = (e.aux & SUB_ABS) != 0;
+        e.aux = 0;
+        if (!abs) ctr_add(e, ent(c, 0));
+        return e;
+    }
 };
 
 enum : int { POLICY_RIGHTMOST = 0, POLICY_EARLY_EXIT = 1 };
@@ -35,10 +52,10 @@ enum : uint32_t { LIFT_OK = 0, LIFT_ERR_NOT_FOUND = 1 };  // NOT_FOUND == the re
 
 // Counters accumulated from the record's first op up to (excluding) op k (op_first <= k < op_end).
 RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k, ClassAcc& acc) {
-    const uint64_t base = (k >> SAMPLE_LOG2) << SAMPLE_LOG2;
+    const uint64_t base = (k >> SUB_LOG2) << SUB_LOG2;
     Ctr c;
     uint64_t j;
-    if (base > r.op_first) { c = v.smp(k >> SAMPLE_LOG2); j = base; }
+    if (base > r.op_first) { c = v.at(k >> SAMPLE_LOG2, (uint32_t)(k & (SAMPLE - 1)) >> SUB_LOG2); j = base; }
     else { c = ctr_zero(); j = r.op_first; }
     acc_reset(acc);
     const uint64_t j0 = j;
@@ -60,6 +77,23 @@ RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k, ClassAcc& a
 #define RB_CONVERGE() ((void)0)
 #endif
 
+// The 32-op chunk whose sampled target prefix is the last one <= p (the chunk find_op starts its walk in).
+RB_HD uint64_t chunk_of(const OpsView& v, const RecInfo& r, uint32_t p) {
+    uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
+    // narrow to the staged chunk window when the answer provably lies inside it (all probes then hit smem)
+    if (v.sc_hi > v.sc_lo) {
+        const uint64_t a = v.sc_lo, z = v.sc_hi - 1;
+        if (a > lo && a <= hi && v.smp_T(a) <= p) lo = a;
+        if (z > lo && z <= hi && v.smp_T(z) > p) hi = z - 1;
+    }
+    while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
+        const uint64_t mid = (lo + hi + 1) >> 1;
+        if (v.smp_T(mid) <= p) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
 // The reference-consuming op i (len > 0) with T_i <= p < T_i + L_i ; o = p - T_i ; `before` = counters before op i.
 // `live` == false: does nothing (keeps the lane in step with its warp).
 RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, uint64_t& i, uint32_t& o, Ctr& before, ClassAcc& acc) {
@@ -68,20 +102,15 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     uint64_t k0 = 0;
     uint32_t n = 0, j = 0;
     if (live && r.op_end > r.op_first) {
-        uint64_t lo = r.op_first >> SAMPLE_LOG2, hi = (r.op_end - 1) >> SAMPLE_LOG2;
-        // narrow to the staged chunk window when the answer provably lies inside it (all probes then hit smem)
-        if (v.sc_hi > v.sc_lo) {
-            const uint64_t a = v.sc_lo, z = v.sc_hi - 1;
-            if (a > lo && a <= hi && v.smp_T(a) <= p) lo = a;
-            if (z > lo && z <= hi && v.smp_T(z) > p) hi = z - 1;
-        }
-        while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
-            const uint64_t mid = (lo + hi + 1) >> 1;
-            if (v.smp_T(mid) <= p) lo = mid;
-            else hi = mid - 1;
-        }
+        const uint64_t lo = chunk_of(v, r, p);
         k0 = lo << SAMPLE_LOG2;
-        if (k0 > r.op_first) c = v.smp(lo);
+        uint32_t s = 0;  // last sub-sample of the chunk that lies inside the record and whose target prefix is <= p
+        for (uint32_t t = SUBS - 1; t >= 1; t--) {
+            const uint64_t pos = k0 + t * SUB_OPS;
+            if (pos > r.op_first && pos < r.op_end && v.sub_T(lo, t) <= p) { s = t; break; }
+        }
+        if (s) { k0 += s * SUB_OPS; c = v.at(lo, s); }
+        else if (k0 > r.op_first) c = v.smp(lo);
         else k0 = r.op_first;
         const uint64_t left = r.op_end - k0;
         n = left > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)left;

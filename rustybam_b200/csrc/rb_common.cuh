@@ -4,8 +4,9 @@
 //   text      u8[N]            concatenated cg:Z: payloads of all records (read once by the tokeniser)
 //   ops       u32[n_ops]       one word per CIGAR op: (len << 4) | code, BAM op codes, len < 2^28
 //   heads     u32[n_ops/32+1]  bit k%32 of word k/32 set  <=>  op k is the first op of a record
-//   samples   Ctr[n_ops/32+1]  sampled segmented prefix sums: samples[c] = counters accumulated from
-//                              the first op of the record containing op 32c up to (excluding) op 32c
+//   samples   Ctr[(n_ops/32+1)*4] sampled segmented prefix sums: samples[4c] = counters accumulated from
+//                              the first op of the record containing op 32c up to (excluding) op 32c;
+//                              samples[4c+s] (s = 1..3) = the same at op 32c + 8s, relative to the chunk start
 //   recs      RecInfo[n_rec]   per-record state after the leading/trailing indel strip
 // Nothing per alignment column is ever materialised (the reference keeps 24 B per column,
 // paf.rs:362-364,501-538); per-op state is 4 B + 1.5 B of samples.
@@ -31,6 +32,14 @@ constexpr uint32_t MAX_OP_LEN = (1u << 28) - 1;
 #endif
 constexpr int SAMPLE_LOG2 = RB_SAMPLE_LOG2;  // 5 or 4
 constexpr uint32_t SAMPLE = 1u << SAMPLE_LOG2;  // ops per sample chunk (== bits of a heads word)
+// Sub-samples: every chunk keeps SUBS counters, one per SUB_OPS ops.  Entry 0 is the absolute sample (counters of
+// the record before the chunk's first op); entries 1.. are RELATIVE to the chunk start — or, when a record starts
+// inside the chunk before that position (SUB_ABS set in aux), relative to that record's first op, i.e. absolute.
+// They cut the per-boundary walk of find_op / ctr_before from <= 31 ops to <= 7.
+constexpr int SUB_LOG2 = 3;
+constexpr uint32_t SUB_OPS = 1u << SUB_LOG2;
+constexpr uint32_t SUBS = SAMPLE / SUB_OPS;
+constexpr uint32_t SUB_ABS = 0x40000000u;
 
 RB_HD uint32_t op_len(uint32_t w) { return w >> 4; }
 RB_HD uint32_t op_code(uint32_t w) { return w & 15u; }

@@ -19,6 +19,7 @@
 #include "lift_core.cuh"
 #include "rb_kernels.cuh"
 #include "rec_core.cuh"
+#include "stream_core.cuh"
 
 namespace rb {
 
@@ -434,14 +435,43 @@ __device__ __forceinline__ SegVal lookback_seg(uint32_t* state, ScanPayload* agg
     return acc;
 }
 
-__global__ void __launch_bounds__(SMP_THREADS, 3)
-k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
-          Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket) {
-    __shared__ uint32_t s_ops[SMP_THREADS * (SAMPLE + 1)];
-    __shared__ uint32_t s_acc[9 * SMP_THREADS];
+// Windows of one record staged in shared memory as relative boundary positions (stream_core.cuh)
+struct WinStaged {
+    const uint32_t* s_ps;  // ps(j) for j in [js0, ..)
+    const uint32_t* s_pe;  // pe(j) for j in [je0, ..)
+    uint32_t js0, je0;
+    __device__ __forceinline__ uint32_t ps(uint32_t j) const { return s_ps[j - js0]; }
+    __device__ __forceinline__ uint32_t pe(uint32_t j) const { return s_pe[j - je0]; }
+};
+__device__ __forceinline__ void store_half(void* dst, const void* src) {  // 64-byte half result, 4 vector stores
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int k = 0; k < 4; k++) d4[k] = s4[k];
+}
+
+// K2 (+K4 on the sorted-BED fast path).  One thread per 32-op chunk:
+//   walk 1   class sums of the chunk -> block-level segmented scan -> decoupled look-back -> samples[chunk]
+//   walk 2   (LIFT) the chunk re-walks its ops from shared memory with exact counters and resolves every window
+//            boundary whose target position falls into it (stream_core.cuh) -> one 64-byte half result per boundary.
+// When the whole block lies inside one record (the common case at scale) the record's window boundaries that fall
+// into the block's target range are staged in shared memory first, so the per-chunk searches never leave the SM.
+template <bool LIFT>
+__global__ void __launch_bounds__(SMP_THREADS, LIFT ? 2 : RB_SMP_MINB)
+k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
+            Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
+            LiftArgs la) {
+    extern __shared__ __align__(16) uint32_t s_dyn[];
+    uint32_t* s_ops = s_dyn;                                   // SMP_THREADS * (SAMPLE + 1)
+    uint32_t* s_acc = s_ops + SMP_THREADS * (SAMPLE + 1);      // 9 * SMP_THREADS
+    uint32_t* s_ps = s_acc + 9 * SMP_THREADS;                  // LIFT: SL_WCAP
+    uint32_t* s_pe = s_ps + SL_WCAP;                           // LIFT: SL_WCAP
     __shared__ SegVal s_warp[SMP_THREADS / 32];
     __shared__ SegVal s_blk;
     __shared__ unsigned int s_b;
+    __shared__ uint32_t s_hc[SMP_THREADS / 32];
+    __shared__ uint32_t s_rblk;
+    __shared__ uint32_t s_jr[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t n_ops = *n_ops_dev;
     if (tid == 0) s_b = atomicAdd(ticket, 1u);
@@ -456,6 +486,14 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
         const uint32_t idx = (uint32_t)i * SMP_THREADS + tid;
         const uint64_t g = op0 + idx;
         s_ops[(idx >> SAMPLE_LOG2) * (SAMPLE + 1) + (idx & (SAMPLE - 1))] = (g < n_ops) ? ops[g] : 0u;
+    }
+    if (LIFT && tid == 32) {  // record that holds the block's first op (largest r with op_off[r] <= op0), off the critical path
+        uint32_t lo = 0, hi = la.n_rec;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (la.op_off[mid] <= op0) lo = mid + 1; else hi = mid;
+        }
+        s_rblk = lo ? lo - 1 : 0u;
     }
     __syncthreads();
 
@@ -479,6 +517,23 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
         const uint32_t w = my_ops[j];
         const bool head = (h >> j) & 1u;
         if (head) { acc_reset(acc); slowc = 0; }  // a record starts here: the span before it is not part of this aggregate
+        if (j && (j & (int)(SUB_OPS - 1)) == 0) {  // sub-sample: counters since the chunk start (or since the last head)
+            Ctr sub = ctr_zero();
+            if (acc.big >= ACC_BIG) {  // a class sum may have wrapped: exact counters
+                int j0 = 0;
+                for (int t = 0; t <= j; t++)
+                    if ((h >> t) & 1u) j0 = t;
+                for (int t = j0; t < j; t++) ctr_add_op(sub, my_ops[t]);
+            } else {
+                acc_flush(acc, sub);
+            }
+            sub.aux = (((h >> 1) & ((1u << j) - 1u)) != 0u) ? SUB_ABS : 0u;
+            uint4* dst = reinterpret_cast<uint4*>(samples + chunk * SUBS + (uint32_t)(j >> SUB_LOG2));
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(&sub);
+            dst[0] = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+            dst[1] = make_uint4(sw[4], sw[5], sw[6], sw[7]);
+            dst[2] = make_uint4(sw[8], sw[9], sw[10], sw[11]);
+        }
         const uint32_t code = op_code(w);
         slowc += (op_len(w) == 0u) | ((!head) & (code == prev_code));
         acc_add_op(acc, w);
@@ -495,33 +550,126 @@ k_samples(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_d
     mine.c.aux = (mine.c.aux & AUX_OVF) | (slowc & AUX_CNT);
     mine.flag = (h != 0u);
 
-    // block-level segmented scan of the per-chunk aggregates
+    // block-level segmented scan of the per-chunk aggregates (+ LIFT: count of record heads after the block's first op)
     SegVal inc = mine;
+    const uint32_t hc = LIFT ? (uint32_t)__popc(tid == 0 ? (h & ~1u) : h) : 0u;
+    uint32_t hinc = hc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const SegVal y = seg_shfl(inc, (lane - d) & 31);
         if (lane >= d) inc = seg_combine(y, inc);
+        if (LIFT) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, hinc, d);
+            if (lane >= d) hinc += t;
+        }
     }
-    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 31) { s_warp[warp] = inc; if (LIFT) s_hc[warp] = hinc; }
     SegVal exl = seg_shfl(inc, (lane - 1) & 31);
     if (lane == 0) exl = seg_identity();
     __syncthreads();
     SegVal wpre = seg_identity(), btot = seg_identity();
+    uint32_t hpre = 0, htot = 0;
 #pragma unroll
     for (int k = 0; k < SMP_THREADS / 32; k++) {
         const SegVal t = s_warp[k];
         if (k < warp) wpre = seg_combine(wpre, t);
         btot = seg_combine(btot, t);
+        if (LIFT) {
+            const uint32_t u = s_hc[k];
+            if (k < warp) hpre += u;
+            htot += u;
+        }
     }
     if (warp == 0) {
         const SegVal ex = lookback_seg(blk_state, blk_agg, blk_pre, b, btot);
         if (lane == 0) s_blk = ex;
     }
     __syncthreads();
-    if (nvalid) {
-        SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
-        if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
-        samples[chunk] = pre.c;
+    SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
+    if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
+    if (nvalid) samples[chunk * SUBS] = pre.c;
+    if (!LIFT) return;
+
+    // ---------------- walk 2: window boundaries that fall into this chunk ----------------
+    OpsView v;
+    v.ops = ops; v.samples = nullptr;
+    const uint32_t r_blk = s_rblk;
+    const bool one_record = (htot == 0u) && r_blk < la.n_rec;  // block-uniform
+    if (one_record) {
+        const RecInfo& R = la.recs[r_blk];
+        SegRec sr;
+        sr.eo0 = R.eo0; sr.eo1 = R.eo1; sr.wlo = R.wlo; sr.whi = R.whi;
+        if (sr.whi <= sr.wlo || op0 < R.op_first || op0 >= R.op_end) return;  // block-uniform
+        sr.pair0 = la.pair_off[la.rec_rank[r_blk]];
+        const WinGlobal wg{la.w_st, la.w_en, R.t_st, R.t_en};
+        // the block's own target range -> the slice of window boundaries to stage
+        if (warp == 0) {
+            const uint32_t T0b = __shfl_sync(0xffffffffu, pre.c.T, 0);  // thread 0's prefix == the block's
+            const uint32_t T1b = T0b + btot.c.T;
+            uint32_t x = 0;
+            if (lane == 0) x = first_true(sr.wlo, sr.whi, [&](uint32_t j) { return wg.ps(j) >= T0b; });
+            if (lane == 1) x = first_true(sr.wlo, sr.whi, [&](uint32_t j) { return wg.ps(j) >= T1b; });
+            if (lane == 2) x = first_true(sr.wlo, sr.whi, [&](uint32_t j) { return wg.pe(j) > T0b; });
+            if (lane == 3) x = first_true(sr.wlo, sr.whi, [&](uint32_t j) { return wg.pe(j) > T1b; });
+            if (lane < 4) s_jr[lane] = x;
+        }
+        __syncthreads();
+        const uint32_t js0 = s_jr[0], js1 = s_jr[1], je0 = s_jr[2], je1 = s_jr[3];
+        if (js1 <= js0 && je1 <= je0) return;  // no boundary in this block (block-uniform)
+        const bool staged = (js1 - js0 <= (uint32_t)SL_WCAP) && (je1 - je0 <= (uint32_t)SL_WCAP);
+        if (staged) {
+            for (uint32_t i = tid; i < js1 - js0; i += SMP_THREADS) s_ps[i] = wg.ps(js0 + i);
+            for (uint32_t i = tid; i < je1 - je0; i += SMP_THREADS) s_pe[i] = wg.pe(je0 + i);
+        }
+        __syncthreads();
+        if (nvalid == 0) return;
+        auto seg_op = [&](uint32_t j) { return my_ops[j]; };
+        auto emit_s = [&](uint64_t p, const HalfS& hh) { store_half(&la.hs[p], &hh); };
+        auto emit_e = [&](uint64_t p, const HalfE& hh) { store_half(&la.he[p], &hh); };
+        if (staged) {
+            SegRec s2 = sr;
+            s2.s_lo = js0; s2.s_hi = js1; s2.e_lo = je0; s2.e_hi = je1;
+            const WinStaged ws{s_ps, s_pe, js0, je0};
+            stream_segment(v, s2, ws, first, (uint32_t)nvalid, seg_op, pre.c, mine.c.T, acc, emit_s, emit_e);
+        } else {
+            sr.s_lo = sr.e_lo = sr.wlo; sr.s_hi = sr.e_hi = sr.whi;
+            stream_segment(v, sr, wg, first, (uint32_t)nvalid, seg_op, pre.c, mine.c.T, acc, emit_s, emit_e);
+        }
+        return;
+    }
+
+    // general layout: records start inside the block -> every chunk handles its own segments against global memory
+    if (nvalid == 0) return;
+    const uint32_t hex = hpre + (hinc - hc);  // heads after op0 and before this chunk
+    uint32_t r = r_blk + hex + ((tid > 0) ? (h & 1u) : 0u);
+    int jb = 0;
+    Ctr base = pre.c;
+    for (;;) {
+        const uint32_t hm = (jb >= 31) ? 0u : (h & ~((2u << jb) - 1u));
+        const int je = hm ? (__ffs(hm) - 1) : nvalid;
+        const uint64_t k0 = first + (uint64_t)jb;
+        if (r < la.n_rec && la.op_off[r] <= k0 && k0 < la.op_off[r + 1]) {
+            const RecInfo& R = la.recs[r];
+            SegRec sr;
+            sr.eo0 = R.eo0; sr.eo1 = R.eo1; sr.wlo = R.wlo; sr.whi = R.whi;
+            sr.s_lo = sr.e_lo = sr.wlo; sr.s_hi = sr.e_hi = sr.whi;
+            if (sr.whi > sr.wlo) {
+                sr.pair0 = la.pair_off[la.rec_rank[r]];
+                const WinGlobal wg{la.w_st, la.w_en, R.t_st, R.t_en};
+                uint32_t Tseg = 0;
+                for (int j = jb; j < je; j++) {
+                    const uint32_t w = my_ops[j];
+                    if (is_ref(op_code(w))) Tseg += op_len(w);
+                }
+                stream_segment(v, sr, wg, k0, (uint32_t)(je - jb), [&](uint32_t j) { return my_ops[jb + (int)j]; }, base, Tseg, acc,
+                               [&](uint64_t p, const HalfS& hh) { store_half(&la.hs[p], &hh); },
+                               [&](uint64_t p, const HalfE& hh) { store_half(&la.he[p], &hh); });
+            }
+        }
+        if (je >= nvalid) break;
+        jb = je;
+        r++;
+        base = ctr_zero();
     }
 }
 
@@ -549,6 +697,9 @@ __device__ __forceinline__ void write_stats(const StatsDev& st, uint64_t i, uint
     st.id_m[i] = __fdiv_rn(num, __uint2float_rn(equal + diff));
 }
 
+// mode 0  rb stats --paf (after the scan): integrity + counters of the record as read
+// mode 1  liftover phase A (needs ops only, runs BEFORE the scan): indel strip + window join -> RecInfo, pair_cnt
+// mode 2  liftover phase B (after the scan): integrity, RF_SLOW, counters of the stripped op range
 __global__ void __launch_bounds__(128)
 k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uint32_t* __restrict__ ops,
            const Ctr* __restrict__ samples, WinView win, RecInfo* __restrict__ recs, uint32_t* __restrict__ pair_cnt, StatsDev st,
@@ -561,22 +712,58 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     ClassAcc acc;
     acc.sum = s_acc + threadIdx.x; acc.stride = 128;
     RecInfo ri;
-    ri.op_first = op_off[r]; ri.op_end = op_off[r + 1];
-    ri.eo0 = ri.op_first; ri.eo1 = ri.op_end;
-    ri.t_st = in.t_st[r]; ri.t_en = in.t_en[r];
-    ri.q_st0 = in.q_st[r]; ri.q_en0 = in.q_en[r];
-    ri.q_st = ri.q_st0; ri.q_en = ri.q_en0;
-    ri.q_len = in.q_len[r]; ri.t_len = in.t_len[r]; ri.mapq = in.mapq[r];
-    ri.q_name = in.q_id[r]; ri.t_name = in.t_id[r];
-    ri.flags = (in.strand[r] == '-') ? RF_MINUS : 0u;
-    ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.pad = 0;
-    ri.tot = ctr_zero();
+    if (mode == 2) {
+        ri = recs[r];
+    } else {
+        ri.op_first = op_off[r]; ri.op_end = op_off[r + 1];
+        ri.eo0 = ri.op_first; ri.eo1 = ri.op_end;
+        ri.t_st = in.t_st[r]; ri.t_en = in.t_en[r];
+        ri.q_st0 = in.q_st[r]; ri.q_en0 = in.q_en[r];
+        ri.q_st = ri.q_st0; ri.q_en = ri.q_en0;
+        ri.q_len = in.q_len[r]; ri.t_len = in.t_len[r]; ri.mapq = in.mapq[r];
+        ri.q_name = in.q_id[r]; ri.t_name = in.t_id[r];
+        ri.flags = (in.strand[r] == '-') ? RF_MINUS : 0u;
+        ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.pad = 0;
+        ri.tot = ctr_zero();
+    }
+
+    if (mode == 1) {
+        const uint32_t e = strip_record(ops, ri);
+        if (e != RE_OK) {
+            report(err.rec, r, e);
+            pair_cnt[r] = 0;
+            recs[r] = ri;
+            return;
+        }
+        // join: windows of this contig with en > t_st && st < t_en (paf.rs:622-627, on stripped coordinates)
+        uint32_t cnt = 0;
+        if (win.st != nullptr && !win.general) {
+            const uint32_t clo = win.cont_lo[ri.t_name], chi = win.cont_hi[ri.t_name];
+            uint32_t lo = clo, hi = chi;
+            while (lo < hi) {  // first window whose running max of `en` exceeds t_st
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (win.en_pm[mid] > ri.t_st) hi = mid; else lo = mid + 1;
+            }
+            ri.wlo = lo;
+            hi = chi;
+            while (lo < hi) {  // first window with st >= t_en
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (win.st[mid] >= ri.t_en) hi = mid; else lo = mid + 1;
+            }
+            ri.whi = lo;
+            cnt = ri.whi - ri.wlo;
+        }
+        pair_cnt[r] = cnt;
+        recs[r] = ri;
+        return;
+    }
 
     // integrity at load (paf.rs:70): spans of the UNSTRIPPED record against the full CIGAR
+    const uint64_t t_en_in = (mode == 2) ? in.t_en[r] : ri.t_en;
     Ctr full = ctr_zero();
     if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end, acc);
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
-    if ((uint64_t)full.T != ri.t_en - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
+    if ((uint64_t)full.T != t_en_in - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
     if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
     if (ri.op_end > ri.op_first) {  // the sampled count stops at the last chunk boundary: look at the tail ops too
         const uint64_t base = ((ri.op_end - 1) >> SAMPLE_LOG2) << SAMPLE_LOG2;
@@ -585,41 +772,13 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
             if (op_len(w) == 0u || (k > ri.op_first && op_code(w) == op_code(ops[k - 1]))) ri.flags |= RF_SLOW;
         }
     }
-
     if (mode == 0) {  // rb stats --paf: counters of the record as read (bamstats.rs:91-105)
         ri.tot = full;
         write_stats(st, r, full.EQ, full.X + full.M, full.I, full.D, full.IEV, full.DEV, full.M);
         recs[r] = ri;
         return;
     }
-    const uint32_t e = strip_record(ops, ri);
-    if (e != RE_OK) {
-        report(err.rec, r, e);
-        pair_cnt[r] = 0;
-        recs[r] = ri;
-        return;
-    }
     ri.tot = (ri.eo0 == ri.op_first && ri.eo1 == ri.op_end) ? full : ctr_range(v, ri, ri.eo0, ri.eo1, acc);
-
-    // join: windows of this contig with en > t_st && st < t_en (paf.rs:622-627, on stripped coordinates)
-    uint32_t cnt = 0;
-    if (win.st != nullptr && !win.general) {
-        const uint32_t clo = win.cont_lo[ri.t_name], chi = win.cont_hi[ri.t_name];
-        uint32_t lo = clo, hi = chi;
-        while (lo < hi) {  // first window whose running max of `en` exceeds t_st
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (win.en_pm[mid] > ri.t_st) hi = mid; else lo = mid + 1;
-        }
-        ri.wlo = lo;
-        hi = chi;
-        while (lo < hi) {  // first window with st >= t_en
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (win.st[mid] >= ri.t_en) hi = mid; else lo = mid + 1;
-        }
-        ri.whi = lo;
-        cnt = ri.whi - ri.wlo;
-    }
-    pair_cnt[r] = cnt;
     recs[r] = ri;
 }
 
@@ -719,15 +878,73 @@ __device__ __forceinline__ uint32_t rank_of_pair(const uint64_t* __restrict__ pa
     return lo;
 }
 
-__global__ void __launch_bounds__(128)
+// CTA = LIFT_THREADS consecutive pairs in emission order.  On the sorted-BED path the pairs of a block that belong
+// to one record touch a contiguous run of ops (start of the first window .. end of the last one): that run and
+// its samples are staged in shared memory once (coalesced), so the per-pair searches and <=32-op walks of
+// lift_pair never leave the SM.  Blocks that straddle records, explicit pair lists (general path) and runs that
+// do not fit fall back to global memory through the same OpsView accessor.
+__global__ void __launch_bounds__(LIFT_THREADS, RB_LIFT_MINB)
 k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
        const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
        const uint64_t* __restrict__ names_off, int policy, PairRes* __restrict__ res, uint32_t* __restrict__ line_len, ErrSlots err) {
-    __shared__ uint32_t s_acc[9 * 128];
-    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_acc[9 * LIFT_THREADS];
+    __shared__ __align__(16) uint32_t s_ops[(LIFT_CCAP + 1) * SAMPLE];
+    __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
+    __shared__ uint32_t s_k[2];
+    __shared__ unsigned long long s_c[2];
+    const int tid = threadIdx.x;
+    const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
+    const uint64_t plast = (p0 + LIFT_THREADS <= n_pairs ? p0 + LIFT_THREADS : n_pairs) - 1;
+    const uint64_t p = p0 + tid;
+    OpsView v;
+    v.ops = ops; v.samples = samples;
+
+    // ---- block-level staging (fast path only) ----
+    if (win.pair_win == nullptr) {
+        if (tid == 0) s_k[0] = rank_of_pair(pair_off, n_rec, p0);
+        if (tid == 32) s_k[1] = rank_of_pair(pair_off, n_rec, plast);
+        __syncthreads();
+        const uint32_t k0 = s_k[0];
+        if (k0 == s_k[1]) {  // one record for the whole block (block-uniform branch)
+            const uint32_t r = rec_order[k0];
+            const RecInfo& R = recs[r];
+            const uint64_t pbase = pair_off[k0];
+            if (tid == 0 || tid == 32) {
+                unsigned long long c = ~0ull;
+                if (R.op_end > R.op_first && R.t_en > R.t_st) {
+                    if (tid == 0) {  // chunk that holds the start boundary of the block's first pair
+                        const uint64_t st = win.st[R.wlo + (uint32_t)(p0 - pbase)];
+                        c = chunk_of(v, R, (uint32_t)((st > R.t_st ? st : R.t_st) - R.t_st));
+                    } else {         // chunk that holds the end boundary of the block's last pair
+                        const uint64_t en = win.en[R.wlo + (uint32_t)(plast - pbase)];
+                        c = chunk_of(v, R, (uint32_t)((en < R.t_en ? en : R.t_en) - 1 - R.t_st));
+                    }
+                }
+                s_c[tid >> 5] = c;
+            }
+            __syncthreads();
+            const uint64_t c_lo = s_c[0], c_hi = s_c[1];
+            if (c_lo != ~0ull && c_hi != ~0ull && c_hi >= c_lo && c_hi - c_lo < (uint64_t)LIFT_CCAP) {
+                const uint64_t o_lo = c_lo << SAMPLE_LOG2;
+                uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
+                if (o_hi > R.op_end) o_hi = R.op_end;
+                for (uint64_t k = o_lo + tid; k < o_hi; k += LIFT_THREADS) s_ops[k - o_lo] = ops[k];
+                const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
+                const uint64_t c_max = (R.op_end - 1) >> SAMPLE_LOG2;
+                constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
+                for (uint64_t i = tid; i < nc * V; i += LIFT_THREADS) {
+                    const uint64_t c = c_lo + i / V;
+                    if (c <= c_max) reinterpret_cast<uint4*>(s_smp)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(samples) + c * V + i % V);
+                }
+                v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
+                v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = (c_hi + 1 <= c_max ? c_hi + 2 : c_hi + 1);
+            }
+            __syncthreads();
+        }
+    }
     if (p >= n_pairs) return;
     ClassAcc acc;
-    acc.sum = s_acc + threadIdx.x; acc.stride = 128;
+    acc.sum = s_acc + tid; acc.stride = LIFT_THREADS;
     const uint32_t k = rank_of_pair(pair_off, n_rec, p);
     const uint32_t r = rec_order[k];
     const RecInfo ri = recs[r];
@@ -736,11 +953,48 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     const uint64_t w_st = win.st[w], w_en = win.en[w];
     PairRes pr;
     uint32_t len = 0;
-    OpsView v;
-    v.ops = ops; v.samples = samples;
     const bool overlaps = ri.t_en > w_st && ri.t_st < w_en;  // the brute-force / nested-window candidates can be a superset
     const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, overlaps, pr, acc);
     __syncwarp();
+    if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
+    if (pr.kind != PK_DROP) {
+        const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
+        const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
+        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+        len = line_bytes(ri, pr, qn, tn, idl);
+    }
+    res[p] = pr;
+    line_len[p] = len;
+}
+
+// K4' (fast path): joins the two half results k_scan_lift left for each pair -> PairRes + line size
+__global__ void __launch_bounds__(128)
+k_combine(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
+          const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, WinView win, const uint64_t* __restrict__ names_off,
+          const HalfS* __restrict__ hs, const HalfE* __restrict__ he, PairRes* __restrict__ res, uint32_t* __restrict__ line_len,
+          ErrSlots err) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint32_t k = rank_of_pair(pair_off, n_rec, p);
+    const uint32_t r = rec_order[k];
+    const RecInfo ri = recs[r];
+    const uint32_t w = ri.wlo + (uint32_t)(p - pair_off[k]);
+    const uint64_t w_st = win.st[w], w_en = win.en[w];
+    HalfS a;
+    HalfE b;
+    {
+        const uint4* pa = reinterpret_cast<const uint4*>(hs + p);
+        const uint4* pb = reinterpret_cast<const uint4*>(he + p);
+        uint4* qa = reinterpret_cast<uint4*>(&a);
+        uint4* qb = reinterpret_cast<uint4*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { qa[i] = ld_nc_v4(pa + i); qb[i] = ld_nc_v4(pb + i); }
+    }
+    OpsView v;
+    v.ops = ops; v.samples = nullptr;
+    PairRes pr;
+    uint32_t len = 0;
+    const uint32_t e = combine_pair(v, ri, w_st, w_en, a, b, pr);
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
         const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
@@ -1105,11 +1359,33 @@ void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_r
     const uint64_t warps = (uint64_t)n_rec + 1;
     k_rec_ops<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(text, cigar_off, n_rec, tile_state, op_off, heads, err);
 }
-void launch_samples(const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads, Ctr* samples,
-                    uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket, cudaStream_t s) {
+static size_t scan_lift_smem(bool lift) {
+    return (size_t)(SMP_THREADS * (SAMPLE + 1) + 9 * SMP_THREADS + (lift ? 2 * SL_WCAP : 0)) * sizeof(uint32_t);
+}
+void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
+                      Ctr* samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
+                      LiftArgs la, cudaStream_t s) {
     const uint64_t blocks = (n_ops_bound + SMP_OPS - 1) / SMP_OPS;
     if (blocks == 0) return;
-    k_samples<<<(unsigned)blocks, SMP_THREADS, 0, s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_scan_lift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(true));
+        cudaFuncSetAttribute(k_scan_lift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(false));
+        attr_set = true;
+    }
+    if (lift)
+        k_scan_lift<true><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(true), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg,
+                                                                                      blk_pre, ticket, la);
+    else
+        k_scan_lift<false><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(false), s>>>(ops, n_ops_dev, heads, samples, blk_state,
+                                                                                        blk_agg, blk_pre, ticket, la);
+}
+void launch_combine(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                    const uint32_t* ops, WinView win, const uint64_t* names_off, const HalfS* hs, const HalfE* he, PairRes* res,
+                    uint32_t* line_len, ErrSlots err, cudaStream_t s) {
+    if (n_pairs == 0) return;
+    k_combine<<<(unsigned)((n_pairs + 127) / 128), 128, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, win, names_off, hs, he,
+                                                                res, line_len, err);
 }
 void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, ErrSlots err, cudaStream_t s) {
     if (n_rec == 0) return;
@@ -1127,7 +1403,7 @@ void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
                  const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, PairRes* res,
                  uint32_t* line_len, ErrSlots err, cudaStream_t s) {
     if (n_pairs == 0) return;
-    k_lift<<<(unsigned)((n_pairs + 127) / 128), 128, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
+    k_lift<<<(unsigned)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS), LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
                                                              policy, res, line_len, err);
 }
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,

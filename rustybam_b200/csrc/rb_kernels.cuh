@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "lift_core.cuh"
 #include "rb_common.cuh"
 
 namespace rb {
@@ -11,6 +12,22 @@ constexpr int TOK_TILE = TOK_THREADS * 16;  // text bytes per tokeniser tile
 constexpr int TEXT_FRONT_PAD = 16;          // bytes of 0xFF in front of the text (look-behind halo of tile 0)
 constexpr int SMP_THREADS = 256;
 constexpr int SMP_OPS = SMP_THREADS * (int)SAMPLE;  // ops per sample-scan block
+constexpr int SL_WCAP = 2048;                // window boundaries of one block staged in shared memory (each of starts / ends)
+// tuning knobs (overridable with -D for sweeps on the GPU box, see tools/sweep.sh)
+#ifndef RB_LIFT_THREADS
+#define RB_LIFT_THREADS 128
+#endif
+#ifndef RB_LIFT_CCAP
+#define RB_LIFT_CCAP 96
+#endif
+#ifndef RB_LIFT_MINB
+#define RB_LIFT_MINB 6
+#endif
+#ifndef RB_SMP_MINB
+#define RB_SMP_MINB 3
+#endif
+constexpr int LIFT_THREADS = RB_LIFT_THREADS;  // pairs per k_lift block
+constexpr int LIFT_CCAP = RB_LIFT_CCAP;        // 32-op chunks of one record a k_lift block stages in shared memory
 constexpr int LNS_THREADS = 256;
 constexpr int SER_LINES = 128;              // lines per serialiser block
 constexpr int SER_CAP = 40 * 1024;          // smem bytes for composing a line group
@@ -63,10 +80,27 @@ void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsig
                      unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, cudaStream_t s);
 void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,
                     uint64_t* op_off, uint32_t* heads, ErrSlots err, cudaStream_t s);
-void launch_samples(const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads, Ctr* samples,
-                    uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket, cudaStream_t s);
+// fast-path (sorted BED, right-most policy) arguments of k_scan_lift: where the half results go
+struct LiftArgs {
+    const RecInfo* recs;       // after k_rec_prep mode 1
+    const uint64_t* op_off;
+    uint32_t n_rec;
+    const uint32_t* rec_rank;  // record -> position in emission order
+    const uint64_t* pair_off;  // emission-ordered pair offsets
+    const uint64_t* w_st;
+    const uint64_t* w_en;
+    HalfS* hs;
+    HalfE* he;
+};
+// sampled segmented scan; lift == true additionally resolves the window boundaries of every record (fast path)
+void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
+                      Ctr* samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
+                      LiftArgs la, cudaStream_t s);
+void launch_combine(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                    const uint32_t* ops, WinView win, const uint64_t* names_off, const HalfS* hs, const HalfE* he, PairRes* res,
+                    uint32_t* line_len, ErrSlots err, cudaStream_t s);
 void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, ErrSlots err, cudaStream_t s);
-// mode 0: rb stats (full record, no strip) ; mode 1: liftover (strip + join)
+// mode 0: rb stats (after the scan) ; mode 1: liftover phase A (strip + join, before the scan) ; mode 2: phase B (after the scan)
 void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32_t* ops, const Ctr* samples, WinView win,
                      RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s);
 void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s);

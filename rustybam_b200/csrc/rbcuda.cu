@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,6 +54,7 @@ struct rb_ctx {
     bool own_stream = true;
     std::string err;
     bool profiling = false;
+    int lift_mode = RB_LIFT_SEARCH;
     std::vector<KEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<rb_kernel_time> times;
@@ -72,7 +74,7 @@ struct rb_batch {
     DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, cont_lo, cont_hi;
     // intermediates
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
-    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre;
+    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e;
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -241,8 +243,8 @@ NumDev num_view(const rb_batch* b, uint64_t n) {
     return d;
 }
 
-// tokenise + record offsets + sampled scan (shared by liftover and stats)
-int run_front(rb_ctx* ctx, rb_batch* b) {
+// tokenise + record offsets (shared by liftover and stats)
+int run_tok(rb_ctx* ctx, rb_batch* b) {
     cudaStream_t s = ctx->stream;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     CU(cudaMemsetAsync(sc, 0, 4 * sizeof(uint32_t), s));
@@ -262,11 +264,19 @@ int run_front(rb_ctx* ctx, rb_batch* b) {
         launch_rec_ops(text, b->cigar_off.as<uint64_t>(), b->n_rec, b->tile_state.as<unsigned long long>(), b->op_off.as<uint64_t>(),
                        b->heads.as<uint32_t>(), err, s);
     }
+    CU(cudaGetLastError());
+    return RB_OK;
+}
+
+// sampled segmented scan of the prefix counters; `la` != nullptr: fused with the window-boundary resolution (fast path)
+int run_scan(rb_ctx* ctx, rb_batch* b, const LiftArgs* la) {
+    cudaStream_t s = ctx->stream;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
     {
-        KScope k(ctx, "k_samples");
-        launch_samples(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + b->n_rec, b->ops_bound, b->heads.as<uint32_t>(),
-                       b->samples.as<Ctr>(), b->blk_state.as<uint32_t>(), b->blk_agg.as<ScanPayload>(), b->blk_pre.as<ScanPayload>(),
-                       sc + SC_TICKET_SMP, s);
+        KScope k(ctx, la ? "k_scan_lift" : "k_samples");
+        launch_scan_lift(la != nullptr, b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + b->n_rec, b->ops_bound, b->heads.as<uint32_t>(),
+                         b->samples.as<Ctr>(), b->blk_state.as<uint32_t>(), b->blk_agg.as<ScanPayload>(), b->blk_pre.as<ScanPayload>(),
+                         sc + SC_TICKET_SMP, la ? *la : LiftArgs{}, s);
     }
     CU(cudaGetLastError());
     return RB_OK;
@@ -326,7 +336,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
     delete b;
 }
@@ -358,6 +368,12 @@ int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream) {
         ctx->own_stream = true;
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamCreate");
     }
+    return RB_OK;
+}
+
+int rb_ctx_set_lift_mode(rb_ctx* ctx, int mode) {
+    if (!ctx || (mode != RB_LIFT_SEARCH && mode != RB_LIFT_STREAM)) return RB_ERR_BAD_ARG;
+    ctx->lift_mode = mode;
     return RB_OK;
 }
 
@@ -423,7 +439,7 @@ static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_w
     CU(b->ops.ensure(b->ops_bound * 4 + 64));
     CU(b->tile_state.ensure(b->n_tiles * 8));
     CU(b->heads.ensure((b->ops_bound / SAMPLE + 2) * 4));
-    CU(b->samples.ensure((b->ops_bound / SAMPLE + 2) * sizeof(Ctr)));
+    CU(b->samples.ensure((b->ops_bound / SAMPLE + 2) * SUBS * sizeof(Ctr)));
     const size_t smp_blocks = b->ops_bound / SMP_OPS + 2;
     CU(b->blk_state.ensure(smp_blocks * 4));
     CU(b->blk_agg.ensure(smp_blocks * sizeof(ScanPayload)));
@@ -561,7 +577,9 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
-    int rc = run_front(ctx, b);
+    int rc = run_tok(ctx, b);
+    if (rc != RB_OK) return rc;
+    rc = run_scan(ctx, b, nullptr);
     if (rc != RB_OK) return rc;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
@@ -597,16 +615,16 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
-    int rc = run_front(ctx, b);
+    int rc = run_tok(ctx, b);
     if (rc != RB_OK) return rc;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
     WinView win = win_view(b);
     const uint32_t n = b->n_rec;
-    {
+    {   // phase A: indel strip + window join (needs the ops only)
         KScope k(ctx, "k_rec_prep");
-        launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), win,
-                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+        launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), nullptr, win, b->recs.as<RecInfo>(),
+                        b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
     }
     if (b->general && b->n_win) {
         KScope k(ctx, "k_pair_count_bf");
@@ -627,9 +645,15 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
         CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
     }
-    rc = map_err(ctx, b, hs[0], hs[1]);
+    // CIGAR parse errors end the call here; strip panics wait for the integrity check of phase B so that the
+    // error of the FIRST failing record is reported, whatever its kind
+    rc = map_err(ctx, b, hs[0], UINT64_MAX);
     if (rc != RB_OK) { flush_times(ctx); return rc; }
     const uint64_t n_ops = hs[2], P = hs[4];
+    // RB_LIFT_SEARCH (default): sampled scan, then one search per pair out of staged shared memory (k_lift).
+    // RB_LIFT_STREAM (sorted BED + right-most policy only): the scan resolves the window boundaries itself
+    // (k_scan_lift + k_combine) — no per-pair search at all, cost independent of the window count.
+    const bool fused = ctx->lift_mode == RB_LIFT_STREAM && !b->general && policy == RB_POLICY_RIGHTMOST && P > 0;
 
     CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
     CU(b->line_len.ensure(P * 4 + 64));
@@ -640,6 +664,21 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     CU(b->ln_agg.ensure(ln_blocks * 16));
     CU(b->ln_pre.ensure(ln_blocks * 16));
     CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
+    if (fused) {
+        CU(b->half_s.ensure(P * sizeof(HalfS) + 64));
+        CU(b->half_e.ensure(P * sizeof(HalfE) + 64));
+        LiftArgs la{b->recs.as<RecInfo>(), b->op_off.as<uint64_t>(), n, b->rec_rank.as<uint32_t>(), b->pair_off.as<uint64_t>(),
+                    win.st, win.en, b->half_s.as<HalfS>(), b->half_e.as<HalfE>()};
+        rc = run_scan(ctx, b, &la);
+    } else {
+        rc = run_scan(ctx, b, nullptr);
+    }
+    if (rc != RB_OK) return rc;
+    {   // phase B: integrity, RF_SLOW, counters of the stripped op range
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(2, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), win,
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+    }
     if (b->general && P) {
         CU(b->pair_win.ensure(P * 4 + 64));
         KScope k(ctx, "k_pair_fill_bf");
@@ -647,7 +686,12 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                             b->pair_win.as<uint32_t>(), s);
         win.pair_win = b->pair_win.as<uint32_t>();
     }
-    {
+    if (fused) {
+        KScope k(ctx, "k_combine");
+        launch_combine(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(), win,
+                       b->names_off.as<uint64_t>(), b->half_s.as<HalfS>(), b->half_e.as<HalfE>(), b->pair_res.as<PairRes>(),
+                       b->line_len.as<uint32_t>(), err, s);
+    } else {
         KScope k(ctx, "k_lift");
         launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
                     b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->pair_res.as<PairRes>(),

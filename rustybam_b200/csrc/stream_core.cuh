@@ -43,6 +43,8 @@ struct WinGlobal {
 struct SegRec {          // what a segment needs to know about its record
     uint64_t eo0, eo1;   // stripped op range
     uint32_t wlo, whi;   // overlapping windows
+    uint32_t s_lo, s_hi; // search range of the start boundaries ([wlo, whi), or a narrower range known to hold them)
+    uint32_t e_lo, e_hi; // same for the end boundaries
     uint64_t pair0;      // index of pair (record, wlo) in emission order
 };
 
@@ -56,10 +58,10 @@ RB_HD void stream_segment(const OpsView& v, const SegRec& r, const WA& wa, uint6
                           uint32_t Tseg, ClassAcc& acc, EmitS&& emit_s, EmitE&& emit_e) {
     if (Tseg == 0 || r.whi <= r.wlo) return;
     const uint32_t T0 = base.T, T1 = T0 + Tseg;
-    uint32_t js = first_true(r.wlo, r.whi, [&](uint32_t j) { return wa.ps(j) >= T0; });
-    const uint32_t js_end = first_true(js, r.whi, [&](uint32_t j) { return wa.ps(j) >= T1; });
-    uint32_t je = first_true(r.wlo, r.whi, [&](uint32_t j) { return wa.pe(j) > T0; });
-    const uint32_t je_end = first_true(je, r.whi, [&](uint32_t j) { return wa.pe(j) > T1; });
+    uint32_t js = first_true(r.s_lo, r.s_hi, [&](uint32_t j) { return wa.ps(j) >= T0; });
+    const uint32_t js_end = first_true(js, r.s_hi, [&](uint32_t j) { return wa.ps(j) >= T1; });
+    uint32_t je = first_true(r.e_lo, r.e_hi, [&](uint32_t j) { return wa.pe(j) > T0; });
+    const uint32_t je_end = first_true(je, r.e_hi, [&](uint32_t j) { return wa.pe(j) > T1; });
     if (js == js_end && je == je_end) return;
     uint32_t next_s = js < js_end ? wa.ps(js) : 0xFFFFFFFFu;
     uint32_t next_e = je < je_end ? wa.pe(je) : 0xFFFFFFFFu;

@@ -96,13 +96,21 @@ int main(int argc, char** argv) {
     }
     std::vector<uint8_t> head(ops.size() + 1, 0);
     for (size_t r = 0; r < recs.size(); r++) head[op_off[r]] = 1;
-    std::vector<Ctr> samples(ops.size() / SAMPLE + 2);
+    std::vector<Ctr> samples((ops.size() / SAMPLE + 2) * SUBS);
     {
-        Ctr run = ctr_zero();
+        Ctr run = ctr_zero(), rel = ctr_zero();  // run: since the record's first op; rel: since the chunk start / last head in the chunk
+        bool head_in_chunk = false;
         for (size_t k = 0; k < ops.size(); k++) {
-            if (head[k]) run = ctr_zero();
-            if (k % SAMPLE == 0) samples[k / SAMPLE] = run;
+            if (k % SAMPLE == 0) { rel = ctr_zero(); head_in_chunk = false; }
+            if (head[k]) { run = ctr_zero(); rel = ctr_zero(); if (k % SAMPLE) head_in_chunk = true; }
+            if (k % SAMPLE == 0) samples[(k / SAMPLE) * SUBS] = run;
+            else if (k % SUB_OPS == 0) {
+                Ctr e = rel;
+                e.aux = head_in_chunk ? SUB_ABS : 0u;
+                samples[(k / SAMPLE) * SUBS + (k % SAMPLE) / SUB_OPS] = e;
+            }
             ctr_add_op(run, ops[k]);
+            ctr_add_op(rel, ops[k]);
         }
     }
     OpsView view;
@@ -258,7 +266,7 @@ int main(int argc, char** argv) {
             std::vector<HalfS> hs(W, junk_s);
             std::vector<HalfE> he(W, junk_e);
             std::vector<int> ws(W, 0), we(W, 0);
-            SegRec sr{ri.eo0, ri.eo1, 0u, W, 0ull};
+            SegRec sr{ri.eo0, ri.eo1, 0u, W, 0u, W, 0u, W, 0ull};
             WinGlobal wa{wst.data(), wen.data(), ri.t_st, ri.t_en};
             Ctr run = ctr_zero();
             uint64_t k = ri.op_first;

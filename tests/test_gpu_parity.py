@@ -122,6 +122,20 @@ def test_random_eqx_tiling(ctx, seed, policy):
 
 
 @pytest.mark.parametrize("seed", range(6))
+def test_random_streaming_lift_mode(ctx, seed):
+    # RB_LIFT_STREAM: window boundaries resolved inside the prefix scan (k_scan_lift + k_combine)
+    ctx.set_lift_mode(capi.LIFT_STREAM)
+    try:
+        paf_text, contigs = gen.random_paf(400 + seed, n_contigs=4, recs_per_contig=8, style="all" if seed % 2 else "eqx",
+                                           canonical=(seed < 4), allow_zero=(seed >= 4), clips=(seed % 3 == 0))
+        check_against_oracle(ctx, paf_text, gen.tiling_bed(contigs, 5 + seed))
+        check_against_oracle(ctx, paf_text, gen.random_bed(seed, contigs, 80, sort=True))
+        check_against_oracle(ctx, orc.golden_paf(), gen.tiling_bed({"chr20": 66210247, "chr21": 45827691, "chr22": 51353906}, 10_000 + seed))
+    finally:
+        ctx.set_lift_mode(capi.LIFT_SEARCH)
+
+
+@pytest.mark.parametrize("seed", range(6))
 def test_random_unsorted_nested_bed_general_path(ctx, seed):
     # BED file order is never sorted by the reference (Q5); nested + duplicate rows
     paf_text, contigs = gen.random_paf(100 + seed, n_contigs=3, recs_per_contig=6)

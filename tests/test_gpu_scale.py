@@ -131,6 +131,27 @@ def test_full_scale_liftover_properties(ctx, full):
     assert n_early < len(first) // 50
 
 
+@pytest.mark.parametrize("width", [1000, 10_000, 100_000])
+def test_full_scale_streaming_path_equals_search_path(ctx, full, width):
+    """k_scan_lift + k_combine (boundaries resolved while scanning) against k_samples + k_lift (one search per
+    pair, the path the small-case oracle parity also pins): identical bytes, counters and mirror at full size."""
+    wins = full.tiling_windows(width)
+    a = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    ctx.set_lift_mode(capi.LIFT_STREAM)
+    try:
+        b = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    finally:
+        ctx.set_lift_mode(capi.LIFT_SEARCH)
+    assert a["n_out"] == b["n_out"] and a["n_pairs"] == b["n_pairs"]
+    assert a["paf_text"] == b["paf_text"]
+    for k in ("q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len", "rec_idx", "win_idx"):
+        assert (a[k] == b[k]).all(), k
+    for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches"):
+        assert (a["stats"][k] == b["stats"][k]).all(), k
+    for k in ("id_by_matches", "id_by_events", "id_by_all"):
+        assert (a["stats"][k].view(np.uint32) == b["stats"][k].view(np.uint32)).all(), k
+
+
 def test_rb_cli_matches_oracle(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
