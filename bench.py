@@ -168,8 +168,9 @@ def main():
     lib = capi.load()
     # page-lock the big input buffers so that the e2e H2D copies are DMA from pinned memory
     pinned = []
+    ids_bytes = int(wins.c.ids_off[wins.n_win]) if wins.c.ids_off else 0  # 3-column BED: ids are formatted on the GPU
     for ptr, nbytes in ((shard.c.cigar, shard.cigar_nbytes), (wins.c.st, wins.n_win * 8), (wins.c.en, wins.n_win * 8),
-                        (wins.c.ids, int(wins.c.ids_off[wins.n_win])), (wins.c.ids_off, (wins.n_win + 1) * 8),
+                        (wins.c.ids, ids_bytes), (wins.c.ids_off, (wins.n_win + 1) * 8 if ids_bytes else 0),
                         (wins.c.bed_row, wins.n_win * 4), (wins.c.t_id, wins.n_win * 4)):
         addr = C.cast(ptr, C.c_void_p).value
         if addr and nbytes and lib.rb_host_register(C.c_void_p(addr), nbytes) == 0:
@@ -239,7 +240,7 @@ def main():
 
     n_out, n_pairs, n_ops = summ["n_out"], summ["n_pairs"], summ["n_ops"]
     out_bytes, cigar_bytes = summ["out_bytes"], summ["cigar_bytes"]
-    h2d = (cigar_bytes + shard.n_rec * (8 * 8 + 1 + 8) + wins.n_win * (8 + 8 + 8 + 4) + int(wins.c.ids_off[wins.n_win]))
+    h2d = (cigar_bytes + shard.n_rec * (8 * 8 + 1 + 8) + wins.n_win * (8 + 8 + 4) + ((wins.n_win + 1) * 8 + ids_bytes if ids_bytes else 0))
     d2h = out_bytes + (n_out + 1) * 8 + n_out * 40
 
     # ---- reduce over ranks: time = max, units = sum ----

@@ -83,14 +83,16 @@ typedef struct rb_records {
 /* BED windows (src/bed.rs:14-21 Region), SoA, sorted by (t_id, st) — stable, so equal keys keep
  * BED file order.  bed_row = row index in the BED file: it defines the emission order within a
  * record (liftover.rs:123-126) and is echoed in rb_lift_out.win_idx.  ids = Region.id per window
- * (BED column 4, else "{chrom}:{st+1}-{en}", bed.rs:150-153), parallel to st/en. */
+ * (BED column 4, else "{chrom}:{st+1}-{en}", bed.rs:150-153), parallel to st/en.  For a BED file
+ * without a 4th column pass ids = ids_off = NULL: the library formats the default id on the device
+ * (no per-window string ever exists on the host or crosses PCIe). */
 typedef struct rb_windows {
     uint32_t n_win;
     const uint32_t* t_id;
     const uint64_t* st;
     const uint64_t* en;
     const uint32_t* bed_row;
-    const uint8_t* ids;
+    const uint8_t* ids;      /* nullable together with ids_off */
     const uint64_t* ids_off; /* n_win + 1 */
 } rb_windows;
 
@@ -156,6 +158,10 @@ int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream);
 #define RB_LIFT_SEARCH 0
 #define RB_LIFT_STREAM 1
 int rb_ctx_set_lift_mode(rb_ctx* ctx, int mode);
+/* rb_liftover cuts a call whose records are in emission order (PAF grouped by target) into up to 8 slices of
+ * consecutive records, each of at least `min_slice_bytes` of CIGAR text; the device->host copies of a slice overlap the
+ * upload and the kernels of the following ones.  Default 16 MiB; 0 = never slice.  Results do not depend on it. */
+int rb_ctx_set_slicing(rb_ctx* ctx, uint64_t min_slice_bytes);
 /* per-kernel CUDA-event timing (off by default; adds an event pair around every launch) */
 int rb_ctx_set_profiling(rb_ctx* ctx, int on);
 int rb_ctx_kernel_times(rb_ctx* ctx, rb_kernel_time* out, int cap, int reset); /* returns count */

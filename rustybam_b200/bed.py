@@ -9,10 +9,10 @@ from .capi import Windows
 
 
 class Region:
-    __slots__ = ("name", "st", "en", "id")
+    __slots__ = ("name", "st", "en", "id", "default_id")
 
-    def __init__(self, name, st, en, id_):
-        self.name, self.st, self.en, self.id = name, st, en, id_
+    def __init__(self, name, st, en, id_, default_id=False):
+        self.name, self.st, self.en, self.id, self.default_id = name, st, en, id_, default_id
 
 
 def parse_bed_text(text: bytes):
@@ -31,7 +31,7 @@ def parse_bed_text(text: bytes):
         if st > 0xFFFFFFFFFFFFFFFF or en > 0xFFFFFFFFFFFFFFFF:
             continue
         rid = f[3] if len(f) > 3 else f[0] + b":" + str(st + 1).encode() + b"-" + str(en).encode()
-        out.append(Region(f[0], st, en, rid))
+        out.append(Region(f[0], st, en, rid, default_id=len(f) <= 3))
     return out
 
 
@@ -47,5 +47,6 @@ def pack_windows(rgns, name_index: dict) -> Windows:
     t_id = np.array([name_index[r.name] for _, r in keep], dtype=np.uint32)
     st = np.array([r.st for _, r in keep], dtype=np.uint64)
     en = np.array([r.en for _, r in keep], dtype=np.uint64)
-    w = Windows(t_id, st, en, [r.id for _, r in keep])
-    return w
+    # 3-column BED: ids stay on the device side (rb_windows.ids == NULL -> "{chrom}:{st+1}-{en}" is formatted by the GPU)
+    ids = None if keep and all(r.default_id for _, r in keep) else [r.id for _, r in keep]
+    return Windows(t_id, st, en, ids)

@@ -22,7 +22,7 @@ WANT_TEXT, WANT_NUMERIC = 1, 2
 LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
-    "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_kernel_times",
+    "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_set_slicing", "rb_ctx_kernel_times",
     "rb_liftover", "rb_stats", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
     "rb_host_unregister",
@@ -87,6 +87,7 @@ def load():
     lib.rb_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb_ctx_set_profiling.argtypes = [C.c_void_p, C.c_int]
     lib.rb_ctx_set_lift_mode.argtypes = [C.c_void_p, C.c_int]
+    lib.rb_ctx_set_slicing.argtypes = [C.c_void_p, C.c_uint64]
     lib.rb_ctx_kernel_times.argtypes = [C.c_void_p, C.POINTER(RbKernelTime), C.c_int, C.c_int]
     lib.rb_liftover.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.POINTER(RbWindows), C.c_int, C.c_uint32, C.POINTER(RbLiftOut),
                                 C.POINTER(RbStatsOut)]
@@ -159,16 +160,20 @@ class Windows:
         rc = lib.rb_sort_windows(n, _ptr(t_id, u32p), _ptr(st, u64p), _ptr(perm, u32p))
         assert rc == 0
         self.t_id, self.st, self.en, self.bed_row = t_id[perm].copy(), st[perm].copy(), en[perm].copy(), perm
-        ids = [i if isinstance(i, bytes) else i.encode() for i in ids]
-        ids = [ids[j] for j in perm]
-        self.ids_blob = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
-        self.ids_off = np.zeros(n + 1, dtype=np.uint64)
-        if n:
-            self.ids_off[1:] = np.cumsum([len(i) for i in ids], dtype=np.uint64)
         s = RbWindows()
         s.n_win = n
         s.t_id, s.st, s.en = _ptr(self.t_id, u32p), _ptr(self.st, u64p), _ptr(self.en, u64p)
-        s.bed_row, s.ids, s.ids_off = _ptr(self.bed_row, u32p), _ptr(self.ids_blob, u8p), _ptr(self.ids_off, u64p)
+        s.bed_row = _ptr(self.bed_row, u32p)
+        if ids is None:  # default ids: formatted on the device
+            s.ids, s.ids_off = None, None
+        else:
+            ids = [i if isinstance(i, bytes) else i.encode() for i in ids]
+            ids = [ids[j] for j in perm]
+            self.ids_blob = np.frombuffer(b"".join(ids) + b"\0", dtype=np.uint8).copy()
+            self.ids_off = np.zeros(n + 1, dtype=np.uint64)
+            if n:
+                self.ids_off[1:] = np.cumsum([len(i) for i in ids], dtype=np.uint64)
+            s.ids, s.ids_off = _ptr(self.ids_blob, u8p), _ptr(self.ids_off, u64p)
         self.c = s
         self.n_win = n
 
@@ -210,6 +215,9 @@ class Context:
 
     def set_lift_mode(self, mode):
         self._check(self.lib.rb_ctx_set_lift_mode(self.h, int(mode)))
+
+    def set_slicing(self, min_slice_bytes=16 << 20):
+        self._check(self.lib.rb_ctx_set_slicing(self.h, int(min_slice_bytes)))
 
     def set_profiling(self, on=True):
         self._check(self.lib.rb_ctx_set_profiling(self.h, int(on)))

@@ -14,6 +14,7 @@
 //   K5 k_serialise    PAF text + numeric mirror + stats rows (paf.rs:923-943, bamstats.rs:138-142)
 //
 // All of it is HBM-bound integer/byte work: no tensor cores on purpose.
+#include <algorithm>
 #include <cstdio>
 
 #include "lift_core.cuh"
@@ -782,6 +783,29 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     recs[r] = ri;
 }
 
+// Window table checks (the host never walks the 3 M-row table): bit 0 = not sorted by (t_id, st) or t_id out of
+// range, bit 1 = general layout (inside a contig `en` or the BED row number decreases somewhere: nested rows, or a file
+// order that is not the sorted order) -> the brute-force join keeps the reference's emission order (Q5).
+__global__ void __launch_bounds__(256)
+k_win_check(const uint32_t* __restrict__ t_id, const uint64_t* __restrict__ st, const uint64_t* __restrict__ en,
+            const uint32_t* __restrict__ row, uint32_t n_win, uint32_t n_names, uint32_t* flags) {
+    uint32_t f = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_win; i += gridDim.x * blockDim.x) {
+        const uint32_t t = t_id[i];
+        if (t >= n_names) f |= 1u;
+        if (i) {
+            const uint32_t tp = t_id[i - 1];
+            if (t < tp) f |= 1u;
+            if (t == tp) {
+                if (st[i] < st[i - 1]) f |= 1u;
+                if (en[i] < en[i - 1] || row[i] < row[i - 1]) f |= 2u;
+            }
+        }
+    }
+    f = __reduce_or_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(flags, f);
+}
+
 // pair offsets in emission order: exclusive scan of pair_cnt[rec_order[k]] (single block; n_rec is small)
 __global__ void __launch_bounds__(1024) k_pair_scan(const uint32_t* __restrict__ pair_cnt, const uint32_t* __restrict__ rec_order,
                                                     uint32_t n_rec, uint64_t* __restrict__ pair_off) {
@@ -869,6 +893,11 @@ __global__ void __launch_bounds__(256) k_pair_fill_bf(const RecInfo* __restrict_
 // ------------------------------------------------------------------------------------------------
 // K4  lift: one thread per (window, record) pair
 // ------------------------------------------------------------------------------------------------
+// bytes of Region.id of window w: BED column 4, else "{chrom}:{st+1}-{en}" (bed.rs:150-153)
+__device__ __forceinline__ uint32_t win_id_len(const WinView& win, uint32_t w, uint32_t t_name_len, uint64_t w_st, uint64_t w_en) {
+    if (win.ids_off) return (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+    return t_name_len + 1u + ndigits64(w_st + 1) + 1u + ndigits64(w_en);
+}
 __device__ __forceinline__ uint32_t rank_of_pair(const uint64_t* __restrict__ pair_off, uint32_t n_rec, uint64_t p) {
     uint32_t lo = 0, hi = n_rec;  // largest k with pair_off[k] <= p
     while (hi - lo > 1) {
@@ -892,6 +921,9 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
     __shared__ uint32_t s_k[2];
     __shared__ unsigned long long s_c[2];
+    __shared__ __align__(16) RecInfo s_rec;
+    __shared__ uint32_t s_r;
+    bool uniform = false;
     const int tid = threadIdx.x;
     const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
     const uint64_t plast = (p0 + LIFT_THREADS <= n_pairs ? p0 + LIFT_THREADS : n_pairs) - 1;
@@ -906,8 +938,14 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
         __syncthreads();
         const uint32_t k0 = s_k[0];
         if (k0 == s_k[1]) {  // one record for the whole block (block-uniform branch)
+            uniform = true;
             const uint32_t r = rec_order[k0];
-            const RecInfo& R = recs[r];
+            static_assert(sizeof(RecInfo) % 16 == 0, "RecInfo is copied in 16-byte vectors");
+            if (tid < (int)(sizeof(RecInfo) / 16))
+                reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(&recs[r])[tid];
+            if (tid == 0) s_r = r;
+            __syncthreads();
+            const RecInfo& R = s_rec;
             const uint64_t pbase = pair_off[k0];
             if (tid == 0 || tid == 32) {
                 unsigned long long c = ~0ull;
@@ -945,9 +983,16 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     if (p >= n_pairs) return;
     ClassAcc acc;
     acc.sum = s_acc + tid; acc.stride = LIFT_THREADS;
-    const uint32_t k = rank_of_pair(pair_off, n_rec, p);
-    const uint32_t r = rec_order[k];
-    const RecInfo ri = recs[r];
+    uint32_t k, r;
+    const RecInfo* rp;
+    if (uniform) {  // the block's record sits in shared memory: no per-thread search, no per-thread 208-byte load
+        k = s_k[0]; r = s_r; rp = &s_rec;
+    } else {
+        k = rank_of_pair(pair_off, n_rec, p);
+        r = rec_order[k];
+        rp = &recs[r];
+    }
+    const RecInfo& ri = *rp;
     const uint64_t j = p - pair_off[k];
     const uint32_t w = win.pair_win ? win.pair_win[p] : (ri.wlo + (uint32_t)j);
     const uint64_t w_st = win.st[w], w_en = win.en[w];
@@ -960,7 +1005,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     if (pr.kind != PK_DROP) {
         const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
         const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
-        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : win_id_len(win, w, tn, w_st, w_en);
         len = line_bytes(ri, pr, qn, tn, idl);
     }
     res[p] = pr;
@@ -999,7 +1044,7 @@ k_combine(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_
     if (pr.kind != PK_DROP) {
         const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
         const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
-        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : (uint32_t)(win.ids_off[w + 1] - win.ids_off[w]);
+        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : win_id_len(win, w, tn, w_st, w_en);
         len = line_bytes(ri, pr, qn, tn, idl);
     }
     res[p] = pr;
@@ -1203,7 +1248,13 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     if (pr.kind == PK_EARLY) {
         if (ri.flags & RF_STRIPPED) p = put_strip_id(p, ri, a.v);
     } else {
-        p = put_bytes(p, a.win.ids + a.win.ids_off[w], (uint32_t)(a.win.ids_off[w + 1] - a.win.ids_off[w]));
+        if (a.win.ids_off) {
+            p = put_bytes(p, a.win.ids + a.win.ids_off[w], (uint32_t)(a.win.ids_off[w + 1] - a.win.ids_off[w]));
+        } else {  // bed.rs:150-153: "{chrom}:{st+1}-{en}"
+            p = put_bytes(p, a.names + a.names_off[ri.t_name], (uint32_t)(a.names_off[ri.t_name + 1] - a.names_off[ri.t_name]));
+            *p++ = ':'; p = put_u64(p, a.win.st[w] + 1);
+            *p++ = '-'; p = put_u64(p, a.win.en[w]);
+        }
     }
     *p++ = '\t'; *p++ = 'c'; *p++ = 'g'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
     return p;
@@ -1228,7 +1279,8 @@ __device__ __forceinline__ P put_cigar_seq(P p, const SerArgs& a, const RecInfo&
 __global__ void __launch_bounds__(SER_LINES)
 k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
             SerArgs a, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off, const uint64_t* __restrict__ out_idx,
-            uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st) {
+            uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
+            uint32_t rec_base) {
     extern __shared__ __align__(16) uint8_t s_buf[];
     __shared__ uint8_t s_stage[SER_LINES / 32][384];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1253,15 +1305,15 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         r = rec_order[k];
         w = a.win.pair_win ? a.win.pair_win[p] : (a.recs[r].wlo + (uint32_t)(p - pair_off[k]));
         const uint64_t o = out_idx[p];
-        if (out_line_off) out_line_off[o] = my_off;
+        if (out_line_off) out_line_off[o] = my_off + byte_base;  // slices: offsets in the caller's concatenated text
         if (num.q_st) {
             num.q_st[o] = pr.q_st; num.q_en[o] = pr.q_en; num.t_st[o] = pr.t_st; num.t_en[o] = pr.t_en;
             num.nmatch[o] = pr.nmatch; num.aln_len[o] = pr.aln_len;
-            num.rec_idx[o] = r; num.win_idx[o] = a.win.bed_row[w];
+            num.rec_idx[o] = r + rec_base; num.win_idx[o] = a.win.bed_row[w];
         }
         if (st.equal) write_stats(st, o, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
     }
-    if (out_line_off && p0 + SER_LINES >= n_pairs && tid == 0) out_line_off[out_idx[n_pairs]] = line_off[n_pairs];
+    if (out_line_off && p0 + SER_LINES >= n_pairs && tid == 0) out_line_off[out_idx[n_pairs]] = line_off[n_pairs] + byte_base;
     if (out_text == nullptr || region == 0) return;
 
     const bool small = __syncthreads_and(my_len <= 2048) && region <= (uint64_t)(SER_CAP - 16);
@@ -1415,7 +1467,7 @@ void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off,
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                       const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
                       const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
-                      StatsDev st, cudaStream_t s) {
+                      StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1426,7 +1478,24 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     view.ops = ops; view.samples = nullptr;
     SerArgs a{recs, view, win, names_off, names};
     k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
-        n_pairs, pair_off, rec_order, n_rec, a, res, line_off, out_idx, out_text, out_line_off, num, st);
+        n_pairs, pair_off, rec_order, n_rec, a, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base);
+}
+// Device scalars -> mapped pinned host memory with plain SM stores: the host reads them after a stream sync.  (A
+// cudaMemcpyAsync would queue on the device->host DMA engine behind the bulk download of the previous slice.)
+__global__ void k_publish(PublishArgs a) {
+    if (threadIdx.x < (unsigned)a.n) {
+        const int i = threadIdx.x;
+        a.dst[a.slot[i]] = a.wide[i] ? *reinterpret_cast<const unsigned long long*>(a.src[i])
+                                     : (unsigned long long)*reinterpret_cast<const uint32_t*>(a.src[i]);
+        __threadfence_system();
+    }
+}
+void launch_publish(const PublishArgs& a, cudaStream_t s) { k_publish<<<1, 32, 0, s>>>(a); }
+void launch_win_check(const uint32_t* t_id, const uint64_t* st, const uint64_t* en, const uint32_t* row, uint32_t n_win,
+                      uint32_t n_names, uint32_t* flags, cudaStream_t s) {
+    if (n_win == 0) return;
+    const unsigned blocks = (unsigned)std::min<uint64_t>(((uint64_t)n_win + 255) / 256, 148 * 8);
+    k_win_check<<<blocks, 256, 0, s>>>(t_id, st, en, row, n_win, n_names, flags);
 }
 void launch_pair_count_bf(const RecInfo* recs, uint32_t n_rec, WinView win, uint32_t* pair_cnt, cudaStream_t s) {
     if (n_rec == 0) return;

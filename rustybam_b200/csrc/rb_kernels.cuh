@@ -112,7 +112,17 @@ void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off,
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                       const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
                       const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
-                      StatsDev st, cudaStream_t s);
+                      StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s);
+struct PublishArgs {  // up to 8 device scalars (u32 or u64) -> slots of a mapped pinned u64 array
+    const void* src[8];
+    uint8_t slot[8];
+    uint8_t wide[8];
+    int n;
+    unsigned long long* dst;
+};
+void launch_publish(const PublishArgs& a, cudaStream_t s);
+void launch_win_check(const uint32_t* t_id, const uint64_t* st, const uint64_t* en, const uint32_t* row, uint32_t n_win,
+                      uint32_t n_names, uint32_t* flags, cudaStream_t s);
 // general path (unsorted / nested BED rows): the reference's cartesian product + overlap filter (liftover.rs:123-127)
 void launch_pair_count_bf(const RecInfo* recs, uint32_t n_rec, WinView win, uint32_t* pair_cnt, cudaStream_t s);
 void launch_pair_fill_bf(const RecInfo* recs, const uint32_t* rec_rank, uint32_t n_rec, WinView win,

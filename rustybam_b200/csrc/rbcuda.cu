@@ -3,6 +3,7 @@
 // There is NO CPU implementation behind these entry points: without a compute-capability-10
 // device they fail with RB_ERR_NO_DEVICE.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -60,8 +61,14 @@ struct rb_ctx {
     std::vector<rb_kernel_time> times;
     std::vector<PinnedBlock*> pinned;
     rb_batch* scratch = nullptr;  // reused by rb_liftover / rb_stats
+    rb_batch* slice[2] = {nullptr, nullptr};  // ping-pong work areas of the sliced rb_liftover
+    cudaStream_t copy_stream = nullptr;        // device -> host copies of finished slices
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_win = nullptr;
+    uint64_t slice_min_bytes = 16ull << 20;  // rb_ctx_set_slicing (0 = off)
     DevBuf scalars;               // small device scalars
-    void* h_scalars = nullptr;    // pinned mirror
+    void* h_scalars = nullptr;    // pinned, mapped mirror (kernels store into it: k_publish)
+    void* h_scalars_dev = nullptr;  // its device-side address
 };
 
 struct rb_batch {
@@ -69,9 +76,18 @@ struct rb_batch {
     uint64_t n_bytes = 0, n_tiles = 0, ops_bound = 0;
     bool general = false;  // BED rows not (sorted, monotone `en`, file order == sorted order): brute-force join
     std::vector<uint64_t> h_cigar_off;
+    // host staging of the asynchronous uploads (must stay alive until the stream has consumed it)
+    std::vector<uint32_t> h_order, h_rank, h_clo, h_chi;
+    struct { std::vector<uint64_t> st, en, off; std::vector<uint32_t> row; std::vector<uint8_t> ids; } h_gen;
+    bool busy = false;         // uploads of this batch may still be in flight
+    bool win_pending = false;  // the window check kernel's verdict has not been read yet
+    rb_batch* wsrc = nullptr;  // the batch that holds the window tables (nullptr: this one) — slices share their parent's
+    uint32_t rec_base = 0;     // slices: index of this batch's record 0 in the caller's arrays
+    uint64_t byte_base = 0;    // slices: output bytes emitted before this batch (added to line_off)
+    bool default_ids = false;  // rb_windows.ids_off == NULL: window id = "{t_name}:{st+1}-{en}" (bed.rs:150-153)
     // inputs
     DevBuf text_raw, cigar_off, cols64, strand, ids32, names, names_off, rec_order, rec_rank;
-    DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, cont_lo, cont_hi;
+    DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, w_tid, cont_lo, cont_hi;
     // intermediates
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
     DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e;
@@ -86,7 +102,7 @@ struct rb_batch {
 namespace {
 
 // device scalar slots
-enum { SC_TICKET_TOK = 0, SC_TICKET_SMP = 1, SC_TICKET_LNS = 2, SC_MISC = 3, SC_ERR_TOK = 4 /*u64*/, SC_ERR_REC = 6 /*u64*/, SC_WORDS = 8 };
+enum { SC_TICKET_TOK = 0, SC_TICKET_SMP = 1, SC_TICKET_LNS = 2, SC_MISC = 3, SC_ERR_TOK = 4 /*u64*/, SC_ERR_REC = 6 /*u64*/, SC_WINFLAGS = 8, SC_WORDS = 12 };
 
 int fail(rb_ctx* c, int code, const char* fmt, ...) {
     char buf[512];
@@ -178,6 +194,15 @@ void flush_times(rb_ctx* ctx) {  // call after a stream sync
     ctx->pending.clear();
 }
 
+// queue "copy these device scalars into ctx->h_scalars[slot]" (u64 slots) on the context's stream
+struct Publisher {
+    PublishArgs a{};
+    explicit Publisher(rb_ctx* ctx) { a.dst = reinterpret_cast<unsigned long long*>(ctx->h_scalars_dev); a.n = 0; }
+    Publisher& u64(int slot, const void* src) { a.src[a.n] = src; a.slot[a.n] = (uint8_t)slot; a.wide[a.n] = 1; a.n++; return *this; }
+    Publisher& u32(int slot, const void* src) { a.src[a.n] = src; a.slot[a.n] = (uint8_t)slot; a.wide[a.n] = 0; a.n++; return *this; }
+    void go(cudaStream_t s) { launch_publish(a, s); }
+};
+
 int map_err(rb_ctx* ctx, rb_batch* b, uint64_t e_tok, uint64_t e_rec) {
     uint64_t best_rec = UINT64_MAX;
     uint32_t code = 0;
@@ -192,6 +217,7 @@ int map_err(rb_ctx* ctx, rb_batch* b, uint64_t e_tok, uint64_t e_rec) {
         code = (uint32_t)(e_rec & 0xFF);
     }
     if (best_rec == UINT64_MAX) return RB_OK;
+    best_rec += b->rec_base;  // slices report the caller's record index
     switch (code) {
         case RE_CIGAR_PARSE: return fail(ctx, RB_ERR_REF_CIGAR_PARSE, "record %llu: Unable to parse cigar string (reference panics, paf.rs:399)", (unsigned long long)best_rec);
         case RE_INTEGRITY: return fail(ctx, RB_ERR_REF_INTEGRITY, "record %llu: CIGAR does not match the record's spans (check_integrity().unwrap(), paf.rs:70)", (unsigned long long)best_rec);
@@ -214,11 +240,12 @@ RecInput rec_input(const rb_batch* b) {
     in.n_rec = b->n_rec;
     return in;
 }
-WinView win_view(const rb_batch* b) {
+WinView win_view(const rb_batch* self) {
+    const rb_batch* b = self->wsrc ? self->wsrc : self;
     WinView w{};
     if (b->n_win == 0) return w;
     w.st = b->w_st.as<uint64_t>(); w.en = b->w_en.as<uint64_t>(); w.en_pm = w.en;
-    w.ids_off = b->w_ids_off.as<uint64_t>(); w.ids = b->w_ids.as<uint8_t>();
+    w.ids_off = b->default_ids ? nullptr : b->w_ids_off.as<uint64_t>(); w.ids = b->default_ids ? nullptr : b->w_ids.as<uint8_t>();
     w.bed_row = b->w_bed_row.as<uint32_t>();
     w.cont_lo = b->cont_lo.as<uint32_t>(); w.cont_hi = b->cont_hi.as<uint32_t>();
     w.pair_win = nullptr;
@@ -319,7 +346,9 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
     ctx->device = dev;
     cudaSetDevice(dev);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocDefault) != cudaSuccess) {
+        ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&ctx->h_scalars_dev, ctx->h_scalars, 0) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming) != cudaSuccess) {
         (void)cudaGetLastError();
         delete ctx;
         set(RB_ERR_CUDA);
@@ -332,8 +361,9 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
 void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
     if (!b) return;
     if (ctx) cudaSetDevice(ctx->device);
+    if (ctx && b->busy) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&b->text_raw, &b->cigar_off, &b->cols64, &b->strand, &b->ids32, &b->names, &b->names_off, &b->rec_order,
-                     &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->cont_lo, &b->cont_hi, &b->ops,
+                     &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
                      &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
@@ -345,7 +375,15 @@ void rb_ctx_destroy(rb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->scratch) rb_batch_free(ctx, ctx->scratch);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->slice[k]) rb_batch_free(ctx, ctx->slice[k]);
+        if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_win) cudaEventDestroy(ctx->ev_win);
     for (PinnedBlock* b : ctx->pinned) { cudaFreeHost(b->p); delete b; }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->scalars.release();
@@ -368,6 +406,12 @@ int rb_ctx_set_stream(rb_ctx* ctx, void* cuda_stream) {
         ctx->own_stream = true;
         if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamCreate");
     }
+    return RB_OK;
+}
+
+int rb_ctx_set_slicing(rb_ctx* ctx, uint64_t min_slice_bytes) {
+    if (!ctx) return RB_ERR_BAD_ARG;
+    ctx->slice_min_bytes = min_slice_bytes;
     return RB_OK;
 }
 
@@ -405,28 +449,142 @@ int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, ui
 }
 
 // -------------------------------------------------------------------------------------------------
-static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+// Host -> HBM.  Everything is enqueued on the context's stream without a host synchronisation: the big CIGAR
+// copy goes first so that the host-side checks of the window table (3 M rows at 1 kb windows) run while the DMA
+// engine is busy.  Host staging that must outlive the call lives in the batch.
+// records [r0, r1) of R: the CIGAR text, the one big copy — issued before any host-side work
+static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t r0, uint32_t r1) {
     cudaStream_t s = ctx->stream;
     if (!R || (R->n_rec && (!R->cigar_off || !R->q_len || !R->q_st || !R->q_en || !R->t_len || !R->t_st || !R->t_en || !R->mapq ||
                             !R->strand || !R->q_id || !R->t_id || !R->names_off)) ||
         (R->cigar_nbytes && !R->cigar))
         return fail(ctx, RB_ERR_BAD_ARG, "rb_records: null column");
-    const uint32_t n = R->n_rec;
-    b->n_rec = n; b->n_names = R->n_names; b->n_bytes = R->cigar_nbytes;
-    b->n_win = W ? W->n_win : 0;
+    if (R->n_rec && (R->cigar_off[0] != 0 || R->cigar_off[R->n_rec] != R->cigar_nbytes)) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
+    if (!R->n_rec && R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
+    const uint32_t n = r1 - r0;
+    if (b->busy) { CU(cudaStreamSynchronize(s)); b->busy = false; }  // the previous call's copies read the staging below
+    const uint64_t byte0 = n ? R->cigar_off[r0] : 0, byte1 = n ? R->cigar_off[r1] : 0;
+    if (byte1 < byte0 || byte1 > R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone");
+    b->n_rec = n; b->n_names = R->n_names; b->n_bytes = byte1 - byte0;
+    b->rec_base = r0; b->byte_base = 0;
     b->have_lift = b->have_stats = false;
-    b->h_cigar_off.assign(R->cigar_off, R->cigar_off + (n ? n + 1 : 0));
-    if (n == 0) b->h_cigar_off.assign(1, 0);
-    if (b->h_cigar_off[0] != 0 || b->h_cigar_off[n] != R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
-    for (uint32_t i = 0; i < n; i++) {
-        if (b->h_cigar_off[i] > b->h_cigar_off[i + 1]) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone at record %u", i);
-        if (R->q_id[i] >= R->n_names || R->t_id[i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", i);
-    }
     b->n_tiles = b->n_bytes / TOK_TILE + 1;
     b->ops_bound = b->n_bytes / 2 + 1;
     const size_t padded = b->n_tiles * (size_t)TOK_TILE + 32;
-
     CU(b->text_raw.ensure(TEXT_FRONT_PAD + padded));
+    uint8_t* raw = b->text_raw.as<uint8_t>();
+    CU(cudaMemsetAsync(raw, 0xFF, TEXT_FRONT_PAD, s));
+    if (b->n_bytes) CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD, R->cigar + byte0, b->n_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(raw + TEXT_FRONT_PAD + b->n_bytes, '0', padded - b->n_bytes, s));
+    b->busy = true;
+    return RB_OK;
+}
+
+// The window tables, step 1: enqueue the copies of the caller's (sorted) arrays and a check kernel.  The host never
+// walks the table (3 M rows at 1 kb windows = 75 MB of host reads); it only binary-searches t_id for the contig ranges.
+static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    cudaStream_t s = ctx->stream;
+    b->n_win = W ? W->n_win : 0;
+    b->wsrc = nullptr;
+    b->general = false; b->default_ids = false; b->win_pending = false;
+    if (!(W && W->n_win)) return RB_OK;
+    const uint32_t nw = W->n_win;
+    if (!W->t_id || !W->st || !W->en || !W->bed_row || (W->ids_off && !W->ids)) return fail(ctx, RB_ERR_BAD_ARG, "rb_windows: null column");
+    b->default_ids = (W->ids_off == nullptr);
+    CU(b->w_st.ensure((size_t)nw * 8)); CU(b->w_en.ensure((size_t)nw * 8)); CU(b->w_bed_row.ensure((size_t)nw * 4));
+    CU(b->w_tid.ensure((size_t)nw * 4));
+    CU(b->cont_lo.ensure((size_t)(R->n_names + 1) * 4)); CU(b->cont_hi.ensure((size_t)(R->n_names + 1) * 4));
+    CU(cudaMemcpyAsync(b->w_tid.p, W->t_id, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->w_st.p, W->st, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->w_en.p, W->en, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->w_bed_row.p, W->bed_row, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+    b->busy = true;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    CU(cudaMemsetAsync(sc + SC_WINFLAGS, 0, 4, s));
+    launch_win_check(b->w_tid.as<uint32_t>(), b->w_st.as<uint64_t>(), b->w_en.as<uint64_t>(), b->w_bed_row.as<uint32_t>(), nw,
+                     R->n_names, sc + SC_WINFLAGS, s);
+    Publisher(ctx).u32(16, sc + SC_WINFLAGS).go(s);
+    CU(cudaEventRecord(ctx->ev_win, s));
+    b->win_pending = true;
+    if (!b->default_ids) {
+        const uint64_t ids_bytes = W->ids_off[nw];
+        CU(b->w_ids_off.ensure((size_t)(nw + 1) * 8)); CU(b->w_ids.ensure(ids_bytes + 8));
+        CU(cudaMemcpyAsync(b->w_ids_off.p, W->ids_off, (size_t)(nw + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (ids_bytes) CU(cudaMemcpyAsync(b->w_ids.p, W->ids, ids_bytes, cudaMemcpyHostToDevice, s));
+    }
+    // contig ranges: t_id is sorted (verified on the device; an unsorted table only yields ranges nobody will use)
+    b->h_clo.assign(R->n_names + 1, 0); b->h_chi.assign(R->n_names + 1, 0);
+    {
+        const uint32_t* tid = W->t_id;
+        uint32_t i = 0;
+        while (i < nw) {  // gallop from contig to contig: O(contigs * log n_win) host reads
+            const uint32_t t = tid[i];
+            const uint32_t j = (uint32_t)(std::upper_bound(tid + i, tid + nw, t) - tid);
+            if (t < R->n_names) { b->h_clo[t] = i; b->h_chi[t] = j; }
+            i = j > i ? j : i + 1;
+        }
+    }
+    CU(cudaMemcpyAsync(b->cont_lo.p, b->h_clo.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->cont_hi.p, b->h_chi.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
+    return RB_OK;
+}
+
+// step 2: wait for the verdict of the check kernel; the rare general layout (BED rows whose file order is not the
+// sorted order, or nested rows) re-uploads the tables in BED file order per contig (Q5)
+static int upload_windows_end(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    if (!b->win_pending) return RB_OK;
+    b->win_pending = false;
+    cudaStream_t s = ctx->stream;
+    CU(cudaEventSynchronize(ctx->ev_win));
+    const uint32_t flags = (uint32_t)reinterpret_cast<volatile uint64_t*>(ctx->h_scalars)[16];
+    if (flags & 1u) return fail(ctx, RB_ERR_BAD_ARG, "windows must be sorted by (t_id, st) with t_id < n_names (see rb_sort_windows)");
+    b->general = (flags & 2u) != 0;
+    if (!b->general) return RB_OK;
+    const uint32_t nw = W->n_win;
+    std::vector<uint32_t> perm(nw);
+    for (uint32_t i = 0; i < nw; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t c) {
+        if (W->t_id[a] != W->t_id[c]) return W->t_id[a] < W->t_id[c];
+        return W->bed_row[a] < W->bed_row[c];
+    });
+    auto& g = b->h_gen;
+    g.st.resize(nw); g.en.resize(nw); g.row.resize(nw);
+    for (uint32_t i = 0; i < nw; i++) {
+        const uint32_t j = perm[i];
+        g.st[i] = W->st[j]; g.en[i] = W->en[j]; g.row[i] = W->bed_row[j];
+    }
+    CU(cudaMemcpyAsync(b->w_st.p, g.st.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->w_en.p, g.en.data(), (size_t)nw * 8, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->w_bed_row.p, g.row.data(), (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+    if (!b->default_ids) {
+        g.off.resize(nw + 1);
+        g.off[0] = 0;
+        for (uint32_t i = 0; i < nw; i++) g.off[i + 1] = g.off[i] + (W->ids_off[perm[i] + 1] - W->ids_off[perm[i]]);
+        g.ids.resize(g.off[nw] + 1);
+        for (uint32_t i = 0; i < nw; i++) {
+            const uint32_t j = perm[i];
+            memcpy(g.ids.data() + g.off[i], W->ids + W->ids_off[j], W->ids_off[j + 1] - W->ids_off[j]);
+        }
+        CU(cudaMemcpyAsync(b->w_ids_off.p, g.off.data(), (size_t)(nw + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (g.off[nw]) CU(cudaMemcpyAsync(b->w_ids.p, g.ids.data(), g.off[nw], cudaMemcpyHostToDevice, s));
+    }
+    b->busy = true;
+    (void)R;
+    return RB_OK;
+}
+
+// records [r0, r1) of R: numeric columns, names, emission order (small)
+static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t r0, uint32_t r1) {
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = r1 - r0;
+    const uint64_t byte0 = n ? R->cigar_off[r0] : 0;
+    b->h_cigar_off.resize((size_t)n + 1);
+    b->h_cigar_off[0] = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (R->cigar_off[r0 + i] > R->cigar_off[r0 + i + 1]) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone at record %u", r0 + i);
+        b->h_cigar_off[i + 1] = R->cigar_off[r0 + i + 1] - byte0;
+        if (R->q_id[r0 + i] >= R->n_names || R->t_id[r0 + i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", r0 + i);
+    }
     CU(b->cigar_off.ensure((size_t)(n + 1) * 8));
     CU(b->cols64.ensure((size_t)n * 7 * 8 + 8));
     CU(b->strand.ensure(n + 8));
@@ -449,18 +607,14 @@ static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_w
     CU(b->pair_cnt.ensure((size_t)n * 4 + 8));
     CU(b->pair_off.ensure((size_t)(n + 1) * 8));
 
-    uint8_t* raw = b->text_raw.as<uint8_t>();
-    CU(cudaMemsetAsync(raw, 0xFF, TEXT_FRONT_PAD, s));
-    if (b->n_bytes) CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD, R->cigar, b->n_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(raw + TEXT_FRONT_PAD + b->n_bytes, '0', padded - b->n_bytes, s));
     CU(cudaMemcpyAsync(b->cigar_off.p, b->h_cigar_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     const uint64_t* cols[7] = {R->q_len, R->q_st, R->q_en, R->t_len, R->t_st, R->t_en, R->mapq};
     for (int k = 0; k < 7 && n; k++)
-        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k], (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k] + r0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
     if (n) {
-        CU(cudaMemcpyAsync(b->strand.p, R->strand, n, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), R->q_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, R->t_id, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->strand.p, R->strand + r0, n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), R->q_id + r0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, R->t_id + r0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     }
     if (R->n_names) {
         CU(cudaMemcpyAsync(b->names_off.p, R->names_off, (size_t)(R->n_names + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -468,13 +622,13 @@ static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_w
     }
 
     // emission order (liftover.rs:151-164): contigs by first appearance of t_name, records in file order inside
-    std::vector<uint32_t> order(n), rank(n);
+    b->h_order.resize(n); b->h_rank.resize(n);
     {
         std::vector<int64_t> first(R->n_names, -1);
         std::vector<uint32_t> cnt;
         std::vector<uint32_t> grp(n);
         for (uint32_t i = 0; i < n; i++) {
-            int64_t& f = first[R->t_id[i]];
+            int64_t& f = first[R->t_id[r0 + i]];
             if (f < 0) { f = (int64_t)cnt.size(); cnt.push_back(0); }
             grp[i] = (uint32_t)f;
             cnt[grp[i]]++;
@@ -483,83 +637,34 @@ static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_w
         for (size_t g = 0; g < cnt.size(); g++) start[g + 1] = start[g] + cnt[g];
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t k = start[grp[i]]++;
-            order[k] = i;
-            rank[i] = k;
+            b->h_order[k] = i;
+            b->h_rank[i] = k;
         }
     }
     if (n) {
-        CU(cudaMemcpyAsync(b->rec_order.p, order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->rec_rank.p, rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    }
-
-    // windows
-    if (W && W->n_win) {
-        const uint32_t nw = W->n_win;
-        if (!W->t_id || !W->st || !W->en || !W->bed_row || !W->ids_off) return fail(ctx, RB_ERR_BAD_ARG, "rb_windows: null column");
-        bool fast = true;
-        for (uint32_t i = 0; i < nw; i++) {
-            if (W->t_id[i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "window %u: t_id out of range", i);
-            if (i) {
-                if (W->t_id[i] < W->t_id[i - 1] || (W->t_id[i] == W->t_id[i - 1] && W->st[i] < W->st[i - 1]))
-                    return fail(ctx, RB_ERR_BAD_ARG, "windows must be sorted by (t_id, st) (see rb_sort_windows)");
-                if (W->t_id[i] == W->t_id[i - 1] && (W->en[i] < W->en[i - 1] || W->bed_row[i] < W->bed_row[i - 1])) fast = false;
-            }
-        }
-        b->general = !fast;
-        std::vector<uint32_t> perm;
-        std::vector<uint64_t> st_g, en_g, off_g;
-        std::vector<uint32_t> row_g, tid_g;
-        std::vector<uint8_t> ids_g;
-        const uint64_t *h_st = W->st, *h_en = W->en, *h_off = W->ids_off;
-        const uint32_t *h_row = W->bed_row, *h_tid = W->t_id;
-        const uint8_t* h_ids = W->ids;
-        if (b->general) {  // BED file order inside each contig (Q5): stable sort by (t_id, bed_row)
-            perm.resize(nw);
-            for (uint32_t i = 0; i < nw; i++) perm[i] = i;
-            std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t c) {
-                if (W->t_id[a] != W->t_id[c]) return W->t_id[a] < W->t_id[c];
-                return W->bed_row[a] < W->bed_row[c];
-            });
-            st_g.resize(nw); en_g.resize(nw); off_g.resize(nw + 1); row_g.resize(nw); tid_g.resize(nw);
-            off_g[0] = 0;
-            for (uint32_t i = 0; i < nw; i++) {
-                const uint32_t j = perm[i];
-                st_g[i] = W->st[j]; en_g[i] = W->en[j]; row_g[i] = W->bed_row[j]; tid_g[i] = W->t_id[j];
-                off_g[i + 1] = off_g[i] + (W->ids_off[j + 1] - W->ids_off[j]);
-            }
-            ids_g.resize(off_g[nw] + 1);
-            for (uint32_t i = 0; i < nw; i++) {
-                const uint32_t j = perm[i];
-                memcpy(ids_g.data() + off_g[i], W->ids + W->ids_off[j], W->ids_off[j + 1] - W->ids_off[j]);
-            }
-            h_st = st_g.data(); h_en = en_g.data(); h_off = off_g.data(); h_row = row_g.data(); h_tid = tid_g.data();
-            h_ids = ids_g.data();
-        }
-        std::vector<uint32_t> clo(R->n_names + 1, 0), chi(R->n_names + 1, 0);
-        for (uint32_t i = 0; i < nw; i++) {
-            const uint32_t t = h_tid[i];
-            if (i == 0 || h_tid[i - 1] != t) clo[t] = i;
-            chi[t] = i + 1;
-        }
-        const uint64_t ids_bytes = h_off[nw];
-        CU(b->w_st.ensure((size_t)nw * 8)); CU(b->w_en.ensure((size_t)nw * 8)); CU(b->w_ids_off.ensure((size_t)(nw + 1) * 8));
-        CU(b->w_ids.ensure(ids_bytes + 8)); CU(b->w_bed_row.ensure((size_t)nw * 4));
-        CU(b->cont_lo.ensure((size_t)(R->n_names + 1) * 4)); CU(b->cont_hi.ensure((size_t)(R->n_names + 1) * 4));
-        CU(cudaMemcpyAsync(b->w_st.p, h_st, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->w_en.p, h_en, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->w_ids_off.p, h_off, (size_t)(nw + 1) * 8, cudaMemcpyHostToDevice, s));
-        if (ids_bytes) CU(cudaMemcpyAsync(b->w_ids.p, h_ids, ids_bytes, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->w_bed_row.p, h_row, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->cont_lo.p, clo.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->cont_hi.p, chi.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));  // the staging vectors above die at scope exit
-    } else {
-        b->general = false;
-        CU(cudaStreamSynchronize(s));
+        CU(cudaMemcpyAsync(b->rec_order.p, b->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->rec_rank.p, b->h_rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
     }
     b->sum = rb_summary{};
     b->sum.cigar_bytes = b->n_bytes;
     return RB_OK;
+}
+
+static int upload_into_impl(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    int rc = upload_cigar(ctx, b, R, 0, R ? R->n_rec : 0);  // validates R
+    if (rc == RB_OK) rc = upload_windows_begin(ctx, b, R, W);
+    if (rc == RB_OK) rc = upload_columns(ctx, b, R, 0, R->n_rec);
+    if (rc == RB_OK) rc = upload_windows_end(ctx, b, R, W);
+    return rc;
+}
+
+static int upload_into(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    const int rc = upload_into_impl(ctx, b, R, W);
+    if (rc != RB_OK && b->busy) {  // copies out of the caller's buffers may be in flight: do not hand them back early
+        cudaStreamSynchronize(ctx->stream);
+        b->busy = false;
+    }
+    return rc;
 }
 
 rb_batch* rb_batch_upload(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int* status) {
@@ -567,7 +672,12 @@ rb_batch* rb_batch_upload(rb_ctx* ctx, const rb_records* recs, const rb_windows*
     if (!ctx) { set(RB_ERR_NO_DEVICE); return nullptr; }
     cudaSetDevice(ctx->device);
     rb_batch* b = new rb_batch();
-    const int rc = upload_into(ctx, b, recs, wins);
+    int rc = upload_into(ctx, b, recs, wins);
+    if (rc == RB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {  // the caller may reuse its buffers after this call
+        (void)cudaGetLastError();
+        rc = fail(ctx, RB_ERR_CUDA, "upload failed");
+    }
+    b->busy = false;
     set(rc);
     if (rc != RB_OK) { rb_batch_free(ctx, b); return nullptr; }
     return b;
@@ -589,14 +699,13 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
         launch_rec_prep(0, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), WinView{},
                         b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), stats_view(b, b->n_rec), err, s);
     }
-    uint64_t* hs = reinterpret_cast<uint64_t*>(ctx->h_scalars);
-    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 2, b->op_off.as<uint64_t>() + b->n_rec, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 3, sc + SC_MISC, 4, cudaMemcpyDeviceToHost, s));
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + b->n_rec).u32(3, sc + SC_MISC).go(s);
     CU(cudaStreamSynchronize(s));
+    b->busy = false;  // every upload of this batch has been consumed
     if ((uint32_t)hs[3] & 1u) {  // clips present: validate their placement like rust-htslib does
         launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), b->n_rec, err, s);
-        CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+        Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).go(s);
         CU(cudaStreamSynchronize(s));
     }
     flush_times(ctx);
@@ -620,13 +729,14 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
     WinView win = win_view(b);
+    const rb_batch* wb = b->wsrc ? b->wsrc : b;  // holder of the window tables
     const uint32_t n = b->n_rec;
     {   // phase A: indel strip + window join (needs the ops only)
         KScope k(ctx, "k_rec_prep");
         launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), nullptr, win, b->recs.as<RecInfo>(),
                         b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
     }
-    if (b->general && b->n_win) {
+    if (wb->general && wb->n_win) {
         KScope k(ctx, "k_pair_count_bf");
         launch_pair_count_bf(b->recs.as<RecInfo>(), n, win, b->pair_cnt.as<uint32_t>(), s);
     }
@@ -634,15 +744,14 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
         KScope k(ctx, "k_pair_scan");
         launch_pair_scan(b->pair_cnt.as<uint32_t>(), b->rec_order.as<uint32_t>(), n, b->pair_off.as<uint64_t>(), s);
     }
-    uint64_t* hs = reinterpret_cast<uint64_t*>(ctx->h_scalars);
-    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 2, b->op_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 3, sc + SC_MISC, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 4, b->pair_off.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, s));
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC)
+        .u64(4, b->pair_off.as<uint64_t>() + n).go(s);
     CU(cudaStreamSynchronize(s));
+    b->busy = false;  // every upload of this batch has been consumed
     if ((uint32_t)hs[3] & 1u) {
         launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, err, s);
-        CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
+        Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).go(s);
         CU(cudaStreamSynchronize(s));
     }
     // CIGAR parse errors end the call here; strip panics wait for the integrity check of phase B so that the
@@ -653,7 +762,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     // RB_LIFT_SEARCH (default): sampled scan, then one search per pair out of staged shared memory (k_lift).
     // RB_LIFT_STREAM (sorted BED + right-most policy only): the scan resolves the window boundaries itself
     // (k_scan_lift + k_combine) — no per-pair search at all, cost independent of the window count.
-    const bool fused = ctx->lift_mode == RB_LIFT_STREAM && !b->general && policy == RB_POLICY_RIGHTMOST && P > 0;
+    const bool fused = ctx->lift_mode == RB_LIFT_STREAM && !wb->general && policy == RB_POLICY_RIGHTMOST && P > 0;
 
     CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
     CU(b->line_len.ensure(P * 4 + 64));
@@ -679,7 +788,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
         launch_rec_prep(2, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), win,
                         b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
     }
-    if (b->general && P) {
+    if (wb->general && P) {
         CU(b->pair_win.ensure(P * 4 + 64));
         KScope k(ctx, "k_pair_fill_bf");
         launch_pair_fill_bf(b->recs.as<RecInfo>(), b->rec_rank.as<uint32_t>(), n, win, b->pair_off.as<uint64_t>(),
@@ -702,9 +811,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
         launch_scan_lines(b->line_len.as<uint32_t>(), P, b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
                           b->ln_state.as<uint32_t>(), b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
     }
-    CU(cudaMemcpyAsync(hs, sc + SC_ERR_TOK, 16, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 5, b->line_off.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(hs + 6, b->out_idx.as<uint64_t>() + P, 8, cudaMemcpyDeviceToHost, s));
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, b->line_off.as<uint64_t>() + P).u64(6, b->out_idx.as<uint64_t>() + P).go(s);
     CU(cudaStreamSynchronize(s));
     rc = map_err(ctx, b, hs[0], hs[1]);
     if (rc != RB_OK) { flush_times(ctx); return rc; }
@@ -724,7 +831,8 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                          win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(), b->pair_res.as<PairRes>(),
                          b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
-                         (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{}, s);
+                         (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
+                         b->byte_base, b->rec_base, s);
     }
     if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
     CU(cudaGetLastError());
@@ -811,17 +919,258 @@ void rb_free_stats_out(rb_ctx*, rb_stats_out* st) {
     memset(st, 0, sizeof *st);
 }
 
+// ---- rb_liftover in slices -----------------------------------------------------------------------
+// When the records already sit in emission order (the PAF is grouped by target, the usual case) a call is cut into
+// K runs of consecutive records of about equal CIGAR size.  Each slice goes upload -> kernels -> download on its own
+// ping-pong work area, and the download of slice k (copy stream, device->host DMA engine) runs under the upload and
+// the kernels of slices k+1, k+2 (compute stream, host->device engine): PCIe is used in both directions at once and
+// the call approaches the time of its largest transfer instead of the sum of all three stages.  It also bounds the
+// HBM footprint of the intermediates by the slice size.  The rows land in one pinned block in emission order; the
+// window tables are uploaded once and shared by all slices.
+static bool records_in_emission_order(const rb_records* R, std::vector<uint8_t>& seen) {
+    seen.assign(R->n_names, 0);
+    uint32_t prev = UINT32_MAX;
+    for (uint32_t i = 0; i < R->n_rec; i++) {
+        const uint32_t t = R->t_id[i];
+        if (t >= R->n_names) return false;  // reported properly by the unsliced path
+        if (t != prev) {
+            if (seen[t]) return false;
+            seen[t] = 1;
+            prev = t;
+        }
+    }
+    return true;
+}
+
+static int liftover_unsliced(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
+                             rb_stats_out* stats, bool windows_uploaded) {
+    rb_batch* b = ctx->scratch;
+    int rc;
+    if (windows_uploaded) {
+        rc = upload_cigar(ctx, b, recs, 0, recs->n_rec);
+        if (rc == RB_OK) rc = upload_columns(ctx, b, recs, 0, recs->n_rec);
+        if (rc != RB_OK && b->busy) { cudaStreamSynchronize(ctx->stream); b->busy = false; }
+    } else {
+        rc = upload_into(ctx, b, recs, wins);
+    }
+    if (rc != RB_OK) return rc;
+    rc = rb_batch_liftover(ctx, b, policy, want, stats != nullptr, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_lift(ctx, b, want, out, stats);
+}
+
 int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
                 rb_stats_out* stats) {
     if (!ctx) return RB_ERR_NO_DEVICE;
     if (!out) return fail(ctx, RB_ERR_BAD_ARG, "out is null");
     cudaSetDevice(ctx->device);
     if (!ctx->scratch) ctx->scratch = new rb_batch();
-    int rc = upload_into(ctx, ctx->scratch, recs, wins);
-    if (rc != RB_OK) return rc;
-    rc = rb_batch_liftover(ctx, ctx->scratch, policy, want, stats != nullptr, nullptr);
-    if (rc != RB_OK) return rc;
-    return rb_batch_download_lift(ctx, ctx->scratch, want, out, stats);
+    rb_batch* wb = ctx->scratch;
+    const uint64_t SLICE_MIN_BYTES = ctx->slice_min_bytes;
+    std::vector<uint8_t> seen;
+    const bool try_slices = SLICE_MIN_BYTES && !ctx->profiling && recs && wins && wins->n_win && recs->n_rec >= 2 && recs->cigar_off &&
+                            recs->t_id && recs->t_st && recs->t_en && recs->cigar_nbytes >= 2 * SLICE_MIN_BYTES &&
+                            recs->cigar_off[recs->n_rec] == recs->cigar_nbytes && records_in_emission_order(recs, seen);
+    if (!try_slices) return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
+
+    const bool trace = getenv("RB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto T = [&](const char* what, uint32_t k) {
+        if (trace) fprintf(stderr, "[rb_liftover] %8.3f ms  %s %u\n",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, k);
+    };
+    struct TEv { const char* what; uint32_t k; cudaEvent_t e; };
+    std::vector<TEv> tev;
+    auto TE = [&](const char* what, uint32_t k, cudaStream_t st) {  // device-side timeline (RB_TRACE only)
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(TEv{what, k, e});
+    };
+    cudaStream_t A = ctx->stream;
+    if (!ctx->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t B = ctx->copy_stream;
+    if (wb->busy) { CU(cudaStreamSynchronize(A)); wb->busy = false; }
+    wb->n_rec = 0; wb->have_lift = wb->have_stats = false;
+    TE("A start", 0, A);
+    int rc = upload_windows_begin(ctx, wb, recs, wins);
+    if (rc != RB_OK) { cudaStreamSynchronize(A); wb->busy = false; return rc; }
+    T("windows enqueued", 0);
+    TE("A windows uploaded", 0, A);
+
+    // ---- slice boundaries (record granularity, balanced on CIGAR bytes) and an upper bound on the rows ----
+    const uint32_t n = recs->n_rec;
+    const uint64_t total_bytes = recs->cigar_nbytes;
+    const uint32_t K = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
+    std::vector<uint32_t> cut(1, 0);
+    for (uint32_t k = 1; k < K; k++) {
+        const uint64_t target = total_bytes / K * k;
+        const uint32_t r = (uint32_t)(std::lower_bound(recs->cigar_off, recs->cigar_off + n, target) - recs->cigar_off);
+        if (r > cut.back() && r < n) cut.push_back(r);
+    }
+    cut.push_back(n);
+    const uint32_t n_slices = (uint32_t)cut.size() - 1;
+    uint64_t cap_rows = 0;  // pairs of the unstripped records >= pairs examined >= rows
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t lo = wb->h_clo[recs->t_id[i]], hi = wb->h_chi[recs->t_id[i]];
+        const uint64_t* a0 = std::upper_bound(wins->en + lo, wins->en + hi, recs->t_st[i]);   // first en > t_st (en is monotone here)
+        const uint64_t* a1 = std::lower_bound(wins->st + lo, wins->st + hi, recs->t_en[i]);   // first st >= t_en
+        const uint32_t i0 = (uint32_t)(a0 - wins->en), i1 = (uint32_t)(a1 - wins->st);
+        if (i1 > i0) cap_rows += i1 - i0;
+    }
+
+    memset(out, 0, sizeof *out);
+    if (stats) memset(stats, 0, sizeof *stats);
+    PinnedBlock *blk = nullptr, *sblk = nullptr;
+    uint8_t* base = nullptr;
+    size_t o_text = 64, o_loff = 0, o_num = 0, cap_text = 0;
+    uint64_t byte_base = 0, row_base = 0, pairs = 0;
+    auto bail = [&](int code) {
+        cudaStreamSynchronize(A);
+        cudaStreamSynchronize(B);
+        for (int k = 0; k < 2; k++)
+            if (ctx->slice[k]) ctx->slice[k]->busy = false;
+        wb->busy = false;
+        if (blk) blk->in_use = false;
+        if (sblk) sblk->in_use = false;
+        return code;
+    };
+    for (int k = 0; k < 2; k++) {
+        if (!ctx->slice[k]) ctx->slice[k] = new rb_batch();
+        ctx->slice[k]->wsrc = wb;
+    }
+    auto upload_slice = [&](uint32_t k) {
+        rb_batch* sb = ctx->slice[k & 1];
+        int r2 = upload_cigar(ctx, sb, recs, cut[k], cut[k + 1]);
+        if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, cut[k], cut[k + 1]);
+        sb->wsrc = wb;
+        return r2;
+    };
+    rc = upload_slice(0);
+    if (rc != RB_OK) return bail(rc);
+    rc = upload_windows_end(ctx, wb, recs, wins);  // the first slice's copy is already queued behind the window tables
+    if (rc != RB_OK) return bail(rc);
+    T("window tables verified", 0);
+    if (wb->general) {
+        bail(RB_OK);
+        return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, true);
+    }
+    for (uint32_t k = 0; k < n_slices; k++) {
+        rb_batch* sb = ctx->slice[k & 1];
+        if (k + 1 < n_slices) {  // next slice's host->device copies go in front of this slice's kernels
+            rc = upload_slice(k + 1);
+            if (rc != RB_OK) return bail(rc);
+        }
+        T("next upload enqueued", k);
+        TE("A next slice uploaded", k, A);
+        if (k >= 2) CU(cudaStreamWaitEvent(A, ctx->ev_d2h[k & 1], 0));  // this work area's previous rows have left the device
+        TE("A kernels may start", k, A);
+        sb->byte_base = byte_base;
+        rb_summary sm{};
+        rc = rb_batch_liftover(ctx, sb, policy, want, stats != nullptr, &sm);
+        if (rc != RB_OK) return bail(rc);
+        T("kernels enqueued (sizes known)", k);
+        CU(cudaEventRecord(ctx->ev_done[k & 1], A));
+        TE("A kernels done", k, A);
+        if (!blk) {  // sizes of the first slice are known: reserve the pinned output (text size extrapolated, rows bounded)
+            const uint64_t slice_bytes = recs->cigar_off[cut[1]] - recs->cigar_off[cut[0]];
+            const double scale = slice_bytes ? (double)total_bytes / (double)slice_bytes : 1.0;
+            const size_t loff_bytes = (want & RB_WANT_TEXT) ? align_up((cap_rows + 1) * 8, 64) : 0;
+            const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;
+            size_t text_est = 0;
+            if (want & RB_WANT_TEXT) {
+                text_est = (size_t)((double)sm.out_bytes * scale * 1.08) + (1u << 20);
+                if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + (1u << 20);  // nothing to extrapolate from
+            }
+            const size_t need = 64 + align_up(text_est + 1, 64) + loff_bytes + num_bytes;
+            blk = pinned_get(ctx, need);
+            if (!blk) return bail(fail(ctx, RB_ERR_OOM, "pinned allocation of %zu bytes failed", need));
+            base = reinterpret_cast<uint8_t*>(blk->p);
+            // the text gets every byte the pool block has beyond the fixed-size tables
+            const size_t text_room = (blk->cap - 64 - loff_bytes - num_bytes) / 64 * 64;
+            cap_text = (want & RB_WANT_TEXT) ? text_room - 64 : 0;
+            o_loff = 64 + text_room;
+            o_num = o_loff + loff_bytes;
+            if (stats) {
+                sblk = pinned_get(ctx, (size_t)cap_rows * 40 + 64);
+                if (!sblk) return bail(fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)(cap_rows * 40)));
+            }
+        }
+        if ((want & RB_WANT_TEXT) && byte_base + sm.out_bytes > cap_text) {  // the extrapolation was too small: start over, unsliced
+            T("text estimate too small: falling back", k);
+            bail(RB_OK);
+            blk = sblk = nullptr;
+            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, true);
+        }
+        if (row_base + sm.n_out > cap_rows) return bail(fail(ctx, RB_ERR_CUDA, "internal: row bound exceeded"));
+        // ---- device -> host of this slice on the copy stream ----
+        CU(cudaStreamWaitEvent(B, ctx->ev_done[k & 1], 0));
+        TE("B download starts", k, B);
+        const uint64_t nk = sm.n_out;
+        if (want & RB_WANT_TEXT) {
+            if (sm.out_bytes) CU(cudaMemcpyAsync(base + o_text + byte_base, sb->out_text.p, sm.out_bytes, cudaMemcpyDeviceToHost, B));
+            if (nk) CU(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + o_loff) + row_base, sb->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, B));
+        }
+        if ((want & RB_WANT_NUMERIC) && nk) {
+            uint64_t* d = reinterpret_cast<uint64_t*>(base + o_num);
+            const uint64_t* sp = sb->out_num.as<uint64_t>();
+            for (int c = 0; c < 6; c++) CU(cudaMemcpyAsync(d + (size_t)c * cap_rows + row_base, sp + (size_t)c * nk, nk * 8, cudaMemcpyDeviceToHost, B));
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 6 * cap_rows);
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * nk);
+            for (int c = 0; c < 2; c++) CU(cudaMemcpyAsync(d32 + (size_t)c * cap_rows + row_base, s32 + (size_t)c * nk, nk * 4, cudaMemcpyDeviceToHost, B));
+        }
+        if (stats && nk) {
+            uint32_t* d = reinterpret_cast<uint32_t*>(sblk->p);
+            const uint32_t* sp = sb->out_stats.as<uint32_t>();
+            for (int c = 0; c < 10; c++) CU(cudaMemcpyAsync(d + (size_t)c * cap_rows + row_base, sp + (size_t)c * nk, nk * 4, cudaMemcpyDeviceToHost, B));
+        }
+        CU(cudaEventRecord(ctx->ev_d2h[k & 1], B));
+        TE("B download done", k, B);
+        byte_base += sm.out_bytes; row_base += nk; pairs += sm.n_pairs;
+    }
+    T("all slices enqueued", n_slices);
+    CU(cudaStreamSynchronize(B));
+    T("copy stream drained", n_slices);
+    for (size_t i = 0; i < tev.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, tev[0].e, tev[i].e);
+        fprintf(stderr, "[rb_liftover device] %8.3f ms  %s %u\n", ms, tev[i].what, tev[i].k);
+    }
+    for (auto& t : tev) cudaEventDestroy(t.e);
+    // later work on the compute stream (the next call) must not overwrite rows still being copied: B is idle now
+    out->n_out = row_base; out->paf_nbytes = byte_base; out->n_pairs = pairs; out->_owner = blk;
+    if (want & RB_WANT_TEXT) {
+        out->paf_text = base + o_text;
+        out->line_off = reinterpret_cast<uint64_t*>(base + o_loff);
+        out->line_off[row_base] = byte_base;
+        if (row_base == 0) out->line_off[0] = 0;
+        out->paf_text[byte_base] = 0;
+    }
+    if (want & RB_WANT_NUMERIC) {
+        uint64_t* p = reinterpret_cast<uint64_t*>(base + o_num);
+        out->q_st = p; out->q_en = p + cap_rows; out->t_st = p + 2 * cap_rows; out->t_en = p + 3 * cap_rows;
+        out->nmatch = p + 4 * cap_rows; out->aln_len = p + 5 * cap_rows;
+        out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * cap_rows);
+        out->win_idx = out->rec_idx + cap_rows;
+    }
+    if (stats) {
+        uint32_t* p = reinterpret_cast<uint32_t*>(sblk->p);
+        const uint64_t c = cap_rows;
+        stats->n = row_base;
+        stats->equal = p; stats->diff = p + c; stats->ins = p + 2 * c; stats->del = p + 3 * c; stats->ins_events = p + 4 * c;
+        stats->del_events = p + 5 * c; stats->matches = p + 6 * c;
+        stats->id_by_matches = reinterpret_cast<float*>(p + 7 * c); stats->id_by_events = reinterpret_cast<float*>(p + 8 * c);
+        stats->id_by_all = reinterpret_cast<float*>(p + 9 * c);
+        stats->_owner = sblk;
+    }
+    return RB_OK;
 }
 
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {

@@ -202,7 +202,7 @@ std::vector<Region> parse_bed_text(const char* text, size_t n) {
         if (!strict(f[1], r.st) || !strict(f[2], r.en)) continue;
         r.name.assign(text + f[0].first, f[0].second);
         if (f.size() > 3) r.id.assign(text + f[3].first, f[3].second);
-        else r.id = r.name + ":" + std::to_string(r.st + 1) + "-" + std::to_string(r.en);  // bed.rs:150-153
+        else { r.id = r.name + ":" + std::to_string(r.st + 1) + "-" + std::to_string(r.en); r.default_id = true; }  // bed.rs:150-153
         out.push_back(std::move(r));
     }
     return out;
@@ -219,12 +219,16 @@ Windows Windows::pack(const std::vector<Region>& rgns, const Paf& paf) {
     }
     std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) { return a.t != b.t ? a.t < b.t : a.st < b.st; });
     Windows w;
-    w.ids_off.push_back(0);
+    w.default_ids = true;
+    for (const Row& r : rows) w.default_ids = w.default_ids && rgns[r.row].default_id;
+    if (!w.default_ids) w.ids_off.push_back(0);
     for (const Row& r : rows) {
         const Region& g = rgns[r.row];
         w.t_id.push_back(r.t); w.st.push_back(g.st); w.en.push_back(g.en); w.bed_row.push_back(r.row);
-        w.ids.insert(w.ids.end(), g.id.begin(), g.id.end());
-        w.ids_off.push_back(w.ids.size());
+        if (!w.default_ids) {
+            w.ids.insert(w.ids.end(), g.id.begin(), g.id.end());
+            w.ids_off.push_back(w.ids.size());
+        }
     }
     if (w.ids.empty()) w.ids.push_back(0);
     return w;
@@ -233,7 +237,7 @@ rb_windows Windows::view() const {
     rb_windows v{};
     v.n_win = (uint32_t)t_id.size();
     v.t_id = t_id.data(); v.st = st.data(); v.en = en.data(); v.bed_row = bed_row.data();
-    v.ids = ids.data(); v.ids_off = ids_off.data();
+    v.ids = default_ids ? nullptr : ids.data(); v.ids_off = default_ids ? nullptr : ids_off.data();
     return v;
 }
 

@@ -55,6 +55,7 @@ struct Region {
     std::string name;
     uint64_t st = 0, en = 0;
     std::string id;
+    bool default_id = false;  // no 4th BED column: id == "{name}:{st+1}-{en}" (bed.rs:150-153)
 };
 std::vector<Region> parse_bed_text(const char* text, size_t n);
 inline std::vector<Region> parse_bed(const std::string& path) {
@@ -67,6 +68,7 @@ struct Windows {
     std::vector<uint32_t> t_id, bed_row;
     std::vector<uint64_t> st, en, ids_off;
     std::vector<uint8_t> ids;
+    bool default_ids = false;  // every row carries the default id: ids / ids_off stay empty and the GPU formats them
     rb_windows view() const;
     static Windows pack(const std::vector<Region>& rgns, const Paf& paf);
 };

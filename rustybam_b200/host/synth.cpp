@@ -182,20 +182,13 @@ Windows tiling_windows_packed(const Paf& paf, uint64_t width) {
     std::sort(by_tid.begin(), by_tid.end(), [&](size_t a, size_t b) { return tl[a].first < tl[b].first; });
     Windows w;
     const size_t n = row0.back();
-    w.t_id.reserve(n); w.st.reserve(n); w.en.reserve(n); w.bed_row.reserve(n); w.ids_off.reserve(n + 1);
-    w.ids.reserve(n * 24);
-    w.ids_off.push_back(0);
-    char buf[64];
+    w.t_id.reserve(n); w.st.reserve(n); w.en.reserve(n); w.bed_row.reserve(n);
+    w.default_ids = true;  // 3-column BED: the GPU formats "{chrom}:{st+1}-{en}" itself
     for (size_t k : by_tid) {
-        const std::string& nm = paf.names[tl[k].first];
         uint32_t row = row0[k];
         for (uint64_t st = 0; st < tl[k].second; st += width, row++) {
             const uint64_t en = std::min(st + width, tl[k].second);
             w.t_id.push_back(tl[k].first); w.st.push_back(st); w.en.push_back(en); w.bed_row.push_back(row);
-            w.ids.insert(w.ids.end(), nm.begin(), nm.end());
-            const int m = snprintf(buf, sizeof buf, ":%llu-%llu", (unsigned long long)(st + 1), (unsigned long long)en);
-            w.ids.insert(w.ids.end(), buf, buf + m);
-            w.ids_off.push_back(w.ids.size());
         }
     }
     if (w.ids.empty()) w.ids.push_back(0);

@@ -136,6 +136,23 @@ def test_random_streaming_lift_mode(ctx, seed):
 
 
 @pytest.mark.parametrize("seed", range(6))
+def test_random_sliced_calls(ctx, seed):
+    # rb_liftover in slices (forced onto tiny inputs: >= 64 bytes of CIGAR per slice), records grouped by target
+    ctx.set_slicing(64)
+    try:
+        paf_text, contigs = gen.random_paf(500 + seed, n_contigs=5, recs_per_contig=9, style="all" if seed % 2 else "eqx",
+                                           canonical=(seed < 4), allow_zero=(seed >= 4), clips=(seed % 3 == 0), max_ops=200)
+        lines = sorted(paf_text.splitlines(keepends=True), key=lambda ln: ln.split(b"\t")[5])  # group by target: emission == file order
+        paf_text = b"".join(lines)
+        check_against_oracle(ctx, paf_text, gen.tiling_bed(contigs, 5 + seed), seed % 2)
+        check_against_oracle(ctx, paf_text, gen.random_bed(seed, contigs, 80, sort=True, with_ids=(seed % 2 == 0)))
+        check_against_oracle(ctx, paf_text, gen.random_bed(seed, contigs, 40))  # general layout: falls back to one batch
+        check_against_oracle(ctx, orc.golden_paf(), gen.tiling_bed({"chr20": 66210247, "chr21": 45827691, "chr22": 51353906}, 20_000 + seed))
+    finally:
+        ctx.set_slicing()
+
+
+@pytest.mark.parametrize("seed", range(6))
 def test_random_unsorted_nested_bed_general_path(ctx, seed):
     # BED file order is never sorted by the reference (Q5); nested + duplicate rows
     paf_text, contigs = gen.random_paf(100 + seed, n_contigs=3, recs_per_contig=6)

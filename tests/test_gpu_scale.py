@@ -152,6 +152,29 @@ def test_full_scale_streaming_path_equals_search_path(ctx, full, width):
         assert (a["stats"][k].view(np.uint32) == b["stats"][k].view(np.uint32)).all(), k
 
 
+def test_full_scale_sliced_call_equals_unsliced(ctx, full):
+    """rb_liftover in overlapped slices (the default for large calls) returns the bytes of the single-batch call."""
+    wins = full.tiling_windows(1000)
+    a = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    ctx.set_slicing(0)
+    try:
+        b = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    finally:
+        ctx.set_slicing()
+    assert a["n_out"] == b["n_out"] and a["n_pairs"] == b["n_pairs"] and a["paf_text"] == b["paf_text"]
+    for k in ("line_off", "q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len", "rec_idx", "win_idx"):
+        assert (a[k] == b[k]).all(), k
+    for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches"):
+        assert (a["stats"][k] == b["stats"][k]).all(), k
+    for k in ("id_by_matches", "id_by_events", "id_by_all"):
+        assert (a["stats"][k].view(np.uint32) == b["stats"][k].view(np.uint32)).all(), k
+    # text only / numeric only
+    c = ctx.liftover(full, wins, want=capi.WANT_TEXT, stats=False)
+    assert c["paf_text"] == a["paf_text"]
+    d = ctx.liftover(full, wins, want=capi.WANT_NUMERIC, stats=True)
+    assert (d["t_st"] == a["t_st"]).all() and (d["stats"]["equal"] == a["stats"]["equal"]).all()
+
+
 def test_rb_cli_matches_oracle(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
