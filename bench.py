@@ -213,9 +213,15 @@ def main():
     ctx.set_profiling(True)
     ctx.kernel_times(reset=True)
     n_prof = max(3, args.steps // 4)
+    prof_ms = []
     for _ in range(n_prof):
         flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
         ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
+        e1.record(stream)
+        e1.synchronize()
+        prof_ms.append(e0.elapsed_time(e1))
     torch.cuda.synchronize()
     ktimes = ctx.kernel_times(reset=True)
     ctx.set_profiling(False)
@@ -293,6 +299,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg[dom]),
                          "kernel_ms": dom_ms, "kernel_share_of_step": ms_sum / total_k,
+                         "step_ms_with_per_kernel_events": sum(prof_ms) / len(prof_ms),
                          "all_kernels_ms": {k: v[1] / max(v[0], 1) for k, v in ktimes.items()},
                          "all_kernels_frac": {k: (alg[k] / (v[1] / max(v[0], 1) * 1e-3) / 1e9) / peak for k, v in ktimes.items() if k in alg}},
             "wall_s_resident_loop": wall_resident, "gen_s": gen_s,

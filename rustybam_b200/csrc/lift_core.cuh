@@ -263,7 +263,7 @@ RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t
     }
     Ctr d = ce;
     ctr_sub(d, cs);
-    out.nmatch = (uint64_t)(uint32_t)(d.EQ + d.X + d.M);
+    out.nmatch = d.EQ + d.X + d.M;
     out.aln_len = d.A;
     fill_stats(out, d);
     out.si = si; out.ei = ei;
@@ -272,7 +272,10 @@ RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t
         out.cg_bytes = ndigits32(out.s_len) + 1;
     } else {
         out.s_len = L_si - so; out.e_len = eo + 1;
-        out.cg_bytes = ndigits32(out.s_len) + 1 + (txt_before_ei - cs.TXT - (ndigits32(L_si) + 1)) + ndigits32(out.e_len) + 1;
+        const uint32_t first = ndigits32(L_si) + 1;  // text bytes of op si as the input spells it (canonical)
+        out.mid_len = txt_before_ei - cs.TXT - first;
+        out.mid_off = r.text_off + cs.TXT + first;
+        out.cg_bytes = ndigits32(out.s_len) + 1 + out.mid_len + ndigits32(out.e_len) + 1;
     }
     if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
         uint32_t bytes = 0, iev = 0, dev = 0;
@@ -286,7 +289,7 @@ RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t
 }
 
 RB_HD void pair_clear(PairRes& out) {
-    out.pad = 0;
+    out.mid_len = 0; out.mid_off = 0;
     out.kind = PK_DROP;
     out.t_st = out.t_en = out.q_st = out.q_en = out.nmatch = out.aln_len = out.si = out.ei = 0;
     out.s_len = out.e_len = out.cg_bytes = 0;
@@ -296,10 +299,11 @@ RB_HD void pair_clear(PairRes& out) {
 RB_HD void pair_early(const RecInfo& r, PairRes& out) {
     out.kind = PK_EARLY;
     out.t_st = r.t_st; out.t_en = r.t_en; out.q_st = r.q_st; out.q_en = r.q_en;
-    out.nmatch = (uint64_t)(uint32_t)(r.tot.EQ + r.tot.X + r.tot.M);
+    out.nmatch = r.tot.EQ + r.tot.X + r.tot.M;
     out.aln_len = r.tot.A;
     out.si = r.eo0; out.ei = r.eo1 - 1;
     out.cg_bytes = r.tot.TXT;
+    out.mid_len = r.tot.TXT; out.mid_off = r.text_off + r.lead_txt;
     fill_stats(out, r.tot);
 }
 
@@ -367,7 +371,7 @@ RB_HD uint32_t combine_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, u
 // Bytes of the printed PAF line (paf.rs:923-943), '\n' included.
 RB_HD uint32_t line_bytes(const RecInfo& r, const PairRes& p, uint32_t q_name_len, uint32_t t_name_len, uint32_t id_len) {
     return q_name_len + t_name_len + id_len + ndigits64(r.q_len) + ndigits64(p.q_st) + ndigits64(p.q_en) + 1 /*strand*/ +
-           ndigits64(r.t_len) + ndigits64(p.t_st) + ndigits64(p.t_en) + ndigits64(p.nmatch) + ndigits64(p.aln_len) +
+           ndigits64(r.t_len) + ndigits64(p.t_st) + ndigits64(p.t_en) + ndigits32(p.nmatch) + ndigits32(p.aln_len) +
            ndigits64(r.mapq) + 11 /*tabs between the 12 columns*/ + 6 /*\tid:Z:*/ + 6 /*\tcg:Z:*/ + p.cg_bytes + 1 /*\n*/;
 }
 

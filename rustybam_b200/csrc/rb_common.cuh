@@ -208,6 +208,8 @@ enum : uint32_t {
     RF_MINUS = 1u,        // strand '-'
     RF_SLOW = 2u,         // has zero-length ops or adjacent same-class ops: trimmed rows need the merge walk (Q15)
     RF_STRIPPED = 4u,     // leading/trailing indels were stripped (id gets "_TO.<st>.<en>", paf.rs:726-732)
+    RF_CANON = 8u,        // the CIGAR text is canonical (no leading zeros): op k's text starts TXT_prefix(k) bytes into it,
+                          // so untouched ops of a trimmed row are copied from the input text instead of being re-formatted
 };
 
 // Per-record state after remove_trailing_indels (paf.rs:656-783).  Prefix counters in `samples`
@@ -228,21 +230,26 @@ struct RecInfo {
     uint32_t id_len;     // bytes of the "_TO.x.y" id suffix (0 if not stripped)
     Ctr tot;             // counters of the effective op range (early-return rows, integrity, rb stats)
     uint32_t wlo, whi;   // overlapping window range in the contig-sorted window arrays
-    uint32_t pad;
+    uint32_t lead_txt;   // canonical text bytes of the stripped leading ops (text offset of op eo0 inside the CIGAR)
+    uint64_t text_off;   // byte offset of the record's CIGAR in the device text buffer
+    uint64_t pad2;
 };
 
 // One (window, record) pair after lift: everything the serialiser and the numeric mirror need.
-struct PairRes {
+struct PairRes {          // 112 bytes
     uint64_t t_st, t_en, q_st, q_en;
-    uint64_t nmatch, aln_len;
     uint64_t si, ei;      // global op indices of the first / last op of the trimmed CIGAR
+    uint64_t mid_off;     // RF_CANON rows: where the untouched ops (strictly between si and ei; early rows: all ops) start in
+                          // the device text buffer ...
+    uint32_t mid_len;     // ... and how many bytes they are
+    uint32_t nmatch, aln_len;  // u32 like the reference's own accumulators (paf.rs:632-635)
     uint32_t s_len;       // length printed for op si (L_si - s.o, or e.o - s.o + 1 when si == ei)
     uint32_t e_len;       // length printed for op ei (e.o + 1); unused when si == ei
     uint32_t cg_bytes;    // bytes of the trimmed CIGAR text
     uint32_t kind;        // PK_*
     uint32_t equal, diff, ins, del, ins_ev, del_ev, matches;  // bamstats.rs:107-127 on the trimmed CIGAR
-    uint32_t pad;
 };
+static_assert(sizeof(PairRes) == 112, "PairRes layout");
 enum : uint32_t { PK_DROP = 0, PK_TRIM = 1, PK_EARLY = 2 };
 
 }  // namespace rb

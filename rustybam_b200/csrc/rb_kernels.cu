@@ -724,7 +724,8 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
         ri.q_len = in.q_len[r]; ri.t_len = in.t_len[r]; ri.mapq = in.mapq[r];
         ri.q_name = in.q_id[r]; ri.t_name = in.t_id[r];
         ri.flags = (in.strand[r] == '-') ? RF_MINUS : 0u;
-        ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.pad = 0;
+        ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.lead_txt = 0;
+        ri.text_off = in.cigar_off[r]; ri.pad2 = 0;
         ri.tot = ctr_zero();
     }
 
@@ -766,6 +767,7 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
     if ((uint64_t)full.T != t_en_in - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
     if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
+    if ((uint64_t)full.TXT == in.cigar_off[r + 1] - in.cigar_off[r]) ri.flags |= RF_CANON;  // no op is spelled with leading zeros
     if (ri.op_end > ri.op_first) {  // the sampled count stops at the last chunk boundary: look at the tail ops too
         const uint64_t base = ((ri.op_end - 1) >> SAMPLE_LOG2) << SAMPLE_LOG2;
         for (uint64_t k = base > ri.op_first ? base : ri.op_first; k < ri.op_end; k++) {
@@ -907,78 +909,80 @@ __device__ __forceinline__ uint32_t rank_of_pair(const uint64_t* __restrict__ pa
     return lo;
 }
 
+// One thread per block of LIFT_THREADS consecutive pairs: which record the block belongs to (if it is a single one)
+// and which run of 32-op chunks its pairs touch.  Doing the searches here, all blocks in parallel, keeps them out of
+// the prologue of k_lift / k_serialise where a whole block would wait for one thread's chain of dependent loads.
+__global__ void __launch_bounds__(128)
+k_lift_plan(uint64_t n_pairs, uint32_t n_blocks, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order,
+            uint32_t n_rec, const RecInfo* __restrict__ recs, const Ctr* __restrict__ samples, WinView win, LiftPlan* __restrict__ plans) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t p0 = (uint64_t)b * LIFT_THREADS;
+    const uint64_t plast = (p0 + LIFT_THREADS <= n_pairs ? p0 + LIFT_THREADS : n_pairs) - 1;
+    LiftPlan pl;
+    pl.k0 = rank_of_pair(pair_off, n_rec, p0);
+    pl.uniform = (pl.k0 == rank_of_pair(pair_off, n_rec, plast)) ? 1u : 0u;
+    pl.c_lo = pl.c_hi = ~0ull;
+    if (pl.uniform && win.pair_win == nullptr) {
+        const RecInfo& R = recs[rec_order[pl.k0]];
+        if (R.op_end > R.op_first && R.t_en > R.t_st) {
+            OpsView v;
+            v.ops = nullptr; v.samples = samples;
+            const uint64_t pbase = pair_off[pl.k0];
+            const uint64_t t_st = R.t_st, t_en = R.t_en;
+            const uint64_t st = win.st[R.wlo + (uint32_t)(p0 - pbase)];     // start boundary of the block's first pair
+            const uint64_t en = win.en[R.wlo + (uint32_t)(plast - pbase)];  // end boundary of its last pair
+            pl.c_lo = chunk_of(v, R, (uint32_t)((st > t_st ? st : t_st) - t_st));
+            pl.c_hi = chunk_of(v, R, (uint32_t)((en < t_en ? en : t_en) - 1 - t_st));
+        }
+    }
+    plans[b] = pl;
+}
+
 // CTA = LIFT_THREADS consecutive pairs in emission order.  On the sorted-BED path the pairs of a block that belong
 // to one record touch a contiguous run of ops (start of the first window .. end of the last one): that run and
-// its samples are staged in shared memory once (coalesced), so the per-pair searches and <=32-op walks of
+// its samples are staged in shared memory once (coalesced), so the per-pair searches and <=7-op walks of
 // lift_pair never leave the SM.  Blocks that straddle records, explicit pair lists (general path) and runs that
 // do not fit fall back to global memory through the same OpsView accessor.
 __global__ void __launch_bounds__(LIFT_THREADS, RB_LIFT_MINB)
 k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
        const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
-       const uint64_t* __restrict__ names_off, int policy, PairRes* __restrict__ res, uint32_t* __restrict__ line_len, ErrSlots err) {
+       const uint64_t* __restrict__ names_off, int policy, const LiftPlan* __restrict__ plans, PairRes* __restrict__ res,
+       uint32_t* __restrict__ line_len, ErrSlots err) {
     __shared__ uint32_t s_acc[9 * LIFT_THREADS];
     __shared__ __align__(16) uint32_t s_ops[(LIFT_CCAP + 1) * SAMPLE];
     __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
-    __shared__ uint32_t s_k[2];
-    __shared__ unsigned long long s_c[2];
     __shared__ __align__(16) RecInfo s_rec;
-    __shared__ uint32_t s_r;
-    bool uniform = false;
     const int tid = threadIdx.x;
     const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
-    const uint64_t plast = (p0 + LIFT_THREADS <= n_pairs ? p0 + LIFT_THREADS : n_pairs) - 1;
     const uint64_t p = p0 + tid;
     OpsView v;
     v.ops = ops; v.samples = samples;
-
-    // ---- block-level staging (fast path only) ----
-    if (win.pair_win == nullptr) {
-        if (tid == 0) s_k[0] = rank_of_pair(pair_off, n_rec, p0);
-        if (tid == 32) s_k[1] = rank_of_pair(pair_off, n_rec, plast);
-        __syncthreads();
-        const uint32_t k0 = s_k[0];
-        if (k0 == s_k[1]) {  // one record for the whole block (block-uniform branch)
-            uniform = true;
-            const uint32_t r = rec_order[k0];
-            static_assert(sizeof(RecInfo) % 16 == 0, "RecInfo is copied in 16-byte vectors");
-            if (tid < (int)(sizeof(RecInfo) / 16))
-                reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(&recs[r])[tid];
-            if (tid == 0) s_r = r;
-            __syncthreads();
-            const RecInfo& R = s_rec;
-            const uint64_t pbase = pair_off[k0];
-            if (tid == 0 || tid == 32) {
-                unsigned long long c = ~0ull;
-                if (R.op_end > R.op_first && R.t_en > R.t_st) {
-                    if (tid == 0) {  // chunk that holds the start boundary of the block's first pair
-                        const uint64_t st = win.st[R.wlo + (uint32_t)(p0 - pbase)];
-                        c = chunk_of(v, R, (uint32_t)((st > R.t_st ? st : R.t_st) - R.t_st));
-                    } else {         // chunk that holds the end boundary of the block's last pair
-                        const uint64_t en = win.en[R.wlo + (uint32_t)(plast - pbase)];
-                        c = chunk_of(v, R, (uint32_t)((en < R.t_en ? en : R.t_en) - 1 - R.t_st));
-                    }
-                }
-                s_c[tid >> 5] = c;
+    const LiftPlan pl = plans[blockIdx.x];
+    const bool uniform = pl.uniform != 0;
+    uint32_t r_blk = 0;
+    if (uniform) {  // block-uniform: the record and (if it fits) the op run + samples of the block go to shared memory
+        r_blk = rec_order[pl.k0];
+        static_assert(sizeof(RecInfo) % 16 == 0, "RecInfo is copied in 16-byte vectors");
+        if (tid < (int)(sizeof(RecInfo) / 16)) reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(&recs[r_blk])[tid];
+        const uint64_t c_lo = pl.c_lo, c_hi = pl.c_hi;
+        if (c_lo != ~0ull && c_hi != ~0ull && c_hi >= c_lo && c_hi - c_lo < (uint64_t)LIFT_CCAP) {
+            const uint64_t op_end = recs[r_blk].op_end;
+            const uint64_t o_lo = c_lo << SAMPLE_LOG2;
+            uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
+            if (o_hi > op_end) o_hi = op_end;
+            for (uint64_t k = o_lo + tid; k < o_hi; k += LIFT_THREADS) s_ops[k - o_lo] = ops[k];
+            const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
+            const uint64_t c_max = (op_end - 1) >> SAMPLE_LOG2;
+            constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
+            for (uint64_t i = tid; i < nc * V; i += LIFT_THREADS) {
+                const uint64_t c = c_lo + i / V;
+                if (c <= c_max) reinterpret_cast<uint4*>(s_smp)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(samples) + c * V + i % V);
             }
-            __syncthreads();
-            const uint64_t c_lo = s_c[0], c_hi = s_c[1];
-            if (c_lo != ~0ull && c_hi != ~0ull && c_hi >= c_lo && c_hi - c_lo < (uint64_t)LIFT_CCAP) {
-                const uint64_t o_lo = c_lo << SAMPLE_LOG2;
-                uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
-                if (o_hi > R.op_end) o_hi = R.op_end;
-                for (uint64_t k = o_lo + tid; k < o_hi; k += LIFT_THREADS) s_ops[k - o_lo] = ops[k];
-                const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
-                const uint64_t c_max = (R.op_end - 1) >> SAMPLE_LOG2;
-                constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
-                for (uint64_t i = tid; i < nc * V; i += LIFT_THREADS) {
-                    const uint64_t c = c_lo + i / V;
-                    if (c <= c_max) reinterpret_cast<uint4*>(s_smp)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(samples) + c * V + i % V);
-                }
-                v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
-                v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = (c_hi + 1 <= c_max ? c_hi + 2 : c_hi + 1);
-            }
-            __syncthreads();
+            v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
+            v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = (c_hi + 1 <= c_max ? c_hi + 2 : c_hi + 1);
         }
+        __syncthreads();
     }
     if (p >= n_pairs) return;
     ClassAcc acc;
@@ -986,7 +990,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     uint32_t k, r;
     const RecInfo* rp;
     if (uniform) {  // the block's record sits in shared memory: no per-thread search, no per-thread 208-byte load
-        k = s_k[0]; r = s_r; rp = &s_rec;
+        k = pl.k0; r = r_blk; rp = &s_rec;
     } else {
         k = rank_of_pair(pair_off, n_rec, p);
         r = rec_order[k];
@@ -1216,6 +1220,7 @@ struct SerArgs {
     WinView win;
     const uint64_t* names_off;
     const uint8_t* names;
+    const uint8_t* text;  // the input CIGAR text (device copy)
 };
 
 // "_TO.<leading ops>.<trailing ops, last first>" (paf.rs:726-732)
@@ -1241,8 +1246,8 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     *p++ = '\t'; p = put_u64(p, ri.t_len);
     *p++ = '\t'; p = put_u64(p, pr.t_st);
     *p++ = '\t'; p = put_u64(p, pr.t_en);
-    *p++ = '\t'; p = put_u64(p, pr.nmatch);
-    *p++ = '\t'; p = put_u64(p, pr.aln_len);
+    *p++ = '\t'; p = put_u32(p, pr.nmatch);
+    *p++ = '\t'; p = put_u32(p, pr.aln_len);
     *p++ = '\t'; p = put_u64(p, ri.mapq);
     *p++ = '\t'; *p++ = 'i'; *p++ = 'd'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
     if (pr.kind == PK_EARLY) {
@@ -1260,25 +1265,51 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     return p;
 }
 
-// trimmed / early-return CIGAR text, sequential
+// n bytes of the input CIGAR text -> p (4 source bytes per load: aligned words + funnel shift; the text buffer is padded
+// on both sides, so the over-read of up to 7 bytes stays inside it)
+template <class P>
+__device__ __forceinline__ P put_text(P p, const uint8_t* __restrict__ src, uint32_t n) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    uint32_t lo = __ldg(w);
+    for (uint32_t i = 0; i < n; i += 4) {
+        const uint32_t hi = __ldg(++w);
+        const uint32_t x = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        p[i] = (uint8_t)x;
+        if (i + 1 < n) p[i + 1] = (uint8_t)(x >> 8);
+        if (i + 2 < n) p[i + 2] = (uint8_t)(x >> 16);
+        if (i + 3 < n) p[i + 3] = (uint8_t)(x >> 24);
+    }
+    return p + n;
+}
+
+// trimmed / early-return CIGAR text, sequential.  Ops the trim leaves untouched are copied from the input text when
+// the record spells them canonically (RF_CANON) instead of being re-formatted from the op words.
 template <class P>
 __device__ __forceinline__ P put_cigar_seq(P p, const SerArgs& a, const RecInfo& ri, const PairRes& pr) {
     const OpsView& v = a.v;
+    const bool canon = (ri.flags & RF_CANON) != 0;
     if (pr.kind == PK_EARLY) {
+        if (canon) return put_text(p, a.text + pr.mid_off, pr.mid_len);
         for (uint64_t k = pr.si; k <= pr.ei; k++) { const uint32_t w = v.op(k); p = put_op(p, op_len(w), op_code(w)); }
     } else if (ri.flags & RF_SLOW) {
         merged_walk(v, pr.si, pr.ei, pr.s_len, pr.e_len, [&](uint32_t len, uint32_t code) { p = put_op(p, len, code); });
     } else {
         p = put_op(p, pr.s_len, op_code(v.op(pr.si)));
-        for (uint64_t k = pr.si + 1; k < pr.ei; k++) { const uint32_t w = v.op(k); p = put_op(p, op_len(w), op_code(w)); }
-        if (pr.ei > pr.si) p = put_op(p, pr.e_len, op_code(v.op(pr.ei)));
+        if (pr.ei > pr.si) {
+            if (canon) p = put_text(p, a.text + pr.mid_off, pr.mid_len);
+            else for (uint64_t k = pr.si + 1; k < pr.ei; k++) { const uint32_t w = v.op(k); p = put_op(p, op_len(w), op_code(w)); }
+            p = put_op(p, pr.e_len, op_code(v.op(pr.ei)));
+        }
     }
     return p;
 }
 
 __global__ void __launch_bounds__(SER_LINES)
 k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
-            SerArgs a, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off, const uint64_t* __restrict__ out_idx,
+            SerArgs a, const LiftPlan* __restrict__ plans, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
+            const uint64_t* __restrict__ out_idx,
             uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
             uint32_t rec_base) {
     extern __shared__ __align__(16) uint8_t s_buf[];
@@ -1300,8 +1331,11 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         my_len = line_off[p + 1] - my_off;
     }
     const bool live = (pr.kind != PK_DROP);
+    static_assert(SER_LINES == LIFT_THREADS, "k_serialise reuses the per-block plan of k_lift");
+    const LiftPlan pl = plans[blockIdx.x];  // one record for the whole block (the usual case at scale): no per-thread search
+    const bool uniform = pl.uniform != 0;
     if (live) {
-        const uint32_t k = rank_of_pair(pair_off, n_rec, p);
+        const uint32_t k = uniform ? pl.k0 : rank_of_pair(pair_off, n_rec, p);
         r = rec_order[k];
         w = a.win.pair_win ? a.win.pair_win[p] : (a.recs[r].wlo + (uint32_t)(p - pair_off[k]));
         const uint64_t o = out_idx[p];
@@ -1363,6 +1397,20 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         dst += hdr;
         if ((ri.flags & RF_SLOW) && lp.kind == PK_TRIM) {
             if (lane == 0) put_cigar_seq(dst, a, ri, lp);
+        } else if (ri.flags & RF_CANON) {
+            // untouched ops come straight from the input text: one coalesced copy by the whole warp
+            uint64_t pos = 0;
+            if (lp.kind == PK_TRIM) {
+                if (lane == 0) {
+                    uint8_t* e = put_op(dst, lp.s_len, op_code(a.v.op(lp.si)));
+                    if (lp.ei > lp.si) put_op(e + lp.mid_len, lp.e_len, op_code(a.v.op(lp.ei)));
+                }
+                pos = ndigits32(lp.s_len) + 1;
+            }
+            if (lp.kind == PK_EARLY || lp.ei > lp.si) {
+                const uint8_t* src = a.text + lp.mid_off;
+                for (uint32_t i = lane; i < lp.mid_len; i += 32) dst[pos + i] = src[i];
+            }
         } else {
             // 32 ops per round: per-lane text, warp scan of sizes, stage, coalesced byte copy
             uint64_t pos = 0;
@@ -1451,12 +1499,18 @@ void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32
 void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s) {
     k_pair_scan<<<1, 1024, 0, s>>>(pair_cnt, rec_order, n_rec, pair_off);
 }
+void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s) {
+    if (n_pairs == 0) return;
+    const uint32_t nb = (uint32_t)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS);
+    k_lift_plan<<<(nb + 127) / 128, 128, 0, s>>>(n_pairs, nb, pair_off, rec_order, n_rec, recs, samples, win, plans);
+}
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, PairRes* res,
-                 uint32_t* line_len, ErrSlots err, cudaStream_t s) {
+                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s) {
     if (n_pairs == 0) return;
     k_lift<<<(unsigned)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS), LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
-                                                             policy, res, line_len, err);
+                                                             policy, plans, res, line_len, err);
 }
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s) {
@@ -1465,9 +1519,9 @@ void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off,
     k_scan_lines<<<(unsigned)blocks, LNS_THREADS, 0, s>>>(line_len, n, line_off, out_idx, blk_state, blk_agg, blk_pre, ticket);
 }
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                      const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
-                      const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
-                      StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s) {
+                      const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                      const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
+                      uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1476,9 +1530,9 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     }
     OpsView view;
     view.ops = ops; view.samples = nullptr;
-    SerArgs a{recs, view, win, names_off, names};
+    SerArgs a{recs, view, win, names_off, names, text};
     k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
-        n_pairs, pair_off, rec_order, n_rec, a, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base);
+        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base);
 }
 // Device scalars -> mapped pinned host memory with plain SM stores: the host reads them after a stream sync.  (A
 // cudaMemcpyAsync would queue on the device->host DMA engine behind the bulk download of the previous slice.)

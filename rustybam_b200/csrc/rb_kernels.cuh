@@ -104,15 +104,23 @@ void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_
 void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32_t* ops, const Ctr* samples, WinView win,
                      RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s);
 void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s);
+// per block of LIFT_THREADS consecutive pairs (emission order): its record, if it has only one, and the run of chunks it touches
+struct LiftPlan {
+    uint32_t k0;        // emission rank of the record of the block's first pair
+    uint32_t uniform;   // 1: every pair of the block belongs to that record
+    uint64_t c_lo, c_hi;  // chunks of the first start boundary / last end boundary (~0: not applicable)
+};
+void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s);
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, PairRes* res,
-                 uint32_t* line_len, ErrSlots err, cudaStream_t s);
+                 const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s);
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s);
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                      const uint32_t* ops, WinView win, const uint64_t* names_off, const uint8_t* names, const PairRes* res,
-                      const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text, uint64_t* out_line_off, NumDev num,
-                      StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s);
+                      const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                      const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
+                      uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s);
 struct PublishArgs {  // up to 8 device scalars (u32 or u64) -> slots of a mapped pinned u64 array
     const void* src[8];
     uint8_t slot[8];

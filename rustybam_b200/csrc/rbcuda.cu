@@ -90,7 +90,7 @@ struct rb_batch {
     DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, w_tid, cont_lo, cont_hi;
     // intermediates
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
-    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e;
+    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans;
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -366,7 +366,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
     delete b;
 }
@@ -795,6 +795,12 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                             b->pair_win.as<uint32_t>(), s);
         win.pair_win = b->pair_win.as<uint32_t>();
     }
+    CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
+    {
+        KScope k(ctx, "k_lift_plan");
+        launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
+                         b->plans.as<LiftPlan>(), s);
+    }
     if (fused) {
         KScope k(ctx, "k_combine");
         launch_combine(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(), win,
@@ -803,7 +809,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     } else {
         KScope k(ctx, "k_lift");
         launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
-                    b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->pair_res.as<PairRes>(),
+                    b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
                     b->line_len.as<uint32_t>(), err, s);
     }
     {
@@ -828,7 +834,8 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     {
         KScope k(ctx, "k_serialise");
         launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
-                         win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(), b->pair_res.as<PairRes>(),
+                         b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
+                         b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
                          b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                          (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},

@@ -25,7 +25,7 @@ enum : uint32_t {
 RB_HD uint32_t strip_record(const uint32_t* ops, RecInfo& r) {
     r.eo0 = r.op_first; r.eo1 = r.op_end;
     r.q_st = r.q_st0; r.q_en = r.q_en0;
-    r.a_lead = 0; r.n_lead = 0; r.n_trail = 0; r.id_len = 0;
+    r.a_lead = 0; r.n_lead = 0; r.n_trail = 0; r.id_len = 0; r.lead_txt = 0;
     if (r.op_end <= r.op_first) return RE_STRIP_PANIC;  // self.cigar.first().unwrap() on an empty CIGAR
     uint32_t lead_i = 0, trail_i = 0, trail_d = 0, txt = 0;
     uint64_t k = r.op_first;
@@ -38,6 +38,7 @@ RB_HD uint32_t strip_record(const uint32_t* ops, RecInfo& r) {
         r.n_lead++;
     }
     if (k == r.op_end) return RE_STRIP_PANIC;  // nothing but indels: both ends strip everything, spans break
+    r.lead_txt = txt;
     uint64_t k2 = r.op_end;
     while (k2 > k) {
         const uint32_t w = ops[k2 - 1], code = op_code(w);
