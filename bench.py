@@ -34,7 +34,8 @@ CONTIG_LEN = [248387328, 242696752, 201105948, 193574945, 182045439, 172126628, 
               51324926, 154259566, 62460029, 16569]
 CONTIG_NAME = [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY", "chrM"]
 WINDOW = 1000
-CPU_SAMPLE_CONTIGS = ["chr21", "chr22", "chrM"]  # bounded CPU sample: ~96 Mbp of the ~3.1 Gbp workload
+CPU_SAMPLE_CONTIGS = ["chr21", "chr22", "chrM"]  # --impl reference, per step: ~96 Mbp of the ~3.1 Gbp workload
+CPU_BASELINE_CONTIGS = ["chr16", "chr17", "chr18", "chr19", "chr20", "chr21", "chr22", "chrM"]  # cpu_baseline: ~0.5 Gbp, one pass
 
 
 def measured_peak():
@@ -82,15 +83,16 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-def cpu_reference_sample(threads):
+def cpu_reference_sample(threads, contigs=None):
     """The reference's CPU path (restated: oracle/, literal per-base algorithm) on a bounded sample of
-    the same workload: all records of CPU_SAMPLE_CONTIGS + their 1 kb windows -> liftover -> stats."""
+    the same workload: all records of `contigs` + their 1 kb windows -> liftover -> stats."""
+    contigs = contigs or CPU_SAMPLE_CONTIGS
     import orc
     from rustybam_b200 import hostlib
     mask_scale = 1.0
     paf = hostlib.HostPaf.synth(scale=mask_scale, n_hap=1, threads=min(8, os.cpu_count() or 1))
     texts, beds, nrec = [], [], 0
-    for nm in CPU_SAMPLE_CONTIGS:
+    for nm in contigs:
         tid = paf.find_name(nm)
         t, n = paf.text_of_contig(tid)
         texts.append(t)
@@ -108,7 +110,7 @@ def run_reference(args, rank, world):
         return
     import orc
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    threads = min(8, os.cpu_count() or 1)  # the reference's default is -t 8 (cli.rs:17-19)
+    threads = os.cpu_count() or 8  # `rb -t N`: every host core (the reference's default is -t 8, cli.rs:17-19)
     paf_text, bed_text, nrec = cpu_reference_sample(threads)
     times, rows = [], 0
     for i in range(args.warmup + args.steps):
@@ -123,7 +125,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32/u64 (+f32 identities)", "data": "synthetic",
-            "config": {"workload": "C4 sub-sample: liftover 1 kb windows + stats on the host CPU", "window_bp": WINDOW},
+            "config": {"workload": "C4: rb liftover --bed <1 kb tiling windows> over synthetic HG002-vs-CHM13-scale eqx PAF + per-row rb stats --paf",
+                       "window_bp": WINDOW, "sample_per_step": "+".join(CPU_SAMPLE_CONTIGS), "host_cores": os.cpu_count()},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -177,7 +180,12 @@ def main():
             pinned.append(addr)
 
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it and the CUDA events below are recorded on it.  (Handing
+    # the library torch's default stream, handle 0, means "use your own stream" in the C ABI: events recorded on the
+    # default stream would then not bracket the kernels.)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > L2 (126 MB): flushed between timed steps
 
@@ -261,13 +269,16 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         # algorithmic (compulsory) bytes per launch of each kernel, rank 0's shard — DESIGN.md §5
+        smp_bytes = (n_ops // 32) * 4 * 48  # 4 counters blocks (1 sample + 3 sub-samples) of 48 B per 32-op chunk
         alg = {
-            "k_tokenise": cigar_bytes + 4 * n_ops,
-            "k_samples": 4 * n_ops + (n_ops // 32) * (4 + 48),
-            "k_scan_lift": 4 * n_ops + (n_ops // 32) * (4 + 48) + 16 * wins.n_win + 128 * n_pairs,
+            "k_tokenise": cigar_bytes + 4 * n_ops,                       # text in, one 4-byte op word out
+            "k_samples": 4 * n_ops + smp_bytes,                          # op words in, samples out
+            "k_scan_lift": 4 * n_ops + smp_bytes + 16 * wins.n_win + 128 * n_pairs,
             "k_combine": n_pairs * (128 + 16 + 112 + 4),
-            "k_lift": n_pairs * (16 + 116 + 2 * (48 + 64)),
-            "k_serialise": n_pairs * (112 + 16) + 4 * n_ops + out_bytes + n_out * (40 + 8),
+            # windows (16 B) in, PairRes (112 B) + line size (4 B) out per pair; every op word and sample block read once
+            "k_lift": n_pairs * (16 + 112 + 4) + 4 * n_ops + smp_bytes,
+            # PairRes + line offset in, every output byte + the stats row + the line offset out, copied CIGAR text in
+            "k_serialise": n_pairs * (112 + 8) + out_bytes + n_out * (40 + 8) + cigar_bytes,
             "k_scan_lines": n_pairs * (4 + 16),
         }
         total_k = sum(ms for _, ms in ktimes.values()) or 1.0
@@ -307,13 +318,13 @@ def main():
         if not args.no_cpu_baseline:
             import orc
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-            threads = min(8, os.cpu_count() or 1)
-            paf_text, bed_text, nrec = cpu_reference_sample(threads)
+            threads = os.cpu_count() or 8
+            paf_text, bed_text, nrec = cpu_reference_sample(threads, CPU_BASELINE_CONTIGS)
             r = orc.bench_pipeline(paf_text, bed_text, threads=threads)
             sec = r["secs_liftover"] + r["secs_stats"]
             line["cpu_baseline"] = {
                 "value": r["rows"] / sec, "unit": UNIT, "cores": threads, "kind": "port", "host_cores": os.cpu_count(),
-                "seconds": sec, "sample": f"records of {'+'.join(CPU_SAMPLE_CONTIGS)} ({nrec} records) x their 1 kb windows -> {r['rows']} rows; "
+                "seconds": sec, "sample": f"records of {'+'.join(CPU_BASELINE_CONTIGS)} ({nrec} records) x their 1 kb windows -> {r['rows']} rows; "
                                           "restated reference CPU path (oracle/), not the rb binary; PAF parse + liftover + print + stats"}
         print(json.dumps(line))
     for addr in pinned:

@@ -30,7 +30,10 @@ constexpr int LIFT_THREADS = RB_LIFT_THREADS;  // pairs per k_lift block
 constexpr int LIFT_CCAP = RB_LIFT_CCAP;        // 32-op chunks of one record a k_lift block stages in shared memory
 constexpr int LNS_THREADS = 256;
 constexpr int SER_LINES = 128;              // lines per serialiser block
-constexpr int SER_CAP = 40 * 1024;          // smem bytes for composing a line group
+#ifndef RB_SER_CAP_KB
+#define RB_SER_CAP_KB 26
+#endif
+constexpr int SER_CAP = RB_SER_CAP_KB * 1024;  // smem bytes for composing a line group
 
 struct ScanPayload {  // look-back payload of the segmented sample scan: 64 B, 16-byte aligned
     Ctr c;

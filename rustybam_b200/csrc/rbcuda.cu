@@ -724,6 +724,9 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
+    const bool trace = getenv("RB_TRACE_STEP") != nullptr;  // device-side phase times of one resident step
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (trace) { for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], s); }
     int rc = run_tok(ctx, b);
     if (rc != RB_OK) return rc;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
@@ -747,6 +750,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
     Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC)
         .u64(4, b->pair_off.as<uint64_t>() + n).go(s);
+    if (trace) cudaEventRecord(tev[1], s);
     CU(cudaStreamSynchronize(s));
     b->busy = false;  // every upload of this batch has been consumed
     if ((uint32_t)hs[3] & 1u) {
@@ -818,6 +822,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                           b->ln_state.as<uint32_t>(), b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
     }
     Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, b->line_off.as<uint64_t>() + P).u64(6, b->out_idx.as<uint64_t>() + P).go(s);
+    if (trace) cudaEventRecord(tev[2], s);
     CU(cudaStreamSynchronize(s));
     rc = map_err(ctx, b, hs[0], hs[1]);
     if (rc != RB_OK) { flush_times(ctx); return rc; }
@@ -842,6 +847,14 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                          b->byte_base, b->rec_base, s);
     }
     if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
+    if (trace) {
+        cudaEventRecord(tev[3], s);
+        cudaEventSynchronize(tev[3]);
+        float a = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&c, tev[1], tev[2]); cudaEventElapsedTime(&d, tev[2], tev[3]);
+        fprintf(stderr, "[rb_batch_liftover device] tokenise..pair_scan %.3f ms | scan..scan_lines (incl. host sync gap) %.3f ms | serialise %.3f ms\n", a, c, d);
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     CU(cudaGetLastError());
     if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
     b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
@@ -1128,15 +1141,16 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         if ((want & RB_WANT_NUMERIC) && nk) {
             uint64_t* d = reinterpret_cast<uint64_t*>(base + o_num);
             const uint64_t* sp = sb->out_num.as<uint64_t>();
-            for (int c = 0; c < 6; c++) CU(cudaMemcpyAsync(d + (size_t)c * cap_rows + row_base, sp + (size_t)c * nk, nk * 8, cudaMemcpyDeviceToHost, B));
+            // one strided copy per table: columns are nk rows apart on the device and cap_rows apart in the pinned block
+            CU(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, nk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
             uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 6 * cap_rows);
             const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * nk);
-            for (int c = 0; c < 2; c++) CU(cudaMemcpyAsync(d32 + (size_t)c * cap_rows + row_base, s32 + (size_t)c * nk, nk * 4, cudaMemcpyDeviceToHost, B));
+            CU(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, nk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
         }
         if (stats && nk) {
             uint32_t* d = reinterpret_cast<uint32_t*>(sblk->p);
             const uint32_t* sp = sb->out_stats.as<uint32_t>();
-            for (int c = 0; c < 10; c++) CU(cudaMemcpyAsync(d + (size_t)c * cap_rows + row_base, sp + (size_t)c * nk, nk * 4, cudaMemcpyDeviceToHost, B));
+            CU(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, nk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
         }
         CU(cudaEventRecord(ctx->ev_d2h[k & 1], B));
         TE("B download done", k, B);

@@ -22,7 +22,11 @@ paf = hostlib.HostPaf.synth(scale=args.scale)
 wins = paf.tiling_windows(args.window)
 ctx = capi.Context(0)
 b = ctx.upload(paf, None if args.stats_only else wins)
+import torch
+flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 for i in range(args.warmup + args.steps):
+    if os.environ.get('RB_FLUSH'):
+        flush.fill_(1)
     s = ctx.batch_stats(b) if args.stats_only else ctx.batch_liftover(b, with_stats=True, want=capi.WANT_TEXT)
 print(s)
 ctx.batch_free(b)
