@@ -1311,7 +1311,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             SerArgs a, const LiftPlan* __restrict__ plans, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
             const uint64_t* __restrict__ out_idx,
             uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
-            uint32_t rec_base) {
+            uint32_t rec_base, const uint32_t* __restrict__ orig_idx) {
     extern __shared__ __align__(16) uint8_t s_buf[];
     __shared__ uint8_t s_stage[SER_LINES / 32][384];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1343,7 +1343,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         if (num.q_st) {
             num.q_st[o] = pr.q_st; num.q_en[o] = pr.q_en; num.t_st[o] = pr.t_st; num.t_en[o] = pr.t_en;
             num.nmatch[o] = pr.nmatch; num.aln_len[o] = pr.aln_len;
-            num.rec_idx[o] = r + rec_base; num.win_idx[o] = a.win.bed_row[w];
+            num.rec_idx[o] = orig_idx ? orig_idx[r] : r + rec_base; num.win_idx[o] = a.win.bed_row[w];
         }
         if (st.equal) write_stats(st, o, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
     }
@@ -1521,7 +1521,8 @@ void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off,
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
-                      uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, cudaStream_t s) {
+                      uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
+                      cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1532,7 +1533,7 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     view.ops = ops; view.samples = nullptr;
     SerArgs a{recs, view, win, names_off, names, text};
     k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
-        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base);
+        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx);
 }
 // Device scalars -> mapped pinned host memory with plain SM stores: the host reads them after a stream sync.  (A
 // cudaMemcpyAsync would queue on the device->host DMA engine behind the bulk download of the previous slice.)

@@ -77,7 +77,9 @@ struct rb_batch {
     bool general = false;  // BED rows not (sorted, monotone `en`, file order == sorted order): brute-force join
     std::vector<uint64_t> h_cigar_off;
     // host staging of the asynchronous uploads (must stay alive until the stream has consumed it)
-    std::vector<uint32_t> h_order, h_rank, h_clo, h_chi;
+    std::vector<uint32_t> h_order, h_rank, h_clo, h_chi, h_orig, h_qid, h_tid;
+    std::vector<uint64_t> h_cols;
+    std::vector<uint8_t> h_strand;
     struct { std::vector<uint64_t> st, en, off; std::vector<uint32_t> row; std::vector<uint8_t> ids; } h_gen;
     bool busy = false;         // uploads of this batch may still be in flight
     bool win_pending = false;  // the window check kernel's verdict has not been read yet
@@ -90,7 +92,7 @@ struct rb_batch {
     DevBuf w_st, w_en, w_ids_off, w_ids, w_bed_row, w_tid, cont_lo, cont_hi;
     // intermediates
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
-    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans;
+    DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans, orig_idx;
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -217,7 +219,7 @@ int map_err(rb_ctx* ctx, rb_batch* b, uint64_t e_tok, uint64_t e_rec) {
         code = (uint32_t)(e_rec & 0xFF);
     }
     if (best_rec == UINT64_MAX) return RB_OK;
-    best_rec += b->rec_base;  // slices report the caller's record index
+    best_rec = (!b->h_orig.empty() && best_rec < b->h_orig.size()) ? b->h_orig[best_rec] : best_rec + b->rec_base;  // the caller's record index
     switch (code) {
         case RE_CIGAR_PARSE: return fail(ctx, RB_ERR_REF_CIGAR_PARSE, "record %llu: Unable to parse cigar string (reference panics, paf.rs:399)", (unsigned long long)best_rec);
         case RE_INTEGRITY: return fail(ctx, RB_ERR_REF_INTEGRITY, "record %llu: CIGAR does not match the record's spans (check_integrity().unwrap(), paf.rs:70)", (unsigned long long)best_rec);
@@ -366,7 +368,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
     delete b;
 }
@@ -453,7 +455,15 @@ int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, ui
 // copy goes first so that the host-side checks of the window table (3 M rows at 1 kb windows) run while the DMA
 // engine is busy.  Host staging that must outlive the call lives in the batch.
 // records [r0, r1) of R: the CIGAR text, the one big copy — issued before any host-side work
-static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t r0, uint32_t r1) {
+// Which records of the caller's arrays a batch holds: a run [r0, r0 + n), or the list idx[0..n) (slices of a PAF whose
+// file order is not the emission order: the list is in emission order and is gathered run by run).
+struct RecSel {
+    const uint32_t* idx;
+    uint32_t r0, n;
+    uint32_t at(uint32_t i) const { return idx ? idx[i] : r0 + i; }
+};
+
+static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel sel) {
     cudaStream_t s = ctx->stream;
     if (!R || (R->n_rec && (!R->cigar_off || !R->q_len || !R->q_st || !R->q_en || !R->t_len || !R->t_st || !R->t_en || !R->mapq ||
                             !R->strand || !R->q_id || !R->t_id || !R->names_off)) ||
@@ -461,12 +471,19 @@ static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t 
         return fail(ctx, RB_ERR_BAD_ARG, "rb_records: null column");
     if (R->n_rec && (R->cigar_off[0] != 0 || R->cigar_off[R->n_rec] != R->cigar_nbytes)) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
     if (!R->n_rec && R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off must span [0, cigar_nbytes]");
-    const uint32_t n = r1 - r0;
+    const uint32_t n = sel.n;
     if (b->busy) { CU(cudaStreamSynchronize(s)); b->busy = false; }  // the previous call's copies read the staging below
-    const uint64_t byte0 = n ? R->cigar_off[r0] : 0, byte1 = n ? R->cigar_off[r1] : 0;
-    if (byte1 < byte0 || byte1 > R->cigar_nbytes) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone");
-    b->n_rec = n; b->n_names = R->n_names; b->n_bytes = byte1 - byte0;
-    b->rec_base = r0; b->byte_base = 0;
+    // runs of consecutive records -> one copy each; h_cigar_off = offsets inside the batch's own text
+    b->h_cigar_off.resize((size_t)n + 1);
+    b->h_cigar_off[0] = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t r = sel.at(i);
+        if (r >= R->n_rec || R->cigar_off[r] > R->cigar_off[r + 1] || R->cigar_off[r + 1] > R->cigar_nbytes)
+            return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone at record %u", r);
+        b->h_cigar_off[i + 1] = b->h_cigar_off[i] + (R->cigar_off[r + 1] - R->cigar_off[r]);
+    }
+    b->n_rec = n; b->n_names = R->n_names; b->n_bytes = b->h_cigar_off[n];
+    b->rec_base = sel.idx ? 0 : sel.r0; b->byte_base = 0;
     b->have_lift = b->have_stats = false;
     b->n_tiles = b->n_bytes / TOK_TILE + 1;
     b->ops_bound = b->n_bytes / 2 + 1;
@@ -474,7 +491,14 @@ static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t 
     CU(b->text_raw.ensure(TEXT_FRONT_PAD + padded));
     uint8_t* raw = b->text_raw.as<uint8_t>();
     CU(cudaMemsetAsync(raw, 0xFF, TEXT_FRONT_PAD, s));
-    if (b->n_bytes) CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD, R->cigar + byte0, b->n_bytes, cudaMemcpyHostToDevice, s));
+    for (uint32_t i = 0; i < n;) {
+        uint32_t j = i;
+        while (j + 1 < n && sel.at(j + 1) == sel.at(j) + 1) j++;
+        const uint64_t src0 = R->cigar_off[sel.at(i)], src1 = R->cigar_off[sel.at(j) + 1];
+        if (src1 > src0)
+            CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD + b->h_cigar_off[i], R->cigar + src0, src1 - src0, cudaMemcpyHostToDevice, s));
+        i = j + 1;
+    }
     CU(cudaMemsetAsync(raw + TEXT_FRONT_PAD + b->n_bytes, '0', padded - b->n_bytes, s));
     b->busy = true;
     return RB_OK;
@@ -574,16 +598,12 @@ static int upload_windows_end(rb_ctx* ctx, rb_batch* b, const rb_records* R, con
 }
 
 // records [r0, r1) of R: numeric columns, names, emission order (small)
-static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_t r0, uint32_t r1) {
+static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel sel) {
     cudaStream_t s = ctx->stream;
-    const uint32_t n = r1 - r0;
-    const uint64_t byte0 = n ? R->cigar_off[r0] : 0;
-    b->h_cigar_off.resize((size_t)n + 1);
-    b->h_cigar_off[0] = 0;
+    const uint32_t n = sel.n;
     for (uint32_t i = 0; i < n; i++) {
-        if (R->cigar_off[r0 + i] > R->cigar_off[r0 + i + 1]) return fail(ctx, RB_ERR_BAD_ARG, "cigar_off not monotone at record %u", r0 + i);
-        b->h_cigar_off[i + 1] = R->cigar_off[r0 + i + 1] - byte0;
-        if (R->q_id[r0 + i] >= R->n_names || R->t_id[r0 + i] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", r0 + i);
+        const uint32_t r = sel.at(i);
+        if (R->q_id[r] >= R->n_names || R->t_id[r] >= R->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", r);
     }
     CU(b->cigar_off.ensure((size_t)(n + 1) * 8));
     CU(b->cols64.ensure((size_t)n * 7 * 8 + 8));
@@ -609,12 +629,30 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_
 
     CU(cudaMemcpyAsync(b->cigar_off.p, b->h_cigar_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     const uint64_t* cols[7] = {R->q_len, R->q_st, R->q_en, R->t_len, R->t_st, R->t_en, R->mapq};
+    const uint8_t* h_strand = R->strand + sel.r0;
+    const uint32_t *h_qid = R->q_id + sel.r0, *h_tid = R->t_id + sel.r0;
+    b->h_orig.clear();
+    if (sel.idx) {  // gather the (small) numeric columns on the host
+        b->h_cols.resize((size_t)7 * n); b->h_strand.resize(n); b->h_qid.resize(n); b->h_tid.resize(n);
+        b->h_orig.assign(sel.idx, sel.idx + n);
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t r = sel.idx[i];
+            for (int k = 0; k < 7; k++) b->h_cols[(size_t)k * n + i] = cols[k][r];
+            b->h_strand[i] = R->strand[r]; b->h_qid[i] = R->q_id[r]; b->h_tid[i] = R->t_id[r];
+        }
+        for (int k = 0; k < 7; k++) cols[k] = b->h_cols.data() + (size_t)k * n;
+        h_strand = b->h_strand.data(); h_qid = b->h_qid.data(); h_tid = b->h_tid.data();
+        CU(b->orig_idx.ensure((size_t)n * 4 + 8));
+        if (n) CU(cudaMemcpyAsync(b->orig_idx.p, b->h_orig.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    } else {
+        for (int k = 0; k < 7; k++) cols[k] += sel.r0;
+    }
     for (int k = 0; k < 7 && n; k++)
-        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k] + r0, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k], (size_t)n * 8, cudaMemcpyHostToDevice, s));
     if (n) {
-        CU(cudaMemcpyAsync(b->strand.p, R->strand + r0, n, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), R->q_id + r0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, R->t_id + r0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->strand.p, h_strand, n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), h_qid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, h_tid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     }
     if (R->n_names) {
         CU(cudaMemcpyAsync(b->names_off.p, R->names_off, (size_t)(R->n_names + 1) * 8, cudaMemcpyHostToDevice, s));
@@ -628,7 +666,7 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_
         std::vector<uint32_t> cnt;
         std::vector<uint32_t> grp(n);
         for (uint32_t i = 0; i < n; i++) {
-            int64_t& f = first[R->t_id[r0 + i]];
+            int64_t& f = first[h_tid[i]];
             if (f < 0) { f = (int64_t)cnt.size(); cnt.push_back(0); }
             grp[i] = (uint32_t)f;
             cnt[grp[i]]++;
@@ -651,9 +689,10 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, uint32_
 }
 
 static int upload_into_impl(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
-    int rc = upload_cigar(ctx, b, R, 0, R ? R->n_rec : 0);  // validates R
+    const RecSel all{nullptr, 0, R ? R->n_rec : 0};
+    int rc = upload_cigar(ctx, b, R, all);  // validates R
     if (rc == RB_OK) rc = upload_windows_begin(ctx, b, R, W);
-    if (rc == RB_OK) rc = upload_columns(ctx, b, R, 0, R->n_rec);
+    if (rc == RB_OK) rc = upload_columns(ctx, b, R, all);
     if (rc == RB_OK) rc = upload_windows_end(ctx, b, R, W);
     return rc;
 }
@@ -844,7 +883,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                          b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                          (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
-                         b->byte_base, b->rec_base, s);
+                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), s);
     }
     if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
     if (trace) {
@@ -940,24 +979,35 @@ void rb_free_stats_out(rb_ctx*, rb_stats_out* st) {
 }
 
 // ---- rb_liftover in slices -----------------------------------------------------------------------
-// When the records already sit in emission order (the PAF is grouped by target, the usual case) a call is cut into
-// K runs of consecutive records of about equal CIGAR size.  Each slice goes upload -> kernels -> download on its own
+// A call is cut into K runs of records that are consecutive in EMISSION order, of about equal CIGAR size (when the PAF
+// is grouped by target these are plain runs of the caller's arrays; otherwise each slice is gathered run by run).  Each slice goes upload -> kernels -> download on its own
 // ping-pong work area, and the download of slice k (copy stream, device->host DMA engine) runs under the upload and
 // the kernels of slices k+1, k+2 (compute stream, host->device engine): PCIe is used in both directions at once and
 // the call approaches the time of its largest transfer instead of the sum of all three stages.  It also bounds the
 // HBM footprint of the intermediates by the slice size.  The rows land in one pinned block in emission order; the
 // window tables are uploaded once and shared by all slices.
-static bool records_in_emission_order(const rb_records* R, std::vector<uint8_t>& seen) {
-    seen.assign(R->n_names, 0);
-    uint32_t prev = UINT32_MAX;
-    for (uint32_t i = 0; i < R->n_rec; i++) {
+// Emission order of the records (liftover.rs:151-164): contigs by first appearance of t_name, file order inside.
+// Returns false for name ids out of range (reported properly by the unsliced path); `identity` = file order already.
+static bool emission_order(const rb_records* R, std::vector<uint32_t>& ord, bool& identity) {
+    const uint32_t n = R->n_rec;
+    std::vector<int64_t> first(R->n_names, -1);
+    std::vector<uint32_t> cnt, grp(n);
+    for (uint32_t i = 0; i < n; i++) {
         const uint32_t t = R->t_id[i];
-        if (t >= R->n_names) return false;  // reported properly by the unsliced path
-        if (t != prev) {
-            if (seen[t]) return false;
-            seen[t] = 1;
-            prev = t;
-        }
+        if (t >= R->n_names) return false;
+        int64_t& f = first[t];
+        if (f < 0) { f = (int64_t)cnt.size(); cnt.push_back(0); }
+        grp[i] = (uint32_t)f;
+        cnt[grp[i]]++;
+    }
+    std::vector<uint32_t> start(cnt.size() + 1, 0);
+    for (size_t g = 0; g < cnt.size(); g++) start[g + 1] = start[g] + cnt[g];
+    ord.resize(n);
+    identity = true;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t k = start[grp[i]]++;
+        ord[k] = i;
+        identity = identity && (k == i);
     }
     return true;
 }
@@ -967,8 +1017,9 @@ static int liftover_unsliced(rb_ctx* ctx, const rb_records* recs, const rb_windo
     rb_batch* b = ctx->scratch;
     int rc;
     if (windows_uploaded) {
-        rc = upload_cigar(ctx, b, recs, 0, recs->n_rec);
-        if (rc == RB_OK) rc = upload_columns(ctx, b, recs, 0, recs->n_rec);
+        const RecSel all{nullptr, 0, recs->n_rec};
+        rc = upload_cigar(ctx, b, recs, all);
+        if (rc == RB_OK) rc = upload_columns(ctx, b, recs, all);
         if (rc != RB_OK && b->busy) { cudaStreamSynchronize(ctx->stream); b->busy = false; }
     } else {
         rc = upload_into(ctx, b, recs, wins);
@@ -987,10 +1038,11 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     if (!ctx->scratch) ctx->scratch = new rb_batch();
     rb_batch* wb = ctx->scratch;
     const uint64_t SLICE_MIN_BYTES = ctx->slice_min_bytes;
-    std::vector<uint8_t> seen;
+    std::vector<uint32_t> ord;  // records in emission order
+    bool identity = true;
     const bool try_slices = SLICE_MIN_BYTES && !ctx->profiling && recs && wins && wins->n_win && recs->n_rec >= 2 && recs->cigar_off &&
                             recs->t_id && recs->t_st && recs->t_en && recs->cigar_nbytes >= 2 * SLICE_MIN_BYTES &&
-                            recs->cigar_off[recs->n_rec] == recs->cigar_nbytes && records_in_emission_order(recs, seen);
+                            recs->cigar_off[recs->n_rec] == recs->cigar_nbytes && emission_order(recs, ord, identity);
     if (!try_slices) return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
 
     const bool trace = getenv("RB_TRACE") != nullptr;
@@ -1029,11 +1081,16 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     const uint32_t n = recs->n_rec;
     const uint64_t total_bytes = recs->cigar_nbytes;
     const uint32_t K = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
-    std::vector<uint32_t> cut(1, 0);
-    for (uint32_t k = 1; k < K; k++) {
-        const uint64_t target = total_bytes / K * k;
-        const uint32_t r = (uint32_t)(std::lower_bound(recs->cigar_off, recs->cigar_off + n, target) - recs->cigar_off);
-        if (r > cut.back() && r < n) cut.push_back(r);
+    std::vector<uint32_t> cut(1, 0);  // slice k = records ord[cut[k] .. cut[k+1]) : consecutive in EMISSION order
+    {
+        uint64_t acc = 0;
+        uint32_t k = 1;
+        for (uint32_t i = 0; i < n && k < K; i++) {
+            const uint32_t r = ord[i];
+            if (recs->cigar_off[r + 1] < recs->cigar_off[r]) break;  // malformed offsets: reported by the upload
+            acc += recs->cigar_off[r + 1] - recs->cigar_off[r];
+            if (acc >= total_bytes / K * k && i + 1 < n) { cut.push_back(i + 1); k++; }
+        }
     }
     cut.push_back(n);
     const uint32_t n_slices = (uint32_t)cut.size() - 1;
@@ -1068,8 +1125,10 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     }
     auto upload_slice = [&](uint32_t k) {
         rb_batch* sb = ctx->slice[k & 1];
-        int r2 = upload_cigar(ctx, sb, recs, cut[k], cut[k + 1]);
-        if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, cut[k], cut[k + 1]);
+        // file order == emission order: a plain run of the caller's arrays; else the slice is gathered run by run
+        const RecSel sel{identity ? nullptr : ord.data() + cut[k], cut[k], cut[k + 1] - cut[k]};
+        int r2 = upload_cigar(ctx, sb, recs, sel);
+        if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, sel);
         sb->wsrc = wb;
         return r2;
     };
@@ -1100,7 +1159,7 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         CU(cudaEventRecord(ctx->ev_done[k & 1], A));
         TE("A kernels done", k, A);
         if (!blk) {  // sizes of the first slice are known: reserve the pinned output (text size extrapolated, rows bounded)
-            const uint64_t slice_bytes = recs->cigar_off[cut[1]] - recs->cigar_off[cut[0]];
+            const uint64_t slice_bytes = sb->n_bytes;
             const double scale = slice_bytes ? (double)total_bytes / (double)slice_bytes : 1.0;
             const size_t loff_bytes = (want & RB_WANT_TEXT) ? align_up((cap_rows + 1) * 8, 64) : 0;
             const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;

@@ -175,6 +175,25 @@ def test_full_scale_sliced_call_equals_unsliced(ctx, full):
     assert (d["t_st"] == a["t_st"]).all() and (d["stats"]["equal"] == a["stats"]["equal"]).all()
 
 
+def test_two_haplotypes_gathered_slices_equal_unsliced(ctx):
+    """A multi-haplotype PAF (file order: haplotype-major, so contigs interleave) is sliced in emission order with
+    gathered uploads; rows, rec_idx and counters equal the single-batch call."""
+    paf = hostlib.HostPaf.synth(scale=0.25, n_hap=3)
+    wins = paf.tiling_windows(10_000)
+    ctx.set_slicing(4 << 20)
+    try:
+        a = ctx.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+        ctx.set_slicing(0)
+        b = ctx.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    finally:
+        ctx.set_slicing()
+    assert a["n_out"] == b["n_out"] > 100_000 and a["paf_text"] == b["paf_text"]
+    for k in ("line_off", "q_st", "t_en", "rec_idx", "win_idx"):
+        assert (a[k] == b[k]).all(), k
+    assert (a["stats"]["equal"] == b["stats"]["equal"]).all()
+    assert (np.diff(a["rec_idx"].astype(np.int64)) < 0).any()  # emission order is not file order here
+
+
 def test_rb_cli_matches_oracle(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
