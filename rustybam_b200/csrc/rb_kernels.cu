@@ -1311,13 +1311,15 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             SerArgs a, const LiftPlan* __restrict__ plans, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
             const uint64_t* __restrict__ out_idx,
             uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
-            uint32_t rec_base, const uint32_t* __restrict__ orig_idx) {
+            uint32_t rec_base, const uint32_t* __restrict__ orig_idx, uint32_t group) {
+    // `group` = lines per block: SER_LINES normally; 8 when the rows are few and long (100 kb windows: a 4 KB line
+    // per pair), so that the warp-per-line path below spreads over 16x more blocks
     extern __shared__ __align__(16) uint8_t s_buf[];
     __shared__ uint8_t s_stage[SER_LINES / 32][384];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t p0 = (uint64_t)blockIdx.x * SER_LINES;
+    const uint64_t p0 = (uint64_t)blockIdx.x * group;
     const uint64_t p = p0 + tid;
-    const uint64_t pend = (p0 + SER_LINES < n_pairs) ? (p0 + SER_LINES) : n_pairs;
+    const uint64_t pend = (p0 + group < n_pairs) ? (p0 + group) : n_pairs;
     const uint64_t byte0 = line_off[p0], byte1 = line_off[pend];
     const uint64_t region = byte1 - byte0;
 
@@ -1325,14 +1327,14 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
     pr.kind = PK_DROP;
     uint64_t my_off = 0, my_len = 0;
     uint32_t r = 0, w = 0;
-    if (p < n_pairs) {
+    if (p < pend) {
         pr = res[p];
         my_off = line_off[p];
         my_len = line_off[p + 1] - my_off;
     }
     const bool live = (pr.kind != PK_DROP);
     static_assert(SER_LINES == LIFT_THREADS, "k_serialise reuses the per-block plan of k_lift");
-    const LiftPlan pl = plans[blockIdx.x];  // one record for the whole block (the usual case at scale): no per-thread search
+    const LiftPlan pl = plans[p0 / SER_LINES];  // one record for the whole block (the usual case at scale): no per-thread search
     const bool uniform = pl.uniform != 0;
     if (live) {
         const uint32_t k = uniform ? pl.k0 : rank_of_pair(pair_off, n_rec, p);
@@ -1347,7 +1349,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         }
         if (st.equal) write_stats(st, o, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
     }
-    if (out_line_off && p0 + SER_LINES >= n_pairs && tid == 0) out_line_off[out_idx[n_pairs]] = line_off[n_pairs] + byte_base;
+    if (out_line_off && p0 + group >= n_pairs && tid == 0) out_line_off[out_idx[n_pairs]] = line_off[n_pairs] + byte_base;
     if (out_text == nullptr || region == 0) return;
 
     const bool small = __syncthreads_and(my_len <= 2048) && region <= (uint64_t)(SER_CAP - 16);
@@ -1522,7 +1524,7 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
-                      cudaStream_t s) {
+                      uint32_t group, cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1532,8 +1534,9 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     OpsView view;
     view.ops = ops; view.samples = nullptr;
     SerArgs a{recs, view, win, names_off, names, text};
-    k_serialise<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, SER_CAP, s>>>(
-        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx);
+    if (group == 0 || group > (uint32_t)SER_LINES || (SER_LINES % group)) group = SER_LINES;
+    k_serialise<<<(unsigned)((n_pairs + group - 1) / group), SER_LINES, SER_CAP, s>>>(
+        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx, group);
 }
 // Device scalars -> mapped pinned host memory with plain SM stores: the host reads them after a stream sync.  (A
 // cudaMemcpyAsync would queue on the device->host DMA engine behind the bulk download of the previous slice.)

@@ -36,6 +36,23 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// small pinned staging area owned by a batch: the record columns are gathered here on the host and leave by
+// asynchronous DMA (the caller's column arrays may share pages with a buffer it page-locked, which the driver rejects)
+struct PinBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4 + 4096;
+        const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct PinnedBlock {
     void* p = nullptr;
     size_t cap = 0;
@@ -63,6 +80,9 @@ struct rb_ctx {
     rb_batch* scratch = nullptr;  // reused by rb_liftover / rb_stats
     rb_batch* slice[2] = {nullptr, nullptr};  // ping-pong work areas of the sliced rb_liftover
     cudaStream_t copy_stream = nullptr;        // device -> host copies of finished slices
+    cudaStream_t up_stream = nullptr;          // host -> device copies of the next slice
+    cudaStream_t upload_on = nullptr;          // stream upload_cigar / upload_columns enqueue on (nullptr: `stream`)
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     cudaEvent_t ev_win = nullptr;
     uint64_t slice_min_bytes = 16ull << 20;  // rb_ctx_set_slicing (0 = off)
@@ -77,9 +97,9 @@ struct rb_batch {
     bool general = false;  // BED rows not (sorted, monotone `en`, file order == sorted order): brute-force join
     std::vector<uint64_t> h_cigar_off;
     // host staging of the asynchronous uploads (must stay alive until the stream has consumed it)
-    std::vector<uint32_t> h_order, h_rank, h_clo, h_chi, h_orig, h_qid, h_tid;
-    std::vector<uint64_t> h_cols;
-    std::vector<uint8_t> h_strand;
+    std::vector<uint32_t> h_clo, h_chi, h_orig;
+    PinBuf stage;   // pinned copies of the record columns
+    PinBuf wstage;  // pinned copies of the contig ranges of the window table
     struct { std::vector<uint64_t> st, en, off; std::vector<uint32_t> row; std::vector<uint8_t> ids; } h_gen;
     bool busy = false;         // uploads of this batch may still be in flight
     bool win_pending = false;  // the window check kernel's verdict has not been read yet
@@ -370,6 +390,8 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
                      &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
+    b->stage.release();
+    b->wstage.release();
     delete b;
 }
 
@@ -378,6 +400,7 @@ void rb_ctx_destroy(rb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->up_stream) cudaStreamSynchronize(ctx->up_stream);
     if (ctx->scratch) rb_batch_free(ctx, ctx->scratch);
     for (int k = 0; k < 2; k++) {
         if (ctx->slice[k]) rb_batch_free(ctx, ctx->slice[k]);
@@ -385,6 +408,8 @@ void rb_ctx_destroy(rb_ctx* ctx) {
         if (ctx->ev_d2h[k]) cudaEventDestroy(ctx->ev_d2h[k]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
+    for (int k = 0; k < 2; k++) if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
     if (ctx->ev_win) cudaEventDestroy(ctx->ev_win);
     for (PinnedBlock* b : ctx->pinned) { cudaFreeHost(b->p); delete b; }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -464,7 +489,7 @@ struct RecSel {
 };
 
 static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel sel) {
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->upload_on ? ctx->upload_on : ctx->stream;
     if (!R || (R->n_rec && (!R->cigar_off || !R->q_len || !R->q_st || !R->q_en || !R->t_len || !R->t_st || !R->t_en || !R->mapq ||
                             !R->strand || !R->q_id || !R->t_id || !R->names_off)) ||
         (R->cigar_nbytes && !R->cigar))
@@ -548,8 +573,12 @@ static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, c
             i = j > i ? j : i + 1;
         }
     }
-    CU(cudaMemcpyAsync(b->cont_lo.p, b->h_clo.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->cont_hi.p, b->h_chi.data(), (size_t)(R->n_names + 1) * 4, cudaMemcpyHostToDevice, s));
+    const size_t cbytes = (size_t)(R->n_names + 1) * 4;
+    CU(b->wstage.ensure(2 * cbytes));
+    memcpy(b->wstage.p, b->h_clo.data(), cbytes);
+    memcpy(b->wstage.p + cbytes, b->h_chi.data(), cbytes);
+    CU(cudaMemcpyAsync(b->cont_lo.p, b->wstage.p, cbytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->cont_hi.p, b->wstage.p + cbytes, cbytes, cudaMemcpyHostToDevice, s));
     return RB_OK;
 }
 
@@ -599,7 +628,7 @@ static int upload_windows_end(rb_ctx* ctx, rb_batch* b, const rb_records* R, con
 
 // records [r0, r1) of R: numeric columns, names, emission order (small)
 static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel sel) {
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->upload_on ? ctx->upload_on : ctx->stream;
     const uint32_t n = sel.n;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t r = sel.at(i);
@@ -627,40 +656,57 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel 
     CU(b->pair_cnt.ensure((size_t)n * 4 + 8));
     CU(b->pair_off.ensure((size_t)(n + 1) * 8));
 
-    CU(cudaMemcpyAsync(b->cigar_off.p, b->h_cigar_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+    // gather every small column into the batch's pinned staging area, then one asynchronous copy each
     const uint64_t* cols[7] = {R->q_len, R->q_st, R->q_en, R->t_len, R->t_st, R->t_en, R->mapq};
-    const uint8_t* h_strand = R->strand + sel.r0;
-    const uint32_t *h_qid = R->q_id + sel.r0, *h_tid = R->t_id + sel.r0;
+    const size_t nn = R->n_names;
+    const size_t o_off = 0, o_cols = o_off + align_up((size_t)(n + 1) * 8, 64), o_qid = o_cols + align_up((size_t)n * 7 * 8, 64),
+                 o_tid = o_qid + align_up((size_t)n * 4, 64), o_strand = o_tid + align_up((size_t)n * 4, 64),
+                 o_noff = o_strand + align_up((size_t)n, 64), o_names = o_noff + align_up((nn + 1) * 8, 64),
+                 o_order = o_names + align_up(names_bytes + 1, 64), o_rank = o_order + align_up((size_t)n * 4, 64),
+                 o_orig = o_rank + align_up((size_t)n * 4, 64), o_end = o_orig + align_up((size_t)n * 4, 64);
+    CU(b->stage.ensure(o_end));
+    uint8_t* sp = b->stage.p;
+    uint64_t* s_off = reinterpret_cast<uint64_t*>(sp + o_off);
+    uint64_t* s_cols = reinterpret_cast<uint64_t*>(sp + o_cols);
+    uint32_t* s_qid = reinterpret_cast<uint32_t*>(sp + o_qid);
+    uint32_t* s_tid = reinterpret_cast<uint32_t*>(sp + o_tid);
+    uint8_t* s_strand = sp + o_strand;
+    uint32_t* s_orig = reinterpret_cast<uint32_t*>(sp + o_orig);
+    memcpy(s_off, b->h_cigar_off.data(), (size_t)(n + 1) * 8);
     b->h_orig.clear();
-    if (sel.idx) {  // gather the (small) numeric columns on the host
-        b->h_cols.resize((size_t)7 * n); b->h_strand.resize(n); b->h_qid.resize(n); b->h_tid.resize(n);
+    if (sel.idx) {
         b->h_orig.assign(sel.idx, sel.idx + n);
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t r = sel.idx[i];
-            for (int k = 0; k < 7; k++) b->h_cols[(size_t)k * n + i] = cols[k][r];
-            b->h_strand[i] = R->strand[r]; b->h_qid[i] = R->q_id[r]; b->h_tid[i] = R->t_id[r];
+            for (int k = 0; k < 7; k++) s_cols[(size_t)k * n + i] = cols[k][r];
+            s_strand[i] = R->strand[r]; s_qid[i] = R->q_id[r]; s_tid[i] = R->t_id[r]; s_orig[i] = r;
         }
-        for (int k = 0; k < 7; k++) cols[k] = b->h_cols.data() + (size_t)k * n;
-        h_strand = b->h_strand.data(); h_qid = b->h_qid.data(); h_tid = b->h_tid.data();
         CU(b->orig_idx.ensure((size_t)n * 4 + 8));
-        if (n) CU(cudaMemcpyAsync(b->orig_idx.p, b->h_orig.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-    } else {
-        for (int k = 0; k < 7; k++) cols[k] += sel.r0;
+        if (n) CU(cudaMemcpyAsync(b->orig_idx.p, s_orig, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    } else if (n) {
+        for (int k = 0; k < 7; k++) memcpy(s_cols + (size_t)k * n, cols[k] + sel.r0, (size_t)n * 8);
+        memcpy(s_strand, R->strand + sel.r0, n);
+        memcpy(s_qid, R->q_id + sel.r0, (size_t)n * 4);
+        memcpy(s_tid, R->t_id + sel.r0, (size_t)n * 4);
     }
-    for (int k = 0; k < 7 && n; k++)
-        CU(cudaMemcpyAsync(b->cols64.as<uint64_t>() + (size_t)k * n, cols[k], (size_t)n * 8, cudaMemcpyHostToDevice, s));
+    const uint32_t* h_tid = s_tid;
+    CU(cudaMemcpyAsync(b->cigar_off.p, s_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
     if (n) {
-        CU(cudaMemcpyAsync(b->strand.p, h_strand, n, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), h_qid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, h_tid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->cols64.p, s_cols, (size_t)n * 7 * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->strand.p, s_strand, n, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>(), s_qid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->ids32.as<uint32_t>() + n, s_tid, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     }
-    if (R->n_names) {
-        CU(cudaMemcpyAsync(b->names_off.p, R->names_off, (size_t)(R->n_names + 1) * 8, cudaMemcpyHostToDevice, s));
-        if (names_bytes) CU(cudaMemcpyAsync(b->names.p, R->names, names_bytes, cudaMemcpyHostToDevice, s));
+    if (nn) {
+        memcpy(sp + o_noff, R->names_off, (nn + 1) * 8);
+        if (names_bytes) memcpy(sp + o_names, R->names, names_bytes);
+        CU(cudaMemcpyAsync(b->names_off.p, sp + o_noff, (nn + 1) * 8, cudaMemcpyHostToDevice, s));
+        if (names_bytes) CU(cudaMemcpyAsync(b->names.p, sp + o_names, names_bytes, cudaMemcpyHostToDevice, s));
     }
+    uint32_t* s_order = reinterpret_cast<uint32_t*>(sp + o_order);
+    uint32_t* s_rank = reinterpret_cast<uint32_t*>(sp + o_rank);
 
     // emission order (liftover.rs:151-164): contigs by first appearance of t_name, records in file order inside
-    b->h_order.resize(n); b->h_rank.resize(n);
     {
         std::vector<int64_t> first(R->n_names, -1);
         std::vector<uint32_t> cnt;
@@ -675,13 +721,13 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel 
         for (size_t g = 0; g < cnt.size(); g++) start[g + 1] = start[g] + cnt[g];
         for (uint32_t i = 0; i < n; i++) {
             const uint32_t k = start[grp[i]]++;
-            b->h_order[k] = i;
-            b->h_rank[i] = k;
+            s_order[k] = i;
+            s_rank[i] = k;
         }
     }
     if (n) {
-        CU(cudaMemcpyAsync(b->rec_order.p, b->h_order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(b->rec_rank.p, b->h_rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->rec_order.p, s_order, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CU(cudaMemcpyAsync(b->rec_rank.p, s_rank, (size_t)n * 4, cudaMemcpyHostToDevice, s));
     }
     b->sum = rb_summary{};
     b->sum.cigar_bytes = b->n_bytes;
@@ -875,6 +921,9 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     if (want & RB_WANT_NUMERIC) CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
     b->with_stats = with_stats != 0;
     if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
+    // few, long rows (e.g. 100 kb windows: ~4 KB per row): 8 rows per block instead of 128, so the warp-per-line path
+    // has enough blocks to fill the GPU
+    const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? 8u : (uint32_t)SER_LINES;
     {
         KScope k(ctx, "k_serialise");
         launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
@@ -883,7 +932,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                          b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                          (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
-                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), s);
+                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, s);
     }
     if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
     if (trace) {
@@ -1063,12 +1112,14 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     cudaStream_t A = ctx->stream;
     if (!ctx->copy_stream) {
         CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
         for (int k = 0; k < 2; k++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
         }
     }
-    cudaStream_t B = ctx->copy_stream;
+    cudaStream_t B = ctx->copy_stream, U = ctx->up_stream;
     if (wb->busy) { CU(cudaStreamSynchronize(A)); wb->busy = false; }
     wb->n_rec = 0; wb->have_lift = wb->have_stats = false;
     TE("A start", 0, A);
@@ -1110,6 +1161,8 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     size_t o_text = 64, o_loff = 0, o_num = 0, cap_text = 0;
     uint64_t byte_base = 0, row_base = 0, pairs = 0;
     auto bail = [&](int code) {
+        ctx->upload_on = nullptr;
+        cudaStreamSynchronize(U);
         cudaStreamSynchronize(A);
         cudaStreamSynchronize(B);
         for (int k = 0; k < 2; k++)
@@ -1127,9 +1180,15 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         rb_batch* sb = ctx->slice[k & 1];
         // file order == emission order: a plain run of the caller's arrays; else the slice is gathered run by run
         const RecSel sel{identity ? nullptr : ord.data() + cut[k], cut[k], cut[k + 1] - cut[k]};
+        // on the upload stream, so that the copy runs beside the kernels of the previous slice; the work area's own
+        // previous kernels (slice k-2) must have finished reading its inputs
+        if (k >= 2 && cudaStreamWaitEvent(U, ctx->ev_done[k & 1], 0) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamWaitEvent");
+        ctx->upload_on = U;
         int r2 = upload_cigar(ctx, sb, recs, sel);
         if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, sel);
+        ctx->upload_on = nullptr;
         sb->wsrc = wb;
+        if (r2 == RB_OK && cudaEventRecord(ctx->ev_up[k & 1], U) != cudaSuccess) r2 = fail(ctx, RB_ERR_CUDA, "cudaEventRecord");
         return r2;
     };
     rc = upload_slice(0);
@@ -1148,7 +1207,8 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
             if (rc != RB_OK) return bail(rc);
         }
         T("next upload enqueued", k);
-        TE("A next slice uploaded", k, A);
+        TE("U next slice uploaded", k, U);
+        CU(cudaStreamWaitEvent(A, ctx->ev_up[k & 1], 0));                // this slice's inputs have arrived
         if (k >= 2) CU(cudaStreamWaitEvent(A, ctx->ev_d2h[k & 1], 0));  // this work area's previous rows have left the device
         TE("A kernels may start", k, A);
         sb->byte_base = byte_base;
@@ -1165,7 +1225,7 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
             const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;
             size_t text_est = 0;
             if (want & RB_WANT_TEXT) {
-                text_est = (size_t)((double)sm.out_bytes * scale * 1.08) + (1u << 20);
+                text_est = (size_t)((double)sm.out_bytes * scale * 1.25) + (4u << 20);  // slices differ in their rows-per-byte mix
                 if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + (1u << 20);  // nothing to extrapolate from
             }
             const size_t need = 64 + align_up(text_est + 1, 64) + loff_bytes + num_bytes;
