@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -145,6 +146,21 @@ int fail(rb_ctx* c, int code, const char* fmt, ...) {
     } while (0)
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// host -> device copy of a caller buffer, cut at absolute 1 GiB-aligned source addresses (see rb_host_register)
+cudaError_t h2d_copy(void* dst, const void* src, size_t n, cudaStream_t s) {
+    const uint64_t G = 1ull << 30;
+    uint64_t a = reinterpret_cast<uintptr_t>(src);
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    while (n) {
+        const uint64_t e = (a / G + 1) * G;
+        const size_t len = (size_t)std::min<uint64_t>(n, e - a);
+        const cudaError_t rc = cudaMemcpyAsync(d, reinterpret_cast<const void*>(a), len, cudaMemcpyHostToDevice, s);
+        if (rc != cudaSuccess) return rc;
+        a += len; d += len; n -= len;
+    }
+    return cudaSuccess;
+}
 
 PinnedBlock* pinned_get(rb_ctx* ctx, size_t n) {
     PinnedBlock* best = nullptr;
@@ -338,15 +354,46 @@ extern "C" {
 
 const char* rb_version(void) { return "rbcuda 0.1 (sm_100a)"; }
 
+// Page-locks [ptr, ptr + nbytes) in pieces of <= 1 GiB (a single cudaHostRegister of tens of GB can fail where the
+// pieces succeed); rb_host_unregister undoes all pieces of that call.
+static constexpr uint64_t REG_PIECE = 1ull << 30;
+static std::mutex g_reg_mu;
+static std::vector<std::pair<void*, std::vector<void*>>> g_reg;  // base pointer -> registered pieces
+
 int rb_host_register(void* ptr, uint64_t nbytes) {
     if (!ptr || !nbytes) return RB_ERR_BAD_ARG;
-    if (cudaHostRegister(ptr, nbytes, cudaHostRegisterDefault) != cudaSuccess) { (void)cudaGetLastError(); return RB_ERR_CUDA; }
+    // pieces are cut at absolute 1 GiB-aligned addresses: no page is registered twice, and h2d_copy() below cuts its
+    // transfers at the same addresses (one copy must not span two registrations)
+    std::vector<void*> done;
+    const uint64_t a0 = reinterpret_cast<uintptr_t>(ptr), a1 = a0 + nbytes;
+    for (uint64_t a = a0; a < a1;) {
+        uint64_t e = (a / REG_PIECE + 1) * REG_PIECE;
+        if (e > a1) e = a1;
+        if (cudaHostRegister(reinterpret_cast<void*>(a), e - a, cudaHostRegisterDefault) != cudaSuccess) {
+            (void)cudaGetLastError();
+            for (void* q : done) cudaHostUnregister(q);
+            return RB_ERR_CUDA;
+        }
+        done.push_back(reinterpret_cast<void*>(a));
+        a = e;
+    }
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    g_reg.emplace_back(ptr, std::move(done));
     return RB_OK;
 }
 int rb_host_unregister(void* ptr) {
     if (!ptr) return RB_ERR_BAD_ARG;
-    if (cudaHostUnregister(ptr) != cudaSuccess) { (void)cudaGetLastError(); return RB_ERR_CUDA; }
-    return RB_OK;
+    std::vector<void*> pieces;
+    {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        for (size_t i = 0; i < g_reg.size(); i++)
+            if (g_reg[i].first == ptr) { pieces = std::move(g_reg[i].second); g_reg.erase(g_reg.begin() + (long)i); break; }
+    }
+    if (pieces.empty()) return RB_ERR_BAD_ARG;
+    int rc = RB_OK;
+    for (void* q : pieces)
+        if (cudaHostUnregister(q) != cudaSuccess) { (void)cudaGetLastError(); rc = RB_ERR_CUDA; }
+    return rc;
 }
 
 rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
@@ -521,7 +568,7 @@ static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel se
         while (j + 1 < n && sel.at(j + 1) == sel.at(j) + 1) j++;
         const uint64_t src0 = R->cigar_off[sel.at(i)], src1 = R->cigar_off[sel.at(j) + 1];
         if (src1 > src0)
-            CU(cudaMemcpyAsync(raw + TEXT_FRONT_PAD + b->h_cigar_off[i], R->cigar + src0, src1 - src0, cudaMemcpyHostToDevice, s));
+            CU(h2d_copy(raw + TEXT_FRONT_PAD + b->h_cigar_off[i], R->cigar + src0, src1 - src0, s));
         i = j + 1;
     }
     CU(cudaMemsetAsync(raw + TEXT_FRONT_PAD + b->n_bytes, '0', padded - b->n_bytes, s));
@@ -543,10 +590,10 @@ static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, c
     CU(b->w_st.ensure((size_t)nw * 8)); CU(b->w_en.ensure((size_t)nw * 8)); CU(b->w_bed_row.ensure((size_t)nw * 4));
     CU(b->w_tid.ensure((size_t)nw * 4));
     CU(b->cont_lo.ensure((size_t)(R->n_names + 1) * 4)); CU(b->cont_hi.ensure((size_t)(R->n_names + 1) * 4));
-    CU(cudaMemcpyAsync(b->w_tid.p, W->t_id, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->w_st.p, W->st, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->w_en.p, W->en, (size_t)nw * 8, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->w_bed_row.p, W->bed_row, (size_t)nw * 4, cudaMemcpyHostToDevice, s));
+    CU(h2d_copy(b->w_tid.p, W->t_id, (size_t)nw * 4, s));
+    CU(h2d_copy(b->w_st.p, W->st, (size_t)nw * 8, s));
+    CU(h2d_copy(b->w_en.p, W->en, (size_t)nw * 8, s));
+    CU(h2d_copy(b->w_bed_row.p, W->bed_row, (size_t)nw * 4, s));
     b->busy = true;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     CU(cudaMemsetAsync(sc + SC_WINFLAGS, 0, 4, s));
@@ -558,8 +605,8 @@ static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, c
     if (!b->default_ids) {
         const uint64_t ids_bytes = W->ids_off[nw];
         CU(b->w_ids_off.ensure((size_t)(nw + 1) * 8)); CU(b->w_ids.ensure(ids_bytes + 8));
-        CU(cudaMemcpyAsync(b->w_ids_off.p, W->ids_off, (size_t)(nw + 1) * 8, cudaMemcpyHostToDevice, s));
-        if (ids_bytes) CU(cudaMemcpyAsync(b->w_ids.p, W->ids, ids_bytes, cudaMemcpyHostToDevice, s));
+        CU(h2d_copy(b->w_ids_off.p, W->ids_off, (size_t)(nw + 1) * 8, s));
+        if (ids_bytes) CU(h2d_copy(b->w_ids.p, W->ids, ids_bytes, s));
     }
     // contig ranges: t_id is sorted (verified on the device; an unsorted table only yields ranges nobody will use)
     b->h_clo.assign(R->n_names + 1, 0); b->h_chi.assign(R->n_names + 1, 0);
