@@ -368,11 +368,18 @@ RB_HD uint32_t combine_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, u
     return LIFT_OK;
 }
 
-// Bytes of the printed PAF line (paf.rs:923-943), '\n' included.
+// Bytes of the printed PAF line (paf.rs:923-943), '\n' included = a part that depends on the record only ...
+RB_HD uint32_t line_const_bytes(const RecInfo& r, uint32_t q_name_len, uint32_t t_name_len) {
+    return q_name_len + t_name_len + ndigits64(r.q_len) + 1 /*strand*/ + ndigits64(r.t_len) + ndigits64(r.mapq) +
+           11 /*tabs between the 12 columns*/ + 6 /*\tid:Z:*/ + 6 /*\tcg:Z:*/ + 1 /*\n*/;
+}
+// ... plus the lifted coordinates, nmatch / aln_len, the id and the CIGAR
+RB_HD uint32_t line_var_bytes(const PairRes& p, uint32_t id_len) {
+    return id_len + ndigits64(p.q_st) + ndigits64(p.q_en) + ndigits64(p.t_st) + ndigits64(p.t_en) + ndigits32(p.nmatch) +
+           ndigits32(p.aln_len) + p.cg_bytes;
+}
 RB_HD uint32_t line_bytes(const RecInfo& r, const PairRes& p, uint32_t q_name_len, uint32_t t_name_len, uint32_t id_len) {
-    return q_name_len + t_name_len + id_len + ndigits64(r.q_len) + ndigits64(p.q_st) + ndigits64(p.q_en) + 1 /*strand*/ +
-           ndigits64(r.t_len) + ndigits64(p.t_st) + ndigits64(p.t_en) + ndigits32(p.nmatch) + ndigits32(p.aln_len) +
-           ndigits64(r.mapq) + 11 /*tabs between the 12 columns*/ + 6 /*\tid:Z:*/ + 6 /*\tcg:Z:*/ + p.cg_bytes + 1 /*\n*/;
+    return line_const_bytes(r, q_name_len, t_name_len) + line_var_bytes(p, id_len);
 }
 
 }  // namespace rb

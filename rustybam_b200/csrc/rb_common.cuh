@@ -232,7 +232,8 @@ struct RecInfo {
     uint32_t wlo, whi;   // overlapping window range in the contig-sorted window arrays
     uint32_t lead_txt;   // canonical text bytes of the stripped leading ops (text offset of op eo0 inside the CIGAR)
     uint64_t text_off;   // byte offset of the record's CIGAR in the device text buffer
-    uint64_t pad2;
+    uint32_t line_const; // bytes of a printed row that depend on the record only (names, q_len, t_len, mapq, separators)
+    uint32_t pad2;
 };
 
 // One (window, record) pair after lift: everything the serialiser and the numeric mirror need.

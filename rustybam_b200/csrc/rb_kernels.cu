@@ -482,11 +482,22 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
     if (op0 >= n_ops && !(n_ops == 0 && b == 0)) return;  // blocks past the end have no successors
 
     // coalesced load, transposed into a 33-word pitch so that thread t owns s_ops[t*33 .. t*33+31]
+    if (op0 + SMP_OPS <= n_ops) {  // full block: 16-byte loads (op0 is a multiple of 8192 -> aligned), 4 ops per thread per step
+        const uint4* src = reinterpret_cast<const uint4*>(ops + op0);
+#pragma unroll
+        for (int i = 0; i < (int)SAMPLE / 4; i++) {
+            const uint32_t v4 = (uint32_t)i * SMP_THREADS + tid;  // vector index; ops 4*v4 .. 4*v4+3 lie in one chunk
+            const uint4 x = src[v4];
+            uint32_t* d = s_ops + (v4 >> (SAMPLE_LOG2 - 2)) * (SAMPLE + 1) + ((v4 << 2) & (SAMPLE - 1));
+            d[0] = x.x; d[1] = x.y; d[2] = x.z; d[3] = x.w;
+        }
+    } else {
 #pragma unroll 8
-    for (int i = 0; i < (int)SAMPLE; i++) {
-        const uint32_t idx = (uint32_t)i * SMP_THREADS + tid;
-        const uint64_t g = op0 + idx;
-        s_ops[(idx >> SAMPLE_LOG2) * (SAMPLE + 1) + (idx & (SAMPLE - 1))] = (g < n_ops) ? ops[g] : 0u;
+        for (int i = 0; i < (int)SAMPLE; i++) {
+            const uint32_t idx = (uint32_t)i * SMP_THREADS + tid;
+            const uint64_t g = op0 + idx;
+            s_ops[(idx >> SAMPLE_LOG2) * (SAMPLE + 1) + (idx & (SAMPLE - 1))] = (g < n_ops) ? ops[g] : 0u;
+        }
     }
     if (LIFT && tid == 32) {  // record that holds the block's first op (largest r with op_off[r] <= op0), off the critical path
         uint32_t lo = 0, hi = la.n_rec;
@@ -726,6 +737,8 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
         ri.flags = (in.strand[r] == '-') ? RF_MINUS : 0u;
         ri.a_lead = 0; ri.n_lead = 0; ri.n_trail = 0; ri.id_len = 0; ri.wlo = 0; ri.whi = 0; ri.lead_txt = 0;
         ri.text_off = in.cigar_off[r]; ri.pad2 = 0;
+        ri.line_const = line_const_bytes(ri, (uint32_t)(in.names_off[ri.q_name + 1] - in.names_off[ri.q_name]),
+                                         (uint32_t)(in.names_off[ri.t_name + 1] - in.names_off[ri.t_name]));
         ri.tot = ctr_zero();
     }
 
@@ -1007,10 +1020,12 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     __syncwarp();
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
-        const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
-        const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
-        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : win_id_len(win, w, tn, w_st, w_en);
-        len = line_bytes(ri, pr, qn, tn, idl);
+        uint32_t idl = ri.id_len;
+        if (pr.kind != PK_EARLY) {
+            const uint32_t tn = win.ids_off ? 0u : (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
+            idl = win_id_len(win, w, tn, w_st, w_en);
+        }
+        len = ri.line_const + line_var_bytes(pr, idl);
     }
     res[p] = pr;
     line_len[p] = len;
@@ -1046,10 +1061,12 @@ k_combine(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_
     const uint32_t e = combine_pair(v, ri, w_st, w_en, a, b, pr);
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
-        const uint32_t qn = (uint32_t)(names_off[ri.q_name + 1] - names_off[ri.q_name]);
-        const uint32_t tn = (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
-        const uint32_t idl = (pr.kind == PK_EARLY) ? ri.id_len : win_id_len(win, w, tn, w_st, w_en);
-        len = line_bytes(ri, pr, qn, tn, idl);
+        uint32_t idl = ri.id_len;
+        if (pr.kind != PK_EARLY) {
+            const uint32_t tn = win.ids_off ? 0u : (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
+            idl = win_id_len(win, w, tn, w_st, w_en);
+        }
+        len = ri.line_const + line_var_bytes(pr, idl);
     }
     res[p] = pr;
     line_len[p] = len;
@@ -1107,7 +1124,7 @@ __device__ __forceinline__ ulonglong2 lookback_2u64(uint32_t* state, ulonglong2*
     return acc;
 }
 
-constexpr int LNS_ITEMS = 4;  // items per thread
+constexpr int LNS_ITEMS = 16;  // items per thread (4096 per block: four times fewer look-backs than 4)
 __global__ void __launch_bounds__(LNS_THREADS)
 k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t* __restrict__ line_off, uint64_t* __restrict__ out_idx,
              uint32_t* blk_state, ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket) {

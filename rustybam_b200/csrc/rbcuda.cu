@@ -1219,6 +1219,14 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         if (sblk) sblk->in_use = false;
         return code;
     };
+#define CUB(call)                                                                                          \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) {                                                                           \
+            (void)cudaGetLastError();                                                                      \
+            return bail(fail(ctx, e_ == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_))); \
+        }                                                                                                  \
+    } while (0)
     for (int k = 0; k < 2; k++) {
         if (!ctx->slice[k]) ctx->slice[k] = new rb_batch();
         ctx->slice[k]->wsrc = wb;
@@ -1255,15 +1263,15 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         }
         T("next upload enqueued", k);
         TE("U next slice uploaded", k, U);
-        CU(cudaStreamWaitEvent(A, ctx->ev_up[k & 1], 0));                // this slice's inputs have arrived
-        if (k >= 2) CU(cudaStreamWaitEvent(A, ctx->ev_d2h[k & 1], 0));  // this work area's previous rows have left the device
+        CUB(cudaStreamWaitEvent(A, ctx->ev_up[k & 1], 0));                // this slice's inputs have arrived
+        if (k >= 2) CUB(cudaStreamWaitEvent(A, ctx->ev_d2h[k & 1], 0));  // this work area's previous rows have left the device
         TE("A kernels may start", k, A);
         sb->byte_base = byte_base;
         rb_summary sm{};
         rc = rb_batch_liftover(ctx, sb, policy, want, stats != nullptr, &sm);
         if (rc != RB_OK) return bail(rc);
         T("kernels enqueued (sizes known)", k);
-        CU(cudaEventRecord(ctx->ev_done[k & 1], A));
+        CUB(cudaEventRecord(ctx->ev_done[k & 1], A));
         TE("A kernels done", k, A);
         if (!blk) {  // sizes of the first slice are known: reserve the pinned output (text size extrapolated, rows bounded)
             const uint64_t slice_bytes = sb->n_bytes;
@@ -1272,8 +1280,8 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
             const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;
             size_t text_est = 0;
             if (want & RB_WANT_TEXT) {
-                text_est = (size_t)((double)sm.out_bytes * scale * 1.25) + (4u << 20);  // slices differ in their rows-per-byte mix
-                if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + (1u << 20);  // nothing to extrapolate from
+                text_est = (size_t)((double)sm.out_bytes * scale * 1.25) + (size_t)std::min<uint64_t>(4u << 20, total_bytes / 4 + 4096);  // slices differ in their rows-per-byte mix
+                if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + 4096;  // nothing to extrapolate from
             }
             const size_t need = 64 + align_up(text_est + 1, 64) + loff_bytes + num_bytes;
             blk = pinned_get(ctx, need);
@@ -1297,33 +1305,34 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         }
         if (row_base + sm.n_out > cap_rows) return bail(fail(ctx, RB_ERR_CUDA, "internal: row bound exceeded"));
         // ---- device -> host of this slice on the copy stream ----
-        CU(cudaStreamWaitEvent(B, ctx->ev_done[k & 1], 0));
+        CUB(cudaStreamWaitEvent(B, ctx->ev_done[k & 1], 0));
         TE("B download starts", k, B);
         const uint64_t nk = sm.n_out;
         if (want & RB_WANT_TEXT) {
-            if (sm.out_bytes) CU(cudaMemcpyAsync(base + o_text + byte_base, sb->out_text.p, sm.out_bytes, cudaMemcpyDeviceToHost, B));
-            if (nk) CU(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + o_loff) + row_base, sb->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, B));
+            if (sm.out_bytes) CUB(cudaMemcpyAsync(base + o_text + byte_base, sb->out_text.p, sm.out_bytes, cudaMemcpyDeviceToHost, B));
+            if (nk) CUB(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + o_loff) + row_base, sb->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, B));
         }
         if ((want & RB_WANT_NUMERIC) && nk) {
             uint64_t* d = reinterpret_cast<uint64_t*>(base + o_num);
             const uint64_t* sp = sb->out_num.as<uint64_t>();
             // one strided copy per table: columns are nk rows apart on the device and cap_rows apart in the pinned block
-            CU(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, nk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
+            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, nk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
             uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 6 * cap_rows);
             const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * nk);
-            CU(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, nk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
+            CUB(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, nk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
         }
         if (stats && nk) {
             uint32_t* d = reinterpret_cast<uint32_t*>(sblk->p);
             const uint32_t* sp = sb->out_stats.as<uint32_t>();
-            CU(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, nk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
+            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, nk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
         }
-        CU(cudaEventRecord(ctx->ev_d2h[k & 1], B));
+        CUB(cudaEventRecord(ctx->ev_d2h[k & 1], B));
         TE("B download done", k, B);
         byte_base += sm.out_bytes; row_base += nk; pairs += sm.n_pairs;
     }
     T("all slices enqueued", n_slices);
-    CU(cudaStreamSynchronize(B));
+    CUB(cudaStreamSynchronize(B));
+#undef CUB
     T("copy stream drained", n_slices);
     for (size_t i = 0; i < tev.size(); i++) {
         float ms = 0;

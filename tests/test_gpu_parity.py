@@ -153,6 +153,26 @@ def test_random_sliced_calls(ctx, seed):
         ctx.set_slicing()
 
 
+def test_sliced_call_restarts_when_the_text_estimate_is_too_small(capfd, monkeypatch):
+    # the pinned text buffer of a sliced call is sized from the first slice; here the first slice yields one short row
+    # and the later ones whole records, so the estimate is far too small and the call must restart as a single batch
+    paf_text, contigs = gen.random_paf(77, n_contigs=6, recs_per_contig=8, max_ops=300)
+    paf_text = b"".join(sorted(paf_text.splitlines(keepends=True), key=lambda ln: ln.split(b"\t")[5]))
+    names = sorted(contigs)
+    first = [ln for ln in paf_text.splitlines() if ln.split(b"\t")[5].decode() == names[0]][0].split(b"\t")
+    rows = [(names[0], int(first[7]) + 1, int(first[7]) + 3)] + [(nm, 0, contigs[nm] + 1000) for nm in names[1:]]
+    bed_text = gen.bed_text(rows, with_ids=False)
+    monkeypatch.setenv("RB_TRACE", "1")  # the library logs its slice decisions to stderr
+    ctx = capi.Context(0)                # a fresh context: no large pinned block from an earlier call to fall into
+    ctx.set_slicing(64)
+    try:
+        res = check_against_oracle(ctx, paf_text, bed_text)
+    finally:
+        ctx.close()
+    assert res["n_out"] > 30
+    assert "text estimate too small: falling back" in capfd.readouterr().err
+
+
 @pytest.mark.parametrize("seed", range(6))
 def test_random_unsorted_nested_bed_general_path(ctx, seed):
     # BED file order is never sorted by the reference (Q5); nested + duplicate rows
