@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -85,7 +86,7 @@ struct rb_ctx {
     cudaStream_t upload_on = nullptr;          // stream upload_cigar / upload_columns enqueue on (nullptr: `stream`)
     cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-    cudaEvent_t ev_win = nullptr;
+    cudaEvent_t ev_win = nullptr, ev_wfirst = nullptr;
     uint64_t slice_min_bytes = 16ull << 20;  // rb_ctx_set_slicing (0 = off)
     DevBuf scalars;               // small device scalars
     void* h_scalars = nullptr;    // pinned, mapped mirror (kernels store into it: k_publish)
@@ -417,7 +418,8 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&ctx->h_scalars_dev, ctx->h_scalars, 0) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_wfirst, cudaEventDisableTiming) != cudaSuccess) {
         (void)cudaGetLastError();
         delete ctx;
         set(RB_ERR_CUDA);
@@ -458,6 +460,7 @@ void rb_ctx_destroy(rb_ctx* ctx) {
     if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
     for (int k = 0; k < 2; k++) if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
     if (ctx->ev_win) cudaEventDestroy(ctx->ev_win);
+    if (ctx->ev_wfirst) cudaEventDestroy(ctx->ev_wfirst);
     for (PinnedBlock* b : ctx->pinned) { cudaFreeHost(b->p); delete b; }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->scalars.release();
@@ -576,10 +579,8 @@ static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel se
     return RB_OK;
 }
 
-// The window tables, step 1: enqueue the copies of the caller's (sorted) arrays and a check kernel.  The host never
-// walks the table (3 M rows at 1 kb windows = 75 MB of host reads); it only binary-searches t_id for the contig ranges.
-static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
-    cudaStream_t s = ctx->stream;
+// step 1a (host only): argument checks, device buffers, contig ranges
+static int windows_prepare(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
     b->n_win = W ? W->n_win : 0;
     b->wsrc = nullptr;
     b->general = false; b->default_ids = false; b->win_pending = false;
@@ -590,35 +591,40 @@ static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, c
     CU(b->w_st.ensure((size_t)nw * 8)); CU(b->w_en.ensure((size_t)nw * 8)); CU(b->w_bed_row.ensure((size_t)nw * 4));
     CU(b->w_tid.ensure((size_t)nw * 4));
     CU(b->cont_lo.ensure((size_t)(R->n_names + 1) * 4)); CU(b->cont_hi.ensure((size_t)(R->n_names + 1) * 4));
-    CU(h2d_copy(b->w_tid.p, W->t_id, (size_t)nw * 4, s));
-    CU(h2d_copy(b->w_st.p, W->st, (size_t)nw * 8, s));
-    CU(h2d_copy(b->w_en.p, W->en, (size_t)nw * 8, s));
-    CU(h2d_copy(b->w_bed_row.p, W->bed_row, (size_t)nw * 4, s));
+    // contig ranges: t_id is sorted (verified on the device; an unsorted table only yields ranges nobody will use)
+    b->h_clo.assign(R->n_names + 1, 0); b->h_chi.assign(R->n_names + 1, 0);
+    const uint32_t* tid = W->t_id;
+    uint32_t i = 0;
+    while (i < nw) {  // gallop from contig to contig: O(contigs * log n_win) host reads
+        const uint32_t t = tid[i];
+        const uint32_t j = (uint32_t)(std::upper_bound(tid + i, tid + nw, t) - tid);
+        if (t < R->n_names) { b->h_clo[t] = i; b->h_chi[t] = j; }
+        i = j > i ? j : i + 1;
+    }
+    return RB_OK;
+}
+
+// step 1b: rows [lo, hi) of the caller's (sorted) tables -> the same rows of the device tables
+static int windows_upload_rows(rb_ctx* ctx, rb_batch* b, const rb_windows* W, uint32_t lo, uint32_t hi, cudaStream_t s) {
+    if (hi <= lo) return RB_OK;
+    const size_t n = hi - lo;
+    CU(h2d_copy(b->w_tid.as<uint32_t>() + lo, W->t_id + lo, n * 4, s));
+    CU(h2d_copy(b->w_st.as<uint64_t>() + lo, W->st + lo, n * 8, s));
+    CU(h2d_copy(b->w_en.as<uint64_t>() + lo, W->en + lo, n * 8, s));
+    CU(h2d_copy(b->w_bed_row.as<uint32_t>() + lo, W->bed_row + lo, n * 4, s));
     b->busy = true;
-    uint32_t* sc = ctx->scalars.as<uint32_t>();
-    CU(cudaMemsetAsync(sc + SC_WINFLAGS, 0, 4, s));
-    launch_win_check(b->w_tid.as<uint32_t>(), b->w_st.as<uint64_t>(), b->w_en.as<uint64_t>(), b->w_bed_row.as<uint32_t>(), nw,
-                     R->n_names, sc + SC_WINFLAGS, s);
-    Publisher(ctx).u32(16, sc + SC_WINFLAGS).go(s);
-    CU(cudaEventRecord(ctx->ev_win, s));
-    b->win_pending = true;
+    return RB_OK;
+}
+
+// step 1c: what every kernel that touches windows needs besides the rows: contig ranges and (if given) the ids
+static int windows_upload_aux(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W, cudaStream_t s) {
+    if (!b->n_win) return RB_OK;
+    const uint32_t nw = b->n_win;
     if (!b->default_ids) {
         const uint64_t ids_bytes = W->ids_off[nw];
         CU(b->w_ids_off.ensure((size_t)(nw + 1) * 8)); CU(b->w_ids.ensure(ids_bytes + 8));
         CU(h2d_copy(b->w_ids_off.p, W->ids_off, (size_t)(nw + 1) * 8, s));
         if (ids_bytes) CU(h2d_copy(b->w_ids.p, W->ids, ids_bytes, s));
-    }
-    // contig ranges: t_id is sorted (verified on the device; an unsorted table only yields ranges nobody will use)
-    b->h_clo.assign(R->n_names + 1, 0); b->h_chi.assign(R->n_names + 1, 0);
-    {
-        const uint32_t* tid = W->t_id;
-        uint32_t i = 0;
-        while (i < nw) {  // gallop from contig to contig: O(contigs * log n_win) host reads
-            const uint32_t t = tid[i];
-            const uint32_t j = (uint32_t)(std::upper_bound(tid + i, tid + nw, t) - tid);
-            if (t < R->n_names) { b->h_clo[t] = i; b->h_chi[t] = j; }
-            i = j > i ? j : i + 1;
-        }
     }
     const size_t cbytes = (size_t)(R->n_names + 1) * 4;
     CU(b->wstage.ensure(2 * cbytes));
@@ -626,7 +632,36 @@ static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, c
     memcpy(b->wstage.p + cbytes, b->h_chi.data(), cbytes);
     CU(cudaMemcpyAsync(b->cont_lo.p, b->wstage.p, cbytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(b->cont_hi.p, b->wstage.p + cbytes, cbytes, cudaMemcpyHostToDevice, s));
+    b->busy = true;
     return RB_OK;
+}
+
+// step 1d: check kernel over the whole table (all rows must have been enqueued on `s` or on streams `s` waits for);
+// its verdict is read by upload_windows_end.  The host never walks the table (3 M rows at 1 kb windows = 75 MB of host
+// reads); it only binary-searches t_id for the contig ranges.
+static int windows_check(rb_ctx* ctx, rb_batch* b, const rb_records* R, cudaStream_t s) {
+    if (!b->n_win) return RB_OK;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    CU(cudaMemsetAsync(sc + SC_WINFLAGS, 0, 4, s));
+    launch_win_check(b->w_tid.as<uint32_t>(), b->w_st.as<uint64_t>(), b->w_en.as<uint64_t>(), b->w_bed_row.as<uint32_t>(), b->n_win,
+                     R->n_names, sc + SC_WINFLAGS, s);
+    PublishArgs a{};
+    a.dst = reinterpret_cast<unsigned long long*>(ctx->h_scalars_dev);
+    a.src[0] = sc + SC_WINFLAGS; a.slot[0] = 16; a.wide[0] = 0; a.n = 1;
+    launch_publish(a, s);
+    CU(cudaEventRecord(ctx->ev_win, s));
+    b->win_pending = true;
+    return RB_OK;
+}
+
+// The window tables, step 1 for the single-batch path: everything on the context's stream
+static int upload_windows_begin(rb_ctx* ctx, rb_batch* b, const rb_records* R, const rb_windows* W) {
+    cudaStream_t s = ctx->stream;
+    int rc = windows_prepare(ctx, b, R, W);
+    if (rc == RB_OK) rc = windows_upload_rows(ctx, b, W, 0, b->n_win, s);
+    if (rc == RB_OK) rc = windows_check(ctx, b, R, s);
+    if (rc == RB_OK) rc = windows_upload_aux(ctx, b, R, W, s);
+    return rc;
 }
 
 // step 2: wait for the verdict of the check kernel; the rare general layout (BED rows whose file order is not the
@@ -1170,10 +1205,8 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     if (wb->busy) { CU(cudaStreamSynchronize(A)); wb->busy = false; }
     wb->n_rec = 0; wb->have_lift = wb->have_stats = false;
     TE("A start", 0, A);
-    int rc = upload_windows_begin(ctx, wb, recs, wins);
-    if (rc != RB_OK) { cudaStreamSynchronize(A); wb->busy = false; return rc; }
-    T("windows enqueued", 0);
-    TE("A windows uploaded", 0, A);
+    int rc = windows_prepare(ctx, wb, recs, wins);
+    if (rc != RB_OK) return rc;
 
     // ---- slice boundaries (record granularity, balanced on CIGAR bytes) and an upper bound on the rows ----
     const uint32_t n = recs->n_rec;
@@ -1181,13 +1214,16 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     const uint32_t K = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
     std::vector<uint32_t> cut(1, 0);  // slice k = records ord[cut[k] .. cut[k+1]) : consecutive in EMISSION order
     {
-        uint64_t acc = 0;
+        // the first slice is half the size of the others: its rows reach the copy engine sooner, yet their download still
+        // covers the production of the second slice; from then on the download is the bottleneck
+        const uint64_t unit = total_bytes / (2 * (uint64_t)K - 1);  // sizes 1 : 2 : 2 : ... in units
+        uint64_t acc = 0, target = unit;
         uint32_t k = 1;
         for (uint32_t i = 0; i < n && k < K; i++) {
             const uint32_t r = ord[i];
             if (recs->cigar_off[r + 1] < recs->cigar_off[r]) break;  // malformed offsets: reported by the upload
             acc += recs->cigar_off[r + 1] - recs->cigar_off[r];
-            if (acc >= total_bytes / K * k && i + 1 < n) { cut.push_back(i + 1); k++; }
+            if (acc >= target && i + 1 < n) { cut.push_back(i + 1); k++; target = unit + 2 * unit * (uint64_t)(k - 1); }
         }
     }
     cut.push_back(n);
@@ -1231,6 +1267,7 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         if (!ctx->slice[k]) ctx->slice[k] = new rb_batch();
         ctx->slice[k]->wsrc = wb;
     }
+    std::function<int(uint32_t, cudaStream_t)> upload_slice_windows;
     auto upload_slice = [&](uint32_t k) {
         rb_batch* sb = ctx->slice[k & 1];
         // file order == emission order: a plain run of the caller's arrays; else the slice is gathered run by run
@@ -1238,23 +1275,43 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         // on the upload stream, so that the copy runs beside the kernels of the previous slice; the work area's own
         // previous kernels (slice k-2) must have finished reading its inputs
         if (k >= 2 && cudaStreamWaitEvent(U, ctx->ev_done[k & 1], 0) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamWaitEvent");
+        int r2 = k ? upload_slice_windows(k, U) : (int)RB_OK;
+        if (r2 != RB_OK) return r2;
         ctx->upload_on = U;
-        int r2 = upload_cigar(ctx, sb, recs, sel);
+        r2 = upload_cigar(ctx, sb, recs, sel);
         if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, sel);
         ctx->upload_on = nullptr;
         sb->wsrc = wb;
         if (r2 == RB_OK && cudaEventRecord(ctx->ev_up[k & 1], U) != cudaSuccess) r2 = fail(ctx, RB_ERR_CUDA, "cudaEventRecord");
         return r2;
     };
+    // Upload order: a slice only needs the window rows of its own contigs, so those travel right in front of its CIGAR
+    // text (first slice: compute stream; later slices: upload stream, beside the kernels of the slice before).  Rows of
+    // contigs no record refers to follow after the last slice, then the check kernel looks at the whole table; its
+    // verdict is read before the call returns (a bad or nested table discards the slices' work).
+    std::vector<uint8_t> contig_up(recs->n_names, 0);
+    std::vector<std::pair<uint32_t, uint32_t>> rows_up;  // uploaded row ranges
+    upload_slice_windows = [&](uint32_t k, cudaStream_t st) {
+        for (uint32_t i = cut[k]; i < cut[k + 1]; i++) {
+            const uint32_t t = recs->t_id[ord[i]];
+            if (contig_up[t]) continue;
+            contig_up[t] = 1;
+            const uint32_t lo = wb->h_clo[t], hi = wb->h_chi[t];
+            if (hi <= lo) continue;
+            const int r2 = windows_upload_rows(ctx, wb, wins, lo, hi, st);
+            if (r2 != RB_OK) return r2;
+            rows_up.emplace_back(lo, hi);
+        }
+        return (int)RB_OK;
+    };
+    rc = upload_slice_windows(0, A);
+    if (rc == RB_OK) rc = windows_upload_aux(ctx, wb, recs, wins, A);
+    if (rc != RB_OK) return bail(rc);
+    if (cudaEventRecord(ctx->ev_wfirst, A) != cudaSuccess) return bail(fail(ctx, RB_ERR_CUDA, "cudaEventRecord"));
+    TE("A first window rows uploaded", 0, A);
     rc = upload_slice(0);
     if (rc != RB_OK) return bail(rc);
-    rc = upload_windows_end(ctx, wb, recs, wins);  // the first slice's copy is already queued behind the window tables
-    if (rc != RB_OK) return bail(rc);
-    T("window tables verified", 0);
-    if (wb->general) {
-        bail(RB_OK);
-        return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, true);
-    }
+    T("uploads of the first slice enqueued", 0);
     for (uint32_t k = 0; k < n_slices; k++) {
         rb_batch* sb = ctx->slice[k & 1];
         if (k + 1 < n_slices) {  // next slice's host->device copies go in front of this slice's kernels
@@ -1297,13 +1354,14 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
                 if (!sblk) return bail(fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)(cap_rows * 40)));
             }
         }
-        if ((want & RB_WANT_TEXT) && byte_base + sm.out_bytes > cap_text) {  // the extrapolation was too small: start over, unsliced
+        if (((want & RB_WANT_TEXT) && byte_base + sm.out_bytes > cap_text) || row_base + sm.n_out > cap_rows) {
+            // the text extrapolation was too small (or the table is not the sorted, non-nested layout the row bound
+            // assumes): start over as a single batch, which sizes everything exactly
             T("text estimate too small: falling back", k);
             bail(RB_OK);
             blk = sblk = nullptr;
-            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, true);
+            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
         }
-        if (row_base + sm.n_out > cap_rows) return bail(fail(ctx, RB_ERR_CUDA, "internal: row bound exceeded"));
         // ---- device -> host of this slice on the copy stream ----
         CUB(cudaStreamWaitEvent(B, ctx->ev_done[k & 1], 0));
         TE("B download starts", k, B);
@@ -1331,6 +1389,26 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         byte_base += sm.out_bytes; row_base += nk; pairs += sm.n_pairs;
     }
     T("all slices enqueued", n_slices);
+    {   // rows no slice needed (contigs without records), then the table check; U has seen every other row already
+        std::sort(rows_up.begin(), rows_up.end());
+        uint32_t at = 0;
+        rc = RB_OK;
+        for (auto& iv : rows_up) {
+            if (rc == RB_OK && iv.first > at) rc = windows_upload_rows(ctx, wb, wins, at, iv.first, U);
+            at = std::max(at, iv.second);
+        }
+        if (rc == RB_OK && at < wb->n_win) rc = windows_upload_rows(ctx, wb, wins, at, wb->n_win, U);
+        if (rc == RB_OK && cudaStreamWaitEvent(U, ctx->ev_wfirst, 0) != cudaSuccess) rc = fail(ctx, RB_ERR_CUDA, "cudaStreamWaitEvent");
+        if (rc == RB_OK) rc = windows_check(ctx, wb, recs, U);
+        if (rc == RB_OK) rc = upload_windows_end(ctx, wb, recs, wins);  // waits for the verdict
+        if (rc != RB_OK) return bail(rc);
+        if (wb->general) {  // nested rows / file order != sorted order: the single-batch path handles those (rare)
+            T("general window layout: falling back", 0);
+            bail(RB_OK);
+            blk = sblk = nullptr;
+            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
+        }
+    }
     CUB(cudaStreamSynchronize(B));
 #undef CUB
     T("copy stream drained", n_slices);

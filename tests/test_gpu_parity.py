@@ -156,7 +156,7 @@ def test_random_sliced_calls(ctx, seed):
 def test_sliced_call_restarts_when_the_text_estimate_is_too_small(capfd, monkeypatch):
     # the pinned text buffer of a sliced call is sized from the first slice; here the first slice yields one short row
     # and the later ones whole records, so the estimate is far too small and the call must restart as a single batch
-    paf_text, contigs = gen.random_paf(77, n_contigs=6, recs_per_contig=8, max_ops=300)
+    paf_text, contigs = gen.random_paf(77, n_contigs=8, recs_per_contig=20, max_ops=400)
     paf_text = b"".join(sorted(paf_text.splitlines(keepends=True), key=lambda ln: ln.split(b"\t")[5]))
     names = sorted(contigs)
     first = [ln for ln in paf_text.splitlines() if ln.split(b"\t")[5].decode() == names[0]][0].split(b"\t")
