@@ -10,6 +10,8 @@
 // CIGAR text is never tokenised here: the cg:Z: payload bytes are packed verbatim for the GPU.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -17,6 +19,26 @@
 #include "rbcuda.h"
 
 namespace rbh {
+
+// Allocator of the big buffers that cross the C ABI (CIGAR text, window tables): page-aligned and padded to whole pages,
+// so that rb_host_register() page-locks memory this buffer owns alone (a neighbouring heap object sharing its first or
+// last page would otherwise end up half page-locked, which the driver rejects on the next copy out of it).
+template <class T>
+struct PageAlloc {
+    using value_type = T;
+    PageAlloc() = default;
+    template <class U> PageAlloc(const PageAlloc<U>&) {}
+    T* allocate(size_t n) {
+        const size_t bytes = (n * sizeof(T) + 4095) / 4096 * 4096;
+        void* p = aligned_alloc(4096, bytes ? bytes : 4096);
+        if (!p) throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t) { free(p); }
+    template <class U> bool operator==(const PageAlloc<U>&) const { return true; }
+    template <class U> bool operator!=(const PageAlloc<U>&) const { return false; }
+};
+template <class T> using PagedVec = std::vector<T, PageAlloc<T>>;
 
 struct Panic : std::runtime_error {  // the reference would panic (exit status 101)
     explicit Panic(const std::string& m) : std::runtime_error(m) {}
@@ -26,7 +48,7 @@ std::string read_all(const std::string& path);  // "-" = stdin; .gz/.bgz inflate
 
 // Packed records (what rb_records points into).  Name ids are shared by query and target names.
 struct Paf {
-    std::vector<uint8_t> cigar;
+    PagedVec<uint8_t> cigar;
     std::vector<uint64_t> cigar_off{0};
     std::vector<uint64_t> q_len, q_st, q_en, t_len, t_st, t_en, mapq;
     std::vector<uint8_t> strand;
@@ -65,9 +87,9 @@ inline std::vector<Region> parse_bed(const std::string& path) {
 
 // rb_windows builder: drops rows on contigs absent from the PAF, sorts by (t_id, st) keeping bed_row
 struct Windows {
-    std::vector<uint32_t> t_id, bed_row;
-    std::vector<uint64_t> st, en, ids_off;
-    std::vector<uint8_t> ids;
+    PagedVec<uint32_t> t_id, bed_row;
+    PagedVec<uint64_t> st, en, ids_off;
+    PagedVec<uint8_t> ids;
     bool default_ids = false;  // every row carries the default id: ids / ids_off stay empty and the GPU formats them
     rb_windows view() const;
     static Windows pack(const std::vector<Region>& rgns, const Paf& paf);

@@ -31,7 +31,9 @@ def pin(obj_ptrs):
     for ptr, nbytes in obj_ptrs:
         addr = C.cast(ptr, C.c_void_p).value
         if addr and nbytes:
-            lib.rb_host_register(C.c_void_p(addr), nbytes)
+            rc = lib.rb_host_register(C.c_void_p(addr), nbytes)
+            if rc != 0:
+                sys.stderr.write(f"rb_host_register({nbytes} bytes) -> {rc}: this buffer stays pageable\n")
 
 
 def timed(f, steps):
