@@ -172,6 +172,11 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
                 rb_lift_out* out, rb_stats_out* stats /* nullable */);
 /* replaces the `for paf in records { stats_from_paf(paf) }` loop of `rb stats --paf` (main.rs:53-56) */
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats);
+/* replaces the loop of `rb break-paf --max-size N` (main.rs:271-281, liftover::break_paf_on_indels liftover.rs:182-226):
+ * every record is cut at its insertions / deletions longer than max_size; rows in FILE order; win_idx = piece number
+ * within the call; the id of a row is its record's id (empty, or the "_TO.." suffix of the indel strip) */
+int rb_break_paf(rb_ctx* ctx, const rb_records* recs, uint32_t max_size, int policy, uint32_t want, rb_lift_out* out,
+                 rb_stats_out* stats /* nullable */);
 void rb_free_lift_out(rb_ctx* ctx, rb_lift_out* out);
 void rb_free_stats_out(rb_ctx* ctx, rb_stats_out* stats);
 
@@ -180,6 +185,8 @@ rb_batch* rb_batch_upload(rb_ctx* ctx, const rb_records* recs, const rb_windows*
 /* `want`: which outputs the kernels materialise in HBM (RB_WANT_* bits); rb_batch_download_lift may ask for a subset */
 int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int with_stats, rb_summary* summary);
 int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary);
+/* break-paf on a batch uploaded without windows (rows in the batch's emission order) */
+int rb_batch_break(rb_ctx* ctx, rb_batch* b, uint32_t max_size, int policy, uint32_t want, int with_stats, rb_summary* summary);
 int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out* out, rb_stats_out* stats);
 int rb_batch_download_stats(rb_ctx* ctx, rb_batch* b, rb_stats_out* stats);
 void rb_batch_free(rb_ctx* ctx, rb_batch* b);

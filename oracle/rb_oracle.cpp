@@ -787,6 +787,17 @@ std::string run_liftover(const char* paf, size_t paf_n, const char* bed, size_t 
 }
 
 // main.rs:50-58
+// main.rs:271-281 — `rb break-paf --max-size N`: records in FILE order, aligned_pairs (strip) then break_paf_on_indels
+std::string run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int policy) {
+    Paf p = Paf::from_text(paf, paf_n);
+    std::string out;
+    for (PafRecord& r : p.records) {
+        r.aligned_pairs();
+        for (const PafRecord& x : break_paf_on_indels(r, max_size, policy)) { out += x.to_line(); out += '\n'; }
+    }
+    return out;
+}
+
 std::string run_stats(const char* paf, size_t paf_n, bool qbed) {
     std::string out = stats_header(qbed);
     Paf p = Paf::from_text(paf, paf_n);

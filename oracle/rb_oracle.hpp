@@ -144,5 +144,6 @@ std::string fmt_f32(float v);  // Rust `{}` for f32
 std::string run_liftover(const char* paf, size_t paf_n, const char* bed, size_t bed_n, bool qbed,
                          bool largest, int policy, int threads);
 std::string run_stats(const char* paf, size_t paf_n, bool qbed);
+std::string run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int policy);
 
 }  // namespace orc

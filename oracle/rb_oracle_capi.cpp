@@ -39,6 +39,17 @@ int orc_run_liftover(const char* paf, size_t paf_n, const char* bed, size_t bed_
     }
 }
 
+int orc_run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int policy, char** out, size_t* out_n, char* err,
+                      size_t err_cap) {
+    try {
+        *out = dup_out(run_break_paf(paf, paf_n, max_size, policy), out_n);
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    }
+}
+
 int orc_run_stats(const char* paf, size_t paf_n, int qbed, char** out, size_t* out_n, char* err,
                   size_t err_cap) {
     try {

@@ -1015,13 +1015,14 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     const uint64_t w_st = win.st[w], w_en = win.en[w];
     PairRes pr;
     uint32_t len = 0;
-    const bool overlaps = ri.t_en > w_st && ri.t_st < w_en;  // the brute-force / nested-window candidates can be a superset
+    // the brute-force / nested-window candidates can be a superset; break-paf pieces of zero length are never built
+    const bool overlaps = ri.t_en > w_st && ri.t_st < w_en && !(win.from_record && w_en <= w_st);
     const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, overlaps, pr, acc);
     __syncwarp();
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
-        uint32_t idl = ri.id_len;
-        if (pr.kind != PK_EARLY) {
+        uint32_t idl = ri.id_len;  // early rows and break-paf pieces carry their record's id
+        if (pr.kind != PK_EARLY && !win.from_record) {
             const uint32_t tn = win.ids_off ? 0u : (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
             idl = win_id_len(win, w, tn, w_st, w_en);
         }
@@ -1061,8 +1062,8 @@ k_combine(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_
     const uint32_t e = combine_pair(v, ri, w_st, w_en, a, b, pr);
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
-        uint32_t idl = ri.id_len;
-        if (pr.kind != PK_EARLY) {
+        uint32_t idl = ri.id_len;  // early rows and break-paf pieces carry their record's id
+        if (pr.kind != PK_EARLY && !win.from_record) {
             const uint32_t tn = win.ids_off ? 0u : (uint32_t)(names_off[ri.t_name + 1] - names_off[ri.t_name]);
             idl = win_id_len(win, w, tn, w_st, w_en);
         }
@@ -1267,7 +1268,7 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     *p++ = '\t'; p = put_u32(p, pr.aln_len);
     *p++ = '\t'; p = put_u64(p, ri.mapq);
     *p++ = '\t'; *p++ = 'i'; *p++ = 'd'; *p++ = ':'; *p++ = 'Z'; *p++ = ':';
-    if (pr.kind == PK_EARLY) {
+    if (pr.kind == PK_EARLY || a.win.from_record) {
         if (ri.flags & RF_STRIPPED) p = put_strip_id(p, ri, a.v);
     } else {
         if (a.win.ids_off) {
@@ -1362,7 +1363,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         if (num.q_st) {
             num.q_st[o] = pr.q_st; num.q_en[o] = pr.q_en; num.t_st[o] = pr.t_st; num.t_en[o] = pr.t_en;
             num.nmatch[o] = pr.nmatch; num.aln_len[o] = pr.aln_len;
-            num.rec_idx[o] = orig_idx ? orig_idx[r] : r + rec_base; num.win_idx[o] = a.win.bed_row[w];
+            num.rec_idx[o] = orig_idx ? orig_idx[r] : r + rec_base; num.win_idx[o] = a.win.bed_row ? a.win.bed_row[w] : w;
         }
         if (st.equal) write_stats(st, o, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
     }
@@ -1555,6 +1556,106 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     k_serialise<<<(unsigned)((n_pairs + group - 1) / group), SER_LINES, SER_CAP, s>>>(
         n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx, group);
 }
+// ------------------------------------------------------------------------------------------------
+// rb break-paf: windows from the record's own large indels (liftover.rs:182-226)
+// ------------------------------------------------------------------------------------------------
+// thread per 32-op chunk.  FILL == false: number of break ops (I / D longer than max_size, inside the stripped op range)
+// of the chunk.  FILL == true: for break op number b (global, in op order) the target position where the piece in front
+// of it ends (cur_tpos) and where the next piece starts (pre_tpos); per record the index of its first / one past its
+// last break op.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_break_scan(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
+             const Ctr* __restrict__ samples, const uint64_t* __restrict__ op_off, uint32_t n_rec, const RecInfo* __restrict__ recs,
+             uint32_t max_size, uint32_t* __restrict__ cnt, const uint64_t* __restrict__ bp_off, uint64_t* __restrict__ bp_end,
+             uint64_t* __restrict__ bp_next, uint64_t* __restrict__ rec_bp0, uint64_t* __restrict__ rec_bp1) {
+    const uint64_t c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_ops = *n_ops_dev;
+    const uint64_t first = c << SAMPLE_LOG2;
+    if (first >= n_ops) return;
+    const int nvalid = (n_ops - first) < SAMPLE ? (int)(n_ops - first) : (int)SAMPLE;
+    const uint32_t h = (uint32_t)((heads[first >> 5] >> (first & 31u)) & (uint32_t)((1ull << SAMPLE) - 1ull));
+    uint32_t r;  // record that holds op `first`: largest r with op_off[r] <= first
+    {
+        uint32_t lo = 0, hi = n_rec;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (op_off[mid] <= first) lo = mid + 1; else hi = mid;
+        }
+        r = lo ? lo - 1 : 0u;
+    }
+    uint64_t T = (h & 1u) ? 0ull : (uint64_t)samples[c * SUBS].T;  // target bases of the record before op `first`
+    uint64_t eo0 = 0, eo1 = 0, t_st = 0, op_end = 0;
+    auto load_rec = [&]() {
+        if (r < n_rec) { const RecInfo& R = recs[r]; eo0 = R.eo0; eo1 = R.eo1; t_st = R.t_st; op_end = R.op_end; }
+        else { eo0 = eo1 = 0; op_end = 0; }
+    };
+    load_rec();
+    uint32_t local = 0;
+    const uint64_t b0 = FILL ? bp_off[c] : 0ull;
+    for (int j = 0; j < nvalid; j++) {
+        const uint64_t k = first + (uint64_t)j;
+        if ((h >> j) & 1u) {  // a record starts at op k
+            if (j > 0) { r++; load_rec(); }
+            T = 0;
+            if (FILL && r < n_rec) rec_bp0[r] = b0 + local;
+        }
+        const uint32_t w = ops[k];
+        const uint32_t code = op_code(w), len = op_len(w);
+        if (k >= eo0 && k < eo1 && (code == OP_I || code == OP_D) && len > max_size) {
+            if (FILL) {
+                bp_end[b0 + local] = t_st + T;                                     // cur_tpos when the break op is met
+                bp_next[b0 + local] = t_st + T + (code == OP_D ? (uint64_t)len : 0ull);  // pre_tpos after it
+            }
+            local++;
+        }
+        if (is_ref(code)) T += len;
+        if (FILL && k + 1 == op_end && r < n_rec) rec_bp1[r] = b0 + local;
+    }
+    if (!FILL) cnt[c] = local;
+}
+
+// thread per record: its window range [wlo, whi) (one window more than it has break ops) and the windows themselves
+__global__ void __launch_bounds__(128)
+k_break_recs(uint32_t n_rec, RecInfo* __restrict__ recs, const uint64_t* __restrict__ rec_bp0, const uint64_t* __restrict__ rec_bp1,
+             const uint64_t* __restrict__ bp_end, const uint64_t* __restrict__ bp_next, uint64_t* __restrict__ w_st,
+             uint64_t* __restrict__ w_en, uint32_t* __restrict__ pair_cnt) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t B0 = rec_bp0[r], B1 = rec_bp1[r];
+    if (B0 == ~0ull || B1 == ~0ull || B1 < B0) {  // a record without ops: the call fails in the strip check anyway
+        recs[r].wlo = recs[r].whi = 0;
+        pair_cnt[r] = 0;
+        return;
+    }
+    const uint64_t nb = B1 - B0;
+    const uint64_t wlo = B0 + r;  // every earlier record owns one window more than it has break ops
+    const uint64_t t_st = recs[r].t_st, t_en = recs[r].t_en;
+    for (uint64_t j = 0; j <= nb; j++) {
+        w_st[wlo + j] = j ? bp_next[B0 + j - 1] : t_st;
+        w_en[wlo + j] = (j < nb) ? bp_end[B0 + j] : t_en;
+    }
+    recs[r].wlo = (uint32_t)wlo;
+    recs[r].whi = (uint32_t)(wlo + nb + 1);
+    pair_cnt[r] = (uint32_t)(nb + 1);
+}
+
+void launch_break_scan(bool fill, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
+                       const Ctr* samples, const uint64_t* op_off, uint32_t n_rec, const RecInfo* recs, uint32_t max_size,
+                       uint32_t* cnt, const uint64_t* bp_off, uint64_t* bp_end, uint64_t* bp_next, uint64_t* rec_bp0, uint64_t* rec_bp1,
+                       cudaStream_t s) {
+    const uint64_t chunks = (n_ops_bound + SAMPLE - 1) / SAMPLE;
+    if (chunks == 0) return;
+    const unsigned blocks = (unsigned)((chunks + 255) / 256);
+    if (fill) k_break_scan<true><<<blocks, 256, 0, s>>>(ops, n_ops_dev, heads, samples, op_off, n_rec, recs, max_size, cnt, bp_off, bp_end, bp_next, rec_bp0, rec_bp1);
+    else k_break_scan<false><<<blocks, 256, 0, s>>>(ops, n_ops_dev, heads, samples, op_off, n_rec, recs, max_size, cnt, bp_off, bp_end, bp_next, rec_bp0, rec_bp1);
+}
+void launch_break_recs(uint32_t n_rec, RecInfo* recs, const uint64_t* rec_bp0, const uint64_t* rec_bp1, const uint64_t* bp_end,
+                       const uint64_t* bp_next, uint64_t* w_st, uint64_t* w_en, uint32_t* pair_cnt, cudaStream_t s) {
+    if (n_rec == 0) return;
+    k_break_recs<<<(n_rec + 127) / 128, 128, 0, s>>>(n_rec, recs, rec_bp0, rec_bp1, bp_end, bp_next, w_st, w_en, pair_cnt);
+}
+
 // Device scalars -> mapped pinned host memory with plain SM stores: the host reads them after a stream sync.  (A
 // cudaMemcpyAsync would queue on the device->host DMA engine behind the bulk download of the previous slice.)
 __global__ void k_publish(PublishArgs a) {

@@ -52,6 +52,8 @@ struct WinView {
     const uint32_t* cont_hi;
     const uint32_t* pair_win;  // general path: explicit window per pair (nullptr on the fast path)
     uint32_t general;          // 1: arrays are in BED file order (grouped by contig), pairs come from the brute-force join
+    uint32_t from_record;      // 1: `rb break-paf` — the windows were generated from each record's own large indels
+                               //    (liftover.rs:182-226): a row's id is its record's id, empty windows are skipped
 };
 
 struct RecInput {  // device copies of rb_records columns
@@ -133,6 +135,15 @@ struct PublishArgs {  // up to 8 device scalars (u32 or u64) -> slots of a mappe
     unsigned long long* dst;
 };
 void launch_publish(const PublishArgs& a, cudaStream_t s);
+// `rb break-paf` (liftover.rs:182-226, main.rs:271-281): the windows of a record are the target intervals between its
+// insertions / deletions longer than max_size.  count pass (per 32-op chunk) -> exclusive scan -> fill pass -> per-record
+// window ranges and the window table itself; everything downstream is the liftover path.
+void launch_break_scan(bool fill, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
+                       const Ctr* samples, const uint64_t* op_off, uint32_t n_rec, const RecInfo* recs, uint32_t max_size,
+                       uint32_t* cnt, const uint64_t* bp_off, uint64_t* bp_end, uint64_t* bp_next, uint64_t* rec_bp0, uint64_t* rec_bp1,
+                       cudaStream_t s);
+void launch_break_recs(uint32_t n_rec, RecInfo* recs, const uint64_t* rec_bp0, const uint64_t* rec_bp1, const uint64_t* bp_end,
+                       const uint64_t* bp_next, uint64_t* w_st, uint64_t* w_en, uint32_t* pair_cnt, cudaStream_t s);
 void launch_win_check(const uint32_t* t_id, const uint64_t* st, const uint64_t* en, const uint32_t* row, uint32_t n_win,
                       uint32_t n_names, uint32_t* flags, cudaStream_t s);
 // general path (unsorted / nested BED rows): the reference's cartesian product + overlap filter (liftover.rs:123-127)

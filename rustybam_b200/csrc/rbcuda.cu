@@ -104,6 +104,7 @@ struct rb_batch {
     PinBuf wstage;  // pinned copies of the contig ranges of the window table
     struct { std::vector<uint64_t> st, en, off; std::vector<uint32_t> row; std::vector<uint8_t> ids; } h_gen;
     bool busy = false;         // uploads of this batch may still be in flight
+    bool file_order = false;   // emission order = file order (break-paf) instead of contig by contig
     bool win_pending = false;  // the window check kernel's verdict has not been read yet
     rb_batch* wsrc = nullptr;  // the batch that holds the window tables (nullptr: this one) — slices share their parent's
     uint32_t rec_base = 0;     // slices: index of this batch's record 0 in the caller's arrays
@@ -115,6 +116,7 @@ struct rb_batch {
     // intermediates
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
     DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans, orig_idx;
+    DevBuf bp_cnt, bp_off, bp_end, bp_next, rec_bp;  // break-paf: break ops per chunk, their scan, piece boundaries
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -437,7 +439,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
     b->stage.release();
     b->wstage.release();
@@ -802,7 +804,7 @@ static int upload_columns(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel 
         std::vector<uint32_t> start(cnt.size() + 1, 0);
         for (size_t g = 0; g < cnt.size(); g++) start[g + 1] = start[g] + cnt[g];
         for (uint32_t i = 0; i < n; i++) {
-            const uint32_t k = start[grp[i]]++;
+            const uint32_t k = b->file_order ? i : start[grp[i]]++;
             s_order[k] = i;
             s_rank[i] = k;
         }
@@ -885,15 +887,79 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
     return RB_OK;
 }
 
+// plan -> lift (or combine) -> line scan -> [host: output sizes] -> serialise; shared by liftover and break-paf
+static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, bool fused, uint32_t want, int with_stats, uint64_t P,
+                     uint64_t n_ops, rb_summary* summary) {
+    cudaStream_t s = ctx->stream;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    const uint32_t n = b->n_rec;
+    int rc = RB_OK;
+    CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
+    {
+        KScope k(ctx, "k_lift_plan");
+        launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
+                         b->plans.as<LiftPlan>(), s);
+    }
+    if (fused) {
+        KScope k(ctx, "k_combine");
+        launch_combine(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(), win,
+                       b->names_off.as<uint64_t>(), b->half_s.as<HalfS>(), b->half_e.as<HalfE>(), b->pair_res.as<PairRes>(),
+                       b->line_len.as<uint32_t>(), err, s);
+    } else {
+        KScope k(ctx, "k_lift");
+        launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                    b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
+                    b->line_len.as<uint32_t>(), err, s);
+    }
+    {
+        KScope k(ctx, "k_scan_lines");
+        launch_scan_lines(b->line_len.as<uint32_t>(), P, b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
+                          b->ln_state.as<uint32_t>(), b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
+    }
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, b->line_off.as<uint64_t>() + P).u64(6, b->out_idx.as<uint64_t>() + P).go(s);
+    CU(cudaStreamSynchronize(s));
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) { flush_times(ctx); return rc; }
+    const uint64_t out_bytes = hs[5], n_out = hs[6];
+
+    b->want = want;
+    if (want & RB_WANT_TEXT) {
+        CU(b->out_text.ensure(out_bytes + 64));
+        CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
+    }
+    if (want & RB_WANT_NUMERIC) CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
+    b->with_stats = with_stats != 0;
+    if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
+    // few, long rows (e.g. 100 kb windows: ~4 KB per row): 8 rows per block instead of 128, so the warp-per-line path
+    // has enough blocks to fill the GPU
+    const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? 8u : (uint32_t)SER_LINES;
+    {
+        KScope k(ctx, "k_serialise");
+        launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                         b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
+                         b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
+                         b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
+                         (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
+                         (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
+                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, s);
+    }
+    if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
+    CU(cudaGetLastError());
+    if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
+    b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
+    b->have_lift = true; b->stats_n = n_out;
+    if (summary) *summary = b->sum;
+    return RB_OK;
+}
+
 int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int with_stats, rb_summary* summary) {
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
-    const bool trace = getenv("RB_TRACE_STEP") != nullptr;  // device-side phase times of one resident step
-    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (trace) { for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], s); }
     int rc = run_tok(ctx, b);
     if (rc != RB_OK) return rc;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
@@ -917,7 +983,6 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
     Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC)
         .u64(4, b->pair_off.as<uint64_t>() + n).go(s);
-    if (trace) cudaEventRecord(tev[1], s);
     CU(cudaStreamSynchronize(s));
     b->busy = false;  // every upload of this batch has been consumed
     if ((uint32_t)hs[3] & 1u) {
@@ -966,71 +1031,105 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                             b->pair_win.as<uint32_t>(), s);
         win.pair_win = b->pair_win.as<uint32_t>();
     }
-    CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
-    {
-        KScope k(ctx, "k_lift_plan");
-        launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
-                         b->plans.as<LiftPlan>(), s);
+    return lift_tail(ctx, b, win, policy, fused, want, with_stats, P, n_ops, summary);
+}
+
+// `rb break-paf` on a resident batch (uploaded WITHOUT windows): every record is cut at its insertions / deletions
+// longer than max_size (liftover.rs:182-226); rows come out in FILE order, record by record (main.rs:271-281).
+int rb_batch_break(rb_ctx* ctx, rb_batch* b, uint32_t max_size, int policy, uint32_t want, int with_stats, rb_summary* summary) {
+    if (!ctx || !b) return RB_ERR_BAD_ARG;
+    if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
+    if (b->wsrc || b->n_win) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_break wants a batch uploaded without windows");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    b->have_lift = false;
+    int rc = run_tok(ctx, b);
+    if (rc != RB_OK) return rc;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    const uint32_t n = b->n_rec;
+    {   // phase A without windows: the indel strip only
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), nullptr, WinView{}, b->recs.as<RecInfo>(),
+                        b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
     }
-    if (fused) {
-        KScope k(ctx, "k_combine");
-        launch_combine(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(), win,
-                       b->names_off.as<uint64_t>(), b->half_s.as<HalfS>(), b->half_e.as<HalfE>(), b->pair_res.as<PairRes>(),
-                       b->line_len.as<uint32_t>(), err, s);
-    } else {
-        KScope k(ctx, "k_lift");
-        launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
-                    b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
-                    b->line_len.as<uint32_t>(), err, s);
+    rc = run_scan(ctx, b, nullptr);
+    if (rc != RB_OK) return rc;
+    {
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(2, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), WinView{},
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+    }
+    // count the break ops per 32-op chunk, scan
+    const uint64_t n_chunks = b->ops_bound / SAMPLE + 1;
+    CU(b->bp_cnt.ensure(n_chunks * 4 + 64));
+    CU(b->bp_off.ensure((n_chunks + 1) * 8 + 64));
+    CU(b->out_idx.ensure((n_chunks + 1) * 8 + 64));  // second output of the generic scan kernel (unused here)
+    CU(cudaMemsetAsync(b->bp_cnt.p, 0, n_chunks * 4, s));
+    const size_t ln_blocks0 = n_chunks / ((size_t)LNS_THREADS * 4) + 2;
+    CU(b->ln_state.ensure(ln_blocks0 * 4)); CU(b->ln_agg.ensure(ln_blocks0 * 16)); CU(b->ln_pre.ensure(ln_blocks0 * 16));
+    CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks0 * 4, s));
+    {
+        KScope k(ctx, "k_break_scan");
+        launch_break_scan(false, b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + n, b->ops_bound, b->heads.as<uint32_t>(),
+                          b->samples.as<Ctr>(), b->op_off.as<uint64_t>(), n, b->recs.as<RecInfo>(), max_size, b->bp_cnt.as<uint32_t>(),
+                          nullptr, nullptr, nullptr, nullptr, nullptr, s);
     }
     {
         KScope k(ctx, "k_scan_lines");
-        launch_scan_lines(b->line_len.as<uint32_t>(), P, b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
-                          b->ln_state.as<uint32_t>(), b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
+        launch_scan_lines(b->bp_cnt.as<uint32_t>(), n_chunks, b->bp_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), b->ln_state.as<uint32_t>(),
+                          b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, s);
     }
-    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, b->line_off.as<uint64_t>() + P).u64(6, b->out_idx.as<uint64_t>() + P).go(s);
-    if (trace) cudaEventRecord(tev[2], s);
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC)
+        .u64(4, b->bp_off.as<uint64_t>() + n_chunks).go(s);
     CU(cudaStreamSynchronize(s));
-    rc = map_err(ctx, b, hs[0], hs[1]);
-    if (rc != RB_OK) { flush_times(ctx); return rc; }
-    const uint64_t out_bytes = hs[5], n_out = hs[6];
+    b->busy = false;
+    if ((uint32_t)hs[3] & 1u) {
+        launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, err, s);
+        Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).go(s);
+        CU(cudaStreamSynchronize(s));
+    }
+    rc = map_err(ctx, b, hs[0], hs[1]);  // parse, integrity and strip panics of ANY record end the call (the reference
+    if (rc != RB_OK) { flush_times(ctx); return rc; }  // loads and strips every record before it prints the first row)
+    const uint64_t n_ops = hs[2], total_bp = hs[4];
+    const uint64_t P = total_bp + n;
+    if (P > 0xFFFFFFFFull) return fail(ctx, RB_ERR_UNSUPPORTED, "more than 2^32 pieces");
 
-    b->want = want;
-    if (want & RB_WANT_TEXT) {
-        CU(b->out_text.ensure(out_bytes + 64));
-        CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
-    }
-    if (want & RB_WANT_NUMERIC) CU(b->out_num.ensure(n_out * (6 * 8 + 2 * 4) + 64));
-    b->with_stats = with_stats != 0;
-    if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
-    // few, long rows (e.g. 100 kb windows: ~4 KB per row): 8 rows per block instead of 128, so the warp-per-line path
-    // has enough blocks to fill the GPU
-    const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? 8u : (uint32_t)SER_LINES;
+    // fill pass -> per-record window ranges + the window table (in the batch's own window buffers)
+    CU(b->bp_end.ensure(total_bp * 8 + 64)); CU(b->bp_next.ensure(total_bp * 8 + 64));
+    CU(b->rec_bp.ensure((size_t)n * 16 + 64));
+    CU(b->w_st.ensure(P * 8 + 64)); CU(b->w_en.ensure(P * 8 + 64));
+    CU(cudaMemsetAsync(b->rec_bp.p, 0xFF, (size_t)n * 16, s));
+    uint64_t* rec_bp0 = b->rec_bp.as<uint64_t>();
+    uint64_t* rec_bp1 = rec_bp0 + n;
     {
-        KScope k(ctx, "k_serialise");
-        launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
-                         b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
-                         b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
-                         b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
-                         (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
-                         (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
-                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, s);
+        KScope k(ctx, "k_break_scan");
+        launch_break_scan(true, b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + n, b->ops_bound, b->heads.as<uint32_t>(),
+                          b->samples.as<Ctr>(), b->op_off.as<uint64_t>(), n, b->recs.as<RecInfo>(), max_size, b->bp_cnt.as<uint32_t>(),
+                          b->bp_off.as<uint64_t>(), b->bp_end.as<uint64_t>(), b->bp_next.as<uint64_t>(), rec_bp0, rec_bp1, s);
     }
-    if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
-    if (trace) {
-        cudaEventRecord(tev[3], s);
-        cudaEventSynchronize(tev[3]);
-        float a = 0, c = 0, d = 0;
-        cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&c, tev[1], tev[2]); cudaEventElapsedTime(&d, tev[2], tev[3]);
-        fprintf(stderr, "[rb_batch_liftover device] tokenise..pair_scan %.3f ms | scan..scan_lines (incl. host sync gap) %.3f ms | serialise %.3f ms\n", a, c, d);
-        for (auto& e : tev) cudaEventDestroy(e);
+    {
+        KScope k(ctx, "k_break_recs");
+        launch_break_recs(n, b->recs.as<RecInfo>(), rec_bp0, rec_bp1, b->bp_end.as<uint64_t>(), b->bp_next.as<uint64_t>(),
+                          b->w_st.as<uint64_t>(), b->w_en.as<uint64_t>(), b->pair_cnt.as<uint32_t>(), s);
     }
-    CU(cudaGetLastError());
-    if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
-    b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
-    b->have_lift = true; b->stats_n = n_out;
-    if (summary) *summary = b->sum;
-    return RB_OK;
+    {
+        KScope k(ctx, "k_pair_scan");  // rec_order is the identity for this batch (file order)
+        launch_pair_scan(b->pair_cnt.as<uint32_t>(), b->rec_order.as<uint32_t>(), n, b->pair_off.as<uint64_t>(), s);
+    }
+    WinView win{};
+    win.st = b->w_st.as<uint64_t>(); win.en = b->w_en.as<uint64_t>(); win.en_pm = win.en;
+    win.from_record = 1u;
+    CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
+    CU(b->line_len.ensure(P * 4 + 64));
+    CU(b->line_off.ensure((P + 1) * 8 + 64));
+    CU(b->out_idx.ensure((P + 1) * 8 + 64));
+    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
+    CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
+    CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));  // the line scan reuses the ticket of the break-op scan
+    return lift_tail(ctx, b, win, policy, false, want, with_stats, P, n_ops, summary);
 }
 
 static int download_stats(rb_ctx* ctx, rb_batch* b, uint64_t n, rb_stats_out* st) {
@@ -1445,6 +1544,24 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         stats->_owner = sblk;
     }
     return RB_OK;
+}
+
+// replaces the `for paf in records { aligned_pairs(); break_paf_on_indels(); println! }` loop of `rb break-paf`
+// (main.rs:271-281)
+int rb_break_paf(rb_ctx* ctx, const rb_records* recs, uint32_t max_size, int policy, uint32_t want, rb_lift_out* out,
+                 rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out) return fail(ctx, RB_ERR_BAD_ARG, "out is null");
+    cudaSetDevice(ctx->device);
+    if (!ctx->scratch) ctx->scratch = new rb_batch();
+    rb_batch* b = ctx->scratch;
+    b->file_order = true;  // rows follow the records in file order, not contig by contig
+    int rc = upload_into(ctx, b, recs, nullptr);
+    b->file_order = false;
+    if (rc != RB_OK) return rc;
+    rc = rb_batch_break(ctx, b, max_size, policy, want, stats != nullptr, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_lift(ctx, b, want, out, stats);
 }
 
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {

@@ -2,18 +2,21 @@
 // (src/cli.rs:16-27,49-60,100-115; drivers src/main.rs:50-58,186-214):
 //     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
+//     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
 // Text (plain / .gz / .bgz / stdin) is read and split on the host; CIGAR tokenising, liftover,
 // trimming, serialisation and identity counting run on the B200 through include/rbcuda.h.
 // Exit status 101 where the reference panics.  There is no CPU fallback: without an sm_100
 // device the program fails.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
 #include "rbhost.hpp"
 
 static int usage() {
-    fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n");
+    fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n"
+                    "       rb [-t N] break-paf [--max-size N] [PAF]\n");
     return 2;
 }
 
@@ -21,6 +24,7 @@ int main(int argc, char** argv) {
     std::string cmd, bed, input = "-";
     bool qbed = false, largest = false, paf_flag = false;
     int policy = RB_POLICY_RIGHTMOST;
+    unsigned long max_size = 100;  // cli.rs:163
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         if ((a == "-t" || a == "--threads") && i + 1 < argc) i++;  // accepted for compatibility; the GPU path has no thread knob
@@ -29,11 +33,13 @@ int main(int argc, char** argv) {
         else if (a == "--qbed" || a == "-q") qbed = true;
         else if (a == "--largest" || a == "-l") largest = true;
         else if (a == "--paf" || a == "-p") paf_flag = true;
+        else if ((a == "--max-size" || a == "-m") && i + 1 < argc) max_size = strtoul(argv[++i], nullptr, 10);
         else if (a == "--policy" && i + 1 < argc) policy = strcmp(argv[++i], "early-exit") == 0 ? RB_POLICY_EARLY_EXIT : RB_POLICY_RIGHTMOST;
         else if (cmd.empty()) cmd = a;
         else input = a;
     }
-    if (cmd != "liftover" && !(cmd == "stats" && paf_flag)) return usage();
+    const bool brk = (cmd == "break-paf" || cmd == "breakpaf" || cmd == "bp");
+    if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk) return usage();
     if (cmd == "liftover" && (qbed || largest)) {
         fprintf(stderr, "rb: --qbed / --largest are not on the GPU path yet (SURVEY 8f 'next')\n");
         return 2;
@@ -62,6 +68,16 @@ int main(int argc, char** argv) {
                 }
                 fwrite(out.data(), 1, out.size(), stdout);
                 rb_free_stats_out(ctx, &st);
+            }
+        } else if (brk) {
+            rbh::Paf paf = rbh::Paf::from_file(input);
+            if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
+            rb_records recs = paf.view();
+            rb_lift_out out{};
+            rc = rb_break_paf(ctx, &recs, (uint32_t)max_size, policy, RB_WANT_TEXT, &out, nullptr);
+            if (rc == RB_OK) {
+                fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                rb_free_lift_out(ctx, &out);
             }
         } else {
             if (bed.empty()) return usage();

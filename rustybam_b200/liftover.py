@@ -23,3 +23,19 @@ def run_liftover(ctx, paf_text: bytes, bed_text: bytes, policy=POLICY_RIGHTMOST)
     rgns = _bed.parse_bed_text(bed_text)
     paf = Paf.from_text(paf_text)
     return trim_paf_by_rgns(ctx, rgns, paf, policy=policy, stats=False, want=WANT_TEXT)["paf_text"]
+
+
+def break_paf_on_indels(ctx, paf: Paf, max_size=100, policy=POLICY_RIGHTMOST, stats=True, want=WANT_TEXT | WANT_NUMERIC):
+    """liftover::break_paf_on_indels for every record (src/liftover.rs:182-226, driver src/main.rs:271-281) on the GPU:
+    res["paf_text"] is what `rb break-paf --max-size N` prints."""
+    try:
+        return ctx.break_paf(paf.pack(), max_size=max_size, policy=policy, want=want, stats=stats)
+    except RbError as e:
+        if e.code in REF_PANIC_CODES:
+            raise ReferencePanic(str(e)) from e
+        raise
+
+
+def run_break_paf(ctx, paf_text: bytes, max_size=100, policy=POLICY_RIGHTMOST) -> bytes:
+    """`rb break-paf --max-size N PAF`: stdout bytes."""
+    return break_paf_on_indels(ctx, Paf.from_text(paf_text), max_size, policy, stats=False, want=WANT_TEXT)["paf_text"]

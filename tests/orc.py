@@ -39,6 +39,16 @@ def run_liftover(paf: bytes, bed: bytes, qbed=False, largest=False, policy=RIGHT
     return _take(out, n)
 
 
+def run_break_paf(paf: bytes, max_size=100, policy=RIGHTMOST) -> bytes:
+    """`rb break-paf --max-size N` (main.rs:271-281) on PAF text."""
+    out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
+    rc = lib().orc_run_break_paf(paf, C.c_size_t(len(paf)), C.c_uint32(max_size), policy, C.byref(out), C.byref(n), err, C.c_size_t(512))
+    if rc == 101:
+        raise ReferencePanic(err.value.decode())
+    assert rc == 0
+    return _take(out, n)
+
+
 def run_stats(paf: bytes, qbed=False) -> bytes:
     out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
     rc = lib().orc_run_stats(paf, C.c_size_t(len(paf)), int(qbed), C.byref(out), C.byref(n), err, C.c_size_t(512))

@@ -261,3 +261,48 @@ def test_resident_batch_is_repeatable(ctx):
     out = ctx.batch_download_lift(b)
     assert out["paf_text"] == orc.run_liftover(paf_text, gen.tiling_bed(contigs, 9))
     ctx.batch_free(b)
+
+
+# ---------------------------------------------------------------- rb break-paf: same kernels, windows from the record's own indels
+def check_break_against_oracle(ctx, paf_text, max_size, policy=0):
+    want = orc.run_break_paf(paf_text, max_size, policy)
+    res = liftover.break_paf_on_indels(ctx, Paf.from_text(paf_text), max_size, policy=policy, stats=True)
+    assert res["paf_text"] == want
+    out_paf = Paf.from_text(res["paf_text"])
+    assert len(out_paf) == res["n_out"]
+    st = (bamstats.print_cigar_stats_header() + bamstats.stats_rows(out_paf, res["stats"])).encode()
+    assert st == orc.run_stats(want)
+    rows = [ln.split(b"\t") for ln in want.splitlines()]
+    assert [int(r[7]) for r in rows] == res["t_st"].tolist() and [int(r[3]) for r in rows] == res["q_en"].tolist()
+    return res
+
+
+def test_break_paf_reference_doctest_vectors(ctx):
+    # liftover.rs:169-181: every piece of 5=5I5= / 5=5D5= broken at indels > 0 has a target span of 5
+    for line in (b"Q\t10\t0\t10\t+\tT\t15\t0\t15\t9\t15\t60\tcg:Z:5=5D5=\n", b"Q\t15\t0\t15\t+\tT\t10\t0\t10\t9\t15\t60\tcg:Z:5=5I5=\n",
+                 b"Q\t15\t0\t15\t-\tT\t10\t0\t10\t9\t15\t60\tcg:Z:5=5I5=\n"):
+        res = check_break_against_oracle(ctx, line, 0)
+        assert res["n_out"] == 2 and ((res["t_en"] - res["t_st"]) == 5).all()
+
+
+@pytest.mark.parametrize("max_size", [0, 2, 10, 100])
+@pytest.mark.parametrize("seed", range(4))
+def test_break_paf_random(ctx, seed, max_size):
+    paf_text, _ = gen.random_paf(600 + seed, n_contigs=4, recs_per_contig=8, style="all" if seed % 2 else "eqx", canonical=(seed < 2),
+                                 allow_zero=(seed >= 2), clips=(seed == 3), max_ops=200)
+    check_break_against_oracle(ctx, paf_text, max_size, policy=seed % 2)
+
+
+@pytest.mark.parametrize("max_size", [10, 100, 1000])
+def test_break_paf_bundled_fixture(ctx, max_size):
+    res = check_break_against_oracle(ctx, orc.golden_paf(), max_size)
+    assert res["n_out"] == {10: 5998, 100: 2447, 1000: 553}[max_size]
+
+
+def test_break_paf_panics_like_the_reference(ctx):
+    line = b"Q\t13\t0\t5\t+\tT\t13\t0\t8\t0\t0\t60\tcg:Z:3D5=\n"
+    with pytest.raises(orc.ReferencePanic):
+        orc.run_break_paf(line, 1)
+    with pytest.raises(ReferencePanic):
+        liftover.run_break_paf(ctx, line, 1)
+    assert liftover.run_break_paf(ctx, b"", 1) == b""

@@ -202,6 +202,8 @@ def test_rb_cli_matches_oracle(tmp_path):
     assert lifted == orc.run_liftover(orc.golden_paf(), orc.golden_bed())
     st = subprocess.run([rb, "stats", "--paf", "-"], input=lifted, capture_output=True, check=True).stdout
     assert st == orc.run_stats(lifted)
+    broken = subprocess.run([rb, "break-paf", "--max-size", "100", paf_gz], capture_output=True, check=True).stdout
+    assert broken == orc.run_break_paf(orc.golden_paf(), 100)
     bad = tmp_path / "bad.paf"
     bad.write_bytes(b"Q\t10\t0\t8\t+\tT\t20\t0\t8\t0\t0\t60\tcg:Z:3D5=\n")
     r = subprocess.run([rb, "liftover", "--bed", bed, str(bad)], capture_output=True)
