@@ -58,6 +58,9 @@ typedef enum rb_status {
 /* what rb_liftover / rb_batch_download_lift materialise on the host */
 #define RB_WANT_TEXT 1u    /* paf_text + line_off */
 #define RB_WANT_NUMERIC 2u /* q_st .. aln_len, rec_idx, win_idx */
+/* rb_liftover only: `liftover --qbed` — the windows are in QUERY coordinates; every record swaps query and target
+ * (I <-> D, op order reversed on '-' strands; paf.rs:1050-1094) before it is lifted, and is printed swapped */
+#define RB_WANT_QBED 4u
 
 /* PAF records, SoA, n_rec rows in FILE order (src/paf.rs:346-368 PafRecord, columns 1-12 + cg:Z:). */
 typedef struct rb_records {

@@ -18,7 +18,7 @@ RB_ERR_REF_CIGAR_PARSE, RB_ERR_REF_INTEGRITY, RB_ERR_REF_STRIP, RB_ERR_REF_INDEX
 RB_ERR_UNSUPPORTED, RB_ERR_OOM = -8, -9
 REF_PANIC_CODES = (RB_ERR_REF_CIGAR_PARSE, RB_ERR_REF_INTEGRITY, RB_ERR_REF_STRIP, RB_ERR_REF_INDEX)
 POLICY_RIGHTMOST, POLICY_EARLY_EXIT = 0, 1
-WANT_TEXT, WANT_NUMERIC = 1, 2
+WANT_TEXT, WANT_NUMERIC, WANT_QBED = 1, 2, 4
 LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
@@ -234,7 +234,7 @@ class Context:
         out, st = RbLiftOut(), RbStatsOut()
         self._check(self.lib.rb_liftover(self.h, C.byref(recs.c), C.byref(wins.c), policy, want, C.byref(out),
                                          C.byref(st) if stats else None))
-        res = self._collect_lift(out, st if stats else None, want) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
+        res = self._collect_lift(out, st if stats else None, want & ~WANT_QBED) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
         self.lib.rb_free_lift_out(self.h, C.byref(out))
         if stats:
             self.lib.rb_free_stats_out(self.h, C.byref(st))

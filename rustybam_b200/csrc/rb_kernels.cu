@@ -310,6 +310,39 @@ k_rec_ops(const uint8_t* __restrict__ text, const uint64_t* __restrict__ cigar_o
     }
 }
 
+// liftover --qbed: cigar_swap_target_query (paf.rs:1050-1066) in place.  Thread per op; on a '-' record the thread of
+// op i (first half) exchanges it with its mirror image, flipping both.
+__device__ __forceinline__ uint32_t flip_indel(uint32_t w) {
+    const uint32_t c = op_code(w);
+    return (c == OP_I || c == OP_D) ? (w ^ 3u) : w;  // codes 1 <-> 2
+}
+__global__ void __launch_bounds__(256)
+k_invert_ops(uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_off, uint32_t n_rec, const uint8_t* __restrict__ strand) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_rec == 0 || k >= op_off[n_rec]) return;
+    uint32_t lo = 0, hi = n_rec;  // largest r with op_off[r] <= k and op_off[r+1] > k
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (op_off[mid] <= k) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t r = lo - 1;
+    const uint64_t a = op_off[r], b = op_off[r + 1];
+    if (strand[r] != '-') { ops[k] = flip_indel(ops[k]); return; }
+    const uint64_t i = k - a, m = b - 1 - i;  // mirror position
+    if (k < m) {
+        const uint32_t x = ops[k], y = ops[m];
+        ops[k] = flip_indel(y);
+        ops[m] = flip_indel(x);
+    } else if (k == m) {
+        ops[k] = flip_indel(ops[k]);
+    }
+}
+void launch_invert_ops(uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, const uint8_t* strand, uint64_t n_ops_bound,
+                       cudaStream_t s) {
+    if (n_rec == 0 || n_ops_bound == 0) return;
+    k_invert_ops<<<(unsigned)((n_ops_bound + 255) / 256), 256, 0, s>>>(ops, op_off, n_rec, strand);
+}
+
 // rust-htslib placement rules for clips (rare; only launched when the tokeniser saw S or H):
 // H only as the first or last op; S only at the ends or separated from them by H only.
 __global__ void k_check_clips(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_off, uint32_t n_rec, ErrSlots err) {
@@ -780,7 +813,7 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
     if ((uint64_t)full.T != t_en_in - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
     if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
-    if ((uint64_t)full.TXT == in.cigar_off[r + 1] - in.cigar_off[r]) ri.flags |= RF_CANON;  // no op is spelled with leading zeros
+    if (!in.no_text && (uint64_t)full.TXT == in.cigar_off[r + 1] - in.cigar_off[r]) ri.flags |= RF_CANON;  // no op is spelled with leading zeros
     if (ri.op_end > ri.op_first) {  // the sampled count stops at the last chunk boundary: look at the tail ops too
         const uint64_t base = ((ri.op_end - 1) >> SAMPLE_LOG2) << SAMPLE_LOG2;
         for (uint64_t k = base > ri.op_first ? base : ri.op_first; k < ri.op_end; k++) {

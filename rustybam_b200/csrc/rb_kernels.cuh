@@ -64,6 +64,7 @@ struct RecInput {  // device copies of rb_records columns
     const uint64_t* names_off;
     const uint8_t* names;
     uint32_t n_rec;
+    uint32_t no_text;  // 1: the op words no longer spell the input text (query/target swapped): never copy ops from it
 };
 
 struct StatsDev {  // device SoA of rb_stats_out
@@ -104,6 +105,9 @@ void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev,
 void launch_combine(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                     const uint32_t* ops, WinView win, const uint64_t* names_off, const HalfS* hs, const HalfE* he, PairRes* res,
                     uint32_t* line_len, ErrSlots err, cudaStream_t s);
+// liftover --qbed (paf.rs:1050-1094 paf_swap_query_and_target): I <-> D in every op, op order reversed on '-' records
+void launch_invert_ops(uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, const uint8_t* strand, uint64_t n_ops_bound,
+                       cudaStream_t s);
 void launch_check_clips(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, ErrSlots err, cudaStream_t s);
 // mode 0: rb stats (after the scan) ; mode 1: liftover phase A (strip + join, before the scan) ; mode 2: phase B (after the scan)
 void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32_t* ops, const Ctr* samples, WinView win,

@@ -75,6 +75,7 @@ struct rb_ctx {
     std::string err;
     bool profiling = false;
     int lift_mode = RB_LIFT_SEARCH;
+    bool invert = false;          // the call in progress is a --qbed liftover
     std::vector<KEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<rb_kernel_time> times;
@@ -105,6 +106,7 @@ struct rb_batch {
     struct { std::vector<uint64_t> st, en, off; std::vector<uint32_t> row; std::vector<uint8_t> ids; } h_gen;
     bool busy = false;         // uploads of this batch may still be in flight
     bool file_order = false;   // emission order = file order (break-paf) instead of contig by contig
+    bool invert = false;       // liftover --qbed: the uploaded columns are swapped, the ops get inverted after tokenising
     bool win_pending = false;  // the window check kernel's verdict has not been read yet
     rb_batch* wsrc = nullptr;  // the batch that holds the window tables (nullptr: this one) — slices share their parent's
     uint32_t rec_base = 0;     // slices: index of this batch's record 0 in the caller's arrays
@@ -279,6 +281,7 @@ RecInput rec_input(const rb_batch* b) {
     in.q_id = b->ids32.as<uint32_t>(); in.t_id = b->ids32.as<uint32_t>() + n;
     in.names_off = b->names_off.as<uint64_t>(); in.names = b->names.as<uint8_t>();
     in.n_rec = b->n_rec;
+    in.no_text = b->invert ? 1u : 0u;
     return in;
 }
 WinView win_view(const rb_batch* self) {
@@ -331,6 +334,10 @@ int run_tok(rb_ctx* ctx, rb_batch* b) {
         KScope k(ctx, "k_rec_ops");
         launch_rec_ops(text, b->cigar_off.as<uint64_t>(), b->n_rec, b->tile_state.as<unsigned long long>(), b->op_off.as<uint64_t>(),
                        b->heads.as<uint32_t>(), err, s);
+    }
+    if (b->invert) {  // --qbed: query and target change roles (the columns were swapped at upload)
+        KScope k(ctx, "k_invert_ops");
+        launch_invert_ops(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), b->n_rec, b->strand.as<uint8_t>(), b->ops_bound, s);
     }
     CU(cudaGetLastError());
     return RB_OK;
@@ -561,6 +568,7 @@ static int upload_cigar(rb_ctx* ctx, rb_batch* b, const rb_records* R, RecSel se
     }
     b->n_rec = n; b->n_names = R->n_names; b->n_bytes = b->h_cigar_off[n];
     b->rec_base = sel.idx ? 0 : sel.r0; b->byte_base = 0;
+    b->invert = ctx->invert;
     b->have_lift = b->have_stats = false;
     b->n_tiles = b->n_bytes / TOK_TILE + 1;
     b->ops_bound = b->n_bytes / 2 + 1;
@@ -1264,6 +1272,18 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
                 rb_stats_out* stats) {
     if (!ctx) return RB_ERR_NO_DEVICE;
     if (!out) return fail(ctx, RB_ERR_BAD_ARG, "out is null");
+    // liftover --qbed (liftover.rs:139-148): every record swaps query and target first — here the column pointers
+    // change places and the ops are inverted on the device right after tokenising
+    rb_records swapped;
+    struct InvertScope { rb_ctx* c; ~InvertScope() { c->invert = false; } } invert_scope{ctx};
+    if ((want & RB_WANT_QBED) && recs) {
+        swapped = *recs;
+        std::swap(swapped.q_len, swapped.t_len); std::swap(swapped.q_st, swapped.t_st); std::swap(swapped.q_en, swapped.t_en);
+        std::swap(swapped.q_id, swapped.t_id);
+        recs = &swapped;
+        ctx->invert = true;
+    }
+    want &= ~RB_WANT_QBED;
     cudaSetDevice(ctx->device);
     if (!ctx->scratch) ctx->scratch = new rb_batch();
     rb_batch* wb = ctx->scratch;

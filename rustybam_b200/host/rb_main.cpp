@@ -1,6 +1,6 @@
 // rb — the host CLI for the two subcommands on the hot path, same flags as the reference
 // (src/cli.rs:16-27,49-60,100-115; drivers src/main.rs:50-58,186-214):
-//     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]
+//     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]     (--qbed: inversion on the GPU; --largest: host filter)
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
 //     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
 // Text (plain / .gz / .bgz / stdin) is read and split on the host; CIGAR tokenising, liftover,
@@ -40,10 +40,6 @@ int main(int argc, char** argv) {
     }
     const bool brk = (cmd == "break-paf" || cmd == "breakpaf" || cmd == "bp");
     if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk) return usage();
-    if (cmd == "liftover" && (qbed || largest)) {
-        fprintf(stderr, "rb: --qbed / --largest are not on the GPU path yet (SURVEY 8f 'next')\n");
-        return 2;
-    }
     int status = 0;
     rb_ctx* ctx = rb_ctx_create(nullptr, 0, &status);
     if (!ctx) {
@@ -88,9 +84,15 @@ int main(int argc, char** argv) {
             rb_records recs = paf.view();
             rb_windows w = wins.view();
             rb_lift_out out{};
-            rc = rb_liftover(ctx, &recs, &w, policy, RB_WANT_TEXT, &out, nullptr);
+            const uint32_t want = RB_WANT_TEXT | (largest ? RB_WANT_NUMERIC : 0u) | (qbed ? RB_WANT_QBED : 0u);
+            rc = rb_liftover(ctx, &recs, &w, policy, want, &out, nullptr);
             if (rc == RB_OK) {
-                fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                if (largest) {  // main.rs:200-208
+                    const std::string rows = rbh::largest_rows(out);
+                    fwrite(rows.data(), 1, rows.size(), stdout);
+                } else {
+                    fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                }
                 rb_free_lift_out(ctx, &out);
             }
         }

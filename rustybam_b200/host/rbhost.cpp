@@ -242,6 +242,41 @@ rb_windows Windows::view() const {
 }
 
 // ---------------------------------------------------------------------------------------------
+// --largest (host-side post-filter over the rows the GPU produced; needs RB_WANT_TEXT | RB_WANT_NUMERIC)
+// ---------------------------------------------------------------------------------------------
+std::string largest_rows(const rb_lift_out& out) {
+    struct Row { const uint8_t* id; size_t id_n; uint64_t span; uint64_t i; };
+    std::vector<Row> rows((size_t)out.n_out);
+    for (uint64_t i = 0; i < out.n_out; i++) {
+        const uint8_t* ln = out.paf_text + out.line_off[i];
+        const uint8_t* end = out.paf_text + out.line_off[i + 1];
+        const uint8_t* p = ln;
+        for (int tabs = 0; tabs < 12 && p < end; p++) tabs += (*p == '\t');  // 13th column: id:Z:<id>
+        const uint8_t* id = p + 5;
+        const uint8_t* q = id;
+        while (q < end && *q != '\t') q++;
+        rows[(size_t)i] = Row{id, (size_t)(q - id), out.t_en[i] - out.t_st[i], i};
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+        const int c = memcmp(a.id, b.id, std::min(a.id_n, b.id_n));
+        return c ? c < 0 : a.id_n < b.id_n;
+    });
+    std::string res;
+    size_t i = 0;
+    while (i < rows.size()) {
+        size_t j = i, best = i;
+        while (j < rows.size() && rows[j].id_n == rows[i].id_n && memcmp(rows[j].id, rows[i].id, rows[i].id_n) == 0) {
+            if (rows[j].span >= rows[best].span) best = j;  // max_by_key keeps the last maximum
+            j++;
+        }
+        const uint64_t k = rows[best].i;
+        res.append(reinterpret_cast<const char*>(out.paf_text + out.line_off[k]), (size_t)(out.line_off[k + 1] - out.line_off[k]));
+        i = j;
+    }
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
 // printing
 // ---------------------------------------------------------------------------------------------
 std::string fmt_f32(float v) {

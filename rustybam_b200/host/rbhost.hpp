@@ -95,6 +95,9 @@ struct Windows {
     static Windows pack(const std::vector<Region>& rgns, const Paf& paf);
 };
 
+// `rb liftover --largest` (main.rs:200-208): rows stably sorted by id, one row per id: the LAST one of maximal target span
+std::string largest_rows(const rb_lift_out& out);
+
 std::string fmt_f32(float v);                 // Rust `{}` for f32 (shortest round trip, positional)
 std::string stats_header(bool qbed);          // bamstats.rs:225-236
 // bamstats.rs:239-270 for row i of `paf` with the GPU counters of row i

@@ -306,3 +306,55 @@ def test_break_paf_panics_like_the_reference(ctx):
     with pytest.raises(ReferencePanic):
         liftover.run_break_paf(ctx, line, 1)
     assert liftover.run_break_paf(ctx, b"", 1) == b""
+
+
+# ---------------------------------------------------------------- liftover --qbed / --largest
+def query_bed(paf_text, seed, width):
+    """BED rows in QUERY coordinates (tiling every query), for --qbed."""
+    qlens = {}
+    for ln in paf_text.splitlines():
+        f = ln.split(b"\t")
+        qlens[f[0].decode()] = int(f[1])
+    return gen.tiling_bed(qlens, width)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_liftover_qbed_random(ctx, seed):
+    # paf_swap_query_and_target (paf.rs:1050-1094): I <-> D, op order reversed on '-' strands, then the same liftover
+    # (= X I D only: N / S / H keep their meaning across the swap, so a record holding one fails check_integrity in the
+    #  reference as well — see the next test)
+    paf_text, contigs = gen.random_paf(700 + seed, n_contigs=4, recs_per_contig=8, style="eqx",
+                                       canonical=(seed < 4), allow_zero=(seed >= 4), clips=False, lead_trail=False)
+    bed_text = query_bed(paf_text, seed, 7 + seed)
+    want = orc.run_liftover(paf_text, bed_text, qbed=True, policy=seed % 2, threads=2)
+    got = liftover.run_liftover(ctx, paf_text, bed_text, policy=seed % 2, qbed=True)
+    assert got == want and len(want) > 0
+    ctx.set_slicing(64)  # and through the sliced pipeline
+    try:
+        assert liftover.run_liftover(ctx, paf_text, bed_text, policy=seed % 2, qbed=True) == want
+    finally:
+        ctx.set_slicing()
+
+
+def test_liftover_qbed_soft_clips_panic_like_the_reference(ctx):
+    # S consumes the query on both sides of the swap, so the swapped record's target span no longer matches its CIGAR
+    for line in (b"Q\t30\t0\t13\t+\tT\t40\t5\t15\t0\t0\t60\tcg:Z:3S10=\n", b"Q\t30\t0\t10\t-\tT\t40\t5\t20\t0\t0\t60\tcg:Z:5=5N5=\n"):
+        with pytest.raises(orc.ReferencePanic):
+            orc.run_liftover(line, b"Q\t0\t30\n", qbed=True)
+        with pytest.raises(ReferencePanic):
+            liftover.run_liftover(ctx, line, b"Q\t0\t30\n", qbed=True)
+
+
+def test_liftover_qbed_bundled_fixture(ctx):
+    paf_text = orc.golden_paf()
+    bed_text = query_bed(paf_text, 0, 200_000)
+    want = orc.run_liftover(paf_text, bed_text, qbed=True, threads=4)
+    assert liftover.run_liftover(ctx, paf_text, bed_text, qbed=True) == want and want.count(b"\n") > 100
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_liftover_largest(ctx, seed):
+    paf_text, contigs = gen.random_paf(800 + seed, n_contigs=3, recs_per_contig=10)
+    for bed_text in (gen.tiling_bed(contigs, 25), gen.random_bed(seed, contigs, 60, with_ids=True), gen.random_bed(seed, contigs, 60, with_ids=False)):
+        want = orc.run_liftover(paf_text, bed_text, largest=True, threads=1)
+        assert liftover.run_liftover(ctx, paf_text, bed_text, largest=True) == want

@@ -202,6 +202,8 @@ def test_rb_cli_matches_oracle(tmp_path):
     assert lifted == orc.run_liftover(orc.golden_paf(), orc.golden_bed())
     st = subprocess.run([rb, "stats", "--paf", "-"], input=lifted, capture_output=True, check=True).stdout
     assert st == orc.run_stats(lifted)
+    big = subprocess.run([rb, "liftover", "--largest", "--bed", bed, paf_gz], capture_output=True, check=True).stdout
+    assert big == orc.run_liftover(orc.golden_paf(), orc.golden_bed(), largest=True)
     broken = subprocess.run([rb, "break-paf", "--max-size", "100", paf_gz], capture_output=True, check=True).stdout
     assert broken == orc.run_break_paf(orc.golden_paf(), 100)
     bad = tmp_path / "bad.paf"
