@@ -14,6 +14,15 @@ def pytest_configure(config):
 
 
 @pytest.fixture(scope="session", autouse=True)
+def _build_product():
+    """The in-tree native artefacts (CUDA library, C++ host library, rb) are built once per session — nvcc cross-compiles
+    without a GPU — so that spawned worker processes and CLI tests find them."""
+    from rustybam_b200 import build
+    build.build_all()
+    yield
+
+
+@pytest.fixture(scope="session", autouse=True)
 def _build_oracle():
     """The CPU checker is built on demand (seconds); it is test infrastructure only."""
     so = os.path.join(ROOT, "oracle", "_build", "liborc.so")
