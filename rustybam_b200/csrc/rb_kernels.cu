@@ -1158,10 +1158,15 @@ __device__ __forceinline__ ulonglong2 lookback_2u64(uint32_t* state, ulonglong2*
     return acc;
 }
 
-constexpr int LNS_ITEMS = 16;  // items per thread (4096 per block: four times fewer look-backs than 4)
+constexpr int LNS_ITEMS = 16;                       // items per thread and tile
+constexpr int LNS_TILE = LNS_THREADS * LNS_ITEMS;   // 4096 items
+// A few hundred blocks, each owning a contiguous span of whole tiles: pass 1 reduces the span (coalesced), one
+// decoupled look-back over <= LNS_MAX_BLOCKS predecessors gives the span's prefix, pass 2 scans the span tile by tile
+// with a running carry.  (One tile per block meant ~800 chained look-backs at 3 M items: the kernel was pure latency.)
+constexpr int LNS_MAX_BLOCKS = 296;
 __global__ void __launch_bounds__(LNS_THREADS)
-k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t* __restrict__ line_off, uint64_t* __restrict__ out_idx,
-             uint32_t* blk_state, ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket) {
+k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t span, uint64_t* __restrict__ line_off,
+             uint64_t* __restrict__ out_idx, uint32_t* blk_state, ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket) {
     __shared__ ulonglong2 s_warp[LNS_THREADS / 32];
     __shared__ ulonglong2 s_blk;
     __shared__ unsigned int s_b;
@@ -1169,45 +1174,59 @@ k_scan_lines(const uint32_t* __restrict__ line_len, uint64_t n, uint64_t* __rest
     if (tid == 0) s_b = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint64_t b = s_b;
-    const uint64_t i0 = (b * LNS_THREADS + tid) * LNS_ITEMS;
-    uint32_t x[LNS_ITEMS];
+    const uint64_t lo = b * span, hi = (lo + span < n) ? lo + span : n;
+    if (n == 0) {
+        if (b == 0 && tid == 0) { line_off[0] = 0; out_idx[0] = 0; }
+        return;
+    }
+    // ---- pass 1: aggregate of the span ----
     unsigned long long sb = 0, sc = 0;
-#pragma unroll
-    for (int k = 0; k < LNS_ITEMS; k++) {
-        x[k] = (i0 + k < n) ? line_len[i0 + k] : 0u;
-        sb += x[k];
-        sc += (x[k] != 0u);
+    for (uint64_t i = lo + tid; i < hi; i += LNS_THREADS) {
+        const uint32_t x = line_len[i];
+        sb += x;
+        sc += (x != 0u);
     }
-    unsigned long long ib = sb, ic = sc;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long tb = __shfl_up_sync(0xffffffffu, ib, d), tc = __shfl_up_sync(0xffffffffu, ic, d);
-        if (lane >= d) { ib += tb; ic += tc; }
+    for (int d = 16; d > 0; d >>= 1) {
+        sb += __shfl_xor_sync(0xffffffffu, sb, d);
+        sc += __shfl_xor_sync(0xffffffffu, sc, d);
     }
-    if (lane == 31) s_warp[warp] = make_ulonglong2(ib, ic);
+    if (lane == 0) s_warp[warp] = make_ulonglong2(sb, sc);
     __syncthreads();
-    unsigned long long wb = 0, wc = 0, tb = 0, tc = 0;
-#pragma unroll
-    for (int k = 0; k < LNS_THREADS / 32; k++) {
-        const ulonglong2 t = s_warp[k];
-        if (k < warp) { wb += t.x; wc += t.y; }
-        tb += t.x; tc += t.y;
-    }
     if (warp == 0) {
+        unsigned long long tb = 0, tc = 0;
+#pragma unroll
+        for (int k = 0; k < LNS_THREADS / 32; k++) { tb += s_warp[k].x; tc += s_warp[k].y; }
         const ulonglong2 ex = lookback_2u64(blk_state, blk_agg, blk_pre, b, make_ulonglong2(tb, tc));
         if (lane == 0) s_blk = ex;
     }
     __syncthreads();
-    unsigned long long ob = s_blk.x + wb + ib - sb, oc = s_blk.y + wc + ic - sc;
+    unsigned long long base_b = s_blk.x, base_c = s_blk.y;
+    // ---- pass 2: rows of LNS_THREADS consecutive items (coalesced loads and stores), one block scan per row ----
+    for (uint64_t r0 = lo; r0 < hi; r0 += LNS_THREADS) {
+        const uint64_t i = r0 + tid;
+        const uint32_t x = (i < hi) ? line_len[i] : 0u;
+        unsigned long long ib = x, ic = (x != 0u);
 #pragma unroll
-    for (int k = 0; k < LNS_ITEMS; k++) {
-        if (i0 + k < n) { line_off[i0 + k] = ob; out_idx[i0 + k] = oc; }
-        ob += x[k];
-        oc += (x[k] != 0u);
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long ub = __shfl_up_sync(0xffffffffu, ib, d), uc = __shfl_up_sync(0xffffffffu, ic, d);
+            if (lane >= d) { ib += ub; ic += uc; }
+        }
+        __syncthreads();  // s_warp is reused from the previous row / pass 1
+        if (lane == 31) s_warp[warp] = make_ulonglong2(ib, ic);
+        __syncthreads();
+        unsigned long long wb = 0, wc = 0, allb = 0, allc = 0;
+#pragma unroll
+        for (int k = 0; k < LNS_THREADS / 32; k++) {
+            const ulonglong2 t = s_warp[k];
+            if (k < warp) { wb += t.x; wc += t.y; }
+            allb += t.x; allc += t.y;
+        }
+        if (i < hi) { line_off[i] = base_b + wb + ib - x; out_idx[i] = base_c + wc + ic - (x != 0u); }
+        base_b += allb; base_c += allc;
     }
-    // the block that owns the last item also writes the totals at index n
-    if (i0 < n && i0 + LNS_ITEMS >= n) { line_off[n] = ob; out_idx[n] = oc; }
-    if (n == 0 && b == 0 && tid == 0) { line_off[0] = 0; out_idx[0] = 0; }
+    // the block whose span ends the array also writes the totals at index n
+    if (hi == n && lo < n && tid == 0) { line_off[n] = base_b; out_idx[n] = base_c; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1567,9 +1586,11 @@ void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
 }
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s) {
-    const uint64_t per = (uint64_t)LNS_THREADS * LNS_ITEMS;
-    const uint64_t blocks = n ? (n + per - 1) / per : 1;
-    k_scan_lines<<<(unsigned)blocks, LNS_THREADS, 0, s>>>(line_len, n, line_off, out_idx, blk_state, blk_agg, blk_pre, ticket);
+    const uint64_t tiles = n ? (n + LNS_TILE - 1) / LNS_TILE : 1;
+    const uint64_t blocks = tiles < (uint64_t)LNS_MAX_BLOCKS ? tiles : (uint64_t)LNS_MAX_BLOCKS;
+    const uint64_t span = (tiles + blocks - 1) / blocks * LNS_TILE;  // whole tiles per block
+    const uint64_t used = n ? (n + span - 1) / span : 1;              // blocks that own at least one item
+    k_scan_lines<<<(unsigned)used, LNS_THREADS, 0, s>>>(line_len, n, span, line_off, out_idx, blk_state, blk_agg, blk_pre, ticket);
 }
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
