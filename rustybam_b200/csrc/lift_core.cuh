@@ -29,6 +29,12 @@ struct OpsView {
     RB_HD const Ctr& ent(uint64_t c, uint32_t s) const {  // entry s of chunk c (0 = absolute sample, 1.. = sub-samples)
         return (c - sc_lo < sc_hi - sc_lo) ? s_smp[(c - sc_lo) * SUBS + s] : samples[c * SUBS + s];
     }
+    // the SUBS entries of chunk c are contiguous in either place: one range check for all of them
+    RB_HD const Ctr* chunk(uint64_t c) const { return &ent(c, 0); }
+    // ops [k, k + n) as one pointer when the whole run is staged, else nullptr (callers then go through op())
+    RB_HD const uint32_t* op_run(uint64_t k, uint32_t n) const {
+        return (k - so_lo < so_hi - so_lo && so_hi - k >= n) ? s_ops + (k - so_lo) : nullptr;
+    }
     RB_HD Ctr smp(uint64_t c) const { return ent(c, 0); }
     RB_HD uint32_t smp_T(uint64_t c) const { return ent(c, 0).T; }
     // target bases of the record before op 32c + 8s (s >= 1; the position must lie inside the record)
@@ -86,6 +92,15 @@ RB_HD uint64_t chunk_of(const OpsView& v, const RecInfo& r, uint32_t p) {
         if (a > lo && a <= hi && v.smp_T(a) <= p) lo = a;
         if (z > lo && z <= hi && v.smp_T(z) > p) hi = z - 1;
     }
+    if (lo >= v.sc_lo && hi < v.sc_hi) {  // the whole search range is staged: 32-bit indices, no range checks
+        uint32_t a = (uint32_t)(lo - v.sc_lo), z = (uint32_t)(hi - v.sc_lo);
+        while (a < z) {
+            const uint32_t mid = (a + z + 1) >> 1;
+            if (v.s_smp[mid * SUBS].T <= p) a = mid;
+            else z = mid - 1;
+        }
+        return v.sc_lo + a;
+    }
     while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
         const uint64_t mid = (lo + hi + 1) >> 1;
         if (v.smp_T(mid) <= p) lo = mid;
@@ -104,13 +119,21 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     if (live && r.op_end > r.op_first) {
         const uint64_t lo = chunk_of(v, r, p);
         k0 = lo << SAMPLE_LOG2;
+        const Ctr* e = v.chunk(lo);  // entry 0 = absolute sample, 1.. = sub-samples (relative unless SUB_ABS)
+        const uint32_t T0 = e[0].T;
         uint32_t s = 0;  // last sub-sample of the chunk that lies inside the record and whose target prefix is <= p
         for (uint32_t t = SUBS - 1; t >= 1; t--) {
             const uint64_t pos = k0 + t * SUB_OPS;
-            if (pos > r.op_first && pos < r.op_end && v.sub_T(lo, t) <= p) { s = t; break; }
+            if (pos > r.op_first && pos < r.op_end && ((e[t].aux & SUB_ABS) ? e[t].T : e[t].T + T0) <= p) { s = t; break; }
         }
-        if (s) { k0 += s * SUB_OPS; c = v.at(lo, s); }
-        else if (k0 > r.op_first) c = v.smp(lo);
+        if (s) {
+            k0 += s * SUB_OPS;
+            c = e[s];
+            const bool abs = (c.aux & SUB_ABS) != 0;
+            c.aux = 0;
+            if (!abs) ctr_add(c, e[0]);
+        }
+        else if (k0 > r.op_first) c = e[0];
         else k0 = r.op_first;
         const uint64_t left = r.op_end - k0;
         n = left > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)left;
@@ -118,7 +141,17 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     RB_CONVERGE();
     const uint32_t rel = p - c.T;  // target offset relative to the chunk start
     acc_reset(acc);
-    for (; j < n; j++) {
+    const uint32_t near = n < SUB_OPS ? n : SUB_OPS;  // the op is normally within the sub-sample block
+    const uint32_t* run = near ? v.op_run(k0, near) : nullptr;
+    if (run) {  // staged run: plain shared-memory reads
+        for (; j < near; j++) {
+            const uint32_t w = run[j];
+            const uint32_t L = op_len(w);
+            if (is_ref(op_code(w)) && L > 0 && rel - acc.T < L) { found = true; break; }
+            acc_add_op(acc, w);
+        }
+    }
+    for (; !found && j < n; j++) {
         const uint32_t w = v.op(k0 + j);
         const uint32_t L = op_len(w);
         if (is_ref(op_code(w)) && L > 0 && rel - acc.T < L) { found = true; break; }

@@ -54,21 +54,19 @@ RB_HD uint32_t clz32(uint32_t v) {
     return v ? (uint32_t)__builtin_clz(v) : 32u;
 #endif
 }
-// decimal digits of v (v < 2^32)
+// decimal digits of v (v < 2^32): bit length -> estimate of log10 -> one compare against a power of ten
+#if defined(__CUDACC__)
+static __constant__ uint32_t c_digits_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+#endif
 RB_HD uint32_t ndigits32(uint32_t v) {
-    uint32_t n = 1u;
-    if (v >= 10u) n++;
-    if (v >= 100u) n++;
-    if (v >= 1000u) n++;
-    if (v >= 10000u) {
-        n++;
-        if (v >= 100000u) n++;
-        if (v >= 1000000u) n++;
-        if (v >= 10000000u) n++;
-        if (v >= 100000000u) n++;
-        if (v >= 1000000000u) n++;
-    }
-    return n;
+    const uint32_t x = v | 1u;                         // 0 prints as "0": one digit (x has the digit count of v for every v)
+    const uint32_t t = ((32u - clz32(x)) * 1233u) >> 12;  // floor(bits * log10(2)): digits - 1 or digits
+#if defined(__CUDA_ARCH__)
+    return t + (x >= c_digits_pow10[t] ? 1u : 0u);
+#else
+    static const uint32_t p10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+    return t + (x >= p10[t] ? 1u : 0u);
+#endif
 }
 RB_HD uint32_t ndigits64(uint64_t v) {
     if (v < 4294967296ull) return ndigits32((uint32_t)v);

@@ -1017,7 +1017,13 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
             const uint64_t o_lo = c_lo << SAMPLE_LOG2;
             uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
             if (o_hi > op_end) o_hi = op_end;
-            for (uint64_t k = o_lo + tid; k < o_hi; k += LIFT_THREADS) s_ops[k - o_lo] = ops[k];
+            {   // o_lo is a multiple of 32 ops: 16-byte loads, then the (< 4 op) tail
+                const uint32_t n_stage = (uint32_t)(o_hi - o_lo), n4 = n_stage >> 2;
+                const uint4* src4 = reinterpret_cast<const uint4*>(ops + o_lo);
+                uint4* dst4 = reinterpret_cast<uint4*>(s_ops);
+                for (uint32_t k = tid; k < n4; k += LIFT_THREADS) dst4[k] = src4[k];
+                for (uint32_t k = (n4 << 2) + tid; k < n_stage; k += LIFT_THREADS) s_ops[k] = ops[o_lo + k];
+            }
             const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
             const uint64_t c_max = (op_end - 1) >> SAMPLE_LOG2;
             constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
