@@ -997,7 +997,9 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
        uint32_t* __restrict__ line_len, ErrSlots err) {
     __shared__ uint32_t s_acc[9 * LIFT_THREADS];
     __shared__ __align__(16) uint32_t s_ops[(LIFT_CCAP + 1) * SAMPLE];
+#if RB_LIFT_STAGE_SMP
     __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
+#endif
     __shared__ __align__(16) RecInfo s_rec;
     const int tid = threadIdx.x;
     const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
@@ -1024,6 +1026,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
                 for (uint32_t k = tid; k < n4; k += LIFT_THREADS) dst4[k] = src4[k];
                 for (uint32_t k = (n4 << 2) + tid; k < n_stage; k += LIFT_THREADS) s_ops[k] = ops[o_lo + k];
             }
+#if RB_LIFT_STAGE_SMP
             const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
             const uint64_t c_max = (op_end - 1) >> SAMPLE_LOG2;
             constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
@@ -1031,8 +1034,9 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
                 const uint64_t c = c_lo + i / V;
                 if (c <= c_max) reinterpret_cast<uint4*>(s_smp)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(samples) + c * V + i % V);
             }
-            v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
             v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = (c_hi + 1 <= c_max ? c_hi + 2 : c_hi + 1);
+#endif
+            v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
         }
         __syncthreads();
     }

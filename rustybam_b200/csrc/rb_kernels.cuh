@@ -23,6 +23,9 @@ constexpr int SL_WCAP = 2048;                // window boundaries of one block s
 #ifndef RB_LIFT_MINB
 #define RB_LIFT_MINB 6
 #endif
+#ifndef RB_LIFT_STAGE_SMP
+#define RB_LIFT_STAGE_SMP 1  // 0: the samples of a k_lift block stay in global memory (L1/L2), only its ops are staged
+#endif
 #ifndef RB_SMP_MINB
 #define RB_SMP_MINB 3
 #endif
