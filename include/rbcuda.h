@@ -199,7 +199,9 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b);
 int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, uint32_t* perm_out);
 
 /* ---- host helper: page-lock caller-owned buffers (cudaHostRegister) so that the H2D copies of
- * rb_liftover / rb_batch_upload are asynchronous DMA; for hosts without their own CUDA binding. */
+ * rb_liftover / rb_batch_upload are asynchronous DMA; for hosts without their own CUDA binding.  Allocate such buffers
+ * page-aligned and padded to whole pages (a page shared with another object would end up half page-locked), and call
+ * rb_host_unregister BEFORE freeing them.  Large ranges are registered in GiB-aligned pieces. */
 int rb_host_register(void* ptr, uint64_t nbytes);
 int rb_host_unregister(void* ptr);
 

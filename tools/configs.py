@@ -27,6 +27,9 @@ ctx.set_stream(stream.cuda_stream)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
+PINNED = []
+
+
 def pin(obj_ptrs):
     for ptr, nbytes in obj_ptrs:
         addr = C.cast(ptr, C.c_void_p).value
@@ -34,6 +37,16 @@ def pin(obj_ptrs):
             rc = lib.rb_host_register(C.c_void_p(addr), nbytes)
             if rc != 0:
                 sys.stderr.write(f"rb_host_register({nbytes} bytes) -> {rc}: this buffer stays pageable\n")
+            else:
+                PINNED.append(addr)
+
+
+def unpin_all():
+    """Page-locked buffers must be unregistered BEFORE their memory is freed (a later allocation that reuses the
+    addresses would otherwise collide with the stale registration)."""
+    torch.cuda.synchronize()
+    while PINNED:
+        lib.rb_host_unregister(C.c_void_p(PINNED.pop()))
 
 
 def timed(f, steps):
@@ -82,6 +95,13 @@ def run(name, paf, width, steps, resident=True):
             out.update(cigar_ops=s["n_ops"], pairs=s["n_pairs"], rows=s["n_out"], out_bytes=s["out_bytes"])
         out["e2e_ms"], r = wall(lambda: ctx.liftover(paf, wins, want=capi.WANT_TEXT, stats=True, copy=False), steps)
         out.update(rows=r["n_out"], out_bytes=r["paf_nbytes"], pairs=r["n_pairs"])
+    if width is not None:
+        unpin_win = PINNED[-4:]  # the four window columns registered above die with `wins`
+        torch.cuda.synchronize()
+        for a in unpin_win:
+            lib.rb_host_unregister(C.c_void_p(a))
+            PINNED.remove(a)
+        wins.close()
     out["rows_per_s_e2e"] = out["rows"] / (out["e2e_ms"] * 1e-3)
     out["cigar_gb_per_s_e2e"] = out["cigar_bytes"] / (out["e2e_ms"] * 1e-3) / 1e9
     if "resident_ms" in out:
@@ -95,6 +115,7 @@ pin(((one.c.cigar, one.cigar_nbytes),))
 run("C2: rb stats --paf, 1 haplotype (~50 M ops)", one, None, args.steps)
 run("C3: liftover 100 kb windows + stats, 1 haplotype", one, 100_000, args.steps)
 run("C4: liftover 1 kb windows + stats, 1 haplotype", one, 1000, args.steps)
+unpin_all()
 one.close()
 if args.haps > 1:
     t0 = time.time()
@@ -103,4 +124,5 @@ if args.haps > 1:
     sys.stderr.write(f"generated {args.haps} haplotypes in {time.time() - t0:.1f} s ({many.cigar_nbytes / 1e9:.2f} GB of CIGAR text)\n")
     run(f"C5-style: {args.haps} haplotypes vs CHM13-like, 10 kb windows + stats, ONE GPU (sliced, emission-order gather)", many, 10_000,
         max(2, args.steps // 2), resident=(args.haps <= 24))
+    unpin_all()
 ctx.close()
