@@ -8,6 +8,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <thread>
+#include <atomic>
 #include <iostream>
 #include <sstream>
 
@@ -94,50 +96,133 @@ int64_t Paf::find_name(const std::string& s) const {
 // paf.rs:62-78 + 379-430: lines() split at '\n' (one trailing '\r' dropped), split_ascii_whitespace,
 // >= 12 columns or panic, every extra token must look like a tag or panic, first cg:Z: wins,
 // unparsable numeric column -> the line is skipped.  The CIGAR payload is copied verbatim.
+// first ASCII-whitespace byte in [p, e) ('\n' cannot occur inside a line): libc's vectorised memchr instead of a
+// byte loop — the cg:Z: token of a whole-genome record is hundreds of kilobytes long
+static inline const char* next_ws(const char* p, const char* e) {
+    const char* q = (const char*)memchr(p, '\t', (size_t)(e - p));
+    if (!q) q = e;
+    static const char others[3] = {' ', '\x0C', '\r'};
+    for (char c : others) {
+        const char* r = (const char*)memchr(p, c, (size_t)(q - p));
+        if (r) q = r;
+    }
+    return q;
+}
+
+namespace {
+struct ParsedLine {     // what PafRecord::new extracts from one line (paf.rs:379-430), before name interning
+    const char *q_name = nullptr, *t_name = nullptr, *cg = nullptr;
+    size_t q_name_n = 0, t_name_n = 0, cg_n = 0;
+    uint64_t v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint8_t strand = '+';
+    uint8_t state = 0;  // 0 ok, 1 skipped (unparsable numeric column), 2 panic: < 12 columns, 3 panic: bad tag
+};
+
+void parse_line(const char* text, size_t i, size_t e, ParsedLine& L) {
+    std::pair<const char*, size_t> t[12];
+    size_t nt = 0, p = i;
+    const char* end = text + e;
+    auto next_token = [&](const char*& tok, size_t& tn) {
+        const char* a = text + p;
+        while (a < end && is_ws(*a)) a++;
+        if (a >= end) { p = e; return false; }
+        const char* b = next_ws(a, end);
+        tok = a; tn = (size_t)(b - a);
+        p = (size_t)(b - text);
+        return true;
+    };
+    const char* tok; size_t tn;
+    while (nt < 12 && next_token(tok, tn)) t[nt++] = {tok, tn};
+    if (nt < 12) { L.state = 2; return; }
+    while (next_token(tok, tn)) {  // tags: (..):(.):(.*) somewhere in the token (paf.rs:21,387-389); first cg wins
+        size_t m = SIZE_MAX;
+        for (size_t a = 0; a + 5 <= tn; a++)
+            if (tok[a + 2] == ':' && tok[a + 4] == ':') { m = a; break; }
+        if (m == SIZE_MAX) { L.state = 3; return; }
+        if (tok[m] == 'c' && tok[m + 1] == 'g' && L.cg_n == 0) { L.cg = tok + m + 5; L.cg_n = tn - (m + 5); }
+    }
+    static const int colidx[9] = {1, 2, 3, 6, 7, 8, 9, 10, 11};
+    bool ok = true;
+    for (int c = 0; c < 9 && ok; c++) ok = parse_u64(t[colidx[c]].first, t[colidx[c]].second, L.v[c]);
+    if (!ok || t[4].second != 1) { L.state = 1; return; }
+    L.strand = (uint8_t)t[4].first[0];
+    L.q_name = t[0].first; L.q_name_n = t[0].second;
+    L.t_name = t[5].first; L.t_name_n = t[5].second;
+}
+}  // namespace
+
+// Lines are parsed in parallel (host threads), records are assembled in file order: name ids, skipped-line count
+// and the first panic are exactly those of the serial loop of Paf::from_file (paf.rs:62-78).
 Paf Paf::from_text(const char* text, size_t n) {
     Paf paf;
-    size_t i = 0;
-    std::vector<std::pair<const char*, size_t>> t;
-    while (i < n) {
+    std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the line terminator
+    for (size_t i = 0; i < n;) {
         const char* nl = (const char*)memchr(text + i, '\n', n - i);
         const size_t j = nl ? (size_t)(nl - text) : n;
         size_t e = j;
         if (nl && e > i && text[e - 1] == '\r') e--;
-        t.clear();
-        size_t p = i;
-        while (p < e) {
-            while (p < e && is_ws(text[p])) p++;
-            size_t q = p;
-            while (q < e && !is_ws(text[q])) q++;
-            if (q > p) t.emplace_back(text + p, q - p);
-            p = q;
-        }
+        lines.emplace_back(i, e);
         i = nl ? j + 1 : n;
-        if (t.size() < 12) throw Panic("assertion failed: t.len() >= 12");
-        const char* cg = nullptr;
-        size_t cg_n = 0;
-        for (size_t k = 12; k < t.size(); k++) {
-            const char* tok = t[k].first;
-            const size_t tn = t[k].second;
-            size_t m = SIZE_MAX;
-            for (size_t a = 0; a + 5 <= tn; a++)
-                if (tok[a + 2] == ':' && tok[a + 4] == ':') { m = a; break; }
-            if (m == SIZE_MAX) throw Panic("assertion failed: PAF_TAG.is_match(token)");
-            if (tok[m] == 'c' && tok[m + 1] == 'g' && cg_n == 0) { cg = tok + m + 5; cg_n = tn - (m + 5); }
-        }
-        uint64_t v[9];
-        static const int colidx[9] = {1, 2, 3, 6, 7, 8, 9, 10, 11};
-        bool ok = true;
-        for (int c = 0; c < 9 && ok; c++) ok = parse_u64(t[colidx[c]].first, t[colidx[c]].second, v[c]);
-        if (!ok || t[4].second != 1) { paf.skipped++; continue; }
-        paf.q_len.push_back(v[0]); paf.q_st.push_back(v[1]); paf.q_en.push_back(v[2]);
-        paf.t_len.push_back(v[3]); paf.t_st.push_back(v[4]); paf.t_en.push_back(v[5]);
-        paf.mapq.push_back(v[8]);
-        paf.strand.push_back((uint8_t)t[4].first[0]);
-        paf.q_id.push_back(paf.name_id(std::string(t[0].first, t[0].second)));
-        paf.t_id.push_back(paf.name_id(std::string(t[5].first, t[5].second)));
-        if (cg_n) paf.cigar.insert(paf.cigar.end(), (const uint8_t*)cg, (const uint8_t*)cg + cg_n);
-        paf.cigar_off.push_back(paf.cigar.size());
+    }
+    std::vector<ParsedLine> parsed(lines.size());
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(n < (8u << 20) ? 1 : hw, std::max<size_t>(1, lines.size()));
+    if (nt <= 1) {
+        for (size_t k = 0; k < lines.size(); k++) parse_line(text, lines[k].first, lines[k].second, parsed[k]);
+    } else {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&] {
+                for (;;) {
+                    const size_t k = next.fetch_add(1);
+                    if (k >= lines.size()) break;
+                    parse_line(text, lines[k].first, lines[k].second, parsed[k]);
+                }
+            });
+        for (auto& th : pool) th.join();
+    }
+    size_t total_cg = 0, n_ok = 0;
+    for (const ParsedLine& L : parsed) {
+        if (L.state == 2) throw Panic("assertion failed: t.len() >= 12");
+        if (L.state == 3) throw Panic("assertion failed: PAF_TAG.is_match(token)");
+        if (L.state == 0) { total_cg += L.cg_n; n_ok++; }
+    }
+    paf.cigar.resize(total_cg);
+    paf.cigar_off.reserve(n_ok + 1);
+    std::vector<std::pair<const ParsedLine*, size_t>> copies;  // (line, destination offset) of the CIGAR payloads
+    copies.reserve(n_ok);
+    size_t off = 0;
+    for (const ParsedLine& L : parsed) {
+        if (L.state == 1) { paf.skipped++; continue; }
+        paf.q_len.push_back(L.v[0]); paf.q_st.push_back(L.v[1]); paf.q_en.push_back(L.v[2]);
+        paf.t_len.push_back(L.v[3]); paf.t_st.push_back(L.v[4]); paf.t_en.push_back(L.v[5]);
+        paf.mapq.push_back(L.v[8]);
+        paf.strand.push_back(L.strand);
+        paf.q_id.push_back(paf.name_id(std::string(L.q_name, L.q_name_n)));
+        paf.t_id.push_back(paf.name_id(std::string(L.t_name, L.t_name_n)));
+        copies.emplace_back(&L, off);
+        off += L.cg_n;
+        paf.cigar_off.push_back(off);
+    }
+    auto copy_range = [&](size_t a, size_t b) {
+        for (size_t k = a; k < b; k++)
+            if (copies[k].first->cg_n) memcpy(paf.cigar.data() + copies[k].second, copies[k].first->cg, copies[k].first->cg_n);
+    };
+    if (nt <= 1 || copies.size() < 2) {
+        copy_range(0, copies.size());
+    } else {  // the payload copy is the other O(bytes) step: spread it over the same threads
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++)
+            pool.emplace_back([&] {
+                for (;;) {
+                    const size_t k = next.fetch_add(1);
+                    if (k >= copies.size()) break;
+                    copy_range(k, k + 1);
+                }
+            });
+        for (auto& th : pool) th.join();
     }
     return paf;
 }
