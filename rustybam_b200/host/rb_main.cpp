@@ -57,12 +57,7 @@ int main(int argc, char** argv) {
             rb_stats_out st{};
             rc = rb_stats(ctx, &recs, &st);
             if (rc == RB_OK) {
-                std::string out;
-                for (size_t i = 0; i < paf.size(); i++) {
-                    rbh::append_stats_row(out, paf, i, st, qbed);
-                    if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
-                }
-                fwrite(out.data(), 1, out.size(), stdout);
+                rbh::write_stats_rows(stdout, paf, st, qbed);
                 rb_free_stats_out(ctx, &st);
             }
         } else if (brk) {

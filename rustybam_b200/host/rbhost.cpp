@@ -326,6 +326,37 @@ rb_windows Windows::view() const {
     return v;
 }
 
+void write_stats_rows(FILE* f, const Paf& paf, const rb_stats_out& st, bool qbed) {
+    const size_t n = paf.size();
+    const size_t block = 1u << 15;  // rows per work item
+    const size_t n_blocks = (n + block - 1) / block;
+    const unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, n_blocks));
+    if (nt <= 1) {
+        std::string out;
+        for (size_t i = 0; i < n; i++) {
+            append_stats_row(out, paf, i, st, qbed);
+            if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), f); out.clear(); }
+        }
+        fwrite(out.data(), 1, out.size(), f);
+        return;
+    }
+    // waves of nt blocks: formatted in parallel, written in order
+    std::vector<std::string> bufs(nt);
+    for (size_t b0 = 0; b0 < n_blocks; b0 += nt) {
+        const size_t nb = std::min<size_t>(nt, n_blocks - b0);
+        std::vector<std::thread> pool;
+        for (size_t k = 0; k < nb; k++)
+            pool.emplace_back([&, k] {
+                std::string& out = bufs[k];
+                out.clear();
+                const size_t lo = (b0 + k) * block, hi = std::min(n, lo + block);
+                for (size_t i = lo; i < hi; i++) append_stats_row(out, paf, i, st, qbed);
+            });
+        for (auto& th : pool) th.join();
+        for (size_t k = 0; k < nb; k++) fwrite(bufs[k].data(), 1, bufs[k].size(), f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // --largest (host-side post-filter over the rows the GPU produced; needs RB_WANT_TEXT | RB_WANT_NUMERIC)
 // ---------------------------------------------------------------------------------------------

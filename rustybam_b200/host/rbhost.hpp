@@ -10,6 +10,7 @@
 // CIGAR text is never tokenised here: the cg:Z: payload bytes are packed verbatim for the GPU.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <new>
 #include <stdexcept>
@@ -102,6 +103,8 @@ std::string fmt_f32(float v);                 // Rust `{}` for f32 (shortest rou
 std::string stats_header(bool qbed);          // bamstats.rs:225-236
 // bamstats.rs:239-270 for row i of `paf` with the GPU counters of row i
 void append_stats_row(std::string& out, const Paf& paf, size_t i, const rb_stats_out& st, bool qbed);
+// every row of `paf` (bamstats.rs:239-270), formatted on all host threads, written to `f` in row order
+void write_stats_rows(FILE* f, const Paf& paf, const rb_stats_out& st, bool qbed);
 
 // ---- synthetic whole-genome-scale eqx PAF ----
 struct SynthParams {

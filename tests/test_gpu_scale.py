@@ -194,6 +194,17 @@ def test_two_haplotypes_gathered_slices_equal_unsliced(ctx):
     assert (np.diff(a["rec_idx"].astype(np.int64)) < 0).any()  # emission order is not file order here
 
 
+def test_rb_cli_stats_on_many_rows(ctx, full):
+    """`rb liftover | rb stats --paf` at volume: 100 k lifted rows through the CLI (parallel host parse, GPU counters,
+    parallel row formatting) equal the oracle's `rb stats --paf` of the same rows."""
+    wins = full.tiling_windows(1000)
+    res = ctx.liftover(full, wins, want=capi.WANT_TEXT, stats=False)
+    sub = res["paf_text"][:int(res["line_off"][100_000])]
+    rb = os.path.join(ROOT, "rustybam_b200", "rb")
+    got = subprocess.run([rb, "stats", "--paf", "-"], input=sub, capture_output=True, check=True).stdout
+    assert got == orc.run_stats(sub)
+
+
 def test_rb_cli_matches_oracle(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
