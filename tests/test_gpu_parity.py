@@ -153,6 +153,26 @@ def test_random_sliced_calls(ctx, seed):
         ctx.set_slicing()
 
 
+def test_sliced_call_fails_cleanly_when_a_late_slice_panics(ctx):
+    # a record of the LAST contig has a leading deletion (remove_trailing_indels panics, Q9): the sliced call has
+    # already downloaded earlier slices by then; it must fail like the single-batch call and leave the context usable
+    paf_text, contigs = gen.random_paf(91, n_contigs=5, recs_per_contig=8, max_ops=200, lead_trail=False)
+    lines = sorted(paf_text.splitlines(keepends=True), key=lambda ln: ln.split(b"\t")[5])
+    bad = b"Qbad\t13\t0\t5\t+\t" + lines[-1].split(b"\t")[5] + b"\t100000\t10\t18\t0\t0\t60\tcg:Z:3D5=\n"
+    paf_text = b"".join(lines) + bad
+    bed_text = gen.tiling_bed(contigs, 9)
+    with pytest.raises(orc.ReferencePanic):
+        orc.run_liftover(paf_text, bed_text)
+    ctx.set_slicing(64)
+    try:
+        with pytest.raises(ReferencePanic):
+            liftover.run_liftover(ctx, paf_text, bed_text)
+        good = b"".join(lines)
+        assert liftover.run_liftover(ctx, good, bed_text) == orc.run_liftover(good, bed_text)
+    finally:
+        ctx.set_slicing()
+
+
 def test_sliced_call_restarts_when_the_text_estimate_is_too_small(capfd, monkeypatch):
     # the pinned text buffer of a sliced call is sized from the first slice; here the first slice yields one short row
     # and the later ones whole records, so the estimate is far too small and the call must restart as a single batch
