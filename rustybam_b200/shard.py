@@ -55,3 +55,37 @@ def make_shard(rank, world, scale=1.0, seed=20261017, threads=8):
     shard = take_contigs(full, bins[rank])
     full.close()
     return shard, {"bins": world, "balance": max(loads) / (sum(loads) / world), "contigs": len(bins[rank])}
+
+
+def split_by_target(paf_text: bytes):
+    """Rows of one rank's `rb liftover` output grouped by target name: {t_name: bytes}.  A rank emits its contigs one after
+    the other (liftover.rs:155-164), so each target is one contiguous run of lines."""
+    out, order = {}, []
+    start, cur = 0, None
+    pos = 0
+    n = len(paf_text)
+    while pos < n:
+        end = paf_text.index(b"\n", pos) + 1
+        f = paf_text[pos:end].split(b"\t", 6)
+        t = f[5]
+        if t != cur:
+            if cur is not None:
+                out[cur] = out.get(cur, b"") + paf_text[start:pos]
+            if t not in out:
+                order.append(t)
+            cur, start = t, pos
+        pos = end
+    if cur is not None:
+        out[cur] = out.get(cur, b"") + paf_text[start:n]
+    return out
+
+
+def merge_outputs(contig_order, per_rank_text):
+    """Concatenates the ranks' outputs in the reference's emission order: contigs by first appearance of t_name in the
+    whole PAF (liftover.rs:151), each contig's rows taken from the rank that owns it.  contig_order: list of t_name bytes."""
+    by_target = {}
+    for text in per_rank_text:
+        for t, rows in split_by_target(text).items():
+            assert t not in by_target, "a target contig belongs to exactly one rank"
+            by_target[t] = rows
+    return b"".join(by_target.get(t, b"") for t in contig_order)

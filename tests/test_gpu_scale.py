@@ -194,6 +194,28 @@ def test_two_haplotypes_gathered_slices_equal_unsliced(ctx):
     assert (np.diff(a["rec_idx"].astype(np.int64)) < 0).any()  # emission order is not file order here
 
 
+def test_contig_shards_merge_to_the_single_call_output(ctx):
+    """The multi-GPU recipe on one device: records split by target contig (LPT on CIGAR bytes), every shard lifted on
+    its own, outputs concatenated in emission order == the output of the unsharded call (and of the oracle)."""
+    from rustybam_b200 import shard
+    paf = hostlib.HostPaf.synth(scale=0.02, n_hap=2)
+    bed_text = paf.tiling_bed_text(10_000)
+    whole = ctx.liftover(paf, paf.windows_from_bed_text(bed_text), want=capi.WANT_TEXT, stats=False)["paf_text"]
+    weights = shard.contig_bytes(paf)
+    bins, loads = shard.lpt_bins(weights, 3)
+    outs = []
+    for tids in bins:
+        part = shard.take_contigs(paf, tids)
+        outs.append(ctx.liftover(part, part.windows_from_bed_text(bed_text), want=capi.WANT_TEXT, stats=False)["paf_text"])
+    order = []
+    for ln in paf.text().splitlines():
+        t = ln.split(b"\t")[5]
+        if t not in order:
+            order.append(t)
+    assert shard.merge_outputs(order, outs) == whole
+    assert whole == orc.run_liftover(paf.text(), bed_text, threads=8)
+
+
 def test_rb_cli_stats_on_many_rows(ctx, full):
     """`rb liftover | rb stats --paf` at volume: 100 k lifted rows through the CLI (parallel host parse, GPU counters,
     parallel row formatting) equal the oracle's `rb stats --paf` of the same rows."""

@@ -50,6 +50,50 @@ def test_two_rank_sharding_covers_everything_once():
     assert balance < 1.2
 
 
+def _merge_worker(rank, world, port, q):
+    """Each rank lifts the records of its own contigs (here with the CPU oracle: no GPU in this test), rank 0 gathers the
+    outputs and concatenates them in the reference's emission order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import gen
+    import orc
+    from rustybam_b200 import shard
+    paf_text, contigs = gen.random_paf(5, n_contigs=5, recs_per_contig=7)   # contigs interleave in the file
+    bed_text = gen.tiling_bed(contigs, 13)
+    lines = paf_text.splitlines(keepends=True)
+    order = []
+    for ln in lines:
+        t = ln.split(b"\t")[5]
+        if t not in order:
+            order.append(t)
+    weights = {t: sum(len(ln) for ln in lines if ln.split(b"\t")[5] == t) for t in order}
+    bins, _ = shard.lpt_bins(weights, world)
+    mine = b"".join(ln for ln in lines if ln.split(b"\t")[5] in bins[rank])
+    out = orc.run_liftover(mine, bed_text) if mine else b""
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)      # host-side gather of the finished rows; no collective on the data path
+    if rank == 0:
+        q.put((shard.merge_outputs(order, gathered), orc.run_liftover(paf_text, bed_text)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_outputs_concatenate_in_emission_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_merge_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, whole = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert merged == whole and len(whole) > 0
+
+
 def test_lpt_bins_balance():
     from rustybam_b200 import shard
     lens = [248387328, 242696752, 201105948, 193574945, 182045439, 172126628, 160567428, 146259331, 150617247, 134758134, 135127769,
