@@ -18,6 +18,78 @@ namespace rbh {
 // ---------------------------------------------------------------------------------------------
 // myio.rs:41-64 — extension decides: .gz / .bgz -> inflate (zlib reads concatenated BGZF members), else plain
 // ---------------------------------------------------------------------------------------------
+static std::string read_plain(const std::string& path) {
+    std::string out;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw Panic("Error: cannot read input file " + path);
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (sz > 0) {
+        out.resize((size_t)sz);
+        if (fread(&out[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); throw Panic("short read on " + path); }
+    }
+    fclose(f);
+    return out;
+}
+
+// BGZF: a series of gzip members, each with a 'BC' extra subfield holding (block size - 1) and at most 64 KiB of
+// payload, ISIZE in the trailer.  Blocks are located serially (header hops), inflated in parallel (raw deflate).
+// Returns false if `raw` is not a well-formed BGZF file.
+static bool inflate_bgzf(const std::string& raw, std::string& text) {
+    struct Block { size_t cdata, clen, out_off, out_len; };
+    std::vector<Block> blocks;
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(raw.data());
+    const size_t n = raw.size();
+    size_t pos = 0, total = 0;
+    while (pos < n) {
+        if (n - pos < 18 || p[pos] != 0x1f || p[pos + 1] != 0x8b || p[pos + 2] != 8 || !(p[pos + 3] & 4)) return false;
+        const size_t xlen = p[pos + 10] | (p[pos + 11] << 8);
+        size_t x = pos + 12, xend = x + xlen, bsize = 0;
+        if (xend > n) return false;
+        while (x + 4 <= xend) {
+            const size_t slen = p[x + 2] | (p[x + 3] << 8);
+            if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = (size_t)(p[x + 4] | (p[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize == 0 || pos + bsize > n || bsize < xlen + 20) return false;
+        const size_t isize = (size_t)p[pos + bsize - 4] | ((size_t)p[pos + bsize - 3] << 8) | ((size_t)p[pos + bsize - 2] << 16) |
+                             ((size_t)p[pos + bsize - 1] << 24);
+        blocks.push_back(Block{xend, bsize - xlen - 20, total, isize});
+        total += isize;
+        pos += bsize;
+    }
+    text.resize(total);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> ok{true};
+    auto work = [&] {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= blocks.size() || !ok.load()) break;
+            const Block& b = blocks[k];
+            if (b.out_len == 0) continue;
+            z_stream zs;
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, -15) != Z_OK) { ok = false; break; }
+            zs.next_in = const_cast<Bytef*>(p + b.cdata);
+            zs.avail_in = (uInt)b.clen;
+            zs.next_out = reinterpret_cast<Bytef*>(&text[b.out_off]);
+            zs.avail_out = (uInt)b.out_len;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0) { ok = false; break; }
+        }
+    };
+    const unsigned nt = (unsigned)std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), std::max<size_t>(1, blocks.size() / 16));
+    if (nt <= 1) work();
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(work);
+        for (auto& th : pool) th.join();
+    }
+    return ok.load();
+}
+
 std::string read_all(const std::string& path) {
     auto ends_with = [&](const char* suf) {
         const size_t n = strlen(suf);
@@ -28,6 +100,12 @@ std::string read_all(const std::string& path) {
         std::ostringstream ss;
         ss << std::cin.rdbuf();
         return ss.str();
+    }
+    if (ends_with(".bgz")) {  // BGZF (myio.rs:56-60): independent blocks -> inflated on all host threads
+        std::string raw = read_plain(path);
+        std::string text;
+        if (inflate_bgzf(raw, text)) return text;
+        // not BGZF after all: fall through to the serial gzip reader
     }
     if (ends_with(".gz") || ends_with(".bgz")) {
         gzFile f = gzopen(path.c_str(), "rb");
@@ -43,18 +121,9 @@ std::string read_all(const std::string& path) {
         gzclose(f);
         return out;
     }
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) throw Panic("Error: cannot read input file " + path);
-    fseek(f, 0, SEEK_END);
-    const long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    if (sz > 0) {
-        out.resize((size_t)sz);
-        if (fread(&out[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); throw Panic("short read on " + path); }
-    }
-    fclose(f);
-    return out;
+    return read_plain(path);
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // PAF

@@ -30,6 +30,14 @@ void* rbh_paf_from_text(const char* text, size_t n, char* err, size_t err_cap) {
         return nullptr;
     }
 }
+// file contents as the readers of myio.rs:41-64 deliver them (plain / .gz / .bgz); nullptr on I/O errors
+char* rbh_read_all(const char* path, size_t* n) {
+    try {
+        return dup_str(read_all(path), n);
+    } catch (const Panic&) {
+        return nullptr;
+    }
+}
 void rbh_paf_view(void* paf, rb_records* out) { *out = static_cast<Paf*>(paf)->view(); }
 uint64_t rbh_paf_size(void* paf) { return static_cast<Paf*>(paf)->size(); }
 uint64_t rbh_paf_skipped(void* paf) { return static_cast<Paf*>(paf)->skipped; }

@@ -43,6 +43,8 @@ def load():
     lib.rbh_windows_free.argtypes = [C.c_void_p]
     lib.rbh_tiling_bed_text.restype = C.c_void_p
     lib.rbh_tiling_bed_text.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.POINTER(C.c_size_t)]
+    lib.rbh_read_all.restype = C.c_void_p
+    lib.rbh_read_all.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
     lib.rbh_free_str.argtypes = [C.c_void_p]
     lib.rbh_fmt_f32.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
     _lib = lib
@@ -53,6 +55,15 @@ def _take(p, n):
     s = C.string_at(p, n.value)
     load().rbh_free_str(p)
     return s
+
+
+def read_all(path: str) -> bytes:
+    """File contents through the host reader (plain, .gz, .bgz — BGZF blocks are inflated on all host threads)."""
+    n = C.c_size_t()
+    p = load().rbh_read_all(path.encode(), C.byref(n))
+    if not p:
+        raise OSError(f"cannot read {path}")
+    return _take(p, n)
 
 
 class HostPanic(Exception):

@@ -96,3 +96,33 @@ def test_fmt_f32_matches_oracle():
     vals = (np.float32(100.0) * eq.astype(np.float32)) / np.maximum(tot, 1).astype(np.float32)
     for v in list(vals) + [np.float32("nan"), np.float32(0), np.float32(100), np.float32(1e-7), np.float32(50)]:
         assert bamstats.fmt_f32(v) == orc.fmt_f32(float(v)), v
+
+
+def _write_bgzf(path, data: bytes, block=60000):
+    """Minimal BGZF writer (SAM spec 4.1): gzip members with a 'BC' extra field, ISIZE trailer, empty EOF block."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        for off in list(range(0, len(data), block)) + [None]:
+            chunk = b"" if off is None else data[off:off + block]
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            cdata = co.compress(chunk) + co.flush()
+            bsize = len(cdata) + 25  # 12 header + 6 extra + cdata + 8 trailer - 1
+            f.write(b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize))
+            f.write(cdata + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+
+
+def test_host_reader_inflates_bgzf_blocks_in_parallel(tmp_path):
+    # myio.rs:33-40: .paf, .paf.gz and .paf.bgz hold the same lines; the .bgz reader works block by block on all threads
+    import gzip
+    from rustybam_b200 import hostlib
+    text = orc.golden_paf()
+    bgz, gz, plain = tmp_path / "a.paf.bgz", tmp_path / "a.paf.gz", tmp_path / "a.paf"
+    _write_bgzf(bgz, text)
+    gz.write_bytes(gzip.compress(text))
+    plain.write_bytes(text)
+    assert hostlib.read_all(str(bgz)) == text
+    assert hostlib.read_all(str(gz)) == text
+    assert hostlib.read_all(str(plain)) == text
+    (tmp_path / "b.paf.bgz").write_bytes(gzip.compress(text))  # a plain gzip stream behind a .bgz name still reads
+    assert hostlib.read_all(str(tmp_path / "b.paf.bgz")) == text
