@@ -242,7 +242,8 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
         __syncthreads();
         const uint64_t base = s_base;
         const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_text);
-        uint32_t seen_clip = 0;
+        uint32_t seen_codes = 0;                            // bit c set: an op of code c was seen
+        uint32_t* out_ops = ops + base;
         for (uint32_t q = tid; q < total; q += TOK_THREADS) {
             const uint32_t e = s_pos[q];                    // op character at tile byte e
             const uint32_t a = (e + 8) >> 2, sh = ((e + 8) & 3) * 8;
@@ -259,18 +260,20 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
             }
             const uint32_t code = s_lut[s_text[16 + e]];
             uint32_t len;
-            if (nd == 0u || nd == 8u || code == 15u) {      // rare: empty length, >= 8 digits, bad op character
+            if (nd - 1u >= 7u || code == 15u) {             // rare: empty length, >= 8 digits, bad op character
                 uint32_t ecode = RE_CIGAR_PARSE;
                 len = 0;
                 if (code == 15u || !exact_len(text, tbase + e, len, ecode)) { report(err.tok, tbase + e, ecode); len = 0; }
             } else {
-                hi &= (nd >= 4u) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8u * (4u - nd)));
-                len = parse4(hi);
-                if (nd > 4u) len += parse4(lo & (0xFFFFFFFFu << (8u * (8u - nd)))) * 10000u;
+                // zero the bytes in front of the digit run (they read as leading zeros): one 64-bit mask
+                const unsigned long long x = (((unsigned long long)hi << 32) | lo) & (~0ull << (8u * (8u - nd)));
+                len = parse4((uint32_t)(x >> 32));
+                if (nd > 4u) len += parse4((uint32_t)x) * 10000u;
             }
-            seen_clip |= (code == OP_S) | (code == OP_H);
-            ops[base + q] = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
+            seen_codes |= 1u << code;
+            out_ops[q] = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
         }
+        const uint32_t seen_clip = seen_codes & ((1u << OP_S) | (1u << OP_H));
         if (seen_clip) atomicOr(misc_flags, 1u);
     }
 }
@@ -1352,14 +1355,18 @@ __device__ __forceinline__ P put_text(P p, const uint8_t* __restrict__ src, uint
     const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
     uint32_t lo = __ldg(w);
-    for (uint32_t i = 0; i < n; i += 4) {
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
         const uint32_t hi = __ldg(++w);
         const uint32_t x = __funnelshift_r(lo, hi, sh);
         lo = hi;
+        p[i] = (uint8_t)x; p[i + 1] = (uint8_t)(x >> 8); p[i + 2] = (uint8_t)(x >> 16); p[i + 3] = (uint8_t)(x >> 24);
+    }
+    if (i < n) {
+        const uint32_t x = __funnelshift_r(lo, __ldg(++w), sh);
         p[i] = (uint8_t)x;
         if (i + 1 < n) p[i + 1] = (uint8_t)(x >> 8);
         if (i + 2 < n) p[i + 2] = (uint8_t)(x >> 16);
-        if (i + 3 < n) p[i + 3] = (uint8_t)(x >> 24);
     }
     return p + n;
 }
