@@ -269,7 +269,9 @@ class Context:
         n = int(out.n_out)
         res = dict(n_out=n, n_pairs=int(out.n_pairs), paf_nbytes=int(out.paf_nbytes))
         if want & WANT_TEXT:
-            res["paf_text"] = C.string_at(out.paf_text, int(out.paf_nbytes)) if out.paf_nbytes else b""
+            nb = int(out.paf_nbytes)  # (ctypes.string_at takes a C int: texts of 2 GiB and more go through a buffer view)
+            addr = C.cast(out.paf_text, C.c_void_p).value
+            res["paf_text"] = bytes(memoryview((C.c_ubyte * nb).from_address(addr))) if nb else b""
             res["line_off"] = _np(out.line_off, n + 1, np.uint64)
         if want & WANT_NUMERIC:
             for k in ("q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len"):
