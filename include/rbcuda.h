@@ -180,6 +180,10 @@ int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats);
  * within the call; the id of a row is its record's id (empty, or the "_TO.." suffix of the indel strip) */
 int rb_break_paf(rb_ctx* ctx, const rb_records* recs, uint32_t max_size, int policy, uint32_t want, rb_lift_out* out,
                  rb_stats_out* stats /* nullable */);
+/* replaces the loop of `rb invert` (main.rs:176-182, paf::paf_swap_query_and_target paf.rs:1050-1094): one row per record in
+ * FILE order — query and target columns swapped, I and D exchanged, the ops reversed on the '-' strand; nothing is stripped or
+ * merged; nmatch / aln_len are the ones check_integrity infers from the CIGAR (paf.rs:825-857); id empty; win_idx = 0 */
+int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* out);
 void rb_free_lift_out(rb_ctx* ctx, rb_lift_out* out);
 void rb_free_stats_out(rb_ctx* ctx, rb_stats_out* stats);
 

@@ -798,6 +798,14 @@ std::string run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int 
     return out;
 }
 
+// main.rs:176-182 — `rb invert`: every record as read (integrity-checked, not stripped), query and target swapped
+std::string run_invert(const char* paf, size_t paf_n) {
+    Paf p = Paf::from_text(paf, paf_n);
+    std::string out;
+    for (const PafRecord& r : p.records) { out += paf_swap_query_and_target(r).to_line(); out += '\n'; }
+    return out;
+}
+
 std::string run_stats(const char* paf, size_t paf_n, bool qbed) {
     std::string out = stats_header(qbed);
     Paf p = Paf::from_text(paf, paf_n);

@@ -145,5 +145,6 @@ std::string run_liftover(const char* paf, size_t paf_n, const char* bed, size_t 
                          bool largest, int policy, int threads);
 std::string run_stats(const char* paf, size_t paf_n, bool qbed);
 std::string run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int policy);
+std::string run_invert(const char* paf, size_t paf_n);
 
 }  // namespace orc

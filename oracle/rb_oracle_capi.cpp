@@ -50,6 +50,16 @@ int orc_run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int poli
     }
 }
 
+int orc_run_invert(const char* paf, size_t paf_n, char** out, size_t* out_n, char* err, size_t err_cap) {
+    try {
+        *out = dup_out(run_invert(paf, paf_n), out_n);
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    }
+}
+
 int orc_run_stats(const char* paf, size_t paf_n, int qbed, char** out, size_t* out_n, char* err,
                   size_t err_cap) {
     try {

@@ -23,7 +23,7 @@ LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
     "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_set_slicing", "rb_ctx_kernel_times",
-    "rb_liftover", "rb_stats", "rb_break_paf", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
+    "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
     "rb_host_unregister",
 ]
@@ -93,6 +93,7 @@ def load():
                                 C.POINTER(RbStatsOut)]
     lib.rb_stats.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.POINTER(RbStatsOut)]
     lib.rb_break_paf.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_uint32, C.c_int, C.c_uint32, C.POINTER(RbLiftOut), C.POINTER(RbStatsOut)]
+    lib.rb_invert.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_uint32, C.POINTER(RbLiftOut)]
     lib.rb_batch_break.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(RbSummary)]
     lib.rb_free_lift_out.argtypes = [C.c_void_p, C.POINTER(RbLiftOut)]
     lib.rb_free_stats_out.argtypes = [C.c_void_p, C.POINTER(RbStatsOut)]
@@ -248,6 +249,14 @@ class Context:
         self.lib.rb_free_lift_out(self.h, C.byref(out))
         if stats:
             self.lib.rb_free_stats_out(self.h, C.byref(st))
+        return res
+
+    def invert(self, recs: Records, want=WANT_TEXT | WANT_NUMERIC, copy=True):
+        """rb_invert: every record with query and target swapped (paf.rs:1050-1094), rows in file order."""
+        out = RbLiftOut()
+        self._check(self.lib.rb_invert(self.h, C.byref(recs.c), want, C.byref(out)))
+        res = self._collect_lift(out, None, want) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
+        self.lib.rb_free_lift_out(self.h, C.byref(out))
         return res
 
     def stats(self, recs: Records, copy=True):

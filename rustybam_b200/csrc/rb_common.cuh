@@ -249,6 +249,7 @@ struct PairRes {          // 112 bytes
     uint32_t equal, diff, ins, del, ins_ev, del_ev, matches;  // bamstats.rs:107-127 on the trimmed CIGAR
 };
 static_assert(sizeof(PairRes) == 112, "PairRes layout");
-enum : uint32_t { PK_DROP = 0, PK_TRIM = 1, PK_EARLY = 2 };
+enum : uint32_t { PK_DROP = 0, PK_TRIM = 1, PK_EARLY = 2,
+                  PK_WHOLE = 3 };  // rb invert: the record as it is; k_serialise leaves the CIGAR bytes of the row to k_whole_text
 
 }  // namespace rb

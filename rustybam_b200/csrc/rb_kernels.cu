@@ -814,7 +814,18 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     Ctr full = ctr_zero();
     if (ri.op_end > ri.op_first) full = ctr_range(v, ri, ri.op_first, ri.op_end, acc);
     if (full.aux & 0x80000000u) report(err.rec, r, RE_UNSUPPORTED);
-    if ((uint64_t)full.T != t_en_in - ri.t_st || (uint64_t)full.Q != ri.q_en0 - ri.q_st0) report(err.rec, r, RE_INTEGRITY);
+    uint64_t span_t = full.T, span_q = full.Q;
+    if (mode == 0 && in.no_text) {
+        // `rb invert`: the reference checks the record as read, before the swap (paf.rs:70) — undo the I<->D exchange
+        // (N and S keep their side, so the swapped sums are not simply the other span)
+        const uint64_t both = (uint64_t)full.M + full.EQ + full.X;
+        const uint64_t n_skip = (uint64_t)full.T - both - full.D, n_clip = (uint64_t)full.Q - both - full.I;  // N, S bases
+        span_t = both + full.I + n_skip;  // what the file's CIGAR spends on the file's target (= our query columns): M = X D N
+        span_q = both + full.D + n_clip;  // ... and on the file's query: M = X I S
+        if (span_t != ri.q_en0 - ri.q_st0 || span_q != t_en_in - ri.t_st) report(err.rec, r, RE_INTEGRITY);
+    } else if (span_t != t_en_in - ri.t_st || span_q != ri.q_en0 - ri.q_st0) {
+        report(err.rec, r, RE_INTEGRITY);
+    }
     if (full.aux & AUX_CNT) ri.flags |= RF_SLOW;
     if (!in.no_text && (uint64_t)full.TXT == in.cigar_off[r + 1] - in.cigar_off[r]) ri.flags |= RF_CANON;  // no op is spelled with leading zeros
     if (ri.op_end > ri.op_first) {  // the sampled count stops at the last chunk boundary: look at the tail ops too
@@ -832,6 +843,30 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
     }
     ri.tot = (ri.eo0 == ri.op_first && ri.eo1 == ri.op_end) ? full : ctr_range(v, ri, ri.eo0, ri.eo1, acc);
     recs[r] = ri;
+}
+
+// `rb invert` (main.rs:176-182): one row per record, the whole (already inverted) CIGAR, nothing stripped or merged.
+// Fills what k_lift would have: PairRes, line lengths, the identity pair list and the per-block plans of the serialiser.
+__global__ void __launch_bounds__(128)
+k_whole_rows(uint32_t n_rec, const RecInfo* __restrict__ recs, PairRes* __restrict__ res, uint32_t* __restrict__ line_len,
+             uint64_t* __restrict__ pair_off, LiftPlan* __restrict__ plans) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) pair_off[n_rec] = n_rec;
+    if (r >= n_rec) return;
+    const RecInfo ri = recs[r];
+    PairRes pr;
+    pair_clear(pr);
+    pair_early(ri, pr);
+    pr.kind = PK_WHOLE;
+    if (ri.op_end <= ri.op_first) { pr.si = 1; pr.ei = 0; pr.cg_bytes = 0; pr.mid_len = 0; }  // "cg:Z:" with nothing behind it
+    res[r] = pr;
+    line_len[r] = ri.line_const + line_var_bytes(pr, 0u);
+    pair_off[r] = r;
+    if (r % LIFT_THREADS == 0) {
+        LiftPlan pl;
+        pl.k0 = r; pl.uniform = 0u; pl.c_lo = pl.c_hi = ~0ull;
+        plans[r / LIFT_THREADS] = pl;
+    }
 }
 
 // Window table checks (the host never walks the 3 M-row table): bit 0 = not sorted by (t_id, st) or t_id out of
@@ -1447,7 +1482,8 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             const RecInfo& ri = a.recs[r];
             uint8_t* q = s_buf + shift + (my_off - byte0);
             q = put_header(q, a, ri, pr, w);
-            q = put_cigar_seq(q, a, ri, pr);
+            if (pr.kind == PK_WHOLE) q += pr.cg_bytes;  // k_whole_text fills these bytes afterwards
+            else q = put_cigar_seq(q, a, ri, pr);
             *q = '\n';
         }
         __syncthreads();
@@ -1484,7 +1520,9 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         }
         __syncwarp();
         dst += hdr;
-        if ((ri.flags & RF_SLOW) && lp.kind == PK_TRIM) {
+        if (lp.kind == PK_WHOLE) {
+            // the CIGAR of a whole-record row is written by k_whole_text, 32 ops per warp across the whole grid
+        } else if ((ri.flags & RF_SLOW) && lp.kind == PK_TRIM) {
             if (lane == 0) put_cigar_seq(dst, a, ri, lp);
         } else if (ri.flags & RF_CANON) {
             // untouched ops come straight from the input text: one coalesced copy by the whole warp
@@ -1535,9 +1573,71 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
     }
 }
 
+// rb invert: the CIGAR text of the whole-record rows.  One warp per 32-op chunk of the (already inverted) op array:
+// where an op's text starts inside its row is the TXT counter in front of it — the chunk's sample plus a warp scan —
+// so 50 M ops are formatted by as many lanes instead of one warp crawling along each 65 k-op row.  Runs after
+// k_serialise (which wrote the 12 columns, "cg:Z:" and the newline of every row).
+constexpr int WT_THREADS = 256;
+__global__ void __launch_bounds__(WT_THREADS)
+k_whole_text(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_off, uint32_t n_rec, const RecInfo* __restrict__ recs,
+             const Ctr* __restrict__ samples, const uint64_t* __restrict__ line_off, uint8_t* __restrict__ out_text) {
+    __shared__ uint8_t s_stage[WT_THREADS / 32][32 * 11 + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t c = (uint64_t)blockIdx.x * (WT_THREADS / 32) + warp;
+    const uint64_t n_ops = op_off[n_rec];
+    const uint64_t k0 = c << SAMPLE_LOG2;
+    if (k0 >= n_ops) return;
+    const uint64_t k1 = (k0 + SAMPLE < n_ops) ? k0 + SAMPLE : n_ops;
+    const uint64_t k = k0 + lane;
+    auto rec_of = [&](uint64_t op) {  // largest r with op_off[r] <= op (records without ops are skipped over)
+        uint32_t lo = 0, hi = n_rec;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (op_off[mid] <= op) lo = mid + 1; else hi = mid;
+        }
+        return lo - 1;
+    };
+    // where the CIGAR of row r starts: the row ends with it and a newline
+    auto body_of = [&](uint32_t r) { return line_off[r + 1] - 1 - recs[r].tot.TXT; };
+    const uint32_t r0 = rec_of(k0);
+    uint32_t w = 0, nb = 0;
+    if (k < k1) { w = ops[k]; nb = ndigits32(op_len(w)) + 1u; }
+    if (op_off[r0 + 1] >= k1) {  // the whole chunk lies in one record (the usual case)
+        uint32_t inc = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t base = (k0 > op_off[r0]) ? samples[c * SUBS].TXT : 0u;
+        if (nb) put_op(&s_stage[warp][inc - nb], op_len(w), op_code(w));
+        __syncwarp();
+        uint8_t* dst = out_text + body_of(r0) + base;
+        for (uint32_t i = lane; i < tot; i += 32) dst[i] = s_stage[warp][i];
+        return;
+    }
+    // a chunk that holds a record boundary: every lane for itself
+    if (k >= k1) return;
+    const uint32_t r = rec_of(k);
+    const uint64_t a = op_off[r];
+    uint64_t j = a;
+    uint32_t pos = 0;
+    if (k0 > a) { j = k0; pos = samples[c * SUBS].TXT; }
+    for (; j < k; j++) pos += ndigits32(op_len(ops[j])) + 1u;
+    put_op(out_text + body_of(r) + pos, op_len(w), op_code(w));
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+void launch_whole_text(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, const RecInfo* recs, const Ctr* samples,
+                       const uint64_t* line_off, uint8_t* out_text, uint64_t n_ops_bound, cudaStream_t s) {
+    if (n_rec == 0 || n_ops_bound == 0 || out_text == nullptr) return;
+    const uint64_t chunks = (n_ops_bound + SAMPLE - 1) / SAMPLE;
+    k_whole_text<<<(unsigned)((chunks + WT_THREADS / 32 - 1) / (WT_THREADS / 32)), WT_THREADS, 0, s>>>(ops, op_off, n_rec, recs, samples,
+                                                                                                    line_off, out_text);
+}
 void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsigned long long* tile_state, unsigned int* ticket,
                      ErrSlots err, uint32_t* misc_flags, cudaStream_t s) {
     if (n_tiles == 0) return;
@@ -1584,6 +1684,10 @@ void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32
                      RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s) {
     if (in.n_rec == 0) return;
     k_rec_prep<<<(in.n_rec + 127) / 128, 128, 0, s>>>(mode, in, op_off, ops, samples, win, recs, pair_cnt, st, err);
+}
+void launch_whole_rows(uint32_t n_rec, const RecInfo* recs, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans,
+                       cudaStream_t s) {
+    k_whole_rows<<<n_rec / 128 + 1, 128, 0, s>>>(n_rec, recs, res, line_len, pair_off, plans);
 }
 void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s) {
     k_pair_scan<<<1, 1024, 0, s>>>(pair_cnt, rec_order, n_rec, pair_off);

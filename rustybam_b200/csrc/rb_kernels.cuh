@@ -122,6 +122,12 @@ struct LiftPlan {
     uint32_t uniform;   // 1: every pair of the block belongs to that record
     uint64_t c_lo, c_hi;  // chunks of the first start boundary / last end boundary (~0: not applicable)
 };
+// rb invert: the CIGAR bytes of the whole-record rows (after launch_serialise)
+void launch_whole_text(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, const RecInfo* recs, const Ctr* samples,
+                       const uint64_t* line_off, uint8_t* out_text, uint64_t n_ops_bound, cudaStream_t s);
+// rb invert: one whole-record row per record (fills PairRes, line lengths, pair list, plans)
+void launch_whole_rows(uint32_t n_rec, const RecInfo* recs, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans,
+                       cudaStream_t s);
 void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                       const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s);
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,

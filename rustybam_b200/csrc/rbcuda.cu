@@ -896,7 +896,8 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
 }
 
 // plan -> lift (or combine) -> line scan -> [host: output sizes] -> serialise; shared by liftover and break-paf
-static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, bool fused, uint32_t want, int with_stats, uint64_t P,
+enum : int { TAIL_SEARCH = 0, TAIL_COMBINE = 1, TAIL_WHOLE = 2 };  // who fills PairRes: k_lift, k_combine, k_whole_rows (rb invert)
+static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail, uint32_t want, int with_stats, uint64_t P,
                      uint64_t n_ops, rb_summary* summary) {
     cudaStream_t s = ctx->stream;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
@@ -905,12 +906,16 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, bool fus
     const uint32_t n = b->n_rec;
     int rc = RB_OK;
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
-    {
+    if (tail != TAIL_WHOLE) {
         KScope k(ctx, "k_lift_plan");
         launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
                          b->plans.as<LiftPlan>(), s);
     }
-    if (fused) {
+    if (tail == TAIL_WHOLE) {
+        KScope k(ctx, "k_whole_rows");
+        launch_whole_rows(n, b->recs.as<RecInfo>(), b->pair_res.as<PairRes>(), b->line_len.as<uint32_t>(), b->pair_off.as<uint64_t>(),
+                          b->plans.as<LiftPlan>(), s);
+    } else if (tail == TAIL_COMBINE) {
         KScope k(ctx, "k_combine");
         launch_combine(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(), win,
                        b->names_off.as<uint64_t>(), b->half_s.as<HalfS>(), b->half_e.as<HalfE>(), b->pair_res.as<PairRes>(),
@@ -942,7 +947,9 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, bool fus
     if (with_stats) CU(b->out_stats.ensure(n_out * 40 + 64));
     // few, long rows (e.g. 100 kb windows: ~4 KB per row): 8 rows per block instead of 128, so the warp-per-line path
     // has enough blocks to fill the GPU
-    const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? 8u : (uint32_t)SER_LINES;
+    // (whole-record rows of rb invert: 4 per block, a warp each)
+    const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? (tail == TAIL_WHOLE ? 4u : 8u)
+                                                                                               : (uint32_t)SER_LINES;
     {
         KScope k(ctx, "k_serialise");
         launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
@@ -952,6 +959,11 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, bool fus
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                          (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
                          b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, s);
+    }
+    if (tail == TAIL_WHOLE && (want & RB_WANT_TEXT)) {
+        KScope k(ctx, "k_whole_text");
+        launch_whole_text(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(),
+                          b->line_off.as<uint64_t>(), b->out_text.as<uint8_t>(), b->ops_bound, s);
     }
     if (P == 0 && (want & RB_WANT_TEXT)) CU(cudaMemsetAsync(b->out_line_off.p, 0, 8, s));
     CU(cudaGetLastError());
@@ -1039,7 +1051,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                             b->pair_win.as<uint32_t>(), s);
         win.pair_win = b->pair_win.as<uint32_t>();
     }
-    return lift_tail(ctx, b, win, policy, fused, want, with_stats, P, n_ops, summary);
+    return lift_tail(ctx, b, win, policy, fused ? TAIL_COMBINE : TAIL_SEARCH, want, with_stats, P, n_ops, summary);
 }
 
 // `rb break-paf` on a resident batch (uploaded WITHOUT windows): every record is cut at its insertions / deletions
@@ -1137,7 +1149,54 @@ int rb_batch_break(rb_ctx* ctx, rb_batch* b, uint32_t max_size, int policy, uint
     CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
     CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
     CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));  // the line scan reuses the ticket of the break-op scan
-    return lift_tail(ctx, b, win, policy, false, want, with_stats, P, n_ops, summary);
+    return lift_tail(ctx, b, win, policy, TAIL_SEARCH, want, with_stats, P, n_ops, summary);
+}
+
+// `rb invert` on a batch uploaded by rb_invert (columns swapped, ctx->invert set): tokenise + invert the ops, counters and
+// integrity of every record, then one whole-record row each
+static int batch_invert(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_summary* summary) {
+    if (!ctx || !b) return RB_ERR_BAD_ARG;
+    if (!b->invert) return fail(ctx, RB_ERR_BAD_ARG, "batch_invert wants a batch uploaded by rb_invert");
+    if (b->wsrc || b->n_win) return fail(ctx, RB_ERR_BAD_ARG, "batch_invert wants a batch uploaded without windows");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    b->have_lift = false;
+    int rc = run_tok(ctx, b);
+    if (rc != RB_OK) return rc;
+    rc = run_scan(ctx, b, nullptr);
+    if (rc != RB_OK) return rc;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    const uint32_t n = b->n_rec;
+    CU(b->out_stats.ensure((size_t)n * 40 + 64));
+    {
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(0, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), WinView{},
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), stats_view(b, n), err, s);
+    }
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC).go(s);
+    CU(cudaStreamSynchronize(s));
+    b->busy = false;
+    if ((uint32_t)hs[3] & 1u) {
+        launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, err, s);
+        Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).go(s);
+        CU(cudaStreamSynchronize(s));
+    }
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) { flush_times(ctx); return rc; }
+    const uint64_t n_ops = hs[2], P = n;
+    CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
+    CU(b->line_len.ensure(P * 4 + 64));
+    CU(b->line_off.ensure((P + 1) * 8 + 64));
+    CU(b->out_idx.ensure((P + 1) * 8 + 64));
+    CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
+    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
+    CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
+    WinView win{};
+    win.from_record = 1u;  // a row's id is its record's (empty)
+    return lift_tail(ctx, b, win, RB_POLICY_RIGHTMOST, TAIL_WHOLE, want, 0, P, n_ops, summary);
 }
 
 static int download_stats(rb_ctx* ctx, rb_batch* b, uint64_t n, rb_stats_out* st) {
@@ -1582,6 +1641,28 @@ int rb_break_paf(rb_ctx* ctx, const rb_records* recs, uint32_t max_size, int pol
     rc = rb_batch_break(ctx, b, max_size, policy, want, stats != nullptr, nullptr);
     if (rc != RB_OK) return rc;
     return rb_batch_download_lift(ctx, b, want, out, stats);
+}
+
+// replaces the `for rec in &paf.records { println!("{}", paf_swap_query_and_target(rec)); }` loop of `rb invert`
+// (main.rs:176-182, paf.rs:1050-1094)
+int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* out) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out || !recs) return fail(ctx, RB_ERR_BAD_ARG, "recs / out is null");
+    cudaSetDevice(ctx->device);
+    if (!ctx->scratch) ctx->scratch = new rb_batch();
+    rb_batch* b = ctx->scratch;
+    rb_records swapped = *recs;  // the column pointers change places; the ops are inverted on the device after tokenising
+    std::swap(swapped.q_len, swapped.t_len); std::swap(swapped.q_st, swapped.t_st); std::swap(swapped.q_en, swapped.t_en);
+    std::swap(swapped.q_id, swapped.t_id);
+    struct InvertScope { rb_ctx* c; ~InvertScope() { c->invert = false; } } invert_scope{ctx};
+    ctx->invert = true;
+    b->file_order = true;
+    int rc = upload_into(ctx, b, &swapped, nullptr);
+    b->file_order = false;
+    if (rc != RB_OK) return rc;
+    rc = batch_invert(ctx, b, want & ~RB_WANT_QBED, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_lift(ctx, b, want & ~RB_WANT_QBED, out, nullptr);
 }
 
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {

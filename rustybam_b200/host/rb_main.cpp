@@ -3,6 +3,7 @@
 //     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]     (--qbed: inversion on the GPU; --largest: host filter)
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
 //     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
+//     rb [-t N] invert [PAF|-]                          (src/cli.rs:89-94, main.rs:176-182)
 // Text (plain / .gz / .bgz / stdin) is read and split on the host; CIGAR tokenising, liftover,
 // trimming, serialisation and identity counting run on the B200 through include/rbcuda.h.
 // Exit status 101 where the reference panics.  There is no CPU fallback: without an sm_100
@@ -16,7 +17,7 @@
 
 static int usage() {
     fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n"
-                    "       rb [-t N] break-paf [--max-size N] [PAF]\n");
+                    "       rb [-t N] break-paf [--max-size N] [PAF]\n       rb [-t N] invert [PAF]\n");
     return 2;
 }
 
@@ -39,7 +40,8 @@ int main(int argc, char** argv) {
         else input = a;
     }
     const bool brk = (cmd == "break-paf" || cmd == "breakpaf" || cmd == "bp");
-    if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk) return usage();
+    const bool inv = (cmd == "invert");
+    if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk && !inv) return usage();
     int status = 0;
     rb_ctx* ctx = rb_ctx_create(nullptr, 0, &status);
     if (!ctx) {
@@ -66,6 +68,16 @@ int main(int argc, char** argv) {
             rb_records recs = paf.view();
             rb_lift_out out{};
             rc = rb_break_paf(ctx, &recs, (uint32_t)max_size, policy, RB_WANT_TEXT, &out, nullptr);
+            if (rc == RB_OK) {
+                fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                rb_free_lift_out(ctx, &out);
+            }
+        } else if (inv) {
+            rbh::Paf paf = rbh::Paf::from_file(input);
+            if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
+            rb_records recs = paf.view();
+            rb_lift_out out{};
+            rc = rb_invert(ctx, &recs, RB_WANT_TEXT, &out);
             if (rc == RB_OK) {
                 fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
                 rb_free_lift_out(ctx, &out);

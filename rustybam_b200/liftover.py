@@ -56,6 +56,22 @@ def break_paf_on_indels(ctx, paf: Paf, max_size=100, policy=POLICY_RIGHTMOST, st
         raise
 
 
+def paf_swap_query_and_target(ctx, paf: Paf, want=WANT_TEXT | WANT_NUMERIC):
+    """paf::paf_swap_query_and_target for every record (src/paf.rs:1050-1094, driver src/main.rs:176-182) on the GPU:
+    res["paf_text"] is what `rb invert` prints."""
+    try:
+        return ctx.invert(paf.pack(), want=want)
+    except RbError as e:
+        if e.code in REF_PANIC_CODES:
+            raise ReferencePanic(str(e)) from e
+        raise
+
+
+def run_invert(ctx, paf_text: bytes) -> bytes:
+    """`rb invert PAF`: stdout bytes."""
+    return paf_swap_query_and_target(ctx, Paf.from_text(paf_text), want=WANT_TEXT)["paf_text"]
+
+
 def run_break_paf(ctx, paf_text: bytes, max_size=100, policy=POLICY_RIGHTMOST) -> bytes:
     """`rb break-paf --max-size N PAF`: stdout bytes."""
     return break_paf_on_indels(ctx, Paf.from_text(paf_text), max_size, policy, stats=False, want=WANT_TEXT)["paf_text"]

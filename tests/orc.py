@@ -49,6 +49,16 @@ def run_break_paf(paf: bytes, max_size=100, policy=RIGHTMOST) -> bytes:
     return _take(out, n)
 
 
+def run_invert(paf: bytes) -> bytes:
+    """`rb invert` (main.rs:176-182) on PAF text."""
+    out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
+    rc = lib().orc_run_invert(paf, C.c_size_t(len(paf)), C.byref(out), C.byref(n), err, C.c_size_t(512))
+    if rc == 101:
+        raise ReferencePanic(err.value.decode())
+    assert rc == 0
+    return _take(out, n)
+
+
 def run_stats(paf: bytes, qbed=False) -> bytes:
     out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
     rc = lib().orc_run_stats(paf, C.c_size_t(len(paf)), int(qbed), C.byref(out), C.byref(n), err, C.c_size_t(512))

@@ -372,6 +372,68 @@ def test_liftover_qbed_bundled_fixture(ctx):
     assert liftover.run_liftover(ctx, paf_text, bed_text, qbed=True) == want and want.count(b"\n") > 100
 
 
+# ---------------------------------------------------------------- rb invert: whole records, query <-> target
+def check_invert_against_oracle(ctx, paf_text):
+    want = orc.run_invert(paf_text)
+    res = liftover.paf_swap_query_and_target(ctx, Paf.from_text(paf_text))
+    assert res["paf_text"] == want
+    rows = [ln.split(b"\t") for ln in want.splitlines()]
+    assert res["n_out"] == len(rows)
+    assert [int(r[7]) for r in rows] == res["t_st"].tolist() and [int(r[3]) for r in rows] == res["q_en"].tolist()
+    assert [int(r[9]) for r in rows] == res["nmatch"].tolist() and [int(r[10]) for r in rows] == res["aln_len"].tolist()
+    assert res["rec_idx"].tolist() == list(range(len(rows)))
+    return want
+
+
+def test_invert_reference_vectors(ctx):
+    # paf.rs:1050-1065 on make_fake_paf_rec (paf.rs:1096-1100) and the two strands of one record
+    assert check_invert_against_oracle(ctx, b"Q\t10\t2\t10\t-\tT\t20\t12\t20\t3\t9\t60\tcg:Z:4M1I1D3=\n") == \
+        b"T\t20\t12\t20\t-\tQ\t10\t2\t10\t7\t9\t60\tid:Z:\tcg:Z:3=1I1D4M\n"
+    assert check_invert_against_oracle(ctx, b"Q\t10\t2\t10\t+\tT\t20\t12\t20\t3\t9\t60\tcg:Z:4M1I1D3=\n") == \
+        b"T\t20\t12\t20\t+\tQ\t10\t2\t10\t7\t9\t60\tid:Z:\tcg:Z:4M1D1I3=\n"
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_invert_random(ctx, seed):
+    # nothing is stripped or merged: leading / trailing indels, repeated classes, zero lengths, clips and N all pass through
+    paf_text, _ = gen.random_paf(900 + seed, n_contigs=4, recs_per_contig=8, style="all" if seed % 2 else "eqx", canonical=(seed < 4),
+                                 allow_zero=(seed >= 4), clips=(seed in (3, 7)), max_ops=300)
+    want = check_invert_against_oracle(ctx, paf_text)
+    if seed % 2:
+        # N and S keep their side across the swap, so the inverted record no longer passes check_integrity when it is read
+        # back: the reference panics on its own output, and so does the GPU path
+        with pytest.raises(orc.ReferencePanic):
+            orc.run_invert(want)
+        with pytest.raises(ReferencePanic):
+            liftover.run_invert(ctx, want)
+        return
+    # involution: inverting twice gives the records back (12 columns + cg; tags are dropped, nmatch / aln_len re-inferred)
+    assert liftover.run_invert(ctx, want) == orc.run_invert(want)
+    twice = liftover.run_invert(ctx, want).splitlines()
+    for a, b in zip(paf_text.splitlines(), twice):
+        fa, fb = a.split(b"\t"), b.split(b"\t")
+        assert fa[:9] == fb[:9] and fa[11] == fb[11]
+
+
+def test_invert_bundled_fixture(ctx):
+    want = check_invert_against_oracle(ctx, orc.golden_paf())
+    assert want.count(b"\n") == 249
+    assert liftover.run_invert(ctx, b"") == b""
+
+
+def test_invert_panics_like_the_reference(ctx):
+    # check_integrity at load (paf.rs:70) is on the record as read: spans that do not match the CIGAR panic ...
+    bad = b"Q\t30\t0\t13\t+\tT\t40\t5\t16\t0\t0\t60\tcg:Z:3S10=\n"
+    with pytest.raises(orc.ReferencePanic):
+        orc.run_invert(bad)
+    with pytest.raises(ReferencePanic):
+        liftover.run_invert(ctx, bad)
+    # ... while S / N, which keep their side across the swap, are fine when the spans are right
+    for ok in (b"Q\t30\t0\t13\t+\tT\t40\t5\t15\t0\t0\t60\tcg:Z:3S10=\n", b"Q\t30\t0\t10\t-\tT\t40\t5\t20\t0\t0\t60\tcg:Z:5=5N5=\n",
+               b"Q\t30\t0\t12\t-\tT\t40\t5\t15\t0\t0\t60\tcg:Z:2I4=1X3D2=3I\n"):
+        check_invert_against_oracle(ctx, ok)
+
+
 @pytest.mark.parametrize("seed", range(4))
 def test_liftover_largest(ctx, seed):
     paf_text, contigs = gen.random_paf(800 + seed, n_contigs=3, recs_per_contig=10)

@@ -227,6 +227,33 @@ def test_rb_cli_stats_on_many_rows(ctx, full):
     assert got == orc.run_stats(sub)
 
 
+def test_full_scale_invert_properties(ctx, full):
+    # rb invert over the whole ~50 M-op PAF: one row per record, in file order; the swap is an involution on the
+    # 12 columns + CIGAR, and a fixed point of invert . invert is reached after one application (canonical spelling)
+    res = ctx.invert(full, want=capi.WANT_TEXT | capi.WANT_NUMERIC)
+    assert res["n_out"] == full.n_rec and res["rec_idx"].tolist() == list(range(full.n_rec))
+    c = full.c
+    n = full.n_rec
+    assert res["q_st"].tolist() == [c.t_st[i] for i in range(n)] and res["t_en"].tolist() == [c.q_en[i] for i in range(n)]
+    rec_stats = ctx.stats(full)
+    assert (res["nmatch"] == rec_stats["equal"].astype(np.uint64) + rec_stats["diff"]).all()
+    once = res["paf_text"]
+    twice = ctx.invert(hostlib.HostPaf.from_text(once), want=capi.WANT_TEXT)["paf_text"]
+    thrice = ctx.invert(hostlib.HostPaf.from_text(twice), want=capi.WANT_TEXT)["paf_text"]
+    assert thrice == once and twice != once
+    # twice == the input records (same 9 leading columns, mapq and CIGAR; nmatch / aln_len re-inferred)
+    orig = full.text().split(b"\n")
+    back = twice.split(b"\n")
+    assert len(orig) == len(back)
+    for a, b in zip(orig[:-1], back[:-1]):
+        fa, fb = a.split(b"\t"), b.split(b"\t")
+        assert fa[:9] == fb[:9] and fa[11] == fb[11] and fa[-1] == fb[-1]
+    # the stats of an inverted record are the record's with ins <-> del
+    inv_stats = ctx.stats(hostlib.HostPaf.from_text(once))
+    assert (inv_stats["ins"] == rec_stats["del"]).all() and (inv_stats["del_events"] == rec_stats["ins_events"]).all()
+    assert (inv_stats["equal"] == rec_stats["equal"]).all()
+
+
 def test_rb_cli_matches_oracle(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf_gz = os.path.join(ROOT, "tests", "golden", "asm_small.paf.gz")
@@ -239,6 +266,8 @@ def test_rb_cli_matches_oracle(tmp_path):
     assert big == orc.run_liftover(orc.golden_paf(), orc.golden_bed(), largest=True)
     broken = subprocess.run([rb, "break-paf", "--max-size", "100", paf_gz], capture_output=True, check=True).stdout
     assert broken == orc.run_break_paf(orc.golden_paf(), 100)
+    inverted = subprocess.run([rb, "invert", paf_gz], capture_output=True, check=True).stdout
+    assert inverted == orc.run_invert(orc.golden_paf())
     bad = tmp_path / "bad.paf"
     bad.write_bytes(b"Q\t10\t0\t8\t+\tT\t20\t0\t8\t0\t0\t60\tcg:Z:3D5=\n")
     r = subprocess.run([rb, "liftover", "--bed", bed, str(bad)], capture_output=True)

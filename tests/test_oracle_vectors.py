@@ -175,3 +175,22 @@ def test_q2_policies_differ_only_after_insertions():
     assert a.split("\t")[7] == "15" and a.endswith("cg:Z:3=")
     b = orc.trim_line(line, "T", 14, 18, "W", orc.EARLY_EXIT)
     assert b.split("\t")[7] in ("14", "15")
+
+
+def test_invert_known_answers():
+    # `rb invert` (main.rs:176-182, paf.rs:1050-1094).  The reference's only test of the swap (liftover.rs:327-360,
+    # check_invertible) has its body commented out, so these answers are worked by hand from the code: columns swapped,
+    # I <-> D, ops reversed on '-', nmatch / aln_len as check_integrity infers them at load (paf.rs:70, 825-857: M, X and =
+    # all count as matches), tags dropped, id empty
+    fake = b"Q\t10\t2\t10\t-\tT\t20\t12\t20\t3\t9\t60\ttp:A:P\tcg:Z:4M1I1D3=\n"  # make_fake_paf_rec (paf.rs:1096-1100)
+    assert orc.run_invert(fake) == b"T\t20\t12\t20\t-\tQ\t10\t2\t10\t7\t9\t60\tid:Z:\tcg:Z:3=1I1D4M\n"
+    assert orc.run_invert(fake.replace(b"\t-\t", b"\t+\t")) == b"T\t20\t12\t20\t+\tQ\t10\t2\t10\t7\t9\t60\tid:Z:\tcg:Z:4M1D1I3=\n"
+    # nothing is stripped or merged; S and N stay on their side
+    assert orc.run_invert(b"Q\t30\t0\t12\t-\tT\t40\t5\t15\t0\t0\t60\tcg:Z:2I4=1X3D2=3I\n") == \
+        b"T\t40\t5\t15\t-\tQ\t30\t0\t12\t7\t15\t60\tid:Z:\tcg:Z:3D2=3I1X4=2D\n"
+    assert orc.run_invert(b"Q\t30\t0\t13\t+\tT\t40\t5\t15\t0\t0\t60\tcg:Z:3S10=\n") == b"T\t40\t5\t15\t+\tQ\t30\t0\t13\t10\t13\t60\tid:Z:\tcg:Z:3S10=\n"
+    # applied twice it gives the record back
+    twice = orc.run_invert(orc.run_invert(fake))
+    assert twice == b"Q\t10\t2\t10\t-\tT\t20\t12\t20\t7\t9\t60\tid:Z:\tcg:Z:4M1I1D3=\n"
+    with pytest.raises(orc.ReferencePanic):  # integrity is checked on the record as read
+        orc.run_invert(b"Q\t30\t0\t13\t+\tT\t40\t5\t16\t0\t0\t60\tcg:Z:3S10=\n")
