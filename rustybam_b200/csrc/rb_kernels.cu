@@ -617,16 +617,21 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
     __syncthreads();
     SegVal wpre = seg_identity(), btot = seg_identity();
     uint32_t hpre = 0, htot = 0;
+    if (LIFT) {
 #pragma unroll
-    for (int k = 0; k < SMP_THREADS / 32; k++) {
-        const SegVal t = s_warp[k];
-        if (k < warp) wpre = seg_combine(wpre, t);
-        btot = seg_combine(btot, t);
-        if (LIFT) {
+        for (int k = 0; k < SMP_THREADS / 32; k++) {
+            const SegVal t = s_warp[k];
+            if (k < warp) wpre = seg_combine(wpre, t);
+            btot = seg_combine(btot, t);
             const uint32_t u = s_hc[k];
             if (k < warp) hpre += u;
             htot += u;
         }
+    } else if (warp == 0) {  // only the look-back warp needs the block total ...
+#pragma unroll
+        for (int k = 0; k < SMP_THREADS / 32; k++) btot = seg_combine(btot, s_warp[k]);
+    } else {                 // ... the others the warps in front of them (warp-uniform trip count)
+        for (int k = 0; k < warp; k++) wpre = seg_combine(wpre, s_warp[k]);
     }
     if (warp == 0) {
         const SegVal ex = lookback_seg(blk_state, blk_agg, blk_pre, b, btot);

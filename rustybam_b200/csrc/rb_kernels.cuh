@@ -10,7 +10,10 @@ namespace rb {
 constexpr int TOK_THREADS = 256;
 constexpr int TOK_TILE = TOK_THREADS * 16;  // text bytes per tokeniser tile
 constexpr int TEXT_FRONT_PAD = 16;          // bytes of 0xFF in front of the text (look-behind halo of tile 0)
-constexpr int SMP_THREADS = 256;
+#ifndef RB_SMP_THREADS
+#define RB_SMP_THREADS 256
+#endif
+constexpr int SMP_THREADS = RB_SMP_THREADS;
 constexpr int SMP_OPS = SMP_THREADS * (int)SAMPLE;  // ops per sample-scan block
 constexpr int SL_WCAP = 2048;                // window boundaries of one block staged in shared memory (each of starts / ends)
 // tuning knobs (overridable with -D for sweeps on the GPU box, see tools/sweep.sh)
