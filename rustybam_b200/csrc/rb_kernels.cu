@@ -1028,6 +1028,102 @@ k_lift_plan(uint64_t n_pairs, uint32_t n_blocks, const uint64_t* __restrict__ pa
     plans[b] = pl;
 }
 
+// ---- chained boundaries (tiling windows) ----
+// On a tiling BED the end boundary of window j (last base, position pe) and the start boundary of window j + 1
+// (position pe + 1) are neighbours: the start lookup of a pair is one step past the end lookup its left neighbour
+// just finished, so it is derived from that instead of being searched for again.
+struct ChainSlot {  // what lane 31 of a warp leaves for lane 0 of the next one
+    uint64_t i;
+    uint32_t o, pe, ok, pad;
+    Ctr c;
+};
+// (i, o, counters before i) of target position p  ->  the same for p + 1
+__device__ __forceinline__ bool advance_one(const OpsView& v, const RecInfo& r, uint64_t i, uint32_t o, const Ctr& before, uint64_t& ni,
+                                            uint32_t& no, Ctr& nbefore) {
+    const uint32_t w = v.op(i);
+    if (o + 1u < op_len(w)) { ni = i; no = o + 1u; nbefore = before; return true; }
+    Ctr c = before;
+    ctr_add_op(c, w);
+    uint64_t k = i + 1;
+    for (; k < r.op_end; k++) {  // the next reference-consuming op of non-zero length (same condition as find_op)
+        const uint32_t w2 = v.op(k);
+        if (is_ref(op_code(w2)) && op_len(w2) > 0u) break;
+        ctr_add_op(c, w2);
+    }
+    if (k >= r.op_end) return false;
+    ni = k; no = 0u; nbefore = c;
+    return true;
+}
+// lift_pair (lift_core.cuh) with the END boundary looked up first and the START boundary chained to the left
+// neighbour's END where the two are adjacent positions of the same record (`chain` is block-uniform: every pair of the
+// block belongs to one record, windows consecutive).  Same results as lift_pair by construction: find_op is a pure
+// function of (record, position), and the failure checks are applied in lift_pair's order.
+__device__ __forceinline__ uint32_t lift_pair_chain(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, int policy,
+                                                    bool enabled, bool chain, PairRes& out, ClassAcc& acc, ChainSlot* s_x) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t status = LIFT_OK;
+    bool live = enabled;
+    pair_clear(out);
+    if (live && r.t_st > w_st && r.t_en < w_en) {
+        pair_early(r, out);
+        live = false;
+    } else if (live && r.t_en <= r.t_st) {
+        status = LIFT_ERR_NOT_FOUND;
+        live = false;
+    }
+    const uint32_t ps = live ? (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st) : 0u;
+    const uint32_t pe = live ? (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st) : 0u;
+
+    uint64_t ie = 0; uint32_t oe = 0; Ctr be = ctr_zero();
+    const bool fe = find_op(v, r, live, pe, ie, oe, be, acc);
+
+    // hand (ie, oe, be) to the right neighbour
+    bool derive = false;
+    uint64_t pi = 0; uint32_t po = 0; Ctr pb = ctr_zero();
+    if (chain) {
+        const uint32_t ok = (live && fe) ? 1u : 0u;
+        if (lane == 31) {
+            ChainSlot& x = s_x[warp];
+            x.i = ie; x.o = oe; x.pe = pe; x.ok = ok; x.c = be;
+        }
+        __syncthreads();
+        uint32_t p_ok = __shfl_up_sync(FULL, ok, 1), p_pe = __shfl_up_sync(FULL, pe, 1);
+        po = __shfl_up_sync(FULL, oe, 1);
+        pi = __shfl_up_sync(FULL, ie, 1);
+        uint32_t* dw = reinterpret_cast<uint32_t*>(&pb);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&be);
+#pragma unroll
+        for (int t = 0; t < 12; t++) dw[t] = __shfl_up_sync(FULL, sw[t], 1);
+        if (lane == 0) {
+            p_ok = 0u;
+            if (warp > 0) {
+                const ChainSlot& x = s_x[warp - 1];
+                p_ok = x.ok; p_pe = x.pe; po = x.o; pi = x.i; pb = x.c;
+            }
+        }
+        derive = live && p_ok && ps == p_pe + 1u;
+    }
+    uint64_t i = 0; uint32_t o = 0; Ctr before = ctr_zero();
+    bool fs = false;
+    const bool search = live && !derive;
+    if (__any_sync(FULL, search)) fs = find_op(v, r, search, ps, i, o, before, acc);
+    if (derive) fs = advance_one(v, r, pi, po, pb, i, o, before);
+    __syncwarp();
+    if (!fs && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    uint64_t si = 0; uint32_t so = 0; Ctr cs = ctr_zero();
+    if (live && !lift_start(v, r.eo1, r.a_lead, r.tot.A, policy, i, o, before, si, so, cs)) live = false;
+    __syncwarp();
+    if (live && !fe) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    if (live) {
+        uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
+        if (lift_end(v, r.eo0, ie, oe, be, ei, eo, ce, txt_before_ei))
+            lift_finish(v, r, si, so, cs, op_len(v.op(si)), ei, eo, ce, txt_before_ei, out);
+    }
+    __syncwarp();
+    return status;
+}
+
 // CTA = LIFT_THREADS consecutive pairs in emission order.  On the sorted-BED path the pairs of a block that belong
 // to one record touch a contiguous run of ops (start of the first window .. end of the last one): that run and
 // its samples are staged in shared memory once (coalesced), so the per-pair searches and <=7-op walks of
@@ -1044,6 +1140,9 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
 #endif
     __shared__ __align__(16) RecInfo s_rec;
+#if RB_LIFT_CHAIN
+    __shared__ __align__(16) ChainSlot s_chain[LIFT_THREADS / 32];
+#endif
     const int tid = threadIdx.x;
     const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
     const uint64_t p = p0 + tid;
@@ -1083,7 +1182,8 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
         }
         __syncthreads();
     }
-    if (p >= n_pairs) return;
+    const bool in_range = p < n_pairs;  // (no early return: the chained lookup below has a block barrier)
+    const uint64_t pc = in_range ? p : n_pairs - 1;
     ClassAcc acc;
     acc.sum = s_acc + tid; acc.stride = LIFT_THREADS;
     uint32_t k, r;
@@ -1091,20 +1191,26 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     if (uniform) {  // the block's record sits in shared memory: no per-thread search, no per-thread 208-byte load
         k = pl.k0; r = r_blk; rp = &s_rec;
     } else {
-        k = rank_of_pair(pair_off, n_rec, p);
+        k = rank_of_pair(pair_off, n_rec, pc);
         r = rec_order[k];
         rp = &recs[r];
     }
     const RecInfo& ri = *rp;
-    const uint64_t j = p - pair_off[k];
-    const uint32_t w = win.pair_win ? win.pair_win[p] : (ri.wlo + (uint32_t)j);
+    const uint64_t j = pc - pair_off[k];
+    const uint32_t w = win.pair_win ? win.pair_win[pc] : (ri.wlo + (uint32_t)j);
     const uint64_t w_st = win.st[w], w_en = win.en[w];
     PairRes pr;
     uint32_t len = 0;
     // the brute-force / nested-window candidates can be a superset; break-paf pieces of zero length are never built
-    const bool overlaps = ri.t_en > w_st && ri.t_st < w_en && !(win.from_record && w_en <= w_st);
+    const bool overlaps = in_range && ri.t_en > w_st && ri.t_st < w_en && !(win.from_record && w_en <= w_st);
+#if RB_LIFT_CHAIN
+    const bool chain = uniform && win.pair_win == nullptr;  // block-uniform
+    const uint32_t e = lift_pair_chain(v, ri, w_st, w_en, policy, overlaps, chain, pr, acc, s_chain);
+#else
     const uint32_t e = lift_pair(v, ri, w_st, w_en, policy, overlaps, pr, acc);
+#endif
     __syncwarp();
+    if (!in_range) return;
     if (e != LIFT_OK) { report(err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
     if (pr.kind != PK_DROP) {
         uint32_t idl = ri.id_len;  // early rows and break-paf pieces carry their record's id

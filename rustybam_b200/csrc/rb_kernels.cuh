@@ -29,6 +29,9 @@ constexpr int SL_WCAP = 2048;                // window boundaries of one block s
 #ifndef RB_LIFT_STAGE_SMP
 #define RB_LIFT_STAGE_SMP 1  // 0: the samples of a k_lift block stay in global memory (L1/L2), only its ops are staged
 #endif
+#ifndef RB_LIFT_CHAIN
+#define RB_LIFT_CHAIN 1  // 1: on tiling windows a pair's start boundary is derived from its left neighbour's end boundary
+#endif
 #ifndef RB_SMP_MINB
 #define RB_SMP_MINB 3
 #endif
