@@ -1143,6 +1143,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
 #if RB_LIFT_CHAIN
     __shared__ __align__(16) ChainSlot s_chain[LIFT_THREADS / 32];
 #endif
+    __shared__ __align__(8) unsigned long long s_bar;
     const int tid = threadIdx.x;
     const uint64_t p0 = (uint64_t)blockIdx.x * LIFT_THREADS;
     const uint64_t p = p0 + tid;
@@ -1151,6 +1152,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     const LiftPlan pl = plans[blockIdx.x];
     const bool uniform = pl.uniform != 0;
     uint32_t r_blk = 0;
+    bool staged = false;
     if (uniform) {  // block-uniform: the record and (if it fits) the op run + samples of the block go to shared memory
         r_blk = rec_order[pl.k0];
         static_assert(sizeof(RecInfo) % 16 == 0, "RecInfo is copied in 16-byte vectors");
@@ -1161,26 +1163,29 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
             const uint64_t o_lo = c_lo << SAMPLE_LOG2;
             uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
             if (o_hi > op_end) o_hi = op_end;
-            {   // o_lo is a multiple of 32 ops: 16-byte loads, then the (< 4 op) tail
-                const uint32_t n_stage = (uint32_t)(o_hi - o_lo), n4 = n_stage >> 2;
-                const uint4* src4 = reinterpret_cast<const uint4*>(ops + o_lo);
-                uint4* dst4 = reinterpret_cast<uint4*>(s_ops);
-                for (uint32_t k = tid; k < n4; k += LIFT_THREADS) dst4[k] = src4[k];
-                for (uint32_t k = (n4 << 2) + tid; k < n_stage; k += LIFT_THREADS) s_ops[k] = ops[o_lo + k];
-            }
-#if RB_LIFT_STAGE_SMP
-            const uint64_t nc = c_hi - c_lo + 2;  // samples (+ sub-samples) of chunks [c_lo, c_hi + 1]
+            // both runs are contiguous in HBM and 16-byte aligned (o_lo is a multiple of 32 ops): one thread hands them to
+            // the bulk-copy engine, the block waits on the mbarrier — no per-thread load / store loop, everything in flight
+            const uint32_t n_stage = (uint32_t)(o_hi - o_lo), n4 = n_stage >> 2;
             const uint64_t c_max = (op_end - 1) >> SAMPLE_LOG2;
-            constexpr uint32_t V = SUBS * 3;  // 16-byte vectors per chunk
-            for (uint64_t i = tid; i < nc * V; i += LIFT_THREADS) {
-                const uint64_t c = c_lo + i / V;
-                if (c <= c_max) reinterpret_cast<uint4*>(s_smp)[i] = ld_nc_v4(reinterpret_cast<const uint4*>(samples) + c * V + i % V);
+            const uint64_t c_top = (c_hi + 1 <= c_max) ? c_hi + 1 : c_max;  // samples (+ sub-samples) of chunks [c_lo, c_top]
+            const uint32_t smp_bytes = RB_LIFT_STAGE_SMP ? (uint32_t)((c_top - c_lo + 1) * SUBS * sizeof(Ctr)) : 0u;
+            if (tid == 0) {
+                mbar_init(&s_bar, 1);
+                mbar_expect_tx(&s_bar, n4 * 16u + smp_bytes);
+                if (n4) bulk_g2s(s_ops, ops + o_lo, n4 * 16u, &s_bar);
+#if RB_LIFT_STAGE_SMP
+                bulk_g2s(s_smp, samples + c_lo * SUBS, smp_bytes, &s_bar);
+#endif
             }
-            v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = (c_hi + 1 <= c_max ? c_hi + 2 : c_hi + 1);
+            for (uint32_t k = (n4 << 2) + tid; k < n_stage; k += LIFT_THREADS) s_ops[k] = ops[o_lo + k];  // the (< 4 op) tail
+#if RB_LIFT_STAGE_SMP
+            v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = c_top + 1;
 #endif
             v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
+            staged = true;
         }
-        __syncthreads();
+        __syncthreads();  // s_rec, the tail ops and the mbarrier's initialisation are visible to everybody
+        if (staged) mbar_wait(&s_bar, 0);
     }
     const bool in_range = p < n_pairs;  // (no early return: the chained lookup below has a block barrier)
     const uint64_t pc = in_range ? p : n_pairs - 1;
