@@ -152,6 +152,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global through the same engine: smem writes of the block must be fenced into the async proxy first
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -1602,17 +1609,19 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             else q = put_cigar_seq(q, a, ri, pr);
             *q = '\n';
         }
+        fence_proxy_async();
         __syncthreads();
         uint8_t* dst = out_text + byte0;
         const uint32_t n = (uint32_t)region;
         const uint32_t head = (16u - shift) & 15u;  // bytes until dst is 16-byte aligned
         const uint32_t hb = head < n ? head : n;
-        for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = s_buf[shift + i];
         const uint32_t nvec = (n - hb) >> 4;
-        const uint4* sv = reinterpret_cast<const uint4*>(s_buf + shift + hb);
-        uint4* dv = reinterpret_cast<uint4*>(dst + hb);
-        for (uint32_t i = tid; i < nvec; i += SER_LINES) dv[i] = sv[i];
+        // the 16-byte aligned body goes out as one bulk copy (shared -> global) issued by one thread ...
+        if (tid == 0 && nvec) bulk_s2g(dst + hb, s_buf + shift + hb, nvec << 4);
+        // ... the ragged ends by the others
+        for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = s_buf[shift + i];
         for (uint32_t i = hb + (nvec << 4) + tid; i < n; i += SER_LINES) dst[i] = s_buf[shift + i];
+        if (tid == 0 && nvec) bulk_wait_read();  // the block's shared memory must outlive the engine's read of it
         return;
     }
 
