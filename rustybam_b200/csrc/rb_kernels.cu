@@ -1191,26 +1191,27 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
             v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
             staged = true;
         }
-        __syncthreads();  // s_rec, the tail ops and the mbarrier's initialisation are visible to everybody
-        if (staged) mbar_wait(&s_bar, 0);
     }
     const bool in_range = p < n_pairs;  // (no early return: the chained lookup below has a block barrier)
     const uint64_t pc = in_range ? p : n_pairs - 1;
     ClassAcc acc;
     acc.sum = s_acc + tid; acc.stride = LIFT_THREADS;
     uint32_t k, r;
-    const RecInfo* rp;
     if (uniform) {  // the block's record sits in shared memory: no per-thread search, no per-thread 208-byte load
-        k = pl.k0; r = r_blk; rp = &s_rec;
+        k = pl.k0; r = r_blk;
     } else {
         k = rank_of_pair(pair_off, n_rec, pc);
         r = rec_order[k];
-        rp = &recs[r];
     }
-    const RecInfo& ri = *rp;
+    // this pair's window: loaded while the bulk copies above are still in flight
     const uint64_t j = pc - pair_off[k];
-    const uint32_t w = win.pair_win ? win.pair_win[pc] : (ri.wlo + (uint32_t)j);
+    const uint32_t w = win.pair_win ? win.pair_win[pc] : (recs[r].wlo + (uint32_t)j);
     const uint64_t w_st = win.st[w], w_en = win.en[w];
+    if (uniform) {
+        __syncthreads();  // s_rec, the tail ops and the mbarrier's initialisation are visible to everybody
+        if (staged) mbar_wait(&s_bar, 0);
+    }
+    const RecInfo& ri = uniform ? s_rec : recs[r];
     PairRes pr;
     uint32_t len = 0;
     // the brute-force / nested-window candidates can be a superset; break-paf pieces of zero length are never built
