@@ -334,6 +334,169 @@ bool PafRecord::tpos_to_idx_match(uint64_t tpos, bool search_right, int policy, 
     return true;
 }
 
+// ---- rb trim-paf (query space) -------------------------------------------------------------------
+// core::slice::binary_search_by with an arbitrary three-way comparator `cmp(probe)` (<0 Less, 0 Equal, >0 Greater),
+// in the two shapes std has shipped (see bsearch_rightmost / bsearch_early_exit above).
+template <class F>
+static bool bsearch_by(size_t n, int policy, F&& cmp, size_t& idx) {
+    if (policy == POLICY_EARLY_EXIT) {
+        size_t size = n, left = 0, right = n;
+        while (left < right) {
+            size_t mid = left + size / 2;
+            const int c = cmp(mid);
+            if (c < 0) left = mid + 1;
+            else if (c > 0) right = mid;
+            else { idx = mid; return true; }
+            size = right - left;
+        }
+        return false;
+    }
+    size_t size = n;
+    if (size == 0) return false;
+    size_t base = 0;
+    while (size > 1) {
+        size_t half = size / 2, mid = base + half;
+        if (!(cmp(mid) > 0)) base = mid;
+        size -= half;
+    }
+    if (cmp(base) == 0) { idx = base; return true; }
+    return false;
+}
+
+// paf.rs:564-574
+bool PafRecord::qpos_to_idx(uint64_t qpos, int policy, size_t& idx) const {
+    const std::vector<uint64_t>& a = qpos_aln;
+    if (strand == '-')  // probe.cmp(&qpos).reverse()
+        return bsearch_by(a.size(), policy, [&](size_t m) { return a[m] > qpos ? -1 : (a[m] < qpos ? 1 : 0); }, idx);
+    return bsearch_by(a.size(), policy, [&](size_t m) { return a[m] < qpos ? -1 : (a[m] > qpos ? 1 : 0); }, idx);
+}
+
+// paf.rs:577-591
+bool PafRecord::qpos_to_idx_match(uint64_t qpos, bool search_right, int policy, size_t& idx) const {
+    if (!qpos_to_idx(qpos, policy, idx)) return false;
+    const size_t max_idx = long_cigar.size();
+    if ((search_right && strand == '+') || (!search_right && strand == '-')) {
+        while (idx < max_idx && !is_match(long_cigar[idx].op)) idx++;
+    } else {
+        while (idx > 0 && !is_match(long_cigar[idx].op)) idx--;
+    }
+    return true;
+}
+
+// paf.rs:489-498
+void PafRecord::make_long_cigar() {
+    long_cigar.clear();
+    for (const Cig& o : cigar)
+        for (uint32_t k = 0; k < o.len; k++) long_cigar.push_back(Cig{1, o.op});
+}
+
+// paf.rs:785-823.  Every panic of the reference (assert!, unwrap on Err, slice index out of range, integer
+// underflow in a debug build / the search miss it causes in a release build) is an Abort here.
+void PafRecord::truncate_record_by_query(uint64_t new_q_st, uint64_t new_q_en, int policy) {
+    if (!(new_q_st >= q_st)) throw Abort("New start is less than old start.");
+    if (!(new_q_en <= q_en)) throw Abort("New end is greater than old end.");
+    make_long_cigar();
+    if (new_q_en == 0) throw Abort("truncate_record_by_query: new_q_en - 1 underflows");
+    size_t aln_st, aln_en;
+    if (!qpos_to_idx_match(new_q_st, true, policy, aln_st)) throw Abort("truncate_record_by_query: qpos_to_idx_match(start) is Err");
+    if (!qpos_to_idx_match(new_q_en - 1, false, policy, aln_en)) throw Abort("truncate_record_by_query: qpos_to_idx_match(end) is Err");
+    if (aln_st >= qpos_aln.size() || aln_en >= qpos_aln.size()) throw Abort("truncate_record_by_query: index out of bounds");
+    const uint64_t new_new_q_st = qpos_aln[aln_st];
+    const uint64_t new_new_q_en = qpos_aln[aln_en] + 1;
+    if (aln_st > aln_en) std::swap(aln_st, aln_en);
+    const uint64_t new_t_st = tpos_aln[aln_st];
+    const uint64_t new_t_en = tpos_aln[aln_en] + 1;
+    long_cigar = subset_cigar(aln_st, aln_en);
+    cigar = collapse_long_cigar(long_cigar);
+    t_st = new_t_st; t_en = new_t_en;
+    q_st = new_new_q_st; q_en = new_new_q_en;
+    remove_trailing_indels();
+    std::string why;
+    if (!check_integrity(&why)) throw Abort("truncate_record_by_query: check_integrity failed: " + why);
+}
+
+// trim_overlap.rs:6-20
+int score_of_qpos(const PafRecord& rec, uint64_t pos, int match_score, int diff_score, int indel_score, int policy) {
+    size_t idx;
+    if (!rec.qpos_to_idx(pos, policy, idx)) throw Abort("score_of_qpos: qpos_to_idx is Err");
+    const uint32_t op = rec.long_cigar[idx].op;
+    if (op == OP_EQ) return match_score;
+    if (op == OP_I || op == OP_D) return -indel_score;
+    return -diff_score;
+}
+
+// trim_overlap.rs:36-86
+void trim_overlapping_pafs(PafRecord& left, PafRecord& right, int match_score, int diff_score, int indel_score, int policy) {
+    const uint64_t st_ovl = std::max(left.q_st, right.q_st);
+    const uint64_t en_ovl = std::min(left.q_en, right.q_en);
+    std::vector<int32_t> l_score{0}, r_score;
+    for (uint64_t pos = st_ovl; pos < en_ovl; pos++) {
+        l_score.push_back(score_of_qpos(left, pos, match_score, diff_score, indel_score, policy));
+        r_score.push_back(score_of_qpos(right, pos, match_score, diff_score, indel_score, policy));
+    }
+    r_score.push_back(0);
+    int32_t acc = 0;
+    for (size_t k = 0; k < l_score.size(); k++) { acc += l_score[k]; l_score[k] = acc; }
+    acc = 0;
+    for (size_t k = r_score.size(); k-- > 0;) { acc += r_score[k]; r_score[k] = acc; }
+    uint64_t max_idx = 0;
+    int32_t mx = 0;
+    for (size_t k = 0; k < l_score.size() && k < r_score.size(); k++) {
+        if (l_score[k] + r_score[k] > mx) { mx = l_score[k] + r_score[k]; max_idx = k; }
+    }
+    left.truncate_record_by_query(left.q_st, st_ovl + max_idx, policy);
+    right.truncate_record_by_query(st_ovl + max_idx, right.q_en, policy);
+}
+
+// paf.rs:210-305
+void Paf::overlapping_paf_recs(int match_score, int diff_score, int indel_score, bool remove_contained, int policy) {
+    for (PafRecord& rec : records) rec.remove_trailing_indels();
+    struct Pair { uint64_t overlap; size_t i, j; };
+    std::vector<Pair> overlap_pairs;
+    std::stable_sort(records.begin(), records.end(), [](const PafRecord& a, const PafRecord& b) { return a.q_name < b.q_name; });
+    std::vector<bool> contained(records.size(), false);
+    if (records.size() < 2) return;
+    for (size_t i = 0; i + 1 < records.size(); i++) {
+        const PafRecord& rec1 = records[i];
+        for (size_t j = i + 1; j < records.size() && rec1.q_name == records[j].q_name; j++) {
+            const PafRecord& rec2 = records[j];
+            const uint64_t mn = std::min(rec1.q_en, rec2.q_en), mxs = std::max(rec1.q_st, rec2.q_st);  // bed.rs:74-85
+            const uint64_t overlap = mn < mxs ? 0 : mn - mxs;
+            if (overlap < 1) continue;
+            else if (overlap == rec2.q_en - rec2.q_st) contained[j] = true;
+            else if (overlap == rec1.q_en - rec1.q_st) contained[i] = true;
+            else if (rec1.q_st <= rec2.q_st) overlap_pairs.push_back(Pair{overlap, i, j});
+            else overlap_pairs.push_back(Pair{overlap, j, i});
+        }
+    }
+    std::stable_sort(overlap_pairs.begin(), overlap_pairs.end(),
+                     [](const Pair& a, const Pair& b) { return UINT64_MAX - a.overlap < UINT64_MAX - b.overlap; });
+    std::vector<std::string> q_seen;  // HashSet<String>: membership only
+    size_t unseen = 0;
+    for (const Pair& p : overlap_pairs) {
+        PafRecord left = records[p.i], right = records[p.j];
+        const std::string q_name = left.q_name;
+        if (std::find(q_seen.begin(), q_seen.end(), q_name) == q_seen.end()) {
+            left.aligned_pairs();
+            right.aligned_pairs();
+            trim_overlapping_pafs(left, right, match_score, diff_score, indel_score, policy);
+            records[p.i] = std::move(left);
+            records[p.j] = std::move(right);
+            q_seen.push_back(q_name);
+        } else {
+            unseen++;
+        }
+    }
+    if (unseen > 0) {
+        overlapping_paf_recs(match_score, diff_score, indel_score, remove_contained, policy);
+    } else if (remove_contained) {
+        std::vector<PafRecord> kept;
+        for (size_t i = 0; i < records.size(); i++)
+            if (!contained[i]) kept.push_back(records[i]);
+        records.swap(kept);
+    }
+}
+
 // paf.rs:593-600
 CigarString PafRecord::subset_cigar(size_t start_idx, size_t end_idx) const {
     return CigarString(long_cigar.begin() + (ptrdiff_t)start_idx,
@@ -803,6 +966,16 @@ std::string run_invert(const char* paf, size_t paf_n) {
     Paf p = Paf::from_text(paf, paf_n);
     std::string out;
     for (const PafRecord& r : p.records) { out += paf_swap_query_and_target(r).to_line(); out += '\n'; }
+    return out;
+}
+
+// main.rs:218-230 — `rb trim-paf`: every record of the (sorted, trimmed) set, in the set's order
+std::string run_trim_paf(const char* paf, size_t paf_n, int match_score, int diff_score, int indel_score,
+                         bool remove_contained, int policy) {
+    Paf p = Paf::from_text(paf, paf_n);
+    p.overlapping_paf_recs(match_score, diff_score, indel_score, remove_contained, policy);
+    std::string out;
+    for (const PafRecord& r : p.records) { out += r.to_line(); out += '\n'; }
     return out;
 }
 

@@ -22,6 +22,10 @@
 //   src/liftover.rs:17-105   trim_paf_rec_to_rgn  -> trim_paf_rec_to_rgn
 //   src/liftover.rs:107-167  trim_helper/_by_rgns -> trim_helper / trim_paf_by_rgns
 //   src/liftover.rs:182-226  break_paf_on_indels  -> break_paf_on_indels
+//   src/paf.rs:564-591       qpos_to_idx(_match)  -> PafRecord::qpos_to_idx(_match)
+//   src/paf.rs:785-823       truncate_record_by_query -> PafRecord::truncate_record_by_query
+//   src/paf.rs:210-305       overlapping_paf_recs -> Paf::overlapping_paf_recs            (LITERAL rounds)
+//   src/trim_overlap.rs:6-86 score / split        -> score_of_qpos / trim_overlapping_pafs (LITERAL, per base)
 //   src/bamstats.rs:91-154   stats                -> stats_from_paf / add_stats_from_cigar (u32 + f32)
 //   src/bamstats.rs:225-270  printers             -> stats_header / stats_row
 //   src/bed.rs:140-194       BED -> Region        -> parse_bed_text
@@ -101,6 +105,11 @@ struct PafRecord {
     // Ok(idx) -> returns true and sets idx ; Err(_) -> false
     bool tpos_to_idx(uint64_t tpos, int policy, size_t& idx) const;
     bool tpos_to_idx_match(uint64_t tpos, bool search_right, int policy, size_t& idx) const;
+    // paf.rs:564-591 (query space; the array runs downward on '-' records, binary_search_by with a reversed comparator)
+    bool qpos_to_idx(uint64_t qpos, int policy, size_t& idx) const;
+    bool qpos_to_idx_match(uint64_t qpos, bool search_right, int policy, size_t& idx) const;
+    void make_long_cigar();                                                             // paf.rs:489-498
+    void truncate_record_by_query(uint64_t new_q_st, uint64_t new_q_en, int policy);   // paf.rs:785-823
     CigarString subset_cigar(size_t start_idx, size_t end_idx) const;
     static CigarString collapse_long_cigar(const CigarString& c);
     bool overlaps(const Region& r) const;
@@ -114,6 +123,8 @@ struct Paf {
     std::vector<PafRecord> records;
     // `skipped` counts lines that hit ParseSkip (stderr note in the reference)
     static Paf from_text(const char* text, size_t n, size_t* skipped = nullptr);
+    // paf.rs:210-305 — `rb trim-paf`: rounds of pairwise overlap trimming in query space
+    void overlapping_paf_recs(int match_score, int diff_score, int indel_score, bool remove_contained, int policy);
 };
 
 std::vector<Region> parse_bed_text(const char* text, size_t n);
@@ -126,6 +137,9 @@ std::vector<PafRecord> trim_paf_by_rgns(const std::vector<Region>& rgns,
                                         int policy, int threads);
 std::vector<PafRecord> break_paf_on_indels(const PafRecord& paf, uint32_t break_length, int policy);
 PafRecord paf_swap_query_and_target(const PafRecord& paf);
+// trim_overlap.rs:6-86 — split point of two query-overlapping records by cumulative per-base scores, then truncation
+int score_of_qpos(const PafRecord& rec, uint64_t pos, int match_score, int diff_score, int indel_score, int policy);
+void trim_overlapping_pafs(PafRecord& left, PafRecord& right, int match_score, int diff_score, int indel_score, int policy);
 
 struct Stats {
     std::string q_nm, r_nm;
@@ -146,5 +160,7 @@ std::string run_liftover(const char* paf, size_t paf_n, const char* bed, size_t 
 std::string run_stats(const char* paf, size_t paf_n, bool qbed);
 std::string run_break_paf(const char* paf, size_t paf_n, uint32_t max_size, int policy);
 std::string run_invert(const char* paf, size_t paf_n);
+std::string run_trim_paf(const char* paf, size_t paf_n, int match_score, int diff_score, int indel_score,
+                         bool remove_contained, int policy);
 
 }  // namespace orc

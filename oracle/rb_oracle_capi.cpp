@@ -60,6 +60,36 @@ int orc_run_invert(const char* paf, size_t paf_n, char** out, size_t* out_n, cha
     }
 }
 
+// trim_overlap.rs:22-34 (doctest shape): two record lines -> aligned_pairs on both -> trim_overlapping_pafs -> two lines
+int orc_trim_pair(const char* left_line, const char* right_line, int match_score, int diff_score, int indel_score, int policy,
+                  char** out, size_t* out_n, char* err, size_t err_cap) {
+    try {
+        PafRecord l = PafRecord::parse(left_line), r = PafRecord::parse(right_line);
+        l.aligned_pairs();
+        r.aligned_pairs();
+        trim_overlapping_pafs(l, r, match_score, diff_score, indel_score, policy);
+        *out = dup_out(l.to_line() + "\n" + r.to_line() + "\n", out_n);
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    } catch (const ParseSkip&) {
+        set_err(err, err_cap, "line skipped");
+        return 2;
+    }
+}
+
+int orc_run_trim_paf(const char* paf, size_t paf_n, int match_score, int diff_score, int indel_score, int remove_contained,
+                     int policy, char** out, size_t* out_n, char* err, size_t err_cap) {
+    try {
+        *out = dup_out(run_trim_paf(paf, paf_n, match_score, diff_score, indel_score, remove_contained != 0, policy), out_n);
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    }
+}
+
 int orc_run_stats(const char* paf, size_t paf_n, int qbed, char** out, size_t* out_n, char* err,
                   size_t err_cap) {
     try {

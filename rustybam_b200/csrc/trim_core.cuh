@@ -1,0 +1,236 @@
+// trim_core.cuh — run-length ("closed form") statement of `rb trim-paf`'s per-pair work.
+//
+// Replaces, per pair of query-overlapping records, the reference's per-base machinery:
+//   trim_overlap.rs:6-20    score_of_qpos            (binary search over 8 B/column per overlap base, per record)
+//   trim_overlap.rs:36-86   trim_overlapping_pafs    (two per-base score vectors, two cumulative passes, arg-max)
+//   paf.rs:564-591          qpos_to_idx / qpos_to_idx_match
+//   paf.rs:785-823          truncate_record_by_query (subset_cigar + collapse_long_cigar + check_integrity)
+// with per-op prefix arrays in QUERY space (qp = query bases before the op, wp = score of the query positions before
+// the op; 12 B per op, built once per call by k_trim_scan) and searches over them:
+//   * the score of a query position depends only on the op that owns it, except for the LAST position of a
+//     query-consuming op that is followed by columns that do not advance the query (D, N, H, P): all of them carry
+//     the same query position, binary_search returns the right-most one (Rust < 1.52 / >= 1.82), so that
+//     position scores as the last such column;
+//   * cumulative-left + cumulative-right (trim_overlap.rs:60-69) is, up to a constant, a piecewise linear function of
+//     the split point whose break points are op boundaries of either record: the first arg-max lies on one of them;
+//   * truncation = two column look-ups + the slide to the nearest M/=/X column, all in (op, offset) space; a record
+//     that has been truncated is a VIEW (first / last column) on its unchanged ops, so later rounds reuse the arrays.
+// Only the right-most duplicate policy is implemented for this sub-command (the caller is refused otherwise).
+//
+// __host__ __device__: fuzzed on the CPU against the literal per-base oracle (tests/native/trim_core_check.cpp) and
+// run by k_trim_pairs / k_trim_rows on the GPU.
+#pragma once
+#include "lift_core.cuh"
+
+namespace rb {
+
+struct TrimScores { int32_t match, diff, indel; };  // trim_overlap.rs:8-10 (CLI defaults 1 / 1 / 1)
+struct TrimArr {
+    const uint32_t* qp;    // [global op] query bases of the record before this op (counted from op_first, like Ctr::Q)
+    const long long* wp;   // [global op] score of the query positions owned by the effective ops before this op
+};
+struct TrimView {          // 64 bytes per record
+    uint64_t si, ei;       // ops holding the first / last alignment column of the (possibly truncated) record
+    uint32_t so, eo;       // offsets of those columns inside their ops
+    uint64_t q_st, q_en;   // current query span
+    long long w_tot;       // score of all query positions of the effective (stripped) record
+    uint32_t x_end;        // query bases before op eo1 (end of the effective range in the qp frame)
+    uint32_t trimmed;      // truncations applied so far
+    uint32_t bad;          // effective record does not start and end on an M/=/X op of positive length: unsupported here
+    uint32_t pad;
+};
+enum : uint32_t { TRIM_OK = 0, TRIM_ABORT = 1 };  // ABORT == the reference panics (check_integrity().unwrap(), paf.rs:822)
+constexpr uint32_t TRIM_NO_TAIL = 0xFFu;
+
+// trim_overlap.rs:14-19
+RB_HD int32_t trim_col_score(uint32_t code, const TrimScores& sc) {
+    return code == OP_EQ ? sc.match : ((code == OP_I || code == OP_D) ? -sc.indel : -sc.diff);
+}
+// The last op (len > 0) of the run of non-query-consuming ops that follows op k, looking no further than op `last`
+// (inclusive); TRIM_NO_TAIL if the next op of positive length advances the query (or there is none).
+RB_HD uint32_t trim_tail(const OpsView& v, uint64_t k, uint64_t last, uint64_t* tail_op = nullptr) {
+    uint32_t tail = TRIM_NO_TAIL;
+    for (uint64_t j = k + 1; j <= last; j++) {
+        const uint32_t w = v.op(j);
+        if (op_len(w) == 0) continue;
+        if (is_qry(op_code(w))) break;
+        tail = op_code(w);
+        if (tail_op) *tail_op = j;
+    }
+    return tail;
+}
+// score of the query positions owned by op k of a record whose effective range ends at eo1 (exclusive)
+RB_HD long long trim_w_op(const OpsView& v, uint64_t k, uint64_t eo1, const TrimScores& sc) {
+    const uint32_t w = v.op(k), L = op_len(w), code = op_code(w);
+    if (L == 0 || !is_qry(code)) return 0;
+    const int32_t s = trim_col_score(code, sc);
+    long long t = (long long)L * s;
+    const uint32_t tail = trim_tail(v, k, eo1 - 1);
+    if (tail != TRIM_NO_TAIL) t += trim_col_score(tail, sc) - s;
+    return t;
+}
+// right-most op k in [lo, hi) with qp[k] <= x  (== the query-consuming op that owns query offset x)
+RB_HD uint64_t trim_find_q(const TrimArr& a, uint64_t lo, uint64_t hi, uint32_t x) {
+    hi--;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi + 1) >> 1;
+        if (a.qp[mid] <= x) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+// query offset (qp frame) of absolute query position p
+RB_HD uint32_t trim_x(const RecInfo& r, uint64_t p) {
+    return (r.flags & RF_MINUS) ? (uint32_t)(r.q_en0 - 1 - p) : (uint32_t)(p - r.q_st0);
+}
+// score of the first x query positions in column order (x in the qp frame, >= qp[eo0])
+RB_HD long long trim_G(const OpsView& v, const TrimArr& a, const RecInfo& r, const TrimView& tv, uint32_t x, const TrimScores& sc) {
+    if (x >= tv.x_end) return tv.w_tot;
+    const uint64_t k = trim_find_q(a, r.eo0, r.eo1, x);
+    return a.wp[k] + (long long)(x - a.qp[k]) * trim_col_score(op_code(v.op(k)), sc);
+}
+// sum of score_of_qpos over the absolute query positions [qa, qb) of the record as it is now (view tv)
+RB_HD long long trim_S(const OpsView& v, const TrimArr& a, const RecInfo& r, const TrimView& tv, uint64_t qa, uint64_t qb,
+                       const TrimScores& sc) {
+    if (qb <= qa) return 0;
+    long long s;
+    if (r.flags & RF_MINUS) s = trim_G(v, a, r, tv, (uint32_t)(r.q_en0 - qa), sc) - trim_G(v, a, r, tv, (uint32_t)(r.q_en0 - qb), sc);
+    else s = trim_G(v, a, r, tv, (uint32_t)(qb - r.q_st0), sc) - trim_G(v, a, r, tv, (uint32_t)(qa - r.q_st0), sc);
+    // the view's last column lost the non-query columns that followed it in the untruncated record
+    const uint32_t we = v.op(tv.ei);
+    if (tv.eo == op_len(we) - 1u) {
+        const uint32_t tail = trim_tail(v, tv.ei, r.eo1 - 1);
+        if (tail != TRIM_NO_TAIL) {
+            const uint32_t xe = a.qp[tv.ei] + tv.eo;
+            const uint64_t pe = (r.flags & RF_MINUS) ? r.q_en0 - 1 - xe : r.q_st0 + xe;
+            if (pe >= qa && pe < qb) s += trim_col_score(op_code(we), sc) - trim_col_score(tail, sc);
+        }
+    }
+    return s;
+}
+
+struct TrimBest {       // arg-max state: larger total wins, ties go to the smaller split point
+    long long total;
+    uint64_t c;
+};
+RB_HD void trim_best_merge(TrimBest& b, long long total, uint64_t c) {
+    if (total > b.total || (total == b.total && c < b.c)) { b.total = total; b.c = c; }
+}
+// total(c) - Rtot for a split at absolute query position c in [A, B]: score of the left record over [A, c) minus the
+// score of the right record over [A, c)   (trim_overlap.rs:60-77 with the constant Rtot = right over [A, B) taken out)
+RB_HD long long trim_val(const OpsView& v, const TrimArr& a, const RecInfo& rl, const TrimView& tl, const RecInfo& rr, const TrimView& tr,
+                         uint64_t A, uint64_t c, const TrimScores& sc) {
+    return trim_S(v, a, rl, tl, A, c, sc) - trim_S(v, a, rr, tr, A, c, sc);
+}
+// Candidate split points contributed by record `rx` (either of the pair): the op boundaries (and the one-base segments
+// in front of non-query runs) that fall into [A, B].  Work item t of n (a thread of the block; 0 of 1 on the host).
+RB_HD void trim_scan_candidates(const OpsView& v, const TrimArr& a, const RecInfo& rx, const RecInfo& rl, const TrimView& tl,
+                                const RecInfo& rr, const TrimView& tr, uint64_t A, uint64_t B, const TrimScores& sc, uint32_t t,
+                                uint32_t n, TrimBest& best) {
+    uint64_t k0 = trim_find_q(a, rx.eo0, rx.eo1, trim_x(rx, A)), k1 = trim_find_q(a, rx.eo0, rx.eo1, trim_x(rx, B - 1));
+    if (k0 > k1) { const uint64_t tmp = k0; k0 = k1; k1 = tmp; }
+    const bool minus = (rx.flags & RF_MINUS) != 0;
+    for (uint64_t k = k0 + t; k <= k1; k += n) {
+        const uint32_t w = v.op(k), L = op_len(w);
+        if (L == 0 || !is_qry(op_code(w))) continue;
+        uint64_t lo, hi, mid;
+        if (minus) { hi = rx.q_en0 - a.qp[k]; lo = hi - L; mid = lo + 1; }
+        else { lo = rx.q_st0 + a.qp[k]; hi = lo + L; mid = hi - 1; }
+        const uint64_t cand[3] = {lo, mid, hi};
+        for (int i = 0; i < 3; i++) {
+            const uint64_t c = cand[i];
+            if (c < A || c > B) continue;
+            trim_best_merge(best, trim_val(v, a, rl, tl, rr, tr, A, c, sc), c);
+        }
+    }
+}
+RB_HD void trim_fixed_candidates(const OpsView& v, const TrimArr& a, const RecInfo& rl, const TrimView& tl, const RecInfo& rr,
+                                 const TrimView& tr, uint64_t A, uint64_t B, const TrimScores& sc, TrimBest& best) {
+    const uint64_t cand[4] = {A, A + 1, B - 1, B};
+    for (int i = 0; i < 4; i++)
+        if (cand[i] >= A && cand[i] <= B) trim_best_merge(best, trim_val(v, a, rl, tl, rr, tr, A, cand[i], sc), cand[i]);
+}
+// split point from the arg-max over all candidates (trim_overlap.rs:71-77: `if l + r > max` starting from max = 0)
+RB_HD uint64_t trim_split(const TrimBest& best, long long r_tot, uint64_t A) { return (best.total + r_tot > 0) ? best.c : A; }
+
+// ---- truncate_record_by_query (paf.rs:785-823) in (op, offset) space ---------------------------------------------
+struct TrimCol { uint64_t k; uint32_t o; };
+RB_HD bool trim_col_lt(const TrimCol& x, const TrimCol& y) { return x.k < y.k || (x.k == y.k && x.o < y.o); }
+
+// qpos_to_idx (right-most policy): `base` = the query-consuming column of position p, `last` = the right-most column
+// that repeats that position (the end of the non-query run behind it, inside the view)
+RB_HD void trim_col_of(const OpsView& v, const TrimArr& a, const RecInfo& r, const TrimView& tv, uint64_t p, TrimCol& base, TrimCol& last) {
+    const uint32_t x = trim_x(r, p);
+    base.k = trim_find_q(a, r.eo0, r.eo1, x);
+    base.o = x - a.qp[base.k];
+    last = base;
+    if (base.o == op_len(v.op(base.k)) - 1u && base.k < tv.ei) {
+        uint64_t j = 0;
+        if (trim_tail(v, base.k, tv.ei, &j) != TRIM_NO_TAIL) { last.k = j; last.o = op_len(v.op(j)) - 1u; }
+    }
+}
+// `while idx < max_idx && !match { idx += 1 }` from column `last` (whose query-consuming column is `base`)
+RB_HD bool trim_slide_right(const OpsView& v, const TrimView& tv, const TrimCol& base, const TrimCol& last, TrimCol& out) {
+    if (last.k == base.k && is_match(op_code(v.op(base.k)))) { out = base; return true; }
+    for (uint64_t j = last.k + 1; j <= tv.ei; j++) {
+        const uint32_t w = v.op(j);
+        if (op_len(w) > 0 && is_match(op_code(w))) { out.k = j; out.o = 0; return true; }
+    }
+    return false;  // idx == number of columns: the reference indexes out of bounds
+}
+// `while idx > 0 && !match { idx -= 1 }`
+RB_HD void trim_slide_left(const OpsView& v, const TrimView& tv, const TrimCol& base, TrimCol& out) {
+    if (is_match(op_code(v.op(base.k)))) { out = base; return; }
+    for (uint64_t j = base.k; j > tv.si;) {
+        j--;
+        const uint32_t w = v.op(j);
+        if (op_len(w) > 0 && is_match(op_code(w))) { out.k = j; out.o = op_len(w) - 1u; return; }
+    }
+    out.k = tv.si; out.o = tv.so;  // column 0 of the view
+}
+// Truncates the view to the query interval [nqs, nqe) (q_st <= nqs < nqe <= q_en).
+RB_HD uint32_t trim_truncate(const OpsView& v, const TrimArr& a, const RecInfo& r, TrimView& tv, uint64_t nqs, uint64_t nqe) {
+    TrimCol b0, l0, b1, l1, cs, ce;
+    trim_col_of(v, a, r, tv, nqs, b0, l0);
+    trim_col_of(v, a, r, tv, nqe - 1, b1, l1);
+    if (r.flags & RF_MINUS) {  // paf.rs:582: the directions swap on '-'; columns run against the query
+        trim_slide_left(v, tv, b0, ce);                       // aln_st (from new_q_st): the higher column
+        if (!trim_slide_right(v, tv, b1, l1, cs)) return TRIM_ABORT;  // aln_en (from new_q_en - 1): the lower column
+    } else {
+        if (!trim_slide_right(v, tv, b0, l0, cs)) return TRIM_ABORT;
+        trim_slide_left(v, tv, b1, ce);
+    }
+    if (trim_col_lt(ce, cs)) return TRIM_ABORT;  // crossed: spans and CIGAR disagree -> check_integrity().unwrap() panics
+    tv.si = cs.k; tv.so = cs.o; tv.ei = ce.k; tv.eo = ce.o;
+    const uint32_t xs = a.qp[cs.k] + cs.o, xe = a.qp[ce.k] + ce.o + 1u;
+    if (r.flags & RF_MINUS) { tv.q_st = r.q_en0 - xe; tv.q_en = r.q_en0 - xs; }
+    else { tv.q_st = r.q_st0 + xs; tv.q_en = r.q_st0 + xe; }
+    tv.trimmed++;
+    return TRIM_OK;
+}
+
+// The untruncated view of a record (after k_rec_prep's strip); w_tot / x_end are filled by the scan.
+RB_HD void trim_view_init(const OpsView& v, const RecInfo& r, TrimView& tv) {
+    const uint32_t w0 = v.op(r.eo0), w1 = v.op(r.eo1 - 1);
+    tv.si = r.eo0; tv.so = 0;
+    tv.ei = r.eo1 - 1; tv.eo = op_len(w1) - 1u;
+    tv.q_st = r.q_st; tv.q_en = r.q_en;
+    tv.trimmed = 0; tv.pad = 0;
+    tv.bad = (op_len(w0) > 0 && is_match(op_code(w0)) && op_len(w1) > 0 && is_match(op_code(w1))) ? 0u : 1u;
+}
+
+// The printed row of one record after all rounds: untouched -> the (stripped) record itself, uncollapsed;
+// truncated -> the view, re-collapsed (paf.rs:807-808), nmatch / aln_len from check_integrity (paf.rs:822).
+RB_HD void trim_row(const OpsView& v, const RecInfo& r, const TrimView& tv, ClassAcc& acc, PairRes& out) {
+    pair_clear(out);
+    if (!tv.trimmed) { pair_early(r, out); return; }
+    const uint32_t ws = v.op(tv.si), we = v.op(tv.ei);
+    Ctr cs = ctr_before(v, r, tv.si, acc);
+    ctr_add_bases(cs, op_code(ws), tv.so);
+    Ctr ce = ctr_before(v, r, tv.ei, acc);
+    const uint32_t txt_before_ei = ce.TXT;
+    ctr_add_bases(ce, op_code(we), tv.eo + 1u);
+    lift_finish(v, r, tv.si, tv.so, cs, op_len(ws), tv.ei, tv.eo, ce, txt_before_ei, out);
+}
+
+}  // namespace rb

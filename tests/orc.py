@@ -59,6 +59,28 @@ def run_invert(paf: bytes) -> bytes:
     return _take(out, n)
 
 
+def run_trim_paf(paf: bytes, match_score=1, diff_score=1, indel_score=1, remove_contained=False, policy=RIGHTMOST) -> bytes:
+    """`rb trim-paf` (main.rs:218-230, paf.rs:210-305, trim_overlap.rs:36-86) on PAF text."""
+    out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
+    rc = lib().orc_run_trim_paf(paf, C.c_size_t(len(paf)), int(match_score), int(diff_score), int(indel_score), int(remove_contained),
+                                policy, C.byref(out), C.byref(n), err, C.c_size_t(512))
+    if rc == 101:
+        raise ReferencePanic(err.value.decode())
+    assert rc == 0
+    return _take(out, n)
+
+
+def trim_pair(left: str, right: str, match_score=1, diff_score=1, indel_score=1, policy=RIGHTMOST):
+    """aligned_pairs on both + trim_overlapping_pafs (trim_overlap.rs:36-86); returns the two output lines."""
+    out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
+    rc = lib().orc_trim_pair(left.encode(), right.encode(), int(match_score), int(diff_score), int(indel_score), policy,
+                             C.byref(out), C.byref(n), err, C.c_size_t(512))
+    if rc == 101:
+        raise ReferencePanic(err.value.decode())
+    assert rc == 0, rc
+    return _take(out, n).decode().splitlines()
+
+
 def run_stats(paf: bytes, qbed=False) -> bytes:
     out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)
     rc = lib().orc_run_stats(paf, C.c_size_t(len(paf)), int(qbed), C.byref(out), C.byref(n), err, C.c_size_t(512))
