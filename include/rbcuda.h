@@ -184,6 +184,16 @@ int rb_break_paf(rb_ctx* ctx, const rb_records* recs, uint32_t max_size, int pol
  * FILE order — query and target columns swapped, I and D exchanged, the ops reversed on the '-' strand; nothing is stripped or
  * merged; nmatch / aln_len are the ones check_integrity infers from the CIGAR (paf.rs:825-857); id empty; win_idx = 0 */
 int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* out);
+/* replaces `paf.overlapping_paf_recs(match, diff, indel, remove_contained)` + the print loop of `rb trim-paf` (main.rs:218-230;
+ * paf.rs:210-305, trim_overlap.rs:36-86): records that overlap on the same query are cut at the split point that maximises
+ * (score of the left record before it) + (score of the right record after it), largest overlap first, one pair per query name
+ * and round until no pair is left.  One row per record, ordered by query name (stable, byte-wise — the reference's
+ * sort_by_key); rec_idx = the caller's record index, win_idx = 0; untouched records are printed as they are (after the indel
+ * strip), truncated ones re-collapsed.  Only RB_POLICY_RIGHTMOST is implemented for this call (RB_ERR_UNSUPPORTED otherwise);
+ * records must start and end on an M/=/X op after the strip.  Where a truncation leaves spans that disagree with the CIGAR the
+ * reference panics (paf.rs:819-822) -> RB_ERR_REF_INTEGRITY. */
+int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,
+                uint32_t want, rb_lift_out* out, rb_stats_out* stats /* nullable */);
 void rb_free_lift_out(rb_ctx* ctx, rb_lift_out* out);
 void rb_free_stats_out(rb_ctx* ctx, rb_stats_out* stats);
 

@@ -23,7 +23,7 @@ LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
     "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_set_slicing", "rb_ctx_kernel_times",
-    "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
+    "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_trim_paf", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
     "rb_host_unregister",
 ]
@@ -94,6 +94,8 @@ def load():
     lib.rb_stats.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.POINTER(RbStatsOut)]
     lib.rb_break_paf.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_uint32, C.c_int, C.c_uint32, C.POINTER(RbLiftOut), C.POINTER(RbStatsOut)]
     lib.rb_invert.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_uint32, C.POINTER(RbLiftOut)]
+    lib.rb_trim_paf.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(RbLiftOut),
+                                C.POINTER(RbStatsOut)]
     lib.rb_batch_break.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(RbSummary)]
     lib.rb_free_lift_out.argtypes = [C.c_void_p, C.POINTER(RbLiftOut)]
     lib.rb_free_stats_out.argtypes = [C.c_void_p, C.POINTER(RbStatsOut)]
@@ -245,6 +247,19 @@ class Context:
         """rb_break_paf: every record cut at its indels longer than max_size (liftover.rs:182-226), rows in file order."""
         out, st = RbLiftOut(), RbStatsOut()
         self._check(self.lib.rb_break_paf(self.h, C.byref(recs.c), max_size, policy, want, C.byref(out), C.byref(st) if stats else None))
+        res = self._collect_lift(out, st if stats else None, want) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
+        self.lib.rb_free_lift_out(self.h, C.byref(out))
+        if stats:
+            self.lib.rb_free_stats_out(self.h, C.byref(st))
+        return res
+
+    def trim_paf(self, recs: Records, match_score=1, diff_score=1, indel_score=1, remove_contained=False, policy=POLICY_RIGHTMOST,
+                 want=WANT_TEXT | WANT_NUMERIC, stats=True, copy=True):
+        """rb_trim_paf: query-overlapping records cut at their best split point (paf.rs:210-305, trim_overlap.rs:36-86); one row
+        per record, ordered by query name."""
+        out, st = RbLiftOut(), RbStatsOut()
+        self._check(self.lib.rb_trim_paf(self.h, C.byref(recs.c), int(match_score), int(diff_score), int(indel_score), int(bool(remove_contained)),
+                                         policy, want, C.byref(out), C.byref(st) if stats else None))
         res = self._collect_lift(out, st if stats else None, want) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
         self.lib.rb_free_lift_out(self.h, C.byref(out))
         if stats:

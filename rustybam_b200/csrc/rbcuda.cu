@@ -16,6 +16,7 @@
 #include "../../include/rbcuda.h"
 #include "rb_kernels.cuh"
 #include "rec_core.cuh"
+#include "trim_rounds.hpp"
 
 using namespace rb;
 
@@ -119,6 +120,8 @@ struct rb_batch {
     DevBuf ops, tile_state, heads, samples, blk_state, blk_agg, blk_pre, op_off, recs, pair_cnt, pair_off;
     DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans, orig_idx;
     DevBuf bp_cnt, bp_off, bp_end, bp_next, rec_bp;  // break-paf: break ops per chunk, their scan, piece boundaries
+    DevBuf trim_qp, trim_wp, trim_views, trim_sel, trim_out, trim_drop;  // trim-paf: per-op query / score prefixes, record views, one round's pairs
+    bool trim_has_drop = false;
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -446,7 +449,8 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->trim_qp, &b->trim_wp, &b->trim_views,
+                     &b->trim_sel, &b->trim_out, &b->trim_drop, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
     for (DevBuf* d : all) d->release();
     b->stage.release();
     b->wstage.release();
@@ -896,7 +900,7 @@ int rb_batch_stats(rb_ctx* ctx, rb_batch* b, rb_summary* summary) {
 }
 
 // plan -> lift (or combine) -> line scan -> [host: output sizes] -> serialise; shared by liftover and break-paf
-enum : int { TAIL_SEARCH = 0, TAIL_COMBINE = 1, TAIL_WHOLE = 2 };  // who fills PairRes: k_lift, k_combine, k_whole_rows (rb invert)
+enum : int { TAIL_SEARCH = 0, TAIL_COMBINE = 1, TAIL_WHOLE = 2, TAIL_TRIM = 3 };  // who fills PairRes: k_lift, k_combine, k_whole_rows (rb invert), k_trim_rows (rb trim-paf)
 static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail, uint32_t want, int with_stats, uint64_t P,
                      uint64_t n_ops, rb_summary* summary) {
     cudaStream_t s = ctx->stream;
@@ -906,12 +910,17 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     const uint32_t n = b->n_rec;
     int rc = RB_OK;
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
-    if (tail != TAIL_WHOLE) {
+    if (tail == TAIL_SEARCH || tail == TAIL_COMBINE) {
         KScope k(ctx, "k_lift_plan");
         launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
                          b->plans.as<LiftPlan>(), s);
     }
-    if (tail == TAIL_WHOLE) {
+    if (tail == TAIL_TRIM) {
+        KScope k(ctx, "k_trim_rows");
+        launch_trim_rows(n, b->recs.as<RecInfo>(), b->trim_views.as<TrimView>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(),
+                         b->trim_has_drop ? b->trim_drop.as<uint8_t>() : nullptr, b->pair_res.as<PairRes>(), b->line_len.as<uint32_t>(),
+                         b->pair_off.as<uint64_t>(), b->plans.as<LiftPlan>(), s);
+    } else if (tail == TAIL_WHOLE) {
         KScope k(ctx, "k_whole_rows");
         launch_whole_rows(n, b->recs.as<RecInfo>(), b->pair_res.as<PairRes>(), b->line_len.as<uint32_t>(), b->pair_off.as<uint64_t>(),
                           b->plans.as<LiftPlan>(), s);
@@ -1663,6 +1672,162 @@ int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* o
     rc = batch_invert(ctx, b, want & ~RB_WANT_QBED, nullptr);
     if (rc != RB_OK) return rc;
     return rb_batch_download_lift(ctx, b, want & ~RB_WANT_QBED, out, nullptr);
+}
+
+// replaces Paf::overlapping_paf_recs + the print loop of `rb trim-paf` (main.rs:218-230, paf.rs:210-305,
+// trim_overlap.rs:36-86): the round bookkeeping (which pairs of one query overlap, largest first, one pair per query name
+// and round) stays on the host and only ever looks at query spans; scores, split points and truncations run on the device.
+int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,
+                uint32_t want, rb_lift_out* out, rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out || !recs) return fail(ctx, RB_ERR_BAD_ARG, "recs / out is null");
+    if (policy != RB_POLICY_RIGHTMOST)
+        return fail(ctx, RB_ERR_UNSUPPORTED, "rb_trim_paf implements the right-most binary_search policy only (Rust < 1.52 / >= 1.82)");
+    if (recs->n_rec && (!recs->q_id || !recs->names_off || (!recs->names && recs->n_names && recs->names_off[recs->n_names])))
+        return fail(ctx, RB_ERR_BAD_ARG, "rb_records: null column");
+    cudaSetDevice(ctx->device);
+    if (!ctx->scratch) ctx->scratch = new rb_batch();
+    rb_batch* b = ctx->scratch;
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = recs->n_rec;
+    want &= ~RB_WANT_QBED;
+
+    // records.sort_by_key(|rec| rec.q_name.clone()) — stable, byte-wise (paf.rs:224)
+    for (uint32_t i = 0; i < n; i++)
+        if (recs->q_id[i] >= recs->n_names) return fail(ctx, RB_ERR_BAD_ARG, "name id out of range at record %u", i);
+    auto name_of = [&](uint32_t r, const uint8_t*& p, size_t& len) {
+        const uint32_t q = recs->q_id[r];
+        p = recs->names + recs->names_off[q];
+        len = (size_t)(recs->names_off[q + 1] - recs->names_off[q]);
+    };
+    auto name_cmp = [&](uint32_t x, uint32_t y) {
+        const uint8_t *px, *py;
+        size_t lx, ly;
+        name_of(x, px, lx); name_of(y, py, ly);
+        const int c = memcmp(px, py, lx < ly ? lx : ly);
+        return c ? c : (lx < ly ? -1 : (lx > ly ? 1 : 0));
+    };
+    std::vector<uint32_t> perm(n);
+    for (uint32_t i = 0; i < n; i++) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return name_cmp(x, y) < 0; });
+
+    const RecSel sel_all{perm.data(), 0, n};
+    b->file_order = true;
+    int rc = upload_cigar(ctx, b, recs, sel_all);
+    if (rc == RB_OK) rc = windows_prepare(ctx, b, recs, nullptr);
+    if (rc == RB_OK) rc = upload_columns(ctx, b, recs, sel_all);
+    b->file_order = false;
+    if (rc != RB_OK) {
+        if (b->busy) { cudaStreamSynchronize(s); b->busy = false; }
+        return rc;
+    }
+    b->have_lift = false;
+    rc = run_tok(ctx, b);
+    if (rc != RB_OK) return rc;
+    uint32_t* sc = ctx->scalars.as<uint32_t>();
+    ErrSlots err{reinterpret_cast<unsigned long long*>(sc + SC_ERR_TOK), reinterpret_cast<unsigned long long*>(sc + SC_ERR_REC)};
+    {   // remove_trailing_indels on every record (paf.rs:218-221)
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(1, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), nullptr, WinView{}, b->recs.as<RecInfo>(),
+                        b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+    }
+    rc = run_scan(ctx, b, nullptr);
+    if (rc != RB_OK) return rc;
+    {
+        KScope k(ctx, "k_rec_prep");
+        launch_rec_prep(2, rec_input(b), b->op_off.as<uint64_t>(), b->ops.as<uint32_t>(), b->samples.as<Ctr>(), WinView{},
+                        b->recs.as<RecInfo>(), b->pair_cnt.as<uint32_t>(), StatsDev{}, err, s);
+    }
+    volatile uint64_t* hs = reinterpret_cast<volatile uint64_t*>(ctx->h_scalars);
+    Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(2, b->op_off.as<uint64_t>() + n).u32(3, sc + SC_MISC).go(s);
+    CU(cudaStreamSynchronize(s));
+    b->busy = false;
+    if ((uint32_t)hs[3] & 1u) {
+        launch_check_clips(b->ops.as<uint32_t>(), b->op_off.as<uint64_t>(), n, err, s);
+        Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).go(s);
+        CU(cudaStreamSynchronize(s));
+    }
+    rc = map_err(ctx, b, hs[0], hs[1]);
+    if (rc != RB_OK) { flush_times(ctx); return rc; }
+    const uint64_t n_ops = hs[2];
+
+    // per-op query / score prefixes and the untruncated views
+    const TrimScores scores{match_score, diff_score, indel_score};
+    CU(b->trim_qp.ensure(b->ops_bound * 4 + 64));
+    CU(b->trim_wp.ensure(b->ops_bound * 8 + 64));
+    CU(b->trim_views.ensure((size_t)n * sizeof(TrimView) + 64));
+    CU(b->trim_sel.ensure(((size_t)n / 2 + 1) * sizeof(TrimPairSel)));
+    CU(b->trim_out.ensure(((size_t)n / 2 + 1) * 40));
+    {
+        KScope k(ctx, "k_trim_scan");
+        launch_trim_scan(b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), n, scores, b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(),
+                         b->trim_views.as<TrimView>(), s);
+    }
+    std::vector<TrimView> h_views(n);
+    if (n) CU(cudaMemcpyAsync(h_views.data(), b->trim_views.p, (size_t)n * sizeof(TrimView), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    std::vector<TrimSpan> spans(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (h_views[i].bad)
+            return fail(ctx, RB_ERR_UNSUPPORTED, "record %u: rb_trim_paf wants records that start and end on an M/=/X op after the indel strip", perm[i]);
+        spans[i].q_st = h_views[i].q_st; spans[i].q_en = h_views[i].q_en;
+        spans[i].name = i ? spans[i - 1].name + (name_cmp(perm[i - 1], perm[i]) != 0 ? 1u : 0u) : 0u;
+    }
+    const uint64_t max_score = (uint64_t)std::max({std::llabs((long long)match_score), std::llabs((long long)diff_score),
+                                                   std::llabs((long long)indel_score)});
+    std::vector<uint8_t> contained;
+    std::vector<TrimPairSel> sel;
+    struct PairOut { uint64_t l_st, l_en, r_st, r_en; uint32_t status, pad; };
+    std::vector<PairOut> pout;
+    for (uint64_t round = 0;; round++) {
+        const size_t waiting = trim_round(spans, contained, sel);
+        for (const TrimPairSel& p : sel)  // the reference sums the scores in i32 (trim_overlap.rs:52-69)
+            if ((p.en_ovl - p.st_ovl) * max_score >= (1ull << 31))
+                return fail(ctx, RB_ERR_UNSUPPORTED, "records %u / %u: overlap x score exceeds the reference's i32 sums", perm[p.left], perm[p.right]);
+        if (!sel.empty()) {
+            const uint32_t ns = (uint32_t)sel.size();
+            CU(cudaMemcpyAsync(b->trim_sel.p, sel.data(), (size_t)ns * sizeof(TrimPairSel), cudaMemcpyHostToDevice, s));
+            {
+                KScope k(ctx, "k_trim_pairs");
+                launch_trim_pairs(b->trim_sel.p, ns, b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(),
+                                  b->trim_wp.as<long long>(), scores, b->trim_views.as<TrimView>(), b->trim_out.p, s);
+            }
+            pout.resize(ns);
+            CU(cudaMemcpyAsync(pout.data(), b->trim_out.p, (size_t)ns * sizeof(PairOut), cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            for (uint32_t i = 0; i < ns; i++) {
+                if (pout[i].status != 0) {
+                    flush_times(ctx);
+                    return fail(ctx, RB_ERR_REF_INTEGRITY, "records %u / %u: truncate_record_by_query leaves spans that disagree with the CIGAR "
+                                "(check_integrity().unwrap() panics, paf.rs:819-822)", perm[sel[i].left], perm[sel[i].right]);
+                }
+                spans[sel[i].left].q_st = pout[i].l_st; spans[sel[i].left].q_en = pout[i].l_en;
+                spans[sel[i].right].q_st = pout[i].r_st; spans[sel[i].right].q_en = pout[i].r_en;
+            }
+        }
+        if (waiting == 0) break;
+        if (round > (uint64_t)n * n + 8) return fail(ctx, RB_ERR_UNSUPPORTED, "trim rounds do not converge");
+    }
+    b->trim_has_drop = remove_contained != 0 && n > 0;
+    if (b->trim_has_drop) {
+        CU(b->trim_drop.ensure((size_t)n + 64));
+        CU(cudaMemcpyAsync(b->trim_drop.p, contained.data(), n, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));  // `contained` is a pageable local
+    }
+    const uint64_t P = n;
+    CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
+    CU(b->line_len.ensure(P * 4 + 64));
+    CU(b->line_off.ensure((P + 1) * 8 + 64));
+    CU(b->out_idx.ensure((P + 1) * 8 + 64));
+    CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
+    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
+    CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
+    WinView win{};
+    win.from_record = 1u;  // a row's id is its record's: empty, or the "_TO.." suffix of the indel strip
+    rc = lift_tail(ctx, b, win, RB_POLICY_RIGHTMOST, TAIL_TRIM, want, stats != nullptr, P, n_ops, nullptr);
+    if (rc != RB_OK) return rc;
+    return rb_batch_download_lift(ctx, b, want, out, stats);
 }
 
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {

@@ -4,6 +4,7 @@
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
 //     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
 //     rb [-t N] invert [PAF|-]                          (src/cli.rs:89-94, main.rs:176-182)
+//     rb [-t N] trim-paf [-m M] [-d D] [-i I] [-r] [PAF|-]   (aliases trim, tp; src/cli.rs:117-138, main.rs:218-230)
 // Text (plain / .gz / .bgz / stdin) is read and split on the host; CIGAR tokenising, liftover,
 // trimming, serialisation and identity counting run on the B200 through include/rbcuda.h.
 // Exit status 101 where the reference panics.  There is no CPU fallback: without an sm_100
@@ -17,7 +18,8 @@
 
 static int usage() {
     fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n"
-                    "       rb [-t N] break-paf [--max-size N] [PAF]\n       rb [-t N] invert [PAF]\n");
+                    "       rb [-t N] break-paf [--max-size N] [PAF]\n       rb [-t N] invert [PAF]\n"
+                    "       rb [-t N] trim-paf [-m M] [-d D] [-i I] [-r] [PAF]\n");
     return 2;
 }
 
@@ -26,8 +28,18 @@ int main(int argc, char** argv) {
     bool qbed = false, largest = false, paf_flag = false;
     int policy = RB_POLICY_RIGHTMOST;
     unsigned long max_size = 100;  // cli.rs:163
+    int match_score = 1, diff_score = 1, indel_score = 1;  // cli.rs:126-134
+    bool remove_contained = false;
+    bool is_trim = false;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
+        if (cmd.empty() && (a == "trim-paf" || a == "trim" || a == "tp")) { cmd = "trim-paf"; is_trim = true; continue; }
+        if (is_trim) {  // trim-paf reuses short flags of other subcommands (-m, -i, -d, -r)
+            if ((a == "-m" || a == "--match-score") && i + 1 < argc) { match_score = atoi(argv[++i]); continue; }
+            if ((a == "-d" || a == "--diff-score") && i + 1 < argc) { diff_score = atoi(argv[++i]); continue; }
+            if ((a == "-i" || a == "--indel-score") && i + 1 < argc) { indel_score = atoi(argv[++i]); continue; }
+            if (a == "-r" || a == "--remove-contained") { remove_contained = true; continue; }
+        }
         if ((a == "-t" || a == "--threads") && i + 1 < argc) i++;  // accepted for compatibility; the GPU path has no thread knob
         else if (a == "-v" || a == "-vv" || a == "-vvv") {}
         else if ((a == "--bed" || a == "-b") && i + 1 < argc) bed = argv[++i];
@@ -41,7 +53,7 @@ int main(int argc, char** argv) {
     }
     const bool brk = (cmd == "break-paf" || cmd == "breakpaf" || cmd == "bp");
     const bool inv = (cmd == "invert");
-    if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk && !inv) return usage();
+    if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk && !inv && !is_trim) return usage();
     int status = 0;
     rb_ctx* ctx = rb_ctx_create(nullptr, 0, &status);
     if (!ctx) {
@@ -68,6 +80,16 @@ int main(int argc, char** argv) {
             rb_records recs = paf.view();
             rb_lift_out out{};
             rc = rb_break_paf(ctx, &recs, (uint32_t)max_size, policy, RB_WANT_TEXT, &out, nullptr);
+            if (rc == RB_OK) {
+                fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
+                rb_free_lift_out(ctx, &out);
+            }
+        } else if (is_trim) {
+            rbh::Paf paf = rbh::Paf::from_file(input);
+            if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
+            rb_records recs = paf.view();
+            rb_lift_out out{};
+            rc = rb_trim_paf(ctx, &recs, match_score, diff_score, indel_score, remove_contained ? 1 : 0, policy, RB_WANT_TEXT, &out, nullptr);
             if (rc == RB_OK) {
                 fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
                 rb_free_lift_out(ctx, &out);

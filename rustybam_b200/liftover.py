@@ -67,6 +67,23 @@ def paf_swap_query_and_target(ctx, paf: Paf, want=WANT_TEXT | WANT_NUMERIC):
         raise
 
 
+def overlapping_paf_recs(ctx, paf: Paf, match_score=1, diff_score=1, indel_score=1, remove_contained=False, policy=POLICY_RIGHTMOST,
+                         stats=False, want=WANT_TEXT | WANT_NUMERIC):
+    """Paf::overlapping_paf_recs + the print loop of `rb trim-paf` (src/paf.rs:210-305, src/trim_overlap.rs:36-86, driver
+    src/main.rs:218-230) on the GPU: res["paf_text"] is what `rb trim-paf` prints (rows ordered by query name)."""
+    try:
+        return ctx.trim_paf(paf.pack(), match_score, diff_score, indel_score, remove_contained, policy=policy, want=want, stats=stats)
+    except RbError as e:
+        if e.code in REF_PANIC_CODES:
+            raise ReferencePanic(str(e)) from e
+        raise
+
+
+def run_trim_paf(ctx, paf_text: bytes, match_score=1, diff_score=1, indel_score=1, remove_contained=False) -> bytes:
+    """`rb trim-paf [-m M] [-d D] [-i I] [-r] PAF`: stdout bytes."""
+    return overlapping_paf_recs(ctx, Paf.from_text(paf_text), match_score, diff_score, indel_score, remove_contained, want=WANT_TEXT)["paf_text"]
+
+
 def run_invert(ctx, paf_text: bytes) -> bytes:
     """`rb invert PAF`: stdout bytes."""
     return paf_swap_query_and_target(ctx, Paf.from_text(paf_text), want=WANT_TEXT)["paf_text"]

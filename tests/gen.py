@@ -107,3 +107,31 @@ def bed_text(rows, with_ids):
     for i, (n, s, e) in enumerate(rows):
         out.append(f"{n}\t{s}\t{e}\tw{i}\n" if with_ids else f"{n}\t{s}\t{e}\n")
     return "".join(out).encode()
+
+
+def random_trim_paf(seed, n_names=4, recs_per_name=4, max_ops=60, style="eqx", canonical=True, allow_zero=False, lead_trail=True,
+                    span=80, big=0):
+    """PAF text for `rb trim-paf`: records that share query names and overlap on the query (both strands), each starting and
+    ending on an M/=/X op (after the strip of optional leading / trailing indels).  `big` > 0: that many records get ~20x the
+    ops (several scan tiles per record, thousands of split-point candidates per pair)."""
+    rng = random.Random(seed)
+    lines = []
+    for nm in range(n_names):
+        for r in range(rng.randint(1, recs_per_name)):
+            n_ops = rng.randint(1, max_ops) * (20 if len(lines) < big else 1)
+            body = random_cigar(rng, n_ops + 2, style, canonical, allow_zero=allow_zero)
+            if body[0][0] == 0:
+                body[0] = (1, body[0][1])
+            if body[-1][0] == 0:
+                body[-1] = (1, body[-1][1])
+            if lead_trail and rng.random() < 0.2:
+                body = [(rng.randint(1, 4), "I")] + body
+            if lead_trail and rng.random() < 0.2:
+                body = body + [(rng.randint(1, 4), rng.choice("ID"))]
+            t, q = spans(body)
+            t_st = rng.randint(1, 4000)
+            q_st = rng.randint(0, span)
+            lines.append([f"query_{nm}", 10 ** 6, q_st, q_st + q, rng.choice("+-"), f"chr{rng.randint(1, 3)}", 10 ** 7, t_st, t_st + t, 0, 0,
+                          rng.randint(0, 60), "tp:A:P", f"cg:Z:{cigar_str(body)}"])
+    rng.shuffle(lines)  # names interleave in the file: the stable sort by query name has work to do
+    return "".join("\t".join(str(x) for x in ln) + "\n" for ln in lines).encode()

@@ -27,7 +27,8 @@ struct TestRec {
     std::vector<uint32_t> ops;
     uint64_t t_st, t_en, q_st, q_en, q_len, t_len;
     char strand;
-    std::string q_name, line;
+    std::string q_name, t_name, line;
+    uint64_t mapq = 60;
 };
 
 static std::string cig_text(const std::vector<uint32_t>& ops, size_t a, size_t b) {
@@ -36,65 +37,26 @@ static std::string cig_text(const std::vector<uint32_t>& ops, size_t a, size_t b
     return s;
 }
 
-int main(int argc, char** argv) {
-    const unsigned seed = argc > 1 ? (unsigned)atoi(argv[1]) : 1;
-    const int n_groups = argc > 2 ? atoi(argv[2]) : 500;
-    std::mt19937_64 rng(seed);
+
+struct Counts { long n_fail = 0, n_abort = 0, n_trimmed = 0, n_rows = 0, n_rounds_max = 0, n_unsup = 0; };
+
+// one PAF text through the oracle and through the product's closed form; `recs` come from the oracle's own line parser
+static void check_text(const std::string& text, TrimScores sc, bool remove_contained, std::mt19937_64& rng, Counts& C, int g) {
     auto U = [&](uint64_t lo, uint64_t hi) { return lo + rng() % (hi - lo + 1); };
-    long n_fail = 0, n_abort = 0, n_trimmed = 0, n_rows = 0, n_rounds_max = 0, n_unsup = 0;
-
-    for (int g = 0; g < n_groups; g++) {
-        // ---- one PAF: a few query names, a few records each ----
-        std::vector<TestRec> recs;
-        const int n_names = (int)U(1, 3);
-        const int style = (int)U(0, 9);
-        for (int nm = 0; nm < n_names; nm++) {
-            const int n_rec = (int)U(1, 5);
-            for (int r = 0; r < n_rec; r++) {
-                TestRec tr;
-                const int n_ops = (int)U(1, style == 0 ? 60 : 16);
-                std::vector<uint32_t> body;
-                auto push = [&](uint32_t code, uint32_t len) { body.push_back((len << 4) | code); };
-                if (U(0, 5) == 0) push(OP_I, (uint32_t)U(1, 4));  // stripped at load
-                static const uint32_t ends[] = {OP_EQ, OP_EQ, OP_X, OP_M};
-                static const uint32_t codes_eqx[] = {OP_EQ, OP_EQ, OP_EQ, OP_X, OP_I, OP_D};
-                static const uint32_t codes_all[] = {OP_EQ, OP_X, OP_M, OP_I, OP_D, OP_N, OP_P, OP_EQ, OP_I, OP_D, OP_X};
-                push(ends[U(0, 3)], (uint32_t)U(1, 6));
-                uint32_t prev = op_code(body.back());
-                for (int j = 0; j < n_ops; j++) {
-                    uint32_t code = style < 6 ? codes_eqx[U(0, 5)] : codes_all[U(0, 10)];
-                    if (style < 8 && code == prev) code = (code == OP_EQ) ? OP_X : OP_EQ;
-                    uint32_t len = (uint32_t)(U(0, 3) == 0 ? U(1, 30) : U(1, 4));
-                    if (style == 9 && U(0, 6) == 0) len = 0;
-                    push(code, len);
-                    prev = code;
-                }
-                push(ends[U(0, 3)], (uint32_t)U(1, 6));
-                if (U(0, 5) == 0) push(U(0, 1) ? OP_D : OP_I, (uint32_t)U(1, 4));
-                tr.ops = body;
-                uint64_t T = 0, Q = 0;
-                for (uint32_t w : body) {
-                    if (is_ref(op_code(w))) T += op_len(w);
-                    if (is_qry(op_code(w))) Q += op_len(w);
-                }
-                tr.t_st = U(1, 500); tr.t_en = tr.t_st + T; tr.t_len = tr.t_en + U(0, 20);
-                tr.q_st = U(0, 80); tr.q_en = tr.q_st + Q; tr.q_len = 400;
-                tr.strand = U(0, 1) ? '+' : '-';
-                tr.q_name = "q" + std::to_string(nm);
-                tr.line = tr.q_name + "\t" + std::to_string(tr.q_len) + "\t" + std::to_string(tr.q_st) + "\t" +
-                          std::to_string(tr.q_en) + "\t" + tr.strand + "\tchrT\t" + std::to_string(tr.t_len) + "\t" +
-                          std::to_string(tr.t_st) + "\t" + std::to_string(tr.t_en) + "\t0\t0\t60\tcg:Z:" + cig_text(body, 0, body.size());
-                recs.push_back(std::move(tr));
-            }
+    long &n_fail = C.n_fail, &n_abort = C.n_abort, &n_trimmed = C.n_trimmed, &n_rows = C.n_rows, &n_rounds_max = C.n_rounds_max, &n_unsup = C.n_unsup;
+    std::vector<TestRec> recs;
+    try {
+        orc::Paf parsed = orc::Paf::from_text(text.data(), text.size());
+        for (const orc::PafRecord& p : parsed.records) {
+            TestRec tr;
+            for (const orc::Cig& c : p.cigar) tr.ops.push_back((c.len << 4) | c.op);
+            tr.t_st = p.t_st; tr.t_en = p.t_en; tr.q_st = p.q_st; tr.q_en = p.q_en; tr.q_len = p.q_len; tr.t_len = p.t_len;
+            tr.strand = p.strand; tr.q_name = p.q_name; tr.t_name = p.t_name; tr.mapq = p.mapq;
+            recs.push_back(std::move(tr));
         }
-        std::shuffle(recs.begin(), recs.end(), rng);  // file order mixes the names: the stable sort has work to do
-        TrimScores sc{(int32_t)U(1, 3), (int32_t)U(0, 3), (int32_t)U(0, 3)};
-        if (U(0, 2) == 0) sc = TrimScores{1, 1, 1};
-        const bool remove_contained = U(0, 1) == 1;
-
+    } catch (const orc::Abort&) { n_abort++; return; }
+    do {
         // ---- oracle ----
-        std::string text;
-        for (auto& tr : recs) text += tr.line + "\n";
         std::string want;
         bool aborted = false;
         try {
@@ -150,7 +112,7 @@ int main(int argc, char** argv) {
             R = RecInfo{};
             R.op_first = op_off[r]; R.op_end = op_off[r + 1];
             R.t_st = tr.t_st; R.t_en = tr.t_en; R.q_st0 = tr.q_st; R.q_en0 = tr.q_en;
-            R.q_len = tr.q_len; R.t_len = tr.t_len; R.mapq = 60;
+            R.q_len = tr.q_len; R.t_len = tr.t_len; R.mapq = tr.mapq;
             R.flags = tr.strand == '-' ? RF_MINUS : 0;
             if (strip_record(ops.data(), R) != RE_OK) { strip_abort = true; break; }
             for (uint64_t k = R.op_first; k < R.op_end; k++) {
@@ -178,9 +140,9 @@ int main(int argc, char** argv) {
         if (strip_abort) {
             if (!aborted) { n_fail++; fprintf(stderr, "FAIL strip abort but oracle ran\n%s", text.c_str()); }
             else n_abort++;
-            continue;
+            break;
         }
-        if (unsupported) { n_unsup++; continue; }
+        if (unsupported) { n_unsup++; break; }
         TrimArr arr{qp.data(), wp.data()};
         std::vector<uint8_t> contained;
         std::vector<TrimPairSel> sel;
@@ -212,9 +174,9 @@ int main(int argc, char** argv) {
         if (p_abort != aborted) {
             n_fail++;
             if (n_fail < 10) fprintf(stderr, "FAIL abort mismatch product=%d oracle=%d scores %d %d %d\n%s", (int)p_abort, (int)aborted, sc.match, sc.diff, sc.indel, text.c_str());
-            continue;
+            break;
         }
-        if (aborted) { n_abort++; continue; }
+        if (aborted) { n_abort++; break; }
         std::string got;
         for (size_t r = 0; r < order.size(); r++) {
             if (remove_contained && contained[r]) continue;
@@ -235,8 +197,8 @@ int main(int argc, char** argv) {
             } else { n_fail++; fprintf(stderr, "FAIL dropped row\n"); }
             if (cg.size() != pr.cg_bytes) { n_fail++; fprintf(stderr, "FAIL cg_bytes %u vs %zu\n", pr.cg_bytes, cg.size()); }
             got += tr.q_name + "\t" + std::to_string(tr.q_len) + "\t" + std::to_string(pr.q_st) + "\t" + std::to_string(pr.q_en) + "\t" +
-                   tr.strand + "\tchrT\t" + std::to_string(tr.t_len) + "\t" + std::to_string(pr.t_st) + "\t" + std::to_string(pr.t_en) + "\t" +
-                   std::to_string(pr.nmatch) + "\t" + std::to_string(pr.aln_len) + "\t60\tid:Z:" + id + "\tcg:Z:" + cg + "\n";
+                   tr.strand + "\t" + tr.t_name + "\t" + std::to_string(tr.t_len) + "\t" + std::to_string(pr.t_st) + "\t" + std::to_string(pr.t_en) + "\t" +
+                   std::to_string(pr.nmatch) + "\t" + std::to_string(pr.aln_len) + "\t" + std::to_string(tr.mapq) + "\tid:Z:" + id + "\tcg:Z:" + cg + "\n";
             n_rows++;
         }
         if (got != want) {
@@ -245,8 +207,85 @@ int main(int argc, char** argv) {
                 fprintf(stderr, "FAIL group %d scores %d %d %d remove_contained %d\n in:\n%s got:\n%s want:\n%s\n", g, sc.match, sc.diff, sc.indel,
                         (int)remove_contained, text.c_str(), got.c_str(), want.c_str());
         }
+    
+    } while (0);
+}
+int main(int argc, char** argv) {
+    Counts C;
+    if (argc > 1 && strcmp(argv[1], "--paf") == 0) {  // trim_core_check --paf FILE [match diff indel remove_contained]
+        FILE* f = fopen(argv[2], "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
+        std::string text;
+        char buf[1 << 16];
+        size_t k;
+        while ((k = fread(buf, 1, sizeof buf, f)) > 0) text.append(buf, k);
+        fclose(f);
+        TrimScores sc{argc > 3 ? atoi(argv[3]) : 1, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atoi(argv[5]) : 1};
+        std::mt19937_64 rng(7);
+        check_text(text, sc, argc > 6 && atoi(argv[6]) != 0, rng, C, 0);
+        printf("aborts=%ld unsupported=%ld trimmed_pairs=%ld rows=%ld max_rounds=%ld FAIL=%ld\n", C.n_abort, C.n_unsup, C.n_trimmed, C.n_rows, C.n_rounds_max, C.n_fail);
+        return C.n_fail ? 1 : 0;
     }
-    printf("groups=%d aborts=%ld unsupported=%ld trimmed_pairs=%ld rows=%ld max_rounds=%ld FAIL=%ld\n", n_groups, n_abort, n_unsup, n_trimmed, n_rows,
-           n_rounds_max, n_fail);
-    return n_fail ? 1 : 0;
+
+    const unsigned seed = argc > 1 ? (unsigned)atoi(argv[1]) : 1;
+    const int n_groups = argc > 2 ? atoi(argv[2]) : 500;
+    std::mt19937_64 rng(seed);
+    auto U = [&](uint64_t lo, uint64_t hi) { return lo + rng() % (hi - lo + 1); };
+
+    for (int g = 0; g < n_groups; g++) {
+        // ---- one PAF: a few query names, a few records each ----
+        std::vector<TestRec> recs;
+        const int n_names = (int)U(1, 3);
+        const int style = (int)U(0, 9);
+        for (int nm = 0; nm < n_names; nm++) {
+            const int n_rec = (int)U(1, 5);
+            for (int r = 0; r < n_rec; r++) {
+                TestRec tr;
+                const int n_ops = (int)U(1, style == 0 ? 60 : 16);
+                std::vector<uint32_t> body;
+                auto push = [&](uint32_t code, uint32_t len) { body.push_back((len << 4) | code); };
+                if (U(0, 5) == 0) push(OP_I, (uint32_t)U(1, 4));  // stripped at load
+                static const uint32_t ends[] = {OP_EQ, OP_EQ, OP_X, OP_M};
+                static const uint32_t codes_eqx[] = {OP_EQ, OP_EQ, OP_EQ, OP_X, OP_I, OP_D};
+                static const uint32_t codes_all[] = {OP_EQ, OP_X, OP_M, OP_I, OP_D, OP_N, OP_P, OP_EQ, OP_I, OP_D, OP_X};
+                push(ends[U(0, 3)], (uint32_t)U(1, 6));
+                uint32_t prev = op_code(body.back());
+                for (int j = 0; j < n_ops; j++) {
+                    uint32_t code = style < 6 ? codes_eqx[U(0, 5)] : codes_all[U(0, 10)];
+                    if (style < 8 && code == prev) code = (code == OP_EQ) ? OP_X : OP_EQ;
+                    uint32_t len = (uint32_t)(U(0, 3) == 0 ? U(1, 30) : U(1, 4));
+                    if (style == 9 && U(0, 6) == 0) len = 0;
+                    push(code, len);
+                    prev = code;
+                }
+                push(ends[U(0, 3)], (uint32_t)U(1, 6));
+                if (U(0, 5) == 0) push(U(0, 1) ? OP_D : OP_I, (uint32_t)U(1, 4));
+                tr.ops = body;
+                uint64_t T = 0, Q = 0;
+                for (uint32_t w : body) {
+                    if (is_ref(op_code(w))) T += op_len(w);
+                    if (is_qry(op_code(w))) Q += op_len(w);
+                }
+                tr.t_st = U(1, 500); tr.t_en = tr.t_st + T; tr.t_len = tr.t_en + U(0, 20);
+                tr.q_st = U(0, 80); tr.q_en = tr.q_st + Q; tr.q_len = 400;
+                tr.strand = U(0, 1) ? '+' : '-';
+                tr.q_name = "q" + std::to_string(nm); tr.t_name = "chrT";
+                tr.line = tr.q_name + "\t" + std::to_string(tr.q_len) + "\t" + std::to_string(tr.q_st) + "\t" +
+                          std::to_string(tr.q_en) + "\t" + tr.strand + "\t" + tr.t_name + "\t" + std::to_string(tr.t_len) + "\t" +
+                          std::to_string(tr.t_st) + "\t" + std::to_string(tr.t_en) + "\t0\t0\t60\tcg:Z:" + cig_text(body, 0, body.size());
+                recs.push_back(std::move(tr));
+            }
+        }
+        std::shuffle(recs.begin(), recs.end(), rng);  // file order mixes the names: the stable sort has work to do
+        TrimScores sc{(int32_t)U(1, 3), (int32_t)U(0, 3), (int32_t)U(0, 3)};
+        if (U(0, 2) == 0) sc = TrimScores{1, 1, 1};
+        const bool remove_contained = U(0, 1) == 1;
+
+        std::string text;
+        for (auto& tr : recs) text += tr.line + "\n";
+        check_text(text, sc, remove_contained, rng, C, g);
+    }
+    printf("groups=%d aborts=%ld unsupported=%ld trimmed_pairs=%ld rows=%ld max_rounds=%ld FAIL=%ld\n", n_groups, C.n_abort, C.n_unsup, C.n_trimmed, C.n_rows,
+           C.n_rounds_max, C.n_fail);
+    return C.n_fail ? 1 : 0;
 }
