@@ -1757,7 +1757,7 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     CU(b->trim_wp.ensure(b->ops_bound * 8 + 64));
     CU(b->trim_views.ensure((size_t)n * sizeof(TrimView) + 64));
     CU(b->trim_sel.ensure(((size_t)n / 2 + 1) * sizeof(TrimPairSel)));
-    CU(b->trim_out.ensure(((size_t)n / 2 + 1) * 40));
+    CU(b->trim_out.ensure(((size_t)n / 2 + 1) * 48));  // 40 B of results + the 8-byte arg-max key per pair
     {
         KScope k(ctx, "k_trim_scan");
         launch_trim_scan(b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), n, scores, b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(),
@@ -1790,7 +1790,8 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
             {
                 KScope k(ctx, "k_trim_pairs");
                 launch_trim_pairs(b->trim_sel.p, ns, b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(),
-                                  b->trim_wp.as<long long>(), scores, b->trim_views.as<TrimView>(), b->trim_out.p, s);
+                                  b->trim_wp.as<long long>(), scores, b->trim_views.as<TrimView>(),
+                                  reinterpret_cast<unsigned long long*>(b->trim_out.as<uint8_t>() + ((size_t)n / 2 + 1) * 40), b->trim_out.p, s);
             }
             pout.resize(ns);
             CU(cudaMemcpyAsync(pout.data(), b->trim_out.p, (size_t)ns * sizeof(PairOut), cudaMemcpyDeviceToHost, s));

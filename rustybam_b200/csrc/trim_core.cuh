@@ -122,25 +122,75 @@ RB_HD long long trim_val(const OpsView& v, const TrimArr& a, const RecInfo& rl, 
                          uint64_t A, uint64_t c, const TrimScores& sc) {
     return trim_S(v, a, rl, tl, A, c, sc) - trim_S(v, a, rr, tr, A, c, sc);
 }
-// Candidate split points contributed by record `rx` (either of the pair): the op boundaries (and the one-base segments
-// in front of non-query runs) that fall into [A, B].  Work item t of n (a thread of the block; 0 of 1 on the host).
-RB_HD void trim_scan_candidates(const OpsView& v, const TrimArr& a, const RecInfo& rx, const RecInfo& rl, const TrimView& tl,
-                                const RecInfo& rr, const TrimView& tr, uint64_t A, uint64_t B, const TrimScores& sc, uint32_t t,
-                                uint32_t n, TrimBest& best) {
+// What the arg-max needs to know about one record of a pair, computed once per pair (and thread): the cumulative score at
+// the overlap start, and the view-end correction of trim_S as a (position, delta) pair.
+struct TrimSide {
+    long long g_A;     // trim_G at the overlap start A (in the record's own column order)
+    long long delta;   // 0, or what the view's last column gains by having lost its non-query tail
+    uint64_t pe;       // absolute query position of that column
+    uint32_t minus;
+};
+RB_HD TrimSide trim_side(const OpsView& v, const TrimArr& a, const RecInfo& r, const TrimView& tv, uint64_t A, const TrimScores& sc) {
+    TrimSide s;
+    s.minus = (r.flags & RF_MINUS) ? 1u : 0u;
+    s.g_A = trim_G(v, a, r, tv, s.minus ? (uint32_t)(r.q_en0 - A) : (uint32_t)(A - r.q_st0), sc);
+    s.delta = 0; s.pe = 0;
+    const uint32_t we = v.op(tv.ei);
+    if (tv.eo == op_len(we) - 1u) {
+        const uint32_t tail = trim_tail(v, tv.ei, r.eo1 - 1);
+        if (tail != TRIM_NO_TAIL) {
+            const uint32_t xe = a.qp[tv.ei] + tv.eo;
+            s.pe = s.minus ? r.q_en0 - 1 - xe : r.q_st0 + xe;
+            s.delta = trim_col_score(op_code(we), sc) - trim_col_score(tail, sc);
+        }
+    }
+    return s;
+}
+// trim_S over [A, c) from the cumulative score g_c at c (== trim_S(v, a, r, tv, A, c, sc) for A < c)
+RB_HD long long trim_S_at(const TrimSide& s, uint64_t A, uint64_t c, long long g_c) {
+    long long x = s.minus ? s.g_A - g_c : g_c - s.g_A;
+    if (s.delta != 0 && s.pe >= A && s.pe < c) x += s.delta;
+    return x;
+}
+// cumulative score of record r at absolute query position c (one search)
+RB_HD long long trim_G_at(const OpsView& v, const TrimArr& a, const RecInfo& r, const TrimView& tv, uint64_t c, const TrimScores& sc) {
+    return trim_G(v, a, r, tv, (r.flags & RF_MINUS) ? (uint32_t)(r.q_en0 - c) : (uint32_t)(c - r.q_st0), sc);
+}
+// Candidate split points contributed by record `rx` (`x_is_left`: which of the pair it is): the op boundaries (and the
+// one-base segments in front of non-query runs) that fall into [A, B].  Work item t of n (a thread of the grid; 0 of 1 on
+// the host).  The record's own cumulative score at its op boundaries comes straight from wp — only the OTHER record is
+// searched, once per candidate.
+RB_HD void trim_scan_candidates(const OpsView& v, const TrimArr& a, bool x_is_left, const RecInfo& rl, const TrimView& tl, const TrimSide& sl,
+                                const RecInfo& rr, const TrimView& tr, const TrimSide& sr, uint64_t A, uint64_t B, const TrimScores& sc,
+                                uint32_t t, uint32_t n, TrimBest& best) {
+    const RecInfo& rx = x_is_left ? rl : rr;
+    const RecInfo& ry = x_is_left ? rr : rl;
+    const TrimView& ty = x_is_left ? tr : tl;
+    const TrimSide& sx = x_is_left ? sl : sr;
+    const TrimSide& sy = x_is_left ? sr : sl;
     uint64_t k0 = trim_find_q(a, rx.eo0, rx.eo1, trim_x(rx, A)), k1 = trim_find_q(a, rx.eo0, rx.eo1, trim_x(rx, B - 1));
     if (k0 > k1) { const uint64_t tmp = k0; k0 = k1; k1 = tmp; }
     const bool minus = (rx.flags & RF_MINUS) != 0;
     for (uint64_t k = k0 + t; k <= k1; k += n) {
         const uint32_t w = v.op(k), L = op_len(w);
         if (L == 0 || !is_qry(op_code(w))) continue;
-        uint64_t lo, hi, mid;
-        if (minus) { hi = rx.q_en0 - a.qp[k]; lo = hi - L; mid = lo + 1; }
-        else { lo = rx.q_st0 + a.qp[k]; hi = lo + L; mid = hi - 1; }
-        const uint64_t cand[3] = {lo, mid, hi};
+        const long long s1 = trim_col_score(op_code(w), sc);
+        const long long g0 = a.wp[k], gm = g0 + (long long)(L - 1u) * s1, g1 = g0 + trim_w_op(v, k, rx.eo1, sc);
+        uint64_t cand[3];
+        long long gx[3];
+        if (minus) {  // columns run against the query: the op's first column is its highest query position
+            const uint64_t hi = rx.q_en0 - a.qp[k], lo = hi - L;
+            cand[0] = hi; gx[0] = g0; cand[1] = lo + 1; gx[1] = gm; cand[2] = lo; gx[2] = g1;
+        } else {
+            const uint64_t lo = rx.q_st0 + a.qp[k], hi = lo + L;
+            cand[0] = lo; gx[0] = g0; cand[1] = hi - 1; gx[1] = gm; cand[2] = hi; gx[2] = g1;
+        }
         for (int i = 0; i < 3; i++) {
             const uint64_t c = cand[i];
-            if (c < A || c > B) continue;
-            trim_best_merge(best, trim_val(v, a, rl, tl, rr, tr, A, c, sc), c);
+            if (c <= A || c > B) continue;  // c == A is one of the fixed candidates (value 0)
+            const long long own = trim_S_at(sx, A, c, gx[i]);
+            const long long other = trim_S_at(sy, A, c, trim_G_at(v, a, ry, ty, c, sc));
+            trim_best_merge(best, x_is_left ? own - other : other - own, c);
         }
     }
 }
@@ -149,6 +199,18 @@ RB_HD void trim_fixed_candidates(const OpsView& v, const TrimArr& a, const RecIn
     const uint64_t cand[4] = {A, A + 1, B - 1, B};
     for (int i = 0; i < 4; i++)
         if (cand[i] >= A && cand[i] <= B) trim_best_merge(best, trim_val(v, a, rl, tl, rr, tr, A, cand[i], sc), cand[i]);
+}
+// The arg-max as one 64-bit key for atomicMax across the blocks of a pair: larger total first, then the smaller split point.
+// |total| < 2^31 (the reference sums in i32; the caller refuses overlaps whose sums could leave that range) and
+// c - A < 2^32 (per-record query sums are below 2^32).
+RB_HD unsigned long long trim_key(const TrimBest& b, uint64_t A) {
+    return ((unsigned long long)(b.total + 2147483648ll) << 32) | (unsigned long long)(~(uint32_t)(b.c - A));
+}
+RB_HD TrimBest trim_unkey(unsigned long long key, uint64_t A) {
+    TrimBest b;
+    b.total = (long long)(key >> 32) - 2147483648ll;
+    b.c = A + (uint64_t)(~(uint32_t)key);
+    return b;
 }
 // split point from the arg-max over all candidates (trim_overlap.rs:71-77: `if l + r > max` starting from max = 0)
 RB_HD uint64_t trim_split(const TrimBest& best, long long r_tot, uint64_t A) { return (best.total + r_tot > 0) ? best.c : A; }

@@ -3,8 +3,9 @@
 // file only spreads it over the machine:
 //   k_trim_scan   per record: segmented exclusive scan of (query advance, position score) over its ops -> qp / wp
 //                 (12 B per op), the record's total score and its untruncated view
-//   k_trim_pairs  per selected pair of one round (one block each): every thread evaluates the split-point candidates
-//                 of a stride of both records' ops in the overlap, block arg-max, then the two truncations
+//   k_trim_pairs  per selected pair of one round (a column of blocks each): every thread evaluates the split-point
+//                 candidates of a stride of both records' ops in the overlap; warp arg-max, atomicMax on a packed key
+//   k_trim_cut    per selected pair: the split point from the key, then the two truncations
 //   k_trim_rows   per record after the last round: the printed row (PairRes + line size) for the shared serialiser
 #include <climits>
 
@@ -87,12 +88,14 @@ k_trim_scan(const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs, 
 struct TrimPairDev { uint32_t left, right; uint64_t st_ovl, en_ovl; };  // == TrimPairSel (trim_rounds.hpp)
 struct TrimPairOut { uint64_t l_st, l_en, r_st, r_en; uint32_t status, pad; };
 
+// grid = (pairs of this round, slices): every thread of every slice of a pair evaluates a stride of both records' ops in the
+// overlap (coalesced: consecutive threads take consecutive ops); warp shuffle arg-max, then one atomicMax per warp on the
+// pair's packed key (trim_key).  keys[] is zeroed before the launch; slice 0 contributes the fixed candidates, so no key
+// stays zero.
 __global__ void __launch_bounds__(TPAIR_THREADS)
 k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
-             const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, TrimView* __restrict__ views,
-             TrimPairOut* __restrict__ out) {
-    __shared__ long long s_tot[TPAIR_THREADS / 32];
-    __shared__ unsigned long long s_c[TPAIR_THREADS / 32];
+             const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, const TrimView* __restrict__ views,
+             unsigned long long* __restrict__ keys) {
     const uint32_t p = blockIdx.x;
     if (p >= n_sel) return;
     const TrimPairDev ps = sel[p];
@@ -103,26 +106,42 @@ k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t
     v.ops = ops; v.samples = nullptr;
     const TrimArr a{qp, wp};
     const uint64_t A = ps.st_ovl, B = ps.en_ovl;
+    const TrimSide sl = trim_side(v, a, rl, tl, A, sc), sr = trim_side(v, a, rr, tr, A, sc);
+    const uint32_t t = blockIdx.y * TPAIR_THREADS + threadIdx.x, n = gridDim.y * TPAIR_THREADS;
     TrimBest best{LLONG_MIN, 0};
-    if (threadIdx.x == 0) trim_fixed_candidates(v, a, rl, tl, rr, tr, A, B, sc, best);
-    trim_scan_candidates(v, a, rl, rl, tl, rr, tr, A, B, sc, threadIdx.x, TPAIR_THREADS, best);
-    trim_scan_candidates(v, a, rr, rl, tl, rr, tr, A, B, sc, threadIdx.x, TPAIR_THREADS, best);
+    if (t == 0) trim_fixed_candidates(v, a, rl, tl, rr, tr, A, B, sc, best);
+    trim_scan_candidates(v, a, true, rl, tl, sl, rr, tr, sr, A, B, sc, t, n, best);
+    trim_scan_candidates(v, a, false, rl, tl, sl, rr, tr, sr, A, B, sc, t, n, best);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         const long long ot = __shfl_xor_sync(0xffffffffu, best.total, d);
         const unsigned long long oc = __shfl_xor_sync(0xffffffffu, (unsigned long long)best.c, d);
         trim_best_merge(best, ot, oc);
     }
-    if ((threadIdx.x & 31) == 0) { s_tot[threadIdx.x >> 5] = best.total; s_c[threadIdx.x >> 5] = best.c; }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    for (int x = 1; x < TPAIR_THREADS / 32; x++) trim_best_merge(best, s_tot[x], s_c[x]);
-    const long long r_tot = trim_S(v, a, rr, tr, A, B, sc);
+    if ((threadIdx.x & 31) == 0 && best.total != LLONG_MIN) atomicMax(&keys[p], trim_key(best, A));
+}
+
+// one thread per pair: split point from the reduced key, then the two truncations (trim_overlap.rs:71-79)
+__global__ void __launch_bounds__(128)
+k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
+           const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, TrimView* __restrict__ views,
+           const unsigned long long* __restrict__ keys, TrimPairOut* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_sel) return;
+    const TrimPairDev ps = sel[p];
+    const RecInfo& rl = recs[ps.left];
+    const RecInfo& rr = recs[ps.right];
+    OpsView v;
+    v.ops = ops; v.samples = nullptr;
+    const TrimArr a{qp, wp};
+    const uint64_t A = ps.st_ovl, B = ps.en_ovl;
+    TrimView nl = views[ps.left], nr = views[ps.right];
+    const TrimBest best = trim_unkey(keys[p], A);
+    const long long r_tot = trim_S(v, a, rr, nr, A, B, sc);
     const uint64_t s = trim_split(best, r_tot, A);
-    TrimView nl = tl, nr = tr;
     TrimPairOut o;
     o.pad = 0;
-    o.status = trim_truncate(v, a, rl, nl, nl.q_st, s);                       // trim_overlap.rs:78
+    o.status = trim_truncate(v, a, rl, nl, nl.q_st, s);                           // trim_overlap.rs:78
     if (o.status == TRIM_OK) o.status = trim_truncate(v, a, rr, nr, s, nr.q_en);  // trim_overlap.rs:79
     if (o.status == TRIM_OK) { views[ps.left] = nl; views[ps.right] = nr; }
     o.l_st = nl.q_st; o.l_en = nl.q_en; o.r_st = nr.q_st; o.r_en = nr.q_en;
@@ -160,11 +179,17 @@ void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, 
     if (n_rec) k_trim_scan<<<n_rec, TSCAN_THREADS, 0, s>>>(ops, recs, n_rec, sc, qp, wp, views);
 }
 void launch_trim_pairs(const void* sel, uint32_t n_sel, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp, const long long* wp,
-                       TrimScores sc, TrimView* views, void* out, cudaStream_t s) {
+                       TrimScores sc, TrimView* views, unsigned long long* keys, void* out, cudaStream_t s) {
     static_assert(sizeof(TrimPairDev) == 24 && sizeof(TrimPairOut) == 40, "pair layouts");
-    if (n_sel)
-        k_trim_pairs<<<n_sel, TPAIR_THREADS, 0, s>>>(reinterpret_cast<const TrimPairDev*>(sel), n_sel, ops, recs, qp, wp, sc, views,
-                                                     reinterpret_cast<TrimPairOut*>(out));
+    if (!n_sel) return;
+    // enough slices per pair to fill the machine a few times over (148 SMs): few pairs -> many slices each
+    uint32_t slices = (148u * 8u + n_sel - 1) / n_sel;
+    if (slices > 64u) slices = 64u;
+    if (slices < 1u) slices = 1u;
+    cudaMemsetAsync(keys, 0, (size_t)n_sel * 8, s);
+    k_trim_pairs<<<dim3(n_sel, slices), TPAIR_THREADS, 0, s>>>(reinterpret_cast<const TrimPairDev*>(sel), n_sel, ops, recs, qp, wp, sc, views, keys);
+    k_trim_cut<<<(n_sel + 127) / 128, 128, 0, s>>>(reinterpret_cast<const TrimPairDev*>(sel), n_sel, ops, recs, qp, wp, sc, views, keys,
+                                                   reinterpret_cast<TrimPairOut*>(out));
 }
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,
                       const uint8_t* dropped, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans, cudaStream_t s) {

@@ -157,8 +157,17 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
                 const uint64_t A = p.st_ovl, B = p.en_ovl;
                 TrimBest best{LLONG_MIN, 0};
                 trim_fixed_candidates(view, arr, rl, tl, rr, tr, A, B, sc, best);
-                trim_scan_candidates(view, arr, rl, rl, tl, rr, tr, A, B, sc, 0, 1, best);
-                trim_scan_candidates(view, arr, rr, rl, tl, rr, tr, A, B, sc, 0, 1, best);
+                const TrimSide sl = trim_side(view, arr, rl, tl, A, sc), sr = trim_side(view, arr, rr, tr, A, sc);
+                const uint32_t nt = (uint32_t)U(1, 5);  // any split of the work over threads gives the same arg-max
+                for (uint32_t t = 0; t < nt; t++) {
+                    trim_scan_candidates(view, arr, true, rl, tl, sl, rr, tr, sr, A, B, sc, t, nt, best);
+                    trim_scan_candidates(view, arr, false, rl, tl, sl, rr, tr, sr, A, B, sc, t, nt, best);
+                }
+                {   // the packed 64-bit key the kernels reduce with atomicMax decodes to the same arg-max
+                    const unsigned long long key = trim_key(best, A);
+                    TrimBest back = trim_unkey(key, A);
+                    if (back.total != best.total || back.c != best.c) { n_fail++; fprintf(stderr, "FAIL key round trip\n"); }
+                }
                 const long long r_tot = trim_S(view, arr, rr, tr, A, B, sc);
                 const uint64_t s = trim_split(best, r_tot, A);
                 if (trim_truncate(view, arr, rl, tl, tl.q_st, s) != TRIM_OK) { p_abort = true; break; }

@@ -272,3 +272,66 @@ def test_rb_cli_matches_oracle(tmp_path):
     bad.write_bytes(b"Q\t10\t0\t8\t+\tT\t20\t0\t8\t0\t0\t60\tcg:Z:3D5=\n")
     r = subprocess.run([rb, "liftover", "--bed", bed, str(bad)], capture_output=True)
     assert r.returncode == 101 and r.stdout == b""
+
+
+# ---------------------------------------------------------------- rb trim-paf at scale
+def overlapped_on_query(text: bytes, shift=300) -> bytes:
+    """The synthetic PAF's records tile their query without overlap; moving the i-th record of a query name down by
+    300 * i bases makes every record overlap its predecessor by 101..300 bases (no containment)."""
+    seen, out = {}, []
+    for ln in text.split(b"\n"):
+        if not ln:
+            continue
+        f = ln.split(b"\t", 4)
+        i = seen.get(f[0], 0)
+        seen[f[0]] = i + 1
+        f[2], f[3] = str(int(f[2]) - shift * i).encode(), str(int(f[3]) - shift * i).encode()
+        out.append(b"\t".join(f))
+    return b"\n".join(out) + b"\n"
+
+
+def test_trim_paf_synth_2pct_exact_parity(ctx):
+    text = overlapped_on_query(hostlib.HostPaf.synth(scale=0.02).text())
+    want = orc.run_trim_paf(text)
+    hp = hostlib.HostPaf.from_text(text)
+    res = ctx.trim_paf(hp, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    assert res["paf_text"] == want
+    assert sum(a != b for a, b in zip(sorted(text.splitlines()), sorted(want.splitlines()))) > 100  # most records were cut
+    out = Paf.from_text(want)
+    assert (bamstats.print_cigar_stats_header() + bamstats.stats_rows(out, res["stats"])).encode() == orc.run_stats(want)
+
+
+def test_full_scale_trim_paf_properties(ctx, full):
+    # ~50 M ops, 761 records on 25 query names, every record overlapping its predecessor: structural invariants of the result
+    text = overlapped_on_query(full.text())
+    hp = hostlib.HostPaf.from_text(text)
+    n = hp.n_rec
+    res = ctx.trim_paf(hp, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    assert res["n_out"] == n
+    idx = res["rec_idx"].astype(np.int64)
+    assert sorted(idx.tolist()) == list(range(n))
+    c = hp.c
+    q_st_in = np.array([c.q_st[i] for i in range(n)], dtype=np.uint64)[idx]
+    q_en_in = np.array([c.q_en[i] for i in range(n)], dtype=np.uint64)[idx]
+    t_st_in = np.array([c.t_st[i] for i in range(n)], dtype=np.uint64)[idx]
+    t_en_in = np.array([c.t_en[i] for i in range(n)], dtype=np.uint64)[idx]
+    q_id = np.array([c.q_id[i] for i in range(n)], dtype=np.int64)[idx]
+    # every row is a sub-interval of its record, on both sequences
+    assert (res["q_st"] >= q_st_in).all() and (res["q_en"] <= q_en_in).all() and (res["q_st"] < res["q_en"]).all()
+    assert (res["t_st"] >= t_st_in).all() and (res["t_en"] <= t_en_in).all() and (res["t_st"] < res["t_en"]).all()
+    # rows are grouped by query name (stable sort: file order inside a name), and no two neighbours overlap any more
+    same = q_id[1:] == q_id[:-1]
+    starts = np.flatnonzero(np.r_[True, ~same])
+    assert len(starts) == len(set(q_id[starts].tolist())) == 25
+    assert (res["q_en"][:-1][same] <= res["q_st"][1:][same]).all()
+    assert ((q_en_in[:-1][same] > q_st_in[1:][same])).all()  # ... while every such pair did overlap in the input
+    # at most the overlap was given up: what a cut removes from the two records together is bounded by their overlap + the
+    # indel columns slid over (a few bases)
+    st = res["stats"]
+    assert (res["nmatch"] == st["equal"].astype(np.uint64) + st["diff"]).all()
+    assert (res["aln_len"] == st["equal"].astype(np.uint64) + st["diff"] + st["ins"] + st["del"]).all()
+    assert (res["q_en"] - res["q_st"] == st["equal"].astype(np.uint64) + st["diff"] + st["ins"]).all()
+    assert (res["t_en"] - res["t_st"] == st["equal"].astype(np.uint64) + st["diff"] + st["del"]).all()
+    # the output is a valid PAF (spans match the CIGARs: the loader's check_integrity passes) and a fixed point of the command
+    again = ctx.trim_paf(hostlib.HostPaf.from_text(res["paf_text"]), want=capi.WANT_TEXT, stats=False)
+    assert again["paf_text"] == res["paf_text"]
