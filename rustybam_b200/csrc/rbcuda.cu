@@ -1756,8 +1756,6 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     CU(b->trim_qp.ensure(b->ops_bound * 4 + 64));
     CU(b->trim_wp.ensure(b->ops_bound * 8 + 64));
     CU(b->trim_views.ensure((size_t)n * sizeof(TrimView) + 64));
-    CU(b->trim_sel.ensure(((size_t)n / 2 + 1) * sizeof(TrimPairSel)));
-    CU(b->trim_out.ensure(((size_t)n / 2 + 1) * 48));  // 40 B of results + the 8-byte arg-max key per pair
     {
         KScope k(ctx, "k_trim_scan");
         launch_trim_scan(b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), n, scores, b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(),
@@ -1775,46 +1773,48 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     }
     const uint64_t max_score = (uint64_t)std::max({std::llabs((long long)match_score), std::llabs((long long)diff_score),
                                                    std::llabs((long long)indel_score)});
-    std::vector<uint8_t> contained;
-    std::vector<TrimPairSel> sel;
-    struct PairOut { uint64_t l_st, l_en, r_st, r_en; uint32_t status, pad; };
-    std::vector<PairOut> pout;
-    for (uint64_t round = 0;; round++) {
-        const size_t waiting = trim_round(spans, contained, sel);
-        for (const TrimPairSel& p : sel)  // the reference sums the scores in i32 (trim_overlap.rs:52-69)
-            if ((p.en_ovl - p.st_ovl) * max_score >= (1ull << 31))
-                return fail(ctx, RB_ERR_UNSUPPORTED, "records %u / %u: overlap x score exceeds the reference's i32 sums", perm[p.left], perm[p.right]);
-        if (!sel.empty()) {
-            const uint32_t ns = (uint32_t)sel.size();
-            CU(cudaMemcpyAsync(b->trim_sel.p, sel.data(), (size_t)ns * sizeof(TrimPairSel), cudaMemcpyHostToDevice, s));
-            {
-                KScope k(ctx, "k_trim_pairs");
-                launch_trim_pairs(b->trim_sel.p, ns, b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(),
-                                  b->trim_wp.as<long long>(), scores, b->trim_views.as<TrimView>(),
-                                  reinterpret_cast<unsigned long long*>(b->trim_out.as<uint8_t>() + ((size_t)n / 2 + 1) * 40), b->trim_out.p, s);
-            }
-            pout.resize(ns);
-            CU(cudaMemcpyAsync(pout.data(), b->trim_out.p, (size_t)ns * sizeof(PairOut), cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-            for (uint32_t i = 0; i < ns; i++) {
-                if (pout[i].status != 0) {
-                    flush_times(ctx);
-                    return fail(ctx, RB_ERR_REF_INTEGRITY, "records %u / %u: truncate_record_by_query leaves spans that disagree with the CIGAR "
-                                "(check_integrity().unwrap() panics, paf.rs:819-822)", perm[sel[i].left], perm[sel[i].right]);
-                }
-                spans[sel[i].left].q_st = pout[i].l_st; spans[sel[i].left].q_en = pout[i].l_en;
-                spans[sel[i].right].q_st = pout[i].r_st; spans[sel[i].right].q_en = pout[i].r_en;
-            }
+    // query-name groups of the sorted set; the rounds themselves run on the device (k_trim_select picks each name's pair from
+    // the current spans), enqueued in batches — the host only looks at the 32-byte round state after every batch
+    std::vector<uint32_t> grp_off;
+    for (uint32_t i = 0; i < n; i++)
+        if (i == 0 || spans[i].name != spans[i - 1].name) grp_off.push_back(i);
+    const uint32_t n_groups = (uint32_t)grp_off.size();
+    grp_off.push_back(n);
+    for (uint32_t g = 0; g < n_groups; g++)
+        if (grp_off[g + 1] - grp_off[g] > 65535u)
+            return fail(ctx, RB_ERR_UNSUPPORTED, "more than 65535 records on one query name (record %u)", perm[grp_off[g]]);
+    const size_t o_sel = 0, o_keys = o_sel + ((size_t)n_groups + 1) * sizeof(TrimPairSel), o_info = o_keys + ((size_t)n_groups + 1) * 8,
+                 o_grp = o_info + 32, o_end = o_grp + ((size_t)n_groups + 2) * 4;
+    CU(b->trim_sel.ensure(o_end + 64));
+    uint8_t* tb = b->trim_sel.as<uint8_t>();
+    CU(b->trim_drop.ensure((size_t)n + 64));
+    CU(cudaMemsetAsync(b->trim_drop.p, 0, (size_t)n + 1, s));
+    CU(cudaMemsetAsync(tb + o_info, 0, 32, s));
+    CU(cudaMemcpyAsync(tb + o_grp, grp_off.data(), ((size_t)n_groups + 1) * 4, cudaMemcpyHostToDevice, s));
+    struct { uint32_t waiting, done, rounds, status, err_l, err_r, pad[2]; } info{};
+    const int batch = 8;
+    for (uint64_t it = 0;; it++) {
+        {
+            KScope k(ctx, "k_trim_rounds");
+            launch_trim_rounds(batch, reinterpret_cast<const uint32_t*>(tb + o_grp), n_groups, b->ops.as<uint32_t>(), b->recs.as<RecInfo>(),
+                               b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(), scores, max_score, b->trim_views.as<TrimView>(),
+                               b->trim_drop.as<uint8_t>(), tb + o_sel, reinterpret_cast<unsigned long long*>(tb + o_keys), tb + o_info, s);
         }
-        if (waiting == 0) break;
-        if (round > (uint64_t)n * n + 8) return fail(ctx, RB_ERR_UNSUPPORTED, "trim rounds do not converge");
+        CU(cudaMemcpyAsync(&info, tb + o_info, 32, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));  // (also covers the pageable grp_off upload of the first batch)
+        if (info.status == 1) {
+            flush_times(ctx);
+            return fail(ctx, RB_ERR_REF_INTEGRITY, "records %u / %u: truncate_record_by_query leaves spans that disagree with the CIGAR "
+                        "(check_integrity().unwrap() panics, paf.rs:819-822)", perm[info.err_l], perm[info.err_r]);
+        }
+        if (info.status) {
+            flush_times(ctx);
+            return fail(ctx, RB_ERR_UNSUPPORTED, "records %u / %u: overlap x score exceeds the reference's i32 sums", perm[info.err_l], perm[info.err_r]);
+        }
+        if (info.done) break;
+        if (it > (uint64_t)n * n / batch + 8) return fail(ctx, RB_ERR_UNSUPPORTED, "trim rounds do not converge");
     }
     b->trim_has_drop = remove_contained != 0 && n > 0;
-    if (b->trim_has_drop) {
-        CU(b->trim_drop.ensure((size_t)n + 64));
-        CU(cudaMemcpyAsync(b->trim_drop.p, contained.data(), n, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));  // `contained` is a pageable local
-    }
     const uint64_t P = n;
     CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
     CU(b->line_len.ensure(P * 4 + 64));

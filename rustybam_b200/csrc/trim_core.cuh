@@ -215,6 +215,64 @@ RB_HD TrimBest trim_unkey(unsigned long long key, uint64_t A) {
 // split point from the arg-max over all candidates (trim_overlap.rs:71-77: `if l + r > max` starting from max = 0)
 RB_HD uint64_t trim_split(const TrimBest& best, long long r_tot, uint64_t A) { return (best.total + r_tot > 0) ? best.c : A; }
 
+// ---- which pair of a query name is trimmed in a round (paf.rs:229-275) ---------------------------------------------
+// The reference lists the overlapping pairs (i < j, file order within the name), sorts them by overlap (largest first,
+// stable) and trims the first one of every query name; all the others wait for the next round.  "First after a stable sort"
+// == largest overlap, ties to the pair generated first == one max over the key below.
+enum : uint32_t { TRIM_PAIR_NONE = 0, TRIM_PAIR_J_CONTAINED = 1, TRIM_PAIR_I_CONTAINED = 2, TRIM_PAIR_PARTIAL = 3 };
+RB_HD uint32_t trim_pair_class(uint64_t i_st, uint64_t i_en, uint64_t j_st, uint64_t j_en, uint64_t& overlap) {
+    const uint64_t mn = i_en < j_en ? i_en : j_en, mx = i_st > j_st ? i_st : j_st;  // bed.rs:74-85
+    overlap = mn < mx ? 0 : mn - mx;
+    if (overlap < 1) return TRIM_PAIR_NONE;
+    if (overlap == j_en - j_st) return TRIM_PAIR_J_CONTAINED;  // paf.rs:243-245 (checked first)
+    if (overlap == i_en - i_st) return TRIM_PAIR_I_CONTAINED;
+    return TRIM_PAIR_PARTIAL;
+}
+// i, j = positions inside the name's group of m records (m < 65536), overlap < 2^32
+RB_HD unsigned long long trim_sel_key(uint64_t overlap, uint32_t i, uint32_t j, uint32_t m) {
+    return ((unsigned long long)overlap << 32) | (unsigned long long)(~(i * m + j));
+}
+RB_HD void trim_sel_unkey(unsigned long long key, uint32_t m, uint32_t& i, uint32_t& j) {
+    const uint32_t g = ~(uint32_t)key;
+    i = g / m; j = g % m;
+}
+struct TrimPairSelDev { uint32_t left, right; uint64_t st_ovl, en_ovl; };  // == TrimPairSel of trim_rounds.hpp
+constexpr uint32_t TRIM_SEL_NONE = 0xFFFFFFFFu;
+// the selected pair of a group from the winning key (records lo + i, lo + j): left = the one that starts first (paf.rs:251-255)
+RB_HD TrimPairSelDev trim_sel_make(const TrimView* views, uint32_t lo, uint32_t m, unsigned long long key) {
+    uint32_t i, j;
+    trim_sel_unkey(key, m, i, j);
+    const TrimView &a = views[lo + i], &b = views[lo + j];
+    TrimPairSelDev s;
+    if (a.q_st <= b.q_st) { s.left = lo + i; s.right = lo + j; }
+    else { s.left = lo + j; s.right = lo + i; }
+    s.st_ovl = a.q_st > b.q_st ? a.q_st : b.q_st;
+    s.en_ovl = a.q_en < b.q_en ? a.q_en : b.q_en;
+    return s;
+}
+// sequential statement of one group's selection (the kernel spreads the same loop over a block and reduces with atomics)
+RB_HD uint32_t trim_select_group(const TrimView* views, uint32_t lo, uint32_t hi, uint8_t* contained, TrimPairSelDev& sel) {
+    const uint32_t m = hi - lo;
+    unsigned long long best = 0;
+    uint32_t n_pairs = 0;
+    for (uint32_t r = lo; r < hi; r++) contained[r] = 0;
+    for (uint32_t i = 0; i + 1 < m; i++)
+        for (uint32_t j = i + 1; j < m; j++) {
+            uint64_t ov;
+            const uint32_t c = trim_pair_class(views[lo + i].q_st, views[lo + i].q_en, views[lo + j].q_st, views[lo + j].q_en, ov);
+            if (c == TRIM_PAIR_J_CONTAINED) contained[lo + j] = 1;
+            else if (c == TRIM_PAIR_I_CONTAINED) contained[lo + i] = 1;
+            else if (c == TRIM_PAIR_PARTIAL) {
+                n_pairs++;
+                const unsigned long long k = trim_sel_key(ov, i, j, m);
+                if (k > best) best = k;
+            }
+        }
+    sel.left = TRIM_SEL_NONE; sel.right = 0; sel.st_ovl = sel.en_ovl = 0;
+    if (n_pairs) sel = trim_sel_make(views, lo, m, best);
+    return n_pairs;
+}
+
 // ---- truncate_record_by_query (paf.rs:785-823) in (op, offset) space ---------------------------------------------
 struct TrimCol { uint64_t k; uint32_t o; };
 RB_HD bool trim_col_lt(const TrimCol& x, const TrimCol& y) { return x.k < y.k || (x.k == y.k && x.o < y.o); }

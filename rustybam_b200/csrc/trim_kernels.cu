@@ -3,9 +3,11 @@
 // file only spreads it over the machine:
 //   k_trim_scan   per record: segmented exclusive scan of (query advance, position score) over its ops -> qp / wp
 //                 (12 B per op), the record's total score and its untruncated view
+//   k_trim_select per query name and round: containment flags, overlapping pairs, the one pair trimmed this round
 //   k_trim_pairs  per selected pair of one round (a column of blocks each): every thread evaluates the split-point
 //                 candidates of a stride of both records' ops in the overlap; warp arg-max, atomicMax on a packed key
 //   k_trim_cut    per selected pair: the split point from the key, then the two truncations
+//   k_trim_round_end  one thread: nothing had to wait -> done (later rounds of the batch are no-ops)
 //   k_trim_rows   per record after the last round: the printed row (PairRes + line size) for the shared serialiser
 #include <climits>
 
@@ -85,20 +87,90 @@ k_trim_scan(const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs, 
     }
 }
 
-struct TrimPairDev { uint32_t left, right; uint64_t st_ovl, en_ovl; };  // == TrimPairSel (trim_rounds.hpp)
-struct TrimPairOut { uint64_t l_st, l_en, r_st, r_en; uint32_t status, pad; };
+typedef TrimPairSelDev TrimPairDev;
 
-// grid = (pairs of this round, slices): every thread of every slice of a pair evaluates a stride of both records' ops in the
-// overlap (coalesced: consecutive threads take consecutive ops); warp shuffle arg-max, then one atomicMax per warp on the
-// pair's packed key (trim_key).  keys[] is zeroed before the launch; slice 0 contributes the fixed candidates, so no key
-// stays zero.
+// per-call round state on the device (zeroed before the first round)
+struct TrimInfo {
+    uint32_t waiting;  // != 0: some pair of the current round has to wait for the next one (paf.rs:283-285)
+    uint32_t done;     // a round ended with nothing waiting: every later launch of this call is a no-op
+    uint32_t rounds;   // rounds run so far
+    uint32_t status;   // 0, TRIM_ST_ABORT (a truncation the reference panics on) or TRIM_ST_RANGE (overlap x score >= 2^31)
+    uint32_t err_l, err_r;  // the pair that set `status`
+    uint32_t pad[2];
+};
+enum : uint32_t { TRIM_ST_ABORT = 1, TRIM_ST_RANGE = 2 };
+
+// One block per query name (records [grp_off[g], grp_off[g+1]) of the name-sorted set): containment flags, the number of
+// overlapping pairs and the one trimmed this round — max over trim_sel_key (trim_core.cuh: trim_select_group is the
+// sequential statement, fuzzed against the host's trim_round).  O(m^2) span comparisons per group, like the reference.
+__global__ void __launch_bounds__(128)
+k_trim_select(const uint32_t* __restrict__ grp_off, uint32_t n_groups, const TrimView* __restrict__ views, uint8_t* __restrict__ contained,
+              TrimPairDev* __restrict__ sel, unsigned long long* __restrict__ keys, TrimInfo* __restrict__ info, unsigned long long max_score) {
+    __shared__ unsigned long long s_best;
+    __shared__ uint32_t s_cnt, s_skip;
+    // (another block of this launch may set `status` at any time: one thread reads it for the whole block)
+    if (threadIdx.x == 0) s_skip = info->done | info->status;
+    __syncthreads();
+    if (s_skip) return;
+    const uint32_t g = blockIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t lo = grp_off[g], hi = grp_off[g + 1], m = hi - lo;
+    if (threadIdx.x == 0) { s_best = 0; s_cnt = 0; keys[g] = 0; }
+    for (uint32_t r = lo + threadIdx.x; r < hi; r += blockDim.x) contained[r] = 0;
+    __syncthreads();
+    unsigned long long best = 0;
+    uint32_t cnt = 0;
+    for (uint32_t i = 0; i + 1 < m; i++) {
+        const uint64_t i_st = views[lo + i].q_st, i_en = views[lo + i].q_en;
+        bool i_contained = false;
+        for (uint32_t j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
+            uint64_t ov;
+            const uint32_t c = trim_pair_class(i_st, i_en, views[lo + j].q_st, views[lo + j].q_en, ov);
+            if (c == TRIM_PAIR_J_CONTAINED) contained[lo + j] = 1;
+            else if (c == TRIM_PAIR_I_CONTAINED) i_contained = true;
+            else if (c == TRIM_PAIR_PARTIAL) {
+                cnt++;
+                const unsigned long long k = trim_sel_key(ov, i, j, m);
+                if (k > best) best = k;
+            }
+        }
+        if (i_contained) contained[lo + i] = 1;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, d);
+        if (ob > best) best = ob;
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) { atomicMax(&s_best, best); atomicAdd(&s_cnt, cnt); }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    TrimPairDev one;
+    one.left = TRIM_SEL_NONE; one.right = 0; one.st_ovl = one.en_ovl = 0;
+    if (s_cnt) {
+        one = trim_sel_make(views, lo, m, s_best);
+        if (s_cnt > 1) atomicOr(&info->waiting, 1u);
+        if ((one.en_ovl - one.st_ovl) * max_score >= (1ull << 31)) {  // the reference sums the scores in i32 (trim_overlap.rs:52-69)
+            if (atomicCAS(&info->status, 0u, TRIM_ST_RANGE) == 0u) { info->err_l = one.left; info->err_r = one.right; }
+            one.left = TRIM_SEL_NONE;
+        }
+    }
+    sel[g] = one;
+}
+
+// grid = (query names, slices): every thread of every slice of a name's selected pair evaluates a stride of both records'
+// ops in the overlap (coalesced: consecutive threads take consecutive ops); warp shuffle arg-max, then one atomicMax per
+// warp on the pair's packed key (trim_key; zeroed by k_trim_select).  Slice 0 contributes the fixed candidates, so the key
+// of a selected pair never stays zero.
 __global__ void __launch_bounds__(TPAIR_THREADS)
 k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
              const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, const TrimView* __restrict__ views,
-             unsigned long long* __restrict__ keys) {
+             unsigned long long* __restrict__ keys, const TrimInfo* __restrict__ info) {
+    if (info->done | info->status) return;
     const uint32_t p = blockIdx.x;
     if (p >= n_sel) return;
     const TrimPairDev ps = sel[p];
+    if (ps.left == TRIM_SEL_NONE) return;
     const RecInfo& rl = recs[ps.left];
     const RecInfo& rr = recs[ps.right];
     const TrimView tl = views[ps.left], tr = views[ps.right];
@@ -121,14 +193,16 @@ k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t
     if ((threadIdx.x & 31) == 0 && best.total != LLONG_MIN) atomicMax(&keys[p], trim_key(best, A));
 }
 
-// one thread per pair: split point from the reduced key, then the two truncations (trim_overlap.rs:71-79)
+// one thread per selected pair: split point from the reduced key, then the two truncations (trim_overlap.rs:71-79)
 __global__ void __launch_bounds__(128)
 k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
            const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, TrimView* __restrict__ views,
-           const unsigned long long* __restrict__ keys, TrimPairOut* __restrict__ out) {
+           const unsigned long long* __restrict__ keys, TrimInfo* __restrict__ info) {
+    if (info->done | info->status) return;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_sel) return;
     const TrimPairDev ps = sel[p];
+    if (ps.left == TRIM_SEL_NONE) return;
     const RecInfo& rl = recs[ps.left];
     const RecInfo& rr = recs[ps.right];
     OpsView v;
@@ -139,13 +213,20 @@ k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* 
     const TrimBest best = trim_unkey(keys[p], A);
     const long long r_tot = trim_S(v, a, rr, nr, A, B, sc);
     const uint64_t s = trim_split(best, r_tot, A);
-    TrimPairOut o;
-    o.pad = 0;
-    o.status = trim_truncate(v, a, rl, nl, nl.q_st, s);                           // trim_overlap.rs:78
-    if (o.status == TRIM_OK) o.status = trim_truncate(v, a, rr, nr, s, nr.q_en);  // trim_overlap.rs:79
-    if (o.status == TRIM_OK) { views[ps.left] = nl; views[ps.right] = nr; }
-    o.l_st = nl.q_st; o.l_en = nl.q_en; o.r_st = nr.q_st; o.r_en = nr.q_en;
-    out[p] = o;
+    uint32_t st = trim_truncate(v, a, rl, nl, nl.q_st, s);                // trim_overlap.rs:78
+    if (st == TRIM_OK) st = trim_truncate(v, a, rr, nr, s, nr.q_en);      // trim_overlap.rs:79
+    if (st == TRIM_OK) { views[ps.left] = nl; views[ps.right] = nr; }
+    else if (atomicCAS(&info->status, 0u, TRIM_ST_ABORT) == 0u) { info->err_l = ps.left; info->err_r = ps.right; }
+}
+// NOTE on k_trim_cut's early exit: `status` may be set by another block of the same launch; the pairs of a round are
+// disjoint and a failed call produces no output, so it does not matter which of them still get cut.
+
+// after the cuts of a round: nothing waiting -> the call is done (paf.rs:283-300); else the next round starts over
+__global__ void k_trim_round_end(TrimInfo* info) {
+    if (info->done | info->status) return;
+    info->rounds++;
+    if (info->waiting == 0) info->done = 1;
+    info->waiting = 0;
 }
 
 __global__ void __launch_bounds__(128)
@@ -178,18 +259,24 @@ void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, 
                       cudaStream_t s) {
     if (n_rec) k_trim_scan<<<n_rec, TSCAN_THREADS, 0, s>>>(ops, recs, n_rec, sc, qp, wp, views);
 }
-void launch_trim_pairs(const void* sel, uint32_t n_sel, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp, const long long* wp,
-                       TrimScores sc, TrimView* views, unsigned long long* keys, void* out, cudaStream_t s) {
-    static_assert(sizeof(TrimPairDev) == 24 && sizeof(TrimPairOut) == 40, "pair layouts");
-    if (!n_sel) return;
-    // enough slices per pair to fill the machine a few times over (148 SMs): few pairs -> many slices each
-    uint32_t slices = (148u * 8u + n_sel - 1) / n_sel;
+void launch_trim_rounds(int n_rounds, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
+                        const long long* wp, TrimScores sc, unsigned long long max_score, TrimView* views, uint8_t* contained, void* sel,
+                        unsigned long long* keys, void* info, cudaStream_t s) {
+    static_assert(sizeof(TrimPairDev) == 24 && sizeof(TrimInfo) == 32, "layouts");
+    TrimInfo* inf = reinterpret_cast<TrimInfo*>(info);
+    TrimPairDev* sl = reinterpret_cast<TrimPairDev*>(sel);
+    // enough slices per pair to fill the machine a few times over (148 SMs): few names -> many slices each
+    uint32_t slices = n_groups ? (148u * 8u + n_groups - 1) / n_groups : 1u;
     if (slices > 64u) slices = 64u;
     if (slices < 1u) slices = 1u;
-    cudaMemsetAsync(keys, 0, (size_t)n_sel * 8, s);
-    k_trim_pairs<<<dim3(n_sel, slices), TPAIR_THREADS, 0, s>>>(reinterpret_cast<const TrimPairDev*>(sel), n_sel, ops, recs, qp, wp, sc, views, keys);
-    k_trim_cut<<<(n_sel + 127) / 128, 128, 0, s>>>(reinterpret_cast<const TrimPairDev*>(sel), n_sel, ops, recs, qp, wp, sc, views, keys,
-                                                   reinterpret_cast<TrimPairOut*>(out));
+    for (int r = 0; r < n_rounds; r++) {
+        if (n_groups) {
+            k_trim_select<<<n_groups, 128, 0, s>>>(grp_off, n_groups, views, contained, sl, keys, inf, max_score);
+            k_trim_pairs<<<dim3(n_groups, slices), TPAIR_THREADS, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
+            k_trim_cut<<<(n_groups + 127) / 128, 128, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
+        }
+        k_trim_round_end<<<1, 1, 0, s>>>(inf);
+    }
 }
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,
                       const uint8_t* dropped, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans, cudaStream_t s) {

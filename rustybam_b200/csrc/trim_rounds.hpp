@@ -3,8 +3,10 @@
 // The reference sorts the records by query name (stable), lists every pair of records of one query whose query
 // intervals overlap without containment, orders the pairs by overlap (largest first, stable), trims the FIRST pair of
 // every query name and — if any pair had to wait — starts over on the trimmed set.  Only the query spans matter for
-// that bookkeeping; the per-pair work (scores, split point, truncation) runs on the GPU (trim_core.cuh).
-// Plain C++ (no CUDA): shared by rbcuda.cu and the CPU fuzz harness (tests/native/trim_core_check.cpp).
+// that bookkeeping.  This file is the whole-set statement of one round, literal to the reference's loop; the GPU runs the
+// per-name form of it (trim_select_group / k_trim_select in trim_core.cuh / trim_kernels.cu), and the CPU fuzz harness
+// (tests/native/trim_core_check.cpp) checks the two against each other every round and the result against the oracle.
+// Plain C++ (no CUDA).
 #pragma once
 #include <algorithm>
 #include <cstdint>

@@ -151,6 +151,28 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
         for (;;) {
             const size_t waiting = trim_round(spans, contained, sel);
             rounds++;
+            {   // the per-group selection the GPU runs (trim_select_group) picks the same pairs, flags and waiting count
+                std::vector<uint8_t> c2(spans.size(), 7);
+                std::vector<TrimPairSelDev> s2;
+                size_t w2 = 0;
+                for (uint32_t lo = 0; lo < spans.size();) {
+                    uint32_t hi = lo + 1;
+                    while (hi < spans.size() && spans[hi].name == spans[lo].name) hi++;
+                    TrimPairSelDev one;
+                    const uint32_t np = trim_select_group(tv.data(), lo, hi, c2.data(), one);
+                    if (np) { s2.push_back(one); w2 += np - 1; }
+                    lo = hi;
+                }
+                bool same = w2 == waiting && s2.size() == sel.size() && c2 == contained;
+                // trim_round lists its pairs by overlap; per name there is one, so compare as sets keyed by `left`
+                for (size_t x = 0; same && x < sel.size(); x++) {
+                    bool found = false;
+                    for (const TrimPairSelDev& y : s2)
+                        if (y.left == sel[x].left && y.right == sel[x].right && y.st_ovl == sel[x].st_ovl && y.en_ovl == sel[x].en_ovl) found = true;
+                    same = found;
+                }
+                if (!same) { n_fail++; if (n_fail < 10) fprintf(stderr, "FAIL selection differs from trim_round (waiting %zu vs %zu, %zu vs %zu pairs)\n", w2, waiting, s2.size(), sel.size()); }
+            }
             for (const TrimPairSel& p : sel) {
                 const RecInfo &rl = ri[p.left], &rr = ri[p.right];
                 TrimView &tl = tv[p.left], &tr = tv[p.right];

@@ -42,6 +42,7 @@ def both(label, ref_fn, gpu_fn, dump):
 t_end = time.time() + budget
 n = counts = 0
 panics = 0
+n_trim_panics = 0
 seed = seed0
 while time.time() < t_end:
     rng = random.Random(seed)
@@ -104,6 +105,31 @@ while time.time() < t_end:
         dump["in.qbed"] = qbed
         both(f"qbed seed {seed}", lambda: orc.run_liftover(paf_text, qbed, qbed=True, policy=policy, threads=2),
              lambda: liftover.run_liftover(ctx, paf_text, qbed, policy=policy, qbed=True), dump)
+    # rb trim-paf: piles of query-overlapping records, random scores, sometimes one broken record
+    tp = gen.random_trim_paf(seed, n_names=rng.randint(1, 6), recs_per_name=rng.randint(1, 8), max_ops=rng.choice([3, 20, 120, 1500]),
+                             style=style, canonical=canonical, allow_zero=(not canonical and rng.random() < 0.5),
+                             lead_trail=rng.random() < 0.7, span=rng.choice([5, 80, 2000]), big=rng.choice([0, 0, 1]))
+    if rng.random() < 0.1:
+        lines = tp.splitlines()
+        k = rng.randrange(len(lines))
+        f = lines[k].split(b"\t")
+        cg = [i for i, x in enumerate(f) if x.startswith(b"cg:Z:")][0]
+        how = rng.choice(["span_t", "span_q", "lead_d", "bad_op", "no_len", "all_indel"])
+        if how == "span_t": f[8] = str(int(f[8]) + rng.choice([1, 5])).encode()
+        elif how == "span_q": f[3] = str(int(f[3]) + 1).encode()
+        elif how == "lead_d": f[cg] = b"cg:Z:3D" + f[cg][5:]; f[8] = str(int(f[8]) + 3).encode()
+        elif how == "bad_op": f[cg] = f[cg][:-1] + rng.choice([b"Z", b"m", b"*"])
+        elif how == "no_len": f[cg] = b"cg:Z:=" + f[cg][5:]
+        elif how == "all_indel": f[cg] = b"cg:Z:2I3D1I"; f[8] = str(int(f[7]) + 3).encode(); f[3] = str(int(f[2]) + 3).encode()
+        lines[k] = b"\t".join(f)
+        tp = b"\n".join(lines) + b"\n"
+    scores = rng.choice([(1, 1, 1), (1, 1, 1), (rng.randint(1, 4), rng.randint(0, 4), rng.randint(0, 4))])
+    rc_flag = rng.random() < 0.5
+    dump["trim.paf"] = tp
+    dump["info.txt"] += f"trim scores {scores} remove_contained {rc_flag}\n".encode()
+    trimmed = both(f"trim-paf seed {seed}", lambda: orc.run_trim_paf(tp, *scores, rc_flag), lambda: liftover.run_trim_paf(ctx, tp, *scores, rc_flag), dump)
+    n_trim_panics += trimmed == "PANIC"
     n += 1
     seed += 1
+print(f"trim-paf: {n} piles, {n_trim_panics} reference panics reproduced")
 print(f"fuzz ok: {n} cases (seeds {seed0}..{seed - 1}), {panics} reference panics reproduced, {budget:.0f} s")
