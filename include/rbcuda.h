@@ -194,6 +194,17 @@ int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* o
  * reference panics (paf.rs:819-822) -> RB_ERR_REF_INTEGRITY. */
 int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,
                 uint32_t want, rb_lift_out* out, rb_stats_out* stats /* nullable */);
+/* The same in steps, for a record set that is spread over several GPUs BY QUERY NAME (records only ever interact with records
+ * of their own query name, paf.rs:229-239).  The reference's decision to run another round is global — `if unseen > 0` counts
+ * the waiting pairs of ALL names (paf.rs:283-285) — and a name's result depends on it: a record that was contained when its
+ * name's last pair was cut can overlap the cut records partially afterwards, and is only trimmed if some OTHER name forces
+ * one more round.  So every rank runs rb_trim_paf_round() in lockstep, the ranks OR their `waiting` flags (the one collective
+ * of this sub-command: one integer per round) and stop together when nobody waits; rb_trim_paf_end() then returns the rank's
+ * rows, and the name groups of all ranks concatenate in query-name order.  One rb_ctx per rank; begin .. end must not be
+ * interleaved with other calls on the same context. */
+int rb_trim_paf_begin(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int policy);
+int rb_trim_paf_round(rb_ctx* ctx, int* waiting /* out: 1 if a pair of this rank had to wait for the next round */);
+int rb_trim_paf_end(rb_ctx* ctx, int remove_contained, uint32_t want, rb_lift_out* out, rb_stats_out* stats /* nullable */);
 void rb_free_lift_out(rb_ctx* ctx, rb_lift_out* out);
 void rb_free_stats_out(rb_ctx* ctx, rb_stats_out* stats);
 

@@ -448,14 +448,16 @@ void trim_overlapping_pafs(PafRecord& left, PafRecord& right, int match_score, i
     right.truncate_record_by_query(st_ovl + max_idx, right.q_en, policy);
 }
 
-// paf.rs:210-305
-void Paf::overlapping_paf_recs(int match_score, int diff_score, int indel_score, bool remove_contained, int policy) {
+// paf.rs:210-287 — one call of overlapping_paf_recs up to the decision to recurse: strip, sort, list the pairs, trim the first
+// pair of every query name.  Returns `unseen` (pairs that have to wait for the next call); `contained` is this call's fresh
+// vector (paf.rs:226).
+size_t Paf::trim_round(int match_score, int diff_score, int indel_score, int policy, std::vector<bool>& contained) {
     for (PafRecord& rec : records) rec.remove_trailing_indels();
     struct Pair { uint64_t overlap; size_t i, j; };
     std::vector<Pair> overlap_pairs;
     std::stable_sort(records.begin(), records.end(), [](const PafRecord& a, const PafRecord& b) { return a.q_name < b.q_name; });
-    std::vector<bool> contained(records.size(), false);
-    if (records.size() < 2) return;
+    contained.assign(records.size(), false);
+    if (records.size() < 2) return 0;
     for (size_t i = 0; i + 1 < records.size(); i++) {
         const PafRecord& rec1 = records[i];
         for (size_t j = i + 1; j < records.size() && rec1.q_name == records[j].q_name; j++) {
@@ -487,14 +489,23 @@ void Paf::overlapping_paf_recs(int match_score, int diff_score, int indel_score,
             unseen++;
         }
     }
-    if (unseen > 0) {
-        overlapping_paf_recs(match_score, diff_score, indel_score, remove_contained, policy);
-    } else if (remove_contained) {
-        std::vector<PafRecord> kept;
-        for (size_t i = 0; i < records.size(); i++)
-            if (!contained[i]) kept.push_back(records[i]);
-        records.swap(kept);
-    }
+    return unseen;
+}
+
+// paf.rs:290-300 — the `else if remove_contained` arm of the LAST call
+void Paf::drop_contained(const std::vector<bool>& contained) {
+    if (records.size() < 2) return;  // (paf.rs:229-231 returned before anything was flagged)
+    std::vector<PafRecord> kept;
+    for (size_t i = 0; i < records.size(); i++)
+        if (!contained[i]) kept.push_back(records[i]);
+    records.swap(kept);
+}
+
+// paf.rs:210-305 (the tail recursion written as a loop)
+void Paf::overlapping_paf_recs(int match_score, int diff_score, int indel_score, bool remove_contained, int policy) {
+    std::vector<bool> contained;
+    while (trim_round(match_score, diff_score, indel_score, policy, contained) > 0) {}
+    if (remove_contained) drop_contained(contained);
 }
 
 // paf.rs:593-600

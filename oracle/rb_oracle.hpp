@@ -125,6 +125,9 @@ struct Paf {
     static Paf from_text(const char* text, size_t n, size_t* skipped = nullptr);
     // paf.rs:210-305 — `rb trim-paf`: rounds of pairwise overlap trimming in query space
     void overlapping_paf_recs(int match_score, int diff_score, int indel_score, bool remove_contained, int policy);
+    // the same, one recursion level at a time (the multi-rank tests step several sets in lockstep)
+    size_t trim_round(int match_score, int diff_score, int indel_score, int policy, std::vector<bool>& contained);
+    void drop_contained(const std::vector<bool>& contained);
 };
 
 std::vector<Region> parse_bed_text(const char* text, size_t n);

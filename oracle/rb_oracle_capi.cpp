@@ -79,6 +79,38 @@ int orc_trim_pair(const char* left_line, const char* right_line, int match_score
     }
 }
 
+// stepping form of `rb trim-paf` for the multi-rank tests: begin -> round* -> end
+struct TrimHandle { Paf paf; std::vector<bool> contained; };
+void* orc_trim_begin(const char* paf, size_t paf_n, char* err, size_t err_cap) {
+    try {
+        TrimHandle* h = new TrimHandle();
+        h->paf = Paf::from_text(paf, paf_n);
+        return h;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return nullptr;
+    }
+}
+int orc_trim_round(void* hv, int match_score, int diff_score, int indel_score, int policy, int* waiting, char* err, size_t err_cap) {
+    TrimHandle* h = static_cast<TrimHandle*>(hv);
+    try {
+        *waiting = h->paf.trim_round(match_score, diff_score, indel_score, policy, h->contained) > 0 ? 1 : 0;
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    }
+}
+int orc_trim_end(void* hv, int remove_contained, char** out, size_t* out_n) {
+    TrimHandle* h = static_cast<TrimHandle*>(hv);
+    if (remove_contained) h->paf.drop_contained(h->contained);
+    std::string text;
+    for (const PafRecord& r : h->paf.records) { text += r.to_line(); text += '\n'; }
+    *out = dup_out(text, out_n);
+    delete h;
+    return 0;
+}
+
 int orc_run_trim_paf(const char* paf, size_t paf_n, int match_score, int diff_score, int indel_score, int remove_contained,
                      int policy, char** out, size_t* out_n, char* err, size_t err_cap) {
     try {

@@ -23,7 +23,7 @@ LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
     "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_set_slicing", "rb_ctx_kernel_times",
-    "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_trim_paf", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
+    "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_trim_paf", "rb_trim_paf_begin", "rb_trim_paf_round", "rb_trim_paf_end", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
     "rb_host_unregister",
 ]
@@ -96,6 +96,9 @@ def load():
     lib.rb_invert.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_uint32, C.POINTER(RbLiftOut)]
     lib.rb_trim_paf.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.POINTER(RbLiftOut),
                                 C.POINTER(RbStatsOut)]
+    lib.rb_trim_paf_begin.argtypes = [C.c_void_p, C.POINTER(RbRecords), C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.rb_trim_paf_round.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.rb_trim_paf_end.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(RbLiftOut), C.POINTER(RbStatsOut)]
     lib.rb_batch_break.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_int, C.POINTER(RbSummary)]
     lib.rb_free_lift_out.argtypes = [C.c_void_p, C.POINTER(RbLiftOut)]
     lib.rb_free_stats_out.argtypes = [C.c_void_p, C.POINTER(RbStatsOut)]
@@ -261,6 +264,24 @@ class Context:
         self._check(self.lib.rb_trim_paf(self.h, C.byref(recs.c), int(match_score), int(diff_score), int(indel_score), int(bool(remove_contained)),
                                          policy, want, C.byref(out), C.byref(st) if stats else None))
         res = self._collect_lift(out, st if stats else None, want) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
+        self.lib.rb_free_lift_out(self.h, C.byref(out))
+        if stats:
+            self.lib.rb_free_stats_out(self.h, C.byref(st))
+        return res
+
+    # rb trim-paf in steps (multi-GPU form: the ranks OR their `waiting` flags after every round, see rbcuda.h)
+    def trim_paf_begin(self, recs: Records, match_score=1, diff_score=1, indel_score=1, policy=POLICY_RIGHTMOST):
+        self._check(self.lib.rb_trim_paf_begin(self.h, C.byref(recs.c), int(match_score), int(diff_score), int(indel_score), policy))
+
+    def trim_paf_round(self) -> bool:
+        w = C.c_int()
+        self._check(self.lib.rb_trim_paf_round(self.h, C.byref(w)))
+        return bool(w.value)
+
+    def trim_paf_end(self, remove_contained=False, want=WANT_TEXT | WANT_NUMERIC, stats=True):
+        out, st = RbLiftOut(), RbStatsOut()
+        self._check(self.lib.rb_trim_paf_end(self.h, int(bool(remove_contained)), want, C.byref(out), C.byref(st) if stats else None))
+        res = self._collect_lift(out, st if stats else None, want)
         self.lib.rb_free_lift_out(self.h, C.byref(out))
         if stats:
             self.lib.rb_free_stats_out(self.h, C.byref(st))

@@ -169,8 +169,9 @@ void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, 
                       cudaStream_t s);
 // n_rounds rounds of select -> pairs -> cut -> round_end, enqueued back to back (rounds after convergence are no-ops).
 // grp_off = n_groups + 1 record offsets of the query names in the name-sorted set; sel = 24 B, keys = 8 B per group;
-// info = 32 B {waiting, done, rounds, status, err_l, err_r, -, -}, zeroed by the caller before the first round.
-void launch_trim_rounds(int n_rounds, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
+// info = 32 B {waiting, done, rounds, status, err_l, err_r, last_waiting, -}, zeroed by the caller before the first round;
+// auto_done: a round that leaves nothing waiting sets `done` (otherwise the caller decides when to stop).
+void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
                         const long long* wp, TrimScores sc, unsigned long long max_score, TrimView* views, uint8_t* contained, void* sel,
                         unsigned long long* keys, void* info, cudaStream_t s);
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,

@@ -121,7 +121,12 @@ struct rb_batch {
     DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans, orig_idx;
     DevBuf bp_cnt, bp_off, bp_end, bp_next, rec_bp;  // break-paf: break ops per chunk, their scan, piece boundaries
     DevBuf trim_qp, trim_wp, trim_views, trim_sel, trim_out, trim_drop;  // trim-paf: per-op query / score prefixes, record views, one round's pairs
-    bool trim_has_drop = false;
+    bool trim_has_drop = false, trim_ready = false;   // trim_ready: between rb_trim_paf_begin and rb_trim_paf_end
+    std::vector<uint32_t> trim_perm;                   // name-sorted position -> the caller's record index
+    int trim_scores[3] = {1, 1, 1};
+    uint64_t trim_max_score = 1, trim_n_ops = 0;
+    uint32_t trim_groups = 0;
+    size_t trim_o[4] = {0, 0, 0, 0};                   // offsets of sel / keys / round state / group offsets inside trim_sel
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     rb_summary sum{};
@@ -1674,13 +1679,14 @@ int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* o
     return rb_batch_download_lift(ctx, b, want & ~RB_WANT_QBED, out, nullptr);
 }
 
-// replaces Paf::overlapping_paf_recs + the print loop of `rb trim-paf` (main.rs:218-230, paf.rs:210-305,
-// trim_overlap.rs:36-86): the round bookkeeping (which pairs of one query overlap, largest first, one pair per query name
-// and round) stays on the host and only ever looks at query spans; scores, split points and truncations run on the device.
-int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,
-                uint32_t want, rb_lift_out* out, rb_stats_out* stats) {
+// `rb trim-paf` = Paf::overlapping_paf_recs + the print loop (main.rs:218-230, paf.rs:210-305, trim_overlap.rs:36-86) in three
+// steps: begin (upload in query-name order, tokenise, strip, scans, untruncated views), rounds (on the device: per query name
+// the pair to trim, its split point, the two truncations), end (one row per record).  rb_trim_paf() runs them back to back;
+// the stepping calls exist for the multi-GPU form, where the decision to run another round is global (see rbcuda.h).
+int rb_trim_paf_begin(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int policy) {
     if (!ctx) return RB_ERR_NO_DEVICE;
-    if (!out || !recs) return fail(ctx, RB_ERR_BAD_ARG, "recs / out is null");
+    if (!recs) return fail(ctx, RB_ERR_BAD_ARG, "recs is null");
+    if (ctx->scratch) ctx->scratch->trim_ready = false;
     if (policy != RB_POLICY_RIGHTMOST)
         return fail(ctx, RB_ERR_UNSUPPORTED, "rb_trim_paf implements the right-most binary_search policy only (Rust < 1.52 / >= 1.82)");
     if (recs->n_rec && (!recs->q_id || !recs->names_off || (!recs->names && recs->n_names && recs->names_off[recs->n_names])))
@@ -1690,7 +1696,6 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     rb_batch* b = ctx->scratch;
     cudaStream_t s = ctx->stream;
     const uint32_t n = recs->n_rec;
-    want &= ~RB_WANT_QBED;
 
     // records.sort_by_key(|rec| rec.q_name.clone()) — stable, byte-wise (paf.rs:224)
     for (uint32_t i = 0; i < n; i++)
@@ -1707,7 +1712,8 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
         const int c = memcmp(px, py, lx < ly ? lx : ly);
         return c ? c : (lx < ly ? -1 : (lx > ly ? 1 : 0));
     };
-    std::vector<uint32_t> perm(n);
+    std::vector<uint32_t>& perm = b->trim_perm;
+    perm.resize(n);
     for (uint32_t i = 0; i < n; i++) perm[i] = i;
     std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return name_cmp(x, y) < 0; });
 
@@ -1783,6 +1789,8 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     for (uint32_t g = 0; g < n_groups; g++)
         if (grp_off[g + 1] - grp_off[g] > 65535u)
             return fail(ctx, RB_ERR_UNSUPPORTED, "more than 65535 records on one query name (record %u)", perm[grp_off[g]]);
+    b->trim_scores[0] = match_score; b->trim_scores[1] = diff_score; b->trim_scores[2] = indel_score;
+    b->trim_max_score = max_score; b->trim_groups = n_groups; b->trim_n_ops = n_ops;
     const size_t o_sel = 0, o_keys = o_sel + ((size_t)n_groups + 1) * sizeof(TrimPairSel), o_info = o_keys + ((size_t)n_groups + 1) * 8,
                  o_grp = o_info + 32, o_end = o_grp + ((size_t)n_groups + 2) * 4;
     CU(b->trim_sel.ensure(o_end + 64));
@@ -1791,29 +1799,69 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     CU(cudaMemsetAsync(b->trim_drop.p, 0, (size_t)n + 1, s));
     CU(cudaMemsetAsync(tb + o_info, 0, 32, s));
     CU(cudaMemcpyAsync(tb + o_grp, grp_off.data(), ((size_t)n_groups + 1) * 4, cudaMemcpyHostToDevice, s));
-    struct { uint32_t waiting, done, rounds, status, err_l, err_r, pad[2]; } info{};
-    const int batch = 8;
-    for (uint64_t it = 0;; it++) {
-        {
-            KScope k(ctx, "k_trim_rounds");
-            launch_trim_rounds(batch, reinterpret_cast<const uint32_t*>(tb + o_grp), n_groups, b->ops.as<uint32_t>(), b->recs.as<RecInfo>(),
-                               b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(), scores, max_score, b->trim_views.as<TrimView>(),
-                               b->trim_drop.as<uint8_t>(), tb + o_sel, reinterpret_cast<unsigned long long*>(tb + o_keys), tb + o_info, s);
-        }
-        CU(cudaMemcpyAsync(&info, tb + o_info, 32, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));  // (also covers the pageable grp_off upload of the first batch)
-        if (info.status == 1) {
-            flush_times(ctx);
-            return fail(ctx, RB_ERR_REF_INTEGRITY, "records %u / %u: truncate_record_by_query leaves spans that disagree with the CIGAR "
-                        "(check_integrity().unwrap() panics, paf.rs:819-822)", perm[info.err_l], perm[info.err_r]);
-        }
-        if (info.status) {
-            flush_times(ctx);
-            return fail(ctx, RB_ERR_UNSUPPORTED, "records %u / %u: overlap x score exceeds the reference's i32 sums", perm[info.err_l], perm[info.err_r]);
-        }
-        if (info.done) break;
-        if (it > (uint64_t)n * n / batch + 8) return fail(ctx, RB_ERR_UNSUPPORTED, "trim rounds do not converge");
+    CU(cudaStreamSynchronize(s));  // grp_off is a pageable local
+    b->trim_o[0] = o_sel; b->trim_o[1] = o_keys; b->trim_o[2] = o_info; b->trim_o[3] = o_grp;
+    b->trim_ready = true;
+    return RB_OK;
+}
+
+// `batch` rounds enqueued back to back, then one look at the 32-byte round state.  auto_done: a round that leaves nothing
+// waiting ends the call (single-GPU form); otherwise the caller decides (multi-GPU form: OR over the ranks).
+static int trim_rounds(rb_ctx* ctx, rb_batch* b, int batch, bool auto_done, uint32_t* waiting, uint32_t* done) {
+    cudaStream_t s = ctx->stream;
+    uint8_t* tb = b->trim_sel.as<uint8_t>();
+    const size_t o_sel = b->trim_o[0], o_keys = b->trim_o[1], o_info = b->trim_o[2], o_grp = b->trim_o[3];
+    const TrimScores scores{b->trim_scores[0], b->trim_scores[1], b->trim_scores[2]};
+    const std::vector<uint32_t>& perm = b->trim_perm;
+    struct { uint32_t waiting, done, rounds, status, err_l, err_r, last_waiting, pad; } info{};
+    {
+        KScope k(ctx, "k_trim_rounds");
+        launch_trim_rounds(batch, auto_done, reinterpret_cast<const uint32_t*>(tb + o_grp), b->trim_groups, b->ops.as<uint32_t>(),
+                           b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(), scores, b->trim_max_score,
+                           b->trim_views.as<TrimView>(), b->trim_drop.as<uint8_t>(), tb + o_sel,
+                           reinterpret_cast<unsigned long long*>(tb + o_keys), tb + o_info, s);
     }
+    CU(cudaMemcpyAsync(&info, tb + o_info, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (info.status == 1) {
+        flush_times(ctx);
+        b->trim_ready = false;
+        return fail(ctx, RB_ERR_REF_INTEGRITY, "records %u / %u: truncate_record_by_query leaves spans that disagree with the CIGAR "
+                    "(check_integrity().unwrap() panics, paf.rs:819-822)", perm[info.err_l], perm[info.err_r]);
+    }
+    if (info.status) {
+        flush_times(ctx);
+        b->trim_ready = false;
+        return fail(ctx, RB_ERR_UNSUPPORTED, "records %u / %u: overlap x score exceeds the reference's i32 sums", perm[info.err_l], perm[info.err_r]);
+    }
+    if (waiting) *waiting = info.last_waiting;
+    if (done) *done = info.done;
+    return RB_OK;
+}
+
+int rb_trim_paf_round(rb_ctx* ctx, int* waiting) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    rb_batch* b = ctx->scratch;
+    if (!b || !b->trim_ready) return fail(ctx, RB_ERR_BAD_ARG, "rb_trim_paf_round without rb_trim_paf_begin");
+    cudaSetDevice(ctx->device);
+    uint32_t w = 0;
+    const int rc = trim_rounds(ctx, b, 1, false, &w, nullptr);
+    if (waiting) *waiting = w ? 1 : 0;
+    return rc;
+}
+
+int rb_trim_paf_end(rb_ctx* ctx, int remove_contained, uint32_t want, rb_lift_out* out, rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out) return fail(ctx, RB_ERR_BAD_ARG, "out is null");
+    rb_batch* b = ctx->scratch;
+    if (!b || !b->trim_ready) return fail(ctx, RB_ERR_BAD_ARG, "rb_trim_paf_end without rb_trim_paf_begin");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    b->trim_ready = false;
+    const uint32_t n = b->n_rec;
+    const uint64_t n_ops = b->trim_n_ops;
+    want &= ~RB_WANT_QBED;
+    int rc = RB_OK;
     b->trim_has_drop = remove_contained != 0 && n > 0;
     const uint64_t P = n;
     CU(b->pair_res.ensure(P * sizeof(PairRes) + 64));
@@ -1829,6 +1877,25 @@ int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_s
     rc = lift_tail(ctx, b, win, RB_POLICY_RIGHTMOST, TAIL_TRIM, want, stats != nullptr, P, n_ops, nullptr);
     if (rc != RB_OK) return rc;
     return rb_batch_download_lift(ctx, b, want, out, stats);
+}
+
+
+int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,
+                uint32_t want, rb_lift_out* out, rb_stats_out* stats) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!out || !recs) return fail(ctx, RB_ERR_BAD_ARG, "recs / out is null");
+    int rc = rb_trim_paf_begin(ctx, recs, match_score, diff_score, indel_score, policy);
+    if (rc != RB_OK) return rc;
+    rb_batch* b = ctx->scratch;
+    const uint64_t n = b->n_rec;
+    for (uint64_t it = 0;; it++) {  // batches of 8 rounds; rounds after convergence are no-ops on the device
+        uint32_t done = 0;
+        rc = trim_rounds(ctx, b, 8, true, nullptr, &done);
+        if (rc != RB_OK) return rc;
+        if (done) break;
+        if (it > n * n / 8 + 8) { b->trim_ready = false; return fail(ctx, RB_ERR_UNSUPPORTED, "trim rounds do not converge"); }
+    }
+    return rb_trim_paf_end(ctx, remove_contained, want, out, stats);
 }
 
 int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {

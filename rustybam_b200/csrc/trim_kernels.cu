@@ -96,7 +96,8 @@ struct TrimInfo {
     uint32_t rounds;   // rounds run so far
     uint32_t status;   // 0, TRIM_ST_ABORT (a truncation the reference panics on) or TRIM_ST_RANGE (overlap x score >= 2^31)
     uint32_t err_l, err_r;  // the pair that set `status`
-    uint32_t pad[2];
+    uint32_t last_waiting;  // `waiting` of the round that ended last (read by the host in the stepping form)
+    uint32_t pad;
 };
 enum : uint32_t { TRIM_ST_ABORT = 1, TRIM_ST_RANGE = 2 };
 
@@ -222,10 +223,11 @@ k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* 
 // disjoint and a failed call produces no output, so it does not matter which of them still get cut.
 
 // after the cuts of a round: nothing waiting -> the call is done (paf.rs:283-300); else the next round starts over
-__global__ void k_trim_round_end(TrimInfo* info) {
+__global__ void k_trim_round_end(TrimInfo* info, int auto_done) {
     if (info->done | info->status) return;
     info->rounds++;
-    if (info->waiting == 0) info->done = 1;
+    info->last_waiting = info->waiting;
+    if (auto_done && info->waiting == 0) info->done = 1;
     info->waiting = 0;
 }
 
@@ -259,7 +261,7 @@ void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, 
                       cudaStream_t s) {
     if (n_rec) k_trim_scan<<<n_rec, TSCAN_THREADS, 0, s>>>(ops, recs, n_rec, sc, qp, wp, views);
 }
-void launch_trim_rounds(int n_rounds, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
+void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
                         const long long* wp, TrimScores sc, unsigned long long max_score, TrimView* views, uint8_t* contained, void* sel,
                         unsigned long long* keys, void* info, cudaStream_t s) {
     static_assert(sizeof(TrimPairDev) == 24 && sizeof(TrimInfo) == 32, "layouts");
@@ -275,7 +277,7 @@ void launch_trim_rounds(int n_rounds, const uint32_t* grp_off, uint32_t n_groups
             k_trim_pairs<<<dim3(n_groups, slices), TPAIR_THREADS, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
             k_trim_cut<<<(n_groups + 127) / 128, 128, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
         }
-        k_trim_round_end<<<1, 1, 0, s>>>(inf);
+        k_trim_round_end<<<1, 1, 0, s>>>(inf, auto_done ? 1 : 0);
     }
 }
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,

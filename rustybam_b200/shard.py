@@ -89,3 +89,52 @@ def merge_outputs(contig_order, per_rank_text):
             assert t not in by_target, "a target contig belongs to exactly one rank"
             by_target[t] = rows
     return b"".join(by_target.get(t, b"") for t in contig_order)
+
+
+# ---- rb trim-paf: records interact only with records of the SAME QUERY NAME (paf.rs:229-239), so the set
+# shards by query name — LPT on CIGAR bytes again.  But the reference's decision to run another round is GLOBAL (`if unseen > 0`
+# counts the waiting pairs of all names, paf.rs:283-285) and a name's result depends on it (a record that was contained when its
+# name's last pair was cut may overlap the cut records afterwards; it is only trimmed if another name forces one more round).
+# So this sub-command has one real exchange step: after every round the ranks OR one flag.  Every rank's rows come out ordered
+# by query name and the host merges the name groups back into the reference's order (stable sort by q_name, paf.rs:224).
+def split_by_query(paf_text: bytes):
+    """Lines of a PAF grouped by query name, file order kept inside a name: {q_name: bytes}."""
+    out = {}
+    for ln in paf_text.splitlines(keepends=True):
+        if ln.strip():
+            out.setdefault(ln.split(None, 1)[0], []).append(ln)
+    return {k: b"".join(v) for k, v in out.items()}
+
+
+def shard_by_query(paf_text: bytes, world: int):
+    """Per-rank PAF texts for `rb trim-paf`: whole query names, balanced by bytes.  Returns (texts, balance)."""
+    groups = split_by_query(paf_text)
+    bins, loads = lpt_bins({k: len(v) for k, v in groups.items()}, world)
+    owner = {k: r for r, b in enumerate(bins) for k in b}
+    texts = [[] for _ in range(world)]
+    for ln in paf_text.splitlines(keepends=True):  # file order is kept inside every rank (it breaks ties of the stable sort)
+        if ln.strip():
+            texts[owner[ln.split(None, 1)[0]]].append(ln)
+    mean = sum(loads) / world if world else 0
+    return [b"".join(t) for t in texts], (max(loads) / mean if mean else 1.0)
+
+
+def trim_rounds_lockstep(round_fn, any_waiting):
+    """The round loop of one rank: `round_fn()` runs one round on this rank's names and says whether one of its pairs had to
+    wait; `any_waiting(flag)` ORs the flag over all ranks (torch.distributed all_reduce MAX; identity on one rank).  Every
+    rank runs the same number of rounds — the whole set's."""
+    rounds = 1
+    while any_waiting(round_fn()):
+        rounds += 1
+    return rounds
+
+
+def merge_trim_outputs(per_rank_text):
+    """Concatenates the ranks' `rb trim-paf` outputs in the reference's order: query names ascending (byte-wise); a name's
+    rows all come from the rank that owns it, already in their final order."""
+    by_query = {}
+    for text in per_rank_text:
+        for q, rows in split_by_query(text).items():
+            assert q not in by_query, "a query name belongs to exactly one rank"
+            by_query[q] = rows
+    return b"".join(by_query[q] for q in sorted(by_query))

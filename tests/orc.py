@@ -70,6 +70,31 @@ def run_trim_paf(paf: bytes, match_score=1, diff_score=1, indel_score=1, remove_
     return _take(out, n)
 
 
+class TrimSteps:
+    """`rb trim-paf` one recursion level at a time (paf.rs:210-287): begin -> round() until nobody waits -> end()."""
+
+    def __init__(self, paf: bytes, match_score=1, diff_score=1, indel_score=1, policy=RIGHTMOST):
+        err = C.create_string_buffer(512)
+        lib().orc_trim_begin.restype = C.c_void_p
+        self.h = lib().orc_trim_begin(paf, C.c_size_t(len(paf)), err, C.c_size_t(512))
+        if not self.h:
+            raise ReferencePanic(err.value.decode())
+        self.args = (int(match_score), int(diff_score), int(indel_score), policy)
+
+    def round(self) -> bool:
+        w, err = C.c_int(), C.create_string_buffer(512)
+        rc = lib().orc_trim_round(C.c_void_p(self.h), *self.args, C.byref(w), err, C.c_size_t(512))
+        if rc == 101:
+            raise ReferencePanic(err.value.decode())
+        return bool(w.value)
+
+    def end(self, remove_contained=False) -> bytes:
+        out, n = C.c_void_p(), C.c_size_t()
+        lib().orc_trim_end(C.c_void_p(self.h), int(remove_contained), C.byref(out), C.byref(n))
+        self.h = None
+        return _take(out, n)
+
+
 def trim_pair(left: str, right: str, match_score=1, diff_score=1, indel_score=1, policy=RIGHTMOST):
     """aligned_pairs on both + trim_overlapping_pafs (trim_overlap.rs:36-86); returns the two output lines."""
     out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)

@@ -112,6 +112,36 @@ def test_trim_bundled_fixture(ctx):
     assert changed > 100
 
 
+def test_trim_shards_by_query_name(ctx):
+    # the multi-GPU form (shard.shard_by_query + rb_trim_paf_begin / _round / _end): whole query names per rank, one flag
+    # OR-ed over the ranks after every round.  Three "ranks" = three contexts on this GPU, stepped in lockstep.
+    from rustybam_b200 import shard
+    from test_shard_gloo import COUPLED
+    for paf_text in (COUPLED, gen.random_trim_paf(31, n_names=12, recs_per_name=5, max_ops=60, lead_trail=False)):
+        want = orc.run_trim_paf(paf_text, 1, 1, 1, True)
+        assert liftover.run_trim_paf(ctx, paf_text, 1, 1, 1, True) == want      # the single call counts waiting pairs globally
+        texts, balance = shard.shard_by_query(paf_text, 3)
+        ranks = [capi.Context(0) for _ in texts]
+        try:
+            for c, t in zip(ranks, texts):
+                c.trim_paf_begin(Paf.from_text(t).pack(), 1, 1, 1)
+            rounds = 1
+            while any([c.trim_paf_round() for c in ranks]):   # (a list: every rank runs the round before the flags are OR-ed)
+                rounds += 1
+            outs = [c.trim_paf_end(True, want=capi.WANT_TEXT, stats=False)["paf_text"] for c in ranks]
+        finally:
+            for c in ranks:
+                c.close()
+        assert shard.merge_trim_outputs(outs) == want
+        assert sum(t.count(b"\n") for t in texts) == paf_text.count(b"\n")
+    # the coupled set: name X alone stops one round earlier and keeps its contained record untrimmed
+    x_only = b"".join(ln for ln in COUPLED.splitlines(keepends=True) if ln.startswith(b"X"))
+    alone = liftover.run_trim_paf(ctx, x_only, 1, 1, 1, False)
+    assert alone == orc.run_trim_paf(x_only, 1, 1, 1, False)
+    whole = liftover.run_trim_paf(ctx, COUPLED, 1, 1, 1, False)
+    assert [ln for ln in whole.splitlines() if ln.startswith(b"X")] != alone.splitlines()
+
+
 def test_trim_errors(ctx):
     paf = Paf.from_text(gen.random_trim_paf(3))
     with pytest.raises(RbError) as e:  # only the right-most binary_search policy is implemented for this call
