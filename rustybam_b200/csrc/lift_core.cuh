@@ -401,6 +401,15 @@ RB_HD uint32_t combine_pair(const OpsView& v, const RecInfo& r, uint64_t w_st, u
     return LIFT_OK;
 }
 
+// Rows whose untouched ops are a long verbatim run of the input text (whole-record rows of trim-paf, early rows and wide
+// windows over long records): when the rows of a call are few and long, k_serialise leaves that run to k_copy_mid, which
+// spreads it over the grid instead of one warp per row.  Both kernels decide with this predicate.
+constexpr uint32_t MID_BIG = 8192;
+RB_HD bool mid_is_big(const RecInfo& r, const PairRes& p) {
+    return (r.flags & RF_CANON) && p.mid_len >= MID_BIG &&
+           (p.kind == PK_EARLY || (p.kind == PK_TRIM && p.ei > p.si && !(r.flags & RF_SLOW)));
+}
+
 // Bytes of the printed PAF line (paf.rs:923-943), '\n' included = a part that depends on the record only ...
 RB_HD uint32_t line_const_bytes(const RecInfo& r, uint32_t q_name_len, uint32_t t_name_len) {
     return q_name_len + t_name_len + ndigits64(r.q_len) + 1 /*strand*/ + ndigits64(r.t_len) + ndigits64(r.mapq) +

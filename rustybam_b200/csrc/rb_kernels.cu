@@ -1557,7 +1557,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             SerArgs a, const LiftPlan* __restrict__ plans, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
             const uint64_t* __restrict__ out_idx,
             uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
-            uint32_t rec_base, const uint32_t* __restrict__ orig_idx, uint32_t group) {
+            uint32_t rec_base, const uint32_t* __restrict__ orig_idx, uint32_t group, uint32_t defer_big) {
     // `group` = lines per block: SER_LINES normally; 8 when the rows are few and long (100 kb windows: a 4 KB line
     // per pair), so that the warp-per-line path below spreads over 16x more blocks
     extern __shared__ __align__(16) uint8_t s_buf[];
@@ -1660,7 +1660,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
                 }
                 pos = ndigits32(lp.s_len) + 1;
             }
-            if (lp.kind == PK_EARLY || lp.ei > lp.si) {
+            if ((lp.kind == PK_EARLY || lp.ei > lp.si) && !(defer_big && mid_is_big(ri, lp))) {  // (big runs: k_copy_mid)
                 const uint8_t* src = a.text + lp.mid_off;
                 for (uint32_t i = lane; i < lp.mid_len; i += 32) dst[pos + i] = src[i];
             }
@@ -1696,6 +1696,49 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         }
         if (lane == 0) out_text[line_off[q + 1] - 1] = '\n';
         __syncwarp();
+    }
+}
+
+// The long verbatim runs k_serialise deferred (mid_is_big): block (row, y) copies the 64 KB segments y, y + gridDim.y, ... of
+// the row's run from the input text to its place in the output — 16-byte stores, the source re-aligned with funnel shifts
+// (source and destination have unrelated alignments; the text buffer is padded on both sides, so word over-reads stay inside).
+constexpr int CM_THREADS = 256;
+constexpr uint32_t CM_SEG = 65536;
+__global__ void __launch_bounds__(CM_THREADS)
+k_copy_mid(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
+           const RecInfo* __restrict__ recs, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
+           const uint8_t* __restrict__ text, uint8_t* __restrict__ out_text) {
+    const uint64_t q = blockIdx.x;
+    if (q >= n_pairs) return;
+    const PairRes& lp = res[q];
+    if (lp.kind == PK_DROP || lp.mid_len < MID_BIG) return;
+    const uint32_t k = rank_of_pair(pair_off, n_rec, q);
+    const RecInfo& ri = recs[rec_order[k]];
+    if (!mid_is_big(ri, lp)) return;
+    const uint64_t llen = line_off[q + 1] - line_off[q];
+    const uint64_t hdr = llen - lp.cg_bytes - 1;
+    uint8_t* dst0 = out_text + line_off[q] + hdr + (lp.kind == PK_TRIM ? ndigits32(lp.s_len) + 1u : 0u);
+    const uint8_t* src0 = text + lp.mid_off;
+    for (uint64_t seg = (uint64_t)blockIdx.y * CM_SEG; seg < lp.mid_len; seg += (uint64_t)gridDim.y * CM_SEG) {
+        const uint32_t n = (uint32_t)((lp.mid_len - seg < CM_SEG) ? (lp.mid_len - seg) : CM_SEG);
+        uint8_t* dst = dst0 + seg;
+        const uint8_t* src = src0 + seg;
+        const uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+        const uint32_t hb = head < n ? head : n;
+        const uint32_t nvec = (n - hb) >> 4;
+        for (uint32_t i = threadIdx.x; i < hb; i += CM_THREADS) dst[i] = src[i];
+        const uint8_t* sb = src + hb;
+        const uint32_t sh = (uint32_t)((uintptr_t)sb & 3u) * 8u;
+        const uint32_t* w0 = reinterpret_cast<const uint32_t*>((uintptr_t)sb & ~(uintptr_t)3);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + hb);
+        for (uint32_t v = threadIdx.x; v < nvec; v += CM_THREADS) {
+            const uint32_t* w = w0 + (size_t)v * 4;
+            const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2), a3 = __ldg(w + 3), a4 = __ldg(w + 4);
+            uint4 x;
+            x.x = __funnelshift_r(a0, a1, sh); x.y = __funnelshift_r(a1, a2, sh); x.z = __funnelshift_r(a2, a3, sh); x.w = __funnelshift_r(a3, a4, sh);
+            d4[v] = x;
+        }
+        for (uint32_t i = hb + (nvec << 4) + threadIdx.x; i < n; i += CM_THREADS) dst[i] = src[i];
     }
 }
 
@@ -1843,7 +1886,7 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
-                      uint32_t group, cudaStream_t s) {
+                      uint32_t group, uint32_t defer_big, cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1855,7 +1898,15 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     SerArgs a{recs, view, win, names_off, names, text};
     if (group == 0 || group > (uint32_t)SER_LINES || (SER_LINES % group)) group = SER_LINES;
     k_serialise<<<(unsigned)((n_pairs + group - 1) / group), SER_LINES, SER_CAP, s>>>(
-        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx, group);
+        n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx, group,
+        defer_big);
+}
+void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                     const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s) {
+    if (n_pairs == 0 || n_pairs > 0x7FFFFFFFull) return;
+    if (seg_y < 1u) seg_y = 1u;
+    if (seg_y > 64u) seg_y = 64u;
+    k_copy_mid<<<dim3((unsigned)n_pairs, seg_y), CM_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, res, line_off, text, out_text);
 }
 // ------------------------------------------------------------------------------------------------
 // rb break-paf: windows from the record's own large indels (liftover.rs:182-226)

@@ -146,7 +146,10 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
-                      uint32_t group, cudaStream_t s);
+                      uint32_t group, uint32_t defer_big, cudaStream_t s);
+// few, long rows: the long verbatim runs of input text that k_serialise (defer_big = 1) left out, spread over the grid
+void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                     const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s);
 struct PublishArgs {  // up to 8 device scalars (u32 or u64) -> slots of a mapped pinned u64 array
     const void* src[8];
     uint8_t slot[8];

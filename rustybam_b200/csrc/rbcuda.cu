@@ -964,6 +964,12 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     // (whole-record rows of rb invert: 4 per block, a warp each)
     const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? (tail == TAIL_WHOLE ? 4u : 8u)
                                                                                                : (uint32_t)SER_LINES;
+    // in that regime the long verbatim runs of input text inside the rows (whole-record rows, early rows, wide windows) are
+    // copied by the whole grid (k_copy_mid) instead of one warp per row
+    uint64_t max_rec_bytes = 0;
+    const uint32_t defer_big = (ser_group != (uint32_t)SER_LINES && (want & RB_WANT_TEXT) && tail != TAIL_WHOLE && !b->invert) ? 1u : 0u;
+    if (defer_big)
+        for (size_t i = 0; i + 1 < b->h_cigar_off.size(); i++) max_rec_bytes = std::max(max_rec_bytes, b->h_cigar_off[i + 1] - b->h_cigar_off[i]);
     {
         KScope k(ctx, "k_serialise");
         launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
@@ -972,7 +978,13 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
                          b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(), (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr,
                          (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                          (want & RB_WANT_NUMERIC) ? num_view(b, n_out) : NumDev{}, with_stats ? stats_view(b, n_out) : StatsDev{},
-                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, s);
+                         b->byte_base, b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), ser_group, defer_big, s);
+    }
+    if (defer_big) {
+        KScope k(ctx, "k_copy_mid");
+        launch_copy_mid(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->pair_res.as<PairRes>(),
+                        b->line_off.as<uint64_t>(), b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, b->out_text.as<uint8_t>(),
+                        (uint32_t)((max_rec_bytes + 65535) / 65536), s);
     }
     if (tail == TAIL_WHOLE && (want & RB_WANT_TEXT)) {
         KScope k(ctx, "k_whole_text");
