@@ -965,7 +965,8 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     const uint32_t ser_group = (n_out && out_bytes / n_out > 1536 && P / SER_LINES < 4 * 148) ? (tail == TAIL_WHOLE ? 4u : 8u)
                                                                                                : (uint32_t)SER_LINES;
     // in that regime the long verbatim runs of input text inside the rows (whole-record rows, early rows, wide windows) are
-    // copied by the whole grid (k_copy_mid) instead of one warp per row
+    // copied by the whole grid (k_copy_mid) instead of one warp per row; blocks per row are capped so that a call with
+    // many rows and no long run pays one empty block per row
     uint64_t max_rec_bytes = 0;
     const uint32_t defer_big = (ser_group != (uint32_t)SER_LINES && (want & RB_WANT_TEXT) && tail != TAIL_WHOLE && !b->invert) ? 1u : 0u;
     if (defer_big)
@@ -984,7 +985,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         KScope k(ctx, "k_copy_mid");
         launch_copy_mid(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->pair_res.as<PairRes>(),
                         b->line_off.as<uint64_t>(), b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, b->out_text.as<uint8_t>(),
-                        (uint32_t)((max_rec_bytes + 65535) / 65536), s);
+                        (uint32_t)std::min<uint64_t>((max_rec_bytes + 65535) / 65536, std::max<uint64_t>(1, 8192 / std::max<uint64_t>(P, 1))), s);
     }
     if (tail == TAIL_WHOLE && (want & RB_WANT_TEXT)) {
         KScope k(ctx, "k_whole_text");
