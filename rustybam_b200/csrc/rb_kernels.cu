@@ -1699,22 +1699,22 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
     }
 }
 
-// The long verbatim runs k_serialise deferred (mid_is_big): block (row, y) copies the 64 KB segments y, y + gridDim.y, ... of
-// the row's run from the input text to its place in the output — 16-byte stores, the source re-aligned with funnel shifts
+// The long verbatim runs k_serialise deferred (mid_is_big): block (x, y) looks at rows 16x .. 16x + 15 and copies the 64 KB
+// segments y, y + gridDim.y, ... of each long run from the input text to its place in the output — 16-byte stores, the source re-aligned with funnel shifts
 // (source and destination have unrelated alignments; the text buffer is padded on both sides, so word over-reads stay inside).
 constexpr int CM_THREADS = 256;
 constexpr uint32_t CM_SEG = 65536;
+constexpr uint32_t CM_ROWS = 16;  // rows looked at by one block (a call with many rows and no long run pays one block per 16 rows)
 __global__ void __launch_bounds__(CM_THREADS)
 k_copy_mid(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
            const RecInfo* __restrict__ recs, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
            const uint8_t* __restrict__ text, uint8_t* __restrict__ out_text) {
-    const uint64_t q = blockIdx.x;
-    if (q >= n_pairs) return;
+  for (uint64_t q = (uint64_t)blockIdx.x * CM_ROWS; q < n_pairs && q < ((uint64_t)blockIdx.x + 1) * CM_ROWS; q++) {  // (block-uniform)
     const PairRes& lp = res[q];
-    if (lp.kind == PK_DROP || lp.mid_len < MID_BIG) return;
+    if (lp.kind == PK_DROP || lp.mid_len < MID_BIG) continue;
     const uint32_t k = rank_of_pair(pair_off, n_rec, q);
     const RecInfo& ri = recs[rec_order[k]];
-    if (!mid_is_big(ri, lp)) return;
+    if (!mid_is_big(ri, lp)) continue;
     const uint64_t llen = line_off[q + 1] - line_off[q];
     const uint64_t hdr = llen - lp.cg_bytes - 1;
     uint8_t* dst0 = out_text + line_off[q] + hdr + (lp.kind == PK_TRIM ? ndigits32(lp.s_len) + 1u : 0u);
@@ -1740,6 +1740,7 @@ k_copy_mid(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32
         }
         for (uint32_t i = hb + (nvec << 4) + threadIdx.x; i < n; i += CM_THREADS) dst[i] = src[i];
     }
+  }
 }
 
 // rb invert: the CIGAR text of the whole-record rows.  One warp per 32-op chunk of the (already inverted) op array:
@@ -1906,7 +1907,7 @@ void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t*
     if (n_pairs == 0 || n_pairs > 0x7FFFFFFFull) return;
     if (seg_y < 1u) seg_y = 1u;
     if (seg_y > 64u) seg_y = 64u;
-    k_copy_mid<<<dim3((unsigned)n_pairs, seg_y), CM_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, res, line_off, text, out_text);
+    k_copy_mid<<<dim3((unsigned)((n_pairs + CM_ROWS - 1) / CM_ROWS), seg_y), CM_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, res, line_off, text, out_text);
 }
 // ------------------------------------------------------------------------------------------------
 // rb break-paf: windows from the record's own large indels (liftover.rs:182-226)
