@@ -968,7 +968,10 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     // copied by the whole grid (k_copy_mid) instead of one warp per row; blocks per row are capped so that a call with
     // many rows and no long run pays one empty block per row
     uint64_t max_rec_bytes = 0;
-    const uint32_t defer_big = (ser_group != (uint32_t)SER_LINES && (want & RB_WANT_TEXT) && tail != TAIL_WHOLE && !b->invert) ? 1u : 0u;
+    // (whole-record-like rows — trim-paf, break-paf — or rows that are long on average; 100 kb windows over ~16 ops/kb make 4 KB
+    // rows with hardly any run above the threshold, and the extra launch would cost them 2 %)
+    const uint32_t defer_big = (ser_group != (uint32_t)SER_LINES && (want & RB_WANT_TEXT) && tail != TAIL_WHOLE && !b->invert &&
+                                (tail == TAIL_TRIM || win.from_record || out_bytes / n_out >= MID_BIG)) ? 1u : 0u;
     if (defer_big)
         for (size_t i = 0; i + 1 < b->h_cigar_off.size(); i++) max_rec_bytes = std::max(max_rec_bytes, b->h_cigar_off[i + 1] - b->h_cigar_off[i]);
     {

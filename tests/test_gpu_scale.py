@@ -30,7 +30,7 @@ def full():
     return hostlib.HostPaf.synth(scale=1.0)
 
 
-@pytest.mark.parametrize("width", [1000, 100_000])
+@pytest.mark.parametrize("width", [1000, 100_000, 2_000_000])  # 2 Mb windows: ~80 KB rows, their verbatim runs leave through k_copy_mid
 def test_synth_2pct_exact_parity(ctx, width):
     paf = hostlib.HostPaf.synth(scale=0.02)
     wins = paf.tiling_windows(width)
