@@ -857,9 +857,27 @@ std::string fmt_f32(float v) {
     std::string digits;
     int e10 = 0;
     bool neg = v < 0;
+    const float av = std::fabs(v);
     for (int p = 1; p <= 9; p++) {
-        snprintf(buf, sizeof buf, "%.*e", p - 1, (double)std::fabs(v));
-        if (strtof(buf, nullptr) == std::fabs(v) || p == 9) {
+        snprintf(buf, sizeof buf, "%.*e", p - 1, (double)av);  // the p-digit decimal closest to v
+        bool ok = strtof(buf, nullptr) == av || p == 9;
+        if (!ok && strtod(buf, nullptr) < (double)av) {
+            // At an exact power of two the rounding interval reaches twice as far up as down: the closest p-digit decimal can
+            // fall short of it from below while its upper neighbour is inside.  The shortest-digits algorithms (Grisu / Dragon4
+            // in Rust's flt2dec, with `minus = 1, plus = 2` for such mantissas) print that neighbour.  Found by the exhaustive
+            // cross-check against std::to_chars (tests/native/f32_fmt_check.cpp): 2^-96 is the one f32 in [0, 100] it affects.
+            unsigned long long m = 0;
+            const char* e = strchr(buf, 'e');
+            for (const char* c = buf; c < e; c++)
+                if (is_digit(*c)) m = m * 10 + (unsigned long long)(*c - '0');
+            char up[64];
+            snprintf(up, sizeof up, "%llue%d", m + 1, atoi(e + 1) - (p - 1));
+            if (strtof(up, nullptr) == av) {
+                snprintf(buf, sizeof buf, "%.*e", p - 1, strtod(up, nullptr));  // same digits, canonical "d.ddde+xx" spelling
+                ok = true;
+            }
+        }
+        if (ok) {
             const char* e = strchr(buf, 'e');
             e10 = atoi(e + 1);
             for (const char* c = buf; c < e; c++)
