@@ -1775,8 +1775,8 @@ int rb_trim_paf_begin(rb_ctx* ctx, const rb_records* recs, int match_score, int 
 
     // per-op query / score prefixes and the untruncated views
     const TrimScores scores{match_score, diff_score, indel_score};
-    CU(b->trim_qp.ensure(b->ops_bound * 4 + 64));
-    CU(b->trim_wp.ensure(b->ops_bound * 8 + 64));
+    CU(b->trim_qp.ensure(n_ops * 4 + 64));  // (the op count is known by now: 12 B per op, not per byte of text / 2)
+    CU(b->trim_wp.ensure(n_ops * 8 + 64));
     CU(b->trim_views.ensure((size_t)n * sizeof(TrimView) + 64));
     {
         KScope k(ctx, "k_trim_scan");
