@@ -877,6 +877,28 @@ std::string fmt_f32(float v) {
                 ok = true;
             }
         }
+        if (ok && p < 9) {
+            // printf rounds an exact tie to even; Rust's shortest formatter (core::num::flt2dec::strategy::dragon::format_shortest,
+            // which its Grisu fast path defers to whenever the two neighbours are equally close) rounds it UP:
+            // `if up && (!down || *mant.mul_pow2(1) >= scale)`.  A tie = the exact decimal expansion of v has p + 1 significant
+            // digits and ends in 5.  (Stated from knowledge of the std sources — std is not present in this image to confirm;
+            // SURVEY lists the f32 digits as "parity unpinned".)
+            char exact[256];
+            snprintf(exact, sizeof exact, "%.150e", (double)av);  // glibc prints the exact binary value
+            std::string dg;
+            for (const char* c = exact; *c && *c != 'e'; c++)
+                if (is_digit(*c)) dg.push_back(*c);
+            bool tie = dg.size() > (size_t)p && dg[(size_t)p] == '5';
+            for (size_t k = (size_t)p + 1; tie && k < dg.size(); k++) tie = dg[k] == '0';
+            if (tie) {
+                unsigned long long m = 0;
+                for (int k = 0; k < p; k++) m = m * 10 + (unsigned long long)(dg[(size_t)k] - '0');  // truncated p digits
+                const char* e = strchr(exact, 'e');
+                char up[64];
+                snprintf(up, sizeof up, "%llue%d", m + 1, atoi(e + 1) - (p - 1));
+                if (strtof(up, nullptr) == av) snprintf(buf, sizeof buf, "%.*e", p - 1, strtod(up, nullptr));
+            }
+        }
         if (ok) {
             const char* e = strchr(buf, 'e');
             e10 = atoi(e + 1);

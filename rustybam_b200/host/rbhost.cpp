@@ -1,5 +1,6 @@
 // rbhost.cpp — host-side text I/O, packing and printing (see rbhost.hpp for the reference lines).
 #include "rbhost.hpp"
+#include "../csrc/f32_fmt.cuh"
 
 #include <zlib.h>
 
@@ -465,11 +466,11 @@ std::string largest_rows(const rb_lift_out& out) {
 // printing
 // ---------------------------------------------------------------------------------------------
 std::string fmt_f32(float v) {
-    if (std::isnan(v)) return "NaN";
-    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
-    char buf[128];
-    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);  // shortest round trip, positional
-    return std::string(buf, r.ptr);
+    // Rust's `{}` for f32: shortest round-trip digits, closest to the value, an exact tie rounded UP (flt2dec's Dragon; Ryu /
+    // std::to_chars round such ties to even) — csrc/f32_fmt.cuh, the same code a device-side row formatter will call
+    uint8_t buf[96];
+    const int n = rb::f32_display(v, buf);
+    return std::string(reinterpret_cast<const char*>(buf), (size_t)n);
 }
 
 std::string stats_header(bool qbed) {

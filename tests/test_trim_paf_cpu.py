@@ -66,12 +66,13 @@ def test_closed_form_trim_matches_literal_oracle(harness, seed):
 
 def test_f32_display_restatements_agree(tmp_path):
     """Rust's f32 `Display` (shortest round-trip digits, positional; bamstats.rs:262-265) is restated twice, independently:
-    the oracle tries precisions with printf + strtof, the C++ host uses std::to_chars.  No reference test pins the digits
-    ("parity unpinned"), so the two are compared over a strided sweep of every f32 in [0, 100] — the identities' range — plus
-    the neighbourhood of every power of two (where the rounding interval is asymmetric).  The exhaustive sweep (1.12 G values,
-    no difference) is recorded in DESIGN.md section 2."""
+    the oracle tries precisions with printf + strtof (+ an exact-expansion tie test), the product's csrc/f32_fmt.cuh (host
+    formatter today, device-ready) generates Burger-Dybvig free-format digits; std::to_chars is a third opinion that may only
+    differ at exact ties.  No reference test pins the digits ("parity unpinned"), so they are compared over a strided sweep of
+    every f32 in [0, 100] — the identities' range — plus the neighbourhood of every power of two (where the rounding interval
+    is asymmetric).  The exhaustive sweep (1.12 G values, no difference) is recorded in profiles/r01z_f32_fmt.txt."""
     exe = str(tmp_path / "f32_fmt_check")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "oracle"), "-o", exe,
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "rustybam_b200", "csrc"), "-o", exe,
                            os.path.join(ROOT, "tests", "native", "f32_fmt_check.cpp"), os.path.join(ROOT, "oracle", "rb_oracle.cpp")])
     r = subprocess.run([exe, "0", "100", "4099"], capture_output=True, text=True)
     assert r.returncode == 0 and "DIFF=0" in r.stdout, r.stdout + r.stderr
