@@ -55,7 +55,7 @@ def build_host(force=False, verbose=False):
     if not srcs:
         return None
     deps = srcs + _sources(HOST, (".hpp", ".h")) + [os.path.join(ROOT, "include", "rbcuda.h"), os.path.abspath(__file__),
-                                                    os.path.join(CSRC, "f32_fmt.cuh"), os.path.join(CSRC, "rb_common.cuh")]
+                                                    os.path.join(CSRC, "f32_fmt.cuh"), os.path.join(CSRC, "rb_common.cuh")]  # (f32_fast.hpp includes them)
     gxx = shutil.which("g++") or "g++"
     common = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wextra", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", HOST]
     lib_srcs = [s for s in srcs if not s.endswith("rb_main.cpp")]

@@ -1,6 +1,6 @@
 // rbhost.cpp — host-side text I/O, packing and printing (see rbhost.hpp for the reference lines).
 #include "rbhost.hpp"
-#include "../csrc/f32_fmt.cuh"
+#include "f32_fast.hpp"
 
 #include <zlib.h>
 
@@ -467,10 +467,8 @@ std::string largest_rows(const rb_lift_out& out) {
 // ---------------------------------------------------------------------------------------------
 std::string fmt_f32(float v) {
     // Rust's `{}` for f32: shortest round-trip digits, closest to the value, an exact tie rounded UP (flt2dec's Dragon; Ryu /
-    // std::to_chars round such ties to even) — csrc/f32_fmt.cuh, the same code a device-side row formatter will call
-    uint8_t buf[96];
-    const int n = rb::f32_display(v, buf);
-    return std::string(reinterpret_cast<const char*>(buf), (size_t)n);
+    // std::to_chars round such ties to even): std::to_chars unless the value is exactly such a tie, then csrc/f32_fmt.cuh
+    return f32_display_fast(v);
 }
 
 std::string stats_header(bool qbed) {

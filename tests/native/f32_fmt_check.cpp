@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "f32_fmt.cuh"
+#include "../../rustybam_b200/host/f32_fast.hpp"
 #include "rb_oracle.hpp"
 
 static std::string host_fmt(float v) {  // std::to_chars (what the host used before f32_fmt.cuh)
@@ -47,6 +48,10 @@ int main(int argc, char** argv) {
                 all++;
                 if (!no_oracle && a != d) {
                     if (diff < 5) fprintf(stderr, "DIFF bits %08x: oracle %s core %s (to_chars %s)\n", bb, a.c_str(), d.c_str(), c.c_str());
+                    diff++;
+                }
+                if (rbh::f32_display_fast(v) != d) {  // the host's fast path (to_chars + exact tie test) must equal the core
+                    if (diff < 5) fprintf(stderr, "DIFF bits %08x: host fast path %s core %s\n", bb, rbh::f32_display_fast(v).c_str(), d.c_str());
                     diff++;
                 }
                 if (d != c) {  // must be an exact tie: same length, the last digit one higher than std::to_chars' (half-even) choice
