@@ -156,6 +156,30 @@ int orc_bench_pipeline(const char* paf, size_t paf_n, const char* bed, size_t be
     }
 }
 
+// The same pipeline, keeping the bytes both halves print (bench.py compares them with the GPU rows of the same contigs).
+int orc_bench_pipeline_keep(const char* paf, size_t paf_n, const char* bed, size_t bed_n, int policy, int threads,
+                            double* secs_liftover, double* secs_stats, uint64_t* n_rows, char** lifted_out, size_t* lifted_n,
+                            char** stats_out, size_t* stats_n, char* err, size_t err_cap) {
+    try {
+        auto t0 = std::chrono::steady_clock::now();
+        std::string lifted = run_liftover(paf, paf_n, bed, bed_n, false, false, policy, threads);
+        auto t1 = std::chrono::steady_clock::now();
+        std::string st = run_stats(lifted.data(), lifted.size(), false);
+        auto t2 = std::chrono::steady_clock::now();
+        uint64_t rows = 0;
+        for (char c : lifted) rows += (c == '\n');
+        *secs_liftover = std::chrono::duration<double>(t1 - t0).count();
+        *secs_stats = std::chrono::duration<double>(t2 - t1).count();
+        *n_rows = rows;
+        *lifted_out = dup_out(lifted, lifted_n);
+        *stats_out = dup_out(st, stats_n);
+        return 0;
+    } catch (const Abort& e) {
+        set_err(err, err_cap, e.what());
+        return 101;
+    }
+}
+
 // one (record line, region) pair through aligned_pairs + trim_paf_rec_to_rgn
 int orc_trim_line(const char* paf_line, const char* rgn_name, uint64_t st, uint64_t en,
                   const char* rgn_id, int policy, char** out, size_t* out_n, char* err,

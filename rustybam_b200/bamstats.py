@@ -7,13 +7,11 @@ from .paf import Paf, ReferencePanic
 
 
 def fmt_f32(v) -> str:
-    """Rust `{}` for f32: shortest round-trip digits, positional, no trailing '.0'."""
-    v = np.float32(v)
-    if np.isnan(v):
-        return "NaN"
-    if np.isinf(v):
-        return "-inf" if v < 0 else "inf"
-    return np.format_float_positional(v, unique=True, trim="-")
+    """Rust `{}` for f32: shortest round-trip digits, positional, no trailing '.0'; an exact tie between the two shortest
+    candidates rounds UP (flt2dec's Dragon rule) where numpy / printf round to even — so this goes through the C++ host's
+    formatter (host/f32_fast.hpp), e.g. 16.0078125 -> "16.007813"."""
+    from . import hostlib
+    return hostlib.fmt_f32(float(np.float32(v)))
 
 
 def print_cigar_stats_header(qbed=False) -> str:

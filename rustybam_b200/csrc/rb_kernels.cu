@@ -1456,6 +1456,7 @@ __device__ __forceinline__ P put_op(P p, uint32_t len, uint32_t code) {
     return p + 1;
 }
 
+constexpr int EMIT_CAP = 30 * 1024;  // k_emit: smem bytes for composing one round of lines
 struct SerArgs {
     const RecInfo* recs;
     OpsView v;
@@ -1557,7 +1558,10 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
             SerArgs a, const LiftPlan* __restrict__ plans, const PairRes* __restrict__ res, const uint64_t* __restrict__ line_off,
             const uint64_t* __restrict__ out_idx,
             uint8_t* __restrict__ out_text, uint64_t* __restrict__ out_line_off, NumDev num, StatsDev st, uint64_t byte_base,
-            uint32_t rec_base, const uint32_t* __restrict__ orig_idx, uint32_t group, uint32_t defer_big) {
+            uint32_t rec_base, const uint32_t* __restrict__ orig_idx, uint32_t group, uint32_t defer_big,
+            const uint32_t* __restrict__ only_flagged) {
+    // only_flagged != nullptr: the call finishes what k_emit left (blocks of SER_LINES pairs whose flag is set)
+    if (only_flagged && only_flagged[(uint64_t)blockIdx.x * group / SER_LINES] == 0u) return;
     // `group` = lines per block: SER_LINES normally; 8 when the rows are few and long (100 kb windows: a 4 KB line
     // per pair), so that the warp-per-line path below spreads over 16x more blocks
     extern __shared__ __align__(16) uint8_t s_buf[];
@@ -1696,6 +1700,181 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
         }
         if (lane == 0) out_text[line_off[q + 1] - 1] = '\n';
         __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5'  emit: line scan + serialiser in ONE pass over the pairs
+// ------------------------------------------------------------------------------------------------
+// k_scan_lines + k_serialise fused: a block of SER_LINES consecutive pairs (dynamic ticket order) scans its line sizes,
+// gets the byte / row offset of its first line by decoupled look-back over the blocks in front of it (16-byte payload),
+// writes the stats rows / numeric mirror / line offsets of its rows and composes its lines in shared memory in rounds of
+// <= EMIT_CAP bytes, each leaving as one bulk shared->global copy.  Nothing per pair goes back to HBM in between: no
+// line_off / out_idx arrays, no second read of the results.  The output sizes are only known when the kernel ends, so the
+// caller hands in the capacity of its text buffer: a block whose lines would not fit writes no text and raises the
+// overflow flag (the caller grows the buffer to the exact size — the totals are right either way — and runs the kernel
+// again; steady-state calls reuse the buffer of the call before).  Blocks holding a line longer than EMIT_LONG bytes are
+// left to k_serialise's warp-per-line path: they publish their offsets (line_off / out_idx of their pairs) and a flag.
+constexpr uint32_t EMIT_LONG = 2048;
+struct EmitArgs {
+    uint64_t n_pairs;
+    const uint64_t* pair_off;
+    const uint32_t* rec_order;
+    uint32_t n_rec;
+    SerArgs a;
+    const LiftPlan* plans;
+    const PairRes* res;
+    const uint32_t* line_len;
+    uint64_t* line_off;  // written for deferred blocks only
+    uint64_t* out_idx;
+    uint32_t* blk_flags;  // per block: 1 = its text is left to k_serialise
+    uint8_t* out_text;
+    uint64_t cap_text;
+    uint64_t* out_line_off;
+    NumDev num;
+    StatsDev st;
+    uint64_t byte_base;
+    uint32_t rec_base;
+    const uint32_t* orig_idx;
+    uint32_t* state;
+    ulonglong2* agg;
+    ulonglong2* pre;
+    unsigned int* ticket;
+    unsigned long long* totals;  // [0] bytes of text, [1] rows, [2] != 0: the text did not fit, [3] deferred blocks
+};
+
+__global__ void __launch_bounds__(SER_LINES, 7)
+k_emit(const __grid_constant__ EmitArgs e) {
+    extern __shared__ __align__(16) uint8_t s_buf[];
+    __shared__ uint32_t s_rel[SER_LINES + 1];
+    __shared__ ulonglong2 s_warp[SER_LINES / 32];
+    __shared__ ulonglong2 s_base;
+    __shared__ unsigned int s_blk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_blk = atomicAdd(e.ticket, 1u);
+    __syncthreads();
+    const uint64_t blk = s_blk;
+    const uint64_t p0 = blk * SER_LINES;
+    if (p0 >= e.n_pairs) return;
+    const uint64_t p = p0 + tid;
+    const uint64_t pend = (p0 + SER_LINES < e.n_pairs) ? (p0 + SER_LINES) : e.n_pairs;
+    const uint32_t nlines = (uint32_t)(pend - p0);
+
+    PairRes pr;
+    pr.kind = PK_DROP;
+    uint32_t len = 0;
+    if (p < pend) {
+        len = e.line_len[p];
+        if (len) pr = e.res[p];
+    }
+    const bool live = len != 0u;
+
+    // ---- block scan of (bytes, rows), look-back for the block's base ----
+    unsigned long long ib = len;
+    uint32_t ic = live ? 1u : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long ub = __shfl_up_sync(0xffffffffu, ib, d);
+        const uint32_t uc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { ib += ub; ic += uc; }
+    }
+    if (lane == 31) s_warp[warp] = make_ulonglong2(ib, ic);
+    __syncthreads();
+    unsigned long long wb = 0, wc = 0, tb = 0, tc = 0;
+#pragma unroll
+    for (int k = 0; k < SER_LINES / 32; k++) {
+        const ulonglong2 t = s_warp[k];
+        if (k < warp) { wb += t.x; wc += t.y; }
+        tb += t.x; tc += t.y;
+    }
+    if (warp == 0) {
+        const ulonglong2 ex = lookback_2u64(e.state, e.agg, e.pre, blk, make_ulonglong2(tb, tc));
+        if (lane == 0) s_base = ex;
+    }
+    const unsigned long long rel = wb + ib - len;  // bytes of the block's lines in front of mine
+    s_rel[tid] = (uint32_t)rel;
+    if (tid == 0) s_rel[SER_LINES] = (uint32_t)tb;
+    const bool small = __syncthreads_and(len <= EMIT_LONG) != 0;  // (also publishes s_base / s_rel)
+    const unsigned long long byte0 = s_base.x, row0 = s_base.y;
+    const unsigned long long my_off = byte0 + rel, my_row = row0 + wc + ic - (live ? 1u : 0u);
+    const bool overflow = e.out_text != nullptr && byte0 + tb > e.cap_text;
+
+    if (pend == e.n_pairs && tid == 0) {  // the last block knows the totals
+        e.totals[0] = byte0 + tb;
+        e.totals[1] = row0 + tc;
+        if (e.out_line_off) e.out_line_off[row0 + tc] = byte0 + tb + e.byte_base;
+    }
+    uint32_t r = 0, w = 0;
+    if (live) {
+        const LiftPlan pl = e.plans[blk];
+        const uint32_t k = pl.uniform ? pl.k0 : rank_of_pair(e.pair_off, e.n_rec, p);
+        r = e.rec_order[k];
+        w = e.a.win.pair_win ? e.a.win.pair_win[p] : (e.a.recs[r].wlo + (uint32_t)(p - e.pair_off[k]));
+        if (e.out_line_off) e.out_line_off[my_row] = my_off + e.byte_base;
+        if (e.num.q_st) {
+            e.num.q_st[my_row] = pr.q_st; e.num.q_en[my_row] = pr.q_en; e.num.t_st[my_row] = pr.t_st; e.num.t_en[my_row] = pr.t_en;
+            e.num.nmatch[my_row] = pr.nmatch; e.num.aln_len[my_row] = pr.aln_len;
+            e.num.rec_idx[my_row] = e.orig_idx ? e.orig_idx[r] : r + e.rec_base;
+            e.num.win_idx[my_row] = e.a.win.bed_row ? e.a.win.bed_row[w] : w;
+        }
+        if (e.st.equal) write_stats(e.st, my_row, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
+    }
+    if (e.out_text == nullptr || tb == 0) {
+        if (tid == 0) e.blk_flags[blk] = 0u;
+        return;
+    }
+    if (overflow) {
+        if (tid == 0) { e.blk_flags[blk] = 0u; atomicExch(&e.totals[2], 1ull); }
+        return;
+    }
+    if (!small) {  // a long line in the block: k_serialise's warp-per-line path takes the block's text
+        if (p < pend) { e.line_off[p] = my_off; e.out_idx[p] = my_row; }
+        if (tid == 0) {
+            e.line_off[pend] = byte0 + tb;
+            e.out_idx[pend] = row0 + tc;
+            e.blk_flags[blk] = 1u;
+            atomicAdd(&e.totals[3], 1ull);
+        }
+        return;
+    }
+    if (tid == 0) e.blk_flags[blk] = 0u;
+
+    // ---- compose in rounds of whole lines that fit the staging buffer; each round leaves as one bulk copy ----
+    uint32_t cur_line = 0;
+    while (cur_line < nlines) {  // (block-uniform)
+        const uint32_t cur = s_rel[cur_line];
+        uint8_t* dst = e.out_text + byte0 + cur;
+        const uint32_t shift = (uint32_t)((uintptr_t)dst & 15u);  // keep the shared / global 16-byte phase equal
+        const uint32_t room = (uint32_t)EMIT_CAP - 16u - shift;
+        uint32_t lo = cur_line + 1, hi = nlines;  // largest t in [cur_line + 1, nlines] with s_rel[t] - cur <= room
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (s_rel[mid] - cur <= room) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t end_line = lo;
+        const uint32_t n = s_rel[end_line] - cur;  // (s_rel[nlines] is the block's total: threads past the end hold empty lines)
+        if (live && (uint32_t)tid >= cur_line && (uint32_t)tid < end_line) {
+            const RecInfo& ri = e.a.recs[r];
+            uint8_t* q = s_buf + shift + ((uint32_t)rel - cur);
+            q = put_header(q, e.a, ri, pr, w);
+            q = put_cigar_seq(q, e.a, ri, pr);
+            *q = '\n';
+        }
+        fence_proxy_async();
+        __syncthreads();
+        const uint32_t head = (16u - shift) & 15u;  // bytes until dst is 16-byte aligned
+        const uint32_t hb = head < n ? head : n;
+        const uint32_t nvec = (n - hb) >> 4;
+        if (tid == 0 && nvec) bulk_s2g(dst + hb, s_buf + shift + hb, nvec << 4);
+        for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = s_buf[shift + i];
+        for (uint32_t i = hb + (nvec << 4) + tid; i < n; i += SER_LINES) dst[i] = s_buf[shift + i];
+        cur_line = end_line;
+        if (cur_line < nlines) {  // the buffer is written again: the engine must have read it
+            if (tid == 0 && nvec) bulk_wait_read();
+            __syncthreads();
+        } else if (tid == 0 && nvec) {
+            bulk_wait_read();  // the block's shared memory must outlive the engine's read of it
+        }
     }
 }
 
@@ -1887,7 +2066,7 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
-                      uint32_t group, uint32_t defer_big, cudaStream_t s) {
+                      uint32_t group, uint32_t defer_big, cudaStream_t s, const uint32_t* only_flagged) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1900,7 +2079,30 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
     if (group == 0 || group > (uint32_t)SER_LINES || (SER_LINES % group)) group = SER_LINES;
     k_serialise<<<(unsigned)((n_pairs + group - 1) / group), SER_LINES, SER_CAP, s>>>(
         n_pairs, pair_off, rec_order, n_rec, a, plans, res, line_off, out_idx, out_text, out_line_off, num, st, byte_base, rec_base, orig_idx, group,
-        defer_big);
+        defer_big, only_flagged);
+}
+void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                 const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                 const LiftPlan* plans, const PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
+                 uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
+                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, uint32_t* blk_state, ulonglong2* blk_agg,
+                 ulonglong2* blk_pre, unsigned int* ticket, unsigned long long* totals, cudaStream_t s) {
+    if (n_pairs == 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_CAP);
+        attr_set = true;
+    }
+    OpsView view;
+    view.ops = ops; view.samples = nullptr;
+    EmitArgs e{};
+    e.n_pairs = n_pairs; e.pair_off = pair_off; e.rec_order = rec_order; e.n_rec = n_rec;
+    e.a = SerArgs{recs, view, win, names_off, names, text};
+    e.plans = plans; e.res = res; e.line_len = line_len; e.line_off = line_off; e.out_idx = out_idx; e.blk_flags = blk_flags;
+    e.out_text = out_text; e.cap_text = cap_text; e.out_line_off = out_line_off; e.num = num; e.st = st;
+    e.byte_base = byte_base; e.rec_base = rec_base; e.orig_idx = orig_idx;
+    e.state = blk_state; e.agg = blk_agg; e.pre = blk_pre; e.ticket = ticket; e.totals = totals;
+    k_emit<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_CAP, s>>>(e);
 }
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s) {

@@ -146,7 +146,14 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
-                      uint32_t group, uint32_t defer_big, cudaStream_t s);
+                      uint32_t group, uint32_t defer_big, cudaStream_t s, const uint32_t* only_flagged = nullptr);
+// line scan + serialiser in one pass (k_emit): totals[0..3] = bytes, rows, overflow flag, blocks left to k_serialise
+void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
+                 const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                 const LiftPlan* plans, const PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
+                 uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
+                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, uint32_t* blk_state, ulonglong2* blk_agg,
+                 ulonglong2* blk_pre, unsigned int* ticket, unsigned long long* totals, cudaStream_t s);
 // few, long rows: the long verbatim runs of input text that k_serialise (defer_big = 1) left out, spread over the grid
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s);

@@ -76,6 +76,7 @@ struct rb_ctx {
     std::string err;
     bool profiling = false;
     int lift_mode = RB_LIFT_SEARCH;
+    bool fused_emit = true;       // line scan + serialiser in one kernel (k_emit) where the rows are short; RB_NO_FUSED_EMIT=1 disables
     bool invert = false;          // the call in progress is a --qbed liftover
     std::vector<KEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
@@ -129,6 +130,8 @@ struct rb_batch {
     size_t trim_o[4] = {0, 0, 0, 0};                   // offsets of sel / keys / round state / group offsets inside trim_sel
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
+    DevBuf blk_flags, emit_totals;  // k_emit: per-block "left to k_serialise" flags, {bytes, rows, overflow, deferred blocks}
+    uint64_t row_stride = 0;        // rows between the columns of out_num / out_stats (n_out, or the pair count when k_emit wrote them)
     rb_summary sum{};
     bool have_lift = false, have_stats = false, with_stats = false;
     uint32_t want = 0;
@@ -431,6 +434,7 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
     }
     rb_ctx* ctx = new rb_ctx();
     ctx->device = dev;
+    ctx->fused_emit = getenv("RB_NO_FUSED_EMIT") == nullptr;
     cudaSetDevice(dev);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocMapped) != cudaSuccess ||
@@ -455,7 +459,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
                      &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->trim_qp, &b->trim_wp, &b->trim_views,
-                     &b->trim_sel, &b->trim_out, &b->trim_drop, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats};
+                     &b->trim_sel, &b->trim_out, &b->trim_drop, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats, &b->blk_flags, &b->emit_totals};
     for (DevBuf* d : all) d->release();
     b->stage.release();
     b->wstage.release();
@@ -940,6 +944,69 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
                     b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
                     b->line_len.as<uint32_t>(), err, s);
     }
+    // Short rows (the usual tiling-window call): line scan + serialiser in ONE kernel, k_emit — no per-pair offsets in HBM, no
+    // second pass over the results.  The sizes are known only afterwards, so the text buffer is sized from an estimate (or
+    // kept from the call before); a buffer that turns out too small is grown to the exact size and the kernel runs again.
+    if (ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && b->n_bytes / P <= 1024) {
+        const uint64_t nblk = (P + SER_LINES - 1) / SER_LINES;
+        b->want = want;
+        b->with_stats = with_stats != 0;
+        b->row_stride = P;
+        CU(b->blk_flags.ensure(nblk * 4 + 64));
+        CU(b->emit_totals.ensure(64));
+        CU(b->line_off.ensure((P + 1) * 8 + 64));
+        CU(b->out_idx.ensure((P + 1) * 8 + 64));
+        if (want & RB_WANT_TEXT) {
+            const uint64_t est = b->n_bytes + P * 160 + 4096;
+            if (b->out_text.cap < est + 64) CU(b->out_text.ensure(est + 64));
+            CU(b->out_line_off.ensure((P + 1) * 8 + 64));
+        }
+        if (want & RB_WANT_NUMERIC) CU(b->out_num.ensure(P * (6 * 8 + 2 * 4) + 64));
+        if (with_stats) CU(b->out_stats.ensure(P * 40 + 64));
+        unsigned long long* tot = b->emit_totals.as<unsigned long long>();
+        uint64_t out_bytes = 0, n_out = 0, deferred = 0;
+        for (int attempt = 0;; attempt++) {
+            CU(cudaMemsetAsync(tot, 0, 32, s));
+            {
+                KScope k(ctx, "k_emit");
+                launch_emit(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                            b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
+                            b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(), b->line_len.as<uint32_t>(), b->line_off.as<uint64_t>(),
+                            b->out_idx.as<uint64_t>(), b->blk_flags.as<uint32_t>(),
+                            (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr, (want & RB_WANT_TEXT) ? b->out_text.cap - 64 : 0,
+                            (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
+                            (want & RB_WANT_NUMERIC) ? num_view(b, P) : NumDev{}, with_stats ? stats_view(b, P) : StatsDev{}, b->byte_base,
+                            b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), b->ln_state.as<uint32_t>(),
+                            b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, tot, s);
+            }
+            Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, tot).u64(6, tot + 1).u64(7, tot + 2).u64(8, tot + 3).go(s);
+            CU(cudaStreamSynchronize(s));
+            rc = map_err(ctx, b, hs[0], hs[1]);
+            if (rc != RB_OK) { flush_times(ctx); return rc; }
+            out_bytes = hs[5]; n_out = hs[6]; deferred = hs[8];
+            if (!hs[7]) break;
+            if (attempt) return fail(ctx, RB_ERR_CUDA, "k_emit: the text does not fit a buffer of its own size");
+            CU(b->out_text.ensure(out_bytes + 64));  // exact now
+            CU(cudaMemsetAsync(b->ln_state.p, 0, (nblk + 2) * 4, s));
+            CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));
+        }
+        if (deferred && (want & RB_WANT_TEXT)) {  // blocks holding a line > 2 KB: warp-per-line path of the serialiser
+            KScope k(ctx, "k_serialise");
+            launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
+                             b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
+                             b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(), b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
+                             b->out_text.as<uint8_t>(), b->out_line_off.as<uint64_t>(),
+                             (want & RB_WANT_NUMERIC) ? num_view(b, P) : NumDev{}, with_stats ? stats_view(b, P) : StatsDev{}, b->byte_base,
+                             b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), (uint32_t)SER_LINES, 0u, s,
+                             b->blk_flags.as<uint32_t>());
+        }
+        CU(cudaGetLastError());
+        if (ctx->profiling) { CU(cudaStreamSynchronize(s)); flush_times(ctx); }
+        b->sum.n_ops = n_ops; b->sum.n_pairs = P; b->sum.n_out = n_out; b->sum.out_bytes = out_bytes;
+        b->have_lift = true; b->stats_n = n_out;
+        if (summary) *summary = b->sum;
+        return RB_OK;
+    }
     {
         KScope k(ctx, "k_scan_lines");
         launch_scan_lines(b->line_len.as<uint32_t>(), P, b->line_off.as<uint64_t>(), b->out_idx.as<uint64_t>(),
@@ -952,6 +1019,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     const uint64_t out_bytes = hs[5], n_out = hs[6];
 
     b->want = want;
+    b->row_stride = n_out;
     if (want & RB_WANT_TEXT) {
         CU(b->out_text.ensure(out_bytes + 64));
         CU(b->out_line_off.ensure((n_out + 1) * 8 + 64));
@@ -1054,7 +1122,7 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
     CU(b->line_len.ensure(P * 4 + 64));
     CU(b->line_off.ensure((P + 1) * 8 + 64));
     CU(b->out_idx.ensure((P + 1) * 8 + 64));
-    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    const size_t ln_blocks = P / (size_t)SER_LINES + 4;  // k_emit looks back over blocks of SER_LINES pairs (k_scan_lines needs fewer)
     CU(b->ln_state.ensure(ln_blocks * 4));
     CU(b->ln_agg.ensure(ln_blocks * 16));
     CU(b->ln_pre.ensure(ln_blocks * 16));
@@ -1175,7 +1243,7 @@ int rb_batch_break(rb_ctx* ctx, rb_batch* b, uint32_t max_size, int policy, uint
     CU(b->line_len.ensure(P * 4 + 64));
     CU(b->line_off.ensure((P + 1) * 8 + 64));
     CU(b->out_idx.ensure((P + 1) * 8 + 64));
-    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    const size_t ln_blocks = P / (size_t)SER_LINES + 4;  // k_emit looks back over blocks of SER_LINES pairs (k_scan_lines needs fewer)
     CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
     CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
     CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));  // the line scan reuses the ticket of the break-op scan
@@ -1221,7 +1289,7 @@ static int batch_invert(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_summary* sum
     CU(b->line_off.ensure((P + 1) * 8 + 64));
     CU(b->out_idx.ensure((P + 1) * 8 + 64));
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
-    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    const size_t ln_blocks = P / (size_t)SER_LINES + 4;  // k_emit looks back over blocks of SER_LINES pairs (k_scan_lines needs fewer)
     CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
     CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
     WinView win{};
@@ -1229,11 +1297,11 @@ static int batch_invert(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_summary* sum
     return lift_tail(ctx, b, win, RB_POLICY_RIGHTMOST, TAIL_WHOLE, want, 0, P, n_ops, summary);
 }
 
-static int download_stats(rb_ctx* ctx, rb_batch* b, uint64_t n, rb_stats_out* st) {
+static int download_stats(rb_ctx* ctx, rb_batch* b, uint64_t n, uint64_t stride, rb_stats_out* st) {  // columns are `stride` rows apart on the device
     memset(st, 0, sizeof *st);
     PinnedBlock* blk = pinned_get(ctx, (size_t)n * 40 + 64);
     if (!blk) return fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)(n * 40));
-    if (n) CU(cudaMemcpyAsync(blk->p, b->out_stats.p, (size_t)n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) CU(cudaMemcpy2DAsync(blk->p, (size_t)n * 4, b->out_stats.p, (size_t)stride * 4, (size_t)n * 4, 10, cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t* p = reinterpret_cast<uint32_t*>(blk->p);
     st->n = n;
     st->equal = p; st->diff = p + n; st->ins = p + 2 * n; st->del = p + 3 * n; st->ins_events = p + 4 * n;
@@ -1248,7 +1316,7 @@ int rb_batch_download_stats(rb_ctx* ctx, rb_batch* b, rb_stats_out* st) {
     if (!ctx || !b || !st) return RB_ERR_BAD_ARG;
     if (!b->have_stats) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_stats has not run on this batch");
     cudaSetDevice(ctx->device);
-    const int rc = download_stats(ctx, b, b->n_rec, st);
+    const int rc = download_stats(ctx, b, b->n_rec, b->n_rec, st);
     if (rc != RB_OK) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     return RB_OK;
@@ -1279,14 +1347,18 @@ int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out*
     }
     if (want & RB_WANT_NUMERIC) {
         uint64_t* p = reinterpret_cast<uint64_t*>(base + o_num);
-        if (n) CU(cudaMemcpyAsync(p, b->out_num.p, n * 56, cudaMemcpyDeviceToHost, s));
+        if (n) {
+            const uint64_t stride = b->row_stride ? b->row_stride : n;
+            CU(cudaMemcpy2DAsync(p, n * 8, b->out_num.p, stride * 8, n * 8, 6, cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpy2DAsync(p + 6 * n, n * 4, b->out_num.as<uint64_t>() + 6 * stride, stride * 4, n * 4, 2, cudaMemcpyDeviceToHost, s));
+        }
         out->q_st = p; out->q_en = p + n; out->t_st = p + 2 * n; out->t_en = p + 3 * n; out->nmatch = p + 4 * n;
         out->aln_len = p + 5 * n;
         out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * n);
         out->win_idx = out->rec_idx + n;
     }
     if (st) {
-        const int rc = download_stats(ctx, b, n, st);
+        const int rc = download_stats(ctx, b, n, b->row_stride ? b->row_stride : n, st);
         if (rc != RB_OK) return rc;
     }
     CU(cudaStreamSynchronize(s));
@@ -1582,15 +1654,17 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
             uint64_t* d = reinterpret_cast<uint64_t*>(base + o_num);
             const uint64_t* sp = sb->out_num.as<uint64_t>();
             // one strided copy per table: columns are nk rows apart on the device and cap_rows apart in the pinned block
-            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, nk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
+            const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
+            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, sk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
             uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 6 * cap_rows);
-            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * nk);
-            CUB(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, nk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * sk);
+            CUB(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, sk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
         }
         if (stats && nk) {
             uint32_t* d = reinterpret_cast<uint32_t*>(sblk->p);
             const uint32_t* sp = sb->out_stats.as<uint32_t>();
-            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, nk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
+            const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
+            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, sk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
         }
         CUB(cudaEventRecord(ctx->ev_d2h[k & 1], B));
         TE("B download done", k, B);
@@ -1885,7 +1959,7 @@ int rb_trim_paf_end(rb_ctx* ctx, int remove_contained, uint32_t want, rb_lift_ou
     CU(b->line_off.ensure((P + 1) * 8 + 64));
     CU(b->out_idx.ensure((P + 1) * 8 + 64));
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
-    const size_t ln_blocks = P / ((size_t)LNS_THREADS * 4) + 2;
+    const size_t ln_blocks = P / (size_t)SER_LINES + 4;  // k_emit looks back over blocks of SER_LINES pairs (k_scan_lines needs fewer)
     CU(b->ln_state.ensure(ln_blocks * 4)); CU(b->ln_agg.ensure(ln_blocks * 16)); CU(b->ln_pre.ensure(ln_blocks * 16));
     CU(cudaMemsetAsync(b->ln_state.p, 0, ln_blocks * 4, s));
     WinView win{};

@@ -147,20 +147,13 @@ static bool parse_u64(const char* s, size_t n, uint64_t& out) {  // Rust str::pa
 }
 
 uint32_t Paf::name_id(const std::string& s) {
-    // small tables: linear probe over a sorted vector rebuilt lazily would be overkill; use binary search on index_
-    auto it = std::lower_bound(index_.begin(), index_.end(), s,
-                               [](const std::pair<std::string, uint32_t>& a, const std::string& b) { return a.first < b; });
-    if (it != index_.end() && it->first == s) return it->second;
-    const uint32_t id = (uint32_t)names.size();
-    names.push_back(s);
-    index_.insert(it, {s, id});
-    return id;
+    const auto ins = index_.emplace(s, (uint32_t)names.size());  // O(1) amortised per name
+    if (ins.second) names.push_back(s);
+    return ins.first->second;
 }
 int64_t Paf::find_name(const std::string& s) const {
-    auto it = std::lower_bound(index_.begin(), index_.end(), s,
-                               [](const std::pair<std::string, uint32_t>& a, const std::string& b) { return a.first < b; });
-    if (it != index_.end() && it->first == s) return it->second;
-    return -1;
+    const auto it = index_.find(s);
+    return it == index_.end() ? -1 : (int64_t)it->second;
 }
 
 // paf.rs:62-78 + 379-430: lines() split at '\n' (one trailing '\r' dropped), split_ascii_whitespace,

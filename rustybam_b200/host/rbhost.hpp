@@ -15,6 +15,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "rbcuda.h"
@@ -70,8 +71,7 @@ struct Paf {
     rb_records view();  // finalises the name table and returns the SoA view
 
    private:
-    std::vector<std::pair<std::string, uint32_t>> index_;  // sorted lazily
-    bool index_sorted_ = true;
+    std::unordered_map<std::string, uint32_t> index_;  // name -> id; read-level PAFs intern millions of query names
 };
 
 struct Region {

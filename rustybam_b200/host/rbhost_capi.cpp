@@ -69,6 +69,22 @@ char* rbh_tiling_bed_text(void* pafv, uint64_t width, int64_t tid, size_t* n) {
         if (tid < 0 || paf.find_name(r.name) == tid) sel.push_back(std::move(r));
     return dup_str(bed_text(sel, false), n);
 }
+// `rb stats --paf` rows (bamstats.rs:239-270) of the records of `paf` with the counters st_cols[0..7) (equal diff ins del ins_ev
+// del_ev matches) and identities id_cols[0..3) (by_matches by_events by_all) of rows row0 .. row0 + paf.size()
+char* rbh_stats_text(void* pafv, const uint32_t* const* st_cols, const float* const* id_cols, uint64_t row0, int qbed, int header, size_t* n) {
+    Paf& paf = *static_cast<Paf*>(pafv);
+    rb_stats_out st{};
+    st.n = paf.size();
+    st.equal = const_cast<uint32_t*>(st_cols[0]) + row0; st.diff = const_cast<uint32_t*>(st_cols[1]) + row0;
+    st.ins = const_cast<uint32_t*>(st_cols[2]) + row0; st.del = const_cast<uint32_t*>(st_cols[3]) + row0;
+    st.ins_events = const_cast<uint32_t*>(st_cols[4]) + row0; st.del_events = const_cast<uint32_t*>(st_cols[5]) + row0;
+    st.matches = const_cast<uint32_t*>(st_cols[6]) + row0;
+    st.id_by_matches = const_cast<float*>(id_cols[0]) + row0; st.id_by_events = const_cast<float*>(id_cols[1]) + row0;
+    st.id_by_all = const_cast<float*>(id_cols[2]) + row0;
+    std::string out = header ? stats_header(qbed != 0) : std::string();
+    for (size_t i = 0; i < paf.size(); i++) append_stats_row(out, paf, i, st, qbed != 0);
+    return dup_str(out, n);
+}
 void rbh_free_str(char* p) { free(p); }
 void rbh_fmt_f32(float v, char* buf, size_t cap) {
     std::string s = fmt_f32(v);

@@ -47,6 +47,8 @@ def load():
     lib.rbh_read_all.argtypes = [C.c_char_p, C.POINTER(C.c_size_t)]
     lib.rbh_free_str.argtypes = [C.c_void_p]
     lib.rbh_fmt_f32.argtypes = [C.c_float, C.c_char_p, C.c_size_t]
+    lib.rbh_stats_text.restype = C.c_void_p
+    lib.rbh_stats_text.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     _lib = lib
     return lib
 
@@ -118,6 +120,17 @@ class HostPaf:
 
     def windows_from_bed_text(self, bed: bytes) -> "HostWindows":
         return HostWindows(self.lib.rbh_windows_from_bed_text(self.h, bed, len(bed)))
+
+    def stats_text(self, st: dict, row0=0, qbed=False, header=True) -> bytes:
+        """What `rb stats --paf` prints for these records given the GPU counters `st` (rows row0 .. row0 + n_rec of its arrays)."""
+        import numpy as np
+        cols = [np.ascontiguousarray(st[k], dtype=np.uint32) for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches")]
+        ids = [np.ascontiguousarray(st[k], dtype=np.float32) for k in ("id_by_matches", "id_by_events", "id_by_all")]
+        assert all(len(c) >= row0 + self.n_rec for c in cols + ids)
+        pc = (C.c_void_p * 7)(*[c.ctypes.data for c in cols])
+        pi = (C.c_void_p * 3)(*[c.ctypes.data for c in ids])
+        n = C.c_size_t()
+        return _take(self.lib.rbh_stats_text(self.h, pc, pi, row0, int(qbed), int(header), C.byref(n)), n)
 
     def close(self):
         if self.h:

@@ -125,6 +125,18 @@ def bench_pipeline(paf: bytes, bed: bytes, policy=RIGHTMOST, threads=8):
     return dict(secs_liftover=sl.value, secs_stats=ss.value, rows=rows.value, out_bytes=ob.value)
 
 
+def bench_pipeline_keep(paf: bytes, bed: bytes, policy=RIGHTMOST, threads=8):
+    """bench_pipeline that also returns what `rb liftover` and `rb stats --paf` print (for byte comparisons)."""
+    sl, ss, rows = C.c_double(), C.c_double(), C.c_uint64()
+    lo, ln, so, sn = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+    err = C.create_string_buffer(512)
+    rc = lib().orc_bench_pipeline_keep(paf, C.c_size_t(len(paf)), bed, C.c_size_t(len(bed)), policy, threads, C.byref(sl), C.byref(ss),
+                                       C.byref(rows), C.byref(lo), C.byref(ln), C.byref(so), C.byref(sn), err, C.c_size_t(512))
+    if rc == 101:
+        raise ReferencePanic(err.value.decode())
+    return dict(secs_liftover=sl.value, secs_stats=ss.value, rows=rows.value, lifted=_take(lo, ln), stats=_take(so, sn))
+
+
 def trim_line(line: str, name: str, st: int, en: int, rid: str = "", policy=RIGHTMOST):
     """aligned_pairs + trim_paf_rec_to_rgn on one record line; returns the output line or None."""
     out, n, err = C.c_void_p(), C.c_size_t(), C.create_string_buffer(512)

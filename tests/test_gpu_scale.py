@@ -131,6 +131,96 @@ def test_full_scale_liftover_properties(ctx, full):
     assert n_early < len(first) // 50
 
 
+# ---------------------------------------------------------------- byte parity at the BASELINE sizes
+# The literal oracle needs 24 B per alignment column, so it cannot run the whole ~3.1 Gbp input in seconds — but rows are
+# emitted contig by contig, record-major (liftover.rs:151-164), so the rows of one contig in the FULL-SIZE call are exactly
+# what `rb liftover` prints for that contig's records and windows alone: the GPU rows of a few contigs of the full-scale
+# call are compared byte for byte with the oracle run on those contigs (paf.rs:379-430 parse -> liftover.rs:107-167 ->
+# paf.rs:923-943 print -> bamstats.rs:91-154,225-270).
+PARITY_CONTIGS = ["chr20", "chr21", "chr22", "chrM"]
+
+
+def _rows_of_records(res, rec_lo, rec_hi):
+    """Row range of records [rec_lo, rec_hi) (consecutive in file order, one target): rows are record-major."""
+    idx = res["rec_idx"].astype(np.int64)
+    rows = np.flatnonzero((idx >= rec_lo) & (idx < rec_hi))
+    if len(rows) == 0:
+        return 0, 0
+    assert rows[-1] - rows[0] + 1 == len(rows)  # one contiguous run of rows
+    return int(rows[0]), int(rows[-1]) + 1
+
+
+def _record_runs(paf, tid):
+    """Runs of consecutive records whose target is `tid` (one run per haplotype in a haplotype-major PAF)."""
+    t = np.ctypeslib.as_array(paf.c.t_id, shape=(paf.n_rec,))
+    r = np.flatnonzero(t == tid)
+    cuts = np.flatnonzero(np.diff(r) != 1) + 1
+    return [(int(x[0]), int(x[-1]) + 1) for x in np.split(r, cuts)]
+
+
+@pytest.mark.parametrize("width", [1000, 100_000])  # C4 and C3 at their stated size
+def test_full_scale_liftover_bytes_equal_oracle_on_contigs(ctx, full, width):
+    wins = full.tiling_windows(width)
+    res = ctx.liftover(full, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    off, checked = res["line_off"].astype(np.int64), 0
+    for nm in PARITY_CONTIGS:
+        tid = full.find_name(nm)
+        (lo, hi), = _record_runs(full, tid)
+        want = orc.bench_pipeline_keep(full.text(lo, hi), full.tiling_bed_text(width, tid), threads=os.cpu_count() or 8)
+        r0, r1 = _rows_of_records(res, lo, hi)
+        got = res["paf_text"][off[r0]:off[r1]]
+        assert r1 - r0 == want["rows"] and got == want["lifted"], nm
+        assert hostlib.HostPaf.from_text(got).stats_text(res["stats"], row0=r0) == want["stats"], nm  # fused per-row stats
+        checked += r1 - r0
+    assert checked > (150_000 if width == 1000 else 1_500)
+
+
+def test_full_scale_stats_bytes_equal_oracle_on_contigs(ctx, full):
+    # C2: `rb stats --paf` over the whole synthetic PAF; rows of the parity contigs against the oracle's printout
+    st = ctx.stats(full)
+    for nm in PARITY_CONTIGS:
+        (lo, hi), = _record_runs(full, full.find_name(nm))
+        text = full.text(lo, hi)
+        assert hostlib.HostPaf.from_text(text).stats_text(st, row0=lo) == orc.run_stats(text), nm
+
+
+def test_c5_shape_beyond_4gib_bytes_equal_oracle_on_contigs(ctx):
+    # C5-shaped: 33 haplotypes concatenated haplotype-major (4.4 GB of CIGAR text: byte offsets cross 2^32 in the input and in
+    # the output, slices are gathered in emission order, pinned ranges are split at GiB boundaries), 10 kb windows.
+    # Compared with the oracle: chr21 of the first / a middle / the last haplotype and chrM of every haplotype.
+    n_hap, width = 33, 10_000
+    paf = hostlib.HostPaf.synth(scale=1.0, n_hap=n_hap, threads=os.cpu_count() or 8)
+    assert paf.cigar_nbytes > 1 << 32
+    lib = capi.load()
+    addr = C.cast(paf.c.cigar, C.c_void_p).value
+    pinned = lib.rb_host_register(C.c_void_p(addr), paf.cigar_nbytes) == 0
+    try:
+        wins = paf.tiling_windows(width)
+        res = ctx.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+    finally:
+        if pinned:
+            lib.rb_host_unregister(C.c_void_p(addr))
+    off = res["line_off"].astype(np.int64)
+    assert int(off[-1]) == len(res["paf_text"]) > 1 << 32 and (np.diff(off) > 0).all()
+    checked = 0
+    for nm, haps in (("chr21", (0, n_hap // 2, n_hap - 1)), ("chrM", range(n_hap))):
+        tid = paf.find_name(nm)
+        runs = _record_runs(paf, tid)
+        assert len(runs) == n_hap
+        bed_text = paf.tiling_bed_text(width, tid)
+        for h in haps:
+            lo, hi = runs[h]
+            want = orc.bench_pipeline_keep(paf.text(lo, hi), bed_text, threads=os.cpu_count() or 8)
+            r0, r1 = _rows_of_records(res, lo, hi)
+            got = res["paf_text"][off[r0]:off[r1]]
+            assert r1 - r0 == want["rows"] and got == want["lifted"], (nm, h)
+            assert hostlib.HostPaf.from_text(got).stats_text(res["stats"], row0=r0) == want["stats"], (nm, h)
+            checked += r1 - r0
+    assert checked > 10_000
+    # the last rows of the call (beyond 4 GiB of output text) belong to the last contig in emission order
+    assert int(off[_rows_of_records(res, *_record_runs(paf, paf.find_name("chrM"))[-1])[0]]) > 1 << 32
+
+
 @pytest.mark.parametrize("width", [1000, 10_000, 100_000])
 def test_full_scale_streaming_path_equals_search_path(ctx, full, width):
     """k_scan_lift + k_combine (boundaries resolved while scanning) against k_samples + k_lift (one search per

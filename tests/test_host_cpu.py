@@ -10,7 +10,7 @@ import pytest
 
 import gen
 import orc
-from rustybam_b200 import bamstats, bed, build, capi
+from rustybam_b200 import bamstats, bed, build, capi, hostlib
 from rustybam_b200.paf import Paf, ReferencePanic
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -96,6 +96,23 @@ def test_fmt_f32_matches_oracle():
     vals = (np.float32(100.0) * eq.astype(np.float32)) / np.maximum(tot, 1).astype(np.float32)
     for v in list(vals) + [np.float32("nan"), np.float32(0), np.float32(100), np.float32(1e-7), np.float32(50)]:
         assert bamstats.fmt_f32(v) == orc.fmt_f32(float(v)), v
+    # exact ties between the two shortest candidates round UP in Rust's Display (numpy / printf: to even):
+    # 100 * 2049 / 12800 = 16.0078125 is reachable (2049 '=' bases, 10751 'X' bases)
+    assert bamstats.fmt_f32(np.float32(16.0078125)) == "16.007813" == orc.fmt_f32(16.0078125)
+    for k in range(1, 4000, 7):  # odd multiples of 2^-7 in [16, 32): 8 significant digits, the 9th is an exact 5
+        v = np.float32(16.0 + (2 * k + 1) / 128.0)
+        assert bamstats.fmt_f32(v) == orc.fmt_f32(float(v)), v
+
+
+def test_name_interning_scales():
+    """A read-level PAF interns one name per record: 200 k distinct query names must parse in seconds, not minutes."""
+    import time
+    n = 200_000
+    lines = b"".join(b"q%07d\t100\t0\t10\t+\tchr1\t1000\t0\t10\t10\t10\t60\tcg:Z:10=\n" % (n - i) for i in range(n))
+    t0 = time.time()
+    paf = hostlib.HostPaf.from_text(lines)
+    assert paf.n_rec == n and time.time() - t0 < 20
+    assert paf.find_name("q%07d" % 5) >= 0 and paf.find_name("nope") == -1
 
 
 def _write_bgzf(path, data: bytes, block=60000):
