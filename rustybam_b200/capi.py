@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librbcuda.so")
+LIB_PATH = os.environ.get("RBCUDA_LIB") or os.path.join(HERE, "librbcuda.so")  # (RBCUDA_LIB: tuning builds, tools/variants.sh)
 
 RB_OK = 0
 RB_ERR_NO_DEVICE, RB_ERR_CUDA, RB_ERR_BAD_ARG = -1, -2, -3

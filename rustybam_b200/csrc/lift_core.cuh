@@ -111,6 +111,9 @@ RB_HD uint64_t chunk_of(const OpsView& v, const RecInfo& r, uint32_t p) {
 
 // The reference-consuming op i (len > 0) with T_i <= p < T_i + L_i ; o = p - T_i ; `before` = counters before op i.
 // `live` == false: does nothing (keeps the lane in step with its warp).
+// FAST (k_emit's fused path): the record is known to hold no op of ACC_BIG bases or more (such records are RF_SLOW), so the
+// class sums of a short walk cannot wrap and the exact re-accumulation is compiled out.
+template <bool FAST = false>
 RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, uint64_t& i, uint32_t& o, Ctr& before, ClassAcc& acc) {
     bool found = false;
     Ctr c = ctr_zero();
@@ -159,7 +162,7 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
     }
     RB_CONVERGE();
     if (found) {
-        if (acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
+        if (!FAST && acc.big >= ACC_BIG) {  // a class sum might have wrapped: exact (slow) accumulation
             for (uint32_t t = 0; t < j; t++) ctr_add_op(c, v.op(k0 + t));
         } else {
             acc_flush(acc, c);
@@ -281,6 +284,7 @@ RB_HD bool lift_end(const OpsView& v, uint64_t eo0, uint64_t i, uint32_t o, cons
 
 // FINISH: coordinates, nmatch / aln_len, fused stats and the trimmed CIGAR's byte count from the two ends.
 // L_si = length of op si.  Leaves out.kind == PK_DROP when start column > end column (Q7).
+template <bool FAST = false>
 RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t so, const Ctr& cs, uint32_t L_si, uint64_t ei,
                        uint32_t eo, const Ctr& ce, uint32_t txt_before_ei, PairRes& out) {
     if (cs.A >= ce.A) return;  // start column > end column: window lies inside an indel (Q7)
@@ -310,7 +314,7 @@ RB_HD void lift_finish(const OpsView& v, const RecInfo& r, uint64_t si, uint32_t
         out.mid_off = r.text_off + cs.TXT + first;
         out.cg_bytes = ndigits32(out.s_len) + 1 + out.mid_len + ndigits32(out.e_len) + 1;
     }
-    if (r.flags & RF_SLOW) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
+    if (!FAST && (r.flags & RF_SLOW)) {  // Q15: re-collapse (rare: zero-length or adjacent same-class ops in the input)
         uint32_t bytes = 0, iev = 0, dev = 0;
         merged_walk(v, si, ei, out.s_len, out.e_len, [&](uint32_t len, uint32_t c2) {
             bytes += ndigits32(len) + 1;

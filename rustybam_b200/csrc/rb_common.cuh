@@ -204,7 +204,9 @@ constexpr uint32_t ACC_BIG = 1u << 26;
 // record flags
 enum : uint32_t {
     RF_MINUS = 1u,        // strand '-'
-    RF_SLOW = 2u,         // has zero-length ops or adjacent same-class ops: trimmed rows need the merge walk (Q15)
+    RF_SLOW = 2u,         // has zero-length ops or adjacent same-class ops: trimmed rows need the merge walk (Q15); also set for
+                          // records holding an op of >= 2^26 bases (the walks' class sums could wrap): such records stay on
+                          // the general kernels, the fused fast path never sees them
     RF_STRIPPED = 4u,     // leading/trailing indels were stripped (id gets "_TO.<st>.<en>", paf.rs:726-732)
     RF_CANON = 8u,        // the CIGAR text is canonical (no leading zeros): op k's text starts TXT_prefix(k) bytes into it,
                           // so untouched ops of a trimmed row are copied from the input text instead of being re-formatted

@@ -119,6 +119,37 @@ __device__ __forceinline__ unsigned long long lookback_u64(unsigned long long* s
     return excl;
 }
 
+// The same look-back in two steps, for blocks that have work to do between knowing their aggregate and needing their
+// prefix (k_emit composes its lines in between, which gives the blocks in front time to publish theirs):
+// lb_publish by one lane as early as possible, lb_walk by one full warp when the prefix is needed.
+__device__ __forceinline__ void lb_publish(unsigned long long* state, uint64_t tile, unsigned long long agg) {
+    atomicExch(&state[tile], (tile == 0 ? LB_PRE : LB_AGG) | agg);
+}
+__device__ __forceinline__ unsigned long long lb_walk(unsigned long long* state, uint64_t tile, unsigned long long agg) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) return 0;
+    unsigned long long excl = 0;
+    long long look = (long long)tile - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        unsigned long long s = LB_PRE;  // before tile 0: prefix 0
+        if (idx >= 0) {
+            s = ld_volatile_u64(&state[idx]);
+            while ((s >> 62) == 0) { __nanosleep(64); s = ld_volatile_u64(&state[idx]); }  // (sleeping frees the issue slots)
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        unsigned long long v = (lane <= first) ? (s & LB_VAL) : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        excl += v;
+        if (pm) break;
+        look -= 32;
+    }
+    if (lane == 0) atomicExch(&state[tile], LB_PRE | (excl + agg));
+    return excl;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1  tokeniser
 // ------------------------------------------------------------------------------------------------
@@ -590,7 +621,7 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
             dst[2] = make_uint4(sw[8], sw[9], sw[10], sw[11]);
         }
         const uint32_t code = op_code(w);
-        slowc += (op_len(w) == 0u) | ((!head) & (code == prev_code));
+        slowc += (op_len(w) == 0u) | (op_len(w) >= ACC_BIG) | ((!head) & (code == prev_code));
         acc_add_op(acc, w);
         prev_code = code;
     }
@@ -844,7 +875,7 @@ k_rec_prep(int mode, RecInput in, const uint64_t* __restrict__ op_off, const uin
         const uint64_t base = ((ri.op_end - 1) >> SAMPLE_LOG2) << SAMPLE_LOG2;
         for (uint64_t k = base > ri.op_first ? base : ri.op_first; k < ri.op_end; k++) {
             const uint32_t w = ops[k];
-            if (op_len(w) == 0u || (k > ri.op_first && op_code(w) == op_code(ops[k - 1]))) ri.flags |= RF_SLOW;
+            if (op_len(w) == 0u || op_len(w) >= ACC_BIG || (k > ri.op_first && op_code(w) == op_code(ops[k - 1]))) ri.flags |= RF_SLOW;
         }
     }
     if (mode == 0) {  // rb stats --paf: counters of the record as read (bamstats.rs:91-105)
@@ -1010,14 +1041,15 @@ __device__ __forceinline__ uint32_t rank_of_pair(const uint64_t* __restrict__ pa
 // the prologue of k_lift / k_serialise where a whole block would wait for one thread's chain of dependent loads.
 __global__ void __launch_bounds__(128)
 k_lift_plan(uint64_t n_pairs, uint32_t n_blocks, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order,
-            uint32_t n_rec, const RecInfo* __restrict__ recs, const Ctr* __restrict__ samples, WinView win, LiftPlan* __restrict__ plans) {
+            uint32_t n_rec, const RecInfo* __restrict__ recs, const Ctr* __restrict__ samples, WinView win, LiftPlan* __restrict__ plans,
+            uint32_t mark_fast) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_blocks) return;
     const uint64_t p0 = (uint64_t)b * LIFT_THREADS;
     const uint64_t plast = (p0 + LIFT_THREADS <= n_pairs ? p0 + LIFT_THREADS : n_pairs) - 1;
     LiftPlan pl;
     pl.k0 = rank_of_pair(pair_off, n_rec, p0);
-    pl.uniform = (pl.k0 == rank_of_pair(pair_off, n_rec, plast)) ? 1u : 0u;
+    pl.uniform = (pl.k0 == rank_of_pair(pair_off, n_rec, plast)) ? (uint32_t)PLAN_UNIFORM : 0u;
     pl.c_lo = pl.c_hi = ~0ull;
     if (pl.uniform && win.pair_win == nullptr) {
         const RecInfo& R = recs[rec_order[pl.k0]];
@@ -1030,6 +1062,8 @@ k_lift_plan(uint64_t n_pairs, uint32_t n_blocks, const uint64_t* __restrict__ pa
             const uint64_t en = win.en[R.wlo + (uint32_t)(plast - pbase)];  // end boundary of its last pair
             pl.c_lo = chunk_of(v, R, (uint32_t)((st > t_st ? st : t_st) - t_st));
             pl.c_hi = chunk_of(v, R, (uint32_t)((en < t_en ? en : t_en) - 1 - t_st));
+            // the op run and its samples fit k_emit's staging area and the record needs no special care: k_emit lifts the block
+            if (mark_fast && pl.c_hi >= pl.c_lo && pl.c_hi - pl.c_lo < (uint64_t)LIFT_CCAP && !(R.flags & RF_SLOW)) pl.uniform |= PLAN_FAST;
         }
     }
     plans[b] = pl;
@@ -1140,7 +1174,7 @@ __global__ void __launch_bounds__(LIFT_THREADS, RB_LIFT_MINB)
 k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
        const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
        const uint64_t* __restrict__ names_off, int policy, const LiftPlan* __restrict__ plans, PairRes* __restrict__ res,
-       uint32_t* __restrict__ line_len, ErrSlots err) {
+       uint32_t* __restrict__ line_len, ErrSlots err, uint32_t skip_fast) {
     __shared__ uint32_t s_acc[9 * LIFT_THREADS];
     __shared__ __align__(16) uint32_t s_ops[(LIFT_CCAP + 1) * SAMPLE];
 #if RB_LIFT_STAGE_SMP
@@ -1157,7 +1191,8 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
     OpsView v;
     v.ops = ops; v.samples = samples;
     const LiftPlan pl = plans[blockIdx.x];
-    const bool uniform = pl.uniform != 0;
+    if (skip_fast && (pl.uniform & PLAN_FAST)) return;  // k_emit lifts this block itself (block-uniform)
+    const bool uniform = (pl.uniform & PLAN_UNIFORM) != 0;
     uint32_t r_blk = 0;
     bool staged = false;
     if (uniform) {  // block-uniform: the record and (if it fits) the op run + samples of the block go to shared memory
@@ -1456,7 +1491,6 @@ __device__ __forceinline__ P put_op(P p, uint32_t len, uint32_t code) {
     return p + 1;
 }
 
-constexpr int EMIT_CAP = 30 * 1024;  // k_emit: smem bytes for composing one round of lines
 struct SerArgs {
     const RecInfo* recs;
     OpsView v;
@@ -1531,6 +1565,31 @@ __device__ __forceinline__ P put_text(P p, const uint8_t* __restrict__ src, uint
     return p + n;
 }
 
+// up to 64 bytes of the input CIGAR text -> p: every load is issued before the first store (the byte stores go through a
+// generic pointer, which keeps the compiler from hoisting loads over them: in put_text's loop every load waits for the
+// stores of the word before it), so the line pays one round trip to L2 instead of one per word
+template <class P>
+__device__ __forceinline__ P put_text64(P p, const uint8_t* __restrict__ src, uint32_t n) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t nw = (n + 3u) >> 2;  // output words
+    uint32_t x[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) x[i] = ((uint32_t)i <= nw) ? __ldg(w + i) : 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if ((uint32_t)i * 4u < n) {
+            const uint32_t y = __funnelshift_r(x[i], x[i + 1], sh);
+            const uint32_t b = (uint32_t)i * 4u;
+            p[b] = (uint8_t)y;
+            if (b + 1 < n) p[b + 1] = (uint8_t)(y >> 8);
+            if (b + 2 < n) p[b + 2] = (uint8_t)(y >> 16);
+            if (b + 3 < n) p[b + 3] = (uint8_t)(y >> 24);
+        }
+    }
+    return p + n;
+}
+
 // trimmed / early-return CIGAR text, sequential.  Ops the trim leaves untouched are copied from the input text when
 // the record spells them canonically (RF_CANON) instead of being re-formatted from the op words.
 template <class P>
@@ -1585,7 +1644,7 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
     const bool live = (pr.kind != PK_DROP);
     static_assert(SER_LINES == LIFT_THREADS, "k_serialise reuses the per-block plan of k_lift");
     const LiftPlan pl = plans[p0 / SER_LINES];  // one record for the whole block (the usual case at scale): no per-thread search
-    const bool uniform = pl.uniform != 0;
+    const bool uniform = (pl.uniform & PLAN_UNIFORM) != 0;
     if (live) {
         const uint32_t k = uniform ? pl.k0 : rank_of_pair(pair_off, n_rec, p);
         r = rec_order[k];
@@ -1704,28 +1763,43 @@ k_serialise(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint3
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5'  emit: line scan + serialiser in ONE pass over the pairs
+// K4+K5  k_emit: lift + line scan + serialiser in ONE pass over the pairs
 // ------------------------------------------------------------------------------------------------
-// k_scan_lines + k_serialise fused: a block of SER_LINES consecutive pairs (dynamic ticket order) scans its line sizes,
-// gets the byte / row offset of its first line by decoupled look-back over the blocks in front of it (16-byte payload),
-// writes the stats rows / numeric mirror / line offsets of its rows and composes its lines in shared memory in rounds of
-// <= EMIT_CAP bytes, each leaving as one bulk shared->global copy.  Nothing per pair goes back to HBM in between: no
-// line_off / out_idx arrays, no second read of the results.  The output sizes are only known when the kernel ends, so the
-// caller hands in the capacity of its text buffer: a block whose lines would not fit writes no text and raises the
-// overflow flag (the caller grows the buffer to the exact size — the totals are right either way — and runs the kernel
-// again; steady-state calls reuse the buffer of the call before).  Blocks holding a line longer than EMIT_LONG bytes are
-// left to k_serialise's warp-per-line path: they publish their offsets (line_off / out_idx of their pairs) and a flag.
+// A block owns SER_LINES consecutive pairs (dynamic ticket order).
+//   FAST blocks (k_lift_plan: one record, op run + samples fit the staging area, no RF_SLOW, right-most policy) lift their
+//   pairs right here, out of shared memory (same stages as k_lift, lift_core.cuh) — their results never exist in HBM.
+//   Other blocks read the PairRes / line size k_lift left for them.
+// Then: block scan of (bytes, rows); two single-word decoupled look-backs (warp 0: bytes, warp 1: rows) give the block's
+// place in the output WHILE the other warps already compose their lines in shared memory (the 12 columns come from
+// block-constant fragments, untouched ops are formatted from the staged op words: no global load on that path); the lines
+// leave with 16-byte stores, re-aligned from the staging buffer with funnel shifts (the block's byte offset is not known
+// when composing starts, so shared and global memory are in different 16-byte phases).  Rows that do not fit one buffer
+// go in rounds.  No line_off / out_idx / PairRes arrays, no second pass.
+// The output sizes are only known when the kernel ends, so the caller hands in the capacity of its text buffer: a block
+// whose lines would not fit writes no text and raises the overflow flag (the caller grows the buffer to the exact size —
+// the totals are right either way — and runs the kernel again; steady-state calls reuse the buffer of the call before).
+// Blocks holding a line longer than EMIT_LONG bytes are left to k_serialise's warp-per-line path: they publish their
+// results, offsets (line_off / out_idx of their pairs) and a flag.
 constexpr uint32_t EMIT_LONG = 2048;
+constexpr int EMIT_OPS_BYTES = (LIFT_CCAP + 1) * (int)SAMPLE * 4;                 // staged op words of a FAST block
+constexpr int EMIT_SMP_BYTES = (LIFT_CCAP + 2) * (int)SUBS * (int)sizeof(Ctr);    // ... and its samples
+constexpr int EMIT_ACC_BYTES = 9 * SER_LINES * 4;                                 // class sums of the walks
+constexpr int EMIT_UNI_BYTES = EMIT_SMP_BYTES + EMIT_ACC_BYTES;                   // after the lift: line buffer of a FAST block
+constexpr int EMIT_DYN_BYTES = EMIT_OPS_BYTES + EMIT_UNI_BYTES;                   // (other blocks compose in all of it)
+constexpr uint32_t FRAG_CAP = 96, FRAG_NAME_MAX = 64;
+static_assert(EMIT_OPS_BYTES % 16 == 0 && EMIT_SMP_BYTES % 16 == 0, "staging areas are 16-byte aligned");
+static_assert(EMIT_UNI_BYTES >= (int)EMIT_LONG + 64, "one round holds at least one line");
+
 struct EmitArgs {
     uint64_t n_pairs;
     const uint64_t* pair_off;
     const uint32_t* rec_order;
     uint32_t n_rec;
-    SerArgs a;
+    SerArgs a;            // a.v.samples is set: FAST blocks lift
     const LiftPlan* plans;
-    const PairRes* res;
+    PairRes* res;         // read by the blocks k_lift handled; written by FAST blocks that have to defer
     const uint32_t* line_len;
-    uint64_t* line_off;  // written for deferred blocks only
+    uint64_t* line_off;   // written for deferred blocks only
     uint64_t* out_idx;
     uint32_t* blk_flags;  // per block: 1 = its text is left to k_serialise
     uint8_t* out_text;
@@ -1736,20 +1810,130 @@ struct EmitArgs {
     uint64_t byte_base;
     uint32_t rec_base;
     const uint32_t* orig_idx;
-    uint32_t* state;
-    ulonglong2* agg;
-    ulonglong2* pre;
+    unsigned long long* lb_bytes;  // look-back words (one per block), zeroed by the caller
+    unsigned long long* lb_rows;
     unsigned int* ticket;
     unsigned long long* totals;  // [0] bytes of text, [1] rows, [2] != 0: the text did not fit, [3] deferred blocks
+    ErrSlots err;
 };
 
-__global__ void __launch_bounds__(SER_LINES, 7)
+// n bytes from a 4-byte aligned shared-memory fragment
+__device__ __forceinline__ uint8_t* put_frag(uint8_t* p, const uint8_t* frag, uint32_t n) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(frag);
+    uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t x = w[i >> 2];
+        p[i] = (uint8_t)x; p[i + 1] = (uint8_t)(x >> 8); p[i + 2] = (uint8_t)(x >> 16); p[i + 3] = (uint8_t)(x >> 24);
+    }
+    if (i < n) {
+        const uint32_t x = w[i >> 2];
+        p[i] = (uint8_t)x;
+        if (i + 1 < n) p[i + 1] = (uint8_t)(x >> 8);
+        if (i + 2 < n) p[i + 2] = (uint8_t)(x >> 16);
+    }
+    return p + n;
+}
+
+// n bytes of shared memory (any alignment) -> global memory: 16-byte stores where the destination allows, source words
+// re-aligned with funnel shifts.  Executed by the whole block.
+__device__ __forceinline__ void copy_out_shifted(uint8_t* __restrict__ dst, const uint8_t* sbuf, uint32_t n) {
+    const int tid = threadIdx.x;
+    const uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    const uint32_t hb = head < n ? head : n;
+    const uint32_t nvec = (n - hb) >> 4;
+    for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = sbuf[i];
+    const uint8_t* sb = sbuf + hb;
+    const uint32_t sa = smem_u32(sb);
+    const uint32_t sh = (sa & 3u) * 8u;
+    const uint32_t* w0 = reinterpret_cast<const uint32_t*>(sb - (sa & 3u));  // (over-reads <= 7 bytes behind the data: inside the buffer's slack)
+    uint4* d4 = reinterpret_cast<uint4*>(dst + hb);
+    for (uint32_t v = tid; v < nvec; v += SER_LINES) {
+        const uint32_t* w = w0 + (size_t)v * 4;
+        const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3], a4 = w[4];
+        uint4 x;
+        x.x = __funnelshift_r(a0, a1, sh); x.y = __funnelshift_r(a1, a2, sh); x.z = __funnelshift_r(a2, a3, sh); x.w = __funnelshift_r(a3, a4, sh);
+        d4[v] = x;
+    }
+    for (uint32_t i = hb + (nvec << 4) + tid; i < n; i += SER_LINES) dst[i] = sbuf[i];
+}
+
+// lift_pair_chain of k_lift, specialised for FAST blocks (everything in shared memory, right-most policy, no RF_SLOW)
+__device__ __forceinline__ uint32_t lift_pair_fast(const OpsView& v, const RecInfo& r, uint64_t w_st, uint64_t w_en, bool enabled,
+                                                   PairRes& out, ClassAcc& acc, ChainSlot* s_x) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t status = LIFT_OK;
+    bool live = enabled;
+    pair_clear(out);
+    if (live && r.t_st > w_st && r.t_en < w_en) {
+        pair_early(r, out);
+        live = false;
+    } else if (live && r.t_en <= r.t_st) {
+        status = LIFT_ERR_NOT_FOUND;
+        live = false;
+    }
+    const uint32_t ps = live ? (uint32_t)((w_st > r.t_st ? w_st : r.t_st) - r.t_st) : 0u;
+    const uint32_t pe = live ? (uint32_t)((w_en < r.t_en ? w_en : r.t_en) - 1 - r.t_st) : 0u;
+    uint64_t ie = 0; uint32_t oe = 0; Ctr be = ctr_zero();
+    const bool fe = find_op<true>(v, r, live, pe, ie, oe, be, acc);
+    // hand (ie, oe, be) to the right neighbour (tiling windows: its start boundary is one base further)
+    const uint32_t ok = (live && fe) ? 1u : 0u;
+    if (lane == 31) {
+        ChainSlot& x = s_x[warp];
+        x.i = ie; x.o = oe; x.pe = pe; x.ok = ok; x.c = be;
+    }
+    __syncthreads();
+    uint32_t p_ok = __shfl_up_sync(FULL, ok, 1), p_pe = __shfl_up_sync(FULL, pe, 1);
+    uint32_t po = __shfl_up_sync(FULL, oe, 1);
+    uint64_t pi = __shfl_up_sync(FULL, ie, 1);
+    Ctr pb;
+    {
+        uint32_t* dw = reinterpret_cast<uint32_t*>(&pb);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(&be);
+#pragma unroll
+        for (int t = 0; t < 12; t++) dw[t] = __shfl_up_sync(FULL, sw[t], 1);
+    }
+    if (lane == 0) {
+        p_ok = 0u;
+        if (warp > 0) {
+            const ChainSlot& x = s_x[warp - 1];
+            p_ok = x.ok; p_pe = x.pe; po = x.o; pi = x.i; pb = x.c;
+        }
+    }
+    const bool derive = live && p_ok && ps == p_pe + 1u;
+    uint64_t i = 0; uint32_t o = 0; Ctr before = ctr_zero();
+    bool fs = false;
+    const bool search = live && !derive;
+    if (__any_sync(FULL, search)) fs = find_op<true>(v, r, search, ps, i, o, before, acc);
+    if (derive) fs = advance_one(v, r, pi, po, pb, i, o, before);
+    __syncwarp();
+    if (!fs && live) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    uint64_t si = 0; uint32_t so = 0; Ctr cs = ctr_zero();
+    if (live && !lift_start(v, r.eo1, r.a_lead, r.tot.A, POLICY_RIGHTMOST, i, o, before, si, so, cs)) live = false;
+    __syncwarp();
+    if (live && !fe) { status = LIFT_ERR_NOT_FOUND; live = false; }
+    if (live) {
+        uint64_t ei; uint32_t eo; Ctr ce; uint32_t txt_before_ei;
+        if (lift_end(v, r.eo0, ie, oe, be, ei, eo, ce, txt_before_ei))
+            lift_finish<true>(v, r, si, so, cs, op_len(v.op(si)), ei, eo, ce, txt_before_ei, out);
+    }
+    __syncwarp();
+    return status;
+}
+
+__global__ void __launch_bounds__(SER_LINES, RB_EMIT_MINB)
 k_emit(const __grid_constant__ EmitArgs e) {
-    extern __shared__ __align__(16) uint8_t s_buf[];
+    extern __shared__ __align__(16) uint8_t s_emit[];
     __shared__ uint32_t s_rel[SER_LINES + 1];
-    __shared__ ulonglong2 s_warp[SER_LINES / 32];
-    __shared__ ulonglong2 s_base;
+    __shared__ unsigned long long s_wb[SER_LINES / 32];
+    __shared__ uint32_t s_wc[SER_LINES / 32];
+    __shared__ unsigned long long s_base[2];
     __shared__ unsigned int s_blk;
+    __shared__ __align__(16) RecInfo s_rec;
+    __shared__ __align__(16) ChainSlot s_chain[SER_LINES / 32];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(16) uint8_t s_frag[4][FRAG_CAP];
+    __shared__ uint32_t s_flen[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_blk = atomicAdd(e.ticket, 1u);
     __syncthreads();
@@ -1759,17 +1943,102 @@ k_emit(const __grid_constant__ EmitArgs e) {
     const uint64_t p = p0 + tid;
     const uint64_t pend = (p0 + SER_LINES < e.n_pairs) ? (p0 + SER_LINES) : e.n_pairs;
     const uint32_t nlines = (uint32_t)(pend - p0);
+    const LiftPlan pl = e.plans[blk];
+    const bool fast = (pl.uniform & PLAN_FAST) != 0;  // block-uniform
+    const bool in_range = p < pend;
 
     PairRes pr;
     pr.kind = PK_DROP;
-    uint32_t len = 0;
-    if (p < pend) {
-        len = e.line_len[p];
-        if (len) pr = e.res[p];
+    uint32_t len = 0, r = 0, w = 0;
+    uint64_t w_st = 0, w_en = 0;
+    OpsView v = e.a.v;
+    uint8_t* s_buf;       // line buffer of this block
+    uint32_t buf_cap;
+    if (fast) {
+        // ---- stage the block's op run + samples (bulk-copy engine), the record, the header fragments; lift ----
+        uint32_t* s_ops = reinterpret_cast<uint32_t*>(s_emit);
+        Ctr* s_smp = reinterpret_cast<Ctr*>(s_emit + EMIT_OPS_BYTES);
+        uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_emit + EMIT_OPS_BYTES + EMIT_SMP_BYTES);
+        r = e.rec_order[pl.k0];
+        const RecInfo* gr = &e.a.recs[r];
+        if (tid < (int)(sizeof(RecInfo) / 16)) reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(gr)[tid];
+        const uint64_t c_lo = pl.c_lo, c_hi = pl.c_hi;
+        const uint64_t op_end = gr->op_end;
+        const uint64_t o_lo = c_lo << SAMPLE_LOG2;
+        uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
+        if (o_hi > op_end) o_hi = op_end;
+        const uint32_t n_stage = (uint32_t)(o_hi - o_lo), n4 = n_stage >> 2;
+        const uint64_t c_max = (op_end - 1) >> SAMPLE_LOG2;
+        const uint64_t c_top = (c_hi + 1 <= c_max) ? c_hi + 1 : c_max;
+        const uint32_t smp_bytes = (uint32_t)((c_top - c_lo + 1) * SUBS * sizeof(Ctr));
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, n4 * 16u + smp_bytes);
+            if (n4) bulk_g2s(s_ops, v.ops + o_lo, n4 * 16u, &s_bar);
+            bulk_g2s(s_smp, v.samples + c_lo * SUBS, smp_bytes, &s_bar);
+        }
+        for (uint32_t k = (n4 << 2) + tid; k < n_stage; k += SER_LINES) s_ops[k] = v.ops[o_lo + k];  // the (< 4 op) tail
+        v.s_smp = s_smp; v.sc_lo = c_lo; v.sc_hi = c_top + 1;
+        v.s_ops = s_ops; v.so_lo = o_lo; v.so_hi = o_hi;
+        const uint64_t pc = in_range ? p : e.n_pairs - 1;
+        w = gr->wlo + (uint32_t)(pc - e.pair_off[pl.k0]);
+        w_st = e.a.win.st[w]; w_en = e.a.win.en[w];
+        if (warp == 3 && lane < 4) {  // block-constant pieces of the 12 columns (paf.rs:923-943), one lane each
+            const uint32_t qn = gr->q_name, tn = gr->t_name;
+            const uint64_t qo = e.a.names_off[qn], to = e.a.names_off[tn];
+            const uint32_t ql = (uint32_t)(e.a.names_off[qn + 1] - qo), tl = (uint32_t)(e.a.names_off[tn + 1] - to);
+            uint8_t* f = s_frag[lane];
+            uint8_t* q = f;
+            if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX) {
+                if (lane == 0) {         // q_name \t q_len \t
+                    q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
+                } else if (lane == 1) {  // \t strand \t t_name \t t_len \t
+                    *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
+                    q = put_bytes(q, e.a.names + to, tl); *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t';
+                } else if (lane == 2) {  // \t mapq \t id:Z:
+                    *q++ = '\t'; q = put_u64(q, gr->mapq);
+                    *q++ = '\t'; *q++ = 'i'; *q++ = 'd'; *q++ = ':'; *q++ = 'Z'; *q++ = ':';
+                } else {                 // default window id: t_name :
+                    q = put_bytes(q, e.a.names + to, tl); *q++ = ':';
+                }
+                s_flen[lane] = (uint32_t)(q - f);
+            } else {
+                s_flen[lane] = 0xFFFFFFFFu;  // long names: the generic header writer
+            }
+        }
+        __syncthreads();  // s_rec, the tail ops, the fragments and the mbarrier's initialisation are visible
+        mbar_wait(&s_bar, 0);
+        const RecInfo& ri = s_rec;
+        ClassAcc acc;
+        acc.sum = s_acc + tid; acc.stride = SER_LINES;
+        const bool overlaps = in_range && ri.t_en > w_st && ri.t_st < w_en && !(e.a.win.from_record && w_en <= w_st);
+        const uint32_t st = lift_pair_fast(v, ri, w_st, w_en, overlaps, pr, acc, s_chain);
+        if (in_range && st != LIFT_OK) { report(e.err.rec, r, RE_INDEX_PANIC); pr.kind = PK_DROP; }
+        if (!in_range) pr.kind = PK_DROP;
+        if (pr.kind != PK_DROP) {
+            uint32_t idl = ri.id_len;  // early rows and break-paf pieces carry their record's id
+            if (pr.kind != PK_EARLY && !e.a.win.from_record) {
+                const uint32_t tn = e.a.win.ids_off ? 0u : (uint32_t)(e.a.names_off[ri.t_name + 1] - e.a.names_off[ri.t_name]);
+                idl = win_id_len(e.a.win, w, tn, w_st, w_en);
+            }
+            len = ri.line_const + line_var_bytes(pr, idl);
+        }
+        // the op words stay staged for the serialiser; samples + class sums make room for the lines
+        v.s_smp = nullptr; v.sc_lo = v.sc_hi = 0;
+        s_buf = s_emit + EMIT_OPS_BYTES;
+        buf_cap = (uint32_t)EMIT_UNI_BYTES;
+        __syncthreads();
+    } else {
+        if (in_range) {
+            len = e.line_len[p];
+            if (len) pr = e.res[p];
+        }
+        s_buf = s_emit;
+        buf_cap = (uint32_t)EMIT_DYN_BYTES;
     }
     const bool live = len != 0u;
 
-    // ---- block scan of (bytes, rows), look-back for the block's base ----
+    // ---- block scan of (bytes, rows) ----
     unsigned long long ib = len;
     uint32_t ic = live ? 1u : 0u;
 #pragma unroll
@@ -1778,38 +2047,111 @@ k_emit(const __grid_constant__ EmitArgs e) {
         const uint32_t uc = __shfl_up_sync(0xffffffffu, ic, d);
         if (lane >= d) { ib += ub; ic += uc; }
     }
-    if (lane == 31) s_warp[warp] = make_ulonglong2(ib, ic);
-    __syncthreads();
-    unsigned long long wb = 0, wc = 0, tb = 0, tc = 0;
+    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
+    const bool small = __syncthreads_and(len <= EMIT_LONG) != 0;
+    unsigned long long wb = 0, tb = 0;
+    uint32_t wc = 0, tc = 0;
 #pragma unroll
     for (int k = 0; k < SER_LINES / 32; k++) {
-        const ulonglong2 t = s_warp[k];
-        if (k < warp) { wb += t.x; wc += t.y; }
-        tb += t.x; tc += t.y;
-    }
-    if (warp == 0) {
-        const ulonglong2 ex = lookback_2u64(e.state, e.agg, e.pre, blk, make_ulonglong2(tb, tc));
-        if (lane == 0) s_base = ex;
+        if (k < warp) { wb += s_wb[k]; wc += s_wc[k]; }
+        tb += s_wb[k]; tc += s_wc[k];
     }
     const unsigned long long rel = wb + ib - len;  // bytes of the block's lines in front of mine
     s_rel[tid] = (uint32_t)rel;
     if (tid == 0) s_rel[SER_LINES] = (uint32_t)tb;
-    const bool small = __syncthreads_and(len <= EMIT_LONG) != 0;  // (also publishes s_base / s_rel)
-    const unsigned long long byte0 = s_base.x, row0 = s_base.y;
+
+    if (!live) { r = 0; w = 0; }
+    else if (!fast) {
+        const uint32_t k = (pl.uniform & PLAN_UNIFORM) ? pl.k0 : rank_of_pair(e.pair_off, e.n_rec, p);
+        r = e.rec_order[k];
+        w = e.a.win.pair_win ? e.a.win.pair_win[p] : (e.a.recs[r].wlo + (uint32_t)(p - e.pair_off[k]));
+    }
+    const bool want_text = e.out_text != nullptr && tb != 0;
+    const bool compose_early = want_text && small;  // (block-uniform)
+
+    // one line into the staging buffer at `q` — FAST blocks: fragments + staged ops, no global loads
+    auto compose = [&](uint8_t* q) {
+        const RecInfo& ri = fast ? s_rec : e.a.recs[r];
+        if (fast && s_flen[0] != 0xFFFFFFFFu) {
+            q = put_frag(q, s_frag[0], s_flen[0]);
+            q = put_u64(q, pr.q_st); *q++ = '\t'; q = put_u64(q, pr.q_en);
+            q = put_frag(q, s_frag[1], s_flen[1]);
+            q = put_u64(q, pr.t_st); *q++ = '\t'; q = put_u64(q, pr.t_en);
+            *q++ = '\t'; q = put_u32(q, pr.nmatch);
+            *q++ = '\t'; q = put_u32(q, pr.aln_len);
+            q = put_frag(q, s_frag[2], s_flen[2]);
+            if (pr.kind == PK_EARLY || e.a.win.from_record) {
+                if (ri.flags & RF_STRIPPED) q = put_strip_id(q, ri, v);
+            } else if (e.a.win.ids_off) {
+                q = put_bytes(q, e.a.win.ids + e.a.win.ids_off[w], (uint32_t)(e.a.win.ids_off[w + 1] - e.a.win.ids_off[w]));
+            } else {  // bed.rs:150-153: "{chrom}:{st+1}-{en}"
+                q = put_frag(q, s_frag[3], s_flen[3]);
+                q = put_u64(q, w_st + 1); *q++ = '-'; q = put_u64(q, w_en);
+            }
+            *q++ = '\t'; *q++ = 'c'; *q++ = 'g'; *q++ = ':'; *q++ = 'Z'; *q++ = ':';
+        } else {
+            q = put_header(q, e.a, ri, pr, w);
+        }
+        const uint32_t* run = (fast && pr.kind == PK_TRIM) ? v.op_run(pr.si, (uint32_t)(pr.ei - pr.si + 1)) : nullptr;
+        if (run) {  // the trimmed op range is staged (no RF_SLOW here)
+            const uint32_t n_mid = (uint32_t)(pr.ei - pr.si);
+            q = put_op(q, pr.s_len, op_code(run[0]));
+            if (n_mid) {
+#if RB_EMIT_MID_TEXT
+                if ((ri.flags & RF_CANON) && pr.mid_len <= 64u) {  // untouched ops: their bytes of the input text, loads up front
+                    q = put_text64(q, e.a.text + pr.mid_off, pr.mid_len);
+                } else
+#endif
+                {   // ... or formatted from the staged op words
+                    for (uint32_t k = 1; k < n_mid; k++) q = put_op(q, op_len(run[k]), op_code(run[k]));
+                }
+                q = put_op(q, pr.e_len, op_code(run[n_mid]));
+            }
+        } else {
+            SerArgs a2 = e.a;
+            a2.v = v;
+            q = put_cigar_seq(q, a2, ri, pr);
+        }
+        *q = '\n';
+    };
+    // lines [cur_line, end_line) fit the buffer (whole lines; 8 bytes of slack on either side for the re-aligning copy)
+    auto round_end = [&](uint32_t cur_line) {
+        const uint32_t cur = s_rel[cur_line];
+        uint32_t lo = cur_line + 1, hi = nlines;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi + 1) >> 1;
+            if (s_rel[mid] - cur <= buf_cap - 32u) lo = mid; else hi = mid - 1;
+        }
+        return lo;  // (s_rel[nlines] is the block's total: threads past the end hold empty lines)
+    };
+    __syncthreads();  // s_rel
+    uint32_t cur_line = 0, end_line = 0;
+    // the block's aggregates are published right away; its first round of lines is composed BEFORE it asks where they go,
+    // so the blocks in front have that long to publish theirs (a block cannot leave before every block in front of it has
+    // finished lifting: this is what keeps the wait short)
+    if (tid == 0) lb_publish(e.lb_bytes, blk, tb);
+    if (tid == 32) lb_publish(e.lb_rows, blk, (unsigned long long)tc);
+    if (compose_early) {
+        end_line = round_end(0);
+        if (live && (uint32_t)tid < end_line) compose(s_buf + 16 + (uint32_t)rel);
+    }
+    if (warp == 0) {
+        const unsigned long long ex = lb_walk(e.lb_bytes, blk, tb);
+        if (lane == 0) s_base[0] = ex;
+    } else if (warp == 1) {
+        const unsigned long long ex = lb_walk(e.lb_rows, blk, (unsigned long long)tc);
+        if (lane == 0) s_base[1] = ex;
+    }
+    __syncthreads();
+    const unsigned long long byte0 = s_base[0], row0 = s_base[1];
     const unsigned long long my_off = byte0 + rel, my_row = row0 + wc + ic - (live ? 1u : 0u);
-    const bool overflow = e.out_text != nullptr && byte0 + tb > e.cap_text;
 
     if (pend == e.n_pairs && tid == 0) {  // the last block knows the totals
         e.totals[0] = byte0 + tb;
         e.totals[1] = row0 + tc;
         if (e.out_line_off) e.out_line_off[row0 + tc] = byte0 + tb + e.byte_base;
     }
-    uint32_t r = 0, w = 0;
     if (live) {
-        const LiftPlan pl = e.plans[blk];
-        const uint32_t k = pl.uniform ? pl.k0 : rank_of_pair(e.pair_off, e.n_rec, p);
-        r = e.rec_order[k];
-        w = e.a.win.pair_win ? e.a.win.pair_win[p] : (e.a.recs[r].wlo + (uint32_t)(p - e.pair_off[k]));
         if (e.out_line_off) e.out_line_off[my_row] = my_off + e.byte_base;
         if (e.num.q_st) {
             e.num.q_st[my_row] = pr.q_st; e.num.q_en[my_row] = pr.q_en; e.num.t_st[my_row] = pr.t_st; e.num.t_en[my_row] = pr.t_en;
@@ -1819,16 +2161,19 @@ k_emit(const __grid_constant__ EmitArgs e) {
         }
         if (e.st.equal) write_stats(e.st, my_row, pr.equal, pr.diff, pr.ins, pr.del, pr.ins_ev, pr.del_ev, pr.matches);
     }
-    if (e.out_text == nullptr || tb == 0) {
+    if (!want_text) {
         if (tid == 0) e.blk_flags[blk] = 0u;
         return;
     }
-    if (overflow) {
+    if (byte0 + tb > e.cap_text) {  // does not fit: totals only, the caller grows the buffer and runs again
         if (tid == 0) { e.blk_flags[blk] = 0u; atomicExch(&e.totals[2], 1ull); }
         return;
     }
     if (!small) {  // a long line in the block: k_serialise's warp-per-line path takes the block's text
-        if (p < pend) { e.line_off[p] = my_off; e.out_idx[p] = my_row; }
+        if (in_range) {
+            if (fast) e.res[p] = pr;
+            e.line_off[p] = my_off; e.out_idx[p] = my_row;
+        }
         if (tid == 0) {
             e.line_off[pend] = byte0 + tb;
             e.out_idx[pend] = row0 + tc;
@@ -1838,43 +2183,15 @@ k_emit(const __grid_constant__ EmitArgs e) {
         return;
     }
     if (tid == 0) e.blk_flags[blk] = 0u;
-
-    // ---- compose in rounds of whole lines that fit the staging buffer; each round leaves as one bulk copy ----
-    uint32_t cur_line = 0;
-    while (cur_line < nlines) {  // (block-uniform)
+    for (;;) {  // (block-uniform)
         const uint32_t cur = s_rel[cur_line];
-        uint8_t* dst = e.out_text + byte0 + cur;
-        const uint32_t shift = (uint32_t)((uintptr_t)dst & 15u);  // keep the shared / global 16-byte phase equal
-        const uint32_t room = (uint32_t)EMIT_CAP - 16u - shift;
-        uint32_t lo = cur_line + 1, hi = nlines;  // largest t in [cur_line + 1, nlines] with s_rel[t] - cur <= room
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi + 1) >> 1;
-            if (s_rel[mid] - cur <= room) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t end_line = lo;
-        const uint32_t n = s_rel[end_line] - cur;  // (s_rel[nlines] is the block's total: threads past the end hold empty lines)
-        if (live && (uint32_t)tid >= cur_line && (uint32_t)tid < end_line) {
-            const RecInfo& ri = e.a.recs[r];
-            uint8_t* q = s_buf + shift + ((uint32_t)rel - cur);
-            q = put_header(q, e.a, ri, pr, w);
-            q = put_cigar_seq(q, e.a, ri, pr);
-            *q = '\n';
-        }
-        fence_proxy_async();
-        __syncthreads();
-        const uint32_t head = (16u - shift) & 15u;  // bytes until dst is 16-byte aligned
-        const uint32_t hb = head < n ? head : n;
-        const uint32_t nvec = (n - hb) >> 4;
-        if (tid == 0 && nvec) bulk_s2g(dst + hb, s_buf + shift + hb, nvec << 4);
-        for (uint32_t i = tid; i < hb; i += SER_LINES) dst[i] = s_buf[shift + i];
-        for (uint32_t i = hb + (nvec << 4) + tid; i < n; i += SER_LINES) dst[i] = s_buf[shift + i];
+        copy_out_shifted(e.out_text + byte0 + cur, s_buf + 16, s_rel[end_line] - cur);
         cur_line = end_line;
-        if (cur_line < nlines) {  // the buffer is written again: the engine must have read it
-            if (tid == 0 && nvec) bulk_wait_read();
-            __syncthreads();
-        } else if (tid == 0 && nvec) {
-            bulk_wait_read();  // the block's shared memory must outlive the engine's read of it
-        }
+        if (cur_line >= nlines) break;
+        __syncthreads();  // the buffer is written again
+        end_line = round_end(cur_line);
+        if (live && (uint32_t)tid >= cur_line && (uint32_t)tid < end_line) compose(s_buf + 16 + ((uint32_t)rel - s_rel[cur_line]));
+        __syncthreads();
     }
 }
 
@@ -2042,17 +2359,17 @@ void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint3
     k_pair_scan<<<1, 1024, 0, s>>>(pair_cnt, rec_order, n_rec, pair_off);
 }
 void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s) {
+                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s, bool mark_fast) {
     if (n_pairs == 0) return;
     const uint32_t nb = (uint32_t)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS);
-    k_lift_plan<<<(nb + 127) / 128, 128, 0, s>>>(n_pairs, nb, pair_off, rec_order, n_rec, recs, samples, win, plans);
+    k_lift_plan<<<(nb + 127) / 128, 128, 0, s>>>(n_pairs, nb, pair_off, rec_order, n_rec, recs, samples, win, plans, mark_fast ? 1u : 0u);
 }
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                  const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
-                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s) {
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast) {
     if (n_pairs == 0) return;
     k_lift<<<(unsigned)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS), LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
-                                                             policy, plans, res, line_len, err);
+                                                             policy, plans, res, line_len, err, skip_fast ? 1u : 0u);
 }
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s) {
@@ -2082,27 +2399,27 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
         defer_big, only_flagged);
 }
 void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                 const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
-                 const LiftPlan* plans, const PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
+                 const uint32_t* ops, const Ctr* samples, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                 const LiftPlan* plans, PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
                  uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
-                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, uint32_t* blk_state, ulonglong2* blk_agg,
-                 ulonglong2* blk_pre, unsigned int* ticket, unsigned long long* totals, cudaStream_t s) {
+                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
+                 unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s) {
     if (n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_CAP);
+        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
         attr_set = true;
     }
     OpsView view;
-    view.ops = ops; view.samples = nullptr;
+    view.ops = ops; view.samples = samples;
     EmitArgs e{};
     e.n_pairs = n_pairs; e.pair_off = pair_off; e.rec_order = rec_order; e.n_rec = n_rec;
     e.a = SerArgs{recs, view, win, names_off, names, text};
     e.plans = plans; e.res = res; e.line_len = line_len; e.line_off = line_off; e.out_idx = out_idx; e.blk_flags = blk_flags;
     e.out_text = out_text; e.cap_text = cap_text; e.out_line_off = out_line_off; e.num = num; e.st = st;
     e.byte_base = byte_base; e.rec_base = rec_base; e.orig_idx = orig_idx;
-    e.state = blk_state; e.agg = blk_agg; e.pre = blk_pre; e.ticket = ticket; e.totals = totals;
-    k_emit<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_CAP, s>>>(e);
+    e.lb_bytes = lb_bytes; e.lb_rows = lb_rows; e.ticket = ticket; e.totals = totals; e.err = err;
+    k_emit<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
 }
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s) {

@@ -36,6 +36,12 @@ constexpr int SL_WCAP = 2048;                // window boundaries of one block s
 #ifndef RB_SMP_MINB
 #define RB_SMP_MINB 3
 #endif
+#ifndef RB_EMIT_MINB
+#define RB_EMIT_MINB 6
+#endif
+#ifndef RB_EMIT_MID_TEXT
+#define RB_EMIT_MID_TEXT 0  // k_emit FAST blocks: short runs of untouched ops are copied from the input text (0: formatted from the op words)
+#endif
 constexpr int LIFT_THREADS = RB_LIFT_THREADS;  // pairs per k_lift block
 constexpr int LIFT_CCAP = RB_LIFT_CCAP;        // 32-op chunks of one record a k_lift block stages in shared memory
 constexpr int LNS_THREADS = 256;
@@ -124,9 +130,11 @@ void launch_rec_prep(int mode, RecInput in, const uint64_t* op_off, const uint32
                      RecInfo* recs, uint32_t* pair_cnt, StatsDev st, ErrSlots err, cudaStream_t s);
 void launch_pair_scan(const uint32_t* pair_cnt, const uint32_t* rec_order, uint32_t n_rec, uint64_t* pair_off, cudaStream_t s);
 // per block of LIFT_THREADS consecutive pairs (emission order): its record, if it has only one, and the run of chunks it touches
+enum : uint32_t { PLAN_UNIFORM = 1u,  // every pair of the block belongs to one record
+                  PLAN_FAST = 2u };   // ... and k_emit lifts the block itself, out of shared memory (k_lift skips it)
 struct LiftPlan {
     uint32_t k0;        // emission rank of the record of the block's first pair
-    uint32_t uniform;   // 1: every pair of the block belongs to that record
+    uint32_t uniform;   // PLAN_* flags
     uint64_t c_lo, c_hi;  // chunks of the first start boundary / last end boundary (~0: not applicable)
 };
 // rb invert: the CIGAR bytes of the whole-record rows (after launch_serialise)
@@ -135,11 +143,12 @@ void launch_whole_text(const uint32_t* ops, const uint64_t* op_off, uint32_t n_r
 // rb invert: one whole-record row per record (fills PairRes, line lengths, pair list, plans)
 void launch_whole_rows(uint32_t n_rec, const RecInfo* recs, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans,
                        cudaStream_t s);
+// mark_fast: blocks k_emit can lift itself get PLAN_FAST (the caller then runs k_lift with skip_fast and k_emit)
 void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s);
+                      const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s, bool mark_fast = false);
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                  const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
-                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s);
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast = false);
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s);
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
@@ -147,13 +156,14 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const LiftPlan* plans, const PairRes* res, const uint64_t* line_off, const uint64_t* out_idx, uint8_t* out_text,
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
                       uint32_t group, uint32_t defer_big, cudaStream_t s, const uint32_t* only_flagged = nullptr);
-// line scan + serialiser in one pass (k_emit): totals[0..3] = bytes, rows, overflow flag, blocks left to k_serialise
+// lift (FAST blocks) + line scan + serialiser in one pass (k_emit): totals[0..3] = bytes, rows, overflow flag, blocks left to
+// k_serialise; lb_bytes / lb_rows = one zeroed 64-bit look-back word per block of SER_LINES pairs
 void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
-                 const uint32_t* ops, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
-                 const LiftPlan* plans, const PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
+                 const uint32_t* ops, const Ctr* samples, const uint8_t* text, WinView win, const uint64_t* names_off, const uint8_t* names,
+                 const LiftPlan* plans, PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
                  uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
-                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, uint32_t* blk_state, ulonglong2* blk_agg,
-                 ulonglong2* blk_pre, unsigned int* ticket, unsigned long long* totals, cudaStream_t s);
+                 uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
+                 unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s);
 // few, long rows: the long verbatim runs of input text that k_serialise (defer_big = 1) left out, spread over the grid
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s);

@@ -919,10 +919,14 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     const uint32_t n = b->n_rec;
     int rc = RB_OK;
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
+    // Short rows (the usual tiling-window call): lift + line scan + serialiser in ONE kernel, k_emit.  Blocks of 128 pairs that
+    // belong to one record and fit its staging area are lifted there, out of shared memory (PLAN_FAST); k_lift only sees the rest.
+    const bool fused = ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && b->n_bytes / P <= 1024;
+    const bool fast_lift = fused && tail == TAIL_SEARCH && policy == RB_POLICY_RIGHTMOST && !getenv("RB_NO_FAST_LIFT");
     if (tail == TAIL_SEARCH || tail == TAIL_COMBINE) {
         KScope k(ctx, "k_lift_plan");
         launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
-                         b->plans.as<LiftPlan>(), s);
+                         b->plans.as<LiftPlan>(), s, fast_lift);
     }
     if (tail == TAIL_TRIM) {
         KScope k(ctx, "k_trim_rows");
@@ -942,12 +946,12 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         KScope k(ctx, "k_lift");
         launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
                     b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
-                    b->line_len.as<uint32_t>(), err, s);
+                    b->line_len.as<uint32_t>(), err, s, fast_lift);
     }
     // Short rows (the usual tiling-window call): line scan + serialiser in ONE kernel, k_emit — no per-pair offsets in HBM, no
     // second pass over the results.  The sizes are known only afterwards, so the text buffer is sized from an estimate (or
     // kept from the call before); a buffer that turns out too small is grown to the exact size and the kernel runs again.
-    if (ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && b->n_bytes / P <= 1024) {
+    if (fused) {
         const uint64_t nblk = (P + SER_LINES - 1) / SER_LINES;
         b->want = want;
         b->with_stats = with_stats != 0;
@@ -965,19 +969,23 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         if (with_stats) CU(b->out_stats.ensure(P * 40 + 64));
         unsigned long long* tot = b->emit_totals.as<unsigned long long>();
         uint64_t out_bytes = 0, n_out = 0, deferred = 0;
+        unsigned long long* lb_bytes = b->ln_agg.as<unsigned long long>();  // one look-back word per block each
+        unsigned long long* lb_rows = b->ln_pre.as<unsigned long long>();
         for (int attempt = 0;; attempt++) {
             CU(cudaMemsetAsync(tot, 0, 32, s));
+            CU(cudaMemsetAsync(lb_bytes, 0, (nblk + 1) * 8, s));
+            CU(cudaMemsetAsync(lb_rows, 0, (nblk + 1) * 8, s));
             {
                 KScope k(ctx, "k_emit");
                 launch_emit(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
-                            b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
+                            b->samples.as<Ctr>(), b->text_raw.as<uint8_t>() + TEXT_FRONT_PAD, win, b->names_off.as<uint64_t>(), b->names.as<uint8_t>(),
                             b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(), b->line_len.as<uint32_t>(), b->line_off.as<uint64_t>(),
                             b->out_idx.as<uint64_t>(), b->blk_flags.as<uint32_t>(),
                             (want & RB_WANT_TEXT) ? b->out_text.as<uint8_t>() : nullptr, (want & RB_WANT_TEXT) ? b->out_text.cap - 64 : 0,
                             (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                             (want & RB_WANT_NUMERIC) ? num_view(b, P) : NumDev{}, with_stats ? stats_view(b, P) : StatsDev{}, b->byte_base,
-                            b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), b->ln_state.as<uint32_t>(),
-                            b->ln_agg.as<ulonglong2>(), b->ln_pre.as<ulonglong2>(), sc + SC_TICKET_LNS, tot, s);
+                            b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), lb_bytes, lb_rows, sc + SC_TICKET_LNS,
+                            tot, err, s);
             }
             Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, tot).u64(6, tot + 1).u64(7, tot + 2).u64(8, tot + 3).go(s);
             CU(cudaStreamSynchronize(s));
@@ -987,7 +995,6 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
             if (!hs[7]) break;
             if (attempt) return fail(ctx, RB_ERR_CUDA, "k_emit: the text does not fit a buffer of its own size");
             CU(b->out_text.ensure(out_bytes + 64));  // exact now
-            CU(cudaMemsetAsync(b->ln_state.p, 0, (nblk + 2) * 4, s));
             CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));
         }
         if (deferred && (want & RB_WANT_TEXT)) {  // blocks holding a line > 2 KB: warp-per-line path of the serialiser
