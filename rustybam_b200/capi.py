@@ -195,11 +195,14 @@ def _np(ptr, n, dtype):
 class Context:
     """rb_ctx.  One per GPU; not thread-safe (one calling thread per context)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """devices=[d0, d1, ...]: a multi-device context — rb_liftover / rb_stats spread the records over the GPUs and merge
+        the rows into one output (the same id may be listed twice: two contexts on one GPU)."""
         self.lib = load()
         st = C.c_int(0)
-        dev = (C.c_int * 1)(device)
-        self.h = self.lib.rb_ctx_create(dev, 1, C.byref(st))
+        ids = list(devices) if devices else [device]
+        dev = (C.c_int * len(ids))(*ids)
+        self.h = self.lib.rb_ctx_create(dev, len(ids), C.byref(st))
         if not self.h:
             raise RbError(st.value, "rb_ctx_create failed (no sm_100 device? there is no CPU fallback)")
 

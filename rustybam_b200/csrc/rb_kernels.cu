@@ -2297,6 +2297,26 @@ k_whole_text(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_o
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+static size_t scan_lift_smem(bool lift) {
+    return (size_t)(SMP_THREADS * (SAMPLE + 1) + 9 * SMP_THREADS + (lift ? 2 * SL_WCAP : 0)) * sizeof(uint32_t);
+}
+// kernels that ask for more dynamic shared memory than the default limit: once per device (rb_ctx_create, after cudaSetDevice)
+int init_kernel_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(k_scan_lift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(true));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_lift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(false));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
+    return e == cudaSuccess ? 0 : -1;
+}
+// line_off[i] += delta (multi-device calls: a device learns where its rows start in the merged text after its kernels ran)
+__global__ void k_add_u64(unsigned long long* __restrict__ p, uint64_t n, unsigned long long delta) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += delta;
+}
+void launch_add_u64(uint64_t* p, uint64_t n, uint64_t delta, cudaStream_t s) {
+    if (n == 0 || delta == 0) return;
+    k_add_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<unsigned long long*>(p), n, delta);
+}
 void launch_whole_text(const uint32_t* ops, const uint64_t* op_off, uint32_t n_rec, const RecInfo* recs, const Ctr* samples,
                        const uint64_t* line_off, uint8_t* out_text, uint64_t n_ops_bound, cudaStream_t s) {
     if (n_rec == 0 || n_ops_bound == 0 || out_text == nullptr) return;
@@ -2314,20 +2334,11 @@ void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_r
     const uint64_t warps = (uint64_t)n_rec + 1;
     k_rec_ops<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(text, cigar_off, n_rec, tile_state, op_off, heads, err);
 }
-static size_t scan_lift_smem(bool lift) {
-    return (size_t)(SMP_THREADS * (SAMPLE + 1) + 9 * SMP_THREADS + (lift ? 2 * SL_WCAP : 0)) * sizeof(uint32_t);
-}
 void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
                       Ctr* samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
                       LiftArgs la, cudaStream_t s) {
     const uint64_t blocks = (n_ops_bound + SMP_OPS - 1) / SMP_OPS;
     if (blocks == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_scan_lift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(true));
-        cudaFuncSetAttribute(k_scan_lift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(false));
-        attr_set = true;
-    }
     if (lift)
         k_scan_lift<true><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(true), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg,
                                                                                       blk_pre, ticket, la);
@@ -2385,11 +2396,6 @@ void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       uint64_t* out_line_off, NumDev num, StatsDev st, uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx,
                       uint32_t group, uint32_t defer_big, cudaStream_t s, const uint32_t* only_flagged) {
     if (n_pairs == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
-        attr_set = true;
-    }
     OpsView view;
     view.ops = ops; view.samples = nullptr;
     SerArgs a{recs, view, win, names_off, names, text};
@@ -2405,11 +2411,6 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
                  uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
                  unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s) {
     if (n_pairs == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
-        attr_set = true;
-    }
     OpsView view;
     view.ops = ops; view.samples = samples;
     EmitArgs e{};

@@ -98,6 +98,8 @@ struct ErrSlots {
     unsigned long long* rec;  // key = record index
 };
 
+int init_kernel_attrs();  // once per device: dynamic shared-memory limits of the kernels that need more than the default
+void launch_add_u64(uint64_t* p, uint64_t n, uint64_t delta, cudaStream_t s);
 void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsigned long long* tile_state,
                      unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, cudaStream_t s);
 void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,

@@ -4,6 +4,7 @@
 // device they fail with RB_ERR_NO_DEVICE.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +12,7 @@
 #include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rbcuda.h"
@@ -94,6 +96,9 @@ struct rb_ctx {
     DevBuf scalars;               // small device scalars
     void* h_scalars = nullptr;    // pinned, mapped mirror (kernels store into it: k_publish)
     void* h_scalars_dev = nullptr;  // its device-side address
+    std::vector<rb_ctx*> peers;     // multi-device context (rb_ctx_create with n_devices > 1): one context per further device
+    uint64_t err_rec = UINT64_MAX;  // the caller's record index of the error map_err reported last
+    uint64_t multi_min_bytes = 8ull << 20;  // smaller calls stay on the first device (RB_MULTI_MIN_BYTES overrides)
 };
 
 struct rb_batch {
@@ -193,7 +198,7 @@ PinnedBlock* pinned_get(rb_ctx* ctx, size_t n) {
             }
         best = new PinnedBlock();
         const size_t want = n + n / 8 + 4096;
-        if (cudaHostAlloc(&best->p, want, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc(&best->p, want, cudaHostAllocPortable) != cudaSuccess) {  // (portable: every device of a multi-device context copies into it)
             (void)cudaGetLastError();
             delete best;
             return nullptr;
@@ -272,6 +277,7 @@ int map_err(rb_ctx* ctx, rb_batch* b, uint64_t e_tok, uint64_t e_rec) {
     }
     if (best_rec == UINT64_MAX) return RB_OK;
     best_rec = (!b->h_orig.empty() && best_rec < b->h_orig.size()) ? b->h_orig[best_rec] : best_rec + b->rec_base;  // the caller's record index
+    ctx->err_rec = best_rec;
     switch (code) {
         case RE_CIGAR_PARSE: return fail(ctx, RB_ERR_REF_CIGAR_PARSE, "record %llu: Unable to parse cigar string (reference panics, paf.rs:399)", (unsigned long long)best_rec);
         case RE_INTEGRITY: return fail(ctx, RB_ERR_REF_INTEGRITY, "record %llu: CIGAR does not match the record's spans (check_integrity().unwrap(), paf.rs:70)", (unsigned long long)best_rec);
@@ -417,7 +423,7 @@ int rb_host_unregister(void* ptr) {
     return rc;
 }
 
-rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
+static rb_ctx* ctx_create_one(int dev, int* status) {
     auto set = [&](int s) { if (status) *status = s; };
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -425,7 +431,6 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
         set(RB_ERR_NO_DEVICE);
         return nullptr;
     }
-    const int dev = (device_ids && n_devices > 0) ? device_ids[0] : 0;
     cudaDeviceProp prop{};
     if (dev < 0 || dev >= count || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
         (void)cudaGetLastError();
@@ -435,8 +440,9 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
     rb_ctx* ctx = new rb_ctx();
     ctx->device = dev;
     ctx->fused_emit = getenv("RB_NO_FUSED_EMIT") == nullptr;
+    if (const char* e = getenv("RB_MULTI_MIN_BYTES")) ctx->multi_min_bytes = strtoull(e, nullptr, 10);
     cudaSetDevice(dev);
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    if (init_kernel_attrs() != 0 || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         ctx->scalars.ensure(SC_WORDS * 4) != cudaSuccess || cudaHostAlloc(&ctx->h_scalars, 256, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer(&ctx->h_scalars_dev, ctx->h_scalars, 0) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming) != cudaSuccess ||
@@ -447,6 +453,26 @@ rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
         return nullptr;
     }
     set(RB_OK);
+    return ctx;
+}
+
+// device_ids[0 .. n_devices): the GPUs of this context (NULL / 0: device 0).  With more than one, rb_liftover and rb_stats
+// partition the records over them (contiguous runs of the emission order, balanced on CIGAR bytes; one host thread and
+// stream set per device; no exchange between the devices) and merge the rows into ONE output in the reference's emission
+// order; every other call runs on the first device.  The same id may be listed twice (two contexts on one GPU).
+rb_ctx* rb_ctx_create(const int* device_ids, int n_devices, int* status) {
+    const int dev0 = (device_ids && n_devices > 0) ? device_ids[0] : 0;
+    rb_ctx* ctx = ctx_create_one(dev0, status);
+    if (!ctx) return nullptr;
+    for (int i = 1; device_ids && i < n_devices; i++) {
+        rb_ctx* p = ctx_create_one(device_ids[i], status);
+        if (!p) {
+            rb_ctx_destroy(ctx);
+            return nullptr;
+        }
+        ctx->peers.push_back(p);
+    }
+    cudaSetDevice(dev0);
     return ctx;
 }
 
@@ -468,6 +494,8 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
 
 void rb_ctx_destroy(rb_ctx* ctx) {
     if (!ctx) return;
+    for (rb_ctx* p : ctx->peers) rb_ctx_destroy(p);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -1436,6 +1464,292 @@ static int liftover_unsliced(rb_ctx* ctx, const rb_records* recs, const rb_windo
     return rb_batch_download_lift(ctx, b, want, out, stats);
 }
 
+// ---- rb_liftover / rb_stats on a multi-device context -----------------------------------------------
+// The records are cut into one contiguous run of the EMISSION order per device (liftover.rs:151-164: contigs by first
+// appearance, file order inside), balanced on CIGAR bytes; a cut snaps to the nearest contig boundary when that costs less
+// than 5 % of a device's share.  Every device (one host thread each) uploads its records and the window rows of its
+// contigs, runs the whole kernel sequence and reports its row / byte counts; the prefix over the devices says where each
+// device's rows go in the ONE pinned output block, and every device copies its rows there itself (line offsets rebased
+// on the device).  Nothing is exchanged between the GPUs: a (window, record) pair needs that record and that window only.
+extern "C++" {
+namespace {
+struct Rendezvous {  // all device threads meet; the last one to arrive runs `fn` before anybody leaves
+    std::mutex m;
+    std::condition_variable cv;
+    int n, count = 0, gen = 0;
+    explicit Rendezvous(int n_) : n(n_) {}
+    template <class F> void meet(F&& fn) {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n) { fn(); count = 0; gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return g != gen; });
+    }
+};
+
+// cut[d] .. cut[d+1]: positions in `ord` of device d's records
+bool partition_by_bytes(const rb_records* R, const std::vector<uint32_t>& ord, int D, std::vector<uint32_t>& cut) {
+    const uint32_t n = (uint32_t)ord.size();
+    std::vector<uint64_t> pre(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t r = ord[i];
+        if (R->cigar_off[r + 1] < R->cigar_off[r]) return false;
+        pre[i + 1] = pre[i] + (R->cigar_off[r + 1] - R->cigar_off[r]) + 64;  // (+64: records without a CIGAR still cost something)
+    }
+    const uint64_t total = pre[n], share = total / (uint64_t)D, slack = share / 20;
+    cut.assign(1, 0);
+    for (int d = 1; d < D; d++) {
+        const uint64_t target = total * (uint64_t)d / (uint64_t)D;
+        uint32_t i = (uint32_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        if (i > n) i = n;
+        // nearest contig boundary on either side, if it keeps the share within 5 %
+        uint32_t lo = i, hi = i;
+        while (lo > cut.back() && lo < n && R->t_id[ord[lo]] == R->t_id[ord[lo - 1]] && target - pre[lo] < slack) lo--;
+        while (hi < n && hi > 0 && R->t_id[ord[hi]] == R->t_id[ord[hi - 1]] && pre[hi] - target < slack) hi++;
+        const bool lo_ok = lo > cut.back() && lo < n && R->t_id[ord[lo]] != R->t_id[ord[lo - 1]] && target - pre[lo] <= slack;
+        const bool hi_ok = hi < n && hi > 0 && R->t_id[ord[hi]] != R->t_id[ord[hi - 1]] && pre[hi] - target <= slack;
+        if (lo_ok && (!hi_ok || target - pre[lo] <= pre[hi] - target)) i = lo;
+        else if (hi_ok) i = hi;
+        if (i <= cut.back() || i >= n) return false;  // a device would get nothing: not worth spreading
+        cut.push_back(i);
+    }
+    cut.push_back(n);
+    return true;
+}
+}  // namespace
+}  // extern "C++"
+
+// returns 1 when the call was not spread (the caller runs it on the first device), else an rb_status
+static int liftover_multi(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
+                          rb_stats_out* stats) {
+    const int D = 1 + (int)ctx->peers.size();
+    if (!recs || !wins || !wins->n_win || recs->n_rec < 2u * (uint32_t)D || !recs->cigar_off || !recs->t_id ||
+        recs->cigar_nbytes < ctx->multi_min_bytes || recs->cigar_off[recs->n_rec] != recs->cigar_nbytes || ctx->profiling)
+        return 1;
+    std::vector<uint32_t> ord, cut;
+    bool identity = true;
+    if (!emission_order(recs, ord, identity) || !partition_by_bytes(recs, ord, D, cut)) return 1;
+    std::vector<rb_ctx*> cs(1, ctx);
+    cs.insert(cs.end(), ctx->peers.begin(), ctx->peers.end());
+
+    struct Dev { int rc = RB_OK; rb_summary sum{}; uint64_t row_base = 0, byte_base = 0; bool general = false; };
+    std::vector<Dev> dv((size_t)D);
+    Rendezvous rv(D);
+    PinnedBlock *blk = nullptr, *sblk = nullptr;
+    uint8_t* base = nullptr;
+    size_t o_text = 64, o_loff = 0, o_num = 0;
+    uint64_t tot_rows = 0, tot_bytes = 0, tot_pairs = 0;
+    int call_rc = RB_OK;
+    bool fall_back = false;
+
+    auto work = [&](int d) {
+        rb_ctx* c = cs[(size_t)d];
+        Dev& me = dv[(size_t)d];
+        cudaSetDevice(c->device);
+        c->invert = ctx->invert;
+        c->err.clear(); c->err_rec = UINT64_MAX;
+        if (!c->scratch) c->scratch = new rb_batch();
+        rb_batch* b = c->scratch;
+        cudaStream_t s = c->stream;
+        auto run = [&]() -> int {
+            if (b->busy) { if (cudaStreamSynchronize(s) != cudaSuccess) return fail(c, RB_ERR_CUDA, "cudaStreamSynchronize"); b->busy = false; }
+            b->n_rec = 0; b->have_lift = b->have_stats = false;
+            int rc = windows_prepare(c, b, recs, wins);
+            if (rc != RB_OK) return rc;
+            // the window rows of this device's contigs travel in front of its CIGAR text
+            std::vector<uint8_t> up(recs->n_names, 0);
+            std::vector<std::pair<uint32_t, uint32_t>> rows_up;
+            for (uint32_t i = cut[(size_t)d]; i < cut[(size_t)d + 1]; i++) {
+                const uint32_t t = recs->t_id[ord[i]];
+                if (up[t]) continue;
+                up[t] = 1;
+                const uint32_t lo = b->h_clo[t], hi = b->h_chi[t];
+                if (hi <= lo) continue;
+                rc = windows_upload_rows(c, b, wins, lo, hi, s);
+                if (rc != RB_OK) return rc;
+                rows_up.emplace_back(lo, hi);
+            }
+            rc = windows_upload_aux(c, b, recs, wins, s);
+            if (rc != RB_OK) return rc;
+            const RecSel sel{identity ? nullptr : ord.data() + cut[(size_t)d], cut[(size_t)d], cut[(size_t)d + 1] - cut[(size_t)d]};
+            rc = upload_cigar(c, b, recs, sel);
+            if (rc == RB_OK) rc = upload_columns(c, b, recs, sel);
+            if (rc != RB_OK) return rc;
+            rc = rb_batch_liftover(c, b, policy, want, stats != nullptr, &me.sum);
+            if (rc != RB_OK) return rc;
+            if (d == 0) {  // the first device also sees the rest of the table: the check kernel looks at all of it
+                std::sort(rows_up.begin(), rows_up.end());
+                uint32_t at = 0;
+                for (auto& iv : rows_up) {
+                    if (rc == RB_OK && iv.first > at) rc = windows_upload_rows(c, b, wins, at, iv.first, s);
+                    at = std::max(at, iv.second);
+                }
+                if (rc == RB_OK && at < b->n_win) rc = windows_upload_rows(c, b, wins, at, b->n_win, s);
+                if (rc == RB_OK) rc = windows_check(c, b, recs, s);
+                if (rc == RB_OK) rc = upload_windows_end(c, b, recs, wins);  // waits for the verdict
+                me.general = b->general;
+            }
+            return rc;
+        };
+        me.rc = run();
+        if (me.rc != RB_OK && b->busy) { cudaStreamSynchronize(s); b->busy = false; }
+        rv.meet([&] {  // everybody's sizes are known: lay out the one output block
+            uint64_t best_err = UINT64_MAX;
+            for (int k = 0; k < D; k++) {
+                if (dv[(size_t)k].rc != RB_OK && (call_rc == RB_OK || cs[(size_t)k]->err_rec < best_err)) {
+                    call_rc = dv[(size_t)k].rc;
+                    best_err = cs[(size_t)k]->err_rec;
+                    if (k) ctx->err = cs[(size_t)k]->err;
+                }
+                if (dv[(size_t)k].general) fall_back = true;  // nested rows / file order != sorted order: single-batch path
+            }
+            if (call_rc != RB_OK || fall_back) return;
+            for (int k = 0; k < D; k++) {
+                dv[(size_t)k].row_base = tot_rows; dv[(size_t)k].byte_base = tot_bytes;
+                tot_rows += dv[(size_t)k].sum.n_out; tot_bytes += dv[(size_t)k].sum.out_bytes; tot_pairs += dv[(size_t)k].sum.n_pairs;
+            }
+            cudaSetDevice(ctx->device);
+            const size_t text_room = (want & RB_WANT_TEXT) ? align_up(tot_bytes + 1, 64) : 0;
+            const size_t loff_bytes = (want & RB_WANT_TEXT) ? align_up((tot_rows + 1) * 8, 64) : 0;
+            const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(tot_rows * 56, 64) : 0;
+            blk = pinned_get(ctx, 64 + text_room + loff_bytes + num_bytes);
+            if (stats) sblk = pinned_get(ctx, (size_t)tot_rows * 40 + 64);
+            if (!blk || (stats && !sblk)) { call_rc = fail(ctx, RB_ERR_OOM, "pinned allocation of the merged output failed"); return; }
+            base = reinterpret_cast<uint8_t*>(blk->p);
+            o_loff = 64 + text_room;
+            o_num = o_loff + loff_bytes;
+            cudaSetDevice(c->device);
+        });
+        if (call_rc != RB_OK || fall_back) return;
+        // ---- this device's rows -> their place in the merged output ----
+        auto copy = [&]() -> int {
+            rb_ctx* ctx = c;  // (CU reports into this device's context)
+            const uint64_t nk = me.sum.n_out, sk = b->row_stride ? b->row_stride : nk, cap = tot_rows;
+            if (want & RB_WANT_TEXT) {
+                launch_add_u64(b->out_line_off.as<uint64_t>(), nk, me.byte_base, s);
+                if (me.sum.out_bytes) CU(cudaMemcpyAsync(base + o_text + me.byte_base, b->out_text.p, me.sum.out_bytes, cudaMemcpyDeviceToHost, s));
+                if (nk) CU(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + o_loff) + me.row_base, b->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, s));
+            }
+            if ((want & RB_WANT_NUMERIC) && nk) {
+                uint64_t* dn = reinterpret_cast<uint64_t*>(base + o_num);
+                const uint64_t* sp = b->out_num.as<uint64_t>();
+                CU(cudaMemcpy2DAsync(dn + me.row_base, cap * 8, sp, sk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, s));
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(dn + 6 * cap);
+                const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * sk);
+                CU(cudaMemcpy2DAsync(d32 + me.row_base, cap * 4, s32, sk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, s));
+            }
+            if (stats && nk) {
+                uint32_t* ds = reinterpret_cast<uint32_t*>(sblk->p);
+                CU(cudaMemcpy2DAsync(ds + me.row_base, cap * 4, b->out_stats.as<uint32_t>(), sk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, s));
+            }
+            CU(cudaStreamSynchronize(s));
+            return RB_OK;
+        };
+        me.rc = copy();
+    };
+    std::vector<std::thread> pool;
+    for (int d = 1; d < D; d++) pool.emplace_back(work, d);
+    work(0);
+    for (auto& th : pool) th.join();
+    cudaSetDevice(ctx->device);
+    for (rb_ctx* p : ctx->peers) p->invert = false;
+    auto release = [&] { if (blk) blk->in_use = false; if (sblk) sblk->in_use = false; };
+    if (fall_back && call_rc == RB_OK) { release(); return 1; }
+    if (call_rc != RB_OK) { release(); return call_rc; }
+    for (int d = 0; d < D; d++)
+        if (dv[(size_t)d].rc != RB_OK) { if (d) ctx->err = cs[(size_t)d]->err; release(); return dv[(size_t)d].rc; }
+    memset(out, 0, sizeof *out);
+    if (stats) memset(stats, 0, sizeof *stats);
+    out->n_out = tot_rows; out->paf_nbytes = tot_bytes; out->n_pairs = tot_pairs; out->_owner = blk;
+    if (want & RB_WANT_TEXT) {
+        out->paf_text = base + o_text;
+        out->line_off = reinterpret_cast<uint64_t*>(base + o_loff);
+        out->line_off[tot_rows] = tot_bytes;
+        if (tot_rows == 0) out->line_off[0] = 0;
+        out->paf_text[tot_bytes] = 0;
+    }
+    if (want & RB_WANT_NUMERIC) {
+        uint64_t* p = reinterpret_cast<uint64_t*>(base + o_num);
+        const uint64_t c = tot_rows;
+        out->q_st = p; out->q_en = p + c; out->t_st = p + 2 * c; out->t_en = p + 3 * c; out->nmatch = p + 4 * c; out->aln_len = p + 5 * c;
+        out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * c);
+        out->win_idx = out->rec_idx + c;
+    }
+    if (stats) {
+        uint32_t* p = reinterpret_cast<uint32_t*>(sblk->p);
+        const uint64_t c = tot_rows;
+        stats->n = tot_rows;
+        stats->equal = p; stats->diff = p + c; stats->ins = p + 2 * c; stats->del = p + 3 * c; stats->ins_events = p + 4 * c;
+        stats->del_events = p + 5 * c; stats->matches = p + 6 * c;
+        stats->id_by_matches = reinterpret_cast<float*>(p + 7 * c); stats->id_by_events = reinterpret_cast<float*>(p + 8 * c);
+        stats->id_by_all = reinterpret_cast<float*>(p + 9 * c);
+        stats->_owner = sblk;
+    }
+    return RB_OK;
+}
+
+// rb_stats on a multi-device context: runs of records in FILE order, balanced on CIGAR bytes; rows land at their record index
+static int stats_multi(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {
+    const int D = 1 + (int)ctx->peers.size();
+    if (!recs || recs->n_rec < 2u * (uint32_t)D || !recs->cigar_off || recs->cigar_nbytes < ctx->multi_min_bytes ||
+        recs->cigar_off[recs->n_rec] != recs->cigar_nbytes || ctx->profiling)
+        return 1;
+    const uint32_t n = recs->n_rec;
+    std::vector<uint32_t> cut(1, 0);
+    for (int d = 1; d < D; d++) {
+        const uint64_t target = recs->cigar_nbytes / (uint64_t)D * (uint64_t)d;
+        uint32_t i = (uint32_t)(std::lower_bound(recs->cigar_off, recs->cigar_off + n + 1, target) - recs->cigar_off);
+        if (i <= cut.back() || i >= n) return 1;
+        cut.push_back(i);
+    }
+    cut.push_back(n);
+    std::vector<rb_ctx*> cs(1, ctx);
+    cs.insert(cs.end(), ctx->peers.begin(), ctx->peers.end());
+    PinnedBlock* sblk = pinned_get(ctx, (size_t)n * 40 + 64);
+    if (!sblk) return fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)n * 40);
+    std::vector<int> rcs((size_t)D, RB_OK);
+    auto work = [&](int d) {
+        rb_ctx* c = cs[(size_t)d];
+        rb_ctx* ctx = c;  // (CU reports into this device's context)
+        cudaSetDevice(c->device);
+        c->invert = false;
+        c->err.clear(); c->err_rec = UINT64_MAX;
+        if (!c->scratch) c->scratch = new rb_batch();
+        rb_batch* b = c->scratch;
+        auto run = [&]() -> int {
+            if (b->busy) { CU(cudaStreamSynchronize(c->stream)); b->busy = false; }
+            const RecSel sel{nullptr, cut[(size_t)d], cut[(size_t)d + 1] - cut[(size_t)d]};
+            int rc = upload_cigar(c, b, recs, sel);
+            if (rc == RB_OK) rc = windows_prepare(c, b, recs, nullptr);
+            if (rc == RB_OK) rc = upload_columns(c, b, recs, sel);
+            if (rc == RB_OK) rc = rb_batch_stats(c, b, nullptr);
+            if (rc != RB_OK) return rc;
+            const uint64_t nk = sel.n;
+            if (nk) CU(cudaMemcpy2DAsync(reinterpret_cast<uint32_t*>(sblk->p) + sel.r0, (size_t)n * 4, b->out_stats.p, nk * 4, nk * 4, 10,
+                                         cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            return RB_OK;
+        };
+        rcs[(size_t)d] = run();
+        if (rcs[(size_t)d] != RB_OK && b->busy) { cudaStreamSynchronize(c->stream); b->busy = false; }
+    };
+    std::vector<std::thread> pool;
+    for (int d = 1; d < D; d++) pool.emplace_back(work, d);
+    work(0);
+    for (auto& th : pool) th.join();
+    cudaSetDevice(ctx->device);
+    for (int d = 0; d < D; d++)  // devices hold runs of the file order: the first failing device holds the first failing record
+        if (rcs[(size_t)d] != RB_OK) { if (d) ctx->err = cs[(size_t)d]->err; sblk->in_use = false; return rcs[(size_t)d]; }
+    memset(stats, 0, sizeof *stats);
+    uint32_t* p = reinterpret_cast<uint32_t*>(sblk->p);
+    stats->n = n;
+    stats->equal = p; stats->diff = p + n; stats->ins = p + 2 * (size_t)n; stats->del = p + 3 * (size_t)n; stats->ins_events = p + 4 * (size_t)n;
+    stats->del_events = p + 5 * (size_t)n; stats->matches = p + 6 * (size_t)n;
+    stats->id_by_matches = reinterpret_cast<float*>(p + 7 * (size_t)n); stats->id_by_events = reinterpret_cast<float*>(p + 8 * (size_t)n);
+    stats->id_by_all = reinterpret_cast<float*>(p + 9 * (size_t)n);
+    stats->_owner = sblk;
+    return RB_OK;
+}
+
 int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
                 rb_stats_out* stats) {
     if (!ctx) return RB_ERR_NO_DEVICE;
@@ -1453,6 +1767,10 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
     }
     want &= ~RB_WANT_QBED;
     cudaSetDevice(ctx->device);
+    if (!ctx->peers.empty() && (policy == RB_POLICY_RIGHTMOST || policy == RB_POLICY_EARLY_EXIT)) {
+        const int mrc = liftover_multi(ctx, recs, wins, policy, want, out, stats);
+        if (mrc != 1) return mrc;  // (1: not spread — too small, or a window layout the single-batch path handles)
+    }
     if (!ctx->scratch) ctx->scratch = new rb_batch();
     rb_batch* wb = ctx->scratch;
     const uint64_t SLICE_MIN_BYTES = ctx->slice_min_bytes;
@@ -1999,6 +2317,10 @@ int rb_stats(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats) {
     if (!ctx) return RB_ERR_NO_DEVICE;
     if (!stats) return fail(ctx, RB_ERR_BAD_ARG, "stats is null");
     cudaSetDevice(ctx->device);
+    if (!ctx->peers.empty()) {
+        const int mrc = stats_multi(ctx, recs, stats);
+        if (mrc != 1) return mrc;
+    }
     if (!ctx->scratch) ctx->scratch = new rb_batch();
     int rc = upload_into(ctx, ctx->scratch, recs, nullptr);
     if (rc != RB_OK) return rc;

@@ -1,6 +1,7 @@
 // rb — the host CLI for the two subcommands on the hot path, same flags as the reference
 // (src/cli.rs:16-27,49-60,100-115; drivers src/main.rs:50-58,186-214):
-//     rb [-t N] liftover --bed <BED> [--qbed] [--largest] [PAF|-]     (--qbed: inversion on the GPU; --largest: host filter)
+//     rb [-t N] [--gpus G] liftover --bed <BED> [--qbed] [--largest] [PAF|-]  (alias lo, cli.rs visible_aliases; --qbed: inversion on the
+//                                                          GPU; --largest: host filter; --gpus G: spread the records over G B200s)
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
 //     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
 //     rb [-t N] invert [PAF|-]                          (src/cli.rs:89-94, main.rs:176-182)
@@ -17,7 +18,7 @@
 #include "rbhost.hpp"
 
 static int usage() {
-    fprintf(stderr, "usage: rb [-t N] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n"
+    fprintf(stderr, "usage: rb [-t N] [--gpus G] liftover --bed <BED> [PAF]\n       rb [-t N] stats --paf [--qbed] [PAF]\n"
                     "       rb [-t N] break-paf [--max-size N] [PAF]\n       rb [-t N] invert [PAF]\n"
                     "       rb [-t N] trim-paf [-m M] [-d D] [-i I] [-r] [PAF]\n");
     return 2;
@@ -31,8 +32,11 @@ int main(int argc, char** argv) {
     int match_score = 1, diff_score = 1, indel_score = 1;  // cli.rs:126-134
     bool remove_contained = false;
     bool is_trim = false;
+    int n_gpus = 1;  // --gpus G (not in the reference): a multi-device rb_ctx, records spread over devices 0 .. G-1
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
+        if (a == "--gpus" && i + 1 < argc) { n_gpus = atoi(argv[++i]); continue; }
+        if (cmd.empty() && a == "lo") { cmd = "liftover"; continue; }  // cli.rs: visible_aliases = ["lo"]
         if (cmd.empty() && (a == "trim-paf" || a == "trim" || a == "tp")) { cmd = "trim-paf"; is_trim = true; continue; }
         if (is_trim) {  // trim-paf reuses short flags of other subcommands (-m, -i, -d, -r)
             if ((a == "-m" || a == "--match-score") && i + 1 < argc) { match_score = atoi(argv[++i]); continue; }
@@ -55,7 +59,10 @@ int main(int argc, char** argv) {
     const bool inv = (cmd == "invert");
     if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk && !inv && !is_trim) return usage();
     int status = 0;
-    rb_ctx* ctx = rb_ctx_create(nullptr, 0, &status);
+    if (n_gpus < 1 || n_gpus > 64) return usage();
+    int ids[64];
+    for (int d = 0; d < n_gpus; d++) ids[d] = d;
+    rb_ctx* ctx = rb_ctx_create(ids, n_gpus, &status);
     if (!ctx) {
         fprintf(stderr, "rb: no usable sm_100 CUDA device (status %d); this build has no CPU path\n", status);
         return 3;

@@ -7,7 +7,7 @@ import pytest
 
 import gen
 import orc
-from rustybam_b200 import bamstats, bed, capi, liftover
+from rustybam_b200 import bamstats, bed, capi, hostlib, liftover
 from rustybam_b200.paf import Paf, ReferencePanic
 
 pytestmark = pytest.mark.gpu
@@ -440,3 +440,47 @@ def test_liftover_largest(ctx, seed):
     for bed_text in (gen.tiling_bed(contigs, 25), gen.random_bed(seed, contigs, 60, with_ids=True), gen.random_bed(seed, contigs, 60, with_ids=False)):
         want = orc.run_liftover(paf_text, bed_text, largest=True, threads=1)
         assert liftover.run_liftover(ctx, paf_text, bed_text, largest=True) == want
+
+
+# ---------------------------------------------------------------- multi-device context behind the C ABI
+def test_multi_device_context_equals_single_and_oracle(monkeypatch):
+    """rb_ctx_create with several device ids: rb_liftover / rb_stats partition the records over the devices (contiguous runs
+    of the emission order, liftover.rs:151-164) and merge the rows into one output.  Two contexts on GPU 0 stand in for two
+    GPUs here (the partition, the per-device threads and the merge are the same code); results == one device == oracle."""
+    monkeypatch.setenv("RB_MULTI_MIN_BYTES", "0")
+    one, two, three = capi.Context(0), capi.Context(devices=[0, 0]), capi.Context(devices=[0, 0, 0])
+    try:
+        for seed in (11, 12, 13):
+            paf_text, contigs = gen.random_paf(seed, n_contigs=4, recs_per_contig=9, max_ops=300)
+            lines = paf_text.splitlines(keepends=True)
+            rng = np.random.default_rng(seed)
+            paf_text = b"".join(lines[i] for i in rng.permutation(len(lines)))  # contigs interleave: emission order != file order
+            bed_text = gen.tiling_bed(contigs, 40)
+            hp = hostlib.HostPaf.from_text(paf_text)
+            wins = hp.windows_from_bed_text(bed_text)
+            want = orc.run_liftover(paf_text, bed_text)
+            a = one.liftover(hp, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+            assert a["paf_text"] == want
+            for ctx in (two, three):
+                b = ctx.liftover(hp, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+                assert b["paf_text"] == want and b["n_pairs"] == a["n_pairs"]
+                for k in ("line_off", "q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len", "rec_idx", "win_idx"):
+                    assert (a[k] == b[k]).all(), k
+                for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches"):
+                    assert (a["stats"][k] == b["stats"][k]).all(), k
+                assert (a["stats"]["id_by_all"].view(np.uint32) == b["stats"]["id_by_all"].view(np.uint32)).all()
+                st1, st2 = one.stats(hp), ctx.stats(hp)
+                for k in st1:
+                    assert np.array_equal(st1[k], st2[k], equal_nan=True) if k != "n" else st1[k] == st2[k], k
+        # a reference panic on one device's share fails the whole call with that record's error
+        name, ln = next(iter(contigs.items()))
+        bad = paf_text + b"Q\t10\t0\t5\t+\t" + name.encode() + b"\t" + str(ln).encode() + b"\t0\t8\t0\t0\t60\tcg:Z:3D5=\n"
+        hb = hostlib.HostPaf.from_text(bad)
+        with pytest.raises(capi.RbError) as e1:
+            one.liftover(hb, hb.windows_from_bed_text(bed_text))
+        with pytest.raises(capi.RbError) as e2:
+            two.liftover(hb, hb.windows_from_bed_text(bed_text))
+        assert e1.value.code == e2.value.code
+    finally:
+        for c in (one, two, three):
+            c.close()

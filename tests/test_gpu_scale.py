@@ -265,6 +265,33 @@ def test_full_scale_sliced_call_equals_unsliced(ctx, full):
     assert (d["t_st"] == a["t_st"]).all() and (d["stats"]["equal"] == a["stats"]["equal"]).all()
 
 
+def test_full_scale_multi_device_context_equals_single(ctx, full):
+    """rb_liftover / rb_stats on a multi-device rb_ctx (three contexts on GPU 0 standing in for three GPUs; with more GPUs
+    visible the real ones are used): partition in C++ on the packed arrays, one host thread per device, rows merged in
+    emission order into ONE output — the bytes, mirror and counters of the single-device call."""
+    import torch
+    n_gpu = torch.cuda.device_count()
+    ids = list(range(n_gpu)) if n_gpu >= 2 else [0, 0, 0]
+    multi = capi.Context(devices=ids)
+    try:
+        for paf, width in ((full, 1000), (hostlib.HostPaf.synth(scale=0.25, n_hap=3), 10_000)):  # (the second: haplotype-major file order)
+            wins = paf.tiling_windows(width)
+            a = ctx.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+            b = multi.liftover(paf, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+            assert a["n_out"] == b["n_out"] and a["n_pairs"] == b["n_pairs"] and a["paf_text"] == b["paf_text"]
+            for k in ("line_off", "q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len", "rec_idx", "win_idx"):
+                assert (a[k] == b[k]).all(), k
+            for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches"):
+                assert (a["stats"][k] == b["stats"][k]).all(), k
+            for k in ("id_by_matches", "id_by_events", "id_by_all"):
+                assert (a["stats"][k].view(np.uint32) == b["stats"][k].view(np.uint32)).all(), k
+            s1, s2 = ctx.stats(paf), multi.stats(paf)
+            assert all((s1[k] == s2[k]).all() for k in ("equal", "diff", "ins", "del", "ins_events", "del_events", "matches"))
+            assert (s1["id_by_all"].view(np.uint32) == s2["id_by_all"].view(np.uint32)).all()
+    finally:
+        multi.close()
+
+
 def test_two_haplotypes_gathered_slices_equal_unsliced(ctx):
     """A multi-haplotype PAF (file order: haplotype-major, so contigs interleave) is sliced in emission order with
     gathered uploads; rows, rec_idx and counters equal the single-batch call."""
