@@ -249,6 +249,38 @@ class Context:
             self.lib.rb_free_stats_out(self.h, C.byref(st))
         return res
 
+    def liftover_view(self, recs: Records, wins: Windows, policy=POLICY_RIGHTMOST, want=WANT_TEXT | WANT_NUMERIC, stats=True):
+        """rb_liftover without copying the outputs: returns (views, release) — numpy views straight onto the library's pinned
+        block ("paf_text" as a uint8 array), valid until release() is called.  For outputs of many GB (bench.py's checks)."""
+        out, st = RbLiftOut(), RbStatsOut()
+        self._check(self.lib.rb_liftover(self.h, C.byref(recs.c), C.byref(wins.c), policy, want, C.byref(out),
+                                         C.byref(st) if stats else None))
+        n, nb = int(out.n_out), int(out.paf_nbytes)
+
+        def view(ptr, cnt, dt):
+            if not ptr or cnt == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(ptr, shape=(cnt,))
+        res = dict(n_out=n, n_pairs=int(out.n_pairs), paf_nbytes=nb)
+        if want & WANT_TEXT:
+            res["paf_text"], res["line_off"] = view(out.paf_text, nb, np.uint8), view(out.line_off, n + 1, np.uint64)
+        if want & WANT_NUMERIC:
+            for k in ("q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len"):
+                res[k] = view(getattr(out, k), n, np.uint64)
+            res["rec_idx"], res["win_idx"] = view(out.rec_idx, n, np.uint32), view(out.win_idx, n, np.uint32)
+        if stats:
+            res["stats"] = dict(n=n, equal=view(st.equal, n, np.uint32), diff=view(st.diff, n, np.uint32), ins=view(st.ins, n, np.uint32),
+                                **{"del": view(st.del_, n, np.uint32)}, ins_events=view(st.ins_events, n, np.uint32),
+                                del_events=view(st.del_events, n, np.uint32), matches=view(st.matches, n, np.uint32),
+                                id_by_matches=view(st.id_by_matches, n, np.float32), id_by_events=view(st.id_by_events, n, np.float32),
+                                id_by_all=view(st.id_by_all, n, np.float32))
+
+        def release():
+            self.lib.rb_free_lift_out(self.h, C.byref(out))
+            if stats:
+                self.lib.rb_free_stats_out(self.h, C.byref(st))
+        return res, release
+
     def break_paf(self, recs: Records, max_size=100, policy=POLICY_RIGHTMOST, want=WANT_TEXT | WANT_NUMERIC, stats=True, copy=True):
         """rb_break_paf: every record cut at its indels longer than max_size (liftover.rs:182-226), rows in file order."""
         out, st = RbLiftOut(), RbStatsOut()

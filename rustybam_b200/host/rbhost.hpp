@@ -112,6 +112,7 @@ struct SynthParams {
     double scale = 1.0;   // multiplies the CHM13-like contig lengths
     int n_hap = 1;        // haplotypes (independent streams) concatenated
     int threads = 8;
+    uint32_t contig_mask = 0xFFFFFFFFu;  // bit c: generate contig c of the CHM13-like table (a GPU's share of a multi-GPU job)
 };
 Paf synth_paf(const SynthParams& p);
 // `bedtools makewindows`-style tiling of every target contig of `paf`, 3 columns (id = chrom:st+1-en), sorted

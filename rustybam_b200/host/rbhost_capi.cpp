@@ -22,6 +22,11 @@ void* rbh_synth_paf(uint64_t seed, double scale, int n_hap, int threads) {
     p.seed = seed; p.scale = scale; p.n_hap = n_hap; p.threads = threads;
     return new Paf(synth_paf(p));
 }
+void* rbh_synth_paf_mask(uint64_t seed, double scale, int n_hap, int threads, uint32_t contig_mask) {
+    SynthParams p;
+    p.seed = seed; p.scale = scale; p.n_hap = n_hap; p.threads = threads; p.contig_mask = contig_mask;
+    return new Paf(synth_paf(p));
+}
 void* rbh_paf_from_text(const char* text, size_t n, char* err, size_t err_cap) {
     try {
         return new Paf(Paf::from_text(text, n));

@@ -118,6 +118,7 @@ Paf synth_paf(const SynthParams& p) {
             for (;;) {
                 const int k = next.fetch_add(1);
                 if (k >= n_task) break;
+                if (!((p.contig_mask >> (k % N_CONTIG)) & 1u)) continue;  // (one independent stream per haplotype and contig)
                 gen_contig(p.seed, k / N_CONTIG, k % N_CONTIG, p.scale, outs[(size_t)k]);
             }
         });
@@ -131,6 +132,7 @@ Paf synth_paf(const SynthParams& p) {
     for (int k = 0; k < n_task; k++) {
         ContigOut& o = outs[(size_t)k];
         const int hap = k / N_CONTIG, c = k % N_CONTIG;
+        if (!((p.contig_mask >> c) & 1u)) continue;
         const uint32_t tid = paf.name_id(CHM13[c].name);
         const uint32_t qid = paf.name_id("hap" + std::to_string(hap + 1) + "#" + CHM13[c].name);
         const uint64_t base = paf.cigar.size();

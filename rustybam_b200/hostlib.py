@@ -21,6 +21,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.rbh_synth_paf.restype = C.c_void_p
     lib.rbh_synth_paf.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_int]
+    lib.rbh_synth_paf_mask.restype = C.c_void_p
+    lib.rbh_synth_paf_mask.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_uint32]
     lib.rbh_paf_from_text.restype = C.c_void_p
     lib.rbh_paf_from_text.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.rbh_paf_view.argtypes = [C.c_void_p, C.POINTER(capi.RbRecords)]
@@ -84,8 +86,15 @@ class HostPaf:
         self.cigar_nbytes = int(self.c.cigar_nbytes)
 
     @staticmethod
-    def synth(seed=20261017, scale=1.0, n_hap=1, threads=8):
-        return HostPaf(load().rbh_synth_paf(seed, scale, n_hap, threads))
+    def synth(seed=20261017, scale=1.0, n_hap=1, threads=8, contigs=None):
+        """contigs: indices into the CHM13-like table (0 = chr1 .. 21 = chr22, 22 = chrX, 23 = chrY, 24 = chrM) to generate; the
+        streams are independent per (haplotype, contig), so a subset equals those records of the full set."""
+        if contigs is None:
+            return HostPaf(load().rbh_synth_paf(seed, scale, n_hap, threads))
+        mask = 0
+        for c in contigs:
+            mask |= 1 << int(c)
+        return HostPaf(load().rbh_synth_paf_mask(seed, scale, n_hap, threads, mask))
 
     @staticmethod
     def from_text(text: bytes):

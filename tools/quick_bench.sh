@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick resident / e2e timing of the C4 workload on the GPU box: tools/quick_bench.sh <tag>
 TAG=${1:-q}
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+python bench.py --only-c4 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 python - <<P
 import json
 d = json.load(open("gpurun_out/${TAG}_bench.json"))
