@@ -764,6 +764,239 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
     }
 }
 
+// K2 for rb_liftover / rb_stats (no boundary resolution): the same samples as k_scan_lift<false>, leaner.
+//   - op words staged with 16-byte stores into a SWIZZLED tile (unit u of chunk row t sits at t*8 + (u ^ (t & 7))): a thread
+//     reads its 32 ops with eight conflict-free 16-byte loads instead of 32 word loads from a 33-word pitch
+//   - chunks without a record head that lie fully inside the op array (all but ~1 in 2 000) take a fully unrolled walk:
+//     no per-op head / end / sub-sample tests, the zero-length / oversized test is one compare
+//   - everything else (scan, look-back, sample layout) is k_scan_lift's
+#ifndef RB_SMP2_MINB
+#define RB_SMP2_MINB 4
+#endif
+template <bool LOCAL>
+__global__ void __launch_bounds__(SMP_THREADS, RB_SMP2_MINB)
+k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
+           Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket) {
+    static_assert(SAMPLE == 32u, "k_samples2 walks 32-op chunks");
+    extern __shared__ __align__(16) uint32_t s_dyn2[];
+    uint4* s_ops4 = reinterpret_cast<uint4*>(s_dyn2);             // SMP_THREADS rows of 8 units
+    uint32_t* s_acc = s_dyn2 + SMP_THREADS * SAMPLE;              // 9 * SMP_THREADS class sums
+    __shared__ SegVal s_warp[SMP_THREADS / 32];
+    __shared__ SegVal s_blk;
+    __shared__ unsigned int s_b;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_ops = *n_ops_dev;
+    if (!LOCAL) {  // look-back order = ticket order
+        if (tid == 0) s_b = atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+    const uint64_t b = LOCAL ? (uint64_t)blockIdx.x : (uint64_t)s_b;
+    const uint64_t op0 = b * (uint64_t)SMP_OPS;
+    if (op0 >= n_ops && !(n_ops == 0 && b == 0)) {  // blocks past the end
+        if (LOCAL && tid == 0) payload_store(&blk_agg[b], seg_identity());
+        return;
+    }
+
+    {   // coalesced 16-byte loads (op0 is a multiple of 8192 ops), swizzled 16-byte stores
+        const uint4* src = reinterpret_cast<const uint4*>(ops + op0);
+#pragma unroll
+        for (int i = 0; i < (int)SAMPLE / 4; i++) {
+            const uint32_t v4 = (uint32_t)i * SMP_THREADS + tid;
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (op0 + (uint64_t)v4 * 4u < n_ops) x = src[v4];  // (the op array has slack behind n_ops: a straddling vector is in bounds)
+            const uint32_t row = v4 >> 3, u = v4 & 7u;
+            s_ops4[row * 8u + (u ^ (row & 7u))] = x;
+        }
+    }
+    __syncthreads();
+
+    const uint64_t chunk = b * SMP_THREADS + tid;
+    const uint64_t first = chunk << SAMPLE_LOG2;
+    int nvalid = 0;
+    if (first < n_ops) nvalid = (n_ops - first) < SAMPLE ? (int)(n_ops - first) : (int)SAMPLE;
+    const uint32_t h = nvalid ? heads[first >> 5] : 0u;  // (first is a multiple of 32: one heads word per chunk)
+    const uint32_t sw = (uint32_t)tid & 7u;
+    const uint4* row = s_ops4 + (uint32_t)tid * 8u;
+    auto op_at = [&](int j) { return reinterpret_cast<const uint32_t*>(&row[((uint32_t)j >> 2) ^ sw])[j & 3]; };
+    uint32_t prev_code = 99u;
+    if (nvalid) {
+        if (tid > 0) prev_code = op_code(s_ops4[(uint32_t)(tid - 1) * 8u + (7u ^ ((uint32_t)(tid - 1) & 7u))].w);
+        else if (first > 0) prev_code = op_code(ops[first - 1]);
+    }
+    SegVal mine = seg_identity();
+    ClassAcc acc;
+    acc.sum = s_acc + tid; acc.stride = SMP_THREADS;
+    acc_reset(acc);
+    uint32_t slowc = 0;
+    auto store_sub = [&](const Ctr& sub, uint32_t k) {
+        uint4* dst = reinterpret_cast<uint4*>(samples + chunk * SUBS + k);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&sub);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    };
+    if (nvalid == (int)SAMPLE && h == 0u) {
+        // ---- the usual chunk: 32 ops of one record ----
+        uint32_t iev = 0, dev = 0, txt = 0, big = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (u && !(u & 1)) {  // ops 8, 16, 24: sub-sample = counters since the chunk start
+                Ctr sub = ctr_zero();
+                acc.iev = iev; acc.dev = dev; acc.txt = txt; acc.big = big;
+                if (big >= ACC_BIG) { for (int t = 0; t < 4 * u; t++) ctr_add_op(sub, op_at(t)); }  // a class sum may have wrapped: exact
+                else acc_flush(acc, sub);
+                sub.aux = 0u;
+                store_sub(sub, (uint32_t)u >> 1);
+            }
+            const uint4 x = row[(uint32_t)u ^ sw];
+            const uint32_t ws[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t w = ws[k], code = op_code(w), n = op_len(w);
+                acc.sum[code * SMP_THREADS] += n;
+                iev += (code == OP_I);
+                dev += (code == OP_D);
+                txt += ndigits32(n) + 1u;
+                big |= n;
+                slowc += ((n - 1u) >= (ACC_BIG - 1u)) | (code == prev_code);  // zero-length, oversized, or the class of the op before
+                prev_code = code;
+            }
+        }
+        acc.iev = iev; acc.dev = dev; acc.txt = txt; acc.big = big;
+        if (big >= ACC_BIG) { for (int j = 0; j < (int)SAMPLE; j++) ctr_add_op(mine.c, op_at(j)); }
+        else acc_flush(acc, mine.c);
+    } else {
+        // ---- a record starts inside the chunk, or the op array ends in it: k_scan_lift's general walk ----
+        for (int j = 0; j < nvalid; j++) {
+            const uint32_t w = op_at(j);
+            const bool head = (h >> j) & 1u;
+            if (head) { acc_reset(acc); slowc = 0; }
+            if (j && (j & (int)(SUB_OPS - 1)) == 0) {
+                Ctr sub = ctr_zero();
+                if (acc.big >= ACC_BIG) {
+                    int j0 = 0;
+                    for (int t = 0; t <= j; t++)
+                        if ((h >> t) & 1u) j0 = t;
+                    for (int t = j0; t < j; t++) ctr_add_op(sub, op_at(t));
+                } else {
+                    acc_flush(acc, sub);
+                }
+                sub.aux = (((h >> 1) & ((1u << j) - 1u)) != 0u) ? SUB_ABS : 0u;
+                store_sub(sub, (uint32_t)(j >> SUB_LOG2));
+            }
+            const uint32_t code = op_code(w);
+            slowc += (op_len(w) == 0u) | (op_len(w) >= ACC_BIG) | ((!head) & (code == prev_code));
+            acc_add_op(acc, w);
+            prev_code = code;
+        }
+        if (acc.big >= ACC_BIG) {
+            int j0 = 0;
+            for (int j = 0; j < nvalid; j++)
+                if ((h >> j) & 1u) j0 = j;
+            for (int j = j0; j < nvalid; j++) ctr_add_op(mine.c, op_at(j));
+        } else {
+            acc_flush(acc, mine.c);
+        }
+    }
+    mine.c.aux = (mine.c.aux & AUX_OVF) | (slowc & AUX_CNT);
+    mine.flag = (h != 0u);
+
+    // block-level segmented scan of the per-chunk aggregates, look-back, absolute samples (as k_scan_lift)
+    SegVal inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SegVal y = seg_shfl(inc, (lane - d) & 31);
+        if (lane >= d) inc = seg_combine(y, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    SegVal exl = seg_shfl(inc, (lane - 1) & 31);
+    if (lane == 0) exl = seg_identity();
+    __syncthreads();
+    SegVal wpre = seg_identity(), btot = seg_identity();
+    if (LOCAL) {
+        // no look-back: the samples stay relative to the block's first op (SUB_ABS in aux: a record starts in between, the
+        // sample is complete), the block's aggregate goes to blk_agg; k_blk_scan + k_smp_fix add the part in front of the block.
+        // (A chain of 64-byte look-backs over ~6 000 blocks per 50 M ops is what used to bound this kernel, not its walk.)
+        for (int k = 0; k < warp; k++) wpre = seg_combine(wpre, s_warp[k]);
+        if (tid == SMP_THREADS - 1) payload_store(&blk_agg[b], seg_combine(wpre, inc));
+        SegVal pre = seg_combine(wpre, exl);
+        if (h & 1u) { pre.c = ctr_zero(); pre.flag = 1u; }  // op 32c starts a record
+        if (nvalid) {
+            pre.c.aux = (pre.c.aux & ~SUB_ABS) | (pre.flag ? SUB_ABS : 0u);
+            samples[chunk * SUBS] = pre.c;
+        }
+        return;
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < SMP_THREADS / 32; k++) btot = seg_combine(btot, s_warp[k]);
+        const SegVal ex = lookback_seg(blk_state, blk_agg, blk_pre, b, btot);
+        if (lane == 0) s_blk = ex;
+    } else {
+        for (int k = 0; k < warp; k++) wpre = seg_combine(wpre, s_warp[k]);
+    }
+    __syncthreads();
+    SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
+    if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
+    if (nvalid) samples[chunk * SUBS] = pre.c;
+}
+
+// segmented exclusive scan of the block aggregates k_samples2<true> left (one block: the array is small — one 64-byte entry
+// per 8192 ops), then every chunk sample that is not complete yet gets its block's prefix added
+__global__ void __launch_bounds__(1024)
+k_blk_scan(const uint64_t* __restrict__ n_ops_dev, const ScanPayload* __restrict__ blk_agg, ScanPayload* __restrict__ blk_pre) {
+    __shared__ SegVal s_w[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_ops = *n_ops_dev;
+    const uint64_t n_blk = (n_ops + SMP_OPS - 1) / SMP_OPS;
+    const uint64_t per = (n_blk + 1023) / 1024;  // consecutive entries per thread
+    const uint64_t lo = (uint64_t)tid * per, hi = (lo + per < n_blk) ? lo + per : n_blk;
+    SegVal mine = seg_identity();
+    for (uint64_t i = lo; i < hi; i++) mine = seg_combine(mine, payload_load(&blk_agg[i]));
+    SegVal inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SegVal y = seg_shfl(inc, (lane - d) & 31);
+        if (lane >= d) inc = seg_combine(y, inc);
+    }
+    if (lane == 31) s_w[warp] = inc;
+    SegVal exl = seg_shfl(inc, (lane - 1) & 31);
+    if (lane == 0) exl = seg_identity();
+    __syncthreads();
+    SegVal wpre = seg_identity();
+    for (int k = 0; k < warp; k++) wpre = seg_combine(wpre, s_w[k]);
+    SegVal run = seg_combine(wpre, exl);
+    for (uint64_t i = lo; i < hi; i++) {
+        payload_store(&blk_pre[i], run);
+        run = seg_combine(run, payload_load(&blk_agg[i]));
+    }
+}
+__global__ void __launch_bounds__(256)
+k_smp_fix(const uint64_t* __restrict__ n_ops_dev, const ScanPayload* __restrict__ blk_pre, Ctr* __restrict__ samples) {
+    const uint64_t chunk = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    const uint64_t n_ops = *n_ops_dev;
+    if ((chunk << SAMPLE_LOG2) >= n_ops) return;
+    uint4* p = reinterpret_cast<uint4*>(samples + chunk * SUBS);
+    uint4 c = p[2];  // words 8..11: IEV DEV TXT aux
+    if (c.w & SUB_ABS) {  // complete already: only the marker goes
+        c.w &= ~SUB_ABS;
+        p[2] = c;
+        return;
+    }
+    const SegVal pre = payload_load(&blk_pre[chunk / SMP_THREADS]);  // (the same 64 bytes for 256 consecutive chunks)
+    Ctr v;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+    const uint4 a = p[0], b2 = p[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b2.x; w[5] = b2.y; w[6] = b2.z; w[7] = b2.w;
+    w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    Ctr r = pre.c;
+    ctr_add(r, v);
+    const uint32_t* o = reinterpret_cast<const uint32_t*>(&r);
+    p[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    p[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    p[2] = make_uint4(o[8], o[9], o[10], o[11]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3  per-record preparation
 // ------------------------------------------------------------------------------------------------
@@ -2297,6 +2530,7 @@ k_whole_text(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ op_o
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+static size_t samples2_smem() { return (size_t)(SMP_THREADS * SAMPLE + 9 * SMP_THREADS) * sizeof(uint32_t); }
 static size_t scan_lift_smem(bool lift) {
     return (size_t)(SMP_THREADS * (SAMPLE + 1) + 9 * SMP_THREADS + (lift ? 2 * SL_WCAP : 0)) * sizeof(uint32_t);
 }
@@ -2304,6 +2538,8 @@ static size_t scan_lift_smem(bool lift) {
 int init_kernel_attrs() {
     cudaError_t e = cudaFuncSetAttribute(k_scan_lift<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(true));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_lift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(false));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
     return e == cudaSuccess ? 0 : -1;
@@ -2342,9 +2578,18 @@ void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev,
     if (lift)
         k_scan_lift<true><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(true), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg,
                                                                                       blk_pre, ticket, la);
-    else
+    else if (getenv("RB_OLD_SAMPLES"))
         k_scan_lift<false><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(false), s>>>(ops, n_ops_dev, heads, samples, blk_state,
                                                                                         blk_agg, blk_pre, ticket, la);
+    else if (!getenv("RB_SAMPLES_LOCAL"))
+        k_samples2<false><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+    else {  // (measured, not faster: 0.24 + 0.06 + 0.07 ms against 0.31 ms at C4) block-local samples + aggregates, a one-block
+            // scan of the aggregates, the prefixes added to the incomplete samples
+        k_samples2<true><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+        k_blk_scan<<<1, 1024, 0, s>>>(n_ops_dev, blk_agg, blk_pre);
+        const uint64_t chunks = (n_ops_bound + SAMPLE - 1) / SAMPLE;
+        k_smp_fix<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(n_ops_dev, blk_pre, samples);
+    }
 }
 void launch_combine(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                     const uint32_t* ops, WinView win, const uint64_t* names_off, const HalfS* hs, const HalfE* he, PairRes* res,
