@@ -61,6 +61,11 @@ typedef enum rb_status {
 /* rb_liftover only: `liftover --qbed` — the windows are in QUERY coordinates; every record swaps query and target
  * (I <-> D, op order reversed on '-' strands; paf.rs:1050-1094) before it is lifted, and is printed swapped */
 #define RB_WANT_QBED 4u
+/* rb_liftover / rb_batch_liftover only: paf_text + line_off hold, instead of the PAF rows, the rows `rb stats --paf` prints for
+ * them (bamstats.rs:239-270; the header line, main.rs:51, is the host's) — i.e. the final output of
+ * `rb liftover --bed .. | rb stats --paf`, formatted on the device (shortest-round-trip f32 digits included): a third of the
+ * bytes of the PAF rows cross PCIe.  Not together with RB_WANT_TEXT. */
+#define RB_WANT_STATS_TEXT 8u
 
 /* PAF records, SoA, n_rec rows in FILE order (src/paf.rs:346-368 PafRecord, columns 1-12 + cg:Z:). */
 typedef struct rb_records {

@@ -18,7 +18,7 @@ RB_ERR_REF_CIGAR_PARSE, RB_ERR_REF_INTEGRITY, RB_ERR_REF_STRIP, RB_ERR_REF_INDEX
 RB_ERR_UNSUPPORTED, RB_ERR_OOM = -8, -9
 REF_PANIC_CODES = (RB_ERR_REF_CIGAR_PARSE, RB_ERR_REF_INTEGRITY, RB_ERR_REF_STRIP, RB_ERR_REF_INDEX)
 POLICY_RIGHTMOST, POLICY_EARLY_EXIT = 0, 1
-WANT_TEXT, WANT_NUMERIC, WANT_QBED = 1, 2, 4
+WANT_TEXT, WANT_NUMERIC, WANT_QBED, WANT_STATS_TEXT = 1, 2, 4, 8
 LIFT_SEARCH, LIFT_STREAM = 0, 1
 
 EXPORTS = [
@@ -243,7 +243,7 @@ class Context:
         out, st = RbLiftOut(), RbStatsOut()
         self._check(self.lib.rb_liftover(self.h, C.byref(recs.c), C.byref(wins.c), policy, want, C.byref(out),
                                          C.byref(st) if stats else None))
-        res = self._collect_lift(out, st if stats else None, want & ~WANT_QBED) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
+        res = self._collect_lift(out, st if stats else None, (want & ~WANT_QBED) | (WANT_TEXT if want & WANT_STATS_TEXT else 0)) if copy else dict(n_out=int(out.n_out), paf_nbytes=int(out.paf_nbytes), n_pairs=int(out.n_pairs))
         self.lib.rb_free_lift_out(self.h, C.byref(out))
         if stats:
             self.lib.rb_free_stats_out(self.h, C.byref(st))
@@ -262,7 +262,7 @@ class Context:
                 return np.zeros(0, dtype=dt)
             return np.ctypeslib.as_array(ptr, shape=(cnt,))
         res = dict(n_out=n, n_pairs=int(out.n_pairs), paf_nbytes=nb)
-        if want & WANT_TEXT:
+        if want & (WANT_TEXT | WANT_STATS_TEXT):
             res["paf_text"], res["line_off"] = view(out.paf_text, nb, np.uint8), view(out.line_off, n + 1, np.uint64)
         if want & WANT_NUMERIC:
             for k in ("q_st", "q_en", "t_st", "t_en", "nmatch", "aln_len"):

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#include "f32_fmt.cuh"
 #include "lift_core.cuh"
 #include "rb_kernels.cuh"
 #include "rec_core.cuh"
@@ -2048,7 +2049,16 @@ struct EmitArgs {
     unsigned int* ticket;
     unsigned long long* totals;  // [0] bytes of text, [1] rows, [2] != 0: the text did not fit, [3] deferred blocks
     ErrSlots err;
+    uint32_t stats_text;         // RB_WANT_STATS_TEXT: the rows `rb stats --paf` prints for the lifted rows instead of the PAF rows
 };
+
+// bamstats.rs:138-142 — the three f32 identities of a row (IEEE mul + div, no contraction), as bit patterns
+__device__ __forceinline__ void identities(const PairRes& pr, uint32_t bits[3]) {
+    const float num = __fmul_rn(100.0f, __uint2float_rn(pr.equal));
+    bits[0] = __float_as_uint(__fdiv_rn(num, __uint2float_rn(pr.equal + pr.diff)));                            // by matches
+    bits[1] = __float_as_uint(__fdiv_rn(num, __uint2float_rn(pr.equal + pr.diff + pr.del_ev + pr.ins_ev)));    // by events
+    bits[2] = __float_as_uint(__fdiv_rn(num, __uint2float_rn(pr.equal + pr.diff + pr.del + pr.ins)));          // by all
+}
 
 // n bytes from a 4-byte aligned shared-memory fragment
 __device__ __forceinline__ uint8_t* put_frag(uint8_t* p, const uint8_t* frag, uint32_t n) {
@@ -2154,6 +2164,7 @@ __device__ __forceinline__ uint32_t lift_pair_fast(const OpsView& v, const RecIn
     return status;
 }
 
+template <bool STATS_TEXT>  // (a template: the f32 digit generation of the stats rows stays out of the PAF instantiation's registers)
 __global__ void __launch_bounds__(SER_LINES, RB_EMIT_MINB)
 k_emit(const __grid_constant__ EmitArgs e) {
     extern __shared__ __align__(16) uint8_t s_emit[];
@@ -2222,7 +2233,17 @@ k_emit(const __grid_constant__ EmitArgs e) {
             const uint32_t ql = (uint32_t)(e.a.names_off[qn + 1] - qo), tl = (uint32_t)(e.a.names_off[tn + 1] - to);
             uint8_t* f = s_frag[lane];
             uint8_t* q = f;
-            if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX) {
+            if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX && STATS_TEXT) {  // bamstats.rs:239-270 (reference block first)
+                if (lane == 0) {         // t_name \t
+                    q = put_bytes(q, e.a.names + to, tl); *q++ = '\t';
+                } else if (lane == 1) {  // \t t_len \t strand \t q_name \t
+                    *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
+                    q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t';
+                } else if (lane == 2) {  // \t q_len \t
+                    *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
+                }
+                s_flen[lane] = (uint32_t)(q - f);
+            } else if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX) {
                 if (lane == 0) {         // q_name \t q_len \t
                     q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
                 } else if (lane == 1) {  // \t strand \t t_name \t t_len \t
@@ -2269,7 +2290,34 @@ k_emit(const __grid_constant__ EmitArgs e) {
         s_buf = s_emit;
         buf_cap = (uint32_t)EMIT_DYN_BYTES;
     }
-    const bool live = len != 0u;
+    bool live = len != 0u;
+    if (!live) { r = 0; w = 0; }
+    else if (!fast) {
+        const uint32_t k = (pl.uniform & PLAN_UNIFORM) ? pl.k0 : rank_of_pair(e.pair_off, e.n_rec, p);
+        r = e.rec_order[k];
+        w = e.a.win.pair_win ? e.a.win.pair_win[p] : (e.a.recs[r].wlo + (uint32_t)(p - e.pair_off[k]));
+    }
+    // RB_WANT_STATS_TEXT: the row is the `rb stats --paf` row of the lifted record — shortest-round-trip digits of the three
+    // identities now (their lengths decide where the rows go), printed when the row is composed
+    uint32_t id_bits[3] = {0u, 0u, 0u};
+    F32Dec id_dec[3];
+    id_dec[0].n = id_dec[1].n = id_dec[2].n = 0;
+    if (STATS_TEXT && live) {
+        const RecInfo& ri = fast ? s_rec : e.a.recs[r];
+        identities(pr, id_bits);
+        uint32_t n = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            id_dec[i] = f32_shortest_fast(id_bits[i]);
+            n += f32_display_len(id_bits[i], id_dec[i]);
+        }
+        uint32_t cst;  // the record's part: both names, t_len, q_len, strand
+        if (fast && s_flen[0] != 0xFFFFFFFFu) cst = s_flen[0] + s_flen[1] + s_flen[2];
+        else cst = (uint32_t)(e.a.names_off[ri.t_name + 1] - e.a.names_off[ri.t_name]) + (uint32_t)(e.a.names_off[ri.q_name + 1] - e.a.names_off[ri.q_name]) +
+                   ndigits64(ri.t_len) + ndigits64(ri.q_len) + 1u + 7u;
+        len = cst + ndigits64(pr.t_st) + ndigits64(pr.t_en) + ndigits64(pr.q_st) + ndigits64(pr.q_en) + n + ndigits32(pr.equal) +
+              ndigits32(pr.diff) + ndigits32(pr.del_ev) + ndigits32(pr.ins_ev) + ndigits32(pr.del) + ndigits32(pr.ins) + 2u + 8u + 1u;
+    }
 
     // ---- block scan of (bytes, rows) ----
     unsigned long long ib = len;
@@ -2293,18 +2341,33 @@ k_emit(const __grid_constant__ EmitArgs e) {
     s_rel[tid] = (uint32_t)rel;
     if (tid == 0) s_rel[SER_LINES] = (uint32_t)tb;
 
-    if (!live) { r = 0; w = 0; }
-    else if (!fast) {
-        const uint32_t k = (pl.uniform & PLAN_UNIFORM) ? pl.k0 : rank_of_pair(e.pair_off, e.n_rec, p);
-        r = e.rec_order[k];
-        w = e.a.win.pair_win ? e.a.win.pair_win[p] : (e.a.recs[r].wlo + (uint32_t)(p - e.pair_off[k]));
-    }
     const bool want_text = e.out_text != nullptr && tb != 0;
     const bool compose_early = want_text && small;  // (block-uniform)
 
     // one line into the staging buffer at `q` — FAST blocks: fragments + staged ops, no global loads
     auto compose = [&](uint8_t* q) {
         const RecInfo& ri = fast ? s_rec : e.a.recs[r];
+        if (STATS_TEXT) {  // bamstats.rs:239-270: reference block, strand, query block, identities, counters
+            if (fast && s_flen[0] != 0xFFFFFFFFu) {
+                q = put_frag(q, s_frag[0], s_flen[0]);
+                q = put_u64(q, pr.t_st); *q++ = '\t'; q = put_u64(q, pr.t_en);
+                q = put_frag(q, s_frag[1], s_flen[1]);
+                q = put_u64(q, pr.q_st); *q++ = '\t'; q = put_u64(q, pr.q_en);
+                q = put_frag(q, s_frag[2], s_flen[2]);
+            } else {
+                q = put_bytes(q, e.a.names + e.a.names_off[ri.t_name], (uint32_t)(e.a.names_off[ri.t_name + 1] - e.a.names_off[ri.t_name]));
+                *q++ = '\t'; q = put_u64(q, pr.t_st); *q++ = '\t'; q = put_u64(q, pr.t_en); *q++ = '\t'; q = put_u64(q, ri.t_len);
+                *q++ = '\t'; *q++ = (ri.flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
+                q = put_bytes(q, e.a.names + e.a.names_off[ri.q_name], (uint32_t)(e.a.names_off[ri.q_name + 1] - e.a.names_off[ri.q_name]));
+                *q++ = '\t'; q = put_u64(q, pr.q_st); *q++ = '\t'; q = put_u64(q, pr.q_en); *q++ = '\t'; q = put_u64(q, ri.q_len); *q++ = '\t';
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++) { q = f32_display_put(q, id_bits[i], id_dec[i]); *q++ = '\t'; }
+            q = put_u32(q, pr.equal); *q++ = '\t'; q = put_u32(q, pr.diff); *q++ = '\t'; q = put_u32(q, pr.del_ev); *q++ = '\t';
+            q = put_u32(q, pr.ins_ev); *q++ = '\t'; q = put_u32(q, pr.del); *q++ = '\t'; q = put_u32(q, pr.ins);
+            *q = '\n';
+            return;
+        }
         if (fast && s_flen[0] != 0xFFFFFFFFu) {
             q = put_frag(q, s_frag[0], s_flen[0]);
             q = put_u64(q, pr.q_st); *q++ = '\t'; q = put_u64(q, pr.q_en);
@@ -2541,7 +2604,8 @@ int init_kernel_attrs() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
     return e == cudaSuccess ? 0 : -1;
 }
 // line_off[i] += delta (multi-device calls: a device learns where its rows start in the merged text after its kernels ran)
@@ -2654,7 +2718,8 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
                  const LiftPlan* plans, PairRes* res, const uint32_t* line_len, uint64_t* line_off, uint64_t* out_idx,
                  uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
                  uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
-                 unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s) {
+                 unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s,
+                 bool stats_text) {
     if (n_pairs == 0) return;
     OpsView view;
     view.ops = ops; view.samples = samples;
@@ -2665,7 +2730,9 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
     e.out_text = out_text; e.cap_text = cap_text; e.out_line_off = out_line_off; e.num = num; e.st = st;
     e.byte_base = byte_base; e.rec_base = rec_base; e.orig_idx = orig_idx;
     e.lb_bytes = lb_bytes; e.lb_rows = lb_rows; e.ticket = ticket; e.totals = totals; e.err = err;
-    k_emit<<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
+    e.stats_text = stats_text ? 1u : 0u;
+    if (stats_text) k_emit<true><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
+    else k_emit<false><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
 }
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s) {

@@ -80,6 +80,7 @@ struct rb_ctx {
     int lift_mode = RB_LIFT_SEARCH;
     bool fused_emit = true;       // line scan + serialiser in one kernel (k_emit) where the rows are short; RB_NO_FUSED_EMIT=1 disables
     bool invert = false;          // the call in progress is a --qbed liftover
+    bool stats_text = false;      // the call in progress wants RB_WANT_STATS_TEXT rows
     std::vector<KEvent> pending;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<rb_kernel_time> times;
@@ -136,6 +137,7 @@ struct rb_batch {
     // outputs (device)
     DevBuf out_text, out_line_off, out_num, out_stats;
     DevBuf blk_flags, emit_totals;  // k_emit: per-block "left to k_serialise" flags, {bytes, rows, overflow, deferred blocks}
+    bool stats_text = false;        // the rows in out_text are `rb stats --paf` rows (RB_WANT_STATS_TEXT)
     uint64_t row_stride = 0;        // rows between the columns of out_num / out_stats (n_out, or the pair count when k_emit wrote them)
     rb_summary sum{};
     bool have_lift = false, have_stats = false, with_stats = false;
@@ -949,7 +951,9 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     CU(b->plans.ensure((P / LIFT_THREADS + 2) * sizeof(LiftPlan)));
     // Short rows (the usual tiling-window call): lift + line scan + serialiser in ONE kernel, k_emit.  Blocks of 128 pairs that
     // belong to one record and fit its staging area are lifted there, out of shared memory (PLAN_FAST); k_lift only sees the rest.
-    const bool fused = ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && b->n_bytes / P <= 1024;
+    const bool stats_text = b->stats_text && (tail == TAIL_SEARCH || tail == TAIL_COMBINE);  // (rows of ~130 bytes whatever the CIGARs are)
+    const bool fused = ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && (stats_text || b->n_bytes / P <= 1024);
+    if (b->stats_text && !fused && P > 0) return fail(ctx, RB_ERR_UNSUPPORTED, "RB_WANT_STATS_TEXT needs the fused emit kernel (rb_liftover / rb_batch_liftover)");
     const bool fast_lift = fused && tail == TAIL_SEARCH && policy == RB_POLICY_RIGHTMOST && !getenv("RB_NO_FAST_LIFT");
     if (tail == TAIL_SEARCH || tail == TAIL_COMBINE) {
         KScope k(ctx, "k_lift_plan");
@@ -989,7 +993,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         CU(b->line_off.ensure((P + 1) * 8 + 64));
         CU(b->out_idx.ensure((P + 1) * 8 + 64));
         if (want & RB_WANT_TEXT) {
-            const uint64_t est = b->n_bytes + P * 160 + 4096;
+            const uint64_t est = stats_text ? P * 220 + 4096 : b->n_bytes + P * 160 + 4096;
             if (b->out_text.cap < est + 64) CU(b->out_text.ensure(est + 64));
             CU(b->out_line_off.ensure((P + 1) * 8 + 64));
         }
@@ -1013,7 +1017,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
                             (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                             (want & RB_WANT_NUMERIC) ? num_view(b, P) : NumDev{}, with_stats ? stats_view(b, P) : StatsDev{}, b->byte_base,
                             b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), lb_bytes, lb_rows, sc + SC_TICKET_LNS,
-                            tot, err, s);
+                            tot, err, s, stats_text);
             }
             Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, tot).u64(6, tot + 1).u64(7, tot + 2).u64(8, tot + 3).go(s);
             CU(cudaStreamSynchronize(s));
@@ -1025,6 +1029,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
             CU(b->out_text.ensure(out_bytes + 64));  // exact now
             CU(cudaMemsetAsync(sc + SC_TICKET_LNS, 0, 4, s));
         }
+        if (deferred && stats_text) return fail(ctx, RB_ERR_UNSUPPORTED, "RB_WANT_STATS_TEXT: a row longer than 2 KB (names of ~1 KB?)");
         if (deferred && (want & RB_WANT_TEXT)) {  // blocks holding a line > 2 KB: warp-per-line path of the serialiser
             KScope k(ctx, "k_serialise");
             launch_serialise(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
@@ -1110,6 +1115,9 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
 int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int with_stats, rb_summary* summary) {
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
+    if ((want & RB_WANT_STATS_TEXT) && (want & RB_WANT_TEXT)) return fail(ctx, RB_ERR_BAD_ARG, "RB_WANT_STATS_TEXT and RB_WANT_TEXT exclude each other");
+    b->stats_text = ctx->stats_text || (want & RB_WANT_STATS_TEXT);
+    if (want & RB_WANT_STATS_TEXT) want = (want & ~RB_WANT_STATS_TEXT) | RB_WANT_TEXT;  // from here on the rows are "the text"
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
@@ -1193,6 +1201,8 @@ int rb_batch_break(rb_ctx* ctx, rb_batch* b, uint32_t max_size, int policy, uint
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown policy %d", policy);
     if (b->wsrc || b->n_win) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_break wants a batch uploaded without windows");
+    if (want & RB_WANT_STATS_TEXT) return fail(ctx, RB_ERR_BAD_ARG, "RB_WANT_STATS_TEXT is an rb_liftover mode");
+    b->stats_text = false;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
@@ -1291,6 +1301,8 @@ static int batch_invert(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_summary* sum
     if (!ctx || !b) return RB_ERR_BAD_ARG;
     if (!b->invert) return fail(ctx, RB_ERR_BAD_ARG, "batch_invert wants a batch uploaded by rb_invert");
     if (b->wsrc || b->n_win) return fail(ctx, RB_ERR_BAD_ARG, "batch_invert wants a batch uploaded without windows");
+    if (want & RB_WANT_STATS_TEXT) return fail(ctx, RB_ERR_BAD_ARG, "RB_WANT_STATS_TEXT is an rb_liftover mode");
+    b->stats_text = false;
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->have_lift = false;
@@ -1361,6 +1373,10 @@ int rb_batch_download_lift(rb_ctx* ctx, rb_batch* b, uint32_t want, rb_lift_out*
     if (!ctx || !b || !out) return RB_ERR_BAD_ARG;
     if (!b->have_lift) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover has not run on this batch");
     if (st && !b->with_stats) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover ran without stats");
+    if (want & RB_WANT_STATS_TEXT) {
+        if (!b->stats_text) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover did not run with RB_WANT_STATS_TEXT");
+        want = (want & ~RB_WANT_STATS_TEXT) | RB_WANT_TEXT;
+    }
     if (want & ~b->want) return fail(ctx, RB_ERR_BAD_ARG, "rb_batch_liftover did not materialise the requested outputs");
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
@@ -1766,6 +1782,13 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         ctx->invert = true;
     }
     want &= ~RB_WANT_QBED;
+    struct StatsTextScope { rb_ctx* c; ~StatsTextScope() { c->stats_text = false; for (rb_ctx* p : c->peers) p->stats_text = false; } } st_scope{ctx};
+    if (want & RB_WANT_STATS_TEXT) {
+        if (want & RB_WANT_TEXT) return fail(ctx, RB_ERR_BAD_ARG, "RB_WANT_STATS_TEXT and RB_WANT_TEXT exclude each other");
+        want = (want & ~RB_WANT_STATS_TEXT) | RB_WANT_TEXT;  // from here on the stats rows are "the text"
+        ctx->stats_text = true;
+        for (rb_ctx* p : ctx->peers) p->stats_text = true;
+    }
     cudaSetDevice(ctx->device);
     if (!ctx->peers.empty() && (policy == RB_POLICY_RIGHTMOST || policy == RB_POLICY_EARLY_EXIT)) {
         const int mrc = liftover_multi(ctx, recs, wins, policy, want, out, stats);
@@ -2273,6 +2296,8 @@ int rb_trim_paf_end(rb_ctx* ctx, int remove_contained, uint32_t want, rb_lift_ou
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
     b->trim_ready = false;
+    if (want & RB_WANT_STATS_TEXT) return fail(ctx, RB_ERR_BAD_ARG, "RB_WANT_STATS_TEXT is an rb_liftover mode");
+    b->stats_text = false;
     const uint32_t n = b->n_rec;
     const uint64_t n_ops = b->trim_n_ops;
     want &= ~RB_WANT_QBED;

@@ -50,6 +50,15 @@ int main(int argc, char** argv) {
                     if (diff < 5) fprintf(stderr, "DIFF bits %08x: oracle %s core %s (to_chars %s)\n", bb, a.c_str(), d.c_str(), c.c_str());
                     diff++;
                 }
+                {   // the device formatter's fast path (96-bit fixed point; k_emit's stats rows) must equal the core
+                    const rb::F32Dec fd = rb::f32_shortest_fast(bb);
+                    uint8_t fb[96];
+                    const std::string g((const char*)fb, (size_t)(rb::f32_display_put(fb, bb, fd) - fb));
+                    if (g != d || g.size() != rb::f32_display_len(bb, fd)) {
+                        if (diff < 5) fprintf(stderr, "DIFF bits %08x: device fast path %s (len %u) core %s\n", bb, g.c_str(), rb::f32_display_len(bb, fd), d.c_str());
+                        diff++;
+                    }
+                }
                 if (rbh::f32_display_fast(v) != d) {  // the host's fast path (to_chars + exact tie test) must equal the core
                     if (diff < 5) fprintf(stderr, "DIFF bits %08x: host fast path %s core %s\n", bb, rbh::f32_display_fast(v).c_str(), d.c_str());
                     diff++;

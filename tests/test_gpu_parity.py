@@ -484,3 +484,59 @@ def test_multi_device_context_equals_single_and_oracle(monkeypatch):
     finally:
         for c in (one, two, three):
             c.close()
+
+
+# ---------------------------------------------------------------- RB_WANT_STATS_TEXT: `rb liftover | rb stats --paf` rows formatted on the device
+def _stats_header():
+    return bamstats.print_cigar_stats_header().encode()
+
+
+@pytest.mark.parametrize("policy", [orc.RIGHTMOST, orc.EARLY_EXIT])
+def test_stats_text_mode_is_liftover_piped_into_stats(policy):
+    """bamstats.rs:225-270 on the rows of liftover.rs:107-167: the device prints the stats TSV rows itself (f32 identities with
+    Rust's shortest-round-trip Display digits) — byte-identical to the oracle's `rb liftover | rb stats --paf`."""
+    ctx = capi.Context(0)
+    try:
+        cases = [(orc.golden_paf(), orc.golden_bed())]
+        for seed in (21, 22, 23, 24):
+            paf_text, contigs = gen.random_paf(seed, n_contigs=3, recs_per_contig=8, max_ops=250, style="eqx" if seed % 2 else "mixed")
+            cases.append((paf_text, gen.tiling_bed(contigs, 30 + seed, with_ids=bool(seed & 2))))
+            cases.append((paf_text, gen.random_bed(seed, contigs, 60)))
+        for paf_text, bed_text in cases:
+            hp = hostlib.HostPaf.from_text(paf_text)
+            wins = hp.windows_from_bed_text(bed_text)
+            want = orc.run_stats(orc.run_liftover(paf_text, bed_text, policy=policy))
+            got = ctx.liftover(hp, wins, policy=policy, want=capi.WANT_STATS_TEXT, stats=True)
+            assert _stats_header() + got["paf_text"] == want
+            assert got["line_off"][-1] == len(got["paf_text"]) and got["n_out"] == want.count(b"\n") - 1
+            # forced slices and the multi-device merge carry the same rows
+            ctx.set_slicing(64)
+            try:
+                assert ctx.liftover(hp, wins, policy=policy, want=capi.WANT_STATS_TEXT, stats=False)["paf_text"] == got["paf_text"]
+            finally:
+                ctx.set_slicing()
+        with pytest.raises(capi.RbError):
+            ctx.liftover(hp, wins, want=capi.WANT_STATS_TEXT | capi.WANT_TEXT)
+    finally:
+        ctx.close()
+
+
+def test_stats_text_identity_edge_values():
+    """Identities that are exact integers, exact ties (round up, not to even), NaN (0 / 0 cannot happen for a lifted row, but
+    100 * 0 / n = 0 does) and long fractions: rows whose CIGARs are built to hit them."""
+    ctx = capi.Context(0)
+    try:
+        lines = []
+        for i, cg in enumerate(["2049=10751X", "1=1X", "10=", "3X", "1=2X", "7=1X1=3I", "1=99999X", "12345=1X", "999=1X2D5="]):
+            t = sum(int(x) for x in __import__("re").findall(r"(\d+)[=XD]", cg))
+            q = sum(int(x) for x in __import__("re").findall(r"(\d+)[=XI]", cg))
+            lines.append(f"q{i}\t{q + 10}\t0\t{q}\t+\tchr1\t20000000\t{i * 200000}\t{i * 200000 + t}\t0\t0\t60\tcg:Z:{cg}\n".encode())
+        paf_text = b"".join(lines)
+        bed_text = b"chr1\t0\t20000000\n"
+        hp = hostlib.HostPaf.from_text(paf_text)
+        got = ctx.liftover(hp, hp.windows_from_bed_text(bed_text), want=capi.WANT_STATS_TEXT, stats=False)
+        want = orc.run_stats(orc.run_liftover(paf_text, bed_text))
+        assert _stats_header() + got["paf_text"] == want
+        assert b"\t16.007813\t" in got["paf_text"] and b"\t100\t" in got["paf_text"] and b"\t0\t0\t0\t0\t3\t" in got["paf_text"]
+    finally:
+        ctx.close()

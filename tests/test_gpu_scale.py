@@ -175,6 +175,21 @@ def test_full_scale_liftover_bytes_equal_oracle_on_contigs(ctx, full, width):
     assert checked > (150_000 if width == 1000 else 1_500)
 
 
+def test_full_scale_stats_text_mode_equals_oracle_on_contigs(ctx, full):
+    # RB_WANT_STATS_TEXT at C4's size: the rows `rb liftover | rb stats --paf` prints, formatted on the device, sliced pipeline
+    wins = full.tiling_windows(1000)
+    res = ctx.liftover(full, wins, want=capi.WANT_STATS_TEXT | capi.WANT_NUMERIC, stats=True)
+    off = res["line_off"].astype(np.int64)
+    assert res["n_out"] > 3_000_000 and off[-1] == len(res["paf_text"]) < 140 * res["n_out"]
+    hdr = bamstats.print_cigar_stats_header().encode()
+    for nm in PARITY_CONTIGS[1:]:
+        tid = full.find_name(nm)
+        (lo, hi), = _record_runs(full, tid)
+        want = orc.bench_pipeline_keep(full.text(lo, hi), full.tiling_bed_text(1000, tid), threads=os.cpu_count() or 8)
+        r0, r1 = _rows_of_records(res, lo, hi)
+        assert hdr + res["paf_text"][off[r0]:off[r1]] == want["stats"], nm
+
+
 def test_full_scale_stats_bytes_equal_oracle_on_contigs(ctx, full):
     # C2: `rb stats --paf` over the whole synthetic PAF; rows of the parity contigs against the oracle's printout
     st = ctx.stats(full)
