@@ -294,16 +294,18 @@ def measure_resident(torch, ctx, stream, flush, paf, wins, steps, warmup, barrie
     return dict(ms=sum(step_ms) / len(step_ms), summ=summ, ktimes=ktimes, n_prof=n_prof, prof_ms=sum(prof_ms) / len(prof_ms))
 
 
-def measure_e2e(ctx, paf, wins, steps, warmup, barrier, stream=None, torch=None, flush=None):
+def measure_e2e(ctx, paf, wins, steps, warmup, barrier, stream=None, torch=None, flush=None, want=None):
     """rb_liftover() with host buffers in / pinned host buffers out, W + K calls.  Timed with CUDA events on the context's stream
     when it has one the bench can see (single device), else by the host clock around the blocking call (multi-device context:
     the call returns when every device's rows have landed in the merged output)."""
     from rustybam_b200 import capi
+    want = capi.WANT_TEXT if want is None else want
+    with_stats = want == capi.WANT_TEXT  # (the stats rows carry the counters as text: no numeric copy beside them)
     t0 = time.perf_counter()
-    r = ctx.liftover(paf, wins, want=capi.WANT_TEXT, stats=True, copy=False)
+    r = ctx.liftover(paf, wins, want=want, stats=with_stats, copy=False)
     first_ms = (time.perf_counter() - t0) * 1e3
     for _ in range(max(0, warmup - 1)):
-        ctx.liftover(paf, wins, want=capi.WANT_TEXT, stats=True, copy=False)
+        ctx.liftover(paf, wins, want=want, stats=with_stats, copy=False)
     barrier()
     ms = []
     for _ in range(steps):
@@ -312,7 +314,7 @@ def measure_e2e(ctx, paf, wins, steps, warmup, barrier, stream=None, torch=None,
         if stream is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            r = ctx.liftover(paf, wins, want=capi.WANT_TEXT, stats=True, copy=False)
+            r = ctx.liftover(paf, wins, want=want, stats=with_stats, copy=False)
             e1.record(stream)
             e1.synchronize()
             ms.append(e0.elapsed_time(e1))
@@ -320,7 +322,7 @@ def measure_e2e(ctx, paf, wins, steps, warmup, barrier, stream=None, torch=None,
             if torch is not None:
                 torch.cuda.synchronize()
             t0 = time.perf_counter()
-            r = ctx.liftover(paf, wins, want=capi.WANT_TEXT, stats=True, copy=False)
+            r = ctx.liftover(paf, wins, want=want, stats=with_stats, copy=False)
             ms.append((time.perf_counter() - t0) * 1e3)
     barrier()
     return dict(ms=sum(ms) / len(ms), first_call_ms=first_ms, n_out=r["n_out"], out_bytes=r["paf_nbytes"], n_pairs=r["n_pairs"])
@@ -425,6 +427,7 @@ def main():
         r4 = measure_resident(torch, ctx, stream, flush, paf4, wins4, max(args.steps, 10), args.warmup, barrier)
         e4 = measure_e2e(ctx, paf4, wins4, max(args.steps, 10), args.warmup, barrier, stream, torch, flush)
         h2d4, d2h4 = copy_bytes(paf4, wins4, ids4, e4["n_out"], e4["out_bytes"])
+        t4 = measure_e2e(ctx, paf4, wins4, max(args.steps, 10), args.warmup, barrier, stream, torch, flush, want=capi.WANT_STATS_TEXT)
         s4 = r4["summ"]
         c4 = {"workload": "C4: rb liftover --bed <1 kb tiling windows> over synthetic HG002-vs-CHM13-scale eqx PAF + per-row rb stats --paf",
               "value": s4["n_out"] / (r4["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r4["ms"], "records": paf4.n_rec, "bed_rows": wins4.n_win,
@@ -432,6 +435,9 @@ def main():
               "cigar_gb_per_s": s4["cigar_bytes"] / (r4["ms"] * 1e-3) / 1e9,
               "e2e": {"value": e4["n_out"] / (e4["ms"] * 1e-3), "unit": UNIT, "ms_per_step": e4["ms"], "first_call_ms": e4["first_call_ms"],
                       "h2d_bytes_per_step": h2d4, "d2h_bytes_per_step": d2h4},
+              # the pipeline's FINAL output (`rb liftover | rb stats --paf` rows, formatted on the device) instead of PAF rows + counters
+              "e2e_stats_text": {"value": t4["n_out"] / (t4["ms"] * 1e-3), "unit": UNIT, "ms_per_step": t4["ms"], "h2d_bytes_per_step": h2d4,
+                                 "d2h_bytes_per_step": int(t4["out_bytes"] + (t4["n_out"] + 1) * 8)},
               "gpu_launches_per_step": int(sum(v[0] for v in r4["ktimes"].values()) // r4["n_prof"]),
               "roofline": roofline_of(r4, wins4.n_win, paf4.n_rec, peak, peak_src)}
         if not args.no_cpu_baseline:  # rows of a few contigs of the full-size call against the CPU oracle, byte for byte
@@ -463,11 +469,16 @@ def main():
     res = measure_resident(torch, ctx, stream, flush, shard, wins, args.steps, args.warmup, barrier)
     # per-rank end to end: every rank lifts its own shard through rb_liftover (host buffers both ways)
     e2e_rank = measure_e2e(ctx, shard, wins, args.steps, args.warmup, barrier, stream, torch, flush)
+    e2e_st = measure_e2e(ctx, shard, wins, args.steps, args.warmup, barrier, stream, torch, flush, want=capi.WANT_STATS_TEXT)
     summ = res["summ"]
     h2d, d2h = copy_bytes(shard, wins, ids_bytes, e2e_rank["n_out"], e2e_rank["out_bytes"])
     tot = torch.tensor([float(summ["n_out"]), float(summ["cigar_bytes"]), float(summ["out_bytes"]), float(summ["n_pairs"]),
                         float(summ["n_ops"]), float(h2d), float(d2h), float(shard.n_rec), float(wins.n_win)], dtype=torch.float64, device="cuda")
-    tmax = torch.tensor([res["ms"], e2e_rank["ms"], e2e_rank["first_call_ms"]], dtype=torch.float64, device="cuda")
+    tmax = torch.tensor([res["ms"], e2e_rank["ms"], e2e_rank["first_call_ms"], e2e_st["ms"]], dtype=torch.float64, device="cuda")
+    st_bytes = torch.tensor([float(e2e_st["out_bytes"] + (e2e_st["n_out"] + 1) * 8)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(st_bytes, op=dist.ReduceOp.SUM)
+    st_bytes = st_bytes.item()
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -493,9 +504,10 @@ def main():
             idsf = pinf.pin(full, fwins)
             mctx = capi.Context(devices=list(range(world)))
             m = measure_e2e(mctx, full, fwins, args.steps, args.warmup, lambda: None, None, torch, None)
+            mst = measure_e2e(mctx, full, fwins, args.steps, args.warmup, lambda: None, None, torch, None, want=capi.WANT_STATS_TEXT)
             hf, df = copy_bytes(full, fwins, idsf, m["n_out"], m["out_bytes"])
             multi = {"ms": m["ms"], "first_call_ms": m["first_call_ms"], "n_out": m["n_out"], "h2d": hf, "d2h": df, "gen_s": gen_full_s,
-                     "records": full.n_rec}
+                     "records": full.n_rec, "st_ms": mst["ms"], "st_d2h": int(mst["out_bytes"] + (mst["n_out"] + 1) * 8)}
             if not args.no_cpu_baseline:  # the merged output of the N-device call against the oracle (first haplotype, a few contigs)
                 import orc
                 subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
@@ -519,6 +531,10 @@ def main():
                        "balanced on CIGAR bytes), per-device uploads / kernels / downloads and the merge into one pinned output are all inside "
                        "the timed region (host clock around the blocking call)") if multi else
                       "rb_liftover() on one device: sliced pipeline, CUDA events on the library's stream around the call"}
+        st_ms = multi["st_ms"] if multi else tmax[3]
+        e2e["stats_text"] = {"value": n_out_total / (st_ms * 1e-3), "ms_per_step": st_ms, "d2h_bytes_per_step": int(multi["st_d2h"] if multi else st_bytes),
+                             "how": "the same call with RB_WANT_STATS_TEXT: the pipeline's final output (`rb liftover | rb stats --paf` rows, formatted on "
+                                    "the device) comes back instead of PAF rows + counters"}
         if multi:
             e2e["per_rank_form"] = {"value": n_out_total / (tmax[1] * 1e-3), "ms_per_step": tmax[1],
                                     "how": "every rank lifts its own contig shard through rb_liftover on its GPU; max over ranks; no merge"}

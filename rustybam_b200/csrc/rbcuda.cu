@@ -1766,6 +1766,351 @@ static int stats_multi(rb_ctx* ctx, const rb_records* recs, rb_stats_out* stats)
     return RB_OK;
 }
 
+// ---- rb_liftover in slices, on one device or several ------------------------------------------------
+// A large call is cut into K runs of records that are consecutive in EMISSION order (liftover.rs:151-164), of about equal
+// CIGAR size; slice k belongs to device k mod D (D = 1: the whole pipeline on one GPU).  Every device (one host thread each)
+// works through its slices in order on a ping-pong pair of work areas and three streams: the UPLOAD stream copies the next
+// slice (its CIGAR text, gathered run by run when the file order is not the emission order, and the window rows of its
+// contigs), the COMPUTE stream runs the kernels, the COPY stream sends the rows of the slice before to the host — so both
+// PCIe directions and the SMs of every GPU are busy at once, and the HBM footprint of the intermediates is bounded by two
+// slices per device.  The rows of all devices land in ONE pinned block in emission order: where slice k's rows go is the sum
+// of the sizes of the slices before it — a host-side wait on the other device threads, which run the slices just before
+// this one at the same time (nothing else is exchanged between the GPUs).  Row tables are laid out with the exact upper bound
+// on rows (host-side binary searches over the sorted windows); the text size is extrapolated from the first slice, and an
+// underestimate — or a window table that turns out to be nested / not in file order — makes the function return 1: the
+// caller then takes the path that sizes everything exactly.
+static int ensure_slice_streams(rb_ctx* ctx) {
+    if (ctx->copy_stream) return RB_OK;
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
+    }
+    return RB_OK;
+}
+
+static int liftover_sliced(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
+                           rb_stats_out* stats) {
+    const uint64_t SLICE_MIN_BYTES = ctx->slice_min_bytes;
+    const int D = 1 + (int)ctx->peers.size();
+    std::vector<uint32_t> ord;  // records in emission order
+    bool identity = true;
+    const bool try_slices = SLICE_MIN_BYTES && !ctx->profiling && recs && wins && wins->n_win && recs->n_rec >= 2 && recs->cigar_off &&
+                            recs->t_id && recs->t_st && recs->t_en && recs->cigar_nbytes >= 2 * SLICE_MIN_BYTES &&
+                            (policy == RB_POLICY_RIGHTMOST || policy == RB_POLICY_EARLY_EXIT) &&
+                            recs->cigar_off[recs->n_rec] == recs->cigar_nbytes && emission_order(recs, ord, identity);
+    if (!try_slices) return 1;
+    const bool trace = getenv("RB_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto T = [&](const char* what, uint32_t k) {
+        if (trace) fprintf(stderr, "[rb_liftover] %8.3f ms  %s %u\n",
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, k);
+    };
+    std::vector<rb_ctx*> cs(1, ctx);
+    cs.insert(cs.end(), ctx->peers.begin(), ctx->peers.end());
+
+    // ---- slice boundaries (record granularity, balanced on CIGAR bytes) and an upper bound on the rows ----
+    const uint32_t n = recs->n_rec;
+    const uint64_t total_bytes = recs->cigar_nbytes;
+    const uint32_t K = (uint32_t)std::min<uint64_t>(8ull * (uint64_t)D, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
+    std::vector<uint32_t> cut(1, 0);  // slice k = records ord[cut[k] .. cut[k+1]) : consecutive in EMISSION order
+    {
+        // the very first slice is half the size of the others: its rows reach the copy engine sooner, yet their download still
+        // covers the production of the next slice; from then on the downloads are the bottleneck
+        const uint64_t unit = total_bytes / (2 * (uint64_t)K - 1);  // sizes 1 : 2 : 2 : ... in units
+        uint64_t acc = 0, target = unit;
+        uint32_t k = 1;
+        for (uint32_t i = 0; i < n && k < K; i++) {
+            const uint32_t r = ord[i];
+            if (recs->cigar_off[r + 1] < recs->cigar_off[r]) break;  // malformed offsets: reported by the upload
+            acc += recs->cigar_off[r + 1] - recs->cigar_off[r];
+            if (acc >= target && i + 1 < n) { cut.push_back(i + 1); k++; target = unit + 2 * unit * (uint64_t)(k - 1); }
+        }
+    }
+    cut.push_back(n);
+    const uint32_t n_slices = (uint32_t)cut.size() - 1;
+    if (n_slices < (uint32_t)D) return 1;  // fewer slices than devices (a few huge records): the exact multi-device path
+    for (rb_ctx* c : cs) {
+        cudaSetDevice(c->device);
+        if (!c->scratch) c->scratch = new rb_batch();
+        rb_ctx* ctx = c;  // (CU reports into this device's context)
+        CU(ensure_slice_streams(c) == RB_OK ? cudaSuccess : cudaErrorUnknown);
+        if (c->scratch->busy) { CU(cudaStreamSynchronize(c->stream)); c->scratch->busy = false; }
+        c->scratch->n_rec = 0; c->scratch->have_lift = c->scratch->have_stats = false;
+        for (int k = 0; k < 2; k++) {
+            if (!c->slice[k]) c->slice[k] = new rb_batch();
+            c->slice[k]->wsrc = c->scratch;
+        }
+        c->invert = cs[0]->invert; c->stats_text = cs[0]->stats_text;
+        c->err.clear(); c->err_rec = UINT64_MAX;
+    }
+    cudaSetDevice(ctx->device);
+    {   // host-side window bookkeeping (contig ranges) once per device; the rows travel with the slices
+        for (rb_ctx* c : cs) {
+            cudaSetDevice(c->device);
+            const int rc = windows_prepare(c, c->scratch, recs, wins);
+            if (rc != RB_OK) { if (c != ctx) ctx->err = c->err; cudaSetDevice(ctx->device); return rc; }
+        }
+        cudaSetDevice(ctx->device);
+    }
+    rb_batch* wb0 = ctx->scratch;
+    uint64_t cap_rows = 0;  // pairs of the unstripped records >= pairs examined >= rows
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t lo = wb0->h_clo[recs->t_id[i]], hi = wb0->h_chi[recs->t_id[i]];
+        const uint64_t* a0 = std::upper_bound(wins->en + lo, wins->en + hi, recs->t_st[i]);   // first en > t_st (en is monotone here)
+        const uint64_t* a1 = std::lower_bound(wins->st + lo, wins->st + hi, recs->t_en[i]);   // first st >= t_en
+        const uint32_t i0 = (uint32_t)(a0 - wins->en), i1 = (uint32_t)(a1 - wins->st);
+        if (i1 > i0) cap_rows += i1 - i0;
+    }
+
+    // ---- state shared by the device threads ----
+    struct Shared {
+        std::mutex m;
+        std::condition_variable cv;
+        std::vector<rb_summary> sum;       // per slice, valid once known[k]
+        std::vector<uint8_t> known;
+        bool abort = false;                // an error, or the estimates do not hold: everybody stops
+        bool fall_back = false;            // ... and the caller takes the exact path
+        int rc = RB_OK;
+        uint64_t err_rec = UINT64_MAX;
+        std::string err;
+        PinnedBlock *blk = nullptr, *sblk = nullptr;
+        uint8_t* base = nullptr;
+        size_t o_text = 64, o_loff = 0, o_num = 0, cap_text = 0;
+    } sh;
+    sh.sum.assign(n_slices, rb_summary{});
+    sh.known.assign(n_slices, 0);
+    memset(out, 0, sizeof *out);
+    if (stats) memset(stats, 0, sizeof *stats);
+
+    auto raise = [&](rb_ctx* c, int code, bool fall_back) {  // first error in record order wins
+        std::lock_guard<std::mutex> lk(sh.m);
+        if (fall_back) sh.fall_back = true;
+        else if (sh.rc == RB_OK || c->err_rec < sh.err_rec) { sh.rc = code; sh.err_rec = c->err_rec; sh.err = c->err; }
+        sh.abort = true;
+        sh.cv.notify_all();
+    };
+
+    auto work = [&](int d) {
+        rb_ctx* c = cs[(size_t)d];
+        cudaSetDevice(c->device);
+        rb_batch* wb = c->scratch;
+        cudaStream_t A = c->stream, B = c->copy_stream, U = c->up_stream;
+        std::vector<uint32_t> mine;  // this device's slices
+        for (uint32_t k = (uint32_t)d; k < n_slices; k += (uint32_t)D) mine.push_back(k);
+        std::vector<uint8_t> contig_up(recs->n_names, 0);
+        std::vector<std::pair<uint32_t, uint32_t>> rows_up;  // uploaded row ranges
+        auto upload_slice_windows = [&](uint32_t k, cudaStream_t st) {  // a slice only needs the window rows of its own contigs
+            for (uint32_t i = cut[k]; i < cut[k + 1]; i++) {
+                const uint32_t t = recs->t_id[ord[i]];
+                if (contig_up[t]) continue;
+                contig_up[t] = 1;
+                const uint32_t lo = wb->h_clo[t], hi = wb->h_chi[t];
+                if (hi <= lo) continue;
+                const int r2 = windows_upload_rows(c, wb, wins, lo, hi, st);
+                if (r2 != RB_OK) return r2;
+                rows_up.emplace_back(lo, hi);
+            }
+            return (int)RB_OK;
+        };
+        auto upload_slice = [&](size_t j) {  // j = position in `mine`
+            const uint32_t k = mine[j];
+            rb_batch* sb = c->slice[j & 1];
+            const RecSel sel{identity ? nullptr : ord.data() + cut[k], cut[k], cut[k + 1] - cut[k]};
+            // on the upload stream, beside the kernels of the slice before; the work area's own previous kernels (two slices
+            // back) must have finished reading its inputs
+            if (j >= 2 && cudaStreamWaitEvent(U, c->ev_done[j & 1], 0) != cudaSuccess) return fail(c, RB_ERR_CUDA, "cudaStreamWaitEvent");
+            int r2 = j ? upload_slice_windows(k, U) : (int)RB_OK;
+            if (r2 != RB_OK) return r2;
+            c->upload_on = U;
+            r2 = upload_cigar(c, sb, recs, sel);
+            if (r2 == RB_OK) r2 = upload_columns(c, sb, recs, sel);
+            c->upload_on = nullptr;
+            sb->wsrc = wb;
+            if (r2 == RB_OK && cudaEventRecord(c->ev_up[j & 1], U) != cudaSuccess) r2 = fail(c, RB_ERR_CUDA, "cudaEventRecord");
+            return r2;
+        };
+        auto run = [&]() -> int {
+            rb_ctx* ctx = c;  // (CU reports into this device's context)
+            if (mine.empty()) return RB_OK;
+            int rc = upload_slice_windows(mine[0], A);
+            if (rc == RB_OK) rc = windows_upload_aux(c, wb, recs, wins, A);
+            if (rc != RB_OK) return rc;
+            CU(cudaEventRecord(c->ev_wfirst, A));
+            rc = upload_slice(0);
+            if (rc != RB_OK) return rc;
+            for (size_t j = 0; j < mine.size(); j++) {
+                const uint32_t k = mine[j];
+                rb_batch* sb = c->slice[j & 1];
+                if (j + 1 < mine.size()) {  // the next slice's host->device copies go in front of this slice's kernels
+                    rc = upload_slice(j + 1);
+                    if (rc != RB_OK) return rc;
+                }
+                CU(cudaStreamWaitEvent(A, c->ev_up[j & 1], 0));                // this slice's inputs have arrived
+                if (j >= 2) CU(cudaStreamWaitEvent(A, c->ev_d2h[j & 1], 0));  // this work area's previous rows have left the device
+                sb->byte_base = 0;
+                rb_summary sm{};
+                rc = rb_batch_liftover(c, sb, policy, want, stats != nullptr, &sm);
+                if (rc != RB_OK) return rc;
+                if (d == 0) T("kernels enqueued (sizes known)", k);
+                CU(cudaEventRecord(c->ev_done[j & 1], A));
+                uint64_t byte_base = 0, row_base = 0;
+                {   // publish this slice's sizes; wait for the slices in front of it (they run on the other devices right now)
+                    std::unique_lock<std::mutex> lk(sh.m);
+                    sh.sum[k] = sm;
+                    sh.known[k] = 1;
+                    sh.cv.notify_all();
+                    sh.cv.wait(lk, [&] {
+                        if (sh.abort) return true;
+                        for (uint32_t q = 0; q < k; q++)
+                            if (!sh.known[q]) return false;
+                        return k == 0 || sh.blk != nullptr;
+                    });
+                    if (sh.abort) return RB_OK;
+                    for (uint32_t q = 0; q < k; q++) { byte_base += sh.sum[q].out_bytes; row_base += sh.sum[q].n_out; }
+                    if (k == 0) {  // sizes of the first slice are known: reserve the pinned output (text size extrapolated, rows bounded)
+                        const uint64_t slice_bytes = sb->n_bytes;
+                        const double scale = slice_bytes ? (double)total_bytes / (double)slice_bytes : 1.0;
+                        const size_t loff_bytes = (want & RB_WANT_TEXT) ? align_up((cap_rows + 1) * 8, 64) : 0;
+                        const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;
+                        size_t text_est = 0;
+                        if (want & RB_WANT_TEXT) {
+                            text_est = (size_t)((double)sm.out_bytes * scale * 1.25) + (size_t)std::min<uint64_t>(4u << 20, total_bytes / 4 + 4096);  // slices differ in their rows-per-byte mix
+                            if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + 4096;  // nothing to extrapolate from
+                        }
+                        const size_t need = 64 + align_up(text_est + 1, 64) + loff_bytes + num_bytes;
+                        cudaSetDevice(cs[0]->device);
+                        PinnedBlock* blk = pinned_get(cs[0], need);
+                        PinnedBlock* sblk = (blk && stats) ? pinned_get(cs[0], (size_t)cap_rows * 40 + 64) : nullptr;
+                        cudaSetDevice(c->device);
+                        if (!blk || (stats && !sblk)) {
+                            if (blk) blk->in_use = false;
+                            sh.rc = fail(cs[0], RB_ERR_OOM, "pinned allocation of %zu bytes failed", need);
+                            sh.err = cs[0]->err;
+                            sh.abort = true;
+                            sh.cv.notify_all();
+                            return RB_OK;
+                        }
+                        sh.base = reinterpret_cast<uint8_t*>(blk->p);
+                        const size_t text_room = (blk->cap - 64 - loff_bytes - num_bytes) / 64 * 64;  // the text gets every byte the block has beyond the tables
+                        sh.cap_text = (want & RB_WANT_TEXT) ? text_room - 64 : 0;
+                        sh.o_loff = 64 + text_room;
+                        sh.o_num = sh.o_loff + loff_bytes;
+                        sh.sblk = sblk;
+                        sh.blk = blk;
+                        sh.cv.notify_all();
+                    }
+                }
+                if (((want & RB_WANT_TEXT) && byte_base + sm.out_bytes > sh.cap_text) || row_base + sm.n_out > cap_rows) {
+                    // the text extrapolation was too small (or the table is not the sorted, non-nested layout the row bound assumes)
+                    if (d == 0) T("text estimate too small: falling back", k);
+                    raise(c, RB_OK, true);
+                    return RB_OK;
+                }
+                // ---- device -> host of this slice on the copy stream ----
+                CU(cudaStreamWaitEvent(B, c->ev_done[j & 1], 0));
+                const uint64_t nk = sm.n_out;
+                uint8_t* base = sh.base;
+                if (want & RB_WANT_TEXT) {
+                    launch_add_u64(sb->out_line_off.as<uint64_t>(), nk, byte_base, B);  // offsets in the caller's concatenated text
+                    if (sm.out_bytes) CU(cudaMemcpyAsync(base + sh.o_text + byte_base, sb->out_text.p, sm.out_bytes, cudaMemcpyDeviceToHost, B));
+                    if (nk) CU(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + sh.o_loff) + row_base, sb->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, B));
+                }
+                if ((want & RB_WANT_NUMERIC) && nk) {
+                    uint64_t* dn = reinterpret_cast<uint64_t*>(base + sh.o_num);
+                    const uint64_t* sp = sb->out_num.as<uint64_t>();
+                    // one strided copy per table: columns are `row_stride` rows apart on the device and cap_rows apart in the pinned block
+                    const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
+                    CU(cudaMemcpy2DAsync(dn + row_base, cap_rows * 8, sp, sk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(dn + 6 * cap_rows);
+                    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * sk);
+                    CU(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, sk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
+                }
+                if (stats && nk) {
+                    uint32_t* ds = reinterpret_cast<uint32_t*>(sh.sblk->p);
+                    const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
+                    CU(cudaMemcpy2DAsync(ds + row_base, cap_rows * 4, sb->out_stats.as<uint32_t>(), sk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
+                }
+                CU(cudaEventRecord(c->ev_d2h[j & 1], B));
+            }
+            if (d == 0) {  // rows no slice of this device needed, then the table check (its verdict is read before the call returns)
+                std::sort(rows_up.begin(), rows_up.end());
+                uint32_t at = 0;
+                for (auto& iv : rows_up) {
+                    if (rc == RB_OK && iv.first > at) rc = windows_upload_rows(c, wb, wins, at, iv.first, U);
+                    at = std::max(at, iv.second);
+                }
+                if (rc == RB_OK && at < wb->n_win) rc = windows_upload_rows(c, wb, wins, at, wb->n_win, U);
+                if (rc == RB_OK && cudaStreamWaitEvent(U, c->ev_wfirst, 0) != cudaSuccess) rc = fail(c, RB_ERR_CUDA, "cudaStreamWaitEvent");
+                if (rc == RB_OK) rc = windows_check(c, wb, recs, U);
+                if (rc == RB_OK) rc = upload_windows_end(c, wb, recs, wins);  // waits for the verdict
+                if (rc != RB_OK) return rc;
+                if (wb->general) {  // nested rows / file order != sorted order: the single-batch path handles those (rare)
+                    T("general window layout: falling back", 0);
+                    raise(c, RB_OK, true);
+                    return RB_OK;
+                }
+            }
+            CU(cudaStreamSynchronize(B));
+            return RB_OK;
+        };
+        const int rc = run();
+        if (rc != RB_OK) raise(c, rc, false);
+        // whatever happened: nothing of this call may still be in flight on this device when the function returns
+        c->upload_on = nullptr;
+        cudaStreamSynchronize(U);
+        cudaStreamSynchronize(A);
+        cudaStreamSynchronize(B);
+        for (int k = 0; k < 2; k++)
+            if (c->slice[k]) c->slice[k]->busy = false;
+        wb->busy = false;
+    };
+    std::vector<std::thread> pool;
+    for (int d = 1; d < D; d++) pool.emplace_back(work, d);
+    work(0);
+    for (auto& th : pool) th.join();
+    cudaSetDevice(ctx->device);
+    for (rb_ctx* p : ctx->peers) p->invert = false;
+    T("all devices drained", n_slices);
+    if (sh.abort) {
+        if (sh.blk) sh.blk->in_use = false;
+        if (sh.sblk) sh.sblk->in_use = false;
+        if (sh.rc != RB_OK) { ctx->err = sh.err; return sh.rc; }
+        return 1;  // the exact path
+    }
+    uint64_t row_base = 0, byte_base = 0, pairs = 0;
+    for (uint32_t k = 0; k < n_slices; k++) { row_base += sh.sum[k].n_out; byte_base += sh.sum[k].out_bytes; pairs += sh.sum[k].n_pairs; }
+    uint8_t* base = sh.base;
+    out->n_out = row_base; out->paf_nbytes = byte_base; out->n_pairs = pairs; out->_owner = sh.blk;
+    if (want & RB_WANT_TEXT) {
+        out->paf_text = base + sh.o_text;
+        out->line_off = reinterpret_cast<uint64_t*>(base + sh.o_loff);
+        out->line_off[row_base] = byte_base;
+        if (row_base == 0) out->line_off[0] = 0;
+        out->paf_text[byte_base] = 0;
+    }
+    if (want & RB_WANT_NUMERIC) {
+        uint64_t* p = reinterpret_cast<uint64_t*>(base + sh.o_num);
+        out->q_st = p; out->q_en = p + cap_rows; out->t_st = p + 2 * cap_rows; out->t_en = p + 3 * cap_rows;
+        out->nmatch = p + 4 * cap_rows; out->aln_len = p + 5 * cap_rows;
+        out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * cap_rows);
+        out->win_idx = out->rec_idx + cap_rows;
+    }
+    if (stats) {
+        uint32_t* p = reinterpret_cast<uint32_t*>(sh.sblk->p);
+        const uint64_t c = cap_rows;
+        stats->n = row_base;
+        stats->equal = p; stats->diff = p + c; stats->ins = p + 2 * c; stats->del = p + 3 * c; stats->ins_events = p + 4 * c;
+        stats->del_events = p + 5 * c; stats->matches = p + 6 * c;
+        stats->id_by_matches = reinterpret_cast<float*>(p + 7 * c); stats->id_by_events = reinterpret_cast<float*>(p + 8 * c);
+        stats->id_by_all = reinterpret_cast<float*>(p + 9 * c);
+        stats->_owner = sh.sblk;
+    }
+    return RB_OK;
+}
+
 int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int policy, uint32_t want, rb_lift_out* out,
                 rb_stats_out* stats) {
     if (!ctx) return RB_ERR_NO_DEVICE;
@@ -1790,291 +2135,16 @@ int rb_liftover(rb_ctx* ctx, const rb_records* recs, const rb_windows* wins, int
         for (rb_ctx* p : ctx->peers) p->stats_text = true;
     }
     cudaSetDevice(ctx->device);
+    {   // large calls: slices dealt round-robin to the context's devices, both PCIe directions and the SMs busy at once
+        const int src = liftover_sliced(ctx, recs, wins, policy, want, out, stats);
+        if (src != 1) return src;  // (1: not sliced — small call, slicing off, or an estimate / window layout that needs the exact path)
+    }
     if (!ctx->peers.empty() && (policy == RB_POLICY_RIGHTMOST || policy == RB_POLICY_EARLY_EXIT)) {
         const int mrc = liftover_multi(ctx, recs, wins, policy, want, out, stats);
         if (mrc != 1) return mrc;  // (1: not spread — too small, or a window layout the single-batch path handles)
     }
     if (!ctx->scratch) ctx->scratch = new rb_batch();
-    rb_batch* wb = ctx->scratch;
-    const uint64_t SLICE_MIN_BYTES = ctx->slice_min_bytes;
-    std::vector<uint32_t> ord;  // records in emission order
-    bool identity = true;
-    const bool try_slices = SLICE_MIN_BYTES && !ctx->profiling && recs && wins && wins->n_win && recs->n_rec >= 2 && recs->cigar_off &&
-                            recs->t_id && recs->t_st && recs->t_en && recs->cigar_nbytes >= 2 * SLICE_MIN_BYTES &&
-                            recs->cigar_off[recs->n_rec] == recs->cigar_nbytes && emission_order(recs, ord, identity);
-    if (!try_slices) return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
-
-    const bool trace = getenv("RB_TRACE") != nullptr;
-    const auto t_begin = std::chrono::steady_clock::now();
-    auto T = [&](const char* what, uint32_t k) {
-        if (trace) fprintf(stderr, "[rb_liftover] %8.3f ms  %s %u\n",
-                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, k);
-    };
-    struct TEv { const char* what; uint32_t k; cudaEvent_t e; };
-    std::vector<TEv> tev;
-    auto TE = [&](const char* what, uint32_t k, cudaStream_t st) {  // device-side timeline (RB_TRACE only)
-        if (!trace) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        tev.push_back(TEv{what, k, e});
-    };
-    cudaStream_t A = ctx->stream;
-    if (!ctx->copy_stream) {
-        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
-        for (int k = 0; k < 2; k++) {
-            CU(cudaEventCreateWithFlags(&ctx->ev_up[k], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->ev_d2h[k], cudaEventDisableTiming));
-        }
-    }
-    cudaStream_t B = ctx->copy_stream, U = ctx->up_stream;
-    if (wb->busy) { CU(cudaStreamSynchronize(A)); wb->busy = false; }
-    wb->n_rec = 0; wb->have_lift = wb->have_stats = false;
-    TE("A start", 0, A);
-    int rc = windows_prepare(ctx, wb, recs, wins);
-    if (rc != RB_OK) return rc;
-
-    // ---- slice boundaries (record granularity, balanced on CIGAR bytes) and an upper bound on the rows ----
-    const uint32_t n = recs->n_rec;
-    const uint64_t total_bytes = recs->cigar_nbytes;
-    const uint32_t K = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
-    std::vector<uint32_t> cut(1, 0);  // slice k = records ord[cut[k] .. cut[k+1]) : consecutive in EMISSION order
-    {
-        // the first slice is half the size of the others: its rows reach the copy engine sooner, yet their download still
-        // covers the production of the second slice; from then on the download is the bottleneck
-        const uint64_t unit = total_bytes / (2 * (uint64_t)K - 1);  // sizes 1 : 2 : 2 : ... in units
-        uint64_t acc = 0, target = unit;
-        uint32_t k = 1;
-        for (uint32_t i = 0; i < n && k < K; i++) {
-            const uint32_t r = ord[i];
-            if (recs->cigar_off[r + 1] < recs->cigar_off[r]) break;  // malformed offsets: reported by the upload
-            acc += recs->cigar_off[r + 1] - recs->cigar_off[r];
-            if (acc >= target && i + 1 < n) { cut.push_back(i + 1); k++; target = unit + 2 * unit * (uint64_t)(k - 1); }
-        }
-    }
-    cut.push_back(n);
-    const uint32_t n_slices = (uint32_t)cut.size() - 1;
-    uint64_t cap_rows = 0;  // pairs of the unstripped records >= pairs examined >= rows
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t lo = wb->h_clo[recs->t_id[i]], hi = wb->h_chi[recs->t_id[i]];
-        const uint64_t* a0 = std::upper_bound(wins->en + lo, wins->en + hi, recs->t_st[i]);   // first en > t_st (en is monotone here)
-        const uint64_t* a1 = std::lower_bound(wins->st + lo, wins->st + hi, recs->t_en[i]);   // first st >= t_en
-        const uint32_t i0 = (uint32_t)(a0 - wins->en), i1 = (uint32_t)(a1 - wins->st);
-        if (i1 > i0) cap_rows += i1 - i0;
-    }
-
-    memset(out, 0, sizeof *out);
-    if (stats) memset(stats, 0, sizeof *stats);
-    PinnedBlock *blk = nullptr, *sblk = nullptr;
-    uint8_t* base = nullptr;
-    size_t o_text = 64, o_loff = 0, o_num = 0, cap_text = 0;
-    uint64_t byte_base = 0, row_base = 0, pairs = 0;
-    auto bail = [&](int code) {
-        ctx->upload_on = nullptr;
-        cudaStreamSynchronize(U);
-        cudaStreamSynchronize(A);
-        cudaStreamSynchronize(B);
-        for (int k = 0; k < 2; k++)
-            if (ctx->slice[k]) ctx->slice[k]->busy = false;
-        wb->busy = false;
-        if (blk) blk->in_use = false;
-        if (sblk) sblk->in_use = false;
-        return code;
-    };
-#define CUB(call)                                                                                          \
-    do {                                                                                                   \
-        cudaError_t e_ = (call);                                                                           \
-        if (e_ != cudaSuccess) {                                                                           \
-            (void)cudaGetLastError();                                                                      \
-            return bail(fail(ctx, e_ == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_))); \
-        }                                                                                                  \
-    } while (0)
-    for (int k = 0; k < 2; k++) {
-        if (!ctx->slice[k]) ctx->slice[k] = new rb_batch();
-        ctx->slice[k]->wsrc = wb;
-    }
-    std::function<int(uint32_t, cudaStream_t)> upload_slice_windows;
-    auto upload_slice = [&](uint32_t k) {
-        rb_batch* sb = ctx->slice[k & 1];
-        // file order == emission order: a plain run of the caller's arrays; else the slice is gathered run by run
-        const RecSel sel{identity ? nullptr : ord.data() + cut[k], cut[k], cut[k + 1] - cut[k]};
-        // on the upload stream, so that the copy runs beside the kernels of the previous slice; the work area's own
-        // previous kernels (slice k-2) must have finished reading its inputs
-        if (k >= 2 && cudaStreamWaitEvent(U, ctx->ev_done[k & 1], 0) != cudaSuccess) return fail(ctx, RB_ERR_CUDA, "cudaStreamWaitEvent");
-        int r2 = k ? upload_slice_windows(k, U) : (int)RB_OK;
-        if (r2 != RB_OK) return r2;
-        ctx->upload_on = U;
-        r2 = upload_cigar(ctx, sb, recs, sel);
-        if (r2 == RB_OK) r2 = upload_columns(ctx, sb, recs, sel);
-        ctx->upload_on = nullptr;
-        sb->wsrc = wb;
-        if (r2 == RB_OK && cudaEventRecord(ctx->ev_up[k & 1], U) != cudaSuccess) r2 = fail(ctx, RB_ERR_CUDA, "cudaEventRecord");
-        return r2;
-    };
-    // Upload order: a slice only needs the window rows of its own contigs, so those travel right in front of its CIGAR
-    // text (first slice: compute stream; later slices: upload stream, beside the kernels of the slice before).  Rows of
-    // contigs no record refers to follow after the last slice, then the check kernel looks at the whole table; its
-    // verdict is read before the call returns (a bad or nested table discards the slices' work).
-    std::vector<uint8_t> contig_up(recs->n_names, 0);
-    std::vector<std::pair<uint32_t, uint32_t>> rows_up;  // uploaded row ranges
-    upload_slice_windows = [&](uint32_t k, cudaStream_t st) {
-        for (uint32_t i = cut[k]; i < cut[k + 1]; i++) {
-            const uint32_t t = recs->t_id[ord[i]];
-            if (contig_up[t]) continue;
-            contig_up[t] = 1;
-            const uint32_t lo = wb->h_clo[t], hi = wb->h_chi[t];
-            if (hi <= lo) continue;
-            const int r2 = windows_upload_rows(ctx, wb, wins, lo, hi, st);
-            if (r2 != RB_OK) return r2;
-            rows_up.emplace_back(lo, hi);
-        }
-        return (int)RB_OK;
-    };
-    rc = upload_slice_windows(0, A);
-    if (rc == RB_OK) rc = windows_upload_aux(ctx, wb, recs, wins, A);
-    if (rc != RB_OK) return bail(rc);
-    if (cudaEventRecord(ctx->ev_wfirst, A) != cudaSuccess) return bail(fail(ctx, RB_ERR_CUDA, "cudaEventRecord"));
-    TE("A first window rows uploaded", 0, A);
-    rc = upload_slice(0);
-    if (rc != RB_OK) return bail(rc);
-    T("uploads of the first slice enqueued", 0);
-    for (uint32_t k = 0; k < n_slices; k++) {
-        rb_batch* sb = ctx->slice[k & 1];
-        if (k + 1 < n_slices) {  // next slice's host->device copies go in front of this slice's kernels
-            rc = upload_slice(k + 1);
-            if (rc != RB_OK) return bail(rc);
-        }
-        T("next upload enqueued", k);
-        TE("U next slice uploaded", k, U);
-        CUB(cudaStreamWaitEvent(A, ctx->ev_up[k & 1], 0));                // this slice's inputs have arrived
-        if (k >= 2) CUB(cudaStreamWaitEvent(A, ctx->ev_d2h[k & 1], 0));  // this work area's previous rows have left the device
-        TE("A kernels may start", k, A);
-        sb->byte_base = byte_base;
-        rb_summary sm{};
-        rc = rb_batch_liftover(ctx, sb, policy, want, stats != nullptr, &sm);
-        if (rc != RB_OK) return bail(rc);
-        T("kernels enqueued (sizes known)", k);
-        CUB(cudaEventRecord(ctx->ev_done[k & 1], A));
-        TE("A kernels done", k, A);
-        if (!blk) {  // sizes of the first slice are known: reserve the pinned output (text size extrapolated, rows bounded)
-            const uint64_t slice_bytes = sb->n_bytes;
-            const double scale = slice_bytes ? (double)total_bytes / (double)slice_bytes : 1.0;
-            const size_t loff_bytes = (want & RB_WANT_TEXT) ? align_up((cap_rows + 1) * 8, 64) : 0;
-            const size_t num_bytes = (want & RB_WANT_NUMERIC) ? align_up(cap_rows * 56, 64) : 0;
-            size_t text_est = 0;
-            if (want & RB_WANT_TEXT) {
-                text_est = (size_t)((double)sm.out_bytes * scale * 1.25) + (size_t)std::min<uint64_t>(4u << 20, total_bytes / 4 + 4096);  // slices differ in their rows-per-byte mix
-                if (sm.n_out == 0) text_est = (size_t)total_bytes + (size_t)cap_rows * 200 + 4096;  // nothing to extrapolate from
-            }
-            const size_t need = 64 + align_up(text_est + 1, 64) + loff_bytes + num_bytes;
-            blk = pinned_get(ctx, need);
-            if (!blk) return bail(fail(ctx, RB_ERR_OOM, "pinned allocation of %zu bytes failed", need));
-            base = reinterpret_cast<uint8_t*>(blk->p);
-            // the text gets every byte the pool block has beyond the fixed-size tables
-            const size_t text_room = (blk->cap - 64 - loff_bytes - num_bytes) / 64 * 64;
-            cap_text = (want & RB_WANT_TEXT) ? text_room - 64 : 0;
-            o_loff = 64 + text_room;
-            o_num = o_loff + loff_bytes;
-            if (stats) {
-                sblk = pinned_get(ctx, (size_t)cap_rows * 40 + 64);
-                if (!sblk) return bail(fail(ctx, RB_ERR_OOM, "pinned allocation of %llu bytes failed", (unsigned long long)(cap_rows * 40)));
-            }
-        }
-        if (((want & RB_WANT_TEXT) && byte_base + sm.out_bytes > cap_text) || row_base + sm.n_out > cap_rows) {
-            // the text extrapolation was too small (or the table is not the sorted, non-nested layout the row bound
-            // assumes): start over as a single batch, which sizes everything exactly
-            T("text estimate too small: falling back", k);
-            bail(RB_OK);
-            blk = sblk = nullptr;
-            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
-        }
-        // ---- device -> host of this slice on the copy stream ----
-        CUB(cudaStreamWaitEvent(B, ctx->ev_done[k & 1], 0));
-        TE("B download starts", k, B);
-        const uint64_t nk = sm.n_out;
-        if (want & RB_WANT_TEXT) {
-            if (sm.out_bytes) CUB(cudaMemcpyAsync(base + o_text + byte_base, sb->out_text.p, sm.out_bytes, cudaMemcpyDeviceToHost, B));
-            if (nk) CUB(cudaMemcpyAsync(reinterpret_cast<uint64_t*>(base + o_loff) + row_base, sb->out_line_off.p, nk * 8, cudaMemcpyDeviceToHost, B));
-        }
-        if ((want & RB_WANT_NUMERIC) && nk) {
-            uint64_t* d = reinterpret_cast<uint64_t*>(base + o_num);
-            const uint64_t* sp = sb->out_num.as<uint64_t>();
-            // one strided copy per table: columns are nk rows apart on the device and cap_rows apart in the pinned block
-            const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
-            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 8, sp, sk * 8, nk * 8, 6, cudaMemcpyDeviceToHost, B));
-            uint32_t* d32 = reinterpret_cast<uint32_t*>(d + 6 * cap_rows);
-            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sp + 6 * sk);
-            CUB(cudaMemcpy2DAsync(d32 + row_base, cap_rows * 4, s32, sk * 4, nk * 4, 2, cudaMemcpyDeviceToHost, B));
-        }
-        if (stats && nk) {
-            uint32_t* d = reinterpret_cast<uint32_t*>(sblk->p);
-            const uint32_t* sp = sb->out_stats.as<uint32_t>();
-            const uint64_t sk = sb->row_stride ? sb->row_stride : nk;
-            CUB(cudaMemcpy2DAsync(d + row_base, cap_rows * 4, sp, sk * 4, nk * 4, 10, cudaMemcpyDeviceToHost, B));
-        }
-        CUB(cudaEventRecord(ctx->ev_d2h[k & 1], B));
-        TE("B download done", k, B);
-        byte_base += sm.out_bytes; row_base += nk; pairs += sm.n_pairs;
-    }
-    T("all slices enqueued", n_slices);
-    {   // rows no slice needed (contigs without records), then the table check; U has seen every other row already
-        std::sort(rows_up.begin(), rows_up.end());
-        uint32_t at = 0;
-        rc = RB_OK;
-        for (auto& iv : rows_up) {
-            if (rc == RB_OK && iv.first > at) rc = windows_upload_rows(ctx, wb, wins, at, iv.first, U);
-            at = std::max(at, iv.second);
-        }
-        if (rc == RB_OK && at < wb->n_win) rc = windows_upload_rows(ctx, wb, wins, at, wb->n_win, U);
-        if (rc == RB_OK && cudaStreamWaitEvent(U, ctx->ev_wfirst, 0) != cudaSuccess) rc = fail(ctx, RB_ERR_CUDA, "cudaStreamWaitEvent");
-        if (rc == RB_OK) rc = windows_check(ctx, wb, recs, U);
-        if (rc == RB_OK) rc = upload_windows_end(ctx, wb, recs, wins);  // waits for the verdict
-        if (rc != RB_OK) return bail(rc);
-        if (wb->general) {  // nested rows / file order != sorted order: the single-batch path handles those (rare)
-            T("general window layout: falling back", 0);
-            bail(RB_OK);
-            blk = sblk = nullptr;
-            return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
-        }
-    }
-    CUB(cudaStreamSynchronize(B));
-#undef CUB
-    T("copy stream drained", n_slices);
-    for (size_t i = 0; i < tev.size(); i++) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, tev[0].e, tev[i].e);
-        fprintf(stderr, "[rb_liftover device] %8.3f ms  %s %u\n", ms, tev[i].what, tev[i].k);
-    }
-    for (auto& t : tev) cudaEventDestroy(t.e);
-    // later work on the compute stream (the next call) must not overwrite rows still being copied: B is idle now
-    out->n_out = row_base; out->paf_nbytes = byte_base; out->n_pairs = pairs; out->_owner = blk;
-    if (want & RB_WANT_TEXT) {
-        out->paf_text = base + o_text;
-        out->line_off = reinterpret_cast<uint64_t*>(base + o_loff);
-        out->line_off[row_base] = byte_base;
-        if (row_base == 0) out->line_off[0] = 0;
-        out->paf_text[byte_base] = 0;
-    }
-    if (want & RB_WANT_NUMERIC) {
-        uint64_t* p = reinterpret_cast<uint64_t*>(base + o_num);
-        out->q_st = p; out->q_en = p + cap_rows; out->t_st = p + 2 * cap_rows; out->t_en = p + 3 * cap_rows;
-        out->nmatch = p + 4 * cap_rows; out->aln_len = p + 5 * cap_rows;
-        out->rec_idx = reinterpret_cast<uint32_t*>(p + 6 * cap_rows);
-        out->win_idx = out->rec_idx + cap_rows;
-    }
-    if (stats) {
-        uint32_t* p = reinterpret_cast<uint32_t*>(sblk->p);
-        const uint64_t c = cap_rows;
-        stats->n = row_base;
-        stats->equal = p; stats->diff = p + c; stats->ins = p + 2 * c; stats->del = p + 3 * c; stats->ins_events = p + 4 * c;
-        stats->del_events = p + 5 * c; stats->matches = p + 6 * c;
-        stats->id_by_matches = reinterpret_cast<float*>(p + 7 * c); stats->id_by_events = reinterpret_cast<float*>(p + 8 * c);
-        stats->id_by_all = reinterpret_cast<float*>(p + 9 * c);
-        stats->_owner = sblk;
-    }
-    return RB_OK;
+    return liftover_unsliced(ctx, recs, wins, policy, want, out, stats, false);
 }
 
 // replaces the `for paf in records { aligned_pairs(); break_paf_on_indels(); println! }` loop of `rb break-paf`

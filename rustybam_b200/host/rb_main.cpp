@@ -2,6 +2,7 @@
 // (src/cli.rs:16-27,49-60,100-115; drivers src/main.rs:50-58,186-214):
 //     rb [-t N] [--gpus G] liftover --bed <BED> [--qbed] [--largest] [PAF|-]  (alias lo, cli.rs visible_aliases; --qbed: inversion on the
 //                                                          GPU; --largest: host filter; --gpus G: spread the records over G B200s)
+//                                                          --stats: print the rows `| rb stats --paf` would print — formatted on the GPU)
 //     rb [-t N] stats --paf [--qbed] [PAF|-]
 //     rb [-t N] break-paf [--max-size N] [PAF|-]        (aliases breakpaf, bp; src/cli.rs:155-165, main.rs:271-281)
 //     rb [-t N] invert [PAF|-]                          (src/cli.rs:89-94, main.rs:176-182)
@@ -32,6 +33,7 @@ int main(int argc, char** argv) {
     int match_score = 1, diff_score = 1, indel_score = 1;  // cli.rs:126-134
     bool remove_contained = false;
     bool is_trim = false;
+    bool stats_rows = false;
     int n_gpus = 1;  // --gpus G (not in the reference): a multi-device rb_ctx, records spread over devices 0 .. G-1
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -49,6 +51,7 @@ int main(int argc, char** argv) {
         else if ((a == "--bed" || a == "-b") && i + 1 < argc) bed = argv[++i];
         else if (a == "--qbed" || a == "-q") qbed = true;
         else if (a == "--largest" || a == "-l") largest = true;
+        else if (a == "--stats") stats_rows = true;  // (not in the reference) liftover: print what `| rb stats --paf` would print
         else if (a == "--paf" || a == "-p") paf_flag = true;
         else if ((a == "--max-size" || a == "-m") && i + 1 < argc) max_size = strtoul(argv[++i], nullptr, 10);
         else if (a == "--policy" && i + 1 < argc) policy = strcmp(argv[++i], "early-exit") == 0 ? RB_POLICY_EARLY_EXIT : RB_POLICY_RIGHTMOST;
@@ -120,7 +123,9 @@ int main(int argc, char** argv) {
             rb_records recs = paf.view();
             rb_windows w = wins.view();
             rb_lift_out out{};
-            const uint32_t want = RB_WANT_TEXT | (largest ? RB_WANT_NUMERIC : 0u) | (qbed ? RB_WANT_QBED : 0u);
+            if (stats_rows && largest) return usage();
+            const uint32_t want = (stats_rows ? RB_WANT_STATS_TEXT : RB_WANT_TEXT) | (largest ? RB_WANT_NUMERIC : 0u) | (qbed ? RB_WANT_QBED : 0u);
+            if (stats_rows) { fputs(rbh::stats_header(false).c_str(), stdout); fflush(stdout); }  // main.rs:51
             rc = rb_liftover(ctx, &recs, &w, policy, want, &out, nullptr);
             if (rc == RB_OK) {
                 if (largest) {  // main.rs:200-208

@@ -472,6 +472,17 @@ def test_multi_device_context_equals_single_and_oracle(monkeypatch):
                 st1, st2 = one.stats(hp), ctx.stats(hp)
                 for k in st1:
                     assert np.array_equal(st1[k], st2[k], equal_nan=True) if k != "n" else st1[k] == st2[k], k
+            # forced slices: dealt round-robin to the devices, rows land in one block in emission order
+            for ctx in (two, three):
+                ctx.set_slicing(64)
+                try:
+                    b = ctx.liftover(hp, wins, want=capi.WANT_TEXT | capi.WANT_NUMERIC, stats=True)
+                    st = ctx.liftover(hp, wins, want=capi.WANT_STATS_TEXT, stats=False)
+                finally:
+                    ctx.set_slicing()
+                assert b["paf_text"] == want and (a["rec_idx"] == b["rec_idx"]).all() and (a["line_off"] == b["line_off"]).all()
+                assert (a["stats"]["equal"] == b["stats"]["equal"]).all()
+                assert bamstats.print_cigar_stats_header().encode() + st["paf_text"] == orc.run_stats(want)
         # a reference panic on one device's share fails the whole call with that record's error
         name, ln = next(iter(contigs.items()))
         bad = paf_text + b"Q\t10\t0\t5\t+\t" + name.encode() + b"\t" + str(ln).encode() + b"\t0\t8\t0\t0\t60\tcg:Z:3D5=\n"
