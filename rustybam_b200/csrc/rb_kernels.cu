@@ -1776,29 +1776,6 @@ __device__ __forceinline__ P put_header(P p, const SerArgs& a, const RecInfo& ri
     return p;
 }
 
-// n bytes of the input CIGAR text -> p (4 source bytes per load: aligned words + funnel shift; the text buffer is padded
-// on both sides, so the over-read of up to 7 bytes stays inside it)
-template <class P>
-__device__ __forceinline__ P put_text(P p, const uint8_t* __restrict__ src, uint32_t n) {
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
-    uint32_t lo = __ldg(w);
-    uint32_t i = 0;
-    for (; i + 4 <= n; i += 4) {
-        const uint32_t hi = __ldg(++w);
-        const uint32_t x = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-        p[i] = (uint8_t)x; p[i + 1] = (uint8_t)(x >> 8); p[i + 2] = (uint8_t)(x >> 16); p[i + 3] = (uint8_t)(x >> 24);
-    }
-    if (i < n) {
-        const uint32_t x = __funnelshift_r(lo, __ldg(++w), sh);
-        p[i] = (uint8_t)x;
-        if (i + 1 < n) p[i + 1] = (uint8_t)(x >> 8);
-        if (i + 2 < n) p[i + 2] = (uint8_t)(x >> 16);
-    }
-    return p + n;
-}
-
 // up to 64 bytes of the input CIGAR text -> p: every load is issued before the first store (the byte stores go through a
 // generic pointer, which keeps the compiler from hoisting loads over them: in put_text's loop every load waits for the
 // stores of the word before it), so the line pays one round trip to L2 instead of one per word
@@ -1822,6 +1799,20 @@ __device__ __forceinline__ P put_text64(P p, const uint8_t* __restrict__ src, ui
         }
     }
     return p + n;
+}
+
+// n bytes of the input CIGAR text -> p, 64 bytes per round: the 17 source words of a round are all requested before its first
+// byte is stored (see put_text64: with one word per iteration every load waited for the stores before it — one trip to L2 per
+// 4 bytes, the reason the 10 kb-window rows, ~430 bytes of untouched ops each, ran at 15 % issue utilisation).  The text buffer
+// is padded on both sides, so the over-read of up to 7 bytes stays inside it.
+template <class P>
+__device__ __forceinline__ P put_text(P p, const uint8_t* __restrict__ src, uint32_t n) {
+    while (n > 64u) {
+        p = put_text64(p, src, 64u);
+        src += 64;
+        n -= 64u;
+    }
+    return put_text64(p, src, n);
 }
 
 // trimmed / early-return CIGAR text, sequential.  Ops the trim leaves untouched are copied from the input text when
