@@ -201,7 +201,8 @@ RB_HD void trim_fixed_candidates(const OpsView& v, const TrimArr& a, const RecIn
         if (cand[i] >= A && cand[i] <= B) trim_best_merge(best, trim_val(v, a, rl, tl, rr, tr, A, cand[i], sc), cand[i]);
 }
 // The arg-max as one 64-bit key for atomicMax across the blocks of a pair: larger total first, then the smaller split point.
-// |total| < 2^31 (the reference sums in i32; the caller refuses overlaps whose sums could leave that range) and
+// |total| < 2^31: total = L[A,c) - R[A,c) is bounded by 2 x overlap x |score|, and k_trim_select refuses pairs with
+// 2 x overlap x max|score| >= 2^31 (the reference's own i32 sums allow half of that) and
 // c - A < 2^32 (per-record query sums are below 2^32).
 RB_HD unsigned long long trim_key(const TrimBest& b, uint64_t A) {
     return ((unsigned long long)(b.total + 2147483648ll) << 32) | (unsigned long long)(~(uint32_t)(b.c - A));

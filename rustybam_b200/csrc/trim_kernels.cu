@@ -151,7 +151,9 @@ k_trim_select(const uint32_t* __restrict__ grp_off, uint32_t n_groups, const Tri
     if (s_cnt) {
         one = trim_sel_make(views, lo, m, s_best);
         if (s_cnt > 1) atomicOr(&info->waiting, 1u);
-        if ((one.en_ovl - one.st_ovl) * max_score >= (1ull << 31)) {  // the reference sums the scores in i32 (trim_overlap.rs:52-69)
+        // the reference sums the scores in i32 (trim_overlap.rs:52-69); the candidate key packs L[A,c) - R[A,c), which can reach
+        // TWICE overlap x score, into 32 bits (trim_core.cuh trim_key): refuse what could leave that range
+        if (2ull * (one.en_ovl - one.st_ovl) * max_score >= (1ull << 31)) {
             if (atomicCAS(&info->status, 0u, TRIM_ST_RANGE) == 0u) { info->err_l = one.left; info->err_r = one.right; }
             one.left = TRIM_SEL_NONE;
         }

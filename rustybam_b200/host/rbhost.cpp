@@ -173,12 +173,40 @@ static inline const char* next_ws(const char* p, const char* e) {
 }
 
 namespace {
+// CigarString::try_from(&[u8]) of rust-htslib as paf.rs:398-399 calls it (.expect -> panic), syntax only: <digits fitting
+// u32><one of MIDNSHP=X> repeated; H only as the first or last op, S only at the ends or separated from them by H only.
+// Kept records get this check on the GPU (k_tokenise, k_rec_ops, k_check_clips); the host runs it only for lines it is
+// about to SKIP because a numeric column does not parse — the reference parses the cg tag first (paf.rs:386-399) and
+// panics on a malformed one before it ever looks at the numbers (paf.rs:401-417).
+bool cigar_syntax_ok(const char* s, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        size_t j = i;
+        unsigned long long v = 0;
+        while (j < n && s[j] >= '0' && s[j] <= '9') {
+            v = v * 10 + (unsigned long long)(s[j] - '0');
+            if (v > 0xFFFFFFFFull) return false;
+            j++;
+        }
+        if (j == i || j >= n) return false;  // no length, or the text ends in a number
+        const char op = s[j];
+        if (!memchr("MIDNSHP=X", op, 9)) return false;
+        if (op == 'H' && i != 0 && j + 1 != n) return false;
+        if (op == 'S' && i != 0 && j + 1 != n && s[i - 1] != 'H') {
+            for (size_t k = j + 1; k < n; k++)
+                if (!((s[k] >= '0' && s[k] <= '9') || s[k] == 'H')) return false;
+        }
+        i = j + 1;
+    }
+    return true;
+}
+
 struct ParsedLine {     // what PafRecord::new extracts from one line (paf.rs:379-430), before name interning
     const char *q_name = nullptr, *t_name = nullptr, *cg = nullptr;
     size_t q_name_n = 0, t_name_n = 0, cg_n = 0;
     uint64_t v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     uint8_t strand = '+';
-    uint8_t state = 0;  // 0 ok, 1 skipped (unparsable numeric column), 2 panic: < 12 columns, 3 panic: bad tag
+    uint8_t state = 0;  // 0 ok, 1 skipped (unparsable numeric column), 2 panic: < 12 columns, 3 panic: bad tag, 4 panic: bad cg on a skipped line
 };
 
 void parse_line(const char* text, size_t i, size_t e, ParsedLine& L) {
@@ -207,7 +235,10 @@ void parse_line(const char* text, size_t i, size_t e, ParsedLine& L) {
     static const int colidx[9] = {1, 2, 3, 6, 7, 8, 9, 10, 11};
     bool ok = true;
     for (int c = 0; c < 9 && ok; c++) ok = parse_u64(t[colidx[c]].first, t[colidx[c]].second, L.v[c]);
-    if (!ok || t[4].second != 1) { L.state = 1; return; }
+    if (!ok || t[4].second != 1) {  // skipped — unless its cg tag is malformed: the reference panics on that first
+        L.state = (L.cg && !cigar_syntax_ok(L.cg, L.cg_n)) ? 4 : 1;
+        return;
+    }
     L.strand = (uint8_t)t[4].first[0];
     L.q_name = t[0].first; L.q_name_n = t[0].second;
     L.t_name = t[5].first; L.t_name_n = t[5].second;
@@ -249,6 +280,7 @@ Paf Paf::from_text(const char* text, size_t n) {
     for (const ParsedLine& L : parsed) {
         if (L.state == 2) throw Panic("assertion failed: t.len() >= 12");
         if (L.state == 3) throw Panic("assertion failed: PAF_TAG.is_match(token)");
+        if (L.state == 4) throw Panic("Unable to parse cigar string.");
         if (L.state == 0) { total_cg += L.cg_n; n_ok++; }
     }
     paf.cigar.resize(total_cg);

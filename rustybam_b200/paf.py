@@ -4,6 +4,7 @@ Text stays on the host: this module only splits columns and packs the cg:Z: payl
 SoA buffers of include/rbcuda.h.  CIGAR tokenising, integrity checks and everything downstream
 run on the GPU behind the C ABI."""
 import gzip
+import re
 
 import numpy as np
 
@@ -33,6 +34,25 @@ def _parse_u64(t: bytes):
     return int(t)
 
 
+_CIGAR_RE = re.compile(rb"(?:[0-9]+[MIDNSHP=X])*\Z")
+
+
+def _cigar_syntax_ok(cg: bytes) -> bool:
+    """rust-htslib CigarString::try_from, syntax only: lengths fit u32; H only first / last; S only at the ends or next to them over H."""
+    if not _CIGAR_RE.match(cg):
+        return False
+    ops = re.findall(rb"([0-9]+)([MIDNSHP=X])", cg)
+    if any(int(n) > 0xFFFFFFFF for n, _ in ops):
+        return False
+    kinds = [o for _, o in ops]
+    for i, o in enumerate(kinds):
+        if o == b"H" and i not in (0, len(kinds) - 1):
+            return False
+        if o == b"S" and i not in (0, len(kinds) - 1) and kinds[i - 1] != b"H" and any(k != b"H" for k in kinds[i + 1:]):
+            return False
+    return True
+
+
 class Paf:
     """Paf::from_file (paf.rs:62-78): parsed columns of every record, CIGAR payloads still text."""
 
@@ -60,6 +80,10 @@ class Paf:
                     cigar = m[1]
             nums = [_parse_u64(t[i]) for i in (1, 2, 3, 6, 7, 8, 9, 10, 11)]
             if any(v is None for v in nums) or len(t[4]) != 1:
+                # the reference parses the cg tag BEFORE the numeric columns (paf.rs:386-399 vs 401-417): a malformed CIGAR on a
+                # line that would be skipped still panics (kept records get this check on the GPU)
+                if cigar and not _cigar_syntax_ok(cigar):
+                    raise ReferencePanic("Unable to parse cigar string.")
                 paf.skipped += 1  # "Unable to parse PAF record. Skipping line" (paf.rs:73)
                 continue
             paf.cols.append((t[0], nums[0], nums[1], nums[2], t[4], t[5], nums[3], nums[4], nums[5], nums[8]))

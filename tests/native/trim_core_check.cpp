@@ -185,6 +185,15 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
                     trim_scan_candidates(view, arr, true, rl, tl, sl, rr, tr, sr, A, B, sc, t, nt, best);
                     trim_scan_candidates(view, arr, false, rl, tl, sl, rr, tr, sr, A, B, sc, t, nt, best);
                 }
+                {   // the key's field limits: totals of +-(2^31 - 1) survive, order by (total, then the smaller c)
+                    const TrimBest ext[4] = {{2147483647ll, A}, {-2147483647ll, A + 5}, {0, A + 4294967295ull}, {-1, A}};
+                    for (const TrimBest& x : ext) {
+                        const TrimBest y = trim_unkey(trim_key(x, A), A);
+                        if (y.total != x.total || y.c != x.c) { n_fail++; fprintf(stderr, "FAIL key extremes\n"); }
+                    }
+                    if (!(trim_key(ext[0], A) > trim_key(ext[2], A) && trim_key(ext[2], A) > trim_key(ext[3], A) &&
+                          trim_key(TrimBest{7, A + 1}, A) > trim_key(TrimBest{7, A + 2}, A))) { n_fail++; fprintf(stderr, "FAIL key order\n"); }
+                }
                 {   // the packed 64-bit key the kernels reduce with atomicMax decodes to the same arg-max
                     const unsigned long long key = trim_key(best, A);
                     TrimBest back = trim_unkey(key, A);

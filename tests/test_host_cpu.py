@@ -31,6 +31,23 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+def test_rust_binding_declares_only_what_the_header_and_library_have():
+    # rust/src/ffi.rs is the binding a maintainer adds to the reference (no Rust toolchain here: checked as text)
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "rbcuda.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(rb_[a-z_0-9]+)\s*\(", hdr))
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (rb_[a-z_0-9]+)", ffi))
+    assert bound and bound <= declared, bound - declared
+    assert {"rb_ctx_create", "rb_liftover", "rb_stats", "rb_free_lift_out", "rb_free_stats_out", "rb_last_error"} <= bound
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in bound:
+        assert hasattr(lib, name), name
+    for const, val in (("RB_WANT_TEXT", 1), ("RB_WANT_NUMERIC", 2), ("RB_WANT_QBED", 4), ("RB_WANT_STATS_TEXT", 8)):
+        assert re.search(rf"#define {const} {val}u", open(os.path.join(ROOT, "include", "rbcuda.h")).read())
+        assert re.search(rf"pub const {const}: u32 = {val};", ffi)
+    assert os.path.exists(os.path.join(ROOT, "rust", "build.rs"))
+
+
 def test_no_device_means_error_not_fallback():
     import torch
     if torch.cuda.is_available():
@@ -69,6 +86,17 @@ def test_paf_parser_mirrors_reference_quirks():
     assert p.cigars == [b"8="]
     with pytest.raises(ReferencePanic):
         Paf.from_text(b"Q 10 2 10 + T 40 12 20 3 9 60 notatag\n")
+    # a line that would be skipped (bad numeric column) still panics when its cg tag is malformed: the reference parses the
+    # CIGAR first (paf.rs:386-399, .expect) and only then the numbers (paf.rs:401-417) — same in the C++ host and the oracle
+    for bad in (b"Q 10 x 10 + T 40 12 20 3 9 60 cg:Z:8=3\n", b"Q 10 x 10 + T 40 12 20 3 9 60 cg:Z:8Z\n", b"Q 10 x 10 + T 40 12 20 3 9 60 cg:Z:3=2H3=\n"):
+        with pytest.raises(ReferencePanic):
+            Paf.from_text(bad)
+        with pytest.raises(hostlib.HostPanic):
+            hostlib.HostPaf.from_text(bad)
+        with pytest.raises(orc.ReferencePanic):
+            orc.run_stats(bad)
+    ok = b"Q 10 x 10 + T 40 12 20 3 9 60 cg:Z:2S6=\n"
+    assert len(Paf.from_text(ok)) == 0 and hostlib.HostPaf.from_text(ok).skipped == 1 and orc.run_stats(ok).count(b"\n") == 1
 
 
 def test_bed_parser_matches_oracle():
