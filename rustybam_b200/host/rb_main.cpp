@@ -116,10 +116,10 @@ int main(int argc, char** argv) {
             }
         } else {
             if (bed.empty()) return usage();
-            std::vector<rbh::Region> rgns = rbh::parse_bed(bed);
+            const std::string bed_text = rbh::read_all(bed);
             rbh::Paf paf = rbh::Paf::from_file(input);
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
-            rbh::Windows wins = rbh::Windows::pack(rgns, paf);
+            rbh::Windows wins = rbh::Windows::pack_text(bed_text.data(), bed_text.size(), paf);  // bed::parse_bed + sort, all host threads
             rb_records recs = paf.view();
             rb_windows w = wins.view();
             rb_lift_out out{};

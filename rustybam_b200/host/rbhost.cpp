@@ -2,6 +2,8 @@
 #include "rbhost.hpp"
 #include "f32_fast.hpp"
 
+#include <cerrno>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -97,10 +99,16 @@ std::string read_all(const std::string& path) {
         return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
     };
     std::string out;
-    if (path == "-") {
-        std::ostringstream ss;
-        ss << std::cin.rdbuf();
-        return ss.str();
+    if (path == "-") {  // read(2) in 8 MiB pieces (std::cin's stream buffer, synchronised with stdio, moves a byte at a time: 25 s for
+                        // the 510 MB `rb liftover` pipes into `rb stats --paf`)
+        std::vector<char> buf(8u << 20);
+        for (;;) {
+            const ssize_t n = ::read(0, buf.data(), buf.size());
+            if (n < 0) { if (errno == EINTR) continue; throw Panic("error reading stdin"); }
+            if (n == 0) break;
+            out.append(buf.data(), (size_t)n);
+        }
+        return out;
     }
     if (ends_with(".bgz")) {  // BGZF (myio.rs:56-60): independent blocks -> inflated on all host threads
         std::string raw = read_plain(path);
@@ -413,6 +421,115 @@ Windows Windows::pack(const std::vector<Region>& rgns, const Paf& paf) {
     if (w.ids.empty()) w.ids.push_back(0);
     return w;
 }
+// parse_bed_text + pack in one pass over the text, without a std::string per row and on all host threads: what `rb liftover`
+// does with a 3-million-row BED (1 kb windows: 74 MB of text) before the GPU sees anything.  Same rows, same bed_row numbers
+// (position among the rows that parse, whether or not their contig occurs in the PAF), same ids as the two-step form.
+Windows Windows::pack_text(const char* text, size_t n, const Paf& paf) {
+    // line starts (a line ends at \n or \r; runs of them separate lines)
+    std::vector<std::pair<size_t, size_t>> lines;
+    for (size_t i = 0; i < n;) {
+        size_t j = i;
+        while (j < n && text[j] != '\n' && text[j] != '\r') {
+            const char* q = (const char*)memchr(text + j, '\n', n - j);
+            const size_t e = q ? (size_t)(q - text) : n;
+            const char* r = (const char*)memchr(text + j, '\r', e - j);
+            j = r ? (size_t)(r - text) : e;
+        }
+        if (j > i && text[i] != '#') lines.emplace_back(i, j);
+        i = j;
+        while (i < n && (text[i] == '\n' || text[i] == '\r')) i++;
+    }
+    auto n_fields = [&](size_t a, size_t b) {
+        size_t c = 1;
+        for (const char* p = text + a; (p = (const char*)memchr(p, '\t', (size_t)(text + b - p))) != nullptr; p++) c++;
+        return c;
+    };
+    const size_t nf0 = lines.empty() ? 0 : n_fields(lines[0].first, lines[0].second);  // the first record fixes the field count
+    struct Row { uint32_t t; uint32_t row; uint64_t st, en; size_t id_at; uint32_t id_n; };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = (unsigned)std::min<size_t>(lines.size() < 50000 ? 1 : hw, std::max<size_t>(1, lines.size()));
+    std::vector<std::vector<Row>> part(nt);
+    std::vector<size_t> parsed(nt, 0);  // rows of the part that parse (present contig or not): they number the BED rows
+    auto work = [&](unsigned t) {
+        const size_t lo = lines.size() * t / nt, hi = lines.size() * (t + 1) / nt;
+        std::vector<Row>& out = part[t];
+        out.reserve(hi - lo);
+        const char* last_name = nullptr;
+        size_t last_n = 0;
+        int64_t last_id = -1;
+        size_t k_parsed = 0;
+        for (size_t li = lo; li < hi; li++) {
+            const size_t a = lines[li].first, b = lines[li].second;
+            size_t f[5][2];
+            size_t nf = 0, p = a;
+            for (;;) {  // the first four fields; the rest only counted
+                const char* tab = (const char*)memchr(text + p, '\t', b - p);
+                const size_t e = tab ? (size_t)(tab - text) : b;
+                if (nf < 4) { f[nf][0] = p; f[nf][1] = e - p; }
+                nf++;
+                if (!tab) break;
+                p = e + 1;
+            }
+            if (nf != nf0 || nf < 3) continue;
+            auto strict = [&](size_t at, size_t len, uint64_t& v) {
+                if (len == 0) return false;
+                uint64_t x = 0;
+                for (size_t k = 0; k < len; k++) {
+                    const char c = text[at + k];
+                    if (c < '0' || c > '9') return false;
+                    const uint64_t d = (uint64_t)(c - '0');
+                    if (x > (UINT64_MAX - d) / 10) return false;
+                    x = x * 10 + d;
+                }
+                v = x;
+                return true;
+            };
+            Row r{};
+            if (!strict(f[1][0], f[1][1], r.st) || !strict(f[2][0], f[2][1], r.en)) continue;
+            r.row = (uint32_t)k_parsed++;  // (relative to the part; rebased below)
+            if (!(last_name && last_n == f[0][1] && memcmp(last_name, text + f[0][0], last_n) == 0)) {
+                last_name = text + f[0][0]; last_n = f[0][1];
+                last_id = paf.find_name(std::string(last_name, last_n));
+            }
+            if (last_id < 0) continue;  // BED rows on contigs absent from the PAF are never visited (liftover.rs:151-164)
+            r.t = (uint32_t)last_id;
+            if (nf > 3) { r.id_at = f[3][0]; r.id_n = (uint32_t)f[3][1]; }
+            out.push_back(r);
+        }
+        parsed[t] = k_parsed;
+    };
+    if (nt <= 1) work(0);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(work, t);
+        for (auto& th : pool) th.join();
+    }
+    std::vector<Row> rows;
+    size_t total = 0, base = 0;
+    for (auto& v : part) total += v.size();
+    rows.reserve(total);
+    for (unsigned t = 0; t < nt; t++) {
+        for (Row r : part[t]) { r.row += (uint32_t)base; rows.push_back(r); }
+        base += parsed[t];
+        std::vector<Row>().swap(part[t]);
+    }
+    auto less = [](const Row& a, const Row& b) { return a.t != b.t ? a.t < b.t : a.st < b.st; };
+    if (!std::is_sorted(rows.begin(), rows.end(), less)) std::stable_sort(rows.begin(), rows.end(), less);
+    Windows w;
+    w.default_ids = nf0 <= 3;
+    w.t_id.reserve(rows.size()); w.st.reserve(rows.size()); w.en.reserve(rows.size()); w.bed_row.reserve(rows.size());
+    if (!w.default_ids) w.ids_off.push_back(0);
+    for (const Row& r : rows) {
+        w.t_id.push_back(r.t); w.st.push_back(r.st); w.en.push_back(r.en); w.bed_row.push_back(r.row);
+        if (!w.default_ids) {
+            w.ids.insert(w.ids.end(), text + r.id_at, text + r.id_at + r.id_n);
+            w.ids_off.push_back(w.ids.size());
+        }
+    }
+    if (w.ids.empty()) w.ids.push_back(0);
+    return w;
+}
+
 rb_windows Windows::view() const {
     rb_windows v{};
     v.n_win = (uint32_t)t_id.size();

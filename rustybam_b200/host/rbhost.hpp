@@ -94,6 +94,7 @@ struct Windows {
     bool default_ids = false;  // every row carries the default id: ids / ids_off stay empty and the GPU formats them
     rb_windows view() const;
     static Windows pack(const std::vector<Region>& rgns, const Paf& paf);
+    static Windows pack_text(const char* bed_text, size_t n, const Paf& paf);  // == pack(parse_bed_text(..), paf), parallel, no per-row strings
 };
 
 // `rb liftover --largest` (main.rs:200-208): rows stably sorted by id, one row per id: the LAST one of maximal target span

@@ -62,6 +62,10 @@ char* rbh_paf_text_of_contig(void* pafv, uint32_t tid, size_t* n, uint64_t* n_re
 
 void* rbh_tiling_windows(void* paf, uint64_t width) { return new Windows(tiling_windows_packed(*static_cast<Paf*>(paf), width)); }
 void* rbh_windows_from_bed_text(void* paf, const char* bed, size_t n) {
+    return new Windows(Windows::pack_text(bed, n, *static_cast<Paf*>(paf)));
+}
+// the two-step form (a Region per row), kept as the statement the fast one is compared with
+void* rbh_windows_from_bed_text_slow(void* paf, const char* bed, size_t n) {
     return new Windows(Windows::pack(parse_bed_text(bed, n), *static_cast<Paf*>(paf)));
 }
 void rbh_windows_view(void* w, rb_windows* out) { *out = static_cast<Windows*>(w)->view(); }

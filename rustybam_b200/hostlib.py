@@ -41,6 +41,8 @@ def load():
     lib.rbh_tiling_windows.argtypes = [C.c_void_p, C.c_uint64]
     lib.rbh_windows_from_bed_text.restype = C.c_void_p
     lib.rbh_windows_from_bed_text.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.rbh_windows_from_bed_text_slow.restype = C.c_void_p
+    lib.rbh_windows_from_bed_text_slow.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.rbh_windows_view.argtypes = [C.c_void_p, C.POINTER(capi.RbWindows)]
     lib.rbh_windows_free.argtypes = [C.c_void_p]
     lib.rbh_tiling_bed_text.restype = C.c_void_p
@@ -140,6 +142,10 @@ class HostPaf:
         pi = (C.c_void_p * 3)(*[c.ctypes.data for c in ids])
         n = C.c_size_t()
         return _take(self.lib.rbh_stats_text(self.h, pc, pi, row0, int(qbed), int(header), C.byref(n)), n)
+
+    def windows_from_bed_text_slow(self, bed: bytes) -> "HostWindows":
+        """The two-step form (one Region with two strings per row, then pack): what windows_from_bed_text must equal."""
+        return HostWindows(self.lib.rbh_windows_from_bed_text_slow(self.h, bed, len(bed)))
 
     def close(self):
         if self.h:

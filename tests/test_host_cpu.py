@@ -117,6 +117,34 @@ def test_window_packing_sorts_and_keeps_bed_rows():
     assert sorted(w.bed_row.tolist()) == list(range(w.n_win))
 
 
+def test_fast_bed_packer_equals_the_two_step_form():
+    """Windows::pack_text (one parallel pass over the BED text, no per-row strings: what `rb liftover` runs on a 3 M-row BED)
+    == Windows::pack(parse_bed_text(..)): rows, bed_row numbers (counted over every row that parses, bed.rs:140-194) and ids."""
+    import ctypes as C
+
+    def arrs(w):
+        n = w.n_win
+        a = [np.ctypeslib.as_array(getattr(w.c, k), shape=(n,)).copy() if n else np.zeros(0) for k in ("t_id", "st", "en", "bed_row")]
+        ids = None
+        if w.c.ids_off:
+            off = np.ctypeslib.as_array(w.c.ids_off, shape=(n + 1,)).copy()
+            ids = (off, bytes(np.ctypeslib.as_array(w.c.ids, shape=(int(off[-1]),))) if off[-1] else b"")
+        return a, ids
+    for seed in range(12):
+        paf_text, contigs = gen.random_paf(seed)
+        hp = hostlib.HostPaf.from_text(paf_text)
+        beds = [gen.random_bed(seed, contigs, 50), gen.random_bed(seed, contigs, 50, with_ids=False), gen.tiling_bed(contigs, 33, with_ids=bool(seed & 1)),
+                b"#c\nchr1\t5\t9\tA\textra\nchr2\t1\t2\tB\textra\nchr3\t1\t2\n", b"chr1\t5\t9\r\nchr1\tx\t9\nchr1\t10\t12\n\n\nchrZ\t1\t2\nchr1\t1\t3\n", b""]
+        for bed_text in beds:
+            (a, i1), (b, i2) = arrs(hp.windows_from_bed_text(bed_text)), arrs(hp.windows_from_bed_text_slow(bed_text))
+            assert all(np.array_equal(x, y) for x, y in zip(a, b))
+            assert (i1 is None) == (i2 is None) and (i1 is None or (np.array_equal(i1[0], i2[0]) and i1[1] == i2[1]))
+    big = hostlib.HostPaf.synth(scale=0.05)
+    bed_text = big.tiling_bed_text(100)  # 1.5 M rows: the threaded path
+    (a, _), (b, _) = arrs(big.windows_from_bed_text(bed_text)), arrs(big.windows_from_bed_text_slow(bed_text))
+    assert len(a[0]) > 1_000_000 and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_fmt_f32_matches_oracle():
     rng = np.random.default_rng(3)
     eq = rng.integers(0, 2**31, 3000, dtype=np.uint64)
