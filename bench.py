@@ -334,19 +334,25 @@ def copy_bytes(paf, wins, ids_bytes, n_out, out_bytes):
     return int(h2d), int(d2h)
 
 
-def roofline_of(res, wins_n, n_rec, peak, peak_src):
+def roofline_of(res, wins_n, n_rec, peak, peak_src, traffic_key):
     alg, whole = algorithmic_bytes(res["summ"], wins_n, n_rec)
     ktimes = res["ktimes"]
     total_k = sum(ms for _, ms in ktimes.values()) or 1.0
+    if "k_emit" in ktimes and "k_lift" in ktimes and ktimes["k_lift"][1] < 0.25 * ktimes["k_emit"][1]:
+        alg.pop("k_lift")  # k_emit lifted (nearly) every block itself: k_lift only saw the few it could not, its formula does not apply
     dom = max((k for k in ktimes if k in alg), key=lambda k: ktimes[k][1])
     launches, ms_sum = ktimes[dom]
     dom_ms = ms_sum / max(launches, 1)
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    # measured DRAM bytes per launch of that kernel (ncu --set full, profiles/traffic.json: one haplotype), scaled to this launch's CIGAR bytes
+    traffic, step_traffic = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get(dom)
+            t = json.load(open(tpath))
+            scale = res["summ"]["cigar_bytes"] / t["cigar_bytes"]
+            traffic = int(t[traffic_key][dom] * scale) if dom in t[traffic_key] else None
+            step_traffic = int(t[traffic_key + "_step_total"] * scale)
         except Exception:
             traffic = None
     return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -357,7 +363,8 @@ def roofline_of(res, wins_n, n_rec, peak, peak_src):
             # the step's compulsory bytes (text in, windows, coordinates, every output byte, stats rows) over the
             # WHOLE resident step — intermediates are not counted
             "whole_step": {"algorithmic_bytes": int(whole), "ms": res["ms"], "achieved": whole / (res["ms"] * 1e-3) / 1e9,
-                           "frac": whole / (res["ms"] * 1e-3) / 1e9 / peak}}
+                           "frac": whole / (res["ms"] * 1e-3) / 1e9 / peak, "dram_traffic": step_traffic,
+                           "traffic_over_algorithmic": (step_traffic / whole) if step_traffic else None}}
 
 
 def main():
@@ -439,7 +446,7 @@ def main():
               "e2e_stats_text": {"value": t4["n_out"] / (t4["ms"] * 1e-3), "unit": UNIT, "ms_per_step": t4["ms"], "h2d_bytes_per_step": h2d4,
                                  "d2h_bytes_per_step": int(t4["out_bytes"] + (t4["n_out"] + 1) * 8)},
               "gpu_launches_per_step": int(sum(v[0] for v in r4["ktimes"].values()) // r4["n_prof"]),
-              "roofline": roofline_of(r4, wins4.n_win, paf4.n_rec, peak, peak_src)}
+              "roofline": roofline_of(r4, wins4.n_win, paf4.n_rec, peak, peak_src, "c4")}
         if not args.no_cpu_baseline:  # rows of a few contigs of the full-size call against the CPU oracle, byte for byte
             import orc
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
@@ -540,7 +547,7 @@ def main():
                                     "how": "every rank lifts its own contig shard through rb_liftover on its GPU; max over ranks; no merge"}
             if "parity_checked_rows" in multi:
                 e2e["parity_checked_rows"] = multi["parity_checked_rows"]
-        roof = roofline_of(res, wins.n_win if world == 1 else int(tot[8] / world), int(tot[7] / world) if world > 1 else shard.n_rec, peak, peak_src)
+        roof = roofline_of(res, wins.n_win if world == 1 else int(tot[8] / world), int(tot[7] / world) if world > 1 else shard.n_rec, peak, peak_src, "w10k")
         line = {
             "metric": METRIC, "value": n_out_total / (tmax[0] * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tmax[0], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -43,7 +43,8 @@ int main(int argc, char** argv) {
     for (int r = 0; r < n_rec; r++) {
         TestRec tr;
         const int style = (int)U(0, 9);
-        const int n_ops = (int)U(1, style == 0 ? 120 : 24);
+        int n_ops = (int)U(1, style == 0 ? 120 : 24);
+        if (U(0, 11) == 0) n_ops *= (int)U(8, 30);  // long records (10 .. 100+ sample chunks): chunk_of's interpolation step and bisection
         std::vector<uint32_t> body;
         auto push = [&](uint32_t code, uint32_t len) { body.push_back((len << 4) | code); };
         if (U(0, 9) == 0) push(OP_H, (uint32_t)U(1, 5));
