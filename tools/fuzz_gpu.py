@@ -12,12 +12,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import gen  # noqa: E402
 import orc  # noqa: E402
-from rustybam_b200 import bamstats, capi, liftover  # noqa: E402
+from rustybam_b200 import bamstats, capi, hostlib, liftover  # noqa: E402
 from rustybam_b200.paf import ReferencePanic  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
+os.environ.setdefault("RB_MULTI_MIN_BYTES", "0")
 ctx = capi.Context(0)
+multi = capi.Context(devices=[0, 0])
 
 
 def both(label, ref_fn, gpu_fn, dump):
@@ -90,6 +92,19 @@ while time.time() < t_end:
         ctx.set_lift_mode(capi.LIFT_SEARCH)
     if lifted != "PANIC" and lifted:
         both(f"stats of lifted seed {seed}", lambda: orc.run_stats(lifted), lambda: bamstats.run_stats(ctx, lifted), dump)
+        # RB_WANT_STATS_TEXT: the device prints those stats rows itself; and the same call on a multi-device context (two
+        # contexts on this GPU), sometimes in forced slices
+        hp = hostlib.HostPaf.from_text(paf_text)
+        hw = hp.windows_from_bed_text(bed_text)
+        hdr = bamstats.print_cigar_stats_header().encode()
+        both(f"stats-text seed {seed}", lambda: orc.run_stats(lifted),
+             lambda: hdr + ctx.liftover(hp, hw, policy=policy, want=capi.WANT_STATS_TEXT, stats=False)["paf_text"], dump)
+        if rng.random() < 0.5:
+            multi.set_slicing(rng.choice([0, 16, 64, 512]))
+            try:
+                both(f"multi-device seed {seed}", lambda: lifted, lambda: multi.liftover(hp, hw, policy=policy, want=capi.WANT_TEXT, stats=True)["paf_text"], dump)
+            finally:
+                multi.set_slicing()
     else:
         panics += 1
     both(f"stats seed {seed}", lambda: orc.run_stats(paf_text), lambda: bamstats.run_stats(ctx, paf_text), dump)
@@ -100,7 +115,8 @@ while time.time() < t_end:
         qlens = {}
         for ln in paf_text.splitlines():
             f = ln.split(b"\t")
-            qlens[f[0].decode()] = int(f[1])
+            if f[1].isdigit():  # (a record broken in column 2 above has no usable query length: its line is skipped anyway)
+                qlens[f[0].decode()] = int(f[1])
         qbed = gen.tiling_bed(qlens, rng.choice([3, 11, 50]))
         dump["in.qbed"] = qbed
         both(f"qbed seed {seed}", lambda: orc.run_liftover(paf_text, qbed, qbed=True, policy=policy, threads=2),
