@@ -2012,6 +2012,8 @@ constexpr int EMIT_ACC_BYTES = 9 * SER_LINES * 4;                               
 constexpr int EMIT_UNI_BYTES = EMIT_SMP_BYTES + EMIT_ACC_BYTES;                   // after the lift: line buffer of a FAST block
 constexpr int EMIT_DYN_BYTES = EMIT_OPS_BYTES + EMIT_UNI_BYTES;                   // (other blocks compose in all of it)
 constexpr uint32_t FRAG_CAP = 96, FRAG_NAME_MAX = 64;
+constexpr int EMIT_MID_BYTES = SER_LINES * 16;  // the descriptors of copy_mids (blocks that do not lift)
+constexpr uint32_t MID_COOP = 96;  // runs of untouched ops at least this long are copied by a warp instead of their line's thread
 static_assert(EMIT_OPS_BYTES % 16 == 0 && EMIT_SMP_BYTES % 16 == 0, "staging areas are 16-byte aligned");
 static_assert(EMIT_UNI_BYTES >= (int)EMIT_LONG + 64, "one round holds at least one line");
 
@@ -2189,14 +2191,54 @@ k_emit(const __grid_constant__ EmitArgs e) {
     OpsView v = e.a.v;
     uint8_t* s_buf;       // line buffer of this block
     uint32_t buf_cap;
+    // Blocks that lift here: the record goes to shared memory and the block-constant pieces of the rows are composed once — no
+    // thread loads names or record fields again.  (The same for uniform blocks that do NOT lift was measured at 10 kb windows:
+    // 16 % slower — without the wait for the staged ops to hide behind, four lanes chasing names hold up the whole block.)
+    const bool uni = fast;  // block-uniform
+    const RecInfo* gr = nullptr;
+    if (uni) {
+        r = e.rec_order[pl.k0];
+        gr = &e.a.recs[r];
+        if (tid < (int)(sizeof(RecInfo) / 16)) reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(gr)[tid];
+    if (warp == 3 && lane < 4) {  // block-constant pieces of the 12 columns (paf.rs:923-943), one lane each
+        const uint32_t qn = gr->q_name, tn = gr->t_name;
+        const uint64_t qo = e.a.names_off[qn], to = e.a.names_off[tn];
+        const uint32_t ql = (uint32_t)(e.a.names_off[qn + 1] - qo), tl = (uint32_t)(e.a.names_off[tn + 1] - to);
+        uint8_t* f = s_frag[lane];
+        uint8_t* q = f;
+        if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX && STATS_TEXT) {  // bamstats.rs:239-270 (reference block first)
+            if (lane == 0) {         // t_name \t
+                q = put_bytes(q, e.a.names + to, tl); *q++ = '\t';
+            } else if (lane == 1) {  // \t t_len \t strand \t q_name \t
+                *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
+                q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t';
+            } else if (lane == 2) {  // \t q_len \t
+                *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
+            }
+            s_flen[lane] = (uint32_t)(q - f);
+        } else if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX) {
+            if (lane == 0) {         // q_name \t q_len \t
+                q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
+            } else if (lane == 1) {  // \t strand \t t_name \t t_len \t
+                *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
+                q = put_bytes(q, e.a.names + to, tl); *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t';
+            } else if (lane == 2) {  // \t mapq \t id:Z:
+                *q++ = '\t'; q = put_u64(q, gr->mapq);
+                *q++ = '\t'; *q++ = 'i'; *q++ = 'd'; *q++ = ':'; *q++ = 'Z'; *q++ = ':';
+            } else {                 // default window id: t_name :
+                q = put_bytes(q, e.a.names + to, tl); *q++ = ':';
+            }
+            s_flen[lane] = (uint32_t)(q - f);
+        } else {
+            s_flen[lane] = 0xFFFFFFFFu;  // long names: the generic header writer
+        }
+    }
+    }
     if (fast) {
-        // ---- stage the block's op run + samples (bulk-copy engine), the record, the header fragments; lift ----
+        // ---- stage the block's op run + samples (bulk-copy engine); lift ----
         uint32_t* s_ops = reinterpret_cast<uint32_t*>(s_emit);
         Ctr* s_smp = reinterpret_cast<Ctr*>(s_emit + EMIT_OPS_BYTES);
         uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_emit + EMIT_OPS_BYTES + EMIT_SMP_BYTES);
-        r = e.rec_order[pl.k0];
-        const RecInfo* gr = &e.a.recs[r];
-        if (tid < (int)(sizeof(RecInfo) / 16)) reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(gr)[tid];
         const uint64_t c_lo = pl.c_lo, c_hi = pl.c_hi;
         const uint64_t op_end = gr->op_end;
         const uint64_t o_lo = c_lo << SAMPLE_LOG2;
@@ -2218,40 +2260,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
         const uint64_t pc = in_range ? p : e.n_pairs - 1;
         w = gr->wlo + (uint32_t)(pc - e.pair_off[pl.k0]);
         w_st = e.a.win.st[w]; w_en = e.a.win.en[w];
-        if (warp == 3 && lane < 4) {  // block-constant pieces of the 12 columns (paf.rs:923-943), one lane each
-            const uint32_t qn = gr->q_name, tn = gr->t_name;
-            const uint64_t qo = e.a.names_off[qn], to = e.a.names_off[tn];
-            const uint32_t ql = (uint32_t)(e.a.names_off[qn + 1] - qo), tl = (uint32_t)(e.a.names_off[tn + 1] - to);
-            uint8_t* f = s_frag[lane];
-            uint8_t* q = f;
-            if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX && STATS_TEXT) {  // bamstats.rs:239-270 (reference block first)
-                if (lane == 0) {         // t_name \t
-                    q = put_bytes(q, e.a.names + to, tl); *q++ = '\t';
-                } else if (lane == 1) {  // \t t_len \t strand \t q_name \t
-                    *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
-                    q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t';
-                } else if (lane == 2) {  // \t q_len \t
-                    *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
-                }
-                s_flen[lane] = (uint32_t)(q - f);
-            } else if (ql <= FRAG_NAME_MAX && tl <= FRAG_NAME_MAX) {
-                if (lane == 0) {         // q_name \t q_len \t
-                    q = put_bytes(q, e.a.names + qo, ql); *q++ = '\t'; q = put_u64(q, gr->q_len); *q++ = '\t';
-                } else if (lane == 1) {  // \t strand \t t_name \t t_len \t
-                    *q++ = '\t'; *q++ = (gr->flags & RF_MINUS) ? '-' : '+'; *q++ = '\t';
-                    q = put_bytes(q, e.a.names + to, tl); *q++ = '\t'; q = put_u64(q, gr->t_len); *q++ = '\t';
-                } else if (lane == 2) {  // \t mapq \t id:Z:
-                    *q++ = '\t'; q = put_u64(q, gr->mapq);
-                    *q++ = '\t'; *q++ = 'i'; *q++ = 'd'; *q++ = ':'; *q++ = 'Z'; *q++ = ':';
-                } else {                 // default window id: t_name :
-                    q = put_bytes(q, e.a.names + to, tl); *q++ = ':';
-                }
-                s_flen[lane] = (uint32_t)(q - f);
-            } else {
-                s_flen[lane] = 0xFFFFFFFFu;  // long names: the generic header writer
-            }
-        }
-        __syncthreads();  // s_rec, the tail ops, the fragments and the mbarrier's initialisation are visible
+        __syncthreads();  // s_rec, the fragments, the tail ops and the mbarrier's initialisation are visible
         mbar_wait(&s_bar, 0);
         const RecInfo& ri = s_rec;
         ClassAcc acc;
@@ -2279,8 +2288,11 @@ k_emit(const __grid_constant__ EmitArgs e) {
             if (len) pr = e.res[p];
         }
         s_buf = s_emit;
-        buf_cap = (uint32_t)EMIT_DYN_BYTES;
+        buf_cap = (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES);
     }
+    // blocks that do not lift keep, behind their line buffer, one descriptor per line: a run of input text its owner left to the
+    // warps (src lo, src hi, dst offset, bytes)
+    uint4* s_mid = reinterpret_cast<uint4*>(s_emit + EMIT_DYN_BYTES - EMIT_MID_BYTES);
     bool live = len != 0u;
     if (!live) { r = 0; w = 0; }
     else if (!fast) {
@@ -2294,7 +2306,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
     F32Dec id_dec[3];
     id_dec[0].n = id_dec[1].n = id_dec[2].n = 0;
     if (STATS_TEXT && live) {
-        const RecInfo& ri = fast ? s_rec : e.a.recs[r];
+        const RecInfo& ri = uni ? s_rec : e.a.recs[r];
         identities(pr, id_bits);
         uint32_t n = 0;
 #pragma unroll
@@ -2303,7 +2315,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
             n += f32_display_len(id_bits[i], id_dec[i]);
         }
         uint32_t cst;  // the record's part: both names, t_len, q_len, strand
-        if (fast && s_flen[0] != 0xFFFFFFFFu) cst = s_flen[0] + s_flen[1] + s_flen[2];
+        if (uni && s_flen[0] != 0xFFFFFFFFu) cst = s_flen[0] + s_flen[1] + s_flen[2];
         else cst = (uint32_t)(e.a.names_off[ri.t_name + 1] - e.a.names_off[ri.t_name]) + (uint32_t)(e.a.names_off[ri.q_name + 1] - e.a.names_off[ri.q_name]) +
                    ndigits64(ri.t_len) + ndigits64(ri.q_len) + 1u + 7u;
         len = cst + ndigits64(pr.t_st) + ndigits64(pr.t_en) + ndigits64(pr.q_st) + ndigits64(pr.q_en) + n + ndigits32(pr.equal) +
@@ -2337,9 +2349,9 @@ k_emit(const __grid_constant__ EmitArgs e) {
 
     // one line into the staging buffer at `q` — FAST blocks: fragments + staged ops, no global loads
     auto compose = [&](uint8_t* q) {
-        const RecInfo& ri = fast ? s_rec : e.a.recs[r];
+        const RecInfo& ri = uni ? s_rec : e.a.recs[r];
         if (STATS_TEXT) {  // bamstats.rs:239-270: reference block, strand, query block, identities, counters
-            if (fast && s_flen[0] != 0xFFFFFFFFu) {
+            if (uni && s_flen[0] != 0xFFFFFFFFu) {
                 q = put_frag(q, s_frag[0], s_flen[0]);
                 q = put_u64(q, pr.t_st); *q++ = '\t'; q = put_u64(q, pr.t_en);
                 q = put_frag(q, s_frag[1], s_flen[1]);
@@ -2359,7 +2371,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
             *q = '\n';
             return;
         }
-        if (fast && s_flen[0] != 0xFFFFFFFFu) {
+        if (uni && s_flen[0] != 0xFFFFFFFFu) {
             q = put_frag(q, s_frag[0], s_flen[0]);
             q = put_u64(q, pr.q_st); *q++ = '\t'; q = put_u64(q, pr.q_en);
             q = put_frag(q, s_frag[1], s_flen[1]);
@@ -2394,12 +2406,54 @@ k_emit(const __grid_constant__ EmitArgs e) {
                 }
                 q = put_op(q, pr.e_len, op_code(run[n_mid]));
             }
+        } else if (!fast && (ri.flags & RF_CANON) && pr.mid_len >= MID_COOP &&
+                   (pr.kind == PK_EARLY || (pr.kind == PK_TRIM && pr.ei > pr.si && !(ri.flags & RF_SLOW)))) {
+            // a long run of untouched ops (wide windows: ~430 bytes per row at 10 kb): the owner writes what it formats itself
+            // and leaves the run to the block's warps (copy_mids below): coalesced loads of the input text by 32 lanes per
+            // row instead of one lane walking it — and every thread of the block has work while the round is composed
+            if (pr.kind == PK_TRIM) q = put_op(q, pr.s_len, op_code(v.op(pr.si)));
+            s_mid[tid] = make_uint4((uint32_t)pr.mid_off, (uint32_t)(pr.mid_off >> 32), (uint32_t)(q - (s_buf + 16)), pr.mid_len);
+            q += pr.mid_len;
+            if (pr.kind == PK_TRIM) q = put_op(q, pr.e_len, op_code(v.op(pr.ei)));
         } else {
             SerArgs a2 = e.a;
             a2.v = v;
             q = put_cigar_seq(q, a2, ri, pr);
         }
         *q = '\n';
+    };
+    // the runs the owners of lines [a, b) left behind: a warp per line, 4 bytes per lane and step, destination-aligned
+    // shared-memory words assembled from two aligned words of the text (the buffer is padded: over-reads of < 8 bytes are fine)
+    auto copy_mids = [&](uint32_t a, uint32_t b) {
+        for (uint32_t L = a + (uint32_t)warp; L < b; L += SER_LINES / 32) {
+            const uint4 d = s_mid[L];
+            if (d.w == 0u) continue;
+            const uint8_t* src = e.a.text + (((uint64_t)d.y << 32) | d.x);
+            uint8_t* dst = s_buf + 16 + d.z;
+            const uint32_t n = d.w;
+            const uint32_t head = (4u - (smem_u32(dst) & 3u)) & 3u;  // (n >= MID_COOP > 3)
+            if ((uint32_t)lane < head) dst[lane] = __ldg(src + lane);
+            const uint32_t nw = (n - head) >> 2, rem = (n - head) & 3u;
+            const uint8_t* sb = src + head;
+            const uint32_t sh = (uint32_t)((uintptr_t)sb & 3u) * 8u;
+            const uint32_t* w0 = reinterpret_cast<const uint32_t*>((uintptr_t)sb & ~(uintptr_t)3);
+            uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+            for (uint32_t j0 = 0; j0 < nw; j0 += 128) {  // 4 words per lane and step, every load requested before the first store
+                uint32_t lo[4], hi[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t j = j0 + (uint32_t)u * 32u + (uint32_t)lane;
+                    lo[u] = (j < nw) ? __ldg(w0 + j) : 0u;
+                    hi[u] = (j < nw) ? __ldg(w0 + j + 1) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t j = j0 + (uint32_t)u * 32u + (uint32_t)lane;
+                    if (j < nw) dw[j] = __funnelshift_r(lo[u], hi[u], sh);
+                }
+            }
+            if ((uint32_t)lane < rem) dst[head + nw * 4u + lane] = __ldg(sb + nw * 4u + lane);
+        }
     };
     // lines [cur_line, end_line) fit the buffer (whole lines; 8 bytes of slack on either side for the re-aligning copy)
     auto round_end = [&](uint32_t cur_line) {
@@ -2418,9 +2472,14 @@ k_emit(const __grid_constant__ EmitArgs e) {
     // finished lifting: this is what keeps the wait short)
     if (tid == 0) lb_publish(e.lb_bytes, blk, tb);
     if (tid == 32) lb_publish(e.lb_rows, blk, (unsigned long long)tc);
+    if (!fast) s_mid[tid].w = 0u;
     if (compose_early) {
         end_line = round_end(0);
         if (live && (uint32_t)tid < end_line) compose(s_buf + 16 + (uint32_t)rel);
+        if (!fast) {  // (block-uniform)
+            __syncthreads();
+            copy_mids(0, end_line);
+        }
     }
     if (warp == 0) {
         const unsigned long long ex = lb_walk(e.lb_bytes, blk, tb);
@@ -2477,8 +2536,13 @@ k_emit(const __grid_constant__ EmitArgs e) {
         if (cur_line >= nlines) break;
         __syncthreads();  // the buffer is written again
         end_line = round_end(cur_line);
+        if (!fast) s_mid[tid].w = 0u;
         if (live && (uint32_t)tid >= cur_line && (uint32_t)tid < end_line) compose(s_buf + 16 + ((uint32_t)rel - s_rel[cur_line]));
         __syncthreads();
+        if (!fast) {  // (block-uniform)
+            copy_mids(cur_line, end_line);
+            __syncthreads();
+        }
     }
 }
 
