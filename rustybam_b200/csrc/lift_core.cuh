@@ -47,7 +47,7 @@ struct OpsView {
         Ctr e = ent(c, s);
         if (s == 0) return e;
         const bool abs = (e.aux & SUB_ABS) != 0;
-        e.aux = 0;
+        e.aux = abs ? (e.aux & ~SUB_ABS) : 0u;  // absolute entries of k_tok_scan carry the overflow bit and the slow-op count themselves
         if (!abs) ctr_add(e, ent(c, 0));
         return e;
     }
@@ -103,7 +103,10 @@ RB_HD uint64_t chunk_of(const OpsView& v, const RecInfo& r, uint32_t p) {
     }
     // (An interpolation step in front of this bisection — guess the chunk from the position's share of the record's span, bracket,
     // then 3 probes — was measured and made k_lift 38 % SLOWER at 10 kb windows: the upper levels of the bisection are the same
-    // for every pair of a record and hit L1, only the last few probes travel; the guess costs a 64-bit division and four loads.)
+    // for every pair of a record and hit L1, only the last few probes travel; the guess costs a 64-bit division and four loads.
+    // Staging just the T word of every chunk a wide-window block spans (4 B per 32 ops) and bisecting in shared memory changed nothing
+    // either, 1.04 against 1.02 ms at 8 haplotypes x 10 kb: what the pairs wait for is the chunk's entries, its ops and the
+    // neighbours the slide rules look at — one or two dependent trips each — not the bisection.)
     while (lo < hi) {  // largest chunk whose starting T is <= p (chunk `lo` always qualifies)
         const uint64_t mid = (lo + hi + 1) >> 1;
         if (v.smp_T(mid) <= p) lo = mid;

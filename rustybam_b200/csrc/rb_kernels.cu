@@ -227,7 +227,7 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
     __shared__ unsigned int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_lut[tid] = (uint8_t)code_of_char((uint32_t)tid);
+    if (tid < 256) s_lut[tid] = (uint8_t)code_of_char((uint32_t)tid);
     if (tid == 0) {
         s_tile = atomicAdd(ticket, 1u);
         mbar_init(&s_bar, 1);
@@ -940,6 +940,252 @@ k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_
     SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
     if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
     if (nvalid) samples[chunk * SUBS] = pre.c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K2 fused: tokeniser + sampled segmented scan in ONE pass over the text (rb_liftover / rb_stats / rb trim-paf /
+// rb break-paf; not --qbed / rb invert, whose op order changes after tokenising).  The op words never travel back from
+// HBM to be summed: a tile's ops are decoded into shared memory, eight-op groups ALIGNED TO THE GLOBAL OP INDEX (the first
+// look-back — op counts — has given the tile's base by then) are summed by one thread each, a block-level segmented scan +
+// a second decoupled look-back (64-byte counter payload, the one k_samples uses) turns the sums into the record-relative
+// prefix at every 8th op, and those go straight into `samples` — entry k >> 3 of the array is the prefix in front of op k.
+// Sub-samples written here are ABSOLUTE (SUB_ABS set; lift_core.cuh reads both forms).
+// Record heads come from a table built by k_rec_heads: the byte position of every record's first op character and, per
+// tile, the first record whose first op lies in it.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t TS_NONE = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256)
+k_rec_heads(const uint8_t* __restrict__ text, const uint64_t* __restrict__ cigar_off, uint32_t n_rec, uint64_t* __restrict__ head_pos,
+            uint32_t* tile_first) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const uint64_t c = cigar_off[r], e = cigar_off[r + 1];
+    uint64_t hp = ~0ull;
+    // first op character of the record (a length has <= 10 digits; longer digit runs are parse errors the tokeniser reports)
+    const uint64_t lim = (e - c > 16u) ? c + 16u : e;
+    for (uint64_t p = c; p < lim; p++)
+        if (((uint32_t)text[p] - 48u) >= 10u) { hp = p; break; }
+    head_pos[r] = hp;
+    if (hp != ~0ull) atomicMin(&tile_first[hp / TOK_TILE], r);
+}
+
+#ifndef RB_TOKSCAN_MINB
+#define RB_TOKSCAN_MINB 4
+#endif
+__global__ void __launch_bounds__(TOK_THREADS, RB_TOKSCAN_MINB)
+k_tok_scan(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigned long long* tile_state, unsigned int* ticket,
+           ErrSlots err, uint32_t* misc_flags, const uint32_t* __restrict__ tile_first, const uint64_t* __restrict__ head_pos,
+           uint32_t n_rec, Ctr* __restrict__ samples, uint32_t* seg_state, ScanPayload* seg_agg, ScanPayload* seg_pre) {
+    __shared__ __align__(16) uint8_t s_text[16 + TOK_TILE + 16];
+    __shared__ uint16_t s_pos[TOK_TILE / 2];
+    __shared__ uint32_t s_opw[TOK_TILE / 2];
+    __shared__ uint32_t s_head[TOK_TILE / 64 + 1];  // bit j: tile-local op j is the first op of a record
+    __shared__ uint16_t s_excl[TOK_THREADS], s_m16[TOK_THREADS];
+    __shared__ uint8_t s_lut[256];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_warp[TOK_THREADS / 32];
+    __shared__ SegVal s_wagg[TOK_THREADS / 32];
+    __shared__ SegVal s_blk;
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_tile;
+    __shared__ uint32_t s_prev0;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) s_lut[tid] = (uint8_t)code_of_char((uint32_t)tid);
+    if (tid < TOK_TILE / 64 + 1) s_head[tid] = 0u;
+    if (tid == 0) {
+        s_tile = atomicAdd(ticket, 1u);
+        mbar_init(&s_bar, 1);
+        s_prev0 = 99u;
+    }
+    __syncthreads();
+    const uint64_t tile = s_tile;
+    const uint64_t tbase = tile * (uint64_t)TOK_TILE;
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar, 16 + TOK_TILE);
+        bulk_g2s(s_text, text + tbase - 16, 16 + TOK_TILE, &s_bar);  // text[-16..0) is 0xFF padding
+    }
+    uint32_t r_first = TS_NONE;
+    if (warp == TOK_THREADS / 32 - 1) r_first = tile_first[tile];  // (in flight while the tile arrives)
+    mbar_wait(&s_bar, 0);
+
+    const uint4 c = *reinterpret_cast<const uint4*>(s_text + 16 + tid * 16);
+    const uint32_t M = 0x01020408u;  // gathers the low bit of each byte into a nibble
+    const uint32_t m16 = ((((nondigit_bytes(c.x) >> 7) * M) >> 24) & 0xFu) | (((((nondigit_bytes(c.y) >> 7) * M) >> 24) & 0xFu) << 4) |
+                         (((((nondigit_bytes(c.z) >> 7) * M) >> 24) & 0xFu) << 8) | (((((nondigit_bytes(c.w) >> 7) * M) >> 24) & 0xFu) << 12);
+    const uint32_t cnt = __popc(m16);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    s_m16[tid] = (uint16_t)m16;
+    __syncthreads();
+    uint32_t wpre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < TOK_THREADS / 32; w++) {
+        const uint32_t t = s_warp[w];
+        if (w < warp) wpre += t;
+        total += t;
+    }
+    if (warp == 0) {
+        const unsigned long long ex = lookback_u64(tile_state, tile, total);
+        if (lane == 0) s_base = ex;
+    }
+    {
+        uint32_t mm = m16, k = 0;
+        const uint32_t idx = wpre + inc - cnt;
+        s_excl[tid] = (uint16_t)idx;
+        while (mm) {
+            const uint32_t j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            s_pos[idx + k] = (uint16_t)(tid * 16 + j);
+            k++;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = s_base;
+    if (r_first != TS_NONE) {  // (last warp only) records whose first op lies in this tile -> head bits
+        const uint64_t tend = tbase + TOK_TILE;
+        for (uint64_t r = (uint64_t)r_first + lane; r < n_rec; r += 32) {
+            const uint64_t hp = head_pos[r];
+            if (hp == ~0ull) continue;  // empty CIGAR
+            if (hp >= tend) break;
+            const uint32_t bpos = (uint32_t)(hp - tbase), t = bpos >> 4;
+            const uint32_t j = (uint32_t)s_excl[t] + __popc((uint32_t)s_m16[t] & ((1u << (bpos & 15u)) - 1u));
+            atomicOr(&s_head[j >> 5], 1u << (j & 31u));
+        }
+    }
+    {
+        const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_text);
+        uint32_t seen_codes = 0;                            // bit c set: an op of code c was seen
+        uint32_t* out_ops = ops + base;
+        for (uint32_t q = tid; q < total; q += TOK_THREADS) {
+            const uint32_t e = s_pos[q];                    // op character at tile byte e
+            const uint32_t a = (e + 8) >> 2, sh = ((e + 8) & 3) * 8;
+            const uint32_t w0 = s_w[a], w1 = s_w[a + 1], w2 = s_w[a + 2];
+            uint32_t lo = __funnelshift_r(w0, w1, sh);      // bytes e-8 .. e-5
+            uint32_t hi = __funnelshift_r(w1, w2, sh);      // bytes e-4 .. e-1
+            uint32_t nd;                                    // digits right before e (capped at 8)
+            if (q > 0) {
+                nd = e - s_pos[q - 1] - 1u;                 // everything between two op characters is digits
+                nd = nd > 8u ? 8u : nd;
+            } else {                                        // first op of the tile: the run may reach into the halo
+                const uint32_t nh = nondigit_bytes(hi), nl = nondigit_bytes(lo);
+                nd = nh ? (__clz(nh) >> 3) : (4u + (nl ? (__clz(nl) >> 3) : 4u));
+                // the op character in front of that run (the previous tile's last op): the same-class test of op 0 needs it
+                int p = 16 + (int)e - 1;
+                while (p >= 0 && ((uint32_t)s_text[p] - 48u) < 10u) p--;
+                s_prev0 = (p >= 0) ? (uint32_t)s_lut[s_text[p]] : 99u;
+            }
+            const uint32_t code = s_lut[s_text[16 + e]];
+            uint32_t len;
+            if (nd - 1u >= 7u || code == 15u) {             // rare: empty length, >= 8 digits, bad op character
+                uint32_t ecode = RE_CIGAR_PARSE;
+                len = 0;
+                if (code == 15u || !exact_len(text, tbase + e, len, ecode)) { report(err.tok, tbase + e, ecode); len = 0; }
+            } else {
+                const unsigned long long x = (((unsigned long long)hi << 32) | lo) & (~0ull << (8u * (8u - nd)));
+                len = parse4((uint32_t)(x >> 32));
+                if (nd > 4u) len += parse4((uint32_t)x) * 10000u;
+            }
+            seen_codes |= 1u << code;
+            const uint32_t word = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
+            out_ops[q] = word;
+            s_opw[q] = word;
+        }
+        const uint32_t seen_clip = seen_codes & ((1u << OP_S) | (1u << OP_H));
+        if (seen_clip) atomicOr(misc_flags, 1u);
+    }
+    __syncthreads();
+
+    // ---- eight-op groups aligned to the global op index: group g = tile-local ops [8g - off, 8g - off + 8) ----
+    const uint32_t off = (uint32_t)(base & 7u);
+    const uint32_t ngroups = total ? ((total + off + 7u) >> 3) : 0u;
+    const uint32_t per = (ngroups + TOK_THREADS - 1) / TOK_THREADS;  // 1; 2 only for a tile of ~2-byte ops (> 2040 of them)
+    const uint32_t g0 = (uint32_t)tid * per;
+    const int lo_op = (int)(g0 * 8u) - (int)off;
+    const uint32_t j_lo = lo_op < 0 ? 0u : (uint32_t)lo_op;
+    uint32_t j_hi = (g0 + per) * 8u - off;
+    j_hi = j_hi > total ? total : j_hi;
+    SegVal mine = seg_identity();
+    if (g0 < ngroups) {
+        uint32_t slowc = 0;
+        uint32_t prev_code = j_lo ? op_code(s_opw[j_lo - 1]) : s_prev0;
+        for (uint32_t j = j_lo; j < j_hi; j++) {
+            const uint32_t w = s_opw[j];
+            const bool head = (s_head[j >> 5] >> (j & 31u)) & 1u;
+            if (head) { mine.c = ctr_zero(); slowc = 0; mine.flag = 1u; }
+            const uint32_t code = op_code(w), n = op_len(w);
+            slowc += ((n - 1u) >= (ACC_BIG - 1u)) | ((!head) & (code == prev_code));
+            ctr_add_op(mine.c, w);
+            prev_code = code;
+        }
+        mine.c.aux = (mine.c.aux & AUX_OVF) | (slowc & AUX_CNT);
+    }
+    SegVal sinc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const SegVal y = seg_shfl(sinc, (lane - d) & 31);
+        if (lane >= d) sinc = seg_combine(y, sinc);
+    }
+    if (lane == 31) s_wagg[warp] = sinc;
+    SegVal exl = seg_shfl(sinc, (lane - 1) & 31);
+    if (lane == 0) exl = seg_identity();
+    __syncthreads();
+    SegVal wp = seg_identity();
+    if (warp == 0) {
+        SegVal btot = seg_identity();
+#pragma unroll
+        for (int k = 0; k < TOK_THREADS / 32; k++) btot = seg_combine(btot, s_wagg[k]);
+#ifdef RB_TS_NOLB  // (timing experiment only: wrong prefixes)
+        const SegVal ex = btot;
+#else
+        const SegVal ex = lookback_seg(seg_state, seg_agg, seg_pre, tile, btot);
+#endif
+        if (lane == 0) s_blk = ex;
+    } else {
+        for (int k = 0; k < warp; k++) wp = seg_combine(wp, s_wagg[k]);
+    }
+    __syncthreads();
+    if (g0 >= ngroups) return;
+    SegVal pre = seg_combine(seg_combine(s_blk, wp), exl);
+    // the prefix in front of each of this thread's groups -> samples[(base + first op of the group) >> 3]
+    for (uint32_t gi = 0; gi < per && g0 + gi < ngroups; gi++) {
+        const int ls = (int)((g0 + gi) * 8u) - (int)off;  // first op of the group, tile-local (< 0: the group began in the tile before)
+        if (gi) {  // (rare) advance over the previous group
+            const uint32_t a0 = (ls - 8) < 0 ? 0u : (uint32_t)(ls - 8);
+            uint32_t slowc = pre.c.aux & AUX_CNT, ovf = pre.c.aux & AUX_OVF;
+            uint32_t prev_code = a0 ? op_code(s_opw[a0 - 1]) : s_prev0;
+            for (uint32_t j = a0; j < (uint32_t)ls; j++) {
+                const uint32_t w = s_opw[j];
+                const bool head = (s_head[j >> 5] >> (j & 31u)) & 1u;
+                if (head) { pre.c = ctr_zero(); slowc = 0; ovf = 0; }
+                const uint32_t code = op_code(w), n = op_len(w);
+                slowc += ((n - 1u) >= (ACC_BIG - 1u)) | ((!head) & (code == prev_code));
+                pre.c.aux = 0;
+                ctr_add_op(pre.c, w);
+                ovf |= pre.c.aux & AUX_OVF;
+                prev_code = code;
+            }
+            pre.c.aux = ovf | (slowc & AUX_CNT);
+        }
+        if (ls < 0 || (uint32_t)ls >= total) continue;
+        Ctr out = pre.c;
+        if ((s_head[(uint32_t)ls >> 5] >> ((uint32_t)ls & 31u)) & 1u) out = ctr_zero();  // the group starts a record
+        const uint64_t k = base + (uint32_t)ls;
+        if (k & (SAMPLE - 1)) {  // sub-sample, absolute: the marker + the sticky overflow bit + the (saturated) slow-op count
+            const uint32_t cntv = out.aux & AUX_CNT;
+            out.aux = SUB_ABS | (out.aux & AUX_OVF) | (cntv >= SUB_ABS ? SUB_ABS - 1u : cntv);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(samples + (k >> SUB_LOG2));
+        const uint32_t* ow = reinterpret_cast<const uint32_t*>(&out);
+        dst[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        dst[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        dst[2] = make_uint4(ow[8], ow[9], ow[10], ow[11]);
+    }
 }
 
 // segmented exclusive scan of the block aggregates k_samples2<true> left (one block: the array is small — one 64-byte entry
@@ -2683,6 +2929,14 @@ void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsig
                      ErrSlots err, uint32_t* misc_flags, cudaStream_t s) {
     if (n_tiles == 0) return;
     k_tokenise<<<(unsigned)n_tiles, TOK_THREADS, 0, s>>>(text, ops, tile_state, ticket, err, misc_flags);
+}
+void launch_tok_scan(const uint8_t* text, uint64_t n_tiles, const uint64_t* cigar_off, uint32_t n_rec, uint32_t* ops,
+                     unsigned long long* tile_state, unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, uint32_t* tile_first,
+                     uint64_t* head_pos, Ctr* samples, uint32_t* seg_state, ScanPayload* seg_agg, ScanPayload* seg_pre, cudaStream_t s) {
+    if (n_tiles == 0) return;
+    if (n_rec) k_rec_heads<<<(n_rec + 255) / 256, 256, 0, s>>>(text, cigar_off, n_rec, head_pos, tile_first);
+    k_tok_scan<<<(unsigned)n_tiles, TOK_THREADS, 0, s>>>(text, ops, tile_state, ticket, err, misc_flags, tile_first, head_pos, n_rec,
+                                                         samples, seg_state, seg_agg, seg_pre);
 }
 void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,
                     uint64_t* op_off, uint32_t* heads, ErrSlots err, cudaStream_t s) {

@@ -8,7 +8,10 @@
 
 namespace rb {
 
-constexpr int TOK_THREADS = 256;
+#ifndef RB_TOK_THREADS
+#define RB_TOK_THREADS 256
+#endif
+constexpr int TOK_THREADS = RB_TOK_THREADS;
 constexpr int TOK_TILE = TOK_THREADS * 16;  // text bytes per tokeniser tile
 constexpr int TEXT_FRONT_PAD = 16;          // bytes of 0xFF in front of the text (look-behind halo of tile 0)
 #ifndef RB_SMP_THREADS
@@ -102,6 +105,11 @@ int init_kernel_attrs();  // once per device: dynamic shared-memory limits of th
 void launch_add_u64(uint64_t* p, uint64_t n, uint64_t delta, cudaStream_t s);
 void launch_tokenise(const uint8_t* text, uint64_t n_tiles, uint32_t* ops, unsigned long long* tile_state,
                      unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, cudaStream_t s);
+// tokeniser + sampled segmented scan in one pass (k_rec_heads + k_tok_scan): what launch_tokenise + launch_scan_lift(false) produce,
+// without reading the op words back.  tile_first (u32 per tile) must be filled with 0xFF, seg_state (u32 per tile) zeroed.
+void launch_tok_scan(const uint8_t* text, uint64_t n_tiles, const uint64_t* cigar_off, uint32_t n_rec, uint32_t* ops,
+                     unsigned long long* tile_state, unsigned int* ticket, ErrSlots err, uint32_t* misc_flags, uint32_t* tile_first,
+                     uint64_t* head_pos, Ctr* samples, uint32_t* seg_state, ScanPayload* seg_agg, ScanPayload* seg_pre, cudaStream_t s);
 void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_rec, const unsigned long long* tile_state,
                     uint64_t* op_off, uint32_t* heads, ErrSlots err, cudaStream_t s);
 // fast-path (sorted BED, right-most policy) arguments of k_scan_lift: where the half results go

@@ -551,3 +551,18 @@ def test_stats_text_identity_edge_values():
         assert b"\t16.007813\t" in got["paf_text"] and b"\t100\t" in got["paf_text"] and b"\t0\t0\t0\t0\t3\t" in got["paf_text"]
     finally:
         ctx.close()
+
+
+def test_fused_tokeniser_scan_kernel_opt_in():
+    """RB_TOKSCAN=1 (k_tok_scan: tokeniser + sample scan in one kernel, absolute sub-samples) gives the same bytes: the
+    random / tiling / non-canonical / tiny-record / panic cases of this file once more in a process that has it switched on."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("RB_TOKSCAN"):
+        pytest.skip("already inside the RB_TOKSCAN=1 run")
+    env = dict(os.environ, RB_TOKSCAN="1")
+    sel = "c1_ or random_eqx or random_sliced or all_ops or tiny_records or long_numbers or reference_panics or integrity or break_paf_random"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
