@@ -194,7 +194,9 @@ int rb_invert(rb_ctx* ctx, const rb_records* recs, uint32_t want, rb_lift_out* o
  * (score of the left record before it) + (score of the right record after it), largest overlap first, one pair per query name
  * and round until no pair is left.  One row per record, ordered by query name (stable, byte-wise — the reference's
  * sort_by_key); rec_idx = the caller's record index, win_idx = 0; untouched records are printed as they are (after the indel
- * strip), truncated ones re-collapsed.  Only RB_POLICY_RIGHTMOST is implemented for this call (RB_ERR_UNSUPPORTED otherwise);
+ * strip), truncated ones re-collapsed.  Both search policies (paf.rs:564-574 is a binary_search over per-column query positions
+ * that repeat on every deletion column): under RB_POLICY_EARLY_EXIT the score of a position in front of a deletion depends on the
+ * record's current truncation, and the records cut in a round are scanned again on the device;
  * records must start and end on an M/=/X op after the strip.  Where a truncation leaves spans that disagree with the CIGAR the
  * reference panics (paf.rs:819-822) -> RB_ERR_REF_INTEGRITY. */
 int rb_trim_paf(rb_ctx* ctx, const rb_records* recs, int match_score, int diff_score, int indel_score, int remove_contained, int policy,

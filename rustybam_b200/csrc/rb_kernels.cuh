@@ -196,15 +196,16 @@ void launch_break_scan(bool fill, const uint32_t* ops, const uint64_t* n_ops_dev
 void launch_break_recs(uint32_t n_rec, RecInfo* recs, const uint64_t* rec_bp0, const uint64_t* rec_bp1, const uint64_t* bp_end,
                        const uint64_t* bp_next, uint64_t* w_st, uint64_t* w_en, uint32_t* pair_cnt, cudaStream_t s);
 // `rb trim-paf` (trim_overlap.rs:36-86, paf.rs:210-305; kernels in trim_kernels.cu).
-void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, TrimScores sc, uint32_t* qp, long long* wp, TrimView* views,
-                      cudaStream_t s);
+void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, TrimScores sc, uint32_t* qp, uint32_t* ap, long long* wp,
+                      TrimView* views, int policy, cudaStream_t s);
 // n_rounds rounds of select -> pairs -> cut -> round_end, enqueued back to back (rounds after convergence are no-ops).
 // grp_off = n_groups + 1 record offsets of the query names in the name-sorted set; sel = 24 B, keys = 8 B per group;
 // info = 32 B {waiting, done, rounds, status, err_l, err_r, last_waiting, -}, zeroed by the caller before the first round;
 // auto_done: a round that leaves nothing waiting sets `done` (otherwise the caller decides when to stop).
+// policy == POLICY_EARLY_EXIT: the score prefixes (wp) of the records cut in a round are re-scanned for their new views (k_trim_rescan)
 void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
-                        const long long* wp, TrimScores sc, unsigned long long max_score, TrimView* views, uint8_t* contained, void* sel,
-                        unsigned long long* keys, void* info, cudaStream_t s);
+                        long long* wp, const uint32_t* ap, int policy, TrimScores sc, unsigned long long max_score, TrimView* views,
+                        uint8_t* contained, void* sel, unsigned long long* keys, void* info, cudaStream_t s);
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,
                       const uint8_t* dropped, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans, cudaStream_t s);
 void launch_win_check(const uint32_t* t_id, const uint64_t* st, const uint64_t* en, const uint32_t* row, uint32_t n_win,

@@ -129,10 +129,11 @@ struct rb_batch {
     bool have_samples = false;  // run_tok already left the samples (run_scan without boundary resolution has nothing to do)
     DevBuf pair_res, line_len, line_off, out_idx, pair_win, ln_state, ln_agg, ln_pre, half_s, half_e, plans, orig_idx;
     DevBuf bp_cnt, bp_off, bp_end, bp_next, rec_bp;  // break-paf: break ops per chunk, their scan, piece boundaries
-    DevBuf trim_qp, trim_wp, trim_views, trim_sel, trim_out, trim_drop;  // trim-paf: per-op query / score prefixes, record views, one round's pairs
+    DevBuf trim_qp, trim_wp, trim_ap, trim_views, trim_sel, trim_out, trim_drop;  // trim-paf: per-op query / score prefixes, record views, one round's pairs
     bool trim_has_drop = false, trim_ready = false;   // trim_ready: between rb_trim_paf_begin and rb_trim_paf_end
     std::vector<uint32_t> trim_perm;                   // name-sorted position -> the caller's record index
     int trim_scores[3] = {1, 1, 1};
+    int trim_policy = 0;
     uint64_t trim_max_score = 1, trim_n_ops = 0;
     uint32_t trim_groups = 0;
     size_t trim_o[4] = {0, 0, 0, 0};                   // offsets of sel / keys / round state / group offsets inside trim_sel
@@ -505,7 +506,7 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b) {
                      &b->rec_rank, &b->w_st, &b->w_en, &b->w_ids_off, &b->w_ids, &b->w_bed_row, &b->w_tid, &b->cont_lo, &b->cont_hi, &b->ops,
                      &b->tile_state, &b->heads, &b->samples, &b->blk_state, &b->blk_agg, &b->blk_pre, &b->op_off, &b->recs,
                      &b->pair_cnt, &b->pair_off, &b->pair_res, &b->line_len, &b->line_off, &b->out_idx, &b->pair_win, &b->ln_state,
-                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->trim_qp, &b->trim_wp, &b->trim_views,
+                     &b->ln_agg, &b->ln_pre, &b->half_s, &b->half_e, &b->plans, &b->orig_idx, &b->bp_cnt, &b->bp_off, &b->bp_end, &b->bp_next, &b->rec_bp, &b->trim_qp, &b->trim_wp, &b->trim_ap, &b->trim_views,
                      &b->trim_sel, &b->trim_out, &b->trim_drop, &b->tile_first, &b->head_pos, &b->seg_state, &b->seg_agg, &b->seg_pre, &b->out_text, &b->out_line_off, &b->out_num, &b->out_stats, &b->blk_flags, &b->emit_totals};
     for (DevBuf* d : all) d->release();
     b->stage.release();
@@ -2221,8 +2222,7 @@ int rb_trim_paf_begin(rb_ctx* ctx, const rb_records* recs, int match_score, int 
     if (!ctx) return RB_ERR_NO_DEVICE;
     if (!recs) return fail(ctx, RB_ERR_BAD_ARG, "recs is null");
     if (ctx->scratch) ctx->scratch->trim_ready = false;
-    if (policy != RB_POLICY_RIGHTMOST)
-        return fail(ctx, RB_ERR_UNSUPPORTED, "rb_trim_paf implements the right-most binary_search policy only (Rust < 1.52 / >= 1.82)");
+    if (policy != RB_POLICY_RIGHTMOST && policy != RB_POLICY_EARLY_EXIT) return fail(ctx, RB_ERR_BAD_ARG, "unknown search policy %d", policy);
     if (recs->n_rec && (!recs->q_id || !recs->names_off || (!recs->names && recs->n_names && recs->names_off[recs->n_names])))
         return fail(ctx, RB_ERR_BAD_ARG, "rb_records: null column");
     cudaSetDevice(ctx->device);
@@ -2295,11 +2295,13 @@ int rb_trim_paf_begin(rb_ctx* ctx, const rb_records* recs, int match_score, int 
     const TrimScores scores{match_score, diff_score, indel_score};
     CU(b->trim_qp.ensure(n_ops * 4 + 64));  // (the op count is known by now: 12 B per op, not per byte of text / 2)
     CU(b->trim_wp.ensure(n_ops * 8 + 64));
+    CU(b->trim_ap.ensure(n_ops * 4 + 64));  // alignment columns before each op (the early-exit policy's probe arithmetic)
+    b->trim_policy = policy;
     CU(b->trim_views.ensure((size_t)n * sizeof(TrimView) + 64));
     {
         KScope k(ctx, "k_trim_scan");
-        launch_trim_scan(b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), n, scores, b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(),
-                         b->trim_views.as<TrimView>(), s);
+        launch_trim_scan(b->ops.as<uint32_t>(), b->recs.as<RecInfo>(), n, scores, b->trim_qp.as<uint32_t>(), b->trim_ap.as<uint32_t>(),
+                         b->trim_wp.as<long long>(), b->trim_views.as<TrimView>(), policy, s);
     }
     std::vector<TrimView> h_views(n);
     if (n) CU(cudaMemcpyAsync(h_views.data(), b->trim_views.p, (size_t)n * sizeof(TrimView), cudaMemcpyDeviceToHost, s));
@@ -2351,7 +2353,8 @@ static int trim_rounds(rb_ctx* ctx, rb_batch* b, int batch, bool auto_done, uint
     {
         KScope k(ctx, "k_trim_rounds");
         launch_trim_rounds(batch, auto_done, reinterpret_cast<const uint32_t*>(tb + o_grp), b->trim_groups, b->ops.as<uint32_t>(),
-                           b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(), scores, b->trim_max_score,
+                           b->recs.as<RecInfo>(), b->trim_qp.as<uint32_t>(), b->trim_wp.as<long long>(), b->trim_ap.as<uint32_t>(),
+                           b->trim_policy, scores, b->trim_max_score,
                            b->trim_views.as<TrimView>(), b->trim_drop.as<uint8_t>(), tb + o_sel,
                            reinterpret_cast<unsigned long long*>(tb + o_keys), tb + o_info, s);
     }

@@ -15,7 +15,8 @@
 //     the split point whose break points are op boundaries of either record: the first arg-max lies on one of them;
 //   * truncation = two column look-ups + the slide to the nearest M/=/X column, all in (op, offset) space; a record
 //     that has been truncated is a VIEW (first / last column) on its unchanged ops, so later rounds reuse the arrays.
-// Only the right-most duplicate policy is implemented for this sub-command (the caller is refused otherwise).
+// Both duplicate policies of core::slice::binary_search are implemented; the early-exit one makes the score
+// prefix a function of the record's current truncation (see trim_probe_op).
 //
 // __host__ __device__: fuzzed on the CPU against the literal per-base oracle (tests/native/trim_core_check.cpp) and
 // run by k_trim_pairs / k_trim_rows on the GPU.
@@ -28,6 +29,8 @@ struct TrimScores { int32_t match, diff, indel; };  // trim_overlap.rs:8-10 (CLI
 struct TrimArr {
     const uint32_t* qp;    // [global op] query bases of the record before this op (counted from op_first, like Ctr::Q)
     const long long* wp;   // [global op] score of the query positions owned by the effective ops before this op
+    const uint32_t* ap = nullptr;  // [global op] alignment columns of the record before this op (early-exit policy only)
+    int policy = POLICY_RIGHTMOST; // which duplicate core::slice::binary_search returns (in query space here)
 };
 struct TrimView {          // 64 bytes per record
     uint64_t si, ei;       // ops holding the first / last alignment column of the (possibly truncated) record
@@ -69,6 +72,57 @@ RB_HD long long trim_w_op(const OpsView& v, uint64_t k, uint64_t eo1, const Trim
     if (tail != TRIM_NO_TAIL) t += trim_col_score(tail, sc) - s;
     return t;
 }
+// ---- early-exit search policy (Rust 1.52 ..= 1.81) in query space ------------------------------------------------------
+// The last query position of a query-consuming op that is followed by non-query columns is held by columns [ca, cb] of the
+// record AS IT IS NOW (a truncated record's arrays are rebuilt, paf.rs:807-812: column 0 is the view's first column and
+// the column count n is the view's); binary_search returns the first probe that lands in that range, so which class the
+// position scores as — the op's own or one of the tail's — depends on (n, ca, cb): early_exit_probe (lift_core.cuh) replays it.
+// Consequence: wp is a function of the view.  Under this policy it is re-scanned for the two records of every trimmed pair
+// (trim_w_op_view below, the tail limited to the view: no view-end correction is needed then), everything else is shared.
+RB_HD uint32_t trim_view_c0(const TrimArr& a, const TrimView& tv) { return a.ap[tv.si] + tv.so; }            // first column of the view
+RB_HD uint32_t trim_view_n(const TrimArr& a, const TrimView& tv) { return a.ap[tv.ei] + tv.eo + 1u - trim_view_c0(a, tv); }
+// Column (as an op of the tail run + the query-consuming base op) the search returns for the last position of op k;
+// `tail_end` = last op of the non-query run behind k inside the view (k itself if there is none).  Returns the op whose class
+// the position scores as.
+RB_HD uint64_t trim_probe_op(const OpsView& v, const TrimArr& a, const TrimView& tv, uint64_t k, uint64_t* tail_end = nullptr) {
+    uint32_t tail_cols = 0;
+    uint64_t te = k;
+    for (uint64_t j = k + 1; j <= tv.ei; j++) {
+        const uint32_t w = v.op(j);
+        if (op_len(w) == 0) continue;
+        if (is_qry(op_code(w))) break;
+        tail_cols += op_len(w);
+        te = j;
+    }
+    if (tail_end) *tail_end = te;
+    if (tail_cols == 0) return k;
+    if (a.policy != POLICY_EARLY_EXIT) return te;  // right-most duplicate: the end of the run
+    const uint32_t ca = a.ap[k] + op_len(v.op(k)) - 1u - trim_view_c0(a, tv), cb = ca + tail_cols;
+    uint32_t pr = early_exit_probe(trim_view_n(a, tv), ca, cb);
+    if (pr == ca) return k;
+    pr -= ca;  // 1-based column inside the tail run
+    for (uint64_t j = k + 1; j <= te; j++) {
+        const uint32_t w = v.op(j);
+        if (op_len(w) == 0) continue;
+        if (pr <= op_len(w)) return j;
+        pr -= op_len(w);
+    }
+    return te;
+}
+// score of the query positions owned by op k inside view tv (the view's last op counts in full: positions behind the view's
+// last column are never asked for)
+RB_HD long long trim_w_op_view(const OpsView& v, const TrimArr& a, const TrimView& tv, uint64_t k, const TrimScores& sc) {
+    const uint32_t w = v.op(k), L = op_len(w), code = op_code(w);
+    if (L == 0 || !is_qry(code)) return 0;
+    const int32_t s = trim_col_score(code, sc);
+    long long t = (long long)L * s;
+    if (k >= tv.si && k < tv.ei) {
+        const uint64_t j = trim_probe_op(v, a, tv, k);
+        if (j != k) t += trim_col_score(op_code(v.op(j)), sc) - s;
+    }
+    return t;
+}
+
 // right-most op k in [lo, hi) with qp[k] <= x  (== the query-consuming op that owns query offset x)
 RB_HD uint64_t trim_find_q(const TrimArr& a, uint64_t lo, uint64_t hi, uint32_t x) {
     hi--;
@@ -97,8 +151,9 @@ RB_HD long long trim_S(const OpsView& v, const TrimArr& a, const RecInfo& r, con
     if (r.flags & RF_MINUS) s = trim_G(v, a, r, tv, (uint32_t)(r.q_en0 - qa), sc) - trim_G(v, a, r, tv, (uint32_t)(r.q_en0 - qb), sc);
     else s = trim_G(v, a, r, tv, (uint32_t)(qb - r.q_st0), sc) - trim_G(v, a, r, tv, (uint32_t)(qa - r.q_st0), sc);
     // the view's last column lost the non-query columns that followed it in the untruncated record
+    // (early-exit policy: wp was scanned for this very view, nothing to correct)
     const uint32_t we = v.op(tv.ei);
-    if (tv.eo == op_len(we) - 1u) {
+    if (a.policy != POLICY_EARLY_EXIT && tv.eo == op_len(we) - 1u) {
         const uint32_t tail = trim_tail(v, tv.ei, r.eo1 - 1);
         if (tail != TRIM_NO_TAIL) {
             const uint32_t xe = a.qp[tv.ei] + tv.eo;
@@ -136,7 +191,7 @@ RB_HD TrimSide trim_side(const OpsView& v, const TrimArr& a, const RecInfo& r, c
     s.g_A = trim_G(v, a, r, tv, s.minus ? (uint32_t)(r.q_en0 - A) : (uint32_t)(A - r.q_st0), sc);
     s.delta = 0; s.pe = 0;
     const uint32_t we = v.op(tv.ei);
-    if (tv.eo == op_len(we) - 1u) {
+    if (a.policy != POLICY_EARLY_EXIT && tv.eo == op_len(we) - 1u) {
         const uint32_t tail = trim_tail(v, tv.ei, r.eo1 - 1);
         if (tail != TRIM_NO_TAIL) {
             const uint32_t xe = a.qp[tv.ei] + tv.eo;
@@ -165,6 +220,7 @@ RB_HD void trim_scan_candidates(const OpsView& v, const TrimArr& a, bool x_is_le
                                 uint32_t t, uint32_t n, TrimBest& best) {
     const RecInfo& rx = x_is_left ? rl : rr;
     const RecInfo& ry = x_is_left ? rr : rl;
+    const TrimView& tx = x_is_left ? tl : tr;
     const TrimView& ty = x_is_left ? tr : tl;
     const TrimSide& sx = x_is_left ? sl : sr;
     const TrimSide& sy = x_is_left ? sr : sl;
@@ -175,7 +231,8 @@ RB_HD void trim_scan_candidates(const OpsView& v, const TrimArr& a, bool x_is_le
         const uint32_t w = v.op(k), L = op_len(w);
         if (L == 0 || !is_qry(op_code(w))) continue;
         const long long s1 = trim_col_score(op_code(w), sc);
-        const long long g0 = a.wp[k], gm = g0 + (long long)(L - 1u) * s1, g1 = g0 + trim_w_op(v, k, rx.eo1, sc);
+        const long long g0 = a.wp[k], gm = g0 + (long long)(L - 1u) * s1,
+                        g1 = g0 + (a.policy == POLICY_EARLY_EXIT ? trim_w_op_view(v, a, tx, k, sc) : trim_w_op(v, k, rx.eo1, sc));
         uint64_t cand[3];
         long long gx[3];
         if (minus) {  // columns run against the query: the op's first column is its highest query position
@@ -287,7 +344,12 @@ RB_HD void trim_col_of(const OpsView& v, const TrimArr& a, const RecInfo& r, con
     last = base;
     if (base.o == op_len(v.op(base.k)) - 1u && base.k < tv.ei) {
         uint64_t j = 0;
-        if (trim_tail(v, base.k, tv.ei, &j) != TRIM_NO_TAIL) { last.k = j; last.o = op_len(v.op(j)) - 1u; }
+        if (a.policy == POLICY_EARLY_EXIT) {
+            // the probe either returns the query-consuming column itself or one inside the run: the slides only need to know which
+            // (from any column of the run they pass the rest of it, no column of it is a match)
+            uint64_t te = base.k;
+            if (trim_probe_op(v, a, tv, base.k, &te) != base.k) { last.k = te; last.o = op_len(v.op(te)) - 1u; }
+        } else if (trim_tail(v, base.k, tv.ei, &j) != TRIM_NO_TAIL) { last.k = j; last.o = op_len(v.op(j)) - 1u; }
     }
 }
 // `while idx < max_idx && !match { idx += 1 }` from column `last` (whose query-consuming column is `base`)

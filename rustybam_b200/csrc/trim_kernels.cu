@@ -20,11 +20,58 @@ constexpr int TSCAN_THREADS = 256;
 constexpr int TSCAN_ITEMS = 4;
 constexpr int TPAIR_THREADS = 128;
 
-__global__ void __launch_bounds__(TSCAN_THREADS)
-k_trim_scan(const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs, uint32_t n_rec, TrimScores sc, uint32_t* __restrict__ qp,
-            long long* __restrict__ wp, TrimView* __restrict__ views) {
-    __shared__ uint32_t s_q[TSCAN_THREADS / 32];
+// Block-wide exclusive scan of the position scores of record `ri` -> wp[op_first .. op_end); returns the total (every thread).
+// view == nullptr: right-most policy, the scores do not depend on the record's truncation (trim_w_op);
+// else: early-exit policy, the scores of the positions in front of non-query runs follow the view (trim_w_op_view).
+__device__ __forceinline__ long long trim_scan_w(const OpsView& v, const RecInfo& ri, const TrimScores& sc, const TrimArr& arr,
+                                                 const TrimView* view, long long* wp) {
     __shared__ long long s_w[TSCAN_THREADS / 32];
+    const uint64_t first = ri.op_first, end = ri.op_end, eo0 = ri.eo0, eo1 = ri.eo1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long carry_w = 0;
+    for (uint64_t base = first; base < end; base += (uint64_t)TSCAN_THREADS * TSCAN_ITEMS) {
+        const uint64_t k0 = base + (uint64_t)tid * TSCAN_ITEMS;
+        long long dw[TSCAN_ITEMS];
+        long long tw = 0;
+#pragma unroll
+        for (int j = 0; j < TSCAN_ITEMS; j++) {
+            const uint64_t k = k0 + j;
+            dw[j] = 0;
+            if (k < end && k >= eo0 && k < eo1) dw[j] = view ? trim_w_op_view(v, arr, *view, k, sc) : trim_w_op(v, k, eo1, sc);
+            tw += dw[j];
+        }
+        long long iw = tw;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long ow = __shfl_up_sync(0xffffffffu, iw, d);
+            if (lane >= d) iw += ow;
+        }
+        if (lane == 31) s_w[warp] = iw;
+        __syncthreads();
+        long long pw = carry_w, allw = 0;
+        for (int x = 0; x < TSCAN_THREADS / 32; x++) {
+            if (x < warp) pw += s_w[x];
+            allw += s_w[x];
+        }
+        pw += iw - tw;
+#pragma unroll
+        for (int j = 0; j < TSCAN_ITEMS; j++) {
+            const uint64_t k = k0 + j;
+            if (k < end) wp[k] = pw;
+            pw += dw[j];
+        }
+        carry_w += allw;
+        __syncthreads();
+    }
+    return carry_w;
+}
+
+// per record: qp (query bases before each op), ap (alignment columns before each op), the untruncated view, then wp
+__global__ void __launch_bounds__(TSCAN_THREADS)
+k_trim_scan(const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs, uint32_t n_rec, TrimScores sc, uint32_t* qp, uint32_t* ap,
+            long long* wp, TrimView* __restrict__ views, int policy) {
+    __shared__ uint32_t s_q[TSCAN_THREADS / 32], s_a[TSCAN_THREADS / 32];
+    __shared__ TrimView s_tv;
     const uint32_t r = blockIdx.x;
     if (r >= n_rec) return;
     const RecInfo& ri = recs[r];
@@ -32,58 +79,57 @@ k_trim_scan(const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs, 
     OpsView v;
     v.ops = ops; v.samples = nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t carry_q = 0;
-    long long carry_w = 0;
+    uint32_t carry_q = 0, carry_a = 0;
     for (uint64_t base = first; base < end; base += (uint64_t)TSCAN_THREADS * TSCAN_ITEMS) {
         const uint64_t k0 = base + (uint64_t)tid * TSCAN_ITEMS;
-        uint32_t dq[TSCAN_ITEMS];
-        long long dw[TSCAN_ITEMS];
-        uint32_t tq = 0;
-        long long tw = 0;
+        uint32_t dq[TSCAN_ITEMS], da[TSCAN_ITEMS];
+        uint32_t tq = 0, ta = 0;
 #pragma unroll
         for (int j = 0; j < TSCAN_ITEMS; j++) {
             const uint64_t k = k0 + j;
-            dq[j] = 0; dw[j] = 0;
+            dq[j] = 0; da[j] = 0;
             if (k < end) {
                 const uint32_t w = ops[k];
                 if (is_qry(op_code(w))) dq[j] = op_len(w);
-                if (k >= eo0 && k < eo1) dw[j] = trim_w_op(v, k, eo1, sc);
+                da[j] = op_len(w);
             }
-            tq += dq[j]; tw += dw[j];
+            tq += dq[j]; ta += da[j];
         }
-        // block-wide exclusive scan of the per-thread sums: warp shuffles, then the warp totals
-        uint32_t iq = tq;
-        long long iw = tw;
+        uint32_t iq = tq, ia = ta;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t oq = __shfl_up_sync(0xffffffffu, iq, d);
-            const long long ow = __shfl_up_sync(0xffffffffu, iw, d);
-            if (lane >= d) { iq += oq; iw += ow; }
+            const uint32_t oa = __shfl_up_sync(0xffffffffu, ia, d);
+            if (lane >= d) { iq += oq; ia += oa; }
         }
-        if (lane == 31) { s_q[warp] = iq; s_w[warp] = iw; }
+        if (lane == 31) { s_q[warp] = iq; s_a[warp] = ia; }
         __syncthreads();
-        uint32_t pq = carry_q;
-        long long pw = carry_w;
-        for (int x = 0; x < warp; x++) { pq += s_q[x]; pw += s_w[x]; }
-        uint32_t allq = 0;
-        long long allw = 0;
-        for (int x = 0; x < TSCAN_THREADS / 32; x++) { allq += s_q[x]; allw += s_w[x]; }
-        pq += iq - tq; pw += iw - tw;
+        uint32_t pq = carry_q, pa = carry_a, allq = 0, alla = 0;
+        for (int x = 0; x < TSCAN_THREADS / 32; x++) {
+            if (x < warp) { pq += s_q[x]; pa += s_a[x]; }
+            allq += s_q[x]; alla += s_a[x];
+        }
+        pq += iq - tq; pa += ia - ta;
 #pragma unroll
         for (int j = 0; j < TSCAN_ITEMS; j++) {
             const uint64_t k = k0 + j;
-            if (k < end) { qp[k] = pq; wp[k] = pw; }
-            pq += dq[j]; pw += dw[j];
+            if (k < end) { qp[k] = pq; ap[k] = pa; }
+            pq += dq[j]; pa += da[j];
         }
-        carry_q += allq; carry_w += allw;
+        carry_q += allq; carry_a += alla;
         __syncthreads();
     }
-    if (tid == 0 && end > first && eo1 > eo0) {
-        TrimView tv;
-        trim_view_init(v, ri, tv);
-        tv.w_tot = carry_w;
-        tv.x_end = (eo1 < end) ? qp[eo1] : carry_q;  // written by this block before the barrier above
-        views[r] = tv;
+    const bool live = end > first && eo1 > eo0;  // (block-uniform)
+    if (tid == 0 && live) {
+        trim_view_init(v, ri, s_tv);
+        s_tv.x_end = (eo1 < end) ? qp[eo1] : carry_q;  // written by this block before the barrier above
+    }
+    __syncthreads();  // s_tv, and this block's qp / ap writes, are visible to all of its threads
+    const TrimArr arr{qp, wp, ap, policy};
+    const long long w_tot = trim_scan_w(v, ri, sc, arr, (policy == POLICY_EARLY_EXIT && live) ? &s_tv : nullptr, wp);
+    if (tid == 0 && live) {
+        s_tv.w_tot = w_tot;
+        views[r] = s_tv;
     }
 }
 
@@ -167,8 +213,8 @@ k_trim_select(const uint32_t* __restrict__ grp_off, uint32_t n_groups, const Tri
 // of a selected pair never stays zero.
 __global__ void __launch_bounds__(TPAIR_THREADS)
 k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
-             const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, const TrimView* __restrict__ views,
-             unsigned long long* __restrict__ keys, const TrimInfo* __restrict__ info) {
+             const uint32_t* __restrict__ qp, const long long* __restrict__ wp, const uint32_t* __restrict__ ap, int policy, TrimScores sc,
+             const TrimView* __restrict__ views, unsigned long long* __restrict__ keys, const TrimInfo* __restrict__ info) {
     if (info->done | info->status) return;
     const uint32_t p = blockIdx.x;
     if (p >= n_sel) return;
@@ -179,7 +225,7 @@ k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t
     const TrimView tl = views[ps.left], tr = views[ps.right];
     OpsView v;
     v.ops = ops; v.samples = nullptr;
-    const TrimArr a{qp, wp};
+    const TrimArr a{qp, wp, ap, policy};
     const uint64_t A = ps.st_ovl, B = ps.en_ovl;
     const TrimSide sl = trim_side(v, a, rl, tl, A, sc), sr = trim_side(v, a, rr, tr, A, sc);
     const uint32_t t = blockIdx.y * TPAIR_THREADS + threadIdx.x, n = gridDim.y * TPAIR_THREADS;
@@ -199,8 +245,8 @@ k_trim_pairs(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t
 // one thread per selected pair: split point from the reduced key, then the two truncations (trim_overlap.rs:71-79)
 __global__ void __launch_bounds__(128)
 k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
-           const uint32_t* __restrict__ qp, const long long* __restrict__ wp, TrimScores sc, TrimView* __restrict__ views,
-           const unsigned long long* __restrict__ keys, TrimInfo* __restrict__ info) {
+           const uint32_t* __restrict__ qp, const long long* __restrict__ wp, const uint32_t* __restrict__ ap, int policy, TrimScores sc,
+           TrimView* __restrict__ views, const unsigned long long* __restrict__ keys, TrimInfo* __restrict__ info) {
     if (info->done | info->status) return;
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_sel) return;
@@ -210,7 +256,7 @@ k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* 
     const RecInfo& rr = recs[ps.right];
     OpsView v;
     v.ops = ops; v.samples = nullptr;
-    const TrimArr a{qp, wp};
+    const TrimArr a{qp, wp, ap, policy};
     const uint64_t A = ps.st_ovl, B = ps.en_ovl;
     TrimView nl = views[ps.left], nr = views[ps.right];
     const TrimBest best = trim_unkey(keys[p], A);
@@ -223,6 +269,32 @@ k_trim_cut(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* 
 }
 // NOTE on k_trim_cut's early exit: `status` may be set by another block of the same launch; the pairs of a round are
 // disjoint and a failed call produces no output, so it does not matter which of them still get cut.
+
+// early-exit policy only: the score prefix of a record follows its view (trim_core.cuh, trim_probe_op) — the two records of every
+// pair cut in this round are scanned again.  Block 2g / 2g + 1 = left / right record of query name g's pair.
+__global__ void __launch_bounds__(TSCAN_THREADS)
+k_trim_rescan(const TrimPairDev* __restrict__ sel, uint32_t n_sel, const uint32_t* __restrict__ ops, const RecInfo* __restrict__ recs,
+              const uint32_t* __restrict__ qp, long long* wp, const uint32_t* __restrict__ ap, TrimScores sc, TrimView* views,
+              const TrimInfo* __restrict__ info) {
+    __shared__ TrimView s_tv;
+    __shared__ uint32_t s_r;
+    if (threadIdx.x == 0) {
+        s_r = TRIM_SEL_NONE;
+        const uint32_t g = blockIdx.x >> 1;
+        if (!(info->done | info->status) && g < n_sel) {
+            const TrimPairDev ps = sel[g];
+            if (ps.left != TRIM_SEL_NONE) { s_r = (blockIdx.x & 1u) ? ps.right : ps.left; s_tv = views[s_r]; }
+        }
+    }
+    __syncthreads();
+    const uint32_t r = s_r;
+    if (r == TRIM_SEL_NONE) return;
+    OpsView v;
+    v.ops = ops; v.samples = nullptr;
+    const TrimArr arr{qp, wp, ap, POLICY_EARLY_EXIT};
+    const long long w_tot = trim_scan_w(v, recs[r], sc, arr, &s_tv, wp);
+    if (threadIdx.x == 0) views[r].w_tot = w_tot;
+}
 
 // after the cuts of a round: nothing waiting -> the call is done (paf.rs:283-300); else the next round starts over
 __global__ void k_trim_round_end(TrimInfo* info, int auto_done) {
@@ -259,13 +331,13 @@ k_trim_rows(uint32_t n_rec, const RecInfo* __restrict__ recs, const TrimView* __
     }
 }
 
-void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, TrimScores sc, uint32_t* qp, long long* wp, TrimView* views,
-                      cudaStream_t s) {
-    if (n_rec) k_trim_scan<<<n_rec, TSCAN_THREADS, 0, s>>>(ops, recs, n_rec, sc, qp, wp, views);
+void launch_trim_scan(const uint32_t* ops, const RecInfo* recs, uint32_t n_rec, TrimScores sc, uint32_t* qp, uint32_t* ap, long long* wp,
+                      TrimView* views, int policy, cudaStream_t s) {
+    if (n_rec) k_trim_scan<<<n_rec, TSCAN_THREADS, 0, s>>>(ops, recs, n_rec, sc, qp, ap, wp, views, policy);
 }
 void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, uint32_t n_groups, const uint32_t* ops, const RecInfo* recs, const uint32_t* qp,
-                        const long long* wp, TrimScores sc, unsigned long long max_score, TrimView* views, uint8_t* contained, void* sel,
-                        unsigned long long* keys, void* info, cudaStream_t s) {
+                        long long* wp, const uint32_t* ap, int policy, TrimScores sc, unsigned long long max_score, TrimView* views,
+                        uint8_t* contained, void* sel, unsigned long long* keys, void* info, cudaStream_t s) {
     static_assert(sizeof(TrimPairDev) == 24 && sizeof(TrimInfo) == 32, "layouts");
     TrimInfo* inf = reinterpret_cast<TrimInfo*>(info);
     TrimPairDev* sl = reinterpret_cast<TrimPairDev*>(sel);
@@ -276,8 +348,9 @@ void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, u
     for (int r = 0; r < n_rounds; r++) {
         if (n_groups) {
             k_trim_select<<<n_groups, 128, 0, s>>>(grp_off, n_groups, views, contained, sl, keys, inf, max_score);
-            k_trim_pairs<<<dim3(n_groups, slices), TPAIR_THREADS, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
-            k_trim_cut<<<(n_groups + 127) / 128, 128, 0, s>>>(sl, n_groups, ops, recs, qp, wp, sc, views, keys, inf);
+            k_trim_pairs<<<dim3(n_groups, slices), TPAIR_THREADS, 0, s>>>(sl, n_groups, ops, recs, qp, wp, ap, policy, sc, views, keys, inf);
+            k_trim_cut<<<(n_groups + 127) / 128, 128, 0, s>>>(sl, n_groups, ops, recs, qp, wp, ap, policy, sc, views, keys, inf);
+            if (policy == POLICY_EARLY_EXIT) k_trim_rescan<<<2 * n_groups, TSCAN_THREADS, 0, s>>>(sl, n_groups, ops, recs, qp, wp, ap, sc, views, inf);
         }
         k_trim_round_end<<<1, 1, 0, s>>>(inf, auto_done ? 1 : 0);
     }

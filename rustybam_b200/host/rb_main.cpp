@@ -11,6 +11,7 @@
 // trimming, serialisation and identity counting run on the B200 through include/rbcuda.h.
 // Exit status 101 where the reference panics.  There is no CPU fallback: without an sm_100
 // device the program fails.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -63,6 +64,19 @@ int main(int argc, char** argv) {
     if (cmd != "liftover" && !(cmd == "stats" && paf_flag) && !brk && !inv && !is_trim) return usage();
     int status = 0;
     if (n_gpus < 1 || n_gpus > 64) return usage();
+    // RB_TIMING=1: wall-clock of the phases of this (one-shot, cold) process as one JSON line on stderr
+    const bool timing = getenv("RB_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto t_last = t_start;
+    std::string phases;
+    auto mark = [&](const char* name) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, "%s\"%s_ms\": %.1f", phases.empty() ? "" : ", ", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+        phases += buf;
+        t_last = now;
+    };
     int ids[64];
     for (int d = 0; d < n_gpus; d++) ids[d] = d;
     rb_ctx* ctx = rb_ctx_create(ids, n_gpus, &status);
@@ -70,6 +84,7 @@ int main(int argc, char** argv) {
         fprintf(stderr, "rb: no usable sm_100 CUDA device (status %d); this build has no CPU path\n", status);
         return 3;
     }
+    mark("ctx_create");
     int rc = 0;
     try {
         if (cmd == "stats") {
@@ -117,9 +132,12 @@ int main(int argc, char** argv) {
         } else {
             if (bed.empty()) return usage();
             const std::string bed_text = rbh::read_all(bed);
+            mark("read_bed");
             rbh::Paf paf = rbh::Paf::from_file(input);
+            mark("read_parse_paf");
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rbh::Windows wins = rbh::Windows::pack_text(bed_text.data(), bed_text.size(), paf);  // bed::parse_bed + sort, all host threads
+            mark("pack_bed");
             rb_records recs = paf.view();
             rb_windows w = wins.view();
             rb_lift_out out{};
@@ -127,6 +145,7 @@ int main(int argc, char** argv) {
             const uint32_t want = (stats_rows ? RB_WANT_STATS_TEXT : RB_WANT_TEXT) | (largest ? RB_WANT_NUMERIC : 0u) | (qbed ? RB_WANT_QBED : 0u);
             if (stats_rows) { fputs(rbh::stats_header(false).c_str(), stdout); fflush(stdout); }  // main.rs:51
             rc = rb_liftover(ctx, &recs, &w, policy, want, &out, nullptr);
+            mark("rb_liftover");
             if (rc == RB_OK) {
                 if (largest) {  // main.rs:200-208
                     const std::string rows = rbh::largest_rows(out);
@@ -134,6 +153,8 @@ int main(int argc, char** argv) {
                 } else {
                     fwrite(out.paf_text, 1, out.paf_nbytes, stdout);
                 }
+                fflush(stdout);
+                mark("write");
                 rb_free_lift_out(ctx, &out);
             }
         }
@@ -149,5 +170,9 @@ int main(int argc, char** argv) {
         return ref_panic ? 101 : 1;
     }
     rb_ctx_destroy(ctx);
+    mark("destroy");
+    if (timing)
+        fprintf(stderr, "{\"rb_timing\": {%s, \"total_ms\": %.1f}}\n", phases.c_str(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
     return 0;
 }

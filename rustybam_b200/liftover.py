@@ -79,9 +79,10 @@ def overlapping_paf_recs(ctx, paf: Paf, match_score=1, diff_score=1, indel_score
         raise
 
 
-def run_trim_paf(ctx, paf_text: bytes, match_score=1, diff_score=1, indel_score=1, remove_contained=False) -> bytes:
+def run_trim_paf(ctx, paf_text: bytes, match_score=1, diff_score=1, indel_score=1, remove_contained=False, policy=POLICY_RIGHTMOST) -> bytes:
     """`rb trim-paf [-m M] [-d D] [-i I] [-r] PAF`: stdout bytes."""
-    return overlapping_paf_recs(ctx, Paf.from_text(paf_text), match_score, diff_score, indel_score, remove_contained, want=WANT_TEXT)["paf_text"]
+    return overlapping_paf_recs(ctx, Paf.from_text(paf_text), match_score, diff_score, indel_score, remove_contained, policy=policy,
+                                want=WANT_TEXT)["paf_text"]
 
 
 def run_invert(ctx, paf_text: bytes) -> bytes:

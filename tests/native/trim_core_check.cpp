@@ -41,7 +41,7 @@ static std::string cig_text(const std::vector<uint32_t>& ops, size_t a, size_t b
 struct Counts { long n_fail = 0, n_abort = 0, n_trimmed = 0, n_rows = 0, n_rounds_max = 0, n_unsup = 0; };
 
 // one PAF text through the oracle and through the product's closed form; `recs` come from the oracle's own line parser
-static void check_text(const std::string& text, TrimScores sc, bool remove_contained, std::mt19937_64& rng, Counts& C, int g) {
+static void check_text(const std::string& text, TrimScores sc, bool remove_contained, std::mt19937_64& rng, Counts& C, int g, int policy = POLICY_RIGHTMOST) {
     auto U = [&](uint64_t lo, uint64_t hi) { return lo + rng() % (hi - lo + 1); };
     long &n_fail = C.n_fail, &n_abort = C.n_abort, &n_trimmed = C.n_trimmed, &n_rows = C.n_rows, &n_rounds_max = C.n_rounds_max, &n_unsup = C.n_unsup;
     std::vector<TestRec> recs;
@@ -60,7 +60,7 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
         std::string want;
         bool aborted = false;
         try {
-            want = orc::run_trim_paf(text.data(), text.size(), sc.match, sc.diff, sc.indel, remove_contained, orc::POLICY_RIGHTMOST);
+            want = orc::run_trim_paf(text.data(), text.size(), sc.match, sc.diff, sc.indel, remove_contained, policy == POLICY_EARLY_EXIT ? orc::POLICY_EARLY_EXIT : orc::POLICY_RIGHTMOST);
         } catch (const orc::Abort& e) {
             aborted = true;
             if (getenv("RB_DBG")) fprintf(stderr, "abort: %s\n", e.what());
@@ -104,6 +104,25 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
         std::vector<TrimView> tv(order.size());
         std::vector<uint32_t> qp(ops.size() + 1, 0);
         std::vector<long long> wp(ops.size() + 1, 0);
+        std::vector<uint32_t> ap(ops.size() + 1, 0);
+        TrimArr arr{qp.data(), wp.data(), ap.data(), policy};
+        // what k_trim_scan / k_trim_rescan compute for one record and its current view
+        auto scan_record = [&](size_t r) {
+            const RecInfo& R = ri[r];
+            uint32_t q = 0, acol = 0;
+            long long w = 0;
+            for (uint64_t k = R.op_first; k < R.op_end; k++) {
+                qp[k] = q; ap[k] = acol;
+                if (is_qry(op_code(ops[k]))) q += op_len(ops[k]);
+                acol += op_len(ops[k]);
+                if (k + 1 == R.eo1) tv[r].x_end = q;
+            }
+            for (uint64_t k = R.op_first; k < R.op_end; k++) {
+                wp[k] = w;
+                if (k >= R.eo0 && k < R.eo1) w += (policy == POLICY_EARLY_EXIT) ? trim_w_op_view(view, arr, tv[r], k, sc) : trim_w_op(view, k, R.eo1, sc);
+                if (k + 1 == R.eo1) tv[r].w_tot = w;
+            }
+        };
         std::vector<TrimSpan> spans(order.size());
         bool strip_abort = false, unsupported = false;
         for (size_t r = 0; r < order.size(); r++) {
@@ -123,16 +142,8 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
             ctr_add_op(R.tot, ops[R.eo1 - 1]);
             Ctr lead = ctr_before(view, R, R.eo0, acc);
             ctr_sub(R.tot, lead);
-            // what k_trim_scan computes
-            uint32_t q = 0;
-            long long w = 0;
-            for (uint64_t k = R.op_first; k < R.op_end; k++) {
-                qp[k] = q; wp[k] = w;
-                if (is_qry(op_code(ops[k]))) q += op_len(ops[k]);
-                if (k >= R.eo0 && k < R.eo1) w += trim_w_op(view, k, R.eo1, sc);
-                if (k + 1 == R.eo1) { tv[r].w_tot = w; tv[r].x_end = q; }
-            }
             trim_view_init(view, R, tv[r]);
+            scan_record(r);
             if (tv[r].bad) unsupported = true;
             spans[r] = TrimSpan{R.q_st, R.q_en, 0};
             spans[r].name = (r > 0 && recs[order[r - 1]].q_name == tr.q_name) ? spans[r - 1].name : (r > 0 ? spans[r - 1].name + 1 : 0);
@@ -143,7 +154,6 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
             break;
         }
         if (unsupported) { n_unsup++; break; }
-        TrimArr arr{qp.data(), wp.data()};
         std::vector<uint8_t> contained;
         std::vector<TrimPairSel> sel;
         bool p_abort = false;
@@ -203,6 +213,7 @@ static void check_text(const std::string& text, TrimScores sc, bool remove_conta
                 const uint64_t s = trim_split(best, r_tot, A);
                 if (trim_truncate(view, arr, rl, tl, tl.q_st, s) != TRIM_OK) { p_abort = true; break; }
                 if (trim_truncate(view, arr, rr, tr, s, tr.q_en) != TRIM_OK) { p_abort = true; break; }
+                if (policy == POLICY_EARLY_EXIT) { scan_record(p.left); scan_record(p.right); }  // the score prefix follows the view
                 spans[p.left].q_st = tl.q_st; spans[p.left].q_en = tl.q_en;
                 spans[p.right].q_st = tr.q_st; spans[p.right].q_en = tr.q_en;
                 n_trimmed++;
@@ -262,7 +273,7 @@ int main(int argc, char** argv) {
         fclose(f);
         TrimScores sc{argc > 3 ? atoi(argv[3]) : 1, argc > 4 ? atoi(argv[4]) : 1, argc > 5 ? atoi(argv[5]) : 1};
         std::mt19937_64 rng(7);
-        check_text(text, sc, argc > 6 && atoi(argv[6]) != 0, rng, C, 0);
+        check_text(text, sc, argc > 6 && atoi(argv[6]) != 0, rng, C, 0, argc > 7 ? atoi(argv[7]) : POLICY_RIGHTMOST);
         printf("aborts=%ld unsupported=%ld trimmed_pairs=%ld rows=%ld max_rounds=%ld FAIL=%ld\n", C.n_abort, C.n_unsup, C.n_trimmed, C.n_rows, C.n_rounds_max, C.n_fail);
         return C.n_fail ? 1 : 0;
     }
@@ -323,7 +334,7 @@ int main(int argc, char** argv) {
 
         std::string text;
         for (auto& tr : recs) text += tr.line + "\n";
-        check_text(text, sc, remove_contained, rng, C, g);
+        check_text(text, sc, remove_contained, rng, C, g, (argc > 3) ? atoi(argv[3]) : (int)(g & 1));
     }
     printf("groups=%d aborts=%ld unsupported=%ld trimmed_pairs=%ld rows=%ld max_rounds=%ld FAIL=%ld\n", n_groups, C.n_abort, C.n_unsup, C.n_trimmed, C.n_rows,
            C.n_rounds_max, C.n_fail);

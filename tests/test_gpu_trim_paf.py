@@ -23,16 +23,16 @@ def ctx():
     c.close()
 
 
-def check_trim_against_oracle(ctx, paf_text, scores=(1, 1, 1), remove_contained=False):
+def check_trim_against_oracle(ctx, paf_text, scores=(1, 1, 1), remove_contained=False, policy=0):
     """GPU output == oracle output (or both panic); returns the text (None on a panic)."""
     try:
-        want = orc.run_trim_paf(paf_text, *scores, remove_contained)
+        want = orc.run_trim_paf(paf_text, *scores, remove_contained, policy=policy)
     except orc.ReferencePanic:
         with pytest.raises(ReferencePanic):
-            liftover.run_trim_paf(ctx, paf_text, *scores, remove_contained)
+            liftover.run_trim_paf(ctx, paf_text, *scores, remove_contained, policy=policy)
         return None
     paf = Paf.from_text(paf_text)
-    res = liftover.overlapping_paf_recs(ctx, paf, *scores, remove_contained, stats=True)
+    res = liftover.overlapping_paf_recs(ctx, paf, *scores, remove_contained, policy=policy, stats=True)
     assert res["paf_text"] == want
     rows = [ln.split(b"\t") for ln in want.splitlines()]
     assert res["n_out"] == len(rows)
@@ -78,6 +78,9 @@ def test_trim_random(ctx, seed):
     n_ok = 0
     for scores, rc in (((1, 1, 1), False), ((2, 3, 1), True), ((1, 0, 0), False)):
         n_ok += check_trim_against_oracle(ctx, paf_text, scores, rc) is not None
+        # the early-exit binary_search of Rust 1.52 ..= 1.81 (SURVEY Q2 in query space): scores of the positions in front of
+        # deletions follow the record's current truncation, the device re-scans the records it cut (k_trim_rescan)
+        check_trim_against_oracle(ctx, paf_text, scores, rc, policy=orc.EARLY_EXIT)
     assert n_ok or seed in ()  # (panics are rare; a seed where every score set panics would test nothing)
 
 
@@ -86,7 +89,9 @@ def test_trim_many_names_and_rounds(ctx):
     paf_text = gen.random_trim_paf(77, n_names=300, recs_per_name=3, max_ops=40)
     want = check_trim_against_oracle(ctx, paf_text)
     assert want is not None and want.count(b"\n") == paf_text.count(b"\n")
+    check_trim_against_oracle(ctx, paf_text, policy=orc.EARLY_EXIT)
     pile = gen.random_trim_paf(78, n_names=2, recs_per_name=40, max_ops=30, span=600, lead_trail=False)
+    check_trim_against_oracle(ctx, pile, (1, 1, 1), True, policy=orc.EARLY_EXIT)
     want = check_trim_against_oracle(ctx, pile, (1, 1, 1), True)
     if want is not None:
         assert liftover.run_trim_paf(ctx, want) == want  # nothing left to trim: a second pass changes nothing
@@ -99,6 +104,7 @@ def test_trim_long_records(ctx):
     check_trim_against_oracle(ctx, paf_text, (3, 2, 1), True)
     paf_text = gen.random_trim_paf(6, n_names=4, recs_per_name=3, max_ops=2000, span=20000, big=12)
     assert check_trim_against_oracle(ctx, paf_text, (1, 1, 1)) is not None
+    check_trim_against_oracle(ctx, paf_text, (2, 1, 3), False, policy=orc.EARLY_EXIT)
 
 
 def test_trim_bundled_fixture(ctx):
@@ -108,6 +114,8 @@ def test_trim_bundled_fixture(ctx):
     assert want.count(b"\n") == 249
     dropped = check_trim_against_oracle(ctx, paf_text, (3, 2, 1), True)
     assert dropped.count(b"\n") == 241
+    early = check_trim_against_oracle(ctx, paf_text, policy=orc.EARLY_EXIT)
+    assert early.count(b"\n") == 249
     changed = sum(a.split(b"\t")[2:4] != b.split(b"\t")[2:4] for a, b in zip(sorted(paf_text.splitlines()), sorted(want.splitlines())))
     assert changed > 100
 
@@ -144,9 +152,9 @@ def test_trim_shards_by_query_name(ctx):
 
 def test_trim_errors(ctx):
     paf = Paf.from_text(gen.random_trim_paf(3))
-    with pytest.raises(RbError) as e:  # only the right-most binary_search policy is implemented for this call
-        ctx.trim_paf(paf.pack(), policy=capi.POLICY_EARLY_EXIT)
-    assert e.value.code == -8
+    with pytest.raises(RbError) as e:  # neither of the two binary_search policies
+        ctx.trim_paf(paf.pack(), policy=7)
+    assert e.value.code == capi.RB_ERR_BAD_ARG
     # a record that does not start on M/=/X after the strip is outside the documented domain: loud, not wrong
     odd = Paf.from_text(b"Q\t30\t0\t10\t+\tT\t40\t5\t20\t0\t0\t60\tcg:Z:5N5=5=\nQ\t30\t5\t15\t+\tT\t40\t50\t60\t0\t0\t60\tcg:Z:10=\n")
     with pytest.raises(RbError) as e:

@@ -59,7 +59,18 @@ def harness(tmp_path_factory):
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_closed_form_trim_matches_literal_oracle(harness, seed):
+    # (without a third argument the harness alternates the two binary_search policies from group to group)
     r = subprocess.run([harness, str(seed), "1500"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "FAIL=0" in r.stdout
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_closed_form_trim_each_search_policy(harness, policy):
+    """Right-most (Rust < 1.52 / >= 1.82) and early-exit (1.52 ..= 1.81) core::slice::binary_search over the per-column query
+    positions (paf.rs:564-574): the closed form replays the early-exit probe sequence over the duplicate columns of every
+    position in front of a non-query run, for the record's CURRENT truncation (trim_core.cuh, trim_probe_op)."""
+    r = subprocess.run([harness, str(11 + policy), "1200", str(policy)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "FAIL=0" in r.stdout
 

@@ -59,6 +59,14 @@ res = {"paf_bytes": os.path.getsize(P), "bed_bytes": os.path.getsize(B), "host_c
 o1, o2, o3, o4, o5 = (os.path.join(tmp, f"out{i}.tsv") for i in range(5))
 res["rb_piped_s"] = [run(f"{RB} liftover --bed {B} {P} | {RB} stats --paf -", o1) for _ in range(3)]
 res["rb_fused_s"] = [run(f"{RB} liftover --bed {B} --stats {P}", o2) for _ in range(3)]
+# where the one-process form spends its time (RB_TIMING=1: phases of the cold process as JSON on stderr)
+try:
+    pr = subprocess.run(f"RB_TIMING=1 {RB} liftover --bed {B} --stats {P} > {o2}", shell=True, executable="/bin/bash", capture_output=True, text=True)
+    for ln in pr.stderr.splitlines():
+        if ln.startswith('{"rb_timing"'):
+            res["rb_fused_phases"] = json.loads(ln)["rb_timing"]
+except Exception as e:  # noqa: BLE001
+    res["rb_fused_phases"] = str(e)
 res["rows"] = sum(1 for _ in open(o1, "rb")) - 1
 res["piped_equals_fused"] = md5(o1) == md5(o2)
 # the same two on the contig subset the oracle can do in seconds, and the oracle itself

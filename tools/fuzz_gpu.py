@@ -143,7 +143,10 @@ while time.time() < t_end:
     rc_flag = rng.random() < 0.5
     dump["trim.paf"] = tp
     dump["info.txt"] += f"trim scores {scores} remove_contained {rc_flag}\n".encode()
-    trimmed = both(f"trim-paf seed {seed}", lambda: orc.run_trim_paf(tp, *scores, rc_flag), lambda: liftover.run_trim_paf(ctx, tp, *scores, rc_flag), dump)
+    tpol = rng.randint(0, 1)
+    dump["info.txt"] += f"trim policy {tpol}\n".encode()
+    trimmed = both(f"trim-paf seed {seed}", lambda: orc.run_trim_paf(tp, *scores, rc_flag, policy=tpol),
+                   lambda: liftover.run_trim_paf(ctx, tp, *scores, rc_flag, policy=tpol), dump)
     n_trim_panics += trimmed == "PANIC"
     n += 1
     seed += 1
