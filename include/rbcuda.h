@@ -230,6 +230,15 @@ void rb_batch_free(rb_ctx* ctx, rb_batch* b);
  * perm_out[n_win] receives, for each sorted position, the BED row it came from. */
 int rb_sort_windows(uint32_t n_win, const uint32_t* t_id, const uint64_t* st, uint32_t* perm_out);
 
+/* replaces the inflate step of `myio::reader` for BGZF input (myio.rs:41-64: `.bgz` goes through gzp::BgzfSyncReader before
+ * Paf::from_file reads lines, paf.rs:62-78): `bgzf` = the file's bytes (a series of BGZF blocks, what bgzip writes); the blocks are
+ * inflated on the device, one thread per block, CRC-32 and ISIZE of every trailer verified; *text = the inflated bytes in
+ * library-owned pinned host memory (rb_free_text), *text_nbytes their count.  RB_ERR_BAD_ARG: not BGZF / corrupt data.  A plain
+ * single-member .gz is one dependent stream and is not handled here (rb_is_bgzf tells them apart). */
+int rb_is_bgzf(const uint8_t* data, uint64_t nbytes);
+int rb_inflate_bgzf(rb_ctx* ctx, const uint8_t* bgzf, uint64_t nbytes, uint8_t** text, uint64_t* text_nbytes);
+void rb_free_text(rb_ctx* ctx, uint8_t* text);
+
 /* ---- host helper: page-lock caller-owned buffers (cudaHostRegister) so that the H2D copies of
  * rb_liftover / rb_batch_upload are asynchronous DMA; for hosts without their own CUDA binding.  Allocate such buffers
  * page-aligned and padded to whole pages (a page shared with another object would end up half page-locked), and call

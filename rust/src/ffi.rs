@@ -52,6 +52,10 @@ extern "C" {
     pub fn rb_free_lift_out(ctx: *mut rb_ctx, out: *mut rb_lift_out);
     pub fn rb_free_stats_out(ctx: *mut rb_ctx, stats: *mut rb_stats_out);
     pub fn rb_sort_windows(n: u32, t_id: *const u32, st: *const u64, perm_out: *mut u32) -> c_int;
+    /// myio.rs:41-64 — the inflate step of `reader()` for BGZF input, on the device; `text` is pinned, library-owned (rb_free_text)
+    pub fn rb_is_bgzf(data: *const u8, nbytes: u64) -> c_int;
+    pub fn rb_inflate_bgzf(ctx: *mut rb_ctx, bgzf: *const u8, nbytes: u64, text: *mut *mut u8, text_nbytes: *mut u64) -> c_int;
+    pub fn rb_free_text(ctx: *mut rb_ctx, text: *mut u8);
     pub fn rb_host_register(ptr: *mut c_void, nbytes: u64) -> c_int;
     pub fn rb_host_unregister(ptr: *mut c_void) -> c_int;
     pub fn rb_trim_paf_begin(ctx: *mut rb_ctx, recs: *const rb_records, match_score: c_int, diff_score: c_int, indel_score: c_int, policy: c_int) -> c_int;

@@ -25,7 +25,7 @@ EXPORTS = [
     "rb_ctx_create", "rb_ctx_destroy", "rb_last_error", "rb_ctx_set_stream", "rb_ctx_set_profiling", "rb_ctx_set_lift_mode", "rb_ctx_set_slicing", "rb_ctx_kernel_times",
     "rb_liftover", "rb_stats", "rb_break_paf", "rb_invert", "rb_trim_paf", "rb_trim_paf_begin", "rb_trim_paf_round", "rb_trim_paf_end", "rb_batch_break", "rb_free_lift_out", "rb_free_stats_out", "rb_batch_upload", "rb_batch_liftover", "rb_batch_stats",
     "rb_batch_download_lift", "rb_batch_download_stats", "rb_batch_free", "rb_sort_windows", "rb_version", "rb_host_register",
-    "rb_host_unregister",
+    "rb_host_unregister", "rb_is_bgzf", "rb_inflate_bgzf", "rb_free_text",
 ]
 
 u8p, u32p, u64p, f32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_float)
@@ -111,6 +111,9 @@ def load():
     lib.rb_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb_sort_windows.argtypes = [C.c_uint32, u32p, u64p, u32p]
     lib.rb_version.restype = C.c_char_p
+    lib.rb_is_bgzf.argtypes = [C.c_char_p, C.c_uint64]
+    lib.rb_inflate_bgzf.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.rb_free_text.argtypes = [C.c_void_p, C.c_void_p]
     lib.rb_host_register.argtypes = [C.c_void_p, C.c_uint64]
     lib.rb_host_unregister.argtypes = [C.c_void_p]
     _lib = lib
@@ -321,6 +324,14 @@ class Context:
         if stats:
             self.lib.rb_free_stats_out(self.h, C.byref(st))
         return res
+
+    def inflate_bgzf(self, data: bytes) -> bytes:
+        """rb_inflate_bgzf: the blocks of a BGZF file (myio.rs:41-64) inflated on the device, CRC-32 / ISIZE verified."""
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.lib.rb_inflate_bgzf(self.h, data, len(data), C.byref(p), C.byref(n)))
+        out = C.string_at(p.value, n.value) if n.value else b""
+        self.lib.rb_free_text(self.h, p)
+        return out
 
     def invert(self, recs: Records, want=WANT_TEXT | WANT_NUMERIC, copy=True):
         """rb_invert: every record with query and target swapped (paf.rs:1050-1094), rows in file order."""

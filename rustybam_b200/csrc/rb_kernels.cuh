@@ -208,6 +208,13 @@ void launch_trim_rounds(int n_rounds, bool auto_done, const uint32_t* grp_off, u
                         uint8_t* contained, void* sel, unsigned long long* keys, void* info, cudaStream_t s);
 void launch_trim_rows(uint32_t n_rec, const RecInfo* recs, const TrimView* views, const uint32_t* ops, const Ctr* samples,
                       const uint8_t* dropped, PairRes* res, uint32_t* line_len, uint64_t* pair_off, LiftPlan* plans, cudaStream_t s);
+// BGZF inflate on the device (inflate_kernels.cu): one table row per block, one thread per block
+struct BgzfBlock {
+    uint64_t cdata;    // offset of the block's raw DEFLATE payload in the compressed buffer
+    uint64_t out_off;  // where its bytes go in the inflated text
+    uint32_t clen, out_len, crc, pad;  // payload bytes, ISIZE and CRC-32 of the trailer
+};
+void launch_inflate_bgzf(const uint8_t* comp, const BgzfBlock* blk, uint32_t n_blk, uint8_t* out, unsigned long long* err, cudaStream_t s);
 void launch_win_check(const uint32_t* t_id, const uint64_t* st, const uint64_t* en, const uint32_t* row, uint32_t n_win,
                       uint32_t n_names, uint32_t* flags, cudaStream_t s);
 // general path (unsorted / nested BED rows): the reference's cartesian product + overlap filter (liftover.rs:123-127)

@@ -15,6 +15,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/mman.h>
+
 #include "../../include/rbcuda.h"
 #include "rb_kernels.cuh"
 #include "rec_core.cuh"
@@ -62,7 +64,49 @@ struct PinnedBlock {
     void* p = nullptr;
     size_t cap = 0;
     bool in_use = false;
+    bool mapped = false;  // big_pinned_alloc (mmap + cudaHostRegister) instead of cudaHostAlloc
 };
+
+// Page-locked host memory for the large output blocks.  cudaHostAlloc locks pages at ~2.3 GB/s (16 GiB: 7.1 s — the driver
+// faults them in one by one), which made the first rb_liftover of a process that returns C5's 17.6 GB take 12 s.  An anonymous
+// mapping first-touched by a few host threads and then registered takes 0.6 s for 16 GiB and copies at the same
+// 55 GB/s (tools/pin_bench.cu, profiles/r02_pin_bench.json).  Portable: every device of a multi-device context copies into it.
+constexpr size_t BIG_PIN_MIN = 64ull << 20;
+void* big_pinned_alloc(size_t n) {
+    void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (q == MAP_FAILED) return nullptr;
+    madvise(q, n, MADV_HUGEPAGE);
+    unsigned nthr = std::thread::hardware_concurrency();
+    nthr = nthr < 1 ? 1 : (nthr > 16 ? 16 : nthr);
+    {
+        std::vector<std::thread> th;
+        uint8_t* b = static_cast<uint8_t*>(q);
+        for (unsigned t = 0; t < nthr; t++)
+            th.emplace_back([=] {
+                const size_t lo = n / nthr * t, hi = (t + 1 == nthr) ? n : n / nthr * (t + 1);
+                for (size_t i = lo; i < hi; i += 4096) b[i] = 0;
+            });
+        for (auto& x : th) x.join();
+    }
+    // ONE registration for the whole block: the library's copies into it (2-D ones among them) may start and end anywhere, and a
+    // copy must not span two registrations.  If the driver refuses a range this large the caller falls back to cudaHostAlloc.
+    if (cudaHostRegister(q, n, cudaHostRegisterPortable) != cudaSuccess) {
+        (void)cudaGetLastError();
+        munmap(q, n);
+        return nullptr;
+    }
+    return q;
+}
+void big_pinned_free(void* q, size_t n) {
+    cudaHostUnregister(q);
+    munmap(q, n);
+}
+void pinned_block_free(PinnedBlock* b) {
+    if (!b->p) return;
+    if (b->mapped) big_pinned_free(b->p, b->cap);
+    else cudaFreeHost(b->p);
+    b->p = nullptr;
+}
 
 struct KEvent {
     const char* name;
@@ -196,14 +240,19 @@ PinnedBlock* pinned_get(rb_ctx* ctx, size_t n) {
         // drop the largest idle block that is too small, so the pool does not grow without bound
         for (size_t i = 0; i < ctx->pinned.size(); i++)
             if (!ctx->pinned[i]->in_use) {
-                cudaFreeHost(ctx->pinned[i]->p);
+                pinned_block_free(ctx->pinned[i]);
                 delete ctx->pinned[i];
                 ctx->pinned.erase(ctx->pinned.begin() + (long)i);
                 break;
             }
         best = new PinnedBlock();
-        const size_t want = n + n / 8 + 4096;
-        if (cudaHostAlloc(&best->p, want, cudaHostAllocPortable) != cudaSuccess) {  // (portable: every device of a multi-device context copies into it)
+        size_t want = n + n / 8 + 4096;
+        if (want >= BIG_PIN_MIN && !getenv("RB_PIN_HOSTALLOC")) {
+            want = (want + 4095) / 4096 * 4096;
+            best->p = big_pinned_alloc(want);
+            best->mapped = best->p != nullptr;
+        }
+        if (!best->p && cudaHostAlloc(&best->p, want, cudaHostAllocPortable) != cudaSuccess) {  // (portable: every device of a multi-device context copies into it)
             (void)cudaGetLastError();
             delete best;
             return nullptr;
@@ -533,7 +582,7 @@ void rb_ctx_destroy(rb_ctx* ctx) {
     for (int k = 0; k < 2; k++) if (ctx->ev_up[k]) cudaEventDestroy(ctx->ev_up[k]);
     if (ctx->ev_win) cudaEventDestroy(ctx->ev_win);
     if (ctx->ev_wfirst) cudaEventDestroy(ctx->ev_wfirst);
-    for (PinnedBlock* b : ctx->pinned) { cudaFreeHost(b->p); delete b; }
+    for (PinnedBlock* b : ctx->pinned) { pinned_block_free(b); delete b; }
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     ctx->scalars.release();
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
@@ -1453,6 +1502,87 @@ void rb_free_stats_out(rb_ctx*, rb_stats_out* st) {
     if (!st) return;
     if (st->_owner) reinterpret_cast<PinnedBlock*>(st->_owner)->in_use = false;
     memset(st, 0, sizeof *st);
+}
+
+// ---- BGZF inflate (myio.rs:41-64: the `.bgz` reader) ----------------------------------------------
+// One table row per block from a hop over the headers (RFC 1952 + the 'BC' extra field of the SAM spec, 4.1); false if
+// `p` is not a well-formed series of BGZF blocks.
+static bool bgzf_blocks(const uint8_t* p, uint64_t n, std::vector<BgzfBlock>& blocks, uint64_t& total) {
+    uint64_t pos = 0;
+    total = 0;
+    while (pos < n) {
+        if (n - pos < 18 || p[pos] != 0x1f || p[pos + 1] != 0x8b || p[pos + 2] != 8 || !(p[pos + 3] & 4)) return false;
+        const uint64_t xlen = p[pos + 10] | ((uint64_t)p[pos + 11] << 8);
+        uint64_t x = pos + 12, bsize = 0;
+        const uint64_t xend = x + xlen;
+        if (xend > n) return false;
+        while (x + 4 <= xend) {
+            const uint64_t slen = p[x + 2] | ((uint64_t)p[x + 3] << 8);
+            if (p[x] == 'B' && p[x + 1] == 'C' && slen == 2 && x + 6 <= xend) bsize = (uint64_t)(p[x + 4] | (p[x + 5] << 8)) + 1;
+            x += 4 + slen;
+        }
+        if (bsize == 0 || pos + bsize > n || bsize < xlen + 20) return false;
+        auto le32 = [&](uint64_t at) { return (uint32_t)p[at] | ((uint32_t)p[at + 1] << 8) | ((uint32_t)p[at + 2] << 16) | ((uint32_t)p[at + 3] << 24); };
+        BgzfBlock b{};
+        b.cdata = xend; b.clen = (uint32_t)(bsize - xlen - 20); b.out_off = total;
+        b.crc = le32(pos + bsize - 8); b.out_len = le32(pos + bsize - 4);
+        if (b.out_len > 65536u) return false;  // (the format's bound; keeps a block's output offsets in 32 bits)
+        if (b.out_len) blocks.push_back(b);    // (the empty end-of-file marker block has nothing to inflate)
+        total += b.out_len;
+        pos += bsize;
+    }
+    return true;
+}
+int rb_is_bgzf(const uint8_t* data, uint64_t nbytes) {
+    return data && nbytes >= 18 && data[0] == 0x1f && data[1] == 0x8b && data[2] == 8 && (data[3] & 4) && data[12] == 'B' && data[13] == 'C';
+}
+int rb_inflate_bgzf(rb_ctx* ctx, const uint8_t* bgzf, uint64_t nbytes, uint8_t** text, uint64_t* text_nbytes) {
+    if (!ctx) return RB_ERR_NO_DEVICE;
+    if (!text || !text_nbytes || (!bgzf && nbytes)) return fail(ctx, RB_ERR_BAD_ARG, "rb_inflate_bgzf: null argument");
+    *text = nullptr; *text_nbytes = 0;
+    std::vector<BgzfBlock> blocks;
+    uint64_t total = 0;
+    if (!bgzf_blocks(bgzf, nbytes, blocks, total)) return fail(ctx, RB_ERR_BAD_ARG, "rb_inflate_bgzf: not a well-formed series of BGZF blocks");
+    if (blocks.size() > 0xFFFFFFF0ull) return fail(ctx, RB_ERR_UNSUPPORTED, "rb_inflate_bgzf: more than 2^32 blocks");
+    cudaSetDevice(ctx->device);
+    cudaStream_t s = ctx->stream;
+    PinnedBlock* blk = pinned_get(ctx, (size_t)total + 64);
+    if (!blk) return fail(ctx, RB_ERR_OOM, "rb_inflate_bgzf: %llu bytes of pinned host memory", (unsigned long long)total);
+    auto bail = [&](int rc) { blk->in_use = false; return rc; };
+    if (total == 0) { *text = static_cast<uint8_t*>(blk->p); return RB_OK; }
+    DevBuf d_comp, d_blk, d_out, d_err;
+    auto release = [&] { d_comp.release(); d_blk.release(); d_out.release(); d_err.release(); };
+    if (d_comp.ensure(nbytes + 64) != cudaSuccess || d_blk.ensure(blocks.size() * sizeof(BgzfBlock)) != cudaSuccess ||
+        d_out.ensure(total + 64) != cudaSuccess || d_err.ensure(8) != cudaSuccess) {
+        (void)cudaGetLastError();
+        release();
+        return bail(fail(ctx, RB_ERR_OOM, "rb_inflate_bgzf: device memory for %llu + %llu bytes", (unsigned long long)nbytes, (unsigned long long)total));
+    }
+    unsigned long long h_err = ~0ull;
+    cudaError_t e = h2d_copy(d_comp.p, bgzf, nbytes, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_blk.p, blocks.data(), blocks.size() * sizeof(BgzfBlock), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_err.p, 0xFF, 8, s);
+    if (e == cudaSuccess) {
+        KScope k(ctx, "k_inflate_bgzf");
+        launch_inflate_bgzf(d_comp.as<uint8_t>(), d_blk.as<BgzfBlock>(), (uint32_t)blocks.size(), d_out.as<uint8_t>(), d_err.as<unsigned long long>(), s);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h_err, d_err.p, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(blk->p, d_out.p, total, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    flush_times(ctx);
+    release();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return bail(fail(ctx, RB_ERR_CUDA, "rb_inflate_bgzf: %s", cudaGetErrorString(e))); }
+    if (h_err != ~0ull)
+        return bail(fail(ctx, RB_ERR_BAD_ARG, "rb_inflate_bgzf: corrupt DEFLATE data in block %llu (code %u)", (unsigned long long)(h_err >> 8), (unsigned)(h_err & 0xFF)));
+    *text = static_cast<uint8_t*>(blk->p);
+    *text_nbytes = total;
+    return RB_OK;
+}
+void rb_free_text(rb_ctx* ctx, uint8_t* text) {
+    if (!ctx || !text) return;
+    for (PinnedBlock* b : ctx->pinned)
+        if (b->p == text) b->in_use = false;
 }
 
 // ---- rb_liftover in slices -----------------------------------------------------------------------

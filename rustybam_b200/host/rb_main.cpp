@@ -85,12 +85,33 @@ int main(int argc, char** argv) {
         return 3;
     }
     mark("ctx_create");
+    // PAF input (myio.rs:41-64): a `.bgz` / `.gz` file that is BGZF has its blocks inflated on the device (rb_inflate_bgzf) and the
+    // lines are parsed out of the pinned buffer that comes back; RB_GPU_INFLATE=0 keeps the host's block-parallel zlib reader.
+    // A plain gzip member, stdin and uncompressed files go through rbh::read_all as before.
+    auto load_paf = [&](const std::string& path) {
+        auto ends_with = [&](const char* suf) { const size_t n = strlen(suf); return path.size() >= n && path.compare(path.size() - n, n, suf) == 0; };
+        const char* sw = getenv("RB_GPU_INFLATE");
+        if (path != "-" && (ends_with(".bgz") || ends_with(".gz")) && !(sw && sw[0] == '0')) {
+            const std::string raw = rbh::read_raw(path);
+            if (rb_is_bgzf(reinterpret_cast<const uint8_t*>(raw.data()), raw.size())) {
+                uint8_t* text = nullptr;
+                uint64_t n = 0;
+                if (rb_inflate_bgzf(ctx, reinterpret_cast<const uint8_t*>(raw.data()), raw.size(), &text, &n) != RB_OK)
+                    throw rbh::Panic("error inflating " + path + ": " + rb_last_error(ctx));
+                mark("gpu_inflate");
+                rbh::Paf paf = rbh::Paf::from_text(reinterpret_cast<const char*>(text), (size_t)n);
+                rb_free_text(ctx, text);
+                return paf;
+            }
+        }
+        return rbh::Paf::from_file(path);
+    };
     int rc = 0;
     try {
         if (cmd == "stats") {
             fputs(rbh::stats_header(qbed).c_str(), stdout);  // printed before the input is read (main.rs:51)
             fflush(stdout);
-            rbh::Paf paf = rbh::Paf::from_file(input);
+            rbh::Paf paf = load_paf(input);
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rb_records recs = paf.view();
             rb_stats_out st{};
@@ -100,7 +121,7 @@ int main(int argc, char** argv) {
                 rb_free_stats_out(ctx, &st);
             }
         } else if (brk) {
-            rbh::Paf paf = rbh::Paf::from_file(input);
+            rbh::Paf paf = load_paf(input);
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rb_records recs = paf.view();
             rb_lift_out out{};
@@ -110,7 +131,7 @@ int main(int argc, char** argv) {
                 rb_free_lift_out(ctx, &out);
             }
         } else if (is_trim) {
-            rbh::Paf paf = rbh::Paf::from_file(input);
+            rbh::Paf paf = load_paf(input);
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rb_records recs = paf.view();
             rb_lift_out out{};
@@ -120,7 +141,7 @@ int main(int argc, char** argv) {
                 rb_free_lift_out(ctx, &out);
             }
         } else if (inv) {
-            rbh::Paf paf = rbh::Paf::from_file(input);
+            rbh::Paf paf = load_paf(input);
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rb_records recs = paf.view();
             rb_lift_out out{};
@@ -133,7 +154,7 @@ int main(int argc, char** argv) {
             if (bed.empty()) return usage();
             const std::string bed_text = rbh::read_all(bed);
             mark("read_bed");
-            rbh::Paf paf = rbh::Paf::from_file(input);
+            rbh::Paf paf = load_paf(input);
             mark("read_parse_paf");
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rbh::Windows wins = rbh::Windows::pack_text(bed_text.data(), bed_text.size(), paf);  // bed::parse_bed + sort, all host threads

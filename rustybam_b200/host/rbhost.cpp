@@ -93,6 +93,8 @@ static bool inflate_bgzf(const std::string& raw, std::string& text) {
     return ok.load();
 }
 
+std::string read_raw(const std::string& path) { return read_plain(path); }
+
 std::string read_all(const std::string& path) {
     auto ends_with = [&](const char* suf) {
         const size_t n = strlen(suf);

@@ -47,6 +47,7 @@ struct Panic : std::runtime_error {  // the reference would panic (exit status 1
 };
 
 std::string read_all(const std::string& path);  // "-" = stdin; .gz/.bgz inflated with zlib
+std::string read_raw(const std::string& path);  // the file's bytes as they are (the caller inflates: rb_inflate_bgzf)
 
 // Packed records (what rb_records points into).  Name ids are shared by query and target names.
 struct Paf {
