@@ -1971,7 +1971,12 @@ static int liftover_sliced(rb_ctx* ctx, const rb_records* recs, const rb_windows
     // ---- slice boundaries (record granularity, balanced on CIGAR bytes) and an upper bound on the rows ----
     const uint32_t n = recs->n_rec;
     const uint64_t total_bytes = recs->cigar_nbytes;
-    const uint32_t K = (uint32_t)std::min<uint64_t>(8ull * (uint64_t)D, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
+    // at most 8 slices per device (RB_MAX_SLICES overrides).  Measured at C5 on one B200 (12.6 GB up, 17.6 GB down): 8 / 16 / 32 / 64
+    // slices -> 447 / 431 / 433 / 436 ms per call, 30 / 15 / 8 / 4 GB of HBM in use, 1.6 / 2.6 / 2.7 / 3.5 s for the first call:
+    // the fill and drain of the pipeline are not what keeps the call at 70 of the link's 95 GB/s (both directions)
+    uint64_t k_cap = 8ull * (uint64_t)D;
+    if (const char* e = getenv("RB_MAX_SLICES")) k_cap = std::max<uint64_t>(2, strtoull(e, nullptr, 10));
+    const uint32_t K = (uint32_t)std::min<uint64_t>(k_cap, std::max<uint64_t>(2, total_bytes / SLICE_MIN_BYTES));
     std::vector<uint32_t> cut(1, 0);  // slice k = records ord[cut[k] .. cut[k+1]) : consecutive in EMISSION order
     {
         // the very first slice is half the size of the others: its rows reach the copy engine sooner, yet their download still
