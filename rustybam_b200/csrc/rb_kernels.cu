@@ -220,6 +220,9 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
            ErrSlots err, uint32_t* misc_flags) {
     __shared__ __align__(16) uint8_t s_text[16 + TOK_TILE + 16];
     __shared__ uint16_t s_pos[TOK_TILE / 2];
+#if RB_TOK_EARLY_PUBLISH
+    __shared__ uint32_t s_opw[TOK_TILE / 2];  // decoded op words wait here for the tile's place in the op array
+#endif
     __shared__ uint8_t s_lut[256];  // byte -> BAM op code (15 = not an op character)
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ uint32_t s_warp[TOK_THREADS / 32];
@@ -258,7 +261,6 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
         uint32_t mm = m16, k = 0;
         // exclusive index inside the warp is known now; the warp offset is added after the barrier
         const uint32_t wex = inc - cnt;
-        // stash (warp-relative) positions in registers' stead: write after the barrier
         __syncthreads();
         uint32_t wpre = 0, total = 0;
 #pragma unroll
@@ -267,10 +269,17 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
             if (w < warp) wpre += t;
             total += t;
         }
+#if RB_TOK_EARLY_PUBLISH
+        // The tile's op count is published NOW and its place in the op array asked for only after the ops are decoded: the
+        // decode needs no global index, and by then the tiles in front have published theirs (the block used to sit at a
+        // barrier while warp 0 walked the look-back: a third of the kernel's stall samples)
+        if (tid == 0) lb_publish(tile_state, tile, total);
+#else
         if (warp == 0) {
             const unsigned long long ex = lookback_u64(tile_state, tile, total);
             if (lane == 0) s_base = ex;
         }
+#endif
         uint32_t idx = wpre + wex;
         while (mm) {
             const uint32_t j = __ffs(mm) - 1;
@@ -279,10 +288,12 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
             k++;
         }
         __syncthreads();
-        const uint64_t base = s_base;
         const uint32_t* s_w = reinterpret_cast<const uint32_t*>(s_text);
         uint32_t seen_codes = 0;                            // bit c set: an op of code c was seen
+#if !RB_TOK_EARLY_PUBLISH
+        const uint64_t base = s_base;
         uint32_t* out_ops = ops + base;
+#endif
         for (uint32_t q = tid; q < total; q += TOK_THREADS) {
             const uint32_t e = s_pos[q];                    // op character at tile byte e
             const uint32_t a = (e + 8) >> 2, sh = ((e + 8) & 3) * 8;
@@ -310,10 +321,24 @@ k_tokenise(const uint8_t* __restrict__ text, uint32_t* __restrict__ ops, unsigne
                 if (nd > 4u) len += parse4((uint32_t)x) * 10000u;
             }
             seen_codes |= 1u << code;
-            out_ops[q] = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
+            const uint32_t word = (len << 4) | (code == 15u ? (uint32_t)OP_P : code);  // invalid characters were reported above
+#if RB_TOK_EARLY_PUBLISH
+            s_opw[q] = word;
+#else
+            out_ops[q] = word;
+#endif
         }
         const uint32_t seen_clip = seen_codes & ((1u << OP_S) | (1u << OP_H));
         if (seen_clip) atomicOr(misc_flags, 1u);
+#if RB_TOK_EARLY_PUBLISH
+        if (warp == 0) {
+            const unsigned long long ex = lb_walk(tile_state, tile, total);
+            if (lane == 0) s_base = ex;
+        }
+        __syncthreads();
+        uint32_t* out_ops = ops + s_base;
+        for (uint32_t q = tid; q < total; q += TOK_THREADS) out_ops[q] = s_opw[q];
+#endif
     }
 }
 

@@ -12,6 +12,9 @@ namespace rb {
 #define RB_TOK_THREADS 256
 #endif
 constexpr int TOK_THREADS = RB_TOK_THREADS;
+#ifndef RB_TOK_EARLY_PUBLISH
+#define RB_TOK_EARLY_PUBLISH 1  // k_tokenise: op count published before the decode, look-back walked after it (0: the round-1 order)
+#endif
 constexpr int TOK_TILE = TOK_THREADS * 16;  // text bytes per tokeniser tile
 constexpr int TEXT_FRONT_PAD = 16;          // bytes of 0xFF in front of the text (look-behind halo of tile 0)
 #ifndef RB_SMP_THREADS
