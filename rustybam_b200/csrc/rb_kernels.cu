@@ -2284,6 +2284,7 @@ constexpr int EMIT_UNI_BYTES = EMIT_SMP_BYTES + EMIT_ACC_BYTES;                 
 constexpr int EMIT_DYN_BYTES = EMIT_OPS_BYTES + EMIT_UNI_BYTES;                   // (other blocks compose in all of it)
 constexpr uint32_t FRAG_CAP = 96, FRAG_NAME_MAX = 64;
 constexpr int EMIT_MID_BYTES = SER_LINES * 16;  // the descriptors of copy_mids (blocks that do not lift)
+constexpr int EMIT_REL2_BYTES = (SER_LINES + 4) * 4;  // ... and, in front of them, the prefix of their line sizes without the direct runs
 constexpr uint32_t MID_COOP = 96;  // runs of untouched ops at least this long are copied by a warp instead of their line's thread
 static_assert(EMIT_OPS_BYTES % 16 == 0 && EMIT_SMP_BYTES % 16 == 0, "staging areas are 16-byte aligned");
 static_assert(EMIT_UNI_BYTES >= (int)EMIT_LONG + 64, "one round holds at least one line");
@@ -2434,7 +2435,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
     extern __shared__ __align__(16) uint8_t s_emit[];
     __shared__ uint32_t s_rel[SER_LINES + 1];
     __shared__ unsigned long long s_wb[SER_LINES / 32];
-    __shared__ uint32_t s_wc[SER_LINES / 32];
+    __shared__ uint32_t s_wc[SER_LINES / 32], s_w2[SER_LINES / 32];
     __shared__ unsigned long long s_base[2];
     __shared__ unsigned int s_blk;
     __shared__ __align__(16) RecInfo s_rec;
@@ -2559,11 +2560,12 @@ k_emit(const __grid_constant__ EmitArgs e) {
             if (len) pr = e.res[p];
         }
         s_buf = s_emit;
-        buf_cap = (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES);
+        buf_cap = (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);
     }
     // blocks that do not lift keep, behind their line buffer, one descriptor per line: a run of input text its owner left to the
     // warps (src lo, src hi, dst offset, bytes)
     uint4* s_mid = reinterpret_cast<uint4*>(s_emit + EMIT_DYN_BYTES - EMIT_MID_BYTES);
+    uint32_t* s_rel2 = reinterpret_cast<uint32_t*>(s_emit + EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);  // (blocks that do not lift only)
     bool live = len != 0u;
     if (!live) { r = 0; w = 0; }
     else if (!fast) {
@@ -2593,30 +2595,46 @@ k_emit(const __grid_constant__ EmitArgs e) {
               ndigits32(pr.diff) + ndigits32(pr.del_ev) + ndigits32(pr.ins_ev) + ndigits32(pr.del) + ndigits32(pr.ins) + 2u + 8u + 1u;
     }
 
-    // ---- block scan of (bytes, rows) ----
+    // A long run of untouched ops (wide windows: ~430 bytes of a ~560-byte row at 10 kb) can leave the input text for the
+    // output without passing through the line buffer (DIRECT blocks, below): which of my line's bytes are such a run
+    uint32_t dml = 0;
+    if (!STATS_TEXT && !fast && live && pr.mid_len >= MID_COOP) {
+        const uint32_t fl = e.a.recs[r].flags;
+        if ((fl & RF_CANON) && (pr.kind == PK_EARLY || (pr.kind == PK_TRIM && pr.ei > pr.si && !(fl & RF_SLOW)))) dml = pr.mid_len;
+    }
+    // ---- block scan of (bytes, rows, bytes without the direct runs) ----
     unsigned long long ib = len;
-    uint32_t ic = live ? 1u : 0u;
+    uint32_t ic = live ? 1u : 0u, i2 = len - dml;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned long long ub = __shfl_up_sync(0xffffffffu, ib, d);
         const uint32_t uc = __shfl_up_sync(0xffffffffu, ic, d);
-        if (lane >= d) { ib += ub; ic += uc; }
+        const uint32_t u2 = __shfl_up_sync(0xffffffffu, i2, d);
+        if (lane >= d) { ib += ub; ic += uc; i2 += u2; }
     }
-    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
+    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; s_w2[warp] = i2; }
     const bool small = __syncthreads_and(len <= EMIT_LONG) != 0;
     unsigned long long wb = 0, tb = 0;
-    uint32_t wc = 0, tc = 0;
+    uint32_t wc = 0, tc = 0, w2 = 0, t2 = 0;
 #pragma unroll
     for (int k = 0; k < SER_LINES / 32; k++) {
-        if (k < warp) { wb += s_wb[k]; wc += s_wc[k]; }
-        tb += s_wb[k]; tc += s_wc[k];
+        if (k < warp) { wb += s_wb[k]; wc += s_wc[k]; w2 += s_w2[k]; }
+        tb += s_wb[k]; tc += s_wc[k]; t2 += s_w2[k];
     }
     const unsigned long long rel = wb + ib - len;  // bytes of the block's lines in front of mine
+    const uint32_t rel2 = w2 + i2 - (len - dml);    // ... without the direct runs
     s_rel[tid] = (uint32_t)rel;
-    if (tid == 0) s_rel[SER_LINES] = (uint32_t)tb;
+    if (!fast) s_rel2[tid] = rel2;
+    if (tid == 0) { s_rel[SER_LINES] = (uint32_t)tb; if (!fast) s_rel2[SER_LINES] = t2; }
 
     const bool want_text = e.out_text != nullptr && tb != 0;
     const bool compose_early = want_text && small;  // (block-uniform)
+    // DIRECT (block-uniform): a block that does not lift, whose runs are at least half of its bytes, and whose lines WITHOUT
+    // them fit the buffer at once.  Its lines are composed side by side without the runs (one round instead of three at
+    // 10 kb windows), each line's two pieces go out separately, and the runs are copied text -> output by a warp each —
+    // they used to go text -> shared memory -> output, a round of the block's barriers per 26 KB
+    const bool direct = RB_EMIT_DIRECT && !STATS_TEXT && !fast && compose_early && 2ull * (tb - t2) >= tb &&
+                        t2 + 32u <= (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);
 
     // one line into the staging buffer at `q` — FAST blocks: fragments + staged ops, no global loads
     auto compose = [&](uint8_t* q) {
@@ -2683,8 +2701,13 @@ k_emit(const __grid_constant__ EmitArgs e) {
             // and leaves the run to the block's warps (copy_mids below): coalesced loads of the input text by 32 lanes per
             // row instead of one lane walking it — and every thread of the block has work while the round is composed
             if (pr.kind == PK_TRIM) q = put_op(q, pr.s_len, op_code(v.op(pr.si)));
-            s_mid[tid] = make_uint4((uint32_t)pr.mid_off, (uint32_t)(pr.mid_off >> 32), (uint32_t)(q - (s_buf + 16)), pr.mid_len);
-            q += pr.mid_len;
+            if (direct) {  // the run is not given room here: .z = where it goes in the block's OUTPUT bytes
+                const uint32_t hl = (uint32_t)(q - (s_buf + 16)) - rel2;  // (< 2^16: lines of these blocks are at most EMIT_LONG bytes)
+                s_mid[tid] = make_uint4((uint32_t)pr.mid_off, (uint32_t)(pr.mid_off >> 32), (uint32_t)rel + hl, pr.mid_len | (hl << 16));
+            } else {
+                s_mid[tid] = make_uint4((uint32_t)pr.mid_off, (uint32_t)(pr.mid_off >> 32), (uint32_t)(q - (s_buf + 16)), pr.mid_len);
+                q += pr.mid_len;
+            }
             if (pr.kind == PK_TRIM) q = put_op(q, pr.e_len, op_code(v.op(pr.ei)));
         } else {
             SerArgs a2 = e.a;
@@ -2695,14 +2718,15 @@ k_emit(const __grid_constant__ EmitArgs e) {
     };
     // the runs the owners of lines [a, b) left behind: a warp per line, 4 bytes per lane and step, destination-aligned
     // shared-memory words assembled from two aligned words of the text (the buffer is padded: over-reads of < 8 bytes are fine)
+    uint8_t* mid_dst0 = s_buf + 16;  // (DIRECT blocks: the block's place in the output, once it is known)
     auto copy_mids = [&](uint32_t a, uint32_t b) {
         for (uint32_t L = a + (uint32_t)warp; L < b; L += SER_LINES / 32) {
             const uint4 d = s_mid[L];
             if (d.w == 0u) continue;
             const uint8_t* src = e.a.text + (((uint64_t)d.y << 32) | d.x);
-            uint8_t* dst = s_buf + 16 + d.z;
-            const uint32_t n = d.w;
-            const uint32_t head = (4u - (smem_u32(dst) & 3u)) & 3u;  // (n >= MID_COOP > 3)
+            uint8_t* dst = mid_dst0 + d.z;
+            const uint32_t n = direct ? (d.w & 0xFFFFu) : d.w;  // (DIRECT: the bytes in front of the run ride in the high half)
+            const uint32_t head = (4u - (uint32_t)((uintptr_t)dst & 3u)) & 3u;  // (n >= MID_COOP > 3; shared or global: the low bits agree)
             if ((uint32_t)lane < head) dst[lane] = __ldg(src + lane);
             const uint32_t nw = (n - head) >> 2, rem = (n - head) & 3u;
             const uint8_t* sb = src + head;
@@ -2744,7 +2768,10 @@ k_emit(const __grid_constant__ EmitArgs e) {
     if (tid == 0) lb_publish(e.lb_bytes, blk, tb);
     if (tid == 32) lb_publish(e.lb_rows, blk, (unsigned long long)tc);
     if (!fast) s_mid[tid].w = 0u;
-    if (compose_early) {
+    if (compose_early && direct) {  // every line at once, side by side without its run; the runs wait for the block's place
+        end_line = nlines;
+        if (live) compose(s_buf + 16 + rel2);
+    } else if (compose_early) {
         end_line = round_end(0);
         if (live && (uint32_t)tid < end_line) compose(s_buf + 16 + (uint32_t)rel);
         if (!fast) {  // (block-uniform)
@@ -2800,6 +2827,23 @@ k_emit(const __grid_constant__ EmitArgs e) {
         return;
     }
     if (tid == 0) e.blk_flags[blk] = 0u;
+    if (direct) {  // (block-uniform) the two pieces of every line, a warp per line; then the runs, text -> output, a warp per run
+        uint8_t* out0 = e.out_text + byte0;
+        for (uint32_t L = (uint32_t)warp; L < nlines; L += SER_LINES / 32) {
+            const uint32_t c0 = s_rel2[L], cl = s_rel2[L + 1] - c0;
+            if (cl == 0u) continue;
+            const uint8_t* src = s_buf + 16 + c0;
+            uint8_t* dst = out0 + s_rel[L];
+            const uint32_t dw = s_mid[L].w;
+            uint32_t hl = cl, skip = 0u;             // one piece ...
+            if (dw) { hl = dw >> 16; skip = dw & 0xFFFFu; }  // ... or two with the run in between
+            for (uint32_t i = (uint32_t)lane; i < hl; i += 32u) dst[i] = src[i];
+            for (uint32_t i = hl + (uint32_t)lane; i < cl; i += 32u) dst[skip + i] = src[i];
+        }
+        mid_dst0 = out0;
+        copy_mids(0, nlines);
+        return;
+    }
     for (;;) {  // (block-uniform)
         const uint32_t cur = s_rel[cur_line];
         copy_out_shifted(e.out_text + byte0 + cur, s_buf + 16, s_rel[end_line] - cur);

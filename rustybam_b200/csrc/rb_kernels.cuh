@@ -45,6 +45,9 @@ constexpr int SL_WCAP = 2048;                // window boundaries of one block s
 #ifndef RB_EMIT_MINB
 #define RB_EMIT_MINB 6
 #endif
+#ifndef RB_EMIT_DIRECT
+#define RB_EMIT_DIRECT 1  // k_emit: blocks whose rows are mostly long verbatim runs copy those text -> output directly (0: through the line buffer)
+#endif
 #ifndef RB_EMIT_MID_TEXT
 #define RB_EMIT_MID_TEXT 0  // k_emit FAST blocks: short runs of untouched ops are copied from the input text (0: formatted from the op words)
 #endif
