@@ -240,7 +240,8 @@ def algorithmic_bytes(summ, n_win, n_rec):
     """compulsory bytes of one liftover(+fused stats) step, and per kernel given the layout of DESIGN §3."""
     n_ops, n_pairs, n_out = summ["n_ops"], summ["n_pairs"], summ["n_out"]
     out_bytes, cigar_bytes = summ["out_bytes"], summ["cigar_bytes"]
-    smp_bytes = (n_ops // 32) * 4 * 48  # 1 sample + 3 sub-samples of 48 B per 32-op chunk
+    # 1 sample + 3 sub-samples of 48 B per 32-op chunk; wide windows (more than 64 ops per pair): the sample only (rbcuda.cu, RB_SUBS)
+    smp_bytes = (n_ops // 32) * 48 * (1 if (n_pairs and n_ops > 64 * n_pairs) else 4)
     per_kernel = {
         "k_tokenise": cigar_bytes + 4 * n_ops,                       # text in, one 4-byte op word out
         "k_samples": 4 * n_ops + smp_bytes,                          # op words in, samples out

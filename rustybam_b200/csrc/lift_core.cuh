@@ -43,9 +43,12 @@ struct OpsView {
         return (e.aux & SUB_ABS) ? e.T : e.T + ent(c, 0).T;
     }
     // counters of the record before op 32c + 8s (the position must lie inside the record, after its first op)
+    // k_samples leaves the sub-samples out when windows are wide (one boundary per ~100 ops makes them dead weight: three
+    // quarters of its stores) and says so in the chunk's absolute sample: SUB_ABS set in entry 0 = "no entries 1..3 here"
+    RB_HD bool no_subs(uint64_t c) const { return (ent(c, 0).aux & SUB_ABS) != 0; }
     RB_HD Ctr at(uint64_t c, uint32_t s) const {
         Ctr e = ent(c, s);
-        if (s == 0) return e;
+        if (s == 0) { e.aux &= ~SUB_ABS; return e; }
         const bool abs = (e.aux & SUB_ABS) != 0;
         e.aux = abs ? (e.aux & ~SUB_ABS) : 0u;  // absolute entries of k_tok_scan carry the overflow bit and the slow-op count themselves
         if (!abs) ctr_add(e, ent(c, 0));
@@ -58,10 +61,12 @@ enum : uint32_t { LIFT_OK = 0, LIFT_ERR_NOT_FOUND = 1 };  // NOT_FOUND == the re
 
 // Counters accumulated from the record's first op up to (excluding) op k (op_first <= k < op_end).
 RB_HD Ctr ctr_before(const OpsView& v, const RecInfo& r, uint64_t k, ClassAcc& acc) {
-    const uint64_t base = (k >> SUB_LOG2) << SUB_LOG2;
+    uint64_t base = (k >> SUB_LOG2) << SUB_LOG2;
+    const uint64_t cbase = (k >> SAMPLE_LOG2) << SAMPLE_LOG2;
+    if (base > cbase && base > r.op_first && v.no_subs(k >> SAMPLE_LOG2)) base = cbase;  // the chunk carries its absolute sample only
     Ctr c;
     uint64_t j;
-    if (base > r.op_first) { c = v.at(k >> SAMPLE_LOG2, (uint32_t)(k & (SAMPLE - 1)) >> SUB_LOG2); j = base; }
+    if (base > r.op_first) { c = v.at(k >> SAMPLE_LOG2, (uint32_t)(base & (SAMPLE - 1)) >> SUB_LOG2); j = base; }
     else { c = ctr_zero(); j = r.op_first; }
     acc_reset(acc);
     const uint64_t j0 = j;
@@ -131,7 +136,7 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
         const Ctr* e = v.chunk(lo);  // entry 0 = absolute sample, 1.. = sub-samples (relative unless SUB_ABS)
         const uint32_t T0 = e[0].T;
         uint32_t s = 0;  // last sub-sample of the chunk that lies inside the record and whose target prefix is <= p
-        for (uint32_t t = SUBS - 1; t >= 1; t--) {
+        for (uint32_t t = (e[0].aux & SUB_ABS) ? 0u : SUBS - 1; t >= 1; t--) {  // (SUB_ABS in entry 0: the chunk has none)
             const uint64_t pos = k0 + t * SUB_OPS;
             if (pos > r.op_first && pos < r.op_end && ((e[t].aux & SUB_ABS) ? e[t].T : e[t].T + T0) <= p) { s = t; break; }
         }
@@ -142,7 +147,7 @@ RB_HD bool find_op(const OpsView& v, const RecInfo& r, bool live, uint32_t p, ui
             c.aux = 0;
             if (!abs) ctr_add(c, e[0]);
         }
-        else if (k0 > r.op_first) c = e[0];
+        else if (k0 > r.op_first) { c = e[0]; c.aux &= ~SUB_ABS; }
         else k0 = r.op_first;
         const uint64_t left = r.op_end - k0;
         n = left > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)left;

@@ -802,7 +802,8 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
 template <bool LOCAL>
 __global__ void __launch_bounds__(SMP_THREADS, RB_SMP2_MINB)
 k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
-           Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket) {
+           Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
+           uint32_t no_subs /* != 0: absolute samples only, marked SUB_ABS (lift_core.cuh: OpsView::no_subs) */) {
     static_assert(SAMPLE == 32u, "k_samples2 walks 32-op chunks");
     extern __shared__ __align__(16) uint32_t s_dyn2[];
     uint4* s_ops4 = reinterpret_cast<uint4*>(s_dyn2);             // SMP_THREADS rows of 8 units
@@ -866,7 +867,7 @@ k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_
         uint32_t iev = 0, dev = 0, txt = 0, big = 0;
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            if (u && !(u & 1)) {  // ops 8, 16, 24: sub-sample = counters since the chunk start
+            if (u && !(u & 1) && !no_subs) {  // ops 8, 16, 24: sub-sample = counters since the chunk start
                 Ctr sub = ctr_zero();
                 acc.iev = iev; acc.dev = dev; acc.txt = txt; acc.big = big;
                 if (big >= ACC_BIG) { for (int t = 0; t < 4 * u; t++) ctr_add_op(sub, op_at(t)); }  // a class sum may have wrapped: exact
@@ -897,7 +898,7 @@ k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_
             const uint32_t w = op_at(j);
             const bool head = (h >> j) & 1u;
             if (head) { acc_reset(acc); slowc = 0; }
-            if (j && (j & (int)(SUB_OPS - 1)) == 0) {
+            if (j && (j & (int)(SUB_OPS - 1)) == 0 && !no_subs) {
                 Ctr sub = ctr_zero();
                 if (acc.big >= ACC_BIG) {
                     int j0 = 0;
@@ -964,6 +965,7 @@ k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_
     __syncthreads();
     SegVal pre = seg_combine(seg_combine(s_blk, wpre), exl);
     if (h & 1u) pre.c = ctr_zero();  // op 32c starts a record
+    if (no_subs) pre.c.aux = (pre.c.aux & ~SUB_ABS) | SUB_ABS;  // (the slow-op count keeps bits 0..29)
     if (nvalid) samples[chunk * SUBS] = pre.c;
 }
 
@@ -3014,7 +3016,7 @@ void launch_rec_ops(const uint8_t* text, const uint64_t* cigar_off, uint32_t n_r
 }
 void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
                       Ctr* samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
-                      LiftArgs la, cudaStream_t s) {
+                      LiftArgs la, cudaStream_t s, bool no_subs) {
     const uint64_t blocks = (n_ops_bound + SMP_OPS - 1) / SMP_OPS;
     if (blocks == 0) return;
     if (lift)
@@ -3024,10 +3026,11 @@ void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev,
         k_scan_lift<false><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(false), s>>>(ops, n_ops_dev, heads, samples, blk_state,
                                                                                         blk_agg, blk_pre, ticket, la);
     else if (!getenv("RB_SAMPLES_LOCAL"))
-        k_samples2<false><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+        k_samples2<false><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket,
+                                                                                 no_subs ? 1u : 0u);
     else {  // (measured, not faster: 0.24 + 0.06 + 0.07 ms against 0.31 ms at C4) block-local samples + aggregates, a one-block
             // scan of the aggregates, the prefixes added to the incomplete samples
-        k_samples2<true><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket);
+        k_samples2<true><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket, 0u);
         k_blk_scan<<<1, 1024, 0, s>>>(n_ops_dev, blk_agg, blk_pre);
         const uint64_t chunks = (n_ops_bound + SAMPLE - 1) / SAMPLE;
         k_smp_fix<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>(n_ops_dev, blk_pre, samples);

@@ -133,7 +133,7 @@ struct LiftArgs {
 // sampled segmented scan; lift == true additionally resolves the window boundaries of every record (fast path)
 void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev, uint64_t n_ops_bound, const uint32_t* heads,
                       Ctr* samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
-                      LiftArgs la, cudaStream_t s);
+                      LiftArgs la, cudaStream_t s, bool no_subs = false);  // no_subs: absolute samples only (wide windows)
 void launch_combine(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                     const uint32_t* ops, WinView win, const uint64_t* names_off, const HalfS* hs, const HalfE* he, PairRes* res,
                     uint32_t* line_len, ErrSlots err, cudaStream_t s);

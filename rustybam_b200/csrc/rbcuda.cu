@@ -431,7 +431,7 @@ int run_tok(rb_ctx* ctx, rb_batch* b) {
 }
 
 // sampled segmented scan of the prefix counters; `la` != nullptr: fused with the window-boundary resolution (fast path)
-int run_scan(rb_ctx* ctx, rb_batch* b, const LiftArgs* la) {
+int run_scan(rb_ctx* ctx, rb_batch* b, const LiftArgs* la, bool no_subs = false) {
     cudaStream_t s = ctx->stream;
     uint32_t* sc = ctx->scalars.as<uint32_t>();
     if (!la && b->have_samples) return RB_OK;  // k_tok_scan wrote them
@@ -439,7 +439,7 @@ int run_scan(rb_ctx* ctx, rb_batch* b, const LiftArgs* la) {
         KScope k(ctx, la ? "k_scan_lift" : "k_samples");
         launch_scan_lift(la != nullptr, b->ops.as<uint32_t>(), b->op_off.as<uint64_t>() + b->n_rec, b->ops_bound, b->heads.as<uint32_t>(),
                          b->samples.as<Ctr>(), b->blk_state.as<uint32_t>(), b->blk_agg.as<ScanPayload>(), b->blk_pre.as<ScanPayload>(),
-                         sc + SC_TICKET_SMP, la ? *la : LiftArgs{}, s);
+                         sc + SC_TICKET_SMP, la ? *la : LiftArgs{}, s, no_subs && !la);
     }
     CU(cudaGetLastError());
     return RB_OK;
@@ -1253,7 +1253,12 @@ int rb_batch_liftover(rb_ctx* ctx, rb_batch* b, int policy, uint32_t want, int w
                     win.st, win.en, b->half_s.as<HalfS>(), b->half_e.as<HalfE>()};
         rc = run_scan(ctx, b, &la);
     } else {
-        rc = run_scan(ctx, b, nullptr);
+        // wide windows (more than 64 ops per pair: one boundary per ~30 ops or fewer): the per-8-op sub-samples would serve a
+        // few percent of the chunks and cost k_samples three quarters of its stores — absolute samples only, the boundary
+        // walks of k_lift start at the chunk (<= 31 ops instead of <= 7).  RB_SUBS=1 / 0 in the environment forces either form.
+        static const char* subs_env = getenv("RB_SUBS");
+        const bool no_subs = subs_env ? subs_env[0] == '0' : (P > 0 && n_ops > 64ull * P);
+        rc = run_scan(ctx, b, nullptr, no_subs);
     }
     if (rc != RB_OK) return rc;
     {   // phase B: integrity, RF_SLOW, counters of the stripped op range

@@ -114,6 +114,16 @@ int main(int argc, char** argv) {
             ctr_add_op(rel, ops[k]);
         }
     }
+    // k_samples' wide-window form, on a random subset of the chunks (some cases: all of them): the absolute sample only, marked
+    // SUB_ABS, entries 1..3 never written (poisoned here) — every lookup has to come out the same
+    {
+        const uint64_t mode = U(0, 3);  // 0, 1: every chunk keeps its sub-samples; 2: a random half does; 3: none does
+        for (size_t c = 0; mode >= 2 && c * SAMPLE < ops.size(); c++) {
+            if (mode == 2 && U(0, 1)) continue;
+            samples[c * SUBS].aux |= SUB_ABS;
+            for (uint32_t t = 1; t < SUBS; t++) memset(&samples[c * SUBS + t], 0xA5, sizeof(Ctr));
+        }
+    }
     OpsView view;
     view.ops = ops.data(); view.samples = samples.data();
     uint32_t acc_mem[16];
