@@ -2611,23 +2611,39 @@ k_emit(const __grid_constant__ EmitArgs e) {
     for (int d = 1; d < 32; d <<= 1) {
         const unsigned long long ub = __shfl_up_sync(0xffffffffu, ib, d);
         const uint32_t uc = __shfl_up_sync(0xffffffffu, ic, d);
-        const uint32_t u2 = __shfl_up_sync(0xffffffffu, i2, d);
-        if (lane >= d) { ib += ub; ic += uc; i2 += u2; }
+        if (lane >= d) { ib += ub; ic += uc; }
     }
-    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; s_w2[warp] = i2; }
+    if (!fast) {  // (block-uniform: blocks that lift never go DIRECT and skip the third scan)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t u2 = __shfl_up_sync(0xffffffffu, i2, d);
+            if (lane >= d) i2 += u2;
+        }
+        if (lane == 31) s_w2[warp] = i2;
+    }
+    if (lane == 31) { s_wb[warp] = ib; s_wc[warp] = ic; }
     const bool small = __syncthreads_and(len <= EMIT_LONG) != 0;
     unsigned long long wb = 0, tb = 0;
     uint32_t wc = 0, tc = 0, w2 = 0, t2 = 0;
 #pragma unroll
     for (int k = 0; k < SER_LINES / 32; k++) {
-        if (k < warp) { wb += s_wb[k]; wc += s_wc[k]; w2 += s_w2[k]; }
-        tb += s_wb[k]; tc += s_wc[k]; t2 += s_w2[k];
+        if (k < warp) { wb += s_wb[k]; wc += s_wc[k]; }
+        tb += s_wb[k]; tc += s_wc[k];
     }
     const unsigned long long rel = wb + ib - len;  // bytes of the block's lines in front of mine
-    const uint32_t rel2 = w2 + i2 - (len - dml);    // ... without the direct runs
+    uint32_t rel2 = 0;                             // ... without the direct runs
     s_rel[tid] = (uint32_t)rel;
-    if (!fast) s_rel2[tid] = rel2;
-    if (tid == 0) { s_rel[SER_LINES] = (uint32_t)tb; if (!fast) s_rel2[SER_LINES] = t2; }
+    if (tid == 0) s_rel[SER_LINES] = (uint32_t)tb;
+    if (!fast) {
+#pragma unroll
+        for (int k = 0; k < SER_LINES / 32; k++) {
+            if (k < warp) w2 += s_w2[k];
+            t2 += s_w2[k];
+        }
+        rel2 = w2 + i2 - (len - dml);
+        s_rel2[tid] = rel2;
+        if (tid == 0) s_rel2[SER_LINES] = t2;
+    }
 
     const bool want_text = e.out_text != nullptr && tb != 0;
     const bool compose_early = want_text && small;  // (block-uniform)
