@@ -260,16 +260,36 @@ void parse_line(const char* text, size_t i, size_t e, ParsedLine& L) {
 Paf Paf::from_text(const char* text, size_t n) {
     Paf paf;
     std::vector<std::pair<size_t, size_t>> lines;  // [begin, end) without the line terminator
-    for (size_t i = 0; i < n;) {
-        const char* nl = (const char*)memchr(text + i, '\n', n - i);
-        const size_t j = nl ? (size_t)(nl - text) : n;
-        size_t e = j;
-        if (nl && e > i && text[e - 1] == '\r') e--;
-        lines.emplace_back(i, e);
-        i = nl ? j + 1 : n;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    {   // line terminators: every thread scans one piece of the text (one memchr pass over many GB is seconds on one core)
+        const unsigned ns = n < (64u << 20) ? 1u : hw;
+        std::vector<std::vector<size_t>> nls(ns);
+        auto scan = [&](unsigned t) {
+            const size_t a = n / ns * t, b = (t + 1 == ns) ? n : n / ns * (t + 1);
+            for (size_t i = a; i < b;) {
+                const char* nl = (const char*)memchr(text + i, '\n', b - i);
+                if (!nl) break;
+                nls[t].push_back((size_t)(nl - text));
+                i = (size_t)(nl - text) + 1;
+            }
+        };
+        if (ns == 1) scan(0);
+        else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < ns; t++) pool.emplace_back(scan, t);
+            for (auto& th : pool) th.join();
+        }
+        size_t i = 0;
+        for (unsigned t = 0; t < ns; t++)
+            for (const size_t j : nls[t]) {
+                size_t e = j;
+                if (e > i && text[e - 1] == '\r') e--;
+                lines.emplace_back(i, e);
+                i = j + 1;
+            }
+        if (i < n) lines.emplace_back(i, n);  // last line without a terminator
     }
     std::vector<ParsedLine> parsed(lines.size());
-    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const unsigned nt = (unsigned)std::min<size_t>(n < (8u << 20) ? 1 : hw, std::max<size_t>(1, lines.size()));
     if (nt <= 1) {
         for (size_t k = 0; k < lines.size(); k++) parse_line(text, lines[k].first, lines[k].second, parsed[k]);

@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "rbcuda.h"
@@ -41,6 +42,19 @@ struct PageAlloc {
     template <class U> bool operator!=(const PageAlloc<U>&) const { return false; }
 };
 template <class T> using PagedVec = std::vector<T, PageAlloc<T>>;
+// the same for the one buffer of many GB (the packed CIGAR text): resize() default-initialises, i.e. leaves the bytes alone, so
+// the pages are first touched by the threads that copy the payloads in instead of being zeroed by one thread beforehand
+template <class T>
+struct PageAllocNoInit : PageAlloc<T> {
+    template <class U> struct rebind { using other = PageAllocNoInit<U>; };
+    PageAllocNoInit() = default;
+    template <class U> PageAllocNoInit(const PageAllocNoInit<U>&) {}
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U;
+        else ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+using PagedBytes = std::vector<uint8_t, PageAllocNoInit<uint8_t>>;
 
 struct Panic : std::runtime_error {  // the reference would panic (exit status 101)
     explicit Panic(const std::string& m) : std::runtime_error(m) {}
@@ -51,7 +65,7 @@ std::string read_raw(const std::string& path);  // the file's bytes as they are 
 
 // Packed records (what rb_records points into).  Name ids are shared by query and target names.
 struct Paf {
-    PagedVec<uint8_t> cigar;
+    PagedBytes cigar;
     std::vector<uint64_t> cigar_off{0};
     std::vector<uint64_t> q_len, q_st, q_en, t_len, t_st, t_en, mapq;
     std::vector<uint8_t> strand;
