@@ -4,6 +4,9 @@
 
 #include <cerrno>
 #include <unistd.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -350,6 +353,40 @@ Paf Paf::from_text(const char* text, size_t n) {
         for (auto& th : pool) th.join();
     }
     return paf;
+}
+
+// paf.rs:62-78 Paf::from_file.  An uncompressed file is mapped and parsed in place: the lines are only ever read once (the CIGAR
+// payloads are copied into the packed buffer by all threads), so a private copy of many GB — allocated, zeroed and filled by one
+// thread — would cost more than the parse itself.
+Paf Paf::from_file(const std::string& path) {
+    auto ends_with = [&](const char* suf) {
+        const size_t n = strlen(suf);
+        return path.size() >= n && path.compare(path.size() - n, n, suf) == 0;
+    };
+    if (path != "-" && !ends_with(".gz") && !ends_with(".bgz")) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) throw Panic("Error: cannot read input file " + path);
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void* p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (p != MAP_FAILED) {
+                madvise(p, (size_t)st.st_size, MADV_WILLNEED);
+                try {
+                    Paf paf = from_text(static_cast<const char*>(p), (size_t)st.st_size);
+                    munmap(p, (size_t)st.st_size);
+                    ::close(fd);
+                    return paf;
+                } catch (...) {
+                    munmap(p, (size_t)st.st_size);
+                    ::close(fd);
+                    throw;
+                }
+            }
+        }
+        ::close(fd);
+    }
+    std::string t = read_all(path);
+    return from_text(t.data(), t.size());
 }
 
 rb_records Paf::view() {

@@ -79,10 +79,7 @@ struct Paf {
     uint32_t name_id(const std::string& s);            // interns
     int64_t find_name(const std::string& s) const;     // -1 if absent
     static Paf from_text(const char* text, size_t n);  // throws Panic like PafRecord::new's asserts
-    static Paf from_file(const std::string& path) {
-        std::string t = read_all(path);
-        return from_text(t.data(), t.size());
-    }
+    static Paf from_file(const std::string& path);     // plain files are mapped, not copied; "-", .gz, .bgz go through read_all
     rb_records view();  // finalises the name table and returns the SoA view
 
    private:
