@@ -112,12 +112,16 @@ int main(int argc, char** argv) {
             fputs(rbh::stats_header(qbed).c_str(), stdout);  // printed before the input is read (main.rs:51)
             fflush(stdout);
             rbh::Paf paf = load_paf(input);
+            mark("read_parse_paf");
             if (paf.skipped) fprintf(stderr, "\nUnable to parse %zu PAF record(s). Skipped.\n", paf.skipped);
             rb_records recs = paf.view();
             rb_stats_out st{};
             rc = rb_stats(ctx, &recs, &st);
+            mark("rb_stats");
             if (rc == RB_OK) {
                 rbh::write_stats_rows(stdout, paf, st, qbed);
+                fflush(stdout);
+                mark("format_write");
                 rb_free_stats_out(ctx, &st);
             }
         } else if (brk) {

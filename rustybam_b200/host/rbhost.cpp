@@ -174,7 +174,14 @@ int64_t Paf::find_name(const std::string& s) const {
 // unparsable numeric column -> the line is skipped.  The CIGAR payload is copied verbatim.
 // first ASCII-whitespace byte in [p, e) ('\n' cannot occur inside a line): libc's vectorised memchr instead of a
 // byte loop — the cg:Z: token of a whole-genome record is hundreds of kilobytes long
-static inline const char* next_ws(const char* p, const char* e) {
+static inline const char* next_ws(const char* p0, const char* e) {
+    // short tokens (names, numbers, most tags): a byte loop beats four library calls; only what is still going after 48 bytes
+    // (the cg:Z: payload) is handed to memchr
+    const char* lim = (e - p0 > 48) ? p0 + 48 : e;
+    const char* p = p0;
+    for (; p < lim; p++)
+        if (is_ws(*p)) return p;
+    if (p == e) return e;
     const char* q = (const char*)memchr(p, '\t', (size_t)(e - p));
     if (!q) q = e;
     static const char others[3] = {' ', '\x0C', '\r'};
@@ -301,10 +308,11 @@ Paf Paf::from_text(const char* text, size_t n) {
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < nt; t++)
             pool.emplace_back([&] {
-                for (;;) {
-                    const size_t k = next.fetch_add(1);
-                    if (k >= lines.size()) break;
-                    parse_line(text, lines[k].first, lines[k].second, parsed[k]);
+                for (;;) {  // (a few hundred lines per grab: short rows would otherwise fight over the counter)
+                    const size_t k0 = next.fetch_add(256);
+                    if (k0 >= lines.size()) break;
+                    const size_t k1 = std::min(lines.size(), k0 + 256);
+                    for (size_t k = k0; k < k1; k++) parse_line(text, lines[k].first, lines[k].second, parsed[k]);
                 }
             });
         for (auto& th : pool) th.join();
@@ -321,14 +329,29 @@ Paf Paf::from_text(const char* text, size_t n) {
     std::vector<std::pair<const ParsedLine*, size_t>> copies;  // (line, destination offset) of the CIGAR payloads
     copies.reserve(n_ok);
     size_t off = 0;
+    for (std::vector<uint64_t>* v : {&paf.q_len, &paf.q_st, &paf.q_en, &paf.t_len, &paf.t_st, &paf.t_en, &paf.mapq}) v->reserve(n_ok);
+    paf.strand.reserve(n_ok); paf.q_id.reserve(n_ok); paf.t_id.reserve(n_ok);
+    // consecutive records mostly repeat their names (rows of one window run, reads of one contig): the name of the record
+    // before is compared first, the hash map only sees the changes — millions of short rows otherwise spend their time hashing
+    const char *lq = nullptr, *lt = nullptr;
+    size_t lqn = 0, ltn = 0;
+    uint32_t lq_id = 0, lt_id = 0;
     for (const ParsedLine& L : parsed) {
         if (L.state == 1) { paf.skipped++; continue; }
         paf.q_len.push_back(L.v[0]); paf.q_st.push_back(L.v[1]); paf.q_en.push_back(L.v[2]);
         paf.t_len.push_back(L.v[3]); paf.t_st.push_back(L.v[4]); paf.t_en.push_back(L.v[5]);
         paf.mapq.push_back(L.v[8]);
         paf.strand.push_back(L.strand);
-        paf.q_id.push_back(paf.name_id(std::string(L.q_name, L.q_name_n)));
-        paf.t_id.push_back(paf.name_id(std::string(L.t_name, L.t_name_n)));
+        if (!(lq && lqn == L.q_name_n && memcmp(lq, L.q_name, lqn) == 0)) {
+            lq_id = paf.name_id(std::string(L.q_name, L.q_name_n));
+            lq = L.q_name; lqn = L.q_name_n;
+        }
+        if (!(lt && ltn == L.t_name_n && memcmp(lt, L.t_name, ltn) == 0)) {
+            lt_id = paf.name_id(std::string(L.t_name, L.t_name_n));
+            lt = L.t_name; ltn = L.t_name_n;
+        }
+        paf.q_id.push_back(lq_id);
+        paf.t_id.push_back(lt_id);
         copies.emplace_back(&L, off);
         off += L.cg_n;
         paf.cigar_off.push_back(off);
@@ -340,14 +363,19 @@ Paf Paf::from_text(const char* text, size_t n) {
     if (nt <= 1 || copies.size() < 2) {
         copy_range(0, copies.size());
     } else {  // the payload copy is the other O(bytes) step: spread it over the same threads
+        std::vector<size_t> grabs(1, 0);
+        for (size_t k = 0, acc = 0; k < copies.size(); k++) {
+            acc += copies[k].first->cg_n;
+            if (acc >= (4u << 20) || k + 1 == copies.size()) { grabs.push_back(k + 1); acc = 0; }
+        }
         std::atomic<size_t> next{0};
         std::vector<std::thread> pool;
         for (unsigned t = 0; t < nt; t++)
             pool.emplace_back([&] {
-                for (;;) {
-                    const size_t k = next.fetch_add(1);
-                    if (k >= copies.size()) break;
-                    copy_range(k, k + 1);
+                for (;;) {  // (grabs of ~4 MB of payload, or one record if it is larger)
+                    const size_t k0 = next.fetch_add(1);
+                    if (k0 >= grabs.size() - 1) break;
+                    copy_range(grabs[k0], grabs[k0 + 1]);
                 }
             });
         for (auto& th : pool) th.join();
