@@ -536,6 +536,76 @@ __device__ __forceinline__ SegVal lookback_seg(uint32_t* state, ScanPayload* agg
     return acc;
 }
 
+// The same look-back with ONE trip to L2 per round and no fences (k_samples2).  A block's slot is four 16-byte vectors, each
+// three counter words + a tag (0 = nothing yet, 1 = aggregate, 2 = inclusive prefix; the head flag rides in bit 30 of aux):
+// every vector is written and read with a single-copy-atomic 128-bit access (st / ld.relaxed.gpu.b128), a reader that finds four
+// equal non-zero tags holds one consistent version — the aggregate and the prefix that later replaces it carry different
+// tags, so a mix of the two is seen as such and read again.  The slots are zeroed before every launch.
+// Compiled in with -DRB_SMP2_LB2=1 only: measured, it does not pay (rb_kernels.cuh).
+__device__ __forceinline__ void st_b128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const unsigned long long lo = ((unsigned long long)b << 32) | a, hi = ((unsigned long long)d << 32) | c;
+    asm volatile("{\n .reg .b128 r;\n mov.b128 r, {%1, %2};\n st.relaxed.gpu.global.b128 [%0], r;\n}" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ uint4 ld_b128(const void* p) {
+    unsigned long long lo, hi;
+    asm volatile("{\n .reg .b128 r;\n ld.relaxed.gpu.global.b128 r, [%2];\n mov.b128 {%0, %1}, r;\n}" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+__device__ __forceinline__ void slot_store(ScanPayload* slot, const SegVal& v, uint32_t tag) {
+    const uint32_t* in = reinterpret_cast<const uint32_t*>(&v);  // 12 counter words (aux last), then the flag
+    const uint32_t aux = (in[11] & ~SUB_ABS) | (v.flag ? SUB_ABS : 0u);
+    uint4* o = reinterpret_cast<uint4*>(slot);
+    st_b128(o + 0, in[0], in[1], in[2], tag);
+    st_b128(o + 1, in[3], in[4], in[5], tag);
+    st_b128(o + 2, in[6], in[7], in[8], tag);
+    st_b128(o + 3, in[9], in[10], aux, tag);
+}
+__device__ __forceinline__ uint32_t slot_load(const ScanPayload* slot, SegVal& v) {  // the tag, 0 = not there yet (or torn: read again)
+    const uint4* p = reinterpret_cast<const uint4*>(slot);
+    const uint4 a = ld_b128(p + 0), b = ld_b128(p + 1), c = ld_b128(p + 2), d = ld_b128(p + 3);
+    if (a.w != b.w || b.w != c.w || c.w != d.w) return 0u;
+    uint32_t* out = reinterpret_cast<uint32_t*>(&v);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = b.x; out[4] = b.y; out[5] = b.z;
+    out[6] = c.x; out[7] = c.y; out[8] = c.z; out[9] = d.x; out[10] = d.y;
+    out[11] = d.z & ~SUB_ABS;
+    v.flag = (d.z & SUB_ABS) ? 1u : 0u;
+    return a.w;
+}
+__device__ __forceinline__ SegVal lookback_seg2(ScanPayload* slots, uint64_t b, const SegVal& mine) {
+    const int lane = threadIdx.x & 31;
+    SegVal acc = seg_identity();
+    if (b == 0) {
+        if (lane == 0) slot_store(&slots[0], mine, 2u);
+        return acc;
+    }
+    if (lane == 0) slot_store(&slots[b], mine, 1u);
+    long long look = (long long)b - 1;
+    for (;;) {
+        const long long idx = look - lane;
+        uint32_t st = 2u;
+        SegVal x = seg_identity();
+        if (idx >= 0) {
+            do { st = slot_load(&slots[idx], x); } while (st == 0u);
+        }
+        // the chain stops at the nearest predecessor that already has its prefix, or whose span holds a head
+        const unsigned stopm = __ballot_sync(0xffffffffu, st == 2u || x.flag);
+        const int stop = stopm ? (__ffs(stopm) - 1) : 31;
+        if (lane > stop) x = seg_identity();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {  // ordered reduction: lane l absorbs the EARLIER span held by lane l + d
+            const SegVal y = seg_shfl(x, (lane + d) & 31);
+            if (lane + d < 32) x = seg_combine(y, x);
+        }
+        const SegVal tot = seg_shfl(x, 0);
+        acc = seg_combine(tot, acc);
+        if (stopm) break;
+        look -= 32;
+        if (look < 0) break;
+    }
+    if (lane == 0) slot_store(&slots[b], seg_combine(acc, mine), 2u);
+    return acc;
+}
+
 // Windows of one record staged in shared memory as relative boundary positions (stream_core.cuh)
 struct WinStaged {
     const uint32_t* s_ps;  // ps(j) for j in [js0, ..)
@@ -799,11 +869,17 @@ k_scan_lift(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops
 #ifndef RB_SMP2_MINB
 #define RB_SMP2_MINB 4
 #endif
-template <bool LOCAL>
-__global__ void __launch_bounds__(SMP_THREADS, RB_SMP2_MINB)
+#ifndef RB_SMP2_MINB_NOSUBS
+#define RB_SMP2_MINB_NOSUBS 5
+#endif
+// NOSUBS (wide windows): absolute samples only.  Its own instantiation: without the sub-sample flushes the walk needs fewer
+// registers, and a fifth resident block per SM hides more of the two barriers the profile shows (after the walk, behind the look-back)
+template <bool LOCAL, bool NOSUBS = false>
+__global__ void __launch_bounds__(SMP_THREADS, NOSUBS ? RB_SMP2_MINB_NOSUBS : RB_SMP2_MINB)
 k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_dev, const uint32_t* __restrict__ heads,
            Ctr* __restrict__ samples, uint32_t* blk_state, ScanPayload* blk_agg, ScanPayload* blk_pre, unsigned int* ticket,
-           uint32_t no_subs /* != 0: absolute samples only, marked SUB_ABS (lift_core.cuh: OpsView::no_subs) */) {
+           uint32_t no_subs_arg /* != 0: absolute samples only, marked SUB_ABS (lift_core.cuh: OpsView::no_subs) */) {
+    const bool no_subs = NOSUBS || no_subs_arg != 0u;
     static_assert(SAMPLE == 32u, "k_samples2 walks 32-op chunks");
     extern __shared__ __align__(16) uint32_t s_dyn2[];
     uint4* s_ops4 = reinterpret_cast<uint4*>(s_dyn2);             // SMP_THREADS rows of 8 units
@@ -957,7 +1033,11 @@ k_samples2(const uint32_t* __restrict__ ops, const uint64_t* __restrict__ n_ops_
     if (warp == 0) {
 #pragma unroll
         for (int k = 0; k < SMP_THREADS / 32; k++) btot = seg_combine(btot, s_warp[k]);
+#if RB_SMP2_LB2
+        const SegVal ex = lookback_seg2(blk_agg, b, btot);
+#else
         const SegVal ex = lookback_seg(blk_state, blk_agg, blk_pre, b, btot);
+#endif
         if (lane == 0) s_blk = ex;
     } else {
         for (int k = 0; k < warp; k++) wpre = seg_combine(wpre, s_warp[k]);
@@ -2991,6 +3071,7 @@ int init_kernel_attrs() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_scan_lift<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_lift_smem(false));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_samples2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)samples2_smem());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_serialise, cudaFuncAttributeMaxDynamicSharedMemorySize, SER_CAP);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EMIT_DYN_BYTES);
@@ -3041,10 +3122,17 @@ void launch_scan_lift(bool lift, const uint32_t* ops, const uint64_t* n_ops_dev,
     else if (getenv("RB_OLD_SAMPLES"))
         k_scan_lift<false><<<(unsigned)blocks, SMP_THREADS, scan_lift_smem(false), s>>>(ops, n_ops_dev, heads, samples, blk_state,
                                                                                         blk_agg, blk_pre, ticket, la);
-    else if (!getenv("RB_SAMPLES_LOCAL"))
-        k_samples2<false><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket,
-                                                                                 no_subs ? 1u : 0u);
-    else {  // (measured, not faster: 0.24 + 0.06 + 0.07 ms against 0.31 ms at C4) block-local samples + aggregates, a one-block
+    else if (!getenv("RB_SAMPLES_LOCAL")) {
+#if RB_SMP2_LB2
+        cudaMemsetAsync(blk_agg, 0, blocks * sizeof(ScanPayload), s);  // the look-back slots of k_samples2 (tags 0 = nothing yet)
+#endif
+        if (no_subs)
+            k_samples2<false, true><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre,
+                                                                                           ticket, 1u);
+        else
+            k_samples2<false><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket,
+                                                                                     0u);
+    } else {  // (measured, not faster: 0.24 + 0.06 + 0.07 ms against 0.31 ms at C4) block-local samples + aggregates, a one-block
             // scan of the aggregates, the prefixes added to the incomplete samples
         k_samples2<true><<<(unsigned)blocks, SMP_THREADS, samples2_smem(), s>>>(ops, n_ops_dev, heads, samples, blk_state, blk_agg, blk_pre, ticket, 0u);
         k_blk_scan<<<1, 1024, 0, s>>>(n_ops_dev, blk_agg, blk_pre);

@@ -39,6 +39,11 @@ constexpr int SL_WCAP = 2048;                // window boundaries of one block s
 #ifndef RB_LIFT_CHAIN
 #define RB_LIFT_CHAIN 1  // 1: on tiling windows a pair's start boundary is derived from its left neighbour's end boundary
 #endif
+#ifndef RB_SMP2_LB2
+#define RB_SMP2_LB2 0  // k_samples2: 1 = look-back over self-validating 128-bit slots, one L2 trip per round and no fences, instead of
+                       // flag -> fence -> payload.  Parity-clean, measured: 0.309 against 0.319 ms at C4, 1.97 against 1.86 ms at
+                       // 8 haplotypes x 10 kb — the round is dominated by the 13-word ordered reduction, not by the two trips
+#endif
 #ifndef RB_SMP_MINB
 #define RB_SMP_MINB 3
 #endif
