@@ -10,6 +10,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <charconv>
 #include <cmath>
 #include <cstdio>
@@ -221,15 +222,19 @@ bool cigar_syntax_ok(const char* s, size_t n) {
     return true;
 }
 
-struct ParsedLine {     // what PafRecord::new extracts from one line (paf.rs:379-430), before name interning
-    const char *q_name = nullptr, *t_name = nullptr, *cg = nullptr;
-    size_t q_name_n = 0, t_name_n = 0, cg_n = 0;
-    uint64_t v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    uint8_t strand = '+';
-    uint8_t state = 0;  // 0 ok, 1 skipped (unparsable numeric column), 2 panic: < 12 columns, 3 panic: bad tag, 4 panic: bad cg on a skipped line
+struct ParsedLine {     // what PafRecord::new extracts from one line (paf.rs:379-430), before name interning (no initialisers: see from_text)
+    const char *q_name, *t_name, *cg;
+    size_t q_name_n, t_name_n, cg_n;
+    uint64_t v[9];
+    uint8_t strand;
+    uint8_t state;  // 0 ok, 1 skipped (unparsable numeric column), 2 panic: < 12 columns, 3 panic: bad tag, 4 panic: bad cg on a skipped line
 };
 
 void parse_line(const char* text, size_t i, size_t e, ParsedLine& L) {
+    L.q_name = L.t_name = L.cg = nullptr;
+    L.q_name_n = L.t_name_n = L.cg_n = 0;
+    L.strand = '+';
+    L.state = 0;
     std::pair<const char*, size_t> t[12];
     size_t nt = 0, p = i;
     const char* end = text + e;
@@ -299,7 +304,10 @@ Paf Paf::from_text(const char* text, size_t n) {
             }
         if (i < n) lines.emplace_back(i, n);  // last line without a terminator
     }
-    std::vector<ParsedLine> parsed(lines.size());
+    // (one ParsedLine per line, 136 bytes: left uninitialised — parse_line sets every field — so that millions of short rows do
+    // not start with one thread zeroing hundreds of MB)
+    std::unique_ptr<ParsedLine[]> parsed_store(new ParsedLine[lines.size()]);
+    ParsedLine* parsed = parsed_store.get();
     const unsigned nt = (unsigned)std::min<size_t>(n < (8u << 20) ? 1 : hw, std::max<size_t>(1, lines.size()));
     if (nt <= 1) {
         for (size_t k = 0; k < lines.size(); k++) parse_line(text, lines[k].first, lines[k].second, parsed[k]);
@@ -317,69 +325,85 @@ Paf Paf::from_text(const char* text, size_t n) {
             });
         for (auto& th : pool) th.join();
     }
-    size_t total_cg = 0, n_ok = 0;
-    for (const ParsedLine& L : parsed) {
+    // kept records: their index and the place of their CIGAR payload (one serial pass of additions; the first panic in file
+    // order is the one reported, like the serial loop of the reference)
+    const size_t n_lines = lines.size();
+    std::vector<uint32_t> kept;  // line index of record r
+    kept.reserve(n_lines);
+    size_t total_cg = 0;
+    for (size_t k = 0; k < n_lines; k++) {
+        const ParsedLine& L = parsed[k];
         if (L.state == 2) throw Panic("assertion failed: t.len() >= 12");
         if (L.state == 3) throw Panic("assertion failed: PAF_TAG.is_match(token)");
         if (L.state == 4) throw Panic("Unable to parse cigar string.");
-        if (L.state == 0) { total_cg += L.cg_n; n_ok++; }
-    }
-    paf.cigar.resize(total_cg);
-    paf.cigar_off.reserve(n_ok + 1);
-    std::vector<std::pair<const ParsedLine*, size_t>> copies;  // (line, destination offset) of the CIGAR payloads
-    copies.reserve(n_ok);
-    size_t off = 0;
-    for (std::vector<uint64_t>* v : {&paf.q_len, &paf.q_st, &paf.q_en, &paf.t_len, &paf.t_st, &paf.t_en, &paf.mapq}) v->reserve(n_ok);
-    paf.strand.reserve(n_ok); paf.q_id.reserve(n_ok); paf.t_id.reserve(n_ok);
-    // consecutive records mostly repeat their names (rows of one window run, reads of one contig): the name of the record
-    // before is compared first, the hash map only sees the changes — millions of short rows otherwise spend their time hashing
-    const char *lq = nullptr, *lt = nullptr;
-    size_t lqn = 0, ltn = 0;
-    uint32_t lq_id = 0, lt_id = 0;
-    for (const ParsedLine& L : parsed) {
         if (L.state == 1) { paf.skipped++; continue; }
-        paf.q_len.push_back(L.v[0]); paf.q_st.push_back(L.v[1]); paf.q_en.push_back(L.v[2]);
-        paf.t_len.push_back(L.v[3]); paf.t_st.push_back(L.v[4]); paf.t_en.push_back(L.v[5]);
-        paf.mapq.push_back(L.v[8]);
-        paf.strand.push_back(L.strand);
-        if (!(lq && lqn == L.q_name_n && memcmp(lq, L.q_name, lqn) == 0)) {
-            lq_id = paf.name_id(std::string(L.q_name, L.q_name_n));
-            lq = L.q_name; lqn = L.q_name_n;
-        }
-        if (!(lt && ltn == L.t_name_n && memcmp(lt, L.t_name, ltn) == 0)) {
-            lt_id = paf.name_id(std::string(L.t_name, L.t_name_n));
-            lt = L.t_name; ltn = L.t_name_n;
-        }
-        paf.q_id.push_back(lq_id);
-        paf.t_id.push_back(lt_id);
-        copies.emplace_back(&L, off);
-        off += L.cg_n;
-        paf.cigar_off.push_back(off);
+        kept.push_back((uint32_t)k);
+        total_cg += L.cg_n;
     }
-    auto copy_range = [&](size_t a, size_t b) {
-        for (size_t k = a; k < b; k++)
-            if (copies[k].first->cg_n) memcpy(paf.cigar.data() + copies[k].second, copies[k].first->cg, copies[k].first->cg_n);
-    };
-    if (nt <= 1 || copies.size() < 2) {
-        copy_range(0, copies.size());
-    } else {  // the payload copy is the other O(bytes) step: spread it over the same threads
-        std::vector<size_t> grabs(1, 0);
-        for (size_t k = 0, acc = 0; k < copies.size(); k++) {
-            acc += copies[k].first->cg_n;
-            if (acc >= (4u << 20) || k + 1 == copies.size()) { grabs.push_back(k + 1); acc = 0; }
+    if (n_lines > 0xFFFFFFFFull) throw Panic("more than 2^32 lines");
+    const size_t n_ok = kept.size();
+    paf.cigar.resize(total_cg);
+    paf.cigar_off.resize(n_ok + 1);
+    for (std::vector<uint64_t>* v : {&paf.q_len, &paf.q_st, &paf.q_en, &paf.t_len, &paf.t_st, &paf.t_en, &paf.mapq}) v->resize(n_ok);
+    paf.strand.resize(n_ok); paf.q_id.resize(n_ok); paf.t_id.resize(n_ok);
+    {   // payload offsets (serial additions), then ranges of ~4 MB of payload / 4 096 records for the threads
+        size_t off = 0;
+        paf.cigar_off[0] = 0;
+        for (size_t r = 0; r < n_ok; r++) { off += parsed[kept[r]].cg_n; paf.cigar_off[r + 1] = off; }
+    }
+    std::vector<size_t> grabs(1, 0);
+    for (size_t r = 0, acc = 0, cnt = 0; r < n_ok; r++) {
+        acc += parsed[kept[r]].cg_n; cnt++;
+        if (acc >= (4u << 20) || cnt >= 4096 || r + 1 == n_ok) { grabs.push_back(r + 1); acc = 0; cnt = 0; }
+    }
+    auto fill_range = [&](size_t a, size_t b) {  // numeric columns, strand and the CIGAR payload of records [a, b)
+        for (size_t r = a; r < b; r++) {
+            const ParsedLine& L = parsed[kept[r]];
+            paf.q_len[r] = L.v[0]; paf.q_st[r] = L.v[1]; paf.q_en[r] = L.v[2];
+            paf.t_len[r] = L.v[3]; paf.t_st[r] = L.v[4]; paf.t_en[r] = L.v[5];
+            paf.mapq[r] = L.v[8];
+            paf.strand[r] = L.strand;
+            if (L.cg_n) memcpy(paf.cigar.data() + paf.cigar_off[r], L.cg, L.cg_n);
         }
-        std::atomic<size_t> next{0};
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nt; t++)
+    };
+    std::vector<std::thread> pool;
+    std::atomic<size_t> next{0};
+    if (nt > 1 && n_ok >= 2)
+        for (unsigned t = 0; t + 1 < nt; t++)
             pool.emplace_back([&] {
-                for (;;) {  // (grabs of ~4 MB of payload, or one record if it is larger)
-                    const size_t k0 = next.fetch_add(1);
-                    if (k0 >= grabs.size() - 1) break;
-                    copy_range(grabs[k0], grabs[k0 + 1]);
+                for (;;) {
+                    const size_t g = next.fetch_add(1);
+                    if (g + 1 >= grabs.size()) break;
+                    fill_range(grabs[g], grabs[g + 1]);
                 }
             });
-        for (auto& th : pool) th.join();
+    // names meanwhile, on this thread, in file order (ids are handed out by first appearance).  Consecutive records mostly repeat
+    // their names (rows of one window run, reads of one contig): the name of the record before is compared first, the hash
+    // map only sees the changes — millions of short rows otherwise spend their time hashing
+    {
+        const char *lq = nullptr, *lt = nullptr;
+        size_t lqn = 0, ltn = 0;
+        uint32_t lq_id = 0, lt_id = 0;
+        for (size_t r = 0; r < n_ok; r++) {
+            const ParsedLine& L = parsed[kept[r]];
+            if (!(lq && lqn == L.q_name_n && memcmp(lq, L.q_name, lqn) == 0)) {
+                lq_id = paf.name_id(std::string(L.q_name, L.q_name_n));
+                lq = L.q_name; lqn = L.q_name_n;
+            }
+            if (!(lt && ltn == L.t_name_n && memcmp(lt, L.t_name, ltn) == 0)) {
+                lt_id = paf.name_id(std::string(L.t_name, L.t_name_n));
+                lt = L.t_name; ltn = L.t_name_n;
+            }
+            paf.q_id[r] = lq_id;
+            paf.t_id[r] = lt_id;
+        }
     }
+    for (;;) {  // ... then it helps with what is left
+        const size_t g = next.fetch_add(1);
+        if (g + 1 >= grabs.size()) break;
+        fill_range(grabs[g], grabs[g + 1]);
+    }
+    for (auto& th : pool) th.join();
     return paf;
 }
 
