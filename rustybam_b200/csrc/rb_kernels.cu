@@ -2511,6 +2511,28 @@ __device__ __forceinline__ uint32_t lift_pair_fast(const OpsView& v, const RecIn
     return status;
 }
 
+// n bytes of staged input text (shared memory, any alignment) -> the line buffer (shared memory, any alignment): word stores
+// once the destination is aligned, the source words re-aligned with funnel shifts (reads < 4 bytes past the run: staged slack)
+__device__ __forceinline__ uint8_t* put_text_smem(uint8_t* q, const uint8_t* src, uint32_t n) {
+    uint32_t h = (4u - (smem_u32(q) & 3u)) & 3u;
+    h = h < n ? h : n;
+    for (uint32_t i = 0; i < h; i++) q[i] = src[i];
+    q += h; src += h; n -= h;
+    const uint32_t sa = smem_u32(src);
+    const uint32_t sh = (sa & 3u) * 8u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(src - (sa & 3u));
+    uint32_t* d = reinterpret_cast<uint32_t*>(q);
+    const uint32_t nw = n >> 2;
+    uint32_t lo = w[0];
+    for (uint32_t i = 0; i < nw; i++) {
+        const uint32_t hi = w[i + 1];
+        d[i] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+    }
+    for (uint32_t i = nw << 2; i < n; i++) q[i] = src[i];
+    return q + n;
+}
+
 template <bool STATS_TEXT>  // (a template: the f32 digit generation of the stats rows stays out of the PAF instantiation's registers)
 __global__ void __launch_bounds__(SER_LINES, RB_EMIT_MINB)
 k_emit(const __grid_constant__ EmitArgs e) {
@@ -2518,6 +2540,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
     __shared__ uint32_t s_rel[SER_LINES + 1];
     __shared__ unsigned long long s_wb[SER_LINES / 32];
     __shared__ uint32_t s_wc[SER_LINES / 32], s_w2[SER_LINES / 32];
+    __shared__ unsigned long long s_tlo[SER_LINES / 32], s_thi[SER_LINES / 32];
     __shared__ unsigned long long s_base[2];
     __shared__ unsigned int s_blk;
     __shared__ __align__(16) RecInfo s_rec;
@@ -2588,6 +2611,9 @@ k_emit(const __grid_constant__ EmitArgs e) {
         }
     }
     }
+    bool txt_mode = false;          // FAST block composing from staged input text (block-uniform)
+    unsigned long long txt_lo = 0;  // text offset of the first staged byte
+    uint32_t code_s = 0, code_e = 0;
     if (fast) {
         // ---- stage the block's op run + samples (bulk-copy engine); lift ----
         uint32_t* s_ops = reinterpret_cast<uint32_t*>(s_emit);
@@ -2635,6 +2661,38 @@ k_emit(const __grid_constant__ EmitArgs e) {
         v.s_smp = nullptr; v.sc_lo = v.sc_hi = 0;
         s_buf = s_emit + EMIT_OPS_BYTES;
         buf_cap = (uint32_t)EMIT_UNI_BYTES;
+#if RB_EMIT_STAGE_TEXT
+        // ... unless the record spells its CIGAR canonically: then the rows' untouched ops ARE bytes of the input text, and the
+        // span of it this block's rows cover (~6 KB at 1 kb windows) takes the place of the op words — a row copies ~45 bytes
+        // shared -> shared instead of formatting ~15 ops (a quarter of this kernel's instructions at C4)
+        if (!STATS_TEXT && (ri.flags & RF_CANON)) {
+            const bool has_mid = pr.kind == PK_TRIM && pr.ei > pr.si && pr.mid_len > 0u;
+            if (pr.kind == PK_TRIM) { code_s = op_code(v.op(pr.si)); code_e = op_code(v.op(pr.ei)); }
+            unsigned long long lo = has_mid ? pr.mid_off : ~0ull, hi = has_mid ? pr.mid_off + pr.mid_len : 0ull;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const unsigned long long ol = __shfl_xor_sync(0xffffffffu, lo, d), oh = __shfl_xor_sync(0xffffffffu, hi, d);
+                lo = ol < lo ? ol : lo; hi = oh > hi ? oh : hi;
+            }
+            if (lane == 0) { s_tlo[warp] = lo; s_thi[warp] = hi; }
+            __syncthreads();  // every thread has read what it needs of the op words
+            lo = s_tlo[0]; hi = s_thi[0];
+#pragma unroll
+            for (int k = 1; k < SER_LINES / 32; k++) { lo = s_tlo[k] < lo ? s_tlo[k] : lo; hi = s_thi[k] > hi ? s_thi[k] : hi; }
+            if (hi > lo) {
+                txt_lo = lo & ~15ull;
+                const unsigned long long bytes = ((hi + 15ull) & ~15ull) - txt_lo;
+                if (bytes + 16u <= (unsigned long long)EMIT_OPS_BYTES) {  // (block-uniform)
+                    txt_mode = true;
+                    v.s_ops = nullptr; v.so_lo = v.so_hi = 0;  // the op words are gone: early rows / strip ids read HBM
+                    if (tid == 0) {
+                        mbar_expect_tx(&s_bar, (uint32_t)bytes);
+                        bulk_g2s(s_emit, e.a.text + txt_lo, (uint32_t)bytes, &s_bar);  // (the text buffer is padded on both sides)
+                    }
+                }
+            }
+        }
+#endif
         __syncthreads();
     } else {
         if (in_range) {
@@ -2779,7 +2837,13 @@ k_emit(const __grid_constant__ EmitArgs e) {
             q = put_header(q, e.a, ri, pr, w);
         }
         const uint32_t* run = (fast && pr.kind == PK_TRIM) ? v.op_run(pr.si, (uint32_t)(pr.ei - pr.si + 1)) : nullptr;
-        if (run) {  // the trimmed op range is staged (no RF_SLOW here)
+        if (txt_mode && pr.kind == PK_TRIM) {  // first op, the untouched ops as the staged input text spells them, last op
+            q = put_op(q, pr.s_len, code_s);
+            if (pr.ei > pr.si) {
+                if (pr.mid_len) q = put_text_smem(q, s_emit + (uint32_t)(pr.mid_off - txt_lo), pr.mid_len);
+                q = put_op(q, pr.e_len, code_e);
+            }
+        } else if (run) {  // the trimmed op range is staged (no RF_SLOW here)
             const uint32_t n_mid = (uint32_t)(pr.ei - pr.si);
             q = put_op(q, pr.s_len, op_code(run[0]));
             if (n_mid) {
@@ -2859,6 +2923,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
         return lo;  // (s_rel[nlines] is the block's total: threads past the end hold empty lines)
     };
     __syncthreads();  // s_rel
+    if (txt_mode) mbar_wait(&s_bar, 1u);  // the staged text span has landed (every path below may read it, none may leave before)
     uint32_t cur_line = 0, end_line = 0;
     // the block's aggregates are published right away; its first round of lines is composed BEFORE it asks where they go,
     // so the blocks in front have that long to publish theirs (a block cannot leave before every block in front of it has
