@@ -96,6 +96,28 @@ def test_corrupt_input_is_refused(ctx):
     assert ctx.inflate_bgzf(bytes(z)) == text      # the context still works
 
 
+def test_random_corruptions_never_pass_silently(ctx):
+    """A flipped byte anywhere in the file either does not matter (gzip header fields nobody reads) or is refused: structure
+    checks while decoding, then ISIZE and CRC-32 of the block.  (tools/sanitize.sh runs this file under memcheck: a corrupt stream
+    must not write or read out of bounds either.)"""
+    text = orc.golden_paf()[:300000]
+    z = bgzf(text, 20000, 6)
+    rng = random.Random(11)
+    refused = same = 0
+    for _ in range(150):
+        bad = bytearray(z)
+        k = rng.randrange(len(bad))
+        bad[k] ^= 1 << rng.randrange(8)
+        try:
+            got = ctx.inflate_bgzf(bytes(bad))
+        except RbError:
+            refused += 1
+            continue
+        assert got == text, "corruption at byte %d went through" % k
+        same += 1
+    assert refused > 100 and ctx.inflate_bgzf(z) == text
+
+
 def test_cli_reads_bgz_through_the_device(tmp_path):
     rb = os.path.join(ROOT, "rustybam_b200", "rb")
     paf = orc.golden_paf()
