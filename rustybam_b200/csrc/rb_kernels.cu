@@ -1757,15 +1757,22 @@ __device__ __forceinline__ uint32_t lift_pair_chain(const OpsView& v, const RecI
 // its samples are staged in shared memory once (coalesced), so the per-pair searches and <=7-op walks of
 // lift_pair never leave the SM.  Blocks that straddle records, explicit pair lists (general path) and runs that
 // do not fit fall back to global memory through the same OpsView accessor.
-__global__ void __launch_bounds__(LIFT_THREADS, RB_LIFT_MINB)
+#ifndef RB_LIFT_MINB_WIDE
+#define RB_LIFT_MINB_WIDE 8
+#endif
+// STAGE == false: the wide-window form.  No block of such a call fits the staging area (a block's pairs span tens of thousands of
+// ops), so the 31 KB of staging arrays are left out and the register cap lowered: eight resident blocks instead of six for a
+// kernel whose pairs each wait on a chain of dependent trips to L2 / HBM.
+template <bool STAGE>
+__global__ void __launch_bounds__(LIFT_THREADS, STAGE ? RB_LIFT_MINB : RB_LIFT_MINB_WIDE)
 k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* __restrict__ rec_order, uint32_t n_rec,
        const RecInfo* __restrict__ recs, const uint32_t* __restrict__ ops, const Ctr* __restrict__ samples, WinView win,
        const uint64_t* __restrict__ names_off, int policy, const LiftPlan* __restrict__ plans, PairRes* __restrict__ res,
        uint32_t* __restrict__ line_len, ErrSlots err, uint32_t skip_fast) {
     __shared__ uint32_t s_acc[9 * LIFT_THREADS];
-    __shared__ __align__(16) uint32_t s_ops[(LIFT_CCAP + 1) * SAMPLE];
+    __shared__ __align__(16) uint32_t s_ops[STAGE ? (LIFT_CCAP + 1) * SAMPLE : 4];
 #if RB_LIFT_STAGE_SMP
-    __shared__ __align__(16) Ctr s_smp[(LIFT_CCAP + 2) * SUBS];
+    __shared__ __align__(16) Ctr s_smp[STAGE ? (LIFT_CCAP + 2) * SUBS : 1];
 #endif
     __shared__ __align__(16) RecInfo s_rec;
 #if RB_LIFT_CHAIN
@@ -1787,7 +1794,7 @@ k_lift(uint64_t n_pairs, const uint64_t* __restrict__ pair_off, const uint32_t* 
         static_assert(sizeof(RecInfo) % 16 == 0, "RecInfo is copied in 16-byte vectors");
         if (tid < (int)(sizeof(RecInfo) / 16)) reinterpret_cast<uint4*>(&s_rec)[tid] = reinterpret_cast<const uint4*>(&recs[r_blk])[tid];
         const uint64_t c_lo = pl.c_lo, c_hi = pl.c_hi;
-        if (c_lo != ~0ull && c_hi != ~0ull && c_hi >= c_lo && c_hi - c_lo < (uint64_t)LIFT_CCAP) {
+        if (STAGE && c_lo != ~0ull && c_hi != ~0ull && c_hi >= c_lo && c_hi - c_lo < (uint64_t)LIFT_CCAP) {
             const uint64_t op_end = recs[r_blk].op_end;
             const uint64_t o_lo = c_lo << SAMPLE_LOG2;
             uint64_t o_hi = (c_hi + 2) << SAMPLE_LOG2;  // one extra chunk for the look-ahead of the slide rules
@@ -3236,10 +3243,15 @@ void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
 }
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                  const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
-                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast) {
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast, bool wide) {
     if (n_pairs == 0) return;
-    k_lift<<<(unsigned)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS), LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off,
-                                                             policy, plans, res, line_len, err, skip_fast ? 1u : 0u);
+    const unsigned grid = (unsigned)((n_pairs + LIFT_THREADS - 1) / LIFT_THREADS);
+    if (wide)
+        k_lift<false><<<grid, LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off, policy, plans, res,
+                                                    line_len, err, skip_fast ? 1u : 0u);
+    else
+        k_lift<true><<<grid, LIFT_THREADS, 0, s>>>(n_pairs, pair_off, rec_order, n_rec, recs, ops, samples, win, names_off, policy, plans, res,
+                                                   line_len, err, skip_fast ? 1u : 0u);
 }
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s) {

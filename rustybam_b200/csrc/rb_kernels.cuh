@@ -175,7 +175,8 @@ void launch_lift_plan(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t
                       const Ctr* samples, WinView win, LiftPlan* plans, cudaStream_t s, bool mark_fast = false);
 void launch_lift(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                  const uint32_t* ops, const Ctr* samples, WinView win, const uint64_t* names_off, int policy, const LiftPlan* plans,
-                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast = false);
+                 PairRes* res, uint32_t* line_len, ErrSlots err, cudaStream_t s, bool skip_fast = false, bool wide = false);
+                 // wide: the call's windows are wide (no block fits the staging area): the variant without staging arrays, 8 blocks / SM
 void launch_scan_lines(const uint32_t* line_len, uint64_t n, uint64_t* line_off, uint64_t* out_idx, uint32_t* blk_state,
                        ulonglong2* blk_agg, ulonglong2* blk_pre, unsigned int* ticket, cudaStream_t s);
 void launch_serialise(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,

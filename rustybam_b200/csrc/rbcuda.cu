@@ -1054,7 +1054,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         KScope k(ctx, "k_lift");
         launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
                     b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
-                    b->line_len.as<uint32_t>(), err, s, fast_lift);
+                    b->line_len.as<uint32_t>(), err, s, fast_lift, P > 0 && n_ops > 64ull * P);
     }
     // Short rows (the usual tiling-window call): line scan + serialiser in ONE kernel, k_emit — no per-pair offsets in HBM, no
     // second pass over the results.  The sizes are known only afterwards, so the text buffer is sized from an estimate (or
