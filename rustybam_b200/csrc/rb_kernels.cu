@@ -2373,6 +2373,10 @@ constexpr int EMIT_UNI_BYTES = EMIT_SMP_BYTES + EMIT_ACC_BYTES;                 
 constexpr int EMIT_DYN_BYTES = EMIT_OPS_BYTES + EMIT_UNI_BYTES;                   // (other blocks compose in all of it)
 constexpr uint32_t FRAG_CAP = 96, FRAG_NAME_MAX = 64;
 constexpr int EMIT_MID_BYTES = SER_LINES * 16;  // the descriptors of copy_mids (blocks that do not lift)
+// Wide-window calls (no block lifts here: launch_lift_plan was told not to mark any) take less shared memory per block, which the
+// SM hands to L1: their loads are per-thread reads of results, record fields and names plus the streaming text copies, and the
+// full 35 KB x 6 blocks left L1 under 30 KB.  Room for the 128 lines of a DIRECT block (~150 B each without their runs).
+constexpr int EMIT_DYN_WIDE = 22 * 1024 + SER_LINES * 16 + (SER_LINES + 4) * 4;
 constexpr int EMIT_REL2_BYTES = (SER_LINES + 4) * 4;  // ... and, in front of them, the prefix of their line sizes without the direct runs
 constexpr uint32_t MID_COOP = 96;  // runs of untouched ops at least this long are copied by a warp instead of their line's thread
 static_assert(EMIT_OPS_BYTES % 16 == 0 && EMIT_SMP_BYTES % 16 == 0, "staging areas are 16-byte aligned");
@@ -2404,6 +2408,7 @@ struct EmitArgs {
     unsigned long long* totals;  // [0] bytes of text, [1] rows, [2] != 0: the text did not fit, [3] deferred blocks
     ErrSlots err;
     uint32_t stats_text;         // RB_WANT_STATS_TEXT: the rows `rb stats --paf` prints for the lifted rows instead of the PAF rows
+    uint32_t dyn_bytes;          // dynamic shared memory of this launch: EMIT_DYN_BYTES, or EMIT_DYN_WIDE when no block lifts (wide windows)
 };
 
 // bamstats.rs:138-142 — the three f32 identities of a row (IEEE mul + div, no contraction), as bit patterns
@@ -2707,12 +2712,12 @@ k_emit(const __grid_constant__ EmitArgs e) {
             if (len) pr = e.res[p];
         }
         s_buf = s_emit;
-        buf_cap = (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);
+        buf_cap = e.dyn_bytes - (uint32_t)(EMIT_MID_BYTES + EMIT_REL2_BYTES);
     }
     // blocks that do not lift keep, behind their line buffer, one descriptor per line: a run of input text its owner left to the
     // warps (src lo, src hi, dst offset, bytes)
-    uint4* s_mid = reinterpret_cast<uint4*>(s_emit + EMIT_DYN_BYTES - EMIT_MID_BYTES);
-    uint32_t* s_rel2 = reinterpret_cast<uint32_t*>(s_emit + EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);  // (blocks that do not lift only)
+    uint4* s_mid = reinterpret_cast<uint4*>(s_emit + e.dyn_bytes - EMIT_MID_BYTES);
+    uint32_t* s_rel2 = reinterpret_cast<uint32_t*>(s_emit + e.dyn_bytes - EMIT_MID_BYTES - EMIT_REL2_BYTES);  // (blocks that do not lift only)
     bool live = len != 0u;
     if (!live) { r = 0; w = 0; }
     else if (!fast) {
@@ -2797,7 +2802,7 @@ k_emit(const __grid_constant__ EmitArgs e) {
     // 10 kb windows), each line's two pieces go out separately, and the runs are copied text -> output by a warp each —
     // they used to go text -> shared memory -> output, a round of the block's barriers per 26 KB
     const bool direct = RB_EMIT_DIRECT && !STATS_TEXT && !fast && compose_early && 2ull * (tb - t2) >= tb &&
-                        t2 + 32u <= (uint32_t)(EMIT_DYN_BYTES - EMIT_MID_BYTES - EMIT_REL2_BYTES);
+                        t2 + 32u <= e.dyn_bytes - (uint32_t)(EMIT_MID_BYTES + EMIT_REL2_BYTES);
 
     // one line into the staging buffer at `q` — FAST blocks: fragments + staged ops, no global loads
     auto compose = [&](uint8_t* q) {
@@ -3281,7 +3286,7 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
                  uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
                  uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
                  unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s,
-                 bool stats_text) {
+                 bool stats_text, bool wide) {
     if (n_pairs == 0) return;
     OpsView view;
     view.ops = ops; view.samples = samples;
@@ -3293,8 +3298,9 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
     e.byte_base = byte_base; e.rec_base = rec_base; e.orig_idx = orig_idx;
     e.lb_bytes = lb_bytes; e.lb_rows = lb_rows; e.ticket = ticket; e.totals = totals; e.err = err;
     e.stats_text = stats_text ? 1u : 0u;
-    if (stats_text) k_emit<true><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
-    else k_emit<false><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, EMIT_DYN_BYTES, s>>>(e);
+    e.dyn_bytes = (uint32_t)(wide ? EMIT_DYN_WIDE : EMIT_DYN_BYTES);  // wide: the caller's plan marked no block PLAN_FAST
+    if (stats_text) k_emit<true><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, e.dyn_bytes, s>>>(e);
+    else k_emit<false><<<(unsigned)((n_pairs + SER_LINES - 1) / SER_LINES), SER_LINES, e.dyn_bytes, s>>>(e);
 }
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s) {

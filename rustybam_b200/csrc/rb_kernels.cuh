@@ -192,7 +192,7 @@ void launch_emit(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec
                  uint32_t* blk_flags, uint8_t* out_text, uint64_t cap_text, uint64_t* out_line_off, NumDev num, StatsDev st,
                  uint64_t byte_base, uint32_t rec_base, const uint32_t* orig_idx, unsigned long long* lb_bytes,
                  unsigned long long* lb_rows, unsigned int* ticket, unsigned long long* totals, ErrSlots err, cudaStream_t s,
-                 bool stats_text = false);
+                 bool stats_text = false, bool wide = false);  // wide: no block is PLAN_FAST (the plan was made without mark_fast): less smem, more L1
 // few, long rows: the long verbatim runs of input text that k_serialise (defer_big = 1) left out, spread over the grid
 void launch_copy_mid(uint64_t n_pairs, const uint64_t* pair_off, const uint32_t* rec_order, uint32_t n_rec, const RecInfo* recs,
                      const PairRes* res, const uint64_t* line_off, const uint8_t* text, uint8_t* out_text, uint32_t seg_y, cudaStream_t s);

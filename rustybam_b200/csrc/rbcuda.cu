@@ -1030,7 +1030,10 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
     const bool stats_text = b->stats_text && (tail == TAIL_SEARCH || tail == TAIL_COMBINE);  // (rows of ~130 bytes whatever the CIGARs are)
     const bool fused = ctx->fused_emit && (tail == TAIL_SEARCH || tail == TAIL_COMBINE) && P > 0 && (stats_text || b->n_bytes / P <= 1024);
     if (b->stats_text && !fused && P > 0) return fail(ctx, RB_ERR_UNSUPPORTED, "RB_WANT_STATS_TEXT needs the fused emit kernel (rb_liftover / rb_batch_liftover)");
-    const bool fast_lift = fused && tail == TAIL_SEARCH && policy == RB_POLICY_RIGHTMOST && !getenv("RB_NO_FAST_LIFT");
+    // wide windows (the rule k_samples uses for its sub-samples): no block of the call fits k_emit's staging area bar the odd short
+    // record, so none is marked — k_lift<false> lifts everything and k_emit runs with the smaller shared-memory footprint
+    const bool wide = P > 0 && n_ops > 64ull * P && !getenv("RB_NO_WIDE");
+    const bool fast_lift = fused && tail == TAIL_SEARCH && policy == RB_POLICY_RIGHTMOST && !wide && !getenv("RB_NO_FAST_LIFT");
     if (tail == TAIL_SEARCH || tail == TAIL_COMBINE) {
         KScope k(ctx, "k_lift_plan");
         launch_lift_plan(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->samples.as<Ctr>(), win,
@@ -1054,7 +1057,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
         KScope k(ctx, "k_lift");
         launch_lift(P, b->pair_off.as<uint64_t>(), b->rec_order.as<uint32_t>(), n, b->recs.as<RecInfo>(), b->ops.as<uint32_t>(),
                     b->samples.as<Ctr>(), win, b->names_off.as<uint64_t>(), policy, b->plans.as<LiftPlan>(), b->pair_res.as<PairRes>(),
-                    b->line_len.as<uint32_t>(), err, s, fast_lift, P > 0 && n_ops > 64ull * P);
+                    b->line_len.as<uint32_t>(), err, s, fast_lift, wide);
     }
     // Short rows (the usual tiling-window call): line scan + serialiser in ONE kernel, k_emit — no per-pair offsets in HBM, no
     // second pass over the results.  The sizes are known only afterwards, so the text buffer is sized from an estimate (or
@@ -1093,7 +1096,7 @@ static int lift_tail(rb_ctx* ctx, rb_batch* b, WinView win, int policy, int tail
                             (want & RB_WANT_TEXT) ? b->out_line_off.as<uint64_t>() : nullptr,
                             (want & RB_WANT_NUMERIC) ? num_view(b, P) : NumDev{}, with_stats ? stats_view(b, P) : StatsDev{}, b->byte_base,
                             b->rec_base, b->h_orig.empty() ? nullptr : b->orig_idx.as<uint32_t>(), lb_bytes, lb_rows, sc + SC_TICKET_LNS,
-                            tot, err, s, stats_text);
+                            tot, err, s, stats_text, wide && !fast_lift);
             }
             Publisher(ctx).u64(0, sc + SC_ERR_TOK).u64(1, sc + SC_ERR_REC).u64(5, tot).u64(6, tot + 1).u64(7, tot + 2).u64(8, tot + 3).go(s);
             CU(cudaStreamSynchronize(s));
