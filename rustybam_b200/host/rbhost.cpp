@@ -536,41 +536,52 @@ Windows Windows::pack(const std::vector<Region>& rgns, const Paf& paf) {
 // does with a 3-million-row BED (1 kb windows: 74 MB of text) before the GPU sees anything.  Same rows, same bed_row numbers
 // (position among the rows that parse, whether or not their contig occurs in the PAF), same ids as the two-step form.
 Windows Windows::pack_text(const char* text, size_t n, const Paf& paf) {
-    // line starts (a line ends at \n or \r; runs of them separate lines)
-    std::vector<std::pair<size_t, size_t>> lines;
-    for (size_t i = 0; i < n;) {
-        size_t j = i;
-        while (j < n && text[j] != '\n' && text[j] != '\r') {
-            const char* q = (const char*)memchr(text + j, '\n', n - j);
-            const size_t e = q ? (size_t)(q - text) : n;
-            const char* r = (const char*)memchr(text + j, '\r', e - j);
-            j = r ? (size_t)(r - text) : e;
-        }
-        if (j > i && text[i] != '#') lines.emplace_back(i, j);
-        i = j;
-        while (i < n && (text[i] == '\n' || text[i] == '\r')) i++;
-    }
+    // A line ends at \n or \r, runs of them separate lines, lines starting with '#' are comments (bio's bed::Reader over csv).
+    // Every thread takes a byte range of the text, starts at the first line that BEGINS in it and parses line by line: no global
+    // line table, no serial pass over the text.
+    auto is_eol = [](char c) { return c == '\n' || c == '\r'; };
+    auto line_end = [&](size_t i) {  // first \n or \r at or after i
+        const char* q = (const char*)memchr(text + i, '\n', n - i);
+        const size_t e = q ? (size_t)(q - text) : n;
+        const char* r = (const char*)memchr(text + i, '\r', e - i);
+        return r ? (size_t)(r - text) : e;
+    };
     auto n_fields = [&](size_t a, size_t b) {
         size_t c = 1;
         for (const char* p = text + a; (p = (const char*)memchr(p, '\t', (size_t)(text + b - p))) != nullptr; p++) c++;
         return c;
     };
-    const size_t nf0 = lines.empty() ? 0 : n_fields(lines[0].first, lines[0].second);  // the first record fixes the field count
+    size_t nf0 = 0;  // the first record fixes the field count
+    for (size_t i = 0; i < n;) {
+        while (i < n && is_eol(text[i])) i++;
+        if (i >= n) break;
+        const size_t j = line_end(i);
+        if (text[i] != '#') { nf0 = n_fields(i, j); break; }
+        i = j;
+    }
     struct Row { uint32_t t; uint32_t row; uint64_t st, en; size_t id_at; uint32_t id_n; };
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const unsigned nt = (unsigned)std::min<size_t>(lines.size() < 50000 ? 1 : hw, std::max<size_t>(1, lines.size()));
+    const unsigned nt = n < (4u << 20) ? 1u : hw;
     std::vector<std::vector<Row>> part(nt);
     std::vector<size_t> parsed(nt, 0);  // rows of the part that parse (present contig or not): they number the BED rows
     auto work = [&](unsigned t) {
-        const size_t lo = lines.size() * t / nt, hi = lines.size() * (t + 1) / nt;
+        size_t i = n / nt * t;
+        const size_t stop = (t + 1 == nt) ? n : n / nt * (t + 1);
+        if (t > 0) {  // a line that began before this range belongs to the thread in front
+            if (!is_eol(text[i - 1])) i = line_end(i);
+        }
         std::vector<Row>& out = part[t];
-        out.reserve(hi - lo);
+        out.reserve((stop - std::min(i, stop)) / 16 + 16);
         const char* last_name = nullptr;
         size_t last_n = 0;
         int64_t last_id = -1;
         size_t k_parsed = 0;
-        for (size_t li = lo; li < hi; li++) {
-            const size_t a = lines[li].first, b = lines[li].second;
+        for (;;) {
+            while (i < n && is_eol(text[i])) i++;
+            if (i >= stop || i >= n) break;  // (a line is owned by the range its first byte lies in)
+            const size_t a = i, b = line_end(i);
+            i = b;
+            if (text[a] == '#') continue;
             size_t f[5][2];
             size_t nf = 0, p = a;
             for (;;) {  // the first four fields; the rest only counted
@@ -615,27 +626,53 @@ Windows Windows::pack_text(const char* text, size_t n, const Paf& paf) {
         for (unsigned t = 0; t < nt; t++) pool.emplace_back(work, t);
         for (auto& th : pool) th.join();
     }
-    std::vector<Row> rows;
-    size_t total = 0, base = 0;
-    for (auto& v : part) total += v.size();
-    rows.reserve(total);
-    for (unsigned t = 0; t < nt; t++) {
-        for (Row r : part[t]) { r.row += (uint32_t)base; rows.push_back(r); }
-        base += parsed[t];
-        std::vector<Row>().swap(part[t]);
-    }
     auto less = [](const Row& a, const Row& b) { return a.t != b.t ? a.t < b.t : a.st < b.st; };
-    if (!std::is_sorted(rows.begin(), rows.end(), less)) std::stable_sort(rows.begin(), rows.end(), less);
+    std::vector<size_t> at(nt + 1, 0), base(nt + 1, 0);  // where a part's rows go / what its row numbers start at
+    for (unsigned t = 0; t < nt; t++) { at[t + 1] = at[t] + part[t].size(); base[t + 1] = base[t] + parsed[t]; }
+    const size_t total = at[nt];
+    bool sorted = true;  // (the usual case: bedtools makewindows output) — then the parts are written out where they are
+    {
+        const Row* prev = nullptr;
+        for (unsigned t = 0; t < nt && sorted; t++) {
+            if (part[t].empty()) continue;
+            if (prev && less(part[t].front(), *prev)) sorted = false;
+            if (!std::is_sorted(part[t].begin(), part[t].end(), less)) sorted = false;
+            prev = &part[t].back();
+        }
+    }
+    std::vector<Row> rows;
+    if (!sorted) {
+        rows.reserve(total);
+        for (unsigned t = 0; t < nt; t++) {
+            for (Row r : part[t]) { r.row += (uint32_t)base[t]; rows.push_back(r); }
+            std::vector<Row>().swap(part[t]);
+        }
+        std::stable_sort(rows.begin(), rows.end(), less);
+    }
     Windows w;
     w.default_ids = nf0 <= 3;
-    w.t_id.reserve(rows.size()); w.st.reserve(rows.size()); w.en.reserve(rows.size()); w.bed_row.reserve(rows.size());
-    if (!w.default_ids) w.ids_off.push_back(0);
-    for (const Row& r : rows) {
-        w.t_id.push_back(r.t); w.st.push_back(r.st); w.en.push_back(r.en); w.bed_row.push_back(r.row);
-        if (!w.default_ids) {
+    w.t_id.resize(total); w.st.resize(total); w.en.resize(total); w.bed_row.resize(total);
+    auto fill = [&](const Row* src, size_t cnt, size_t dst, uint32_t rebase) {
+        for (size_t k = 0; k < cnt; k++) {
+            const Row& r = src[k];
+            w.t_id[dst + k] = r.t; w.st[dst + k] = r.st; w.en[dst + k] = r.en; w.bed_row[dst + k] = r.row + rebase;
+        }
+    };
+    if (!sorted) fill(rows.data(), total, 0, 0u);
+    else if (nt <= 1) fill(part[0].data(), part[0].size(), 0, 0u);
+    else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back([&, t] { fill(part[t].data(), part[t].size(), at[t], (uint32_t)base[t]); });
+        for (auto& th : pool) th.join();
+    }
+    if (!w.default_ids) {  // (explicit ids: the byte offsets are a serial prefix sum)
+        w.ids_off.push_back(0);
+        auto add = [&](const Row& r) {
             w.ids.insert(w.ids.end(), text + r.id_at, text + r.id_at + r.id_n);
             w.ids_off.push_back(w.ids.size());
-        }
+        };
+        if (!sorted) for (const Row& r : rows) add(r);
+        else for (unsigned t = 0; t < nt; t++) for (const Row& r : part[t]) add(r);
     }
     if (w.ids.empty()) w.ids.push_back(0);
     return w;

@@ -143,6 +143,24 @@ def test_fast_bed_packer_equals_the_two_step_form():
     bed_text = big.tiling_bed_text(100)  # 1.5 M rows: the threaded path
     (a, _), (b, _) = arrs(big.windows_from_bed_text(bed_text)), arrs(big.windows_from_bed_text_slow(bed_text))
     assert len(a[0]) > 1_000_000 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the threaded path on an awkward text: ids, \r\n endings, comments and blank lines in between, rows out of order, a row
+    # that does not parse, a contig the PAF does not have — thread ranges cut lines wherever they fall
+    import random
+    rng = random.Random(5)
+    rows = bed_text.splitlines()[:400_000]
+    rng.shuffle(rows)
+    out = []
+    for k, r in enumerate(rows):
+        out.append(r + b"\tid%d" % k + (b"\r\n" if k % 3 == 0 else b"\n"))
+        if k % 1000 == 0:
+            out.append(b"#comment\n\n")
+        if k % 7777 == 0:
+            out.append(b"chrNOPE\t1\t2\tx\nchr1\tx\t2\ty\n")
+    awkward = b"".join(out)
+    assert len(awkward) > (8 << 20)
+    (a, i1), (b, i2) = arrs(big.windows_from_bed_text(awkward)), arrs(big.windows_from_bed_text_slow(awkward))
+    assert len(a[0]) == 400_000 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(i1[0], i2[0]) and i1[1] == i2[1]
 
 
 def test_fmt_f32_matches_oracle():
