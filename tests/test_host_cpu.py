@@ -203,6 +203,21 @@ def _write_bgzf(path, data: bytes, block=60000):
             f.write(cdata + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
 
 
+def test_bgzf_detection_needs_no_device(tmp_path):
+    # rb_is_bgzf (the switch in front of rb_inflate_bgzf, myio.rs:41-64): BGZF blocks yes, a plain gzip member or text no
+    import gzip
+    from rustybam_b200 import capi
+    lib = capi.load()
+    text = orc.golden_paf()[:100000]
+    p = tmp_path / "a.bgz"
+    _write_bgzf(p, text)
+    z = p.read_bytes()
+    assert lib.rb_is_bgzf(z, len(z)) == 1
+    g = gzip.compress(text)
+    assert lib.rb_is_bgzf(g, len(g)) == 0 and lib.rb_is_bgzf(text, len(text)) == 0 and lib.rb_is_bgzf(b"", 0) == 0
+    assert lib.rb_is_bgzf(z, 10) == 0  # shorter than a block header
+
+
 def test_host_reader_inflates_bgzf_blocks_in_parallel(tmp_path):
     # myio.rs:33-40: .paf, .paf.gz and .paf.bgz hold the same lines; the .bgz reader works block by block on all threads
     import gzip
