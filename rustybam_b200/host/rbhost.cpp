@@ -143,7 +143,9 @@ std::string read_all(const std::string& path) {
 // ---------------------------------------------------------------------------------------------
 // PAF
 // ---------------------------------------------------------------------------------------------
-static inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\x0C' || c == '\r'; }
+static inline bool is_ws(char c) {  // (one compare for the bytes of a token: every ASCII whitespace byte is <= ' ')
+    return (unsigned char)c <= ' ' && (c == ' ' || c == '\t' || c == '\n' || c == '\x0C' || c == '\r');
+}
 
 static bool parse_u64(const char* s, size_t n, uint64_t& out) {  // Rust str::parse::<u64>
     size_t i = 0;
