@@ -10,7 +10,7 @@ fn main() {
         .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
-        .args(["cuda/rb_kernels.cu", "cuda/rbcuda.cu"])   // == rustybam_b200/csrc/*.cu of this repo
+        .args(["cuda/rb_kernels.cu", "cuda/trim_kernels.cu", "cuda/inflate_kernels.cu", "cuda/rbcuda.cu"])   // == rustybam_b200/csrc/*.cu of this repo
         .status().expect("nvcc not found");
     assert!(status.success(), "nvcc failed");
     println!("cargo:rustc-link-search=native={}", out.display());
