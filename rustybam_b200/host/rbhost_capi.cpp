@@ -35,6 +35,15 @@ void* rbh_paf_from_text(const char* text, size_t n, char* err, size_t err_cap) {
         return nullptr;
     }
 }
+// paf.rs:62-78 Paf::from_file: plain files are mapped and parsed in place, "-" / .gz / .bgz go through read_all
+void* rbh_paf_from_file(const char* path, char* err, size_t err_cap) {
+    try {
+        return new Paf(Paf::from_file(path));
+    } catch (const Panic& e) {
+        if (err && err_cap) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+        return nullptr;
+    }
+}
 // file contents as the readers of myio.rs:41-64 deliver them (plain / .gz / .bgz); nullptr on I/O errors
 char* rbh_read_all(const char* path, size_t* n) {
     try {

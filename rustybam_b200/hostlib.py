@@ -25,6 +25,8 @@ def load():
     lib.rbh_synth_paf_mask.argtypes = [C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_uint32]
     lib.rbh_paf_from_text.restype = C.c_void_p
     lib.rbh_paf_from_text.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.rbh_paf_from_file.restype = C.c_void_p
+    lib.rbh_paf_from_file.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
     lib.rbh_paf_view.argtypes = [C.c_void_p, C.POINTER(capi.RbRecords)]
     lib.rbh_paf_size.restype = C.c_uint64
     lib.rbh_paf_size.argtypes = [C.c_void_p]
@@ -102,6 +104,15 @@ class HostPaf:
     def from_text(text: bytes):
         err = C.create_string_buffer(256)
         h = load().rbh_paf_from_text(text, len(text), err, 256)
+        if not h:
+            raise HostPanic(err.value.decode())
+        return HostPaf(h)
+
+    @staticmethod
+    def from_file(path: str):
+        """Paf::from_file (paf.rs:62-78): what the `rb` CLI does with its input argument."""
+        err = C.create_string_buffer(256)
+        h = load().rbh_paf_from_file(path.encode(), err, 256)
         if not h:
             raise HostPanic(err.value.decode())
         return HostPaf(h)

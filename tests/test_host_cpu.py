@@ -203,6 +203,34 @@ def _write_bgzf(path, data: bytes, block=60000):
             f.write(cdata + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
 
 
+def test_paf_from_file_maps_plain_files_and_inflates_the_rest(tmp_path):
+    # Paf::from_file: an uncompressed file is mmap'ed and parsed in place, .gz / .bgz go through the inflating reader; every
+    # form packs to the same records.  Plus the edge shapes of the line scan: no trailing newline, CRLF, an empty file.
+    import gzip
+    from rustybam_b200 import hostlib
+    text = orc.golden_paf()
+    want = hostlib.HostPaf.from_text(text)
+    (tmp_path / "a.paf").write_bytes(text)
+    (tmp_path / "a.paf.gz").write_bytes(gzip.compress(text))
+    _write_bgzf(tmp_path / "a.paf.bgz", text)
+    for name in ("a.paf", "a.paf.gz", "a.paf.bgz"):
+        got = hostlib.HostPaf.from_file(str(tmp_path / name))
+        assert got.n_rec == want.n_rec == 249 and got.text() == want.text()
+        got.close()
+    lines = text.splitlines()[:5]
+    (tmp_path / "b.paf").write_bytes(b"\r\n".join(lines))  # CRLF between lines, nothing after the last one
+    got = hostlib.HostPaf.from_file(str(tmp_path / "b.paf"))
+    assert got.n_rec == 5 and got.text() == hostlib.HostPaf.from_text(b"\n".join(lines) + b"\n").text()
+    got.close()
+    (tmp_path / "c.paf").write_bytes(b"")
+    got = hostlib.HostPaf.from_file(str(tmp_path / "c.paf"))
+    assert got.n_rec == 0
+    got.close()
+    with pytest.raises(hostlib.HostPanic):
+        hostlib.HostPaf.from_file(str(tmp_path / "missing.paf"))
+    want.close()
+
+
 def test_bgzf_detection_needs_no_device(tmp_path):
     # rb_is_bgzf (the switch in front of rb_inflate_bgzf, myio.rs:41-64): BGZF blocks yes, a plain gzip member or text no
     import gzip
