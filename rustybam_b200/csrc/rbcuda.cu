@@ -43,21 +43,38 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// small pinned staging area owned by a batch: the record columns are gathered here on the host and leave by
-// asynchronous DMA (the caller's column arrays may share pages with a buffer it page-locked, which the driver rejects)
+void* big_pinned_alloc(size_t n);
+void big_pinned_free(void* q, size_t n);
+constexpr size_t BIG_PIN_MIN = 64ull << 20;
+
+// pinned staging area owned by a batch: the record columns are gathered here on the host and leave by
+// asynchronous DMA (the caller's column arrays may share pages with a buffer it page-locked, which the driver rejects).
+// Small for whole-genome records; millions of short records (rb stats --paf behind rb liftover: 81 B per record) make it
+// hundreds of MB, which cudaHostAlloc page-locks at ~2.3 GB/s — those sizes take the mapped + registered route (big_pinned_alloc)
 struct PinBuf {
     uint8_t* p = nullptr;
     size_t cap = 0;
+    bool mapped = false;
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        const size_t want = n + n / 4 + 4096;
-        const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
-        return e;
+        release();
+        size_t want = n + n / 4 + 4096;
+        if (want >= BIG_PIN_MIN && !getenv("RB_PIN_HOSTALLOC")) {
+            want = (want + 4095) / 4096 * 4096;
+            p = static_cast<uint8_t*>(big_pinned_alloc(want));
+            mapped = p != nullptr;
+        }
+        if (!p) {
+            const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want, cudaHostAllocDefault);
+            if (e != cudaSuccess) { p = nullptr; return e; }
+        }
+        cap = want;
+        return cudaSuccess;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() {
+        if (p) { if (mapped) big_pinned_free(p, cap); else cudaFreeHost(p); }
+        p = nullptr; cap = 0; mapped = false;
+    }
 };
 
 struct PinnedBlock {
@@ -71,7 +88,6 @@ struct PinnedBlock {
 // faults them in one by one), which made the first rb_liftover of a process that returns C5's 17.6 GB take 12 s.  An anonymous
 // mapping first-touched by a few host threads and then registered takes 0.6 s for 16 GiB and copies at the same
 // 55 GB/s (tools/pin_bench.cu, profiles/r02_pin_bench.json).  Portable: every device of a multi-device context copies into it.
-constexpr size_t BIG_PIN_MIN = 64ull << 20;
 void* big_pinned_alloc(size_t n) {
     void* q = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
     if (q == MAP_FAILED) return nullptr;
