@@ -330,6 +330,7 @@ Paf Paf::from_text(const char* text, size_t n) {
     // kept records: their index and the place of their CIGAR payload (one serial pass of additions; the first panic in file
     // order is the one reported, like the serial loop of the reference)
     const size_t n_lines = lines.size();
+    if (n_lines > 0xFFFFFFFFull) throw Panic("more than 2^32 lines");
     std::vector<uint32_t> kept;  // line index of record r
     kept.reserve(n_lines);
     size_t total_cg = 0;
@@ -342,7 +343,6 @@ Paf Paf::from_text(const char* text, size_t n) {
         kept.push_back((uint32_t)k);
         total_cg += L.cg_n;
     }
-    if (n_lines > 0xFFFFFFFFull) throw Panic("more than 2^32 lines");
     const size_t n_ok = kept.size();
     paf.cigar.resize(total_cg);
     paf.cigar_off.resize(n_ok + 1);
